@@ -1,0 +1,425 @@
+"""CPU oracle: a restatement of the reference's depth-branch / fusion / MANO hot path.
+
+TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this
+module, and only as the checker or the timed CPU baseline.  Nothing under
+``pdfnet_b200/`` imports it; the product path fails loudly when the CUDA
+library is missing.
+
+Parity status: **pinned**.  The reference (zijinxuxu/PDFNet) ships no tests or
+golden vectors, so the pin is the reference itself: every
+function here is checked (``tests/test_oracle_golden.py``) against outputs of
+the UNMODIFIED reference functions run on CPU in the authoring container and
+frozen under ``tests/golden/`` by ``oracle/make_golden.py``.
+
+Arithmetic is numpy / torch-CPU fp32, the same libraries the reference uses.
+Reference citations are ``path:line`` relative to the reference root.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# ----------------------------------------------------------------------------
+# distances + kNN-then-radius-mask ("ball query")
+# ----------------------------------------------------------------------------
+
+
+def sqdist(xyz, n_centroids):
+    """Squared distances d2[b,i,j] = |p_j - p_i|^2 for the first ``n_centroids`` rows.
+
+    lib/utils/utils.py:142-145 (and :169-172): ``diff = p_j - c_i``;
+    ``mul(diff, diff)``; ``sum(2)`` over 3 channels.  torch-CPU / numpy evaluate
+    the 3-term sum as fl(fl(dx2+dy2)+dz2) with no FMA (SURVEY.md section 7,
+    "Bit-exact distances").
+    """
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    c = xyz[:, :n_centroids, None, :]                       # [B,N1,1,3]
+    d = xyz[:, None, :, :] - c                              # p_j - c_i
+    d = d * d
+    return (d[..., 0] + d[..., 1]) + d[..., 2]              # fp32 throughout
+
+
+def knn_ball_indices(xyz, n_centroids, K, r2):
+    """Indices of the K nearest points of every centroid, radius-masked.
+
+    lib/utils/utils.py:146-151 / :173-179: ``topk(K, largest=False,
+    sorted=False)`` then every neighbour with ``d2 > r2`` is replaced by the
+    centroid's own index.  ``r2`` is compared in fp32 (a python scalar against a
+    float32 tensor).  ``topk(sorted=False)`` leaves the order inside a group
+    and the choice among exact ties at the K-th distance implementation-defined
+    (SURVEY.md section 8c); this oracle returns each group SORTED ASCENDING BY
+    INDEX and breaks ties towards the lowest index, which is the canonical form
+    the parity tests compare in.
+    """
+    d2 = sqdist(xyz, n_centroids)                           # [B,N1,N]
+    B, N1, N = d2.shape
+    order = np.argsort(d2, axis=2, kind="stable")[:, :, :K]  # (distance, index) lexicographic
+    dk = np.take_along_axis(d2, order, axis=2)
+    own = np.arange(N1, dtype=np.int64)[None, :, None]
+    idx = np.where(dk > np.float32(r2), own, order.astype(np.int64))
+    return np.sort(idx, axis=2)
+
+
+def canonicalize_indices(idx, xyz):
+    """Map every index to the smallest index holding a bit-identical xyz row,
+    then sort each group (SURVEY.md section 8c parity rule for duplicate points)."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    out = np.empty_like(idx)
+    for b in range(xyz.shape[0]):
+        rows = xyz[b].view(np.uint32).reshape(xyz.shape[1], -1)
+        _, first, inv = np.unique(rows, axis=0, return_index=True, return_inverse=True)
+        canon = first[inv.reshape(-1)]
+        out[b] = canon[idx[b]]
+    return np.sort(out, axis=-1)
+
+
+def group_points(points, opt, idx=None):
+    """lib/utils/utils.py:134-162.  points [B,N,C>=3] f32 ->
+    (x [B,C,N1,K] f32 with centroid-relative xyz, center [B,3,N1,1])."""
+    points = np.ascontiguousarray(points, dtype=np.float32)
+    N1, K = opt.sample_num_level1, opt.knn_K
+    C = opt.INPUT_FEATURE_NUM
+    if idx is None:
+        idx = knn_ball_indices(points[:, :, 0:3], N1, K, opt.ball_radius)
+    B = points.shape[0]
+    g = np.take_along_axis(points[:, :, None, :C], idx.reshape(B, N1 * K, 1, 1), axis=1)
+    g = g.reshape(B, N1, K, C).copy()
+    center = points[:, :N1, None, 0:3]
+    g[..., 0:3] = g[..., 0:3] - center
+    return g.transpose(0, 3, 1, 2), center.transpose(0, 3, 1, 2)
+
+
+def group_points_2(points, N1, N2, K, r2, idx=None):
+    """lib/utils/utils.py:165-187.  points [B,C,N1] f32 (channel-major, xyz =
+    channels 0:3) -> (x [B,C,N2,K], center [B,3,N2,1])."""
+    points = np.ascontiguousarray(points, dtype=np.float32)
+    B, C, _ = points.shape
+    xyz = points[:, 0:3, :].transpose(0, 2, 1)
+    if idx is None:
+        idx = knn_ball_indices(xyz, N2, K, r2)
+    g = np.take_along_axis(points, idx.reshape(B, 1, N2 * K), axis=2).reshape(B, C, N2, K).copy()
+    center = points[:, 0:3, :N2, None]
+    g[:, 0:3] = g[:, 0:3] - center
+    return g, center
+
+
+# ----------------------------------------------------------------------------
+# pixel -> point pyramid gather + SFT modulation
+# ----------------------------------------------------------------------------
+
+
+def tranpose_and_gather_feat(feat, ind):
+    """lib/models/utils.py:12-26: NCHW -> [B,HW,C] then row gather. -> [B,n,C]."""
+    feat = torch.as_tensor(feat)
+    ind = torch.as_tensor(ind).long()
+    B, C = feat.shape[0], feat.shape[1]
+    f = feat.reshape(B, C, -1)
+    return torch.gather(f, 2, ind[:, None, :].expand(B, C, ind.shape[1])).transpose(1, 2).contiguous()
+
+
+def pyramid_index(choose, R):
+    """lib/models/networks/intaghand_encoder.py:125-126 (floor division, int64)."""
+    choose = torch.as_tensor(choose).long()
+    c2 = (choose // R // 2) * (R // 2) + choose % R // 2
+    c4 = (choose // R // 4) * (R // 4) + choose % R // 4
+    return c2, c4
+
+
+def sft_layer(fea, cond, sd, prefix=""):
+    """SFTLayer.forward, intaghand_encoder.py:205-219.
+    fea [B,Cf,n], cond [B,n,Cc] -> [B,n,Cf];  1x1 convs with bias, leaky 0.1."""
+    fea = torch.as_tensor(fea).unsqueeze(3)
+    c = torch.as_tensor(cond).transpose(1, 2).unsqueeze(3)
+
+    def conv(name, x):
+        return F.conv2d(x, sd[prefix + name + ".weight"], sd[prefix + name + ".bias"])
+
+    scale = conv("SFT_scale_conv1", F.leaky_relu(conv("SFT_scale_conv0", c), 0.1))
+    shift = conv("SFT_shift_conv1", F.leaky_relu(conv("SFT_shift_conv0", c), 0.1))
+    return (fea * (scale + 1) + shift).transpose(1, 2).squeeze(-1)
+
+
+def _conv_bn_relu(x, sd, prefix, i_conv, i_bn, eps=1e-5):
+    x = F.conv2d(x, sd["%s.%d.weight" % (prefix, i_conv)], sd["%s.%d.bias" % (prefix, i_conv)])
+    x = F.batch_norm(x, sd["%s.%d.running_mean" % (prefix, i_bn)], sd["%s.%d.running_var" % (prefix, i_bn)],
+                     sd["%s.%d.weight" % (prefix, i_bn)], sd["%s.%d.bias" % (prefix, i_bn)], False, 0.0, eps)
+    return F.relu(x)
+
+
+def point_mlp_max(x, sd, prefix, pool_dim):
+    """netR_1 / netR_2 / netR_3 (intaghand_encoder.py:48-103) in eval mode:
+    (Conv1x1 -> BatchNorm2d -> ReLU) x3 -> max over ``pool_dim``."""
+    x = torch.as_tensor(x)
+    for i_conv, i_bn in ((0, 1), (3, 4), (6, 7)):
+        x = _conv_bn_relu(x, sd, prefix, i_conv, i_bn)
+    return x.max(dim=pool_dim, keepdim=True)[0]
+
+
+def pointnet_plus_forward(sd, points, emb, choose, opt, return_intermediates=False):
+    """PointNet_Plus.forward, intaghand_encoder.py:118-159 (eval mode).
+    points [B,N,3], emb = [l0 [B,3,R,R], l1 [B,64,R/2,R/2], l2 [B,256,R/4,R/4]],
+    choose [B,N] int64 -> [B,1,1024]."""
+    with torch.no_grad():
+        points = torch.as_tensor(points, dtype=torch.float32)
+        choose = torch.as_tensor(choose).long()
+        R = opt.default_resolution
+        N1, N2, K = opt.sample_num_level1, opt.sample_num_level2, opt.knn_K
+        e0 = tranpose_and_gather_feat(emb[0], choose)
+        pts0 = sft_layer(points.transpose(1, 2), e0, sd, "sft0.")                 # [B,N,3]
+        x, y = group_points(pts0.numpy(), opt)
+        x, y = torch.from_numpy(np.ascontiguousarray(x)), torch.from_numpy(np.ascontiguousarray(y))
+        c2, c4 = pyramid_index(choose, R)
+        e1 = tranpose_and_gather_feat(emb[1], c2[:, :N1])
+        e2 = tranpose_and_gather_feat(emb[2], c4[:, :N2])
+        f1 = point_mlp_max(x, sd, "netR_1", 3)                                    # [B,128,N1,1]
+        x1 = torch.cat((y, f1), 1).squeeze(-1)                                    # [B,131,N1]
+        pts1 = sft_layer(x1, e1, sd, "sft1.").transpose(1, 2)                     # [B,131,N1]
+        g2, c2xyz = group_points_2(pts1.numpy(), N1, N2, K, opt.ball_radius2)
+        g2, c2xyz = torch.from_numpy(g2), torch.from_numpy(np.ascontiguousarray(c2xyz))
+        f2 = point_mlp_max(g2, sd, "netR_2", 3)                                   # [B,256,N2,1]
+        x2 = torch.cat((c2xyz, f2), 1)
+        pts2 = sft_layer(x2.squeeze(-1), e2, sd, "sft2.").transpose(1, 2).unsqueeze(3)
+        out = point_mlp_max(pts2, sd, "netR_3", 2).view(-1, 1, 1024)
+        if return_intermediates:
+            return out, dict(pts0=pts0, f1=f1.squeeze(-1), pts1=pts1, f2=f2.squeeze(-1), pts2=pts2.squeeze(-1))
+        return out
+
+
+def fusion_tail(sd_pointnet, sd_sft, cloud, emb, choose, center_features, opt):
+    """ResNetSimple.forward fusion tail, intaghand_encoder.py:805-809.
+    cloud [B,2,N,3], choose [B,2,N], center_features [B,2,1024] -> fuse_feat [B,2,1024]."""
+    with torch.no_grad():
+        left = pointnet_plus_forward(sd_pointnet, cloud[:, 0], emb, choose[:, 0], opt)
+        right = pointnet_plus_forward(sd_pointnet, cloud[:, 1], emb, choose[:, 1], opt)
+        fuse = torch.cat((left, right), dim=1)
+        return sft_layer(fuse.transpose(1, 2).contiguous(), torch.as_tensor(center_features), sd_sft, "")
+
+
+# ----------------------------------------------------------------------------
+# farthest point sampling
+# ----------------------------------------------------------------------------
+
+
+def fps_order(points, n_sample, start_idx):
+    """farthest_point_sampling_fast, lib/datasets/interhand.py:147-178, for
+    pc_num > n_sample, with the random start (:159) injected.  Returns the index
+    sequence IN SELECTION ORDER (the reference returns np.unique of it, :177).
+
+    min_dist = |p - p_start|^2 (fp32, (dx2+dy2)+dz2); each round: argmax (first
+    occurrence), then ONLY entries with min_dist > 1e-8 are lowered (:171-175).
+    """
+    pc = np.ascontiguousarray(points, dtype=np.float32)
+    out = np.zeros((n_sample,), dtype=np.int64)
+    out[0] = start_idx
+    diff = pc - pc[start_idx][None, :]
+    min_dist = np.sum(diff * diff, 1)
+    for s in range(1, n_sample):
+        out[s] = np.argmax(min_dist)
+        valid = min_dist > 1e-8
+        diff = pc[valid] - pc[out[s]][None, :]
+        min_dist[valid] = np.minimum(min_dist[valid], np.sum(diff * diff, 1))
+    return out
+
+
+def fps_batch(xyz, n_sample, start_idx):
+    return np.stack([fps_order(xyz[b], n_sample, int(start_idx[b])) for b in range(xyz.shape[0])])
+
+
+# ----------------------------------------------------------------------------
+# depth back-projection and per-hand cloud construction
+# ----------------------------------------------------------------------------
+
+
+def backproject(depth, K):
+    """get_normal(with_normal=False) -> get_points_coordinate,
+    lib/utils/utils.py:264-275, :251-262.  depth [H,W] (any float), K [3,3] ->
+    xyz [3,H,W] f32 = (inv(K)[:3,:3] @ [u,v,1]) * z, u = column, v = row.
+    ``np.linalg.inv`` runs in the dtype of K; depth2pcl passes float32
+    (intaghand_encoder.py:373)."""
+    depth = np.asarray(depth)
+    H, W = depth.shape
+    Kinv = torch.from_numpy(np.linalg.inv(np.asarray(K)))[:3, :3].unsqueeze(0)
+    d = torch.from_numpy(depth).unsqueeze(0).unsqueeze(-1).float()
+    y, x = torch.meshgrid([torch.arange(0, H, dtype=torch.float32),
+                           torch.arange(0, W, dtype=torch.float32)], indexing="ij")
+    uv1 = torch.stack((x.reshape(-1), y.reshape(-1), torch.ones(H * W)))[None]
+    xyz = torch.matmul(Kinv, uv1) * d.view(1, 1, -1)
+    return xyz.view(3, H, W).numpy()
+
+
+def hand_candidates(xyz, z_min=0.2, z_max=2.5, half_window=0.08):
+    """Candidate flat pixel indices of one hand, intaghand_encoder.py:406-411:
+    mean z over non-zero pixels, window mean+-0.08 clipped to [z_min,z_max]."""
+    z = xyz.reshape(3, -1)[2]
+    nz = z[z != 0]
+    if len(nz) == 0:
+        return None
+    mean_dis = nz.mean()
+    lo, hi = max(z_min, mean_dis - half_window), min(z_max, mean_dis + half_window)
+    return ((z > lo) & (z < hi)).nonzero()[0]
+
+
+def depth2pcl(depth, mask, K, valid, subset_keys, perm, num_points=1024, min_pixels=10):
+    """depth2pcl, intaghand_encoder.py:369-491, batch-1, with the two uses of
+    ``np.random.shuffle`` replaced by injected randomness:
+
+    * >num_points candidates (:418-422): the reference shuffles a 0/1 mask with
+      ``num_points`` ones and keeps candidates where it is 1 (order preserved).
+      Here the kept candidates are those with the ``num_points`` smallest
+      ``subset_keys[h][pixel]`` (ties -> lower pixel), order preserved.
+    * final shuffle (:427): ``choose = choose[perm[h]]``.
+
+    depth [H,W] f32 metres, mask [1,2,H,W] (channel 0 = right, 1 = left, :376-377),
+    valid [1,2] (0 = left, 1 = right, :401,:439).  Returns choose int64 [2,num_points]
+    (row 0 = left) and cloud f32 [2,num_points,3].
+    The mask here is already at depth resolution, so cv2.resize (:376) is identity.
+    """
+    depth = np.asarray(depth, dtype=np.float32)
+    m = (np.asarray(mask) > 0.5).astype(np.uint8)
+    K = np.asarray(K).astype(np.float32)
+    noise = ((0.2 < depth) & (2.5 > depth)).astype(np.uint8)
+    d = depth * noise
+    chooses, clouds = [], []
+    for h, mch in ((0, 1), (1, 0)):                     # left uses mask[0,1], right mask[0,0]
+        if valid[0, h] == 1:
+            xyz = backproject((d * m[0, mch]).squeeze(), K).reshape(3, -1)
+            cand = hand_candidates(xyz)
+            if cand is None or len(cand) < min_pixels:
+                ch = np.zeros((num_points,), dtype=np.int64)
+            elif len(cand) > num_points:
+                keys = np.asarray(subset_keys[h])[cand]
+                keep = np.sort(np.argsort(keys, kind="stable")[:num_points])
+                ch = cand[keep]
+            else:
+                ch = np.pad(cand, (0, num_points - len(cand)), "wrap")
+            ch = ch[np.asarray(perm[h])]
+            pts = xyz.transpose(1, 0)[ch, :]
+        else:
+            ch = np.zeros((num_points,), dtype=np.int64)
+            pts = np.zeros((num_points, 3), dtype=np.float32)
+        chooses.append(ch)
+        clouds.append(pts)
+    return np.stack(chooses), np.stack(clouds)
+
+
+# ----------------------------------------------------------------------------
+# MANO head, coefficient split, linear blend skinning
+# ----------------------------------------------------------------------------
+
+
+def mano_head(x, sd, prefix="mano_head"):
+    """mano_head, intaghand_encoder.py:630-643, eval mode:
+    Linear(1024,512) BN1d ReLU Linear(512,256) BN1d ReLU Linear(256,122)."""
+    x = torch.as_tensor(x)
+    for i_fc, i_bn in ((0, 1), (3, 4)):
+        x = F.linear(x, sd["%s.%d.weight" % (prefix, i_fc)], sd["%s.%d.bias" % (prefix, i_fc)])
+        x = F.batch_norm(x, sd["%s.%d.running_mean" % (prefix, i_bn)], sd["%s.%d.running_var" % (prefix, i_bn)],
+                         sd["%s.%d.weight" % (prefix, i_bn)], sd["%s.%d.bias" % (prefix, i_bn)], False, 0.0, 1e-5)
+        x = F.relu(x)
+    return F.linear(x, sd["%s.6.weight" % prefix], sd["%s.6.bias" % prefix])
+
+
+def split_coeff(theta, index, K, input_res, down_ratio):
+    """ManoRender.Split_coeff non-PCA branch, lib/models/hand3d/Mano_render.py:160-194.
+    theta [B,122], index [B] (flat index on the input_res/down_ratio grid), K [B,3,3].
+    Returns (orient_l, pose_l, betas_l, trans_l, orient_r, pose_r, betas_r, trans_r).
+    Betas are multiplied by 0 (:163,:169); t_z += 0.6 (:165,:171); the SAME
+    centre pixel (cx,cy) is used for both hands (:179-187)."""
+    theta = torch.as_tensor(theta).clone()
+    index = torch.as_tensor(index)
+    K = torch.as_tensor(K)
+    outs = []
+    fx, fy, cw, ch = K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2]
+    g = input_res // down_ratio
+    cx = (index % g) * down_ratio
+    cy = (index // g) * down_ratio
+    for o in (0, 61):
+        orient = theta[:, o:o + 3]
+        pose = theta[:, o + 3:o + 48]
+        betas = theta[:, o + 48:o + 58] * 0
+        t = theta[:, o + 58:o + 61].clone()
+        t[:, 2] = t[:, 2] + 0.6
+        tx = t[:, 2] * (t[:, 0] + cx - cw) / fx
+        ty = t[:, 2] * (t[:, 1] + cy - ch) / fy
+        outs += [orient, pose, betas, torch.stack((tx, ty, t[:, 2]), 1)]
+    return tuple(outs)
+
+
+def rodrigues(axis):
+    """rodrigues_batch, lib/models/networks/manolayer.py:32-48. [n,3] -> [n,3,3]."""
+    axis = torch.as_tensor(axis)
+    n = axis.shape[0]
+    angle = torch.norm(axis, p=2, dim=1, keepdim=True) + 1e-8
+    a = axis / angle
+    s = torch.sin(angle).unsqueeze(2)
+    c = torch.cos(angle).unsqueeze(2)
+    L = torch.zeros((n, 3, 3), dtype=axis.dtype)
+    L[:, 2, 1] = a[:, 0]
+    L[:, 1, 2] = -a[:, 0]
+    L[:, 0, 2] = a[:, 1]
+    L[:, 2, 0] = -a[:, 1]
+    L[:, 1, 0] = a[:, 2]
+    L[:, 0, 1] = -a[:, 2]
+    return torch.eye(3, dtype=axis.dtype).repeat(n, 1, 1) + s * L + (1 - c) * L.bmm(L)
+
+
+MANO_PARENT = [-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 0, 10, 11, 0, 13, 14]       # kintree_table[0]
+MANO_NEW_ORDER = [0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20]
+MANO_TIPS = {"left": [745, 317, 445, 556, 673], "right": [745, 317, 444, 556, 673]}
+
+
+def mano_lbs(tables, root_rotation, pose, shape, trans=None, scale=None, side="left",
+             center_idx=None, new_skel=False):
+    """ManoLayer.forward with use_pca=False, lib/models/networks/manolayer.py:257-334.
+    tables: dict with v_template [778,3], shapedirs [778,3,10], posedirs [778,3,135],
+    J_regressor [16,778] dense, weights [778,16] (f32).  Inputs are axis-angle
+    root [B,3], pose [B,45], shape [B,10].  Returns (v [B,778,3], j [B,21,3])."""
+    T = {k: torch.as_tensor(np.asarray(v), dtype=torch.float32) for k, v in tables.items()
+         if k in ("v_template", "shapedirs", "posedirs", "J_regressor", "weights")}
+    root_rotation = torch.as_tensor(root_rotation, dtype=torch.float32)
+    pose = torch.as_tensor(pose, dtype=torch.float32)
+    shape = torch.as_tensor(shape, dtype=torch.float32)
+    bs = root_rotation.shape[0]
+    Rroot = rodrigues(root_rotation.reshape(-1, 3)).view(bs, 3, 3)
+    Rpose = rodrigues(pose.reshape(-1, 3)).view(bs, 15, 3, 3)
+    v_shaped = T["v_template"] + torch.matmul(T["shapedirs"], shape.permute(1, 0)).permute(2, 0, 1)
+    j_tpose = torch.matmul(T["J_regressor"], v_shaped)
+    pose_shape = Rpose.reshape(bs, -1) - torch.eye(3).repeat(bs, 15, 1, 1).view(bs, -1)
+    v_tpose = v_shaped + torch.matmul(T["posedirs"], pose_shape.permute(1, 0)).permute(2, 0, 1)
+
+    def se3(R, t):
+        pad = torch.zeros((bs, 1, 4))
+        pad[:, 0, 3] = 1.0
+        return torch.cat([torch.cat([R, t], 2), pad], 1)
+
+    eye = torch.eye(3).repeat(bs, 1, 1)
+    G = [se3(Rroot, (eye - Rroot).bmm(j_tpose[:, 0].unsqueeze(2)))]
+    for i in range(1, 16):
+        R = Rpose[:, i - 1]
+        G.append(torch.matmul(G[MANO_PARENT[i]], se3(R, (eye - R).bmm(j_tpose[:, i].unsqueeze(2)))))
+    G = torch.stack(G, dim=1)
+    joints = [j_tpose[:, 0]]
+    one = torch.ones((bs, 1))
+    for i in range(1, 16):
+        joints.append(G[:, MANO_PARENT[i]].bmm(torch.cat([j_tpose[:, i], one], 1).unsqueeze(2))[:, :3, 0])
+    Gv = torch.matmul(T["weights"], G.view(bs, 16, 16)).view(bs, -1, 4, 4)
+    v = (Gv[:, :, :3, :3].matmul(v_tpose.unsqueeze(3)) + Gv[:, :, :3, 3:4])[:, :, :, 0]
+    j = torch.stack(joints + [v[:, t] for t in MANO_TIPS[side]], dim=1)[:, MANO_NEW_ORDER]
+    if center_idx is not None:
+        center = j[:, center_idx:center_idx + 1]
+        v, j = v - center, j - center
+    if scale is not None:
+        s = torch.as_tensor(scale, dtype=torch.float32).unsqueeze(1).unsqueeze(2)
+        v, j = v * s, j * s
+    if trans is not None:
+        t = torch.as_tensor(trans, dtype=torch.float32).unsqueeze(1)
+        v, j = v + t, j + t
+    if new_skel:
+        j = j.clone()
+        j[:, 5] = (v[:, 63] + v[:, 144]) / 2
+        j[:, 9] = (v[:, 271] + v[:, 220]) / 2
+        j[:, 13] = (v[:, 148] + v[:, 290]) / 2
+        j[:, 17] = (v[:, 770] + v[:, 83]) / 2
+    return v, j
