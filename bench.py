@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the PDFNet depth-branch + fusion + MANO hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision bf16|fp32]
+
+One "step" = one pass of the hot path over one batch of synthetic RGB-D frames:
+depth -> per-hand clouds (device depth2pcl) -> 3-level pixel->point gather + SFT0 -> SA1 -> SFT1
+-> SA2 -> SFT2 -> global MLP + max -> final SFT(1024) with centre features -> mano_head ->
+Split_coeff -> MANO LBS.  Workload = BASELINE.json configs[2] restricted to the hot path
+(the RGB ResNet-50 neck and the GCN decoder are out of scope; their
+outputs — feature pyramid, hand masks, centre features, centre indices — are synthetic inputs).
+
+Prints ONE JSON line (rank 0).  Multi-GPU: one process per GPU (torchrun), frames sharded,
+no data-path collective ("scaling": "weak", fixed frames per GPU); time = max over ranks.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rgbd_frames_per_sec_hot_path"
+UNIT = "frames/s"
+
+# algorithmic work per unit (SURVEY.md section 8d / BASELINE.md section 3)
+FLOP_SA1, FLOP_SA2, FLOP_GLOBAL = 817889280, 1080033280, 235274240
+FLOP_SFT1, FLOP_SFT2 = 25559040, 67502080
+
+
+def make_opt(R):
+    return types.SimpleNamespace(SAMPLE_NUM=1024, INPUT_FEATURE_NUM=3, knn_K=64, sample_num_level1=512,
+                                 sample_num_level2=128, ball_radius=0.015, ball_radius2=0.04, default_resolution=R,
+                                 PCA_SZ=63)
+
+
+def make_inputs(n_frames, R, seed):
+    """Synthetic host inputs of the hot path for ``n_frames`` frames."""
+    from pdfnet_b200 import synth
+    depth, mask, K, valid = synth.rgbd_frames(n_frames, R, seed=seed)
+    emb = synth.pyramid(n_frames, R, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    center = torch.randn((n_frames, 2, 1024), generator=g)
+    ind = torch.randint(0, (R // 4) ** 2, (n_frames, 2), generator=g)
+    rs = np.random.RandomState(seed)
+    keys = torch.from_numpy(np.argsort(rs.rand(n_frames, 2, R * R), axis=2).astype(np.int32))
+    perm = torch.from_numpy(np.argsort(rs.rand(n_frames, 2, 1024), axis=2).astype(np.int32))
+    Kinv = torch.from_numpy(np.stack([np.linalg.inv(k) for k in K.numpy()]))   # host, as utils.py:269
+    return dict(depth=depth, mask=mask, K=K, Kinv=Kinv, valid=valid, l0=emb[0], l1=emb[1], l2=emb[2], center=center,
+                ind=ind, keys=keys, perm=perm)
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path (the reference is
+# Python/PyTorch and cannot travel to the GPU box; oracle/pdf_oracle.py restates it 1:1 and is
+# pinned to it by tests/golden).  This is the only place bench.py executes oracle/.
+# ----------------------------------------------------------------------------------------------
+
+def cpu_hot_path(inp, R, mano_tables, state):
+    from oracle import pdf_oracle as O
+    opt = make_opt(R)
+    B = inp["depth"].shape[0]
+    chooses, clouds = [], []
+    for b in range(B):
+        ch, cl = O.depth2pcl(inp["depth"][b].numpy(), inp["mask"][b:b + 1].numpy(), inp["K"][b].numpy(),
+                             inp["valid"][b:b + 1].numpy(), inp["keys"][b].numpy(), inp["perm"][b].numpy())
+        chooses.append(torch.from_numpy(ch))
+        clouds.append(torch.from_numpy(cl))
+    choose, cloud = torch.stack(chooses), torch.stack(clouds)
+    emb = [inp["l0"], inp["l1"], inp["l2"]]
+    with torch.no_grad():
+        feats = [O.pointnet_plus_forward(state["pointnet"], cloud[:, h], emb, choose[:, h], opt) for h in (0, 1)]
+        fuse = O.sft_layer(torch.cat(feats, 1).transpose(1, 2).contiguous(), inp["center"], state["sft"], "")
+        th_l = O.mano_head(feats[0][:, 0], state["mano_head"])
+        th_r = O.mano_head(feats[1][:, 0], state["mano_head"])
+        sl = O.split_coeff(th_l, inp["ind"][:, 0], inp["K"], R, 4)
+        sr = O.split_coeff(th_r, inp["ind"][:, 1], inp["K"], R, 4)
+        vl, jl = O.mano_lbs(mano_tables["left"], sl[0], sl[1], sl[2], side="left")
+        vr, jr = O.mano_lbs(mano_tables["right"], sr[4], sr[5], sr[6], side="right")
+    return fuse, torch.stack((vl, vr), 1), torch.stack((jl, jr), 1)
+
+
+def load_states():
+    from pdfnet_b200 import synth
+    return dict(pointnet=synth.pointnet_plus_state(317), sft=synth.fusion_sft_state(317),
+                mano_head=synth.mano_head_state(317, std=0.05))
+
+
+def load_mano_tables():
+    """Real MANO tables exported to tests/golden (npz); synthetic MANO-shaped tables otherwise."""
+    from pdfnet_b200 import synth
+    out = {}
+    for side in ("left", "right"):
+        p = os.path.join(ROOT, "tests", "golden", "mano_%s.npz" % side)
+        out[side] = dict(np.load(p)) if os.path.exists(p) else synth.to_numpy(synth.synthetic_mano_tables())
+    return out
+
+
+def time_cpu(sample_frames, R, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    inp = make_inputs(sample_frames, R, seed=317)
+    tables, state = load_mano_tables(), load_states()
+    for _ in range(warmup):
+        cpu_hot_path(inp, R, tables, state)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_hot_path(inp, R, tables, state)
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    sample = args.cpu_sample_frames
+    ts = time_cpu(sample, args.res, args.steps, min(args.warmup, 1))
+    ms = 1e3 * sum(ts) / len(ts)
+    val = sample / (ms / 1e3)
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample_frames_per_step": sample, "resolution": args.res},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d frames/step of the same workload, torch CPU fp32, %d threads" % (sample, cores)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+
+def workload_name(args):
+    return ("cfg3-hotpath: %d frames/GPU x 2 hands, %dx%d depth, 1024-pt clouds, N1=512 N2=128 K=64 r2=(0.015,0.04); "
+            "depth2pcl+pyramid gather/SFT+SA1+SA2+global MLP+fusion SFT+mano_head+Split_coeff+LBS"
+            % (args.frames, args.res, args.res))
+
+
+class ClockSampler(object):
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([c.strip() for c in ln.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ours(args):
+    from pdfnet_b200 import parallel
+    rank, world, local = parallel.init_distributed("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    from pdfnet_b200 import HandFusion, ManoLayer, _lib, depth2pcl_batched, mano_tail, ops, profiling
+
+    R, B = args.res, args.frames                      # frames per GPU (weak scaling)
+    opt = make_opt(R)
+    host = make_inputs(B, R, seed=317 + rank)
+    pinned = {k: v.contiguous().pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    state = load_states()
+    tables = load_mano_tables()
+    model = HandFusion(opt, precision=args.precision)
+    sd = {"pointnet_plus." + k: v for k, v in state["pointnet"].items()}
+    sd.update({"sft." + k: v for k, v in state["sft"].items()})
+    sd.update(state["mano_head"])
+    model.load_state_dict(sd, strict=False)
+    model = model.to(dev).eval()
+    mano_l = ManoLayer(tables["left"], center_idx=None).to(dev)
+    mano_r = ManoLayer(tables["right"], center_idx=None).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def hot_path(d):
+        with profiling.stage("depth2pcl"):
+            choose, cloud, _ = ops.depth2pcl(d["depth"], d["mask"], d["Kinv"], d["valid"], d["keys"], d["perm"])
+        fused, theta = model(cloud, [d["l0"], d["l1"], d["l2"]], choose, d["center"], with_mano=True)
+        with profiling.stage("mano_tail"):
+            verts, joints, tl, tr = mano_tail(theta[:, 0].contiguous(), theta[:, 1].contiguous(), d["ind"][:, 0],
+                                              d["ind"][:, 1], d["K"], mano_l, mano_r, input_res=R)
+        return fused, verts, joints
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)                            # evict L2 between timed iterations
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        return parallel.max_over_ranks(ms, dev)
+
+    # ---- device-resident throughput ("value") ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms_dev = timed_loop(lambda: hot_path(resident), args.steps, args.warmup)
+    launches = (_lib.launch_count() - l0) // (args.steps + args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public API with HOST buffers ----
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
+    out_host = {}
+
+    def e2e_step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        fused, verts, joints = hot_path(d)
+        for name, t in (("fused", fused), ("verts", verts), ("joints", joints)):
+            if name not in out_host:
+                out_host[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            out_host[name].copy_(t, non_blocking=True)
+
+    ms_e2e = timed_loop(e2e_step, args.steps, args.warmup)
+    torch.cuda.synchronize()
+    d2h_bytes = sum(v.numel() * v.element_size() for v in out_host.values())
+
+    # ---- per-stage timing (roofline of the dominant kernel), same inputs, L2 flushed ----
+    profiling.enable(True)
+    for _ in range(max(3, min(args.steps, 10))):
+        flush.fill_(1)
+        hot_path(resident)
+    stages = profiling.summary()
+    profiling.enable(False)
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+        return
+
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        j = json.load(open(pk))
+        peaks = {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops"], "source": "measured"}
+    n_clouds = 2 * B
+    stage_ms = {k: t / c for k, (c, t) in stages.items()}
+    flops = {"sa1": FLOP_SA1 * n_clouds, "sa2": FLOP_SA2 * n_clouds, "global_mlp": FLOP_GLOBAL * n_clouds,
+             "sft1": FLOP_SFT1 * n_clouds, "sft2": FLOP_SFT2 * n_clouds}
+    dom = max(flops, key=lambda k: stage_ms.get(k, 0.0))
+    ach = flops[dom] / (stage_ms[dom] * 1e-3) / 1e12
+    tensor_stage = args.precision == "bf16" and dom in ("sa1", "sa2")
+    roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                "pipe": "tcgen05 bf16" if tensor_stage else "FFMA fp32 (stage not yet on tensor cores)",
+                "launch_ms": stage_ms[dom]}
+    stage_report = {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}
+    stage_tflops = {k: round(flops[k] / (stage_ms[k] * 1e-3) / 1e12, 2) for k in flops if k in stage_ms}
+
+    cores = os.cpu_count() or 1
+    cpu_baseline = None
+    if world == 1:
+        cpu_ts = time_cpu(args.cpu_sample_frames, R, 3, 1)
+        cpu_baseline = {"value": args.cpu_sample_frames / min(cpu_ts), "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "%d frames of the same workload, oracle port (torch CPU fp32, %d threads), best of 3"
+                                  % (args.cpu_sample_frames, cores)}
+
+    line = {
+        "metric": METRIC, "value": world * B / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "frames_per_gpu": B, "resolution": R, "precision": args.precision,
+                   "parallelism": "dp%d" % world, "l2": "256 MiB flush write between timed iterations; inputs 1.2 GB > L2",
+                   "randomness": "subset keys / permutations injected as inputs (reference uses np.random)"},
+        "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e,
+                "note": "all hot-path inputs (depth, masks, K, fp32 feature pyramid, centre features, keys) copied "
+                        "from pinned host memory every step; fused features + MANO verts/joints copied back"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "stages_ms": stage_report, "stages_tflops": stage_tflops,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--frames", type=int, default=128, help="frames per GPU per step")
+    ap.add_argument("--res", type=int, default=256)
+    ap.add_argument("--cpu-sample-frames", type=int, default=4)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

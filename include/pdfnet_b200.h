@@ -1,0 +1,190 @@
+/*
+ * pdfnet_b200 — C ABI of the B200-native depth-branch / fusion / MANO hot path.
+ *
+ * The reference (zijinxuxu/PDFNet) has no FFI layer: its boundary is Python call
+ * level.  Every entry point below replaces the body of one
+ * reference function (cited as path:line relative to the reference root); the
+ * Python mirror in pdfnet_b200/*.py binds them with ctypes and keeps the
+ * reference's names, argument meaning and error behaviour.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless the
+ *    name ends in _host.  The caller owns every buffer; the library never
+ *    allocates or frees persistent device memory.
+ *  - every call enqueues asynchronously on `stream` (a cudaStream_t passed as
+ *    void*) and never synchronises.
+ *  - return 0 on success, a negative pdf_status on failure; the message is
+ *    available from pdf_last_error() (thread-local).  Nothing ever exit()s.
+ *  - no CPU fallback exists: without a CUDA device every compute call fails.
+ */
+#ifndef PDFNET_B200_H
+#define PDFNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  PDF_OK = 0,
+  PDF_ERR_BAD_ARG = -1,       /* null pointer, non-positive size, bad enum        */
+  PDF_ERR_UNSUPPORTED = -2,   /* shape outside what the kernels are built for     */
+  PDF_ERR_CUDA = -3           /* launch / runtime error (message has the detail)  */
+} pdf_status;
+
+/* activation codes for pdf_linear_f32 */
+enum { PDF_ACT_NONE = 0, PDF_ACT_RELU = 1, PDF_ACT_LEAKY01 = 2 };
+/* epilogue modes for pdf_linear_f32 */
+enum {
+  PDF_EPI_STORE = 0,     /* Y = act(acc + bias)                                   */
+  PDF_EPI_SFT_SCALE = 1, /* Y = F * ((acc + bias) + 1)      SFTLayer scale branch */
+  PDF_EPI_ACCUM = 2,     /* Y = Y + (acc + bias)            SFTLayer shift branch */
+  PDF_EPI_GROUP_MAX = 3  /* Y[m/G] = max over G consecutive rows of act(acc+bias);
+                            act must be RELU, Y must be zero-filled by the caller */
+};
+
+int pdf_version(void);
+const char* pdf_last_error(void);
+/* number of kernel launches enqueued by this library since load (bench bookkeeping) */
+int64_t pdf_launch_count(void);
+
+/* kNN-then-radius-mask neighbour search.
+ * Replaces the index half of group_points (lib/utils/utils.py:142-151) and
+ * group_points_2 (:169-179): d2 = (dx*dx + dy*dy) + dz*dz in fp32 without FMA,
+ * diff = p_j - c_i; the k smallest per centroid; neighbours with d2 > r2 are
+ * replaced by the centroid's own index.  Centroids are points 0..n_centroids-1.
+ * xyz element (cloud b, point j, channel c) is xyz[b*stride_cloud + j*stride_point
+ * + c*stride_ch] so both [B,N,C] and channel-major [B,C,N] inputs work.
+ * idx_out: int32 [n_clouds, n_centroids, k], each group in ascending point order,
+ * exact distance ties at the k-th neighbour resolved towards the lower index.
+ * Supported: n_points in [k, 1024] and a multiple of 32, k <= 128. */
+int pdf_knn_ball(const float* xyz, int64_t n_clouds, int n_points, int n_centroids, int k, float r2,
+                 int64_t stride_cloud, int64_t stride_point, int64_t stride_ch,
+                 int32_t* idx_out, void* stream);
+
+/* Farthest point sampling in selection order.
+ * Replaces the loop of InterHandDataset.farthest_point_sampling_fast
+ * (lib/datasets/interhand.py:159-175): fp32 (dx2+dy2)+dz2, first-occurrence
+ * argmax, min-distance lowered only where it is > 1e-8.  start_idx[b] is the
+ * injected first sample (:159 draws it from np.random).  idx_out int32
+ * [n_clouds, n_sample].  Supported: n_points <= 4096, 1 <= n_sample <= n_points. */
+int pdf_fps(const float* xyz, int64_t n_clouds, int n_points, int n_sample, const int32_t* start_idx,
+            int64_t stride_cloud, int64_t stride_point, int64_t stride_ch,
+            int32_t* idx_out, void* stream);
+
+/* Row gather from an NCHW map: out[b,i,c] = feat[b / clouds_per_frame, c, ind[b,i]].
+ * Replaces _tranpose_and_gather_feat (lib/models/utils.py:22-26) without the
+ * full-map permute+copy.  feat fp32 [n_frames,C,HW]; ind int64 [n_clouds,n] with
+ * row pitch ind_stride; out fp32 [n_clouds,n,C].  Indices outside [0,HW) fail
+ * the call's contract (checked on the host side of the Python mirror). */
+int pdf_gather_nchw(const float* feat, int64_t n_clouds, int clouds_per_frame, int C, int64_t HW,
+                    const int64_t* ind, int n, int64_t ind_stride, float* out, void* stream);
+
+/* Three-level pixel->point pyramid gather with the level-0 SFT fused.
+ * Replaces intaghand_encoder.py:120-128 (+ SFTLayer sft0, :205-219):
+ *   e0 = l0[:, :, choose]                      (3 channels, all n_points)
+ *   pts0 = xyz * (scale(e0) + 1) + shift(e0)   (fp32; feeds the neighbour search)
+ *   cond1 = l1[:, :, (choose//R//2)*(R//2) + (choose%R)//2]  first n1 points
+ *   cond2 = l2[:, :, (choose//R//4)*(R//4) + (choose%R)//4]  first n2 points
+ * sft0_params: 48 floats = scale_conv0 W[3x3],b[3], scale_conv1 W,b, shift_conv0
+ * W,b, shift_conv1 W,b (row-major [out][in]).  l0 [F,3,R,R], l1 [F,C1,R/2,R/2],
+ * l2 [F,C2,R/4,R/4] fp32.  pts0 [n_clouds,n_points,3], cond1 [n_clouds,n1,C1],
+ * cond2 [n_clouds,n2,C2] fp32. */
+int pdf_pyramid_gather(const float* xyz, const int64_t* choose, int64_t n_clouds, int clouds_per_frame,
+                       int n_points, int n1, int n2, int R,
+                       const float* l0, const float* l1, int C1, const float* l2, int C2,
+                       const float* sft0_params, float* pts0, float* cond1, float* cond2, void* stream);
+
+/* Grouping gather: out[b,g,j,c] = pts[b, idx[b,g,j], c] - (c < 3 ? pts[b,g,c] : 0).
+ * Replaces lib/utils/utils.py:153-158 and :181-186.  pts addressed with
+ * (stride_cloud, stride_point, stride_ch) as in pdf_knn_ball; out fp32
+ * [n_clouds, n_centroids, k, C] with row pitch ld_out >= C;
+ * center (optional, may be null) fp32 [n_clouds, n_centroids, 3]. */
+int pdf_group_gather(const float* pts, int64_t n_clouds, int n_centroids, int k, int C,
+                     int64_t stride_cloud, int64_t stride_point, int64_t stride_ch,
+                     const int32_t* idx, float* out, int64_t ld_out, float* center, void* stream);
+
+/* Y = epilogue(X[M,K] * W[N,K]^T + bias[N]) in fp32 (FFMA, fp32 accumulate).
+ * The shared point-MLP layers (1x1 conv + folded BN + ReLU, intaghand_encoder.py:
+ * 48-103), the SFT 1x1 convs (:205-219) and mano_head (:630-643) are all this.
+ * lda/ldf/ldy are row pitches in elements.  See the PDF_EPI_* modes; `group` is
+ * the row-group size for PDF_EPI_GROUP_MAX. */
+int pdf_linear_f32(const float* X, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                   int64_t M, int N, int K, int act, int epilogue, int group,
+                   const float* F, int64_t ldf, float* Y, int64_t ldy, void* stream);
+
+/* Fused set-abstraction stage on tensor cores (tcgen05 + TMEM, bf16 operands,
+ * fp32 accumulate): neighbour gather + centroid subtraction + 3-layer shared
+ * point-MLP (folded BN, ReLU) + max over the k neighbours, one pass, no
+ * intermediate in HBM.  Replaces utils.py:153-158/181-186 + netR_1 / netR_2
+ * (intaghand_encoder.py:48-84,132,143).
+ * pts fp32 [n_clouds, n_src, ld_pts] (xyz = columns 0..2, c_in columns used);
+ * idx int32 [n_clouds, n_centroids, 64]; wpack = pdf_sa_pack_weights image;
+ * out fp32 [n_clouds, n_centroids, ld_out] columns out_col0 .. out_col0+c3-1.
+ * Supported (c_in,c1,c2,c3): (3,64,64,128) and (131,128,128,256); k = 64. */
+int pdf_sa_mlp_max_bf16(const float* pts, int64_t n_clouds, int n_src, int64_t ld_pts, int c_in,
+                        const int32_t* idx, int n_centroids, int k,
+                        const void* wpack, int c1, int c2, int c3,
+                        float* out, int64_t ld_out, int out_col0, void* stream);
+/* Size in bytes of, and host-side packer for, the weight image above: folded
+ * fp32 weights W1[c1,c_in],b1, W2[c2,c1],b2, W3[c3,c2],b3 -> bf16 tiles in the
+ * UMMA shared-memory layout + fp32 biases.  Pure host code (no CUDA call). */
+int64_t pdf_sa_pack_size(int c_in, int c1, int c2, int c3);
+int pdf_sa_pack_weights_host(const float* W1, const float* b1, const float* W2, const float* b2,
+                             const float* W3, const float* b3, int c_in, int c1, int c2, int c3,
+                             void* out_host);
+
+/* Depth back-projection xyz[b,:,v,u] = (Kinv[b] * [u,v,1]) * depth[b,v,u].
+ * Replaces get_points_coordinate (lib/utils/utils.py:251-262).  depth fp32
+ * [B,H,W], Kinv fp32 [B,3,3] (inverse intrinsics, computed by the caller as the
+ * reference does with np.linalg.inv, :269), xyz fp32 [B,3,H,W]. */
+int pdf_backproject(const float* depth, const float* Kinv, int64_t B, int H, int W, float* xyz, void* stream);
+
+/* Batched per-hand cloud construction from raw depth (device-side depth2pcl).
+ * Replaces depth2pcl (intaghand_encoder.py:369-491) / the dataset twin
+ * (lib/datasets/interhand.py:758-797) for every frame of a batch at once:
+ * noise gate 0.2<z<2.5, hand mask > 0.5, mean z of the non-zero pixels, window
+ * mean +- 0.08 clipped to [0.2,2.5], candidate pixels; < min_pixels -> zeros,
+ * > n_points -> the n_points candidates with the smallest subset_keys (pixel
+ * order kept), else wrap-pad; final order choose[i] = sel[perm[i]]; cloud =
+ * back-projected masked depth at choose.
+ * depth fp32 [B,H,W]; mask fp32 [B,2,H,W] (channel 0 = right hand, 1 = left,
+ * :376-377); Kinv fp32 [B,3,3]; valid fp32 [B,2] (0 = left, 1 = right);
+ * subset_keys int32 [B,2,H*W] (distinct per row; may be null when no hand can
+ * exceed n_points); perm int32 [B,2,n_points] (null = identity).
+ * choose int64 [B,2,n_points] (row 0 = left), cloud fp32 [B,2,n_points,3],
+ * n_cand int32 [B,2] (number of candidate pixels, for diagnostics).
+ * Supported: n_points == 1024. */
+int pdf_depth2pcl(const float* depth, const float* mask, const float* Kinv, const float* valid,
+                  const int32_t* subset_keys, const int32_t* perm, int64_t B, int H, int W,
+                  int n_points, int min_pixels, int64_t* choose, float* cloud, int32_t* n_cand, void* stream);
+
+/* MANO linear blend skinning, one hand per CTA, fp32.
+ * Replaces ManoLayer.forward with use_pca=False (lib/models/networks/manolayer.py:
+ * 257-334) including rodrigues_batch (:32-48).  Tables (device, fp32):
+ *   v_template [778*3]; shapedirs_t [10, 778*3] and posedirs_t [135, 778*3]
+ *   (basis index outermost so a CTA reads them coalesced); j_template [16,3] =
+ *   J_regressor*v_template and j_shapedirs [16,3,10] = J_regressor*shapedirs
+ *   (precomputed on the host in fp64); weights_t [16,778].
+ * Inputs: root [n,3] and pose [n,45] axis-angle, shape [n,10], trans [n,3] or
+ * null, scale [n] or null.  tip_idx_host: the 5 finger-tip vertex ids (:305-308).
+ * center_idx < 0 disables centring (:313-316).  new_skel as :328-332.
+ * Outputs v [n,778,3], j [n,21,3] (joints in the reference's new_order, :110-115). */
+int pdf_mano_lbs(const float* v_template, const float* shapedirs_t, const float* posedirs_t,
+                 const float* j_template, const float* j_shapedirs, const float* weights_t,
+                 const float* root, const float* pose, const float* shape, const float* trans,
+                 const float* scale, int64_t n, const int32_t* tip_idx_host, int center_idx, int new_skel,
+                 float* v, float* j, void* stream);
+
+/* Split_coeff (lib/models/hand3d/Mano_render.py:160-194, non-PCA) for one hand:
+ * theta [n,ld_theta] (61 used columns starting at col0), index int64 [n], K [n,3,3];
+ * writes root [n,3], pose [n,45], shape [n,10] (zeros: betas*0), trans [n,3]. */
+int pdf_split_coeff(const float* theta, int64_t ld_theta, int col0, const int64_t* index, const float* K,
+                    int64_t n, int input_res, int down_ratio,
+                    float* root, float* pose, float* shape, float* trans, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDFNET_B200_H */

@@ -1,0 +1,98 @@
+"""ctypes binding of the C-ABI library (include/pdfnet_b200.h).
+
+There is no CPU or eager-PyTorch fallback: if the shared library is missing the
+import of any compute module fails loudly, and every op raises when handed a
+non-CUDA tensor.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpdfnet_b200.so")
+
+_i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+
+# name -> argtypes, exactly mirroring include/pdfnet_b200.h
+SIGNATURES = {
+    "pdf_knn_ball": [_vp, _i64, _i32, _i32, _i32, _f32, _i64, _i64, _i64, _vp, _vp],
+    "pdf_fps": [_vp, _i64, _i32, _i32, _vp, _i64, _i64, _i64, _vp, _vp],
+    "pdf_gather_nchw": [_vp, _i64, _i32, _i32, _i64, _vp, _i32, _i64, _vp, _vp],
+    "pdf_pyramid_gather": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp,
+                           _vp, _vp],
+    "pdf_group_gather": [_vp, _i64, _i32, _i32, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp],
+    "pdf_linear_f32": [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _vp],
+    "pdf_sa_mlp_max_bf16": [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _i32,
+                            _vp],
+    "pdf_sa_pack_weights_host": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "pdf_backproject": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
+    "pdf_depth2pcl": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+    "pdf_mano_lbs": [_vp] * 11 + [_i64, _vp, _i32, _i32, _vp, _vp, _vp],
+    "pdf_split_coeff": [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
+}
+EXPORTS = sorted(list(SIGNATURES) + ["pdf_version", "pdf_last_error", "pdf_launch_count", "pdf_sa_pack_size"])
+
+ACT_NONE, ACT_RELU, ACT_LEAKY01 = 0, 1, 2
+EPI_STORE, EPI_SFT_SCALE, EPI_ACCUM, EPI_GROUP_MAX = 0, 1, 2, 3
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "pdfnet_b200: %s not found. Build it with `python -m pdfnet_b200.build` "
+            "(or __graft_entry__.build()); there is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    lib.pdf_version.restype = ctypes.c_int
+    lib.pdf_last_error.restype = ctypes.c_char_p
+    lib.pdf_launch_count.restype = ctypes.c_int64
+    lib.pdf_sa_pack_size.argtypes = [_i32, _i32, _i32, _i32]
+    lib.pdf_sa_pack_size.restype = ctypes.c_int64
+    _lib = lib
+    return lib
+
+
+def launch_count():
+    return int(load().pdf_launch_count())
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.pdf_last_error().decode("utf-8", "replace")
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, msg))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("pdfnet_b200 ops run on CUDA tensors only (no CPU fallback); got device %s" % t.device)
+
+
+def f32c(t):
+    """Contiguous fp32 view/copy."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

@@ -1,0 +1,255 @@
+// Device-side, batched depth2pcl: per-hand cloud construction from raw depth.
+// One CTA (1024 threads) per (frame, hand).  The frame is read from L2/HBM twice
+// (z statistics, candidate flags); afterwards everything works on a candidate
+// bitmask held in shared memory, so the algorithmic traffic is depth + 2 masks in,
+// choose + cloud out.
+#include "pdf_common.cuh"
+
+namespace pdf {
+
+constexpr int D2P_THREADS = 1024;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
+  // 1024 threads = 32 warps; returns the exclusive prefix of v over the block.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();                       // protect s_warp reuse
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane];
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    s_warp[lane] = winc - w;             // exclusive warp offsets
+    if (lane == 31) s_warp[32] = winc;   // block total
+  }
+  __syncthreads();
+  total = s_warp[32];
+  return s_warp[warp] + inc - v;
+}
+
+__global__ void __launch_bounds__(D2P_THREADS)
+depth2pcl_kernel(const float* __restrict__ depth, const float* __restrict__ mask, const float* __restrict__ Kinv,
+                 const float* __restrict__ valid, const int32_t* __restrict__ subset_keys,
+                 const int32_t* __restrict__ perm, int H, int W, int n_points, int min_pixels,
+                 int64_t* __restrict__ choose, float* __restrict__ cloud, int32_t* __restrict__ n_cand_out) {
+  extern __shared__ uint32_t s_bits[];             // candidate bitmask, nwords
+  __shared__ int s_sel[1024];
+  __shared__ int s_warp[33];
+  __shared__ double s_dsum[32];
+  __shared__ int s_hist[256];
+  __shared__ float s_lohi[2];
+  __shared__ int s_misc[4];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t f = blockIdx.x >> 1;
+  const int hand = blockIdx.x & 1;                 // 0 = left, 1 = right
+  const int mch = hand == 0 ? 1 : 0;               // intaghand_encoder.py:376-377
+  const int npx = H * W;
+  const int nwords = (npx + 31) >> 5;
+  const float* dep = depth + f * npx;
+  const float* msk = mask + (f * 2 + mch) * npx;
+  const float* Ki = Kinv + f * 9;
+  const float k20 = Ki[6], k21 = Ki[7], k22 = Ki[8];
+  int64_t* ch_out = choose + (f * 2 + hand) * n_points;
+  float* cl_out = cloud + (f * 2 + hand) * n_points * 3;
+
+  if (valid[f * 2 + hand] != 1.f) {                // :401,:430-435 -> zeros
+    for (int i = tid; i < n_points; i += D2P_THREADS) {
+      ch_out[i] = 0;
+      cl_out[i * 3] = 0.f; cl_out[i * 3 + 1] = 0.f; cl_out[i * 3 + 2] = 0.f;
+    }
+    if (tid == 0) n_cand_out[f * 2 + hand] = 0;
+    return;
+  }
+
+  auto masked_depth = [&](int pix) -> float {      // depth * noise_mask * (mask > 0.5)   :392-395
+    const float d = dep[pix];
+    const bool keep = (0.2f < d) && (2.5f > d) && (msk[pix] > 0.5f);
+    return keep ? d : 0.f;
+  };
+  auto z_of = [&](int pix, float zm) -> float {
+    const float u = (float)(pix % W), v = (float)(pix / W);
+    return __fmul_rn(fmaf(k21, v, fmaf(k20, u, k22)), zm);
+  };
+
+  // pass A: mean z over non-zero pixels (:407)
+  double sum = 0.0;
+  int cnt = 0;
+  for (int pix = tid; pix < npx; pix += D2P_THREADS) {
+    const float z = z_of(pix, masked_depth(pix));
+    if (z != 0.f) { sum += (double)z; ++cnt; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) { s_dsum[warp] = sum; s_warp[warp] = cnt; }
+  __syncthreads();
+  if (warp == 0) {
+    double s = s_dsum[lane];
+    int c = s_warp[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) {
+      const float mean = c > 0 ? (float)(s / (double)c) : 0.f;
+      s_lohi[0] = fmaxf(0.2f, __fsub_rn(mean, 0.08f));     // :408
+      s_lohi[1] = fminf(2.5f, __fadd_rn(mean, 0.08f));
+      s_misc[0] = c;
+    }
+  }
+  __syncthreads();
+  const int n_nonzero = s_misc[0];
+  const float lo = s_lohi[0], hi = s_lohi[1];
+
+  // pass B: candidate bitmask (:409), one word per warp iteration (coalesced)
+  int my_cand = 0;
+  for (int w0 = warp; w0 < nwords; w0 += 32) {
+    const int pix = w0 * 32 + lane;
+    bool c = false;
+    if (pix < npx && n_nonzero > 0) {
+      const float z = z_of(pix, masked_depth(pix));
+      c = (z > lo) && (z < hi);
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, c);
+    if (lane == 0) { s_bits[w0] = b; my_cand += __popc(b); }
+  }
+  int n_cand;
+  (void)block_exclusive_scan(my_cand, s_warp, n_cand);
+  if (tid == 0) n_cand_out[f * 2 + hand] = n_cand;
+
+  // words owned by this thread for the ordered enumerations below
+  const int wpt = (nwords + D2P_THREADS - 1) / D2P_THREADS;
+  const int wbeg = min(nwords, tid * wpt), wend = min(nwords, wbeg + wpt);
+
+  int n_sel = 0;                                   // entries valid in s_sel
+  if (n_cand >= min_pixels && n_cand <= n_points) {
+    // keep every candidate in pixel order (:424 pads by wrapping)
+    int c = 0;
+    for (int w = wbeg; w < wend; ++w) c += __popc(s_bits[w]);
+    int tot;
+    int r = block_exclusive_scan(c, s_warp, tot);
+    for (int w = wbeg; w < wend; ++w) {
+      unsigned b = s_bits[w];
+      while (b) { const int bit = __ffs(b) - 1; b &= b - 1; s_sel[r++] = w * 32 + bit; }
+    }
+    n_sel = n_cand;
+  } else if (n_cand > n_points) {
+    // random subset (:418-422): the n_points candidates with the smallest keys
+    const int32_t* keys = subset_keys + (f * 2 + hand) * (int64_t)npx;
+    uint32_t prefix = 0;
+    int remaining = n_points;                      // rank (1-based) of the threshold inside the prefix bucket
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      if (tid < 256) s_hist[tid] = 0;
+      __syncthreads();
+      const uint32_t hmask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+      for (int w = wbeg; w < wend; ++w) {
+        unsigned b = s_bits[w];
+        while (b) {
+          const int bit = __ffs(b) - 1; b &= b - 1;
+          const uint32_t kx = (uint32_t)keys[w * 32 + bit] ^ 0x80000000u;   // signed order -> unsigned
+          if ((kx & hmask) == prefix) atomicAdd(&s_hist[(kx >> shift) & 255], 1);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int acc = 0, d = 0;
+        for (; d < 256; ++d) { if (acc + s_hist[d] >= remaining) break; acc += s_hist[d]; }
+        s_misc[1] = d; s_misc[2] = remaining - acc;
+      }
+      __syncthreads();
+      prefix |= ((uint32_t)s_misc[1]) << shift;
+      remaining = s_misc[2];
+      __syncthreads();
+    }
+    const uint32_t thr = prefix;                   // n_points-th smallest key; `remaining` ties allowed
+    // ordered enumeration: first rank the ties, then the selected set
+    int c_eq = 0;
+    for (int w = wbeg; w < wend; ++w) {
+      unsigned b = s_bits[w];
+      while (b) {
+        const int bit = __ffs(b) - 1; b &= b - 1;
+        c_eq += (((uint32_t)keys[w * 32 + bit] ^ 0x80000000u) == thr) ? 1 : 0;
+      }
+    }
+    int tot;
+    int eq_rank = block_exclusive_scan(c_eq, s_warp, tot);
+    int c_sel = 0;
+    {
+      int er = eq_rank;
+      for (int w = wbeg; w < wend; ++w) {
+        unsigned b = s_bits[w];
+        while (b) {
+          const int bit = __ffs(b) - 1; b &= b - 1;
+          const uint32_t kx = (uint32_t)keys[w * 32 + bit] ^ 0x80000000u;
+          if (kx < thr || (kx == thr && er++ < remaining)) ++c_sel;
+        }
+      }
+    }
+    int r = block_exclusive_scan(c_sel, s_warp, tot);
+    {
+      int er = eq_rank;
+      for (int w = wbeg; w < wend; ++w) {
+        unsigned b = s_bits[w];
+        while (b) {
+          const int bit = __ffs(b) - 1; b &= b - 1;
+          const uint32_t kx = (uint32_t)keys[w * 32 + bit] ^ 0x80000000u;
+          if (kx < thr || (kx == thr && er++ < remaining)) { if (r < 1024) s_sel[r] = w * 32 + bit; ++r; }
+        }
+      }
+    }
+    n_sel = n_points;
+  }
+  __syncthreads();
+
+  // final order + back-projection of the kept pixels (:427-428)
+  const int32_t* pm = perm ? perm + (f * 2 + hand) * (int64_t)n_points : nullptr;
+  for (int i = tid; i < n_points; i += D2P_THREADS) {
+    const int src = pm ? pm[i] : i;
+    const int pix = n_sel > 0 ? s_sel[src % n_sel] : 0;
+    const float zm = masked_depth(pix);
+    const float u = (float)(pix % W), v = (float)(pix / W);
+    ch_out[i] = pix;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      cl_out[i * 3 + r] = __fmul_rn(fmaf(Ki[r * 3 + 1], v, fmaf(Ki[r * 3], u, Ki[r * 3 + 2])), zm);
+  }
+}
+
+}  // namespace pdf
+
+extern "C" int pdf_depth2pcl(const float* depth, const float* mask, const float* Kinv, const float* valid,
+                             const int32_t* subset_keys, const int32_t* perm, int64_t B, int H, int W,
+                             int n_points, int min_pixels, int64_t* choose, float* cloud, int32_t* n_cand,
+                             void* stream) {
+  PDF_REQUIRE(depth && mask && Kinv && valid && choose && cloud && n_cand, PDF_ERR_BAD_ARG,
+              "pdf_depth2pcl: null pointer");
+  PDF_REQUIRE(B >= 0 && H > 0 && W > 0 && min_pixels >= 1, PDF_ERR_BAD_ARG, "pdf_depth2pcl: bad size");
+  PDF_REQUIRE(n_points == 1024, PDF_ERR_UNSUPPORTED, "pdf_depth2pcl: n_points must be 1024 (got %d)", n_points);
+  PDF_REQUIRE((int64_t)H * W <= 1024 * 1024, PDF_ERR_UNSUPPORTED, "pdf_depth2pcl: frame larger than 1024x1024");
+  PDF_REQUIRE(subset_keys != nullptr || (int64_t)H * W <= n_points, PDF_ERR_BAD_ARG,
+              "pdf_depth2pcl: subset_keys required when a hand can exceed n_points pixels");
+  if (B == 0) return PDF_OK;
+  const size_t smem = (size_t)(((int64_t)H * W + 31) / 32) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(pdf::depth2pcl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_set = true;
+  }
+  pdf::depth2pcl_kernel<<<(unsigned)(B * 2), pdf::D2P_THREADS, smem, (cudaStream_t)stream>>>(
+      depth, mask, Kinv, valid, subset_keys, perm, H, W, n_points, min_pixels, choose, cloud, n_cand);
+  return pdf::check_launch("pdf_depth2pcl");
+}

@@ -1,0 +1,226 @@
+// Bandwidth-bound kernels: NCHW row gathers, the 3-level pyramid gather with the
+// level-0 SFT fused, the grouping gather, back-projection and Split_coeff.
+#include "pdf_common.cuh"
+
+namespace pdf {
+
+// out[b,i,c] = feat[b/cpf, c, ind[b,i]] ; thread per output element, c fastest so
+// stores are coalesced; loads hit one 32 B sector each (NCHW hand-off).
+__global__ void gather_nchw_kernel(const float* __restrict__ feat, int clouds_per_frame, int C, int64_t HW,
+                                   const int64_t* __restrict__ ind, int n, int64_t ind_stride,
+                                   float* __restrict__ out, int64_t total) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const int64_t bi = e / C;
+    const int i = (int)(bi % n);
+    const int64_t b = bi / n;
+    const int64_t pix = ind[b * ind_stride + i];
+    out[e] = __ldg(feat + ((b / clouds_per_frame) * C + c) * HW + pix);
+  }
+}
+
+__device__ __forceinline__ float leaky01(float v) { return v > 0.f ? v : 0.1f * v; }
+
+// sft0: 3 -> 3 -> 3 scale and shift branches (intaghand_encoder.py:205-219), fp32.
+__device__ __forceinline__ void sft0_apply(const float* __restrict__ P, const float e[3], float xyz[3]) {
+  float out[2][3];
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    const float* W0 = P + br * 24;
+    const float* b0 = W0 + 9;
+    const float* W1 = b0 + 3;
+    const float* b1 = W1 + 9;
+    float h[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o)
+      h[o] = leaky01(fmaf(W0[o * 3 + 2], e[2], fmaf(W0[o * 3 + 1], e[1], fmaf(W0[o * 3], e[0], b0[o]))));
+#pragma unroll
+    for (int o = 0; o < 3; ++o)
+      out[br][o] = fmaf(W1[o * 3 + 2], h[2], fmaf(W1[o * 3 + 1], h[1], fmaf(W1[o * 3], h[0], b1[o])));
+  }
+#pragma unroll
+  for (int o = 0; o < 3; ++o) xyz[o] = __fadd_rn(__fmul_rn(xyz[o], __fadd_rn(out[0][o], 1.f)), out[1][o]);
+}
+
+// grid.x = cloud; three sections handled by the same CTA:
+//   (1) points 0..n_points-1: gather 3 channels of l0, SFT0, write pts0
+//   (2) n1 x C1 elements of l1 at choose_1_2 ; (3) n2 x C2 elements of l2 at choose_1_4
+__global__ void __launch_bounds__(256)
+pyramid_gather_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ choose, int clouds_per_frame,
+                      int n_points, int n1, int n2, int R,
+                      const float* __restrict__ l0, const float* __restrict__ l1, int C1,
+                      const float* __restrict__ l2, int C2, const float* __restrict__ sft0,
+                      float* __restrict__ pts0, float* __restrict__ cond1, float* __restrict__ cond2) {
+  __shared__ float P[48];
+  const int64_t b = blockIdx.x;
+  const int64_t f = b / clouds_per_frame;
+  if (threadIdx.x < 48) P[threadIdx.x] = sft0[threadIdx.x];
+  __syncthreads();
+  const int64_t* ch = choose + b * n_points;
+  const int64_t RR = (int64_t)R * R;
+  for (int i = threadIdx.x; i < n_points; i += blockDim.x) {
+    const int64_t pix = ch[i];
+    float e[3], p[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      e[c] = __ldg(l0 + (f * 3 + c) * RR + pix);
+      p[c] = xyz[(b * n_points + i) * 3 + c];
+    }
+    sft0_apply(P, e, p);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pts0[(b * n_points + i) * 3 + c] = p[c];
+  }
+  const int R2 = R / 2, R4 = R / 4;
+  const int64_t HW2 = (int64_t)R2 * R2, HW4 = (int64_t)R4 * R4;
+  for (int e = threadIdx.x; e < n1 * C1; e += blockDim.x) {
+    const int i = e / C1, c = e % C1;
+    const int64_t pix = ch[i];
+    const int64_t p2 = (pix / R / 2) * R2 + (pix % R) / 2;     // intaghand_encoder.py:125
+    cond1[(b * n1 + i) * C1 + c] = __ldg(l1 + (f * C1 + c) * HW2 + p2);
+  }
+  for (int e = threadIdx.x; e < n2 * C2; e += blockDim.x) {
+    const int i = e / C2, c = e % C2;
+    const int64_t pix = ch[i];
+    const int64_t p4 = (pix / R / 4) * R4 + (pix % R) / 4;     // intaghand_encoder.py:126
+    cond2[(b * n2 + i) * C2 + c] = __ldg(l2 + (f * C2 + c) * HW4 + p4);
+  }
+}
+
+// out[b,g,j,c] = pts[b,idx[b,g,j],c] - (c<3 ? pts[b,g,c] : 0).  One warp per output
+// row; lanes stride over channels (coalesced for point-major sources).
+__global__ void __launch_bounds__(256)
+group_gather_kernel(const float* __restrict__ pts, int n_centroids, int k, int C,
+                    int64_t stride_cloud, int64_t stride_point, int64_t stride_ch,
+                    const int32_t* __restrict__ idx, float* __restrict__ out, int64_t ld_out,
+                    float* __restrict__ center, int64_t n_rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < n_rows; row += nwarps) {
+    const int64_t bg = row / k;
+    const int g = (int)(bg % n_centroids);
+    const int64_t b = bg / n_centroids;
+    const float* base = pts + b * stride_cloud;
+    const float* src = base + (int64_t)idx[row] * stride_point;
+    const float* cen = base + (int64_t)g * stride_point;
+    float* dst = out + row * ld_out;
+    for (int c = lane; c < C; c += 32) {
+      float v = src[c * stride_ch];
+      if (c < 3) v = __fsub_rn(v, cen[c * stride_ch]);
+      dst[c] = v;
+    }
+    if (center != nullptr && (row % k) == 0 && lane < 3) center[bg * 3 + lane] = cen[lane * stride_ch];
+  }
+}
+
+// xyz[b,r,v,u] = (Kinv[r,0]*u + Kinv[r,1]*v + Kinv[r,2]) * depth  (utils.py:251-262)
+__global__ void backproject_kernel(const float* __restrict__ depth, const float* __restrict__ Kinv,
+                                   int H, int W, float* __restrict__ xyz, int64_t total) {
+  const int64_t HW = (int64_t)H * W;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = e / HW;
+    const int64_t pix = e % HW;
+    const float u = (float)(pix % W), v = (float)(pix / W);
+    const float z = depth[e];
+    const float* Ki = Kinv + b * 9;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float ray = fmaf(Ki[r * 3 + 1], v, fmaf(Ki[r * 3 + 0], u, Ki[r * 3 + 2]));
+      xyz[(b * 3 + r) * HW + pix] = __fmul_rn(ray, z);
+    }
+  }
+}
+
+// Split_coeff, one thread per hand row (Mano_render.py:160-194).
+__global__ void split_coeff_kernel(const float* __restrict__ theta, int64_t ld, int col0,
+                                   const int64_t* __restrict__ index, const float* __restrict__ K, int64_t n,
+                                   int input_res, int down_ratio, float* __restrict__ root,
+                                   float* __restrict__ pose, float* __restrict__ shape, float* __restrict__ trans) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* t = theta + i * ld + col0;
+  for (int c = 0; c < 3; ++c) root[i * 3 + c] = t[c];
+  for (int c = 0; c < 45; ++c) pose[i * 45 + c] = t[3 + c];
+  for (int c = 0; c < 10; ++c) shape[i * 10 + c] = t[48 + c] * 0.f;
+  const float* Ki = K + i * 9;
+  const int g = input_res / down_ratio;
+  const float cx = (float)((index[i] % g) * down_ratio), cy = (float)((index[i] / g) * down_ratio);
+  const float tz = __fadd_rn(t[60], 0.6f);
+  trans[i * 3 + 0] = __fdiv_rn(__fmul_rn(tz, __fsub_rn(__fadd_rn(t[58], cx), Ki[2])), Ki[0]);
+  trans[i * 3 + 1] = __fdiv_rn(__fmul_rn(tz, __fsub_rn(__fadd_rn(t[59], cy), Ki[5])), Ki[4]);
+  trans[i * 3 + 2] = tz;
+}
+
+static inline unsigned grid_for(int64_t total, int block, int max_blocks = 148 * 16) {
+  int64_t g = (total + block - 1) / block;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+}  // namespace pdf
+
+extern "C" int pdf_gather_nchw(const float* feat, int64_t n_clouds, int clouds_per_frame, int C, int64_t HW,
+                               const int64_t* ind, int n, int64_t ind_stride, float* out, void* stream) {
+  PDF_REQUIRE(feat && ind && out, PDF_ERR_BAD_ARG, "pdf_gather_nchw: null pointer");
+  PDF_REQUIRE(n_clouds >= 0 && clouds_per_frame > 0 && C > 0 && HW > 0 && n >= 0, PDF_ERR_BAD_ARG,
+              "pdf_gather_nchw: bad size");
+  const int64_t total = n_clouds * n * C;
+  if (total == 0) return PDF_OK;
+  pdf::gather_nchw_kernel<<<pdf::grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      feat, clouds_per_frame, C, HW, ind, n, ind_stride, out, total);
+  return pdf::check_launch("pdf_gather_nchw");
+}
+
+extern "C" int pdf_pyramid_gather(const float* xyz, const int64_t* choose, int64_t n_clouds, int clouds_per_frame,
+                                  int n_points, int n1, int n2, int R, const float* l0, const float* l1, int C1,
+                                  const float* l2, int C2, const float* sft0_params, float* pts0, float* cond1,
+                                  float* cond2, void* stream) {
+  PDF_REQUIRE(xyz && choose && l0 && l1 && l2 && sft0_params && pts0 && cond1 && cond2, PDF_ERR_BAD_ARG,
+              "pdf_pyramid_gather: null pointer");
+  PDF_REQUIRE(n_clouds >= 0 && clouds_per_frame > 0 && n_points > 0 && n1 >= 0 && n2 >= 0 && n1 <= n_points &&
+                  n2 <= n_points && R >= 4 && C1 > 0 && C2 > 0,
+              PDF_ERR_BAD_ARG, "pdf_pyramid_gather: bad size");
+  if (n_clouds == 0) return PDF_OK;
+  pdf::pyramid_gather_kernel<<<(unsigned)n_clouds, 256, 0, (cudaStream_t)stream>>>(
+      xyz, choose, clouds_per_frame, n_points, n1, n2, R, l0, l1, C1, l2, C2, sft0_params, pts0, cond1, cond2);
+  return pdf::check_launch("pdf_pyramid_gather");
+}
+
+extern "C" int pdf_group_gather(const float* pts, int64_t n_clouds, int n_centroids, int k, int C,
+                                int64_t stride_cloud, int64_t stride_point, int64_t stride_ch, const int32_t* idx,
+                                float* out, int64_t ld_out, float* center, void* stream) {
+  PDF_REQUIRE(pts && idx && out, PDF_ERR_BAD_ARG, "pdf_group_gather: null pointer");
+  PDF_REQUIRE(n_clouds >= 0 && n_centroids > 0 && k > 0 && C >= 3 && ld_out >= C, PDF_ERR_BAD_ARG,
+              "pdf_group_gather: bad size");
+  const int64_t rows = n_clouds * n_centroids * k;
+  if (rows == 0) return PDF_OK;
+  pdf::group_gather_kernel<<<pdf::grid_for(rows * 32, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+      pts, n_centroids, k, C, stride_cloud, stride_point, stride_ch, idx, out, ld_out, center, rows);
+  return pdf::check_launch("pdf_group_gather");
+}
+
+extern "C" int pdf_backproject(const float* depth, const float* Kinv, int64_t B, int H, int W, float* xyz,
+                               void* stream) {
+  PDF_REQUIRE(depth && Kinv && xyz, PDF_ERR_BAD_ARG, "pdf_backproject: null pointer");
+  PDF_REQUIRE(B >= 0 && H > 0 && W > 0, PDF_ERR_BAD_ARG, "pdf_backproject: bad size");
+  const int64_t total = B * H * W;
+  if (total == 0) return PDF_OK;
+  pdf::backproject_kernel<<<pdf::grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(depth, Kinv, H, W, xyz,
+                                                                                       total);
+  return pdf::check_launch("pdf_backproject");
+}
+
+extern "C" int pdf_split_coeff(const float* theta, int64_t ld_theta, int col0, const int64_t* index, const float* K,
+                               int64_t n, int input_res, int down_ratio, float* root, float* pose, float* shape,
+                               float* trans, void* stream) {
+  PDF_REQUIRE(theta && index && K && root && pose && shape && trans, PDF_ERR_BAD_ARG, "pdf_split_coeff: null pointer");
+  PDF_REQUIRE(n >= 0 && input_res > 0 && down_ratio > 0 && col0 >= 0 && ld_theta >= col0 + 61, PDF_ERR_BAD_ARG,
+              "pdf_split_coeff: bad size");
+  if (n == 0) return PDF_OK;
+  pdf::split_coeff_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      theta, ld_theta, col0, index, K, n, input_res, down_ratio, root, pose, shape, trans);
+  return pdf::check_launch("pdf_split_coeff");
+}

@@ -1,0 +1,199 @@
+// MANO linear blend skinning, one hand per CTA, fp32 end to end (the 1e-5 m
+// tolerance rules out bf16 bases, SURVEY.md section 7 "LBS precision").
+// The whole op is 1.17 MFLOP per hand and a 16-step dependent chain: it is
+// latency bound, so the kernel keeps everything of one hand in shared memory and
+// reads the (L2-resident, 1.4 MB) basis tables in a coalesced, transposed layout.
+#include "pdf_common.cuh"
+
+namespace pdf {
+
+constexpr int NV = 778, NE = NV * 3;
+
+__constant__ int c_parent[16] = {-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 0, 10, 11, 0, 13, 14};  // kintree_table[0]
+__constant__ int c_new_order[21] = {0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20};
+
+struct Tips { int v[5]; };
+
+__global__ void __launch_bounds__(256)
+mano_lbs_kernel(const float* __restrict__ v_template, const float* __restrict__ shapedirs_t,
+                const float* __restrict__ posedirs_t, const float* __restrict__ j_template,
+                const float* __restrict__ j_shapedirs, const float* __restrict__ weights_t,
+                const float* __restrict__ root, const float* __restrict__ pose, const float* __restrict__ shape,
+                const float* __restrict__ trans, const float* __restrict__ scale, Tips tips, int center_idx,
+                int new_skel, float* __restrict__ v_out, float* __restrict__ j_out) {
+  __shared__ float s_aa[48];          // axis-angle: root + 15 joints
+  __shared__ float s_beta[10];
+  __shared__ float s_R[16][9];
+  __shared__ float s_pf[135];         // pose feature R - I
+  __shared__ float s_jt[16][3];       // rest joints
+  __shared__ float s_G[16][12];       // global 3x4 transforms
+  __shared__ float s_v[NE];           // v_tpose, then posed vertices
+  __shared__ float s_j[21][3];
+  const int64_t h = blockIdx.x;
+  const int tid = threadIdx.x;
+
+  if (tid < 3) s_aa[tid] = root[h * 3 + tid];
+  else if (tid < 48) s_aa[tid] = pose[h * 45 + tid - 3];
+  else if (tid < 58) s_beta[tid - 48] = shape[h * 10 + tid - 48];
+  __syncthreads();
+
+  if (tid < 16) {                     // rodrigues_batch, manolayer.py:32-48
+    const float ax = s_aa[tid * 3], ay = s_aa[tid * 3 + 1], az = s_aa[tid * 3 + 2];
+    const float angle = sqrtf(ax * ax + ay * ay + az * az) + 1e-8f;
+    const float x = ax / angle, y = ay / angle, z = az / angle;
+    const float sn = sinf(angle), cs = cosf(angle);
+    const float L[9] = {0.f, -z, y, z, 0.f, -x, -y, x, 0.f};
+    const float oc = 1.f - cs;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float ll = L[r * 3] * L[c] + L[r * 3 + 1] * L[3 + c] + L[r * 3 + 2] * L[6 + c];
+        const float v = (r == c ? 1.f : 0.f) + sn * L[r * 3 + c] + oc * ll;
+        s_R[tid][r * 3 + c] = v;
+        if (tid > 0) s_pf[(tid - 1) * 9 + r * 3 + c] = v - (r == c ? 1.f : 0.f);
+      }
+  } else if (tid >= 32 && tid < 80) { // rest joints = J_regressor (v_template + shapedirs beta)
+    const int e = tid - 32;
+    float a = j_template[e];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) a = fmaf(j_shapedirs[e * 10 + k], s_beta[k], a);
+    s_jt[e / 3][e % 3] = a;
+  }
+  __syncthreads();
+
+  // blend shapes: v_tpose = v_template + shapedirs beta + posedirs (R - I)   (:274-282)
+  for (int e = tid; e < NE; e += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) a = fmaf(__ldg(shapedirs_t + k * NE + e), s_beta[k], a);
+    a += __ldg(v_template + e);
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll 9
+    for (int k = 0; k < 135; k += 3) {
+      p0 = fmaf(__ldg(posedirs_t + (k + 0) * NE + e), s_pf[k + 0], p0);
+      p1 = fmaf(__ldg(posedirs_t + (k + 1) * NE + e), s_pf[k + 1], p1);
+      p2 = fmaf(__ldg(posedirs_t + (k + 2) * NE + e), s_pf[k + 2], p2);
+    }
+    s_v[e] = a + ((p0 + p1) + p2);
+  }
+
+  // kinematic chain (:284-293): G_i = G_parent * [R_i | (I - R_i) j_i], warp 0 only
+  if (tid < 32) {
+    const int r = tid / 4, c = tid % 4;           // lanes 0..11 hold one 3x4 entry
+    for (int i = 0; i < 16; ++i) {
+      if (tid < 12) {
+        float l[4];                               // column c of the local transform (rows 0..2)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (c < 3) l[k] = s_R[i][k * 3 + c];
+          else {
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) t = fmaf(((k == q) ? 1.f : 0.f) - s_R[i][k * 3 + q], s_jt[i][q], t);
+            l[k] = t;
+          }
+        }
+        float g;
+        if (i == 0) g = l[r];
+        else {
+          const float* P = s_G[c_parent[i]];
+          g = P[r * 4] * l[0] + P[r * 4 + 1] * l[1] + P[r * 4 + 2] * l[2] + (c == 3 ? P[r * 4 + 3] : 0.f);
+        }
+        s_G[i][r * 4 + c] = g;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // skinning (:301-304)
+  for (int v = tid; v < NV; v += 256) {
+    float g[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) g[q] = 0.f;
+#pragma unroll
+    for (int jn = 0; jn < 16; ++jn) {
+      const float w = __ldg(weights_t + jn * NV + v);
+#pragma unroll
+      for (int q = 0; q < 12; ++q) g[q] = fmaf(w, s_G[jn][q], g[q]);
+    }
+    const float x = s_v[v * 3], y = s_v[v * 3 + 1], z = s_v[v * 3 + 2];
+    const float ox = g[0] * x + g[1] * y + g[2] * z + g[3];
+    const float oy = g[4] * x + g[5] * y + g[6] * z + g[7];
+    const float oz = g[8] * x + g[9] * y + g[10] * z + g[11];
+    s_v[v * 3] = ox; s_v[v * 3 + 1] = oy; s_v[v * 3 + 2] = oz;
+  }
+  __syncthreads();
+
+  // joints: 16 posed joints + 5 tips, reordered (:295-311)
+  if (tid < 21 * 3) {
+    const int jo = tid / 3, c = tid % 3;
+    const int src = c_new_order[jo];
+    float val;
+    if (src == 0) val = s_jt[0][c];
+    else if (src < 16) {
+      const float* P = s_G[c_parent[src]];
+      val = P[c * 4] * s_jt[src][0] + P[c * 4 + 1] * s_jt[src][1] + P[c * 4 + 2] * s_jt[src][2] + P[c * 4 + 3];
+    } else val = s_v[tips.v[src - 16] * 3 + c];
+    s_j[jo][c] = val;
+  }
+  __syncthreads();
+
+  float cen[3] = {0.f, 0.f, 0.f};
+  if (center_idx >= 0) { cen[0] = s_j[center_idx][0]; cen[1] = s_j[center_idx][1]; cen[2] = s_j[center_idx][2]; }
+  const float sc = scale ? scale[h] : 1.f;
+  float tr[3] = {0.f, 0.f, 0.f};
+  if (trans) { tr[0] = trans[h * 3]; tr[1] = trans[h * 3 + 1]; tr[2] = trans[h * 3 + 2]; }
+  __syncthreads();
+  for (int e = tid; e < NE; e += 256) {
+    float val = s_v[e];
+    if (center_idx >= 0) val = val - cen[e % 3];
+    if (scale) val = val * sc;
+    if (trans) val = val + tr[e % 3];
+    s_v[e] = val;
+    v_out[h * NE + e] = val;
+  }
+  if (tid < 63) {
+    float val = s_j[tid / 3][tid % 3];
+    if (center_idx >= 0) val = val - cen[tid % 3];
+    if (scale) val = val * sc;
+    if (trans) val = val + tr[tid % 3];
+    s_j[tid / 3][tid % 3] = val;
+  }
+  __syncthreads();
+  if (tid < 63) {
+    const int jo = tid / 3, c = tid % 3;
+    float val = s_j[jo][c];
+    if (new_skel) {                                 // :328-332
+      if (jo == 5) val = (s_v[63 * 3 + c] + s_v[144 * 3 + c]) / 2.f;
+      else if (jo == 9) val = (s_v[271 * 3 + c] + s_v[220 * 3 + c]) / 2.f;
+      else if (jo == 13) val = (s_v[148 * 3 + c] + s_v[290 * 3 + c]) / 2.f;
+      else if (jo == 17) val = (s_v[770 * 3 + c] + s_v[83 * 3 + c]) / 2.f;
+    }
+    j_out[h * 63 + tid] = val;
+  }
+}
+
+}  // namespace pdf
+
+extern "C" int pdf_mano_lbs(const float* v_template, const float* shapedirs_t, const float* posedirs_t,
+                            const float* j_template, const float* j_shapedirs, const float* weights_t,
+                            const float* root, const float* pose, const float* shape, const float* trans,
+                            const float* scale, int64_t n, const int32_t* tip_idx_host, int center_idx,
+                            int new_skel, float* v, float* j, void* stream) {
+  PDF_REQUIRE(v_template && shapedirs_t && posedirs_t && j_template && j_shapedirs && weights_t, PDF_ERR_BAD_ARG,
+              "pdf_mano_lbs: null table pointer");
+  PDF_REQUIRE(root && pose && shape && v && j && tip_idx_host, PDF_ERR_BAD_ARG, "pdf_mano_lbs: null pointer");
+  PDF_REQUIRE(n >= 0 && center_idx < 21, PDF_ERR_BAD_ARG, "pdf_mano_lbs: bad size");
+  pdf::Tips tips;
+  for (int i = 0; i < 5; ++i) {
+    PDF_REQUIRE(tip_idx_host[i] >= 0 && tip_idx_host[i] < pdf::NV, PDF_ERR_BAD_ARG, "pdf_mano_lbs: tip index");
+    tips.v[i] = tip_idx_host[i];
+  }
+  if (n == 0) return PDF_OK;
+  pdf::mano_lbs_kernel<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(
+      v_template, shapedirs_t, posedirs_t, j_template, j_shapedirs, weights_t, root, pose, shape, trans, scale, tips,
+      center_idx, new_skel, v, j);
+  return pdf::check_launch("pdf_mano_lbs");
+}

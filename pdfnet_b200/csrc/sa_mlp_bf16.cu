@@ -1,0 +1,369 @@
+// Fused set-abstraction stage on 5th-gen tensor cores:
+//   neighbour gather -> centroid subtraction -> 3-layer shared point-MLP (BN folded,
+//   ReLU) -> max over the 64 neighbours, with NO intermediate in HBM.
+//
+// Design (one persistent CTA per SM, S independent "slots" of 128 threads each):
+//   * a tile = 128 neighbour rows = 2 groups (centroids) x 64 neighbours;
+//   * folded bf16 weights of all three layers stay resident in shared memory for the
+//     lifetime of the CTA, in the exact UMMA operand layout, brought in with one
+//     cp.async.bulk (TMA engine) per 32 KB chunk from a host-packed image;
+//   * layers 1 and 2 run "points as M": D[p, c] (TMEM lane = point) so each thread
+//     repacks ITS row to bf16 (cvt.rn.relu.bf16x2) straight into the next operand tile;
+//   * layer 3 runs transposed, "channels as M": D[c, p] (TMEM lane = channel), so the
+//     max over the 64 neighbours is a per-thread reduction over TMEM columns
+//     (3-input FMNMX), no shuffles;
+//   * biases never touch the CUDA cores: every operand tile carries a 16-column
+//     auxiliary K block [x_hi y_hi z_hi 1 | x_lo y_lo z_lo 1 | 0...] against weight
+//     columns [w_x w_y w_z b_hi | w_x w_y w_z b_lo | 0...] (layer 1) or
+//     [0 0 0 b_hi | 0 0 0 b_lo | 0...] (layers 2,3): the relative coordinates enter
+//     as a bf16 hi+lo pair (~fp32 accuracy) and the bias is added by the MMA itself;
+//   * each slot issues its own MMAs (one elected thread) and waits on its own
+//     mbarrier; slots overlap each other's CUDA-core phases with tensor-core phases.
+#include "pdf_common.cuh"
+#include "umma.cuh"
+
+namespace pdf {
+using namespace umma;
+
+template <int CF_, int C1_, int C2_, int C3_, int SLOTS_>
+struct SaCfg {
+  static constexpr int CF = CF_;        // feature channels gathered with each neighbour (0 or 128)
+  static constexpr int C1 = C1_, C2 = C2_, C3 = C3_, SLOTS = SLOTS_;
+  static constexpr int KB1 = CF / 64, KB2 = C1 / 64, KB3 = C2 / 64;       // 64-wide SW128 K blocks per layer
+  // weight image (bytes): [W1 feat blocks][W1 aux][W2 feat][W2 aux][W3 feat][W3 aux]
+  static constexpr int W1_FEAT = KB1 * C1 * 128, W1_AUX = C1 * 32;
+  static constexpr int W2_FEAT = KB2 * C2 * 128, W2_AUX = C2 * 32;
+  static constexpr int W3_FEAT = KB3 * C3 * 128, W3_AUX = C3 * 32;
+  static constexpr int OFF_W1A = W1_FEAT, OFF_W2 = OFF_W1A + W1_AUX, OFF_W2A = OFF_W2 + W2_FEAT;
+  static constexpr int OFF_W3 = OFF_W2A + W2_AUX, OFF_W3A = OFF_W3 + W3_FEAT;
+  static constexpr int W_BYTES = OFF_W3A + W3_AUX;
+  static constexpr int KBMAX = (KB1 > KB2 ? (KB1 > KB3 ? KB1 : KB3) : (KB2 > KB3 ? KB2 : KB3));
+  static constexpr int SLOT_FEAT = KBMAX * 128 * 128;                     // activation tile, in place
+  static constexpr int SLOT_BYTES = SLOT_FEAT + 128 * 32;                 // + geometry/bias aux block
+  static constexpr int SMEM_BYTES = W_BYTES + SLOTS * SLOT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_PER_SLOT = (C3 > C1 + C2) ? C3 : ((C1 + C2) > 128 ? C1 + C2 : 128);
+  static constexpr int THREADS = SLOTS * 128;
+  static_assert(SLOTS * TMEM_PER_SLOT <= 512, "TMEM budget");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+using Sa1Cfg = SaCfg<0, 64, 64, 128, 4>;
+using Sa2Cfg = SaCfg<128, 128, 128, 256, 2>;
+
+// One layer = (KB SW128 K-blocks x 4 K-steps) + 1 aux K-step, accumulating into d_tmem.
+template <int KB>
+__device__ __forceinline__ void issue_layer(uint32_t a_feat, uint32_t a_blk, uint32_t a_aux, uint32_t b_feat,
+                                            uint32_t b_blk, uint32_t b_aux, uint32_t d_tmem, uint32_t idesc) {
+  bool acc = false;
+#pragma unroll
+  for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+    for (int k16 = 0; k16 < 4; ++k16) {
+      mma_bf16(d_tmem, desc_sw128(a_feat + kb * a_blk + k16 * 32), desc_sw128(b_feat + kb * b_blk + k16 * 32), idesc,
+               acc);
+      acc = true;
+    }
+  }
+  mma_bf16(d_tmem, desc_none(a_aux), desc_none(b_aux), idesc, acc);
+}
+
+// Epilogue of layers 1/2: TMEM row (this thread's point) -> ReLU -> bf16 -> SW128 tile row.
+template <int C>
+__device__ __forceinline__ void epilogue_repack(uint32_t tmem_row, uint8_t* feat, int p) {
+#pragma unroll
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_row + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                         // 4 chunks of 8 columns
+      const int col = c0 + q * 8;
+      uint4 w;
+      w.x = pack_relu_bf16(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+      w.y = pack_relu_bf16(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+      w.z = pack_relu_bf16(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+      w.w = pack_relu_bf16(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+      *reinterpret_cast<uint4*>(feat + (col >> 6) * (128 * 128) + sw128_off(p, col & 63)) = w;
+    }
+  }
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, const int32_t* __restrict__ idx,
+                  int n_centroids, const uint8_t* __restrict__ wpack, float* __restrict__ out, int64_t ld_out,
+                  int out_col0, int64_t n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_w = smem;
+  uint8_t* s_slots = smem + Cfg::W_BYTES;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_slots + Cfg::SLOTS * Cfg::SLOT_BYTES);   // [0]=weights, [1+s]=slot
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slot = tid >> 7, p = tid & 127;              // p: tile row (layers 1,2) / channel lane (layer 3)
+  const int wslot = warp & 3;                            // TMEM lane quarter of this warp
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_bar[0]), 1);
+    for (int s = 0; s < Cfg::SLOTS; ++s) mbar_init(smem_u32(&s_bar[1 + s]), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(s_tmem);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (tid == 0) {                                        // resident weights: bulk copies on the TMA engine
+    mbar_expect_tx(smem_u32(&s_bar[0]), Cfg::W_BYTES);
+    for (int off = 0; off < Cfg::W_BYTES; off += 32768) {
+      const int n = (Cfg::W_BYTES - off) < 32768 ? (Cfg::W_BYTES - off) : 32768;
+      bulk_g2s(smem_u32(s_w + off), wpack + off, n, smem_u32(&s_bar[0]));
+    }
+  }
+
+  uint8_t* my_feat = s_slots + slot * Cfg::SLOT_BYTES;
+  uint8_t* my_aux = my_feat + Cfg::SLOT_FEAT;
+  const uint32_t sa_feat = smem_u32(my_feat), sa_aux = smem_u32(my_aux);
+  const uint32_t sw = smem_u32(s_w);
+  const uint32_t bar = smem_u32(&s_bar[1 + slot]);
+  const uint32_t d_base = tmem_base + slot * Cfg::TMEM_PER_SLOT;
+  const uint32_t lane_off = ((uint32_t)(wslot * 32)) << 16;
+  const uint32_t d1 = d_base, d2 = d_base + Cfg::C1, d3 = d_base;
+  uint32_t phase = 0;
+  const int tiles_per_cloud = n_centroids >> 1;
+
+  mbar_wait(smem_u32(&s_bar[0]), 0);                     // weights resident
+
+  for (int64_t t = (int64_t)blockIdx.x * Cfg::SLOTS + slot; t < n_tiles; t += (int64_t)gridDim.x * Cfg::SLOTS) {
+    const int64_t b = t / tiles_per_cloud;
+    const int g0 = (int)(t % tiles_per_cloud) * 2;
+    const float* cloud = pts + b * n_src * ld_pts;
+    const int32_t* tidx = idx + (b * n_centroids + g0) * 64;
+
+    // ---- gather: geometry/bias block (thread = row), feature block (warp per row) ----
+    {
+      const int g = g0 + (p >> 6);
+      const int j = tidx[p];
+      const float* src = cloud + (int64_t)j * ld_pts;
+      const float* cen = cloud + (int64_t)g * ld_pts;
+      const float rx = __fsub_rn(src[0], cen[0]), ry = __fsub_rn(src[1], cen[1]), rz = __fsub_rn(src[2], cen[2]);
+      const float hx = __uint_as_float(pack_bf16(rx, 0.f) << 16), hy = __uint_as_float(pack_bf16(ry, 0.f) << 16),
+                  hz = __uint_as_float(pack_bf16(rz, 0.f) << 16);
+      uint4 w;
+      w.x = pack_bf16(hx, hy);
+      w.y = pack_bf16(hz, 1.f);
+      w.z = pack_bf16(rx - hx, ry - hy);
+      w.w = pack_bf16(rz - hz, 1.f);
+      *reinterpret_cast<uint4*>(my_aux + aux_off(p, 0)) = w;
+      *reinterpret_cast<uint4*>(my_aux + aux_off(p, 8)) = make_uint4(0, 0, 0, 0);
+    }
+    if (Cfg::CF > 0) {
+      // 128 feature floats per row at column 4 of the source row: one warp per row,
+      // lane l loads float4 #l (coalesced 512 B), stores 4 bf16 into the SW128 tile.
+      const int w4 = warp & 3;
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r) {
+        const int row = w4 * 32 + r;
+        const int j = tidx[row];
+        const float4 f = __ldg(reinterpret_cast<const float4*>(cloud + (int64_t)j * ld_pts + 4) + lane);
+        uint2 w;
+        w.x = pack_bf16(f.x, f.y);
+        w.y = pack_bf16(f.z, f.w);
+        const int col = lane * 4;
+        *reinterpret_cast<uint2*>(my_feat + (col >> 6) * (128 * 128) + sw128_off(row, col & 63)) = w;
+      }
+    }
+    fence_async_smem();
+    fence_before_sync();                                 // previous tile's TMEM reads are complete
+    named_bar_sync(1 + slot, 128);
+
+    // ---- layer 1: D1[p, c1] = X[p, :] . W1[c1, :] ----
+    if (p == 0) {
+      fence_after_sync();
+      issue_layer<Cfg::KB1>(sa_feat, 128 * 128, sa_aux, sw, Cfg::C1 * 128, sw + Cfg::OFF_W1A, d1,
+                            idesc_bf16(128, Cfg::C1));
+      commit(bar);
+    }
+    mbar_wait(bar, phase); phase ^= 1;
+    fence_after_sync();
+    epilogue_repack<Cfg::C1>(d1 + lane_off, my_feat, p);
+    fence_async_smem();
+    fence_before_sync();
+    named_bar_sync(1 + slot, 128);
+
+    // ---- layer 2: D2[p, c2] = H1[p, :] . W2[c2, :] ----
+    if (p == 0) {
+      fence_after_sync();
+      issue_layer<Cfg::KB2>(sa_feat, 128 * 128, sa_aux, sw + Cfg::OFF_W2, Cfg::C2 * 128, sw + Cfg::OFF_W2A, d2,
+                            idesc_bf16(128, Cfg::C2));
+      commit(bar);
+    }
+    mbar_wait(bar, phase); phase ^= 1;
+    fence_after_sync();
+    epilogue_repack<Cfg::C2>(d2 + lane_off, my_feat, p);
+    fence_async_smem();
+    fence_before_sync();
+    named_bar_sync(1 + slot, 128);
+
+    // ---- layer 3 (transposed): D3[c3, p] = W3[c3, :] . H2[p, :] ; max over each 64-point group ----
+    if (p == 0) {
+      fence_after_sync();
+#pragma unroll
+      for (int h = 0; h < Cfg::C3 / 128; ++h)
+        issue_layer<Cfg::KB3>(sw + Cfg::OFF_W3 + h * (128 * 128), Cfg::C3 * 128, sw + Cfg::OFF_W3A + h * (128 * 32),
+                              sa_feat, 128 * 128, sa_aux, d3 + h * 128, idesc_bf16(128, 128));
+      commit(bar);
+    }
+    mbar_wait(bar, phase); phase ^= 1;
+    fence_after_sync();
+#pragma unroll
+    for (int h = 0; h < Cfg::C3 / 128; ++h) {
+      float m[2] = {0.f, 0.f};                           // ReLU floor
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(d3 + lane_off + h * 128 + c0, v);
+        tmem_ld_wait();
+        float mm = m[c0 >> 6];
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) mm = max3(mm, __uint_as_float(v[q]), __uint_as_float(v[q + 1]));
+        m[c0 >> 6] = mm;
+      }
+      const int ch = h * 128 + p;
+      float* o = out + (b * n_centroids + g0) * ld_out + out_col0 + ch;
+      o[0] = m[0];
+      o[ld_out] = m[1];
+    }
+    if (p < 8) {                                         // centroid xyz + zero pad in the leading columns
+      const int g = g0 + (p >> 2), c = p & 3;
+      if (c < out_col0)
+        out[(b * n_centroids + g) * ld_out + c] = (c < 3) ? cloud[(int64_t)g * ld_pts + c] : 0.f;
+    }
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+// ---- host-side weight packer -------------------------------------------------------------------
+static inline uint16_t f2bf(float f) {                   // round-to-nearest-even
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+template <class Cfg>
+static void pack_weights(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                         const float* b3, int c_in, uint8_t* out) {
+  memset(out, 0, Cfg::W_BYTES);
+  auto put = [&](int off, uint32_t byte, float v) {
+    const uint16_t h = f2bf(v);
+    memcpy(out + off + byte, &h, 2);
+  };
+  auto aux_bias = [&](int off, int r, float b) {
+    const uint16_t hi = f2bf(b);
+    put(off, aux_off(r, 3), b);
+    put(off, aux_off(r, 7), b - bf2f(hi));
+  };
+  // layer 1: xyz columns 0..2 -> aux (hi and lo copies), features (source columns 3..) -> SW128 blocks
+  const int xyz_cols = 3, feat0 = c_in - Cfg::CF;        // feature k <-> W1 column feat0 + k
+  for (int r = 0; r < Cfg::C1; ++r) {
+    for (int c = 0; c < xyz_cols; ++c) {
+      put(Cfg::OFF_W1A, aux_off(r, c), W1[r * c_in + c]);
+      put(Cfg::OFF_W1A, aux_off(r, 4 + c), W1[r * c_in + c]);
+    }
+    aux_bias(Cfg::OFF_W1A, r, b1[r]);
+    for (int k = 0; k < Cfg::CF; ++k) put((k >> 6) * Cfg::C1 * 128, sw128_off(r, k & 63), W1[r * c_in + feat0 + k]);
+  }
+  for (int r = 0; r < Cfg::C2; ++r) {
+    aux_bias(Cfg::OFF_W2A, r, b2[r]);
+    for (int k = 0; k < Cfg::C1; ++k) put(Cfg::OFF_W2 + (k >> 6) * Cfg::C2 * 128, sw128_off(r, k & 63), W2[r * Cfg::C1 + k]);
+  }
+  for (int r = 0; r < Cfg::C3; ++r) {
+    aux_bias(Cfg::OFF_W3A, r, b3[r]);
+    for (int k = 0; k < Cfg::C2; ++k) put(Cfg::OFF_W3 + (k >> 6) * Cfg::C3 * 128, sw128_off(r, k & 63), W3[r * Cfg::C2 + k]);
+  }
+}
+
+template <class Cfg>
+static int launch_sa(const float* pts, int64_t n_clouds, int n_src, int64_t ld_pts, const int32_t* idx,
+                     int n_centroids, const void* wpack, float* out, int64_t ld_out, int out_col0,
+                     cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(sa_mlp_max_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("pdf_sa_mlp_max_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return PDF_ERR_CUDA;
+    }
+    configured = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t n_tiles = n_clouds * (n_centroids / 2);
+  int64_t grid = (n_tiles + Cfg::SLOTS - 1) / Cfg::SLOTS;
+  if (grid > sms) grid = sms;
+  sa_mlp_max_kernel<Cfg><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(
+      pts, n_src, ld_pts, idx, n_centroids, reinterpret_cast<const uint8_t*>(wpack), out, ld_out, out_col0, n_tiles);
+  return check_launch("pdf_sa_mlp_max_bf16");
+}
+
+}  // namespace pdf
+
+extern "C" int64_t pdf_sa_pack_size(int c_in, int c1, int c2, int c3) {
+  if (c_in == 3 && c1 == 64 && c2 == 64 && c3 == 128) return pdf::Sa1Cfg::W_BYTES;
+  if (c_in == 131 && c1 == 128 && c2 == 128 && c3 == 256) return pdf::Sa2Cfg::W_BYTES;
+  return -1;
+}
+
+extern "C" int pdf_sa_pack_weights_host(const float* W1, const float* b1, const float* W2, const float* b2,
+                                        const float* W3, const float* b3, int c_in, int c1, int c2, int c3,
+                                        void* out_host) {
+  PDF_REQUIRE(W1 && b1 && W2 && b2 && W3 && b3 && out_host, PDF_ERR_BAD_ARG, "pdf_sa_pack_weights_host: null pointer");
+  if (c_in == 3 && c1 == 64 && c2 == 64 && c3 == 128)
+    pdf::pack_weights<pdf::Sa1Cfg>(W1, b1, W2, b2, W3, b3, c_in, (uint8_t*)out_host);
+  else if (c_in == 131 && c1 == 128 && c2 == 128 && c3 == 256)
+    pdf::pack_weights<pdf::Sa2Cfg>(W1, b1, W2, b2, W3, b3, c_in, (uint8_t*)out_host);
+  else {
+    pdf::set_error("pdf_sa_pack_weights_host: unsupported channel plan (%d,%d,%d,%d)", c_in, c1, c2, c3);
+    return PDF_ERR_UNSUPPORTED;
+  }
+  return PDF_OK;
+}
+
+extern "C" int pdf_sa_mlp_max_bf16(const float* pts, int64_t n_clouds, int n_src, int64_t ld_pts, int c_in,
+                                   const int32_t* idx, int n_centroids, int k, const void* wpack, int c1, int c2,
+                                   int c3, float* out, int64_t ld_out, int out_col0, void* stream) {
+  PDF_REQUIRE(pts && idx && wpack && out, PDF_ERR_BAD_ARG, "pdf_sa_mlp_max_bf16: null pointer");
+  PDF_REQUIRE(n_clouds >= 0 && n_src > 0 && n_centroids > 0 && out_col0 >= 0 && out_col0 <= 4, PDF_ERR_BAD_ARG,
+              "pdf_sa_mlp_max_bf16: bad size");
+  PDF_REQUIRE(k == 64 && (n_centroids % 2) == 0, PDF_ERR_UNSUPPORTED,
+              "pdf_sa_mlp_max_bf16: needs k == 64 and an even number of centroids (got k=%d, n=%d)", k, n_centroids);
+  PDF_REQUIRE(ld_out >= out_col0 + c3, PDF_ERR_BAD_ARG, "pdf_sa_mlp_max_bf16: ld_out too small");
+  if (n_clouds == 0) return PDF_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c_in == 3 && c1 == 64 && c2 == 64 && c3 == 128) {
+    PDF_REQUIRE(ld_pts >= 3, PDF_ERR_BAD_ARG, "pdf_sa_mlp_max_bf16: ld_pts too small");
+    return pdf::launch_sa<pdf::Sa1Cfg>(pts, n_clouds, n_src, ld_pts, idx, n_centroids, wpack, out, ld_out, out_col0, s);
+  }
+  if (c_in == 131 && c1 == 128 && c2 == 128 && c3 == 256) {
+    PDF_REQUIRE(ld_pts >= 132 && (ld_pts % 4) == 0, PDF_ERR_UNSUPPORTED,
+                "pdf_sa_mlp_max_bf16: level-2 source rows must be [xyz,pad,128 features] with pitch %% 4 == 0");
+    return pdf::launch_sa<pdf::Sa2Cfg>(pts, n_clouds, n_src, ld_pts, idx, n_centroids, wpack, out, ld_out, out_col0, s);
+  }
+  pdf::set_error("pdf_sa_mlp_max_bf16: unsupported channel plan (%d,%d,%d,%d)", c_in, c1, c2, c3);
+  return PDF_ERR_UNSUPPORTED;
+}

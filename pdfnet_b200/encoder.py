@@ -1,0 +1,334 @@
+"""Depth branch + point/pixel fusion: host-side mirror of the reference modules.
+
+Reference: lib/models/networks/intaghand_encoder.py — ``PointNet_Plus`` :32-159,
+``SFTLayer`` :205-219, ``depth2pcl`` :369-491, the fusion tail of
+``ResNetSimple.forward`` :805-813 — and lib/models/utils.py:22-26.  Class names,
+constructor arguments, parameter names (state-dict keys) and forward signatures
+are the reference's, so a reference checkpoint loads unchanged; the bodies call
+the sm_100a kernels through the C ABI.  Inference (eval-mode BatchNorm, folded on
+the host) only in this round.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from .profiling import stage
+
+nstates_plus_1 = [64, 64, 128]
+nstates_plus_2 = [128, 128, 256]
+nstates_plus_3 = [512, 512, 1024, 1024, 512]
+
+
+def _tranpose_and_gather_feat(feat, ind):
+    """lib/models/utils.py:22-26: feat [B,C,H,W], ind [B,n] int64 -> [B,n,C] (no full-map copy)."""
+    return ops.gather_nchw(feat, ind)
+
+
+def get_points_coordinate(depth, instrinsic_inv, device="cuda"):
+    """lib/utils/utils.py:251-262: depth [B,H,W,1], inverse intrinsics [B,3,3] -> [B,3,H,W]."""
+    B, H, W, _ = depth.shape
+    return ops.backproject(depth.reshape(B, H, W).to(device), instrinsic_inv.to(device))
+
+
+class SFTLayer(nn.Module):
+    """intaghand_encoder.py:205-219.  forward((fea [B,Cf,n], cond [B,n,Cc])) -> [B,n,Cf]."""
+
+    def __init__(self, c_fea, c_cond):
+        super(SFTLayer, self).__init__()
+        self.SFT_scale_conv0 = nn.Conv2d(c_cond, c_cond, 1)
+        self.SFT_scale_conv1 = nn.Conv2d(c_cond, c_fea, 1)
+        self.SFT_shift_conv0 = nn.Conv2d(c_cond, c_cond, 1)
+        self.SFT_shift_conv1 = nn.Conv2d(c_cond, c_fea, 1)
+
+    def _w(self, conv):
+        return conv.weight.detach().view(conv.out_channels, conv.in_channels), conv.bias.detach()
+
+    def weights(self, pad_at=None):
+        """(ws0,bs0,ws1,bs1,wh0,bh0,wh1,bh1); with ``pad_at`` an all-zero output channel is
+        inserted at that index of the second convs (scale=0, shift=0 -> the padded feature
+        column passes through unchanged), matching the 16 B-aligned internal row layout."""
+        out = []
+        for c0, c1 in ((self.SFT_scale_conv0, self.SFT_scale_conv1), (self.SFT_shift_conv0, self.SFT_shift_conv1)):
+            w0, b0 = self._w(c0)
+            w1, b1 = self._w(c1)
+            if pad_at is not None:
+                w1 = torch.cat([w1[:pad_at], torch.zeros_like(w1[:1]), w1[pad_at:]], 0).contiguous()
+                b1 = torch.cat([b1[:pad_at], torch.zeros_like(b1[:1]), b1[pad_at:]], 0).contiguous()
+            out += [w0, b0, w1, b1]
+        return tuple(out)
+
+    def apply_rows(self, fea_rows, cond_rows, out=None, weights=None):
+        """fea_rows [M,Cf] (row pitch free), cond_rows [M,Cc] -> fea*(scale+1)+shift, [M,Cf].
+        ``out`` may alias ``fea_rows`` (in-place modulation)."""
+        ws0, bs0, ws1, bs1, wh0, bh0, wh1, bh1 = weights if weights is not None else self.weights()
+        hs = ops.linear(cond_rows, ws0, bs0, act=L.ACT_LEAKY01)
+        hh = ops.linear(cond_rows, wh0, bh0, act=L.ACT_LEAKY01)
+        if out is None:
+            out = torch.empty((fea_rows.shape[0], fea_rows.shape[1]), dtype=torch.float32, device=fea_rows.device)
+        ops.linear(hs, ws1, bs1, epilogue=L.EPI_SFT_SCALE, f=fea_rows, out=out)
+        ops.linear(hh, wh1, bh1, epilogue=L.EPI_ACCUM, out=out)
+        return out
+
+    def forward(self, x):
+        fea, cond = x[0], x[1]
+        B, Cf, n = fea.shape
+        fea_rows = L.f32c(fea.transpose(1, 2)).view(B * n, Cf)
+        cond_rows = L.f32c(cond).view(B * n, -1)
+        return self.apply_rows(fea_rows, cond_rows).view(B, n, Cf)
+
+    def packed_sft0(self):
+        """48 floats in the layout pdf_pyramid_gather expects (only for c_fea=c_cond=3)."""
+        parts = []
+        for conv in (self.SFT_scale_conv0, self.SFT_scale_conv1, self.SFT_shift_conv0, self.SFT_shift_conv1):
+            parts += [conv.weight.detach().reshape(-1), conv.bias.detach().reshape(-1)]
+        return torch.cat(parts).float().contiguous()
+
+
+def _fold_bn(conv, bn):
+    """conv -> BN(eval) folded into (W [out,in], b [out]) in fp64, returned fp32."""
+    w = conv.weight.detach().double().view(conv.out_channels, -1)
+    b = conv.bias.detach().double() if conv.bias is not None else torch.zeros(conv.out_channels, dtype=torch.float64,
+                                                                               device=w.device)
+    s = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    return (w * s[:, None]).float().contiguous(), ((b - bn.running_mean.detach().double()) * s +
+                                                   bn.bias.detach().double()).float().contiguous()
+
+
+def _mlp(cin, chans, pool):
+    layers = []
+    for c in chans:
+        layers += [nn.Conv2d(cin, c, kernel_size=(1, 1)), nn.BatchNorm2d(c), nn.ReLU(inplace=True)]
+        cin = c
+    layers.append(nn.MaxPool2d(pool, stride=1))
+    return nn.Sequential(*layers)
+
+
+class PointNet_Plus(nn.Module):
+    """intaghand_encoder.py:32-159.  forward(points [B,N,3], emb [l0,l1,l2], choose [B,N])
+    -> [B,1,1024].  ``precision``: 'fp32' (FFMA kernels, 1e-4 parity) or 'bf16' (the two
+    set-abstraction MLPs on tcgen05 with bf16 operands / fp32 accumulate, 2e-2 parity)."""
+
+    def __init__(self, opt, precision="fp32"):
+        super(PointNet_Plus, self).__init__()
+        self.num_outputs = opt.PCA_SZ
+        self.knn_K = opt.knn_K
+        self.ball_radius2 = opt.ball_radius2
+        self.sample_num_level1 = opt.sample_num_level1
+        self.sample_num_level2 = opt.sample_num_level2
+        self.INPUT_FEATURE_NUM = opt.INPUT_FEATURE_NUM
+        self.opt = opt
+        self.precision = precision
+        self.sft0 = SFTLayer(3, 3)
+        self.sft1 = SFTLayer(131, 64)
+        self.sft2 = SFTLayer(259, 256)
+        self.netR_1 = _mlp(self.INPUT_FEATURE_NUM, nstates_plus_1, (1, self.knn_K))
+        self.netR_2 = _mlp(3 + nstates_plus_1[2], nstates_plus_2, (1, self.knn_K))
+        self.netR_3 = _mlp(3 + nstates_plus_2[2], nstates_plus_3[:3], (self.sample_num_level2, 1))
+        self.netR_FC = nn.Sequential(                      # present for state-dict parity; unused (:156)
+            nn.Linear(nstates_plus_3[2], nstates_plus_3[3]), nn.BatchNorm1d(nstates_plus_3[3]), nn.ReLU(inplace=True),
+            nn.Linear(nstates_plus_3[3], nstates_plus_3[4]), nn.BatchNorm1d(nstates_plus_3[4]), nn.ReLU(inplace=True),
+            nn.Linear(nstates_plus_3[4], self.num_outputs))
+        self._folded = None
+        self._folded_key = None
+
+    # -- folded / packed parameters, rebuilt when any parameter or buffer changes --
+    def _params_key(self):
+        ts = list(self.parameters()) + list(self.buffers())
+        return tuple((t.data_ptr(), t._version) for t in ts) + (self.precision,)
+
+    def folded(self):
+        key = self._params_key()
+        if self._folded is None or key != self._folded_key:
+            f = {}
+            for name in ("netR_1", "netR_2", "netR_3"):
+                net = getattr(self, name)
+                f[name] = [_fold_bn(net[i], net[i + 1]) for i in (0, 3, 6)]
+            f["sft0"] = self.sft0.packed_sft0()
+            # internal rows are [x y z 0 | features]: one zero pad column at index 3 keeps the
+            # feature block 16 B aligned (pitch 132 / 260 floats)
+            f["sft1"] = self.sft1.weights(pad_at=3)
+            f["sft2"] = self.sft2.weights(pad_at=3)
+            for name in ("netR_2", "netR_3"):
+                w1, b1 = f[name][0]
+                f[name + "_w1pad"] = torch.cat([w1[:, :3], torch.zeros_like(w1[:, :1]), w1[:, 3:]], 1).contiguous()
+            if self.precision == "bf16":
+                dev = f["sft0"].device
+                for name in ("netR_1", "netR_2"):
+                    (w1, b1), (w2, b2), (w3, b3) = f[name]
+                    f[name + "_pack"] = ops.sa_pack_weights(w1, b1, w2, b2, w3, b3).to(dev)
+            self._folded, self._folded_key = f, key
+        return self._folded
+
+    def forward(self, points, emb, choose, clouds_per_frame=1):
+        if self.training:
+            raise NotImplementedError("pdfnet_b200.PointNet_Plus: inference only (call .eval()); "
+                                      "train-mode BatchNorm is not built in this round")
+        L.require_cuda(points, choose, *emb)
+        with torch.no_grad():
+            B = points.shape[0]
+            chunk = 256 if self.precision == "fp32" else 2048
+            if B <= chunk:
+                return self._forward_chunk(points, emb, choose, clouds_per_frame, 0)
+            assert chunk % clouds_per_frame == 0
+            outs = [self._forward_chunk(points[s:s + chunk], emb, choose[s:s + chunk], clouds_per_frame,
+                                        s // clouds_per_frame) for s in range(0, B, chunk)]
+            return torch.cat(outs, 0)
+
+    def _forward_chunk(self, points, emb, choose, cpf, frame0):
+        opt, f = self.opt, self.folded()
+        N1, N2, K = self.sample_num_level1, self.sample_num_level2, self.knn_K
+        B, N = points.shape[0], points.shape[1]
+        dev = points.device
+        if frame0:
+            nf = (B + cpf - 1) // cpf
+            emb = [e[frame0:frame0 + nf] for e in emb]
+        # level 0: pixel->point gather at three pyramid levels + SFT0 on xyz (:120-128), fp32
+        with stage("pyramid_gather"):
+            pts0, cond1, cond2 = ops.pyramid_gather(points, choose, emb, f["sft0"], N1, N2, opt.default_resolution,
+                                                    cpf)
+        # SA1: neighbour search + grouping + netR_1 + max over K (:123,:132)
+        with stage("knn1"):
+            idx1 = ops.knn_ball(pts0, N1, K, opt.ball_radius)
+        C1p, C2p = 4 + nstates_plus_1[2], 4 + nstates_plus_2[2]              # 132, 260
+        bf16 = self.precision == "bf16"
+        x1 = (torch.empty if bf16 else torch.zeros)((B, N1, C1p), dtype=torch.float32, device=dev)
+        if not bf16:
+            x1[:, :, 0:3] = pts0[:, :N1]                      # torch.cat((y, x), 1) (:134)
+        with stage("sa1"):
+            self._sa(pts0, idx1, "netR_1", f, x1, None)
+        # SFT1 in place, then SA2 (:137-143)
+        x1r = x1.view(B * N1, C1p)
+        with stage("sft1"):
+            self.sft1.apply_rows(x1r, cond1.view(B * N1, -1), out=x1r, weights=f["sft1"])
+        with stage("knn2"):
+            idx2 = ops.knn_ball(x1, N2, K, self.ball_radius2)
+        x2 = (torch.empty if bf16 else torch.zeros)((B, N2, C2p), dtype=torch.float32, device=dev)
+        if not bf16:
+            x2[:, :, 0:3] = x1[:, :N2, 0:3]
+        with stage("sa2"):
+            self._sa(x1, idx2, "netR_2", f, x2, f["netR_2_w1pad"])
+        # SFT2 in place, global MLP + max over the N2 points (:147-154)
+        x2r = x2.view(B * N2, C2p)
+        with stage("sft2"):
+            self.sft2.apply_rows(x2r, cond2.view(B * N2, -1), out=x2r, weights=f["sft2"])
+        (_, b1), (w2, b2), (w3, b3) = f["netR_3"]
+        with stage("global_mlp"):
+            h = ops.linear(x2r, f["netR_3_w1pad"], b1, act=L.ACT_RELU)
+            h = ops.linear(h, w2, b2, act=L.ACT_RELU)
+            out = ops.linear(h, w3, b3, act=L.ACT_RELU, epilogue=L.EPI_GROUP_MAX, group=N2)
+        return out.view(B, 1, nstates_plus_3[2])
+
+    def _sa(self, pts, idx, name, f, xout, w1pad):
+        """One set-abstraction stage: max-pooled features to xout[:, :, 4:], centroid xyz to
+        xout[:, :, 0:3] (written here by the tensor-core kernel, by the caller in fp32 mode)."""
+        B, N1, K = idx.shape
+        (w1, b1), (w2, b2), (w3, b3) = f[name]
+        if self.precision == "bf16":
+            ops.sa_mlp_max_bf16(pts, idx, f[name + "_pack"], w1.shape[1], w1.shape[0], w2.shape[0], w3.shape[0],
+                                xout, 4)
+            return
+        g, _ = ops.group_gather(pts, idx, want_center=False)              # [B,N1,K,C]
+        h = ops.linear(g.view(B * N1 * K, -1), w1 if w1pad is None else w1pad, b1, act=L.ACT_RELU)
+        h = ops.linear(h, w2, b2, act=L.ACT_RELU)
+        ops.linear(h, w3, b3, act=L.ACT_RELU, epilogue=L.EPI_GROUP_MAX, group=K,
+                   out=xout.view(B * N1, -1)[:, 4:])
+
+
+class HandFusion(nn.Module):
+    """Fusion tail of ResNetSimple.forward (intaghand_encoder.py:805-813): both hands of
+    every frame as ONE batch of 2B clouds through PointNet_Plus, the final
+    SFTLayer(1024,1024) with the centre-pixel features, and (optionally, the branch the
+    reference disables at :811) the MANO head.  Parameter names follow ResNetSimple:
+    ``pointnet_plus.*``, ``sft.*``, ``mano_head.*``."""
+
+    def __init__(self, opt, precision="fp32"):
+        super(HandFusion, self).__init__()
+        self.opt = opt
+        self.pointnet_plus = PointNet_Plus(opt, precision)
+        self.sft = SFTLayer(1024, 1024)
+        self.mano_head = nn.Sequential(
+            nn.Linear(1024, 512), nn.BatchNorm1d(512), nn.ReLU(inplace=True),
+            nn.Linear(512, 256), nn.BatchNorm1d(256), nn.ReLU(inplace=True), nn.Linear(256, 122))
+
+    def forward(self, cloud, point_wise_emb, choose, center_features, with_mano=False):
+        """cloud [B,2,N,3], choose [B,2,N], center_features [B,2,1024] ->
+        fuse_feat [B,2,1024] (and theta [B,2,122] = (point2mano_left, point2mano_right))."""
+        B, H, N, _ = cloud.shape
+        feat = self.pointnet_plus(cloud.reshape(B * H, N, 3), point_wise_emb, choose.reshape(B * H, N),
+                                  clouds_per_frame=H)                       # [2B,1,1024]
+        rows = feat.view(B * H, 1024)
+        with torch.no_grad():
+            with stage("fusion_sft"):
+                fused = self.sft.apply_rows(rows, L.f32c(center_features).view(B * H, 1024)).view(B, H, 1024)
+            if not with_mano:
+                return fused
+            with stage("mano_head"):
+                theta = self.mano_head_forward(rows).view(B, H, 122)
+            return fused, theta
+
+    def mano_head_forward(self, x):
+        """mano_head (:630-643) in eval mode: Linear+BN1d folded, ReLU, on the FFMA linear kernel."""
+        m = self.mano_head
+        w1, b1 = _fold_bn_linear(m[0], m[1])
+        w2, b2 = _fold_bn_linear(m[3], m[4])
+        h = ops.linear(x, w1, b1, act=L.ACT_RELU)
+        h = ops.linear(h, w2, b2, act=L.ACT_RELU)
+        return ops.linear(h, m[6].weight.detach(), m[6].bias.detach())
+
+
+def _fold_bn_linear(fc, bn):
+    s = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    w = (fc.weight.detach().double() * s[:, None]).float().contiguous()
+    b = ((fc.bias.detach().double() - bn.running_mean.detach().double()) * s + bn.bias.detach().double())
+    return w, b.float().contiguous()
+
+
+def depth2pcl_batched(depth, mask, K_img, valid, subset_keys=None, perm=None, generator=None, min_pixels=10):
+    """Device-side depth2pcl for a whole batch.  depth [B,H,W] or [B,1,H,W],
+    mask [B,2,H,W] at depth resolution, K_img [B,3,3], valid [B,2] -> choose int64
+    [B,2,1024] (row 0 = left), cloud fp32 [B,2,1024,3].  Randomness (the two
+    np.random.shuffle calls, intaghand_encoder.py:421,427) is injected: ``subset_keys``
+    int32 [B,2,H*W] and ``perm`` int32 [B,2,1024]; by default both are drawn from
+    ``generator`` on the device."""
+    if depth.dim() == 4:
+        depth = depth[:, 0]
+    B, H, W = depth.shape
+    dev = depth.device
+    if mask.shape[-2:] != (H, W):
+        raise RuntimeError("depth2pcl_batched: mask must already be at depth resolution")
+    Kinv = torch.linalg.inv(K_img.float())
+    if subset_keys is None:
+        subset_keys = torch.argsort(torch.rand((B, 2, H * W), device=dev, generator=generator), dim=2).int()
+    if perm is None:
+        perm = torch.argsort(torch.rand((B, 2, 1024), device=dev, generator=generator), dim=2).int()
+    choose, cloud, _ = ops.depth2pcl(depth, mask, Kinv, valid, subset_keys, perm, 1024, min_pixels)
+    return choose, cloud
+
+
+def depth2pcl(depth_256, mask, K_img, valid, subset_keys=None, perm=None):
+    """Drop-in for depth2pcl (intaghand_encoder.py:369-491): batch-1 tensors in, numpy
+    (choose int64 [2,1024], cloud float32 [2,1024,3]) out, as the reference returns them.
+    The inverse intrinsics are computed on the host with numpy in float32 exactly as the
+    reference does (utils.py:269)."""
+    import cv2  # the reference resizes the mask with cv2 (:376-377)
+    d = depth_256.detach()
+    d = d.reshape(d.shape[-2], d.shape[-1]).float()
+    H, W = d.shape
+    m = (mask.detach().float().cpu().numpy() > 0.5).astype(np.uint8)
+    mr = np.stack([cv2.resize(m[0, 0], (W, H)), cv2.resize(m[0, 1], (W, H))]).astype(np.float32)
+    Kinv = np.linalg.inv(K_img.detach().cpu().numpy().astype(np.float32).reshape(3, 3))[:3, :3]
+    dev = d.device if d.is_cuda else torch.device("cuda")
+    rs = np.random
+    if subset_keys is None:
+        subset_keys = np.stack([rs.permutation(H * W) for _ in range(2)])
+    if perm is None:
+        perm = np.stack([rs.permutation(1024) for _ in range(2)])
+    choose, cloud, _ = ops.depth2pcl(
+        d.to(dev)[None], torch.from_numpy(mr).to(dev)[None], torch.from_numpy(Kinv.astype(np.float32)).to(dev)[None],
+        valid.detach().float().reshape(1, 2).to(dev), torch.as_tensor(np.asarray(subset_keys)).to(dev)[None],
+        torch.as_tensor(np.asarray(perm)).to(dev)[None])
+    return choose[0].cpu().numpy(), cloud[0].cpu().numpy()

@@ -1,0 +1,171 @@
+"""MANO tail: ``ManoLayer`` (linear blend skinning) and ``Split_coeff``.
+
+Reference: lib/models/networks/manolayer.py:100-334 and
+lib/models/hand3d/Mano_render.py:145-194.  Same constructor and forward signature;
+the forward is one ``pdf_mano_lbs`` launch (one CTA per hand) instead of ~100
+small bmm/cat launches.
+"""
+import io
+import os
+import pickle
+
+import numpy as np
+import torch
+from torch.nn import Module
+
+from . import ops
+
+NEW_ORDER = [0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20]   # manolayer.py:110-115
+TIPS = {"left": (745, 317, 445, 556, 673), "right": (745, 317, 444, 556, 673)}          # :305-308
+
+
+class _ChumpyStub(object):
+    """Unpickle stand-in for chumpy objects (MANO_*.pkl['shapedirs'] is a
+    chumpy.reordering.Select; manolayer.py:141-144 evaluates it with ``.r``)."""
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {"_state": state})
+
+    @property
+    def r(self):
+        d = self.__dict__
+        if "x" in d and not isinstance(d["x"], _ChumpyStub):
+            return np.asarray(d["x"])
+        base = d["a"].r if isinstance(d["a"], _ChumpyStub) else np.asarray(d["a"])
+        out = np.asarray(base).ravel()[np.asarray(d["idxs"])]
+        return out.reshape(d["preferred_shape"]) if d.get("preferred_shape") is not None else out
+
+
+class _ManoUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        if module.split(".")[0] == "chumpy":
+            return type(name, (_ChumpyStub,), {})
+        return super(_ManoUnpickler, self).find_class(module, name)
+
+
+def load_mano_data(path):
+    """MANO tables as float32 numpy from the reference's .pkl or from an .npz export."""
+    if path.endswith(".npz"):
+        d = dict(np.load(path))
+        return {k: d[k] for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "weights", "hands_components",
+                                  "hands_mean", "faces") if k in d}
+    with open(path, "rb") as fh:
+        raw = _ManoUnpickler(io.BytesIO(fh.read()), encoding="latin1").load()
+    sd = raw["shapedirs"]
+    sd = np.asarray(sd) if isinstance(sd, np.ndarray) else np.asarray(sd.r)
+    J = raw["J_regressor"]
+    J = np.asarray(J.todense()) if hasattr(J, "todense") else np.asarray(J)
+    return dict(v_template=np.asarray(raw["v_template"], np.float32), shapedirs=sd.astype(np.float32),
+                posedirs=np.asarray(raw["posedirs"], np.float32), J_regressor=J.astype(np.float32),
+                weights=np.asarray(raw["weights"], np.float32),
+                hands_components=np.asarray(raw["hands_components"], np.float32),
+                hands_mean=np.asarray(raw["hands_mean"], np.float32), faces=np.asarray(raw["f"]))
+
+
+def kernel_tables(v_template, shapedirs, posedirs, J_regressor, weights, device):
+    """Re-lay the MANO constants for pdf_mano_lbs (see include/pdfnet_b200.h): basis index
+    outermost, rest-joint regressor pre-applied to template and shape basis in fp64."""
+    vt = v_template.double().reshape(778, 3)
+    sd = shapedirs.double().reshape(778, 3, 10)
+    Jr = J_regressor.double().reshape(16, 778)
+    t = dict(
+        v_template=vt.reshape(-1).float(),
+        shapedirs_t=sd.reshape(2334, 10).t().contiguous().float(),
+        posedirs_t=posedirs.float().reshape(2334, 135).t().contiguous(),
+        j_template=(Jr @ vt).reshape(-1).float(),
+        j_shapedirs=torch.einsum("jv,vck->jck", Jr, sd).reshape(48, 10).contiguous().float(),
+        weights_t=weights.float().reshape(778, 16).t().contiguous(),
+    )
+    return {k: v.contiguous().to(device) for k, v in t.items()}
+
+
+class ManoLayer(Module):
+    """manolayer.py:100-334.  Buffers keep the reference's names and shapes
+    (``shapedirs`` [778,3,10], ``posedirs`` [778,3,135], ``J_regressor`` [16,778], ...), so
+    code that edits them (e.g. ``fix_shape``, interhand.py:120-123) keeps working: the
+    kernel-layout copy is rebuilt whenever a buffer changes."""
+
+    def __init__(self, manoPath, center_idx=9, use_pca=False, new_skel=False):
+        super(ManoLayer, self).__init__()
+        self.center_idx = center_idx
+        self.use_pca = use_pca
+        self.new_skel = new_skel
+        data = manoPath if isinstance(manoPath, dict) else load_mano_data(manoPath)
+        self.new_order = list(NEW_ORDER)
+        g = lambda k: torch.as_tensor(np.asarray(data[k]), dtype=torch.float32)
+        if "hands_components" in data:
+            self.register_buffer("hands_components", g("hands_components"))
+            self.register_buffer("hands_components_inv", torch.inverse(self.hands_components))
+            self.register_buffer("hands_mean", g("hands_mean"), persistent=False)
+        self.register_buffer("J_regressor", g("J_regressor"), persistent=False)
+        self.register_buffer("weights", g("weights"), persistent=False)
+        self.register_buffer("posedirs", g("posedirs"), persistent=False)
+        self.register_buffer("v_template", g("v_template"), persistent=False)
+        self.register_buffer("shapedirs", g("shapedirs"), persistent=False)
+        self.faces = data.get("faces")
+        self.parent = [-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 0, 10, 11, 0, 13, 14]
+        self._tables = None
+        self._tables_key = None
+
+    def get_faces(self):
+        return self.faces
+
+    def train(self, mode=True):
+        self.is_train = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def pca2axis(self, pca):
+        return pca.mm(self.hands_components[:pca.shape[1]]) + self.hands_mean
+
+    def _kernel_tables(self, device):
+        bufs = (self.v_template, self.shapedirs, self.posedirs, self.J_regressor, self.weights)
+        key = tuple((b.data_ptr(), b._version) for b in bufs) + (str(device),)
+        if self._tables is None or key != self._tables_key:
+            self._tables = kernel_tables(*[b.detach().cpu() for b in bufs], device)
+            self._tables_key = key
+        return self._tables
+
+    def forward(self, root_rotation, pose, shape, trans=None, scale=None, side="left"):
+        """root_rotation [bs,3] axis-angle, pose [bs,45] axis-angle (use_pca=False, :268-272) or
+        PCA coefficients [bs,ncomps] (use_pca=True; root_rotation must then also be given as
+        axis-angle — the matrix form of :266-267 is not supported), shape [bs,10],
+        trans [bs,3] or None, scale [bs] or None -> (v [bs,778,3], j [bs,21,3])."""
+        if side not in TIPS:
+            raise ValueError("side must be 'left' or 'right'")
+        if not root_rotation.is_cuda:
+            raise RuntimeError("pdfnet_b200.ManoLayer runs on CUDA tensors only (no CPU fallback)")
+        bs = root_rotation.shape[0]
+        if self.use_pca:
+            if root_rotation.dim() != 2 or root_rotation.shape[1] != 3:
+                raise NotImplementedError("ManoLayer(use_pca=True): pass root_rotation as axis-angle [bs,3]")
+            pose = self.pca2axis(pose)
+        with torch.no_grad():
+            return ops.mano_lbs(self._kernel_tables(root_rotation.device), root_rotation.reshape(bs, 3),
+                                pose.reshape(bs, 45), shape.reshape(bs, 10), trans, scale, TIPS[side],
+                                self.center_idx, self.new_skel)
+
+
+def Split_coeff(theta, index, K, input_res=384, down_ratio=4):
+    """ManoRender.Split_coeff, non-PCA branch (Mano_render.py:160-194): theta [B,122],
+    index [B], K [B,3,3] -> (orient_l, pose_l, betas_l, trans_l, orient_r, pose_r, betas_r,
+    trans_r).  Unlike the reference it does not modify ``theta`` in place (:165,:171)."""
+    left = ops.split_coeff(theta, 0, index, K, input_res, down_ratio)
+    right = ops.split_coeff(theta, 61, index, K, input_res, down_ratio)
+    return left + right
+
+
+def mano_tail(theta_left, theta_right, ind_left, ind_right, K, layer_left, layer_right, input_res=384,
+              down_ratio=4):
+    """MANO tail as CtdetLoss.origforward runs it (lib/trains/simplified.py:722-736): each hand has
+    its own 122-vector (point2mano_left / point2mano_right, [B,122]); the left slice of the left
+    vector and the right slice of the right vector are split with that hand's centre index, and the
+    MANO layers are called WITHOUT translation (:733-734).  Returns verts [B,2,778,3],
+    joints [B,2,21,3] and the metric translations (trans_l, trans_r) [B,3]."""
+    ol, pl, bl, tl = ops.split_coeff(theta_left, 0, ind_left, K, input_res, down_ratio)
+    orr, pr, br, tr = ops.split_coeff(theta_right, 61, ind_right, K, input_res, down_ratio)
+    v_l, j_l = layer_left(ol, pl, bl, side="left")
+    v_r, j_r = layer_right(orr, pr, br, side="right")
+    return torch.stack((v_l, v_r), 1), torch.stack((j_l, j_r), 1), tl, tr

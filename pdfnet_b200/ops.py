@@ -1,0 +1,207 @@
+"""Tensor-level wrappers over the C-ABI kernels (one function per entry point).
+
+Everything here takes and returns CUDA tensors, allocates outputs with torch
+(the library never allocates), and enqueues on torch's current stream.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+
+def _strides_point_major(t):
+    """(cloud, point, channel) element strides of a [B,N,C] tensor."""
+    return t.stride(0), t.stride(1), t.stride(2)
+
+
+def knn_ball(xyz, n_centroids, k, r2, channel_major=False):
+    """Neighbour indices int32 [B,n_centroids,k] (see pdf_knn_ball).
+    xyz: fp32 [B,N,C>=3] or, with channel_major=True, [B,C>=3,N]; any strides."""
+    L.require_cuda(xyz)
+    if xyz.dtype != torch.float32:
+        xyz = xyz.float()
+    if channel_major:
+        B, _, N = xyz.shape
+        sc, sch, sp = xyz.stride(0), xyz.stride(1), xyz.stride(2)
+    else:
+        B, N, _ = xyz.shape
+        sc, sp, sch = _strides_point_major(xyz)
+    out = torch.empty((B, n_centroids, k), dtype=torch.int32, device=xyz.device)
+    L.call("pdf_knn_ball", L.ptr(xyz), B, N, n_centroids, k, float(r2), sc, sp, sch, L.ptr(out), L.stream())
+    return out
+
+
+def fps(xyz, n_sample, start_idx):
+    """FPS selection order int32 [B,n_sample]; xyz fp32 [B,N,C>=3], start_idx int [B]."""
+    L.require_cuda(xyz, start_idx)
+    if xyz.dtype != torch.float32:
+        xyz = xyz.float()
+    B, N, _ = xyz.shape
+    start = start_idx.to(torch.int32).contiguous()
+    out = torch.empty((B, n_sample), dtype=torch.int32, device=xyz.device)
+    sc, sp, sch = _strides_point_major(xyz)
+    L.call("pdf_fps", L.ptr(xyz), B, N, n_sample, L.ptr(start), sc, sp, sch, L.ptr(out), L.stream())
+    return out
+
+
+def gather_nchw(feat, ind, clouds_per_frame=1):
+    """out[b,i,:] = feat[b // clouds_per_frame, :, ind[b,i]] ; feat [F,C,H,W] fp32, ind [B,n] int64."""
+    L.require_cuda(feat, ind)
+    feat = L.f32c(feat)
+    ind = ind.long()
+    if ind.stride(-1) != 1:
+        ind = ind.contiguous()
+    Fr, C = feat.shape[0], feat.shape[1]
+    HW = feat[0, 0].numel()
+    B, n = ind.shape
+    out = torch.empty((B, n, C), dtype=torch.float32, device=feat.device)
+    L.call("pdf_gather_nchw", L.ptr(feat), B, clouds_per_frame, C, HW, L.ptr(ind), n, ind.stride(0), L.ptr(out),
+           L.stream())
+    return out
+
+
+def pyramid_gather(xyz, choose, emb, sft0_params, n1, n2, R, clouds_per_frame=1):
+    """Fused 3-level gather + SFT0 (see pdf_pyramid_gather).
+    Returns pts0 [B,N,3], cond1 [B,n1,C1], cond2 [B,n2,C2] (fp32)."""
+    L.require_cuda(xyz, choose, emb[0], emb[1], emb[2], sft0_params)
+    xyz = L.f32c(xyz)
+    choose = choose.long().contiguous()
+    l0, l1, l2 = (L.f32c(e) for e in emb)
+    B, N, _ = xyz.shape
+    C1, C2 = l1.shape[1], l2.shape[1]
+    dev = xyz.device
+    pts0 = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+    cond1 = torch.empty((B, n1, C1), dtype=torch.float32, device=dev)
+    cond2 = torch.empty((B, n2, C2), dtype=torch.float32, device=dev)
+    L.call("pdf_pyramid_gather", L.ptr(xyz), L.ptr(choose), B, clouds_per_frame, N, n1, n2, R, L.ptr(l0), L.ptr(l1),
+           C1, L.ptr(l2), C2, L.ptr(sft0_params), L.ptr(pts0), L.ptr(cond1), L.ptr(cond2), L.stream())
+    return pts0, cond1, cond2
+
+
+def group_gather(pts, idx, channel_major=False, out=None, want_center=True):
+    """Grouped rows [B,N1,k,C] with centroid-relative xyz, and centres [B,N1,3]."""
+    L.require_cuda(pts, idx)
+    if pts.dtype != torch.float32:
+        pts = pts.float()
+    if channel_major:
+        B, C, _ = pts.shape
+        sc, sch, sp = pts.stride(0), pts.stride(1), pts.stride(2)
+    else:
+        B, _, C = pts.shape
+        sc, sp, sch = _strides_point_major(pts)
+    idx = idx.to(torch.int32).contiguous()
+    _, N1, k = idx.shape
+    if out is None:
+        out = torch.empty((B, N1, k, C), dtype=torch.float32, device=pts.device)
+    center = torch.empty((B, N1, 3), dtype=torch.float32, device=pts.device) if want_center else None
+    L.call("pdf_group_gather", L.ptr(pts), B, N1, k, C, sc, sp, sch, L.ptr(idx), L.ptr(out), out.stride(2),
+           L.ptr(center), L.stream())
+    return out, center
+
+
+def linear(x, w, bias=None, act=L.ACT_NONE, epilogue=L.EPI_STORE, group=0, f=None, out=None):
+    """Y = epilogue(x @ w.T + bias); x [M,K] (row pitch free), w [N,K]; see pdf_linear_f32."""
+    L.require_cuda(x, w, bias, f, out)
+    assert x.dim() == 2 and w.dim() == 2 and x.stride(1) == 1 and w.stride(1) == 1
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        if epilogue == L.EPI_GROUP_MAX:
+            out = torch.zeros((M // group, N), dtype=torch.float32, device=x.device)
+        else:
+            out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    assert out.stride(1) == 1
+    ldf = f.stride(0) if f is not None else 0
+    L.call("pdf_linear_f32", L.ptr(x), x.stride(0), L.ptr(w), w.stride(0), L.ptr(bias), M, N, K, act, epilogue, group,
+           L.ptr(f), ldf, L.ptr(out), out.stride(0), L.stream())
+    return out
+
+
+def sa_pack_weights(w1, b1, w2, b2, w3, b3):
+    """Host-side packing of folded fp32 weights into the tcgen05 kernel's bf16 image."""
+    c_in, c1, c2, c3 = w1.shape[1], w1.shape[0], w2.shape[0], w3.shape[0]
+    lib = L.load()
+    size = int(lib.pdf_sa_pack_size(c_in, c1, c2, c3))
+    if size <= 0:
+        raise RuntimeError("pdf_sa_pack_size: unsupported channel plan %s" % ((c_in, c1, c2, c3),))
+    buf = torch.empty((size,), dtype=torch.uint8)
+    host = [t.detach().cpu().float().contiguous() for t in (w1, b1, w2, b2, w3, b3)]
+    args = [ctypes.c_void_p(t.data_ptr()) for t in host]
+    L.call("pdf_sa_pack_weights_host", *args, c_in, c1, c2, c3, ctypes.c_void_p(buf.data_ptr()))
+    return buf
+
+
+def sa_mlp_max_bf16(pts, idx, wpack, c_in, c1, c2, c3, out, out_col0=0):
+    """Fused gather + 3-layer point-MLP + max over k on tcgen05 (see pdf_sa_mlp_max_bf16).
+    pts fp32 [B,n_src,ld] contiguous, idx int32 [B,N1,k]; writes out[:, :, out_col0:out_col0+c3]."""
+    L.require_cuda(pts, idx, wpack, out)
+    assert pts.dtype == torch.float32 and pts.is_contiguous() and idx.dtype == torch.int32 and idx.is_contiguous()
+    assert out.dtype == torch.float32 and out.stride(2) == 1
+    B, n_src, ld = pts.shape
+    _, N1, k = idx.shape
+    L.call("pdf_sa_mlp_max_bf16", L.ptr(pts), B, n_src, ld, c_in, L.ptr(idx), N1, k, L.ptr(wpack), c1, c2, c3,
+           L.ptr(out), out.stride(1), out_col0, L.stream())
+    return out
+
+
+def backproject(depth, Kinv):
+    """xyz [B,3,H,W] = (Kinv @ [u,v,1]) * depth ; depth [B,H,W] fp32, Kinv [B,3,3] fp32."""
+    L.require_cuda(depth, Kinv)
+    depth, Kinv = L.f32c(depth), L.f32c(Kinv)
+    B, H, W = depth.shape
+    xyz = torch.empty((B, 3, H, W), dtype=torch.float32, device=depth.device)
+    L.call("pdf_backproject", L.ptr(depth), L.ptr(Kinv), B, H, W, L.ptr(xyz), L.stream())
+    return xyz
+
+
+def depth2pcl(depth, mask, Kinv, valid, subset_keys=None, perm=None, n_points=1024, min_pixels=10):
+    """Batched device-side cloud builder (see pdf_depth2pcl).
+    Returns choose int64 [B,2,n], cloud fp32 [B,2,n,3], n_cand int32 [B,2]."""
+    L.require_cuda(depth, mask, Kinv, valid, subset_keys, perm)
+    depth, mask, Kinv, valid = L.f32c(depth), L.f32c(mask), L.f32c(Kinv), L.f32c(valid)
+    B, H, W = depth.shape
+    dev = depth.device
+    if subset_keys is not None:
+        subset_keys = subset_keys.to(torch.int32).contiguous()
+    if perm is not None:
+        perm = perm.to(torch.int32).contiguous()
+    choose = torch.empty((B, 2, n_points), dtype=torch.int64, device=dev)
+    cloud = torch.empty((B, 2, n_points, 3), dtype=torch.float32, device=dev)
+    n_cand = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    L.call("pdf_depth2pcl", L.ptr(depth), L.ptr(mask), L.ptr(Kinv), L.ptr(valid), L.ptr(subset_keys), L.ptr(perm), B,
+           H, W, n_points, min_pixels, L.ptr(choose), L.ptr(cloud), L.ptr(n_cand), L.stream())
+    return choose, cloud, n_cand
+
+
+def mano_lbs(tables, root, pose, shape, trans, scale, tips, center_idx, new_skel):
+    """tables: dict of device tensors in the kernel layout (see manolayer.ManoTables)."""
+    L.require_cuda(root, pose, shape, trans, scale)
+    root, pose, shape = L.f32c(root), L.f32c(pose), L.f32c(shape)
+    trans = L.f32c(trans) if trans is not None else None
+    scale = L.f32c(scale) if scale is not None else None
+    n = root.shape[0]
+    v = torch.empty((n, 778, 3), dtype=torch.float32, device=root.device)
+    j = torch.empty((n, 21, 3), dtype=torch.float32, device=root.device)
+    tip_arr = (ctypes.c_int32 * 5)(*[int(t) for t in tips])
+    L.call("pdf_mano_lbs", L.ptr(tables["v_template"]), L.ptr(tables["shapedirs_t"]), L.ptr(tables["posedirs_t"]),
+           L.ptr(tables["j_template"]), L.ptr(tables["j_shapedirs"]), L.ptr(tables["weights_t"]), L.ptr(root),
+           L.ptr(pose), L.ptr(shape), L.ptr(trans), L.ptr(scale), n, ctypes.cast(tip_arr, ctypes.c_void_p),
+           -1 if center_idx is None else int(center_idx), 1 if new_skel else 0, L.ptr(v), L.ptr(j), L.stream())
+    return v, j
+
+
+def split_coeff(theta, col0, index, K, input_res, down_ratio):
+    """One hand's slice of Split_coeff; returns root [n,3], pose [n,45], shape [n,10], trans [n,3]."""
+    L.require_cuda(theta, index, K)
+    theta, K = L.f32c(theta), L.f32c(K)
+    index = index.long().contiguous()
+    n = theta.shape[0]
+    dev = theta.device
+    root = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    pose = torch.empty((n, 45), dtype=torch.float32, device=dev)
+    shape = torch.empty((n, 10), dtype=torch.float32, device=dev)
+    trans = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    L.call("pdf_split_coeff", L.ptr(theta), theta.stride(0), col0, L.ptr(index), L.ptr(K), n, input_res, down_ratio,
+           L.ptr(root), L.ptr(pose), L.ptr(shape), L.ptr(trans), L.stream())
+    return root, pose, shape, trans

@@ -1,0 +1,424 @@
+"""Parity of the CUDA path (through the C ABI) against the reference goldens and the CPU oracle.
+
+Integer / index work is bit-exact; floating point within the tolerances of the north star:
+fused features 1e-4 (fp32) / 2e-2 (bf16) relative, MANO vertices 1e-5 m, back-projection 1e-6.
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, mano_tables
+from oracle import pdf_oracle as O
+from pdfnet_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _opt(**kw):
+    d = dict(SAMPLE_NUM=1024, INPUT_FEATURE_NUM=3, knn_K=64, sample_num_level1=512, sample_num_level2=128,
+             ball_radius=0.015, ball_radius2=0.04, default_resolution=384, PCA_SZ=63)
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+def _index_parity(idx, ref_idx, xyz, n_centroids, K):
+    ref_sorted = np.sort(ref_idx.astype(np.int64), axis=-1)
+    ours = np.sort(idx.astype(np.int64), axis=-1)
+    exact = (ours == ref_sorted).all(-1)
+    if exact.all():
+        return
+    d2 = np.sort(O.sqdist(xyz, n_centroids), axis=2)
+    tie = d2[:, :, K - 1] == d2[:, :, K]
+    assert (exact | tie).all(), "index mismatch in a group without a K-th distance tie"
+    assert (O.canonicalize_indices(ours, xyz) == O.canonicalize_indices(ref_sorted, xyz)).all()
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+# ----------------------------------------------------------------------------- neighbour search
+
+def test_knn_level1_vs_reference_golden():
+    from pdfnet_b200 import ops
+    g = load_golden("knn_level1")
+    pts = torch.from_numpy(g["points"]).to(DEV)
+    for tag, r2 in (("r015", 0.015), ("r010", 0.01)):
+        idx = ops.knn_ball(pts, 512, 64, r2).cpu().numpy()
+        _index_parity(idx, g["idx_" + tag], g["points"], 512, 64)
+        # deterministic tie rule == the oracle's, bit for bit, in the oracle's canonical order
+        assert (np.sort(idx, -1) == O.knn_ball_indices(g["points"], 512, 64, r2)).all()
+    idx = ops.knn_ball(pts[:2], 512, 64, 0.015).cpu().numpy()
+    assert (np.sort(idx, -1) == np.sort(g["idx_r015"][:2].astype(np.int64), -1)).all()
+
+
+def test_knn_level2_channel_major_vs_golden():
+    from pdfnet_b200 import ops
+    g = load_golden("knn_level2")
+    p = torch.from_numpy(g["points"]).to(DEV)
+    idx = ops.knn_ball(p, 128, 64, 0.04, channel_major=True).cpu().numpy()
+    xyz = np.ascontiguousarray(g["points"][:, 0:3].transpose(0, 2, 1))
+    _index_parity(idx, g["idx"], xyz, 128, 64)
+
+
+@pytest.mark.parametrize("n,n1,k,r2", [(1024, 512, 64, 0.01), (512, 128, 64, 0.04), (256, 64, 32, 0.02),
+                                        (1000, 500, 64, 0.015), (96, 96, 96, 0.5)])
+def test_knn_vs_oracle_shapes(n, n1, k, r2):
+    from pdfnet_b200 import ops
+    pts = synth.clouds(5, n_points=n, seed=n + k, sigma=0.07)
+    idx = ops.knn_ball(pts.to(DEV), n1, k, r2).cpu().numpy()
+    assert (np.sort(idx, -1) == O.knn_ball_indices(pts.numpy(), n1, k, r2)).all()
+
+
+def test_knn_full_size_properties():
+    """cfg2/cfg3 sizes: 256 clouds; size-independent properties + oracle on a sample."""
+    from pdfnet_b200 import ops
+    B = 256
+    pts = synth.clouds(B, seed=5, sigma=0.06)
+    d = pts.to(DEV)
+    idx = ops.knn_ball(d, 512, 64, 0.01)
+    assert idx.shape == (B, 512, 64) and idx.dtype == torch.int32
+    assert int(idx.min()) >= 0 and int(idx.max()) < 1024
+    # every neighbour is within the radius or is the centroid itself
+    g = torch.gather(d, 1, idx.view(B, -1, 1).long().expand(-1, -1, 3)).view(B, 512, 64, 3)
+    diff = g - d[:, :512, None, :]
+    d2 = (diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1]) + diff[..., 2] * diff[..., 2]
+    own = torch.arange(512, device=DEV).view(1, 512, 1)
+    assert bool(((d2 <= 0.01) | (idx == own)).all())
+    # the centroid is always its own nearest neighbour
+    assert bool((idx == own).any(-1).all())
+    # idempotent / deterministic
+    assert torch.equal(idx, ops.knn_ball(d, 512, 64, 0.01))
+    sel = [0, 100, 255]
+    assert (np.sort(idx[sel].cpu().numpy(), -1) == O.knn_ball_indices(pts[sel].numpy(), 512, 64, 0.01)).all()
+
+
+def test_group_points_dropin():
+    from pdfnet_b200 import group_points, group_points_2
+    g = load_golden("knn_level1")
+    x, y = group_points(torch.from_numpy(g["points"]).to(DEV), _opt())
+    assert x.shape == (4, 3, 512, 64) and y.shape == (4, 3, 512, 1)
+    assert (y.cpu().numpy() == g["center_r015"]).all()
+
+    def canon(a):
+        r = np.ascontiguousarray(a.transpose(0, 2, 3, 1))
+        k = np.lexsort((r[..., 2], r[..., 1], r[..., 0]), axis=-1)
+        return np.take_along_axis(r, k[..., None], axis=2)
+    assert (canon(x.cpu().numpy()) == canon(g["xyz_r015"])).all()
+
+    g2 = load_golden("knn_level2")
+    x2, y2 = group_points_2(torch.from_numpy(g2["points"]).to(DEV), 512, 128, 64, 0.04)
+    assert (y2.cpu().numpy() == g2["center"]).all()
+    x2 = x2.cpu().numpy()
+    ch = g2["points"].shape[1] - 1
+    C = g2["points"].shape[1]
+    a = np.take_along_axis(x2[:1], np.argsort(x2[:1, ch], -1)[:, None].repeat(C, 1), axis=3)
+    b = np.take_along_axis(g2["grouped"][:1], np.argsort(g2["grouped"][:1, ch], -1)[:, None].repeat(C, 1), axis=3)
+    assert (a == b).all()
+
+
+def test_pointnet2_aliases():
+    from pdfnet_b200 import farthest_point_sample, index_points, query_ball_point, sample_and_group
+    pts = synth.clouds(3, seed=77).to(DEV)
+    idx = query_ball_point(0.01, 64, pts, pts[:, :512])
+    assert (np.sort(idx.cpu().numpy(), -1) == O.knn_ball_indices(pts.cpu().numpy(), 512, 64, 0.01)).all()
+    new_xyz, new_points = sample_and_group(512, 0.01, 64, pts)
+    ref = index_points(pts, idx) - pts[:, :512, None, :]
+    assert torch.equal(new_points, ref) and torch.equal(new_xyz, pts[:, :512])
+    with pytest.raises(RuntimeError):
+        query_ball_point(0.01, 64, pts, pts[:, 1:513])
+    start = torch.tensor([3, 500, 1023], device=DEV)
+    order = farthest_point_sample(pts, 512, start)
+    assert (order.cpu().numpy() == O.fps_batch(pts.cpu().numpy(), 512, start.cpu().numpy())).all()
+
+
+# ----------------------------------------------------------------------------- FPS
+
+def test_fps_vs_reference_golden():
+    from pdfnet_b200 import ops
+    g = load_golden("fps")
+    for tag in "abc":
+        pc = torch.from_numpy(g["pc_" + tag]).to(DEV)[None]
+        order = ops.fps(pc, int(g["n_" + tag]), torch.tensor([int(g["start_" + tag])], device=DEV))[0].cpu().numpy()
+        assert (np.unique(order) == g["unique_" + tag]).all()
+        assert (order == O.fps_order(g["pc_" + tag], int(g["n_" + tag]), int(g["start_" + tag]))).all()
+
+
+def test_fps_batch_sizes():
+    from pdfnet_b200 import ops
+    for n, m in ((1024, 512), (512, 128), (2000, 64), (4096, 32), (100, 100)):
+        pts = synth.clouds(4, n_points=n, seed=n, sigma=0.1)
+        start = torch.tensor([0, n - 1, n // 2, 7])
+        order = ops.fps(pts.to(DEV), m, start.to(DEV)).cpu().numpy()
+        assert (order == O.fps_batch(pts.numpy(), m, start.numpy())).all(), (n, m)
+        if m < n // 4:
+            assert len(np.unique(order[0])) == m
+
+
+# ----------------------------------------------------------------------------- gathers / SFT / MLP
+
+def test_gather_vs_golden():
+    from pdfnet_b200 import _tranpose_and_gather_feat
+    g = load_golden("gather")
+    out = _tranpose_and_gather_feat(torch.from_numpy(g["feat"]).to(DEV), torch.from_numpy(g["ind"]).to(DEV))
+    assert (out.cpu().numpy() == g["out"]).all()
+
+
+def test_sft_vs_golden():
+    from pdfnet_b200 import SFTLayer
+    g = load_golden("sft")
+    for name, (cf, cc) in (("a", (131, 64)), ("b", (3, 3))):
+        m = SFTLayer(cf, cc)
+        m.load_state_dict(synth.sft_state("", cf, cc, seed=20))
+        m = m.to(DEV).eval()
+        o = m((torch.from_numpy(g["fea_" + name]).to(DEV), torch.from_numpy(g["cond_" + name]).to(DEV)))
+        np.testing.assert_allclose(o.cpu().numpy(), g["out_" + name], rtol=2e-5, atol=2e-5)
+
+
+def test_linear_kernel_modes():
+    from pdfnet_b200 import _lib as L
+    from pdfnet_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    for M, N, K in ((64, 64, 16), (130, 70, 37), (1024, 131, 259), (4096, 3, 3)):
+        x = torch.randn((M, K), generator=gen)
+        w = torch.randn((N, K), generator=gen)
+        b = torch.randn((N,), generator=gen)
+        ref = x.double() @ w.double().t() + b.double()
+        y = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), act=L.ACT_RELU).cpu().double()
+        assert rel_err(y, ref.clamp(min=0)) < 1e-5
+        y = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), act=L.ACT_LEAKY01).cpu().double()
+        assert rel_err(y, torch.where(ref > 0, ref, 0.1 * ref)) < 1e-5
+    x = torch.randn((128 * 6, 40), generator=gen)
+    w = torch.randn((70, 40), generator=gen)
+    b = torch.randn((70,), generator=gen)
+    ref = (x.double() @ w.double().t() + b.double()).clamp(min=0)
+    for group in (64, 128, 32):
+        y = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), act=L.ACT_RELU, epilogue=L.EPI_GROUP_MAX, group=group)
+        assert rel_err(y.cpu(), ref.view(-1, group, 70).max(1)[0]) < 1e-5
+
+
+def _pointnet_case():
+    g = load_golden("pointnet_plus")
+    R, B = int(g["R"]), int(g["B"])
+    pts = synth.clouds(B, seed=31)
+    pts[2] = synth.clouds(1, seed=32, wrap_from=500)[0]
+    return g, R, B, pts, synth.choose_indices(B, R, seed=31), synth.pyramid(B, R, seed=31)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_pointnet_plus_vs_reference_golden(precision, tol):
+    from pdfnet_b200 import PointNet_Plus
+    g, R, B, pts, choose, emb = _pointnet_case()
+    m = PointNet_Plus(_opt(default_resolution=R), precision=precision)
+    missing = m.load_state_dict(synth.pointnet_plus_state(seed=317), strict=False)
+    assert all(k.startswith("netR_FC") for k in missing.missing_keys) and not missing.unexpected_keys
+    m = m.to(DEV).eval()
+    out = m(pts.to(DEV), [e.to(DEV) for e in emb], choose.to(DEV))
+    assert out.shape == (B, 1, 1024)
+    err = rel_err(out.cpu().numpy(), g["out"])
+    assert err < tol, err
+
+
+def test_pyramid_gather_and_sft0_vs_golden():
+    from pdfnet_b200 import PointNet_Plus, ops
+    g, R, B, pts, choose, emb = _pointnet_case()
+    m = PointNet_Plus(_opt(default_resolution=R))
+    m.load_state_dict(synth.pointnet_plus_state(seed=317), strict=False)
+    m = m.to(DEV).eval()
+    pts0, c1, c2 = ops.pyramid_gather(pts.to(DEV), choose.to(DEV), [e.to(DEV) for e in emb], m.folded()["sft0"],
+                                      512, 128, R)
+    np.testing.assert_allclose(pts0.cpu().numpy(), g["pts0"], rtol=1e-5, atol=1e-6)
+    ch2, ch4 = O.pyramid_index(choose, R)
+    assert torch.equal(c1.cpu(), O.tranpose_and_gather_feat(emb[1], ch2[:, :512]))
+    assert torch.equal(c2.cpu(), O.tranpose_and_gather_feat(emb[2], ch4[:, :128]))
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_hand_fusion_vs_oracle(precision, tol):
+    """Both hands as one 2B-cloud batch + final SFT(1024,1024) + mano_head, vs the oracle's
+    two sequential per-hand passes (intaghand_encoder.py:805-813)."""
+    from pdfnet_b200 import HandFusion
+    R, B = 64, 4
+    opt = _opt(default_resolution=R)
+    cloud = synth.clouds(2 * B, seed=91).view(B, 2, 1024, 3)
+    choose = synth.choose_indices(2 * B, R, seed=91).view(B, 2, 1024)
+    emb = synth.pyramid(B, R, seed=91)
+    center = torch.randn((B, 2, 1024), generator=torch.Generator().manual_seed(5))
+    sd_p, sd_s, sd_m = synth.pointnet_plus_state(317), synth.fusion_sft_state(317), synth.mano_head_state(317, 0.05)
+    m = HandFusion(opt, precision=precision)
+    sd = {"pointnet_plus." + k: v for k, v in sd_p.items()}
+    sd.update({"sft." + k: v for k, v in sd_s.items()})
+    sd.update(sd_m)
+    missing = m.load_state_dict(sd, strict=False)
+    assert all("netR_FC" in k for k in missing.missing_keys) and not missing.unexpected_keys
+    m = m.to(DEV).eval()
+    fused, theta = m(cloud.to(DEV), [e.to(DEV) for e in emb], choose.to(DEV), center.to(DEV), with_mano=True)
+    ref = O.fusion_tail(sd_p, sd_s, cloud, emb, choose, center, opt)
+    assert rel_err(fused.cpu().numpy(), ref.numpy()) < tol
+    feats = torch.stack([O.pointnet_plus_forward(sd_p, cloud[:, h], emb, choose[:, h], opt)[:, 0] for h in (0, 1)], 1)
+    ref_theta = O.mano_head(feats.reshape(-1, 1024), sd_m).view(B, 2, 122)
+    assert rel_err(theta.cpu().numpy(), ref_theta.numpy()) < max(tol, 1e-4)
+
+
+def test_sa_bf16_kernel_vs_fp32_path():
+    """The tcgen05 set-abstraction kernel against the FFMA path on the same indices (both levels)."""
+    from pdfnet_b200 import PointNet_Plus, ops
+    B = 6
+    pts = synth.clouds(B, seed=12).to(DEV)
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        m = PointNet_Plus(_opt(default_resolution=64), precision=prec)
+        m.load_state_dict(synth.pointnet_plus_state(seed=317), strict=False)
+        m = m.to(DEV).eval()
+        f = m.folded()
+        idx1 = ops.knn_ball(pts, 512, 64, 0.015)
+        x1 = torch.zeros((B, 512, 132), device=DEV)
+        x1[:, :, 0:3] = pts[:, :512]
+        m._sa(pts, idx1, "netR_1", f, x1, None)
+        idx2 = ops.knn_ball(x1, 128, 64, 0.04)
+        x2 = torch.zeros((B, 128, 260), device=DEV)
+        x2[:, :, 0:3] = x1[:, :128, 0:3]
+        m._sa(x1, idx2, "netR_2", f, x2, f["netR_2_w1pad"])
+        outs[prec] = (x1.cpu().numpy(), x2.cpu().numpy())
+    assert (outs["bf16"][0][:, :, :4] == outs["fp32"][0][:, :, :4]).all()
+    e1 = rel_err(outs["bf16"][0], outs["fp32"][0])
+    assert e1 < 2e-2, e1
+    e2 = rel_err(outs["bf16"][1][:, :, 4:], outs["fp32"][1][:, :, 4:])
+    assert e2 < 3e-2, e2
+
+
+# ----------------------------------------------------------------------------- depth -> clouds
+
+def test_backproject_vs_golden():
+    from pdfnet_b200 import get_points_coordinate
+    g = load_golden("backproject")
+    Kinv = torch.from_numpy(np.linalg.inv(g["K"]))[None]
+    xyz = get_points_coordinate(torch.from_numpy(g["depth"])[None, :, :, None], Kinv, DEV)[0].cpu().numpy()
+    assert rel_err(xyz, g["xyz"]) < 1e-6
+    assert ((xyz == 0) == (g["xyz"] == 0)).all()
+
+
+def test_depth2pcl_vs_reference_golden():
+    from pdfnet_b200 import depth2pcl
+    g = load_golden("depth2pcl")
+    for tag in ("full", "wrap_tiny", "invalid", "noise", "h2o"):
+        choose, cloud = depth2pcl(torch.from_numpy(g["depth_" + tag]).to(DEV), torch.from_numpy(g["mask_" + tag]),
+                                  torch.from_numpy(g["K_" + tag]), torch.from_numpy(g["valid_" + tag]),
+                                  subset_keys=g["keys_" + tag], perm=g["perm_" + tag])
+        assert choose.dtype == np.int64 and choose.shape == (2, 1024)
+        assert (choose == g["choose_" + tag]).all(), tag
+        assert rel_err(cloud, g["cloud_" + tag]) < 1e-6, tag
+
+
+def test_depth2pcl_batched_matches_per_frame_oracle():
+    from pdfnet_b200 import ops
+    B, R = 5, 128
+    depth, mask, K, valid = synth.rgbd_frames(B, R, seed=3)
+    valid[1, 0] = 0
+    mask[2, 1, :, :] = 0
+    mask[2, 1, 40:48, 8:40] = 1                       # 256 px -> wrap
+    rs = np.random.RandomState(0)
+    keys = np.stack([[rs.permutation(R * R) for _ in range(2)] for _ in range(B)]).astype(np.int32)
+    perm = np.stack([[rs.permutation(1024) for _ in range(2)] for _ in range(B)]).astype(np.int32)
+    Kinv = torch.linalg.inv(K)
+    choose, cloud, n_cand = ops.depth2pcl(depth.to(DEV), mask.to(DEV), Kinv.to(DEV), valid.to(DEV),
+                                          torch.from_numpy(keys).to(DEV), torch.from_numpy(perm).to(DEV))
+    for b in range(B):
+        ch, cl = O.depth2pcl(depth[b].numpy(), mask[b:b + 1].numpy(), K[b].numpy(), valid[b:b + 1].numpy(),
+                             keys[b], perm[b])
+        assert (choose[b].cpu().numpy() == ch).all(), b
+        assert rel_err(cloud[b].cpu().numpy(), cl) < 1e-6
+
+
+# ----------------------------------------------------------------------------- MANO tail
+
+def test_mano_lbs_vs_reference_golden():
+    from pdfnet_b200 import ManoLayer
+    g = load_golden("mano_lbs")
+    for side in ("left", "right"):
+        T = mano_tables(side)
+        a = {k: torch.from_numpy(g["%s_%s" % (k, side)]).to(DEV) for k in ("rot", "pose", "shape", "trans", "scale")}
+        for tag, kw, ci, ns in (("plain", {}, None, False), ("full", dict(trans=a["trans"], scale=a["scale"]), 9, False),
+                                ("newskel", dict(trans=a["trans"]), None, True)):
+            layer = ManoLayer(T, center_idx=ci, use_pca=False, new_skel=ns)
+            v, j = layer(a["rot"], a["pose"], a["shape"], side=side, **kw)
+            assert np.abs(v.cpu().numpy() - g["v_%s_%s" % (tag, side)]).max() < 1e-5
+            assert np.abs(j.cpu().numpy() - g["j_%s_%s" % (tag, side)]).max() < 1e-5
+
+
+def test_mano_lbs_batch_vs_oracle_and_fix_shape():
+    from pdfnet_b200 import ManoLayer
+    T = mano_tables("left")
+    rot, pose, shape, trans = synth.mano_inputs(256, seed=5)
+    layer = ManoLayer(T, center_idx=None)
+    v, j = layer(rot.to(DEV), pose.to(DEV), shape.to(DEV), trans.to(DEV), side="left")
+    vr, jr = O.mano_lbs(T, rot, pose, shape, trans=trans, side="left")
+    assert np.abs(v.cpu().numpy() - vr.numpy()).max() < 1e-5 and np.abs(j.cpu().numpy() - jr.numpy()).max() < 1e-5
+    # fix_shape (interhand.py:120-123) edits the buffer in place; the kernel tables must follow
+    layer.shapedirs[:, 0, :] *= -1
+    T2 = dict(T)
+    T2["shapedirs"] = T["shapedirs"].copy()
+    T2["shapedirs"][:, 0, :] *= -1
+    v2, _ = layer(rot.to(DEV), pose.to(DEV), shape.to(DEV), trans.to(DEV), side="left")
+    vr2, _ = O.mano_lbs(T2, rot, pose, shape, trans=trans, side="left")
+    assert np.abs(v2.cpu().numpy() - vr2.numpy()).max() < 1e-5
+    assert np.abs(v2.cpu().numpy() - v.cpu().numpy()).max() > 1e-4
+    # zero pose and shape reproduce the template
+    z = torch.zeros((1, 3), device=DEV)
+    v0, _ = ManoLayer(T, center_idx=None)(z, torch.zeros((1, 45), device=DEV), torch.zeros((1, 10), device=DEV))
+    assert np.abs(v0.cpu().numpy()[0] - T["v_template"]).max() < 1e-6
+
+
+def test_split_coeff_and_mano_tail():
+    from pdfnet_b200 import ManoLayer, Split_coeff, mano_tail
+    g = load_golden("split_coeff")
+    outs = Split_coeff(torch.from_numpy(g["theta"]).to(DEV), torch.from_numpy(g["index"]).to(DEV),
+                       torch.from_numpy(g["K"]).to(DEV), 384, 4)
+    for i, o in enumerate(outs):
+        np.testing.assert_allclose(o.cpu().numpy(), g["out%d" % i], rtol=1e-6, atol=1e-7)
+    Tl, Tr = mano_tables("left"), mano_tables("right")
+    ll, lr = ManoLayer(Tl, center_idx=None), ManoLayer(Tr, center_idx=None)
+    theta = torch.from_numpy(g["theta"])
+    idx, K = torch.from_numpy(g["index"]), torch.from_numpy(g["K"])
+    verts, joints, tl, tr = mano_tail(theta.to(DEV), theta.flip(0).to(DEV), idx.to(DEV), idx.flip(0).to(DEV),
+                                      K.to(DEV), ll, lr)
+    so = O.split_coeff(theta, idx, K, 384, 4)
+    vl, jl = O.mano_lbs(Tl, so[0], so[1], so[2], side="left")
+    so_r = O.split_coeff(theta.flip(0), idx.flip(0), K, 384, 4)
+    vr, jr = O.mano_lbs(Tr, so_r[4], so_r[5], so_r[6], side="right")
+    assert np.abs(verts[:, 0].cpu().numpy() - vl.numpy()).max() < 1e-5
+    assert np.abs(verts[:, 1].cpu().numpy() - vr.numpy()).max() < 1e-5
+    assert np.abs(joints[:, 1].cpu().numpy() - jr.numpy()).max() < 1e-5
+    np.testing.assert_allclose(tl.cpu().numpy(), so[3].numpy(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(tr.cpu().numpy(), so_r[7].numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_mano_head_vs_golden():
+    from pdfnet_b200 import HandFusion
+    g = load_golden("mano_head")
+    m = HandFusion(_opt(default_resolution=64))
+    m.load_state_dict(synth.mano_head_state(seed=317, std=0.05), strict=False)
+    m = m.to(DEV).eval()
+    y = m.mano_head_forward(torch.from_numpy(g["x"]).to(DEV))
+    np.testing.assert_allclose(y.cpu().numpy(), g["y"], rtol=1e-4, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------- error behaviour
+
+def test_errors_are_loud():
+    from pdfnet_b200 import PointNet_Plus, ops
+    with pytest.raises(RuntimeError):
+        ops.knn_ball(torch.zeros((1, 1024, 3)), 512, 64, 0.01)                # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        ops.knn_ball(torch.zeros((1, 2048, 3), device=DEV), 512, 64, 0.01)    # unsupported size
+    with pytest.raises(RuntimeError):
+        ops.knn_ball(torch.zeros((1, 32, 3), device=DEV), 16, 64, 0.01)       # k > n
+    m = PointNet_Plus(_opt())
+    with pytest.raises(NotImplementedError):
+        m.train()(torch.zeros((1, 1024, 3), device=DEV), [None] * 3, torch.zeros((1, 1024), device=DEV))
+    assert ops.knn_ball(torch.zeros((0, 1024, 3), device=DEV), 512, 64, 0.01).shape == (0, 512, 64)

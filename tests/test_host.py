@@ -1,0 +1,172 @@
+"""CPU-only checks: the C-ABI library loads and exports what include/pdfnet_b200.h declares,
+host-side logic (BN folding, weight packing, padding, sharding), and loud failure without CUDA."""
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from pdfnet_b200 import synth
+
+
+def _opt(**kw):
+    d = dict(SAMPLE_NUM=1024, INPUT_FEATURE_NUM=3, knn_K=64, sample_num_level1=512, sample_num_level2=128,
+             ball_radius=0.015, ball_radius2=0.04, default_resolution=64, PCA_SZ=63)
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+@pytest.fixture(scope="session")
+def lib():
+    from pdfnet_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from pdfnet_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "pdfnet_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(pdf_[a-z0-9_]+)\s*\(", header)))
+    assert declared == _lib.EXPORTS, (declared, _lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pdf_version() >= 100
+    assert lib.pdf_sa_pack_size(3, 64, 64, 128) == 32768
+    assert lib.pdf_sa_pack_size(131, 128, 128, 256) == 147456
+    assert lib.pdf_sa_pack_size(3, 64, 64, 64) == -1
+
+
+def test_no_cpu_fallback(lib):
+    from pdfnet_b200 import ManoLayer, ops
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.knn_ball(torch.zeros((1, 1024, 3)), 512, 64, 0.01)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.linear(torch.zeros((4, 4)), torch.zeros((4, 4)))
+    layer = ManoLayer(synth.to_numpy(synth.synthetic_mano_tables()), center_idx=None)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        layer(torch.zeros((1, 3)), torch.zeros((1, 45)), torch.zeros((1, 10)))
+
+
+def test_bad_arguments_return_errors_not_crashes(lib):
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    assert lib.pdf_knn_ball(None, 1, 1024, 512, 64, 0.01, 0, 0, 0, None, None) == -1
+    assert b"null" in lib.pdf_last_error()
+    assert lib.pdf_linear_f32(None, 0, None, 0, None, 1, 1, 1, 0, 0, 0, None, 0, None, 0, None) == -1
+    assert lib.pdf_sa_pack_weights_host(None, None, None, None, None, None, 3, 64, 64, 128, None) == -1
+
+
+def test_state_dict_keys_match_reference_layout(lib):
+    from pdfnet_b200 import HandFusion, PointNet_Plus
+    m = PointNet_Plus(_opt())
+    keys = set(m.state_dict().keys())
+    want = set(synth.pointnet_plus_state().keys())
+    assert want <= keys
+    assert all(k.startswith("netR_FC") for k in keys - want)
+    for k, v in synth.pointnet_plus_state().items():
+        assert tuple(m.state_dict()[k].shape) == tuple(v.shape), k
+    hf = HandFusion(_opt())
+    assert set(synth.mano_head_state().keys()) <= set(hf.state_dict().keys())
+    assert {"sft." + k for k in synth.fusion_sft_state()} <= set(hf.state_dict().keys())
+
+
+def test_bn_folding_matches_torch_eval(lib):
+    from pdfnet_b200 import PointNet_Plus
+    from pdfnet_b200.encoder import _fold_bn
+    m = PointNet_Plus(_opt())
+    m.load_state_dict(synth.pointnet_plus_state(), strict=False)
+    m.eval()
+    x = torch.randn((2, 131, 5, 7))
+    w, b = _fold_bn(m.netR_2[0], m.netR_2[1])
+    with torch.no_grad():
+        ref = m.netR_2[1](m.netR_2[0](x))
+    got = torch.einsum("oc,bchw->bohw", w, x) + b[None, :, None, None]
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_padded_weights_are_equivalent(lib):
+    from pdfnet_b200 import PointNet_Plus
+    m = PointNet_Plus(_opt())
+    m.load_state_dict(synth.pointnet_plus_state(), strict=False)
+    m.eval()
+    f = m.folded()
+    w1, _ = f["netR_2"][0]
+    x = torch.randn((9, 131))
+    xp = torch.cat([x[:, :3], torch.full((9, 1), 123.0), x[:, 3:]], 1)   # pad column must be ignored
+    assert torch.allclose(xp @ f["netR_2_w1pad"].t(), x @ w1.t(), rtol=1e-6, atol=1e-5)
+    ws0, bs0, ws1, bs1, wh0, bh0, wh1, bh1 = f["sft1"]
+    assert ws1.shape == (132, 64) and float(ws1[3].abs().sum()) == 0 and float(bs1[3]) == 0 and float(bh1[3]) == 0
+
+
+def _unpack_image(img, off_feat, off_aux, rows, kfeat):
+    """Read a packed layer back with the documented byte offsets (independent re-statement)."""
+    u16 = lambda byte: int(img[byte]) | (int(img[byte + 1]) << 8)
+    def bf(byte):
+        return np.array([u16(byte) << 16], dtype=np.uint32).view(np.float32)[0]
+    feat = np.zeros((rows, kfeat), np.float32)
+    for r in range(rows):
+        for k in range(kfeat):
+            off = (r >> 3) * 1024 + (r & 7) * 128 + ((((k & 63) >> 3) ^ (r & 7)) << 4) + (k & 7) * 2
+            feat[r, k] = bf(off_feat + (k >> 6) * rows * 128 + off)
+    aux = np.zeros((rows, 16), np.float32)
+    for r in range(rows):
+        for k in range(16):
+            aux[r, k] = bf(off_aux + (r >> 3) * 256 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2)
+    return feat, aux
+
+
+def test_sa_weight_image_layout(lib):
+    """The host packer writes bf16 weights at the SW128 / interleave offsets the kernel reads."""
+    from pdfnet_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    w1, b1 = torch.randn((64, 3), generator=g), torch.randn((64,), generator=g)
+    w2, b2 = torch.randn((64, 64), generator=g), torch.randn((64,), generator=g)
+    w3, b3 = torch.randn((128, 64), generator=g), torch.randn((128,), generator=g)
+    img = ops.sa_pack_weights(w1, b1, w2, b2, w3, b3).numpy()
+    assert img.shape == (32768,)
+    bf = lambda t: t.bfloat16().float().numpy()
+    _, aux1 = _unpack_image(img, 0, 0, 64, 0)
+    assert (aux1[:, 0:3] == bf(w1)).all() and (aux1[:, 4:7] == bf(w1)).all()
+    assert np.allclose(aux1[:, 3] + aux1[:, 7], b1.numpy(), rtol=1e-4, atol=1e-6) and (aux1[:, 8:] == 0).all()
+    feat2, aux2 = _unpack_image(img, 2048, 2048 + 8192, 64, 64)
+    assert (feat2 == bf(w2)).all() and (aux2[:, :3] == 0).all() and (aux2[:, 3] == bf(b2)).all()
+    feat3, aux3 = _unpack_image(img, 2048 + 8192 + 2048, 2048 + 8192 + 2048 + 16384, 128, 64)
+    assert (feat3 == bf(w3)).all() and (aux3[:, 3] == bf(b3)).all()
+    # level 2: feature k of the gathered row multiplies W1 column 3 + k
+    w1b, b1b = torch.randn((128, 131), generator=g), torch.randn((128,), generator=g)
+    w2b, b2b = torch.randn((128, 128), generator=g), torch.randn((128,), generator=g)
+    w3b, b3b = torch.randn((256, 128), generator=g), torch.randn((256,), generator=g)
+    img = ops.sa_pack_weights(w1b, b1b, w2b, b2b, w3b, b3b).numpy()
+    feat1, aux1 = _unpack_image(img, 0, 32768, 128, 128)
+    assert (feat1 == bf(w1b[:, 3:])).all() and (aux1[:, 0:3] == bf(w1b[:, :3])).all()
+    feat3, _ = _unpack_image(img, 36864 * 2, 36864 * 2 + 65536, 256, 128)
+    assert (feat3 == bf(w3b)).all()
+
+
+def test_mano_pkl_loader_matches_npz_export(lib):
+    from pdfnet_b200.manolayer import kernel_tables, load_mano_data
+    d = load_mano_data(os.path.join(ROOT, "tests", "golden", "mano_left.npz"))
+    t = kernel_tables(*[torch.from_numpy(d[k]) for k in ("v_template", "shapedirs", "posedirs", "J_regressor",
+                                                           "weights")], "cpu")
+    assert t["posedirs_t"].shape == (135, 2334) and t["shapedirs_t"].shape == (10, 2334)
+    assert t["weights_t"].shape == (16, 778) and t["j_shapedirs"].shape == (48, 10)
+    J = torch.from_numpy(d["J_regressor"]).double() @ torch.from_numpy(d["v_template"]).double()
+    assert torch.allclose(t["j_template"].view(16, 3).double(), J, atol=1e-7)
+    ref_pkl = "/root/reference/lib/models/hand3d/mano_core/MANO_LEFT.pkl"
+    if os.path.exists(ref_pkl):                       # only in the authoring container
+        p = load_mano_data(ref_pkl)
+        for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "weights"):
+            assert (p[k] == d[k]).all(), k
+
+
+def test_shard_range_covers_everything():
+    from pdfnet_b200.parallel import shard_range
+    for n in (0, 1, 7, 128, 1024, 1025):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
