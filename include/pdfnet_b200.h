@@ -135,6 +135,39 @@ int pdf_sa_pack_weights_host(const float* W1, const float* b1, const float* W2, 
                              const float* W3, const float* b3, int c_in, int c1, int c2, int c3,
                              void* out_host);
 
+/* ---- streaming bf16 GEMM on tcgen05 over "tile images" -------------------------------------
+ * A tile image stores a matrix [rows, K] in bf16 as [row-tile of 128 rows][k-block of 64
+ * columns] blocks of 16 KB, each block in the K-major 128-byte-swizzle layout the tensor core
+ * reads from shared memory (rows / K zero-padded to multiples of 128 / 64).
+ * Replaces the dense layers behind the set-abstraction stages: SFT 1x1 convs
+ * (intaghand_encoder.py:205-219), netR_3 + MaxPool (:86-103,152-154) and the fusion
+ * SFT(1024,1024) (:809). */
+int64_t pdf_image_bytes(int64_t rows, int cols);
+/* host-side packer: fp32 W[rows, cols] (row pitch ld) -> bf16 tile image (pure host code) */
+int pdf_pack_image_host(const float* W, int64_t rows, int cols, int64_t ld, void* out_host);
+/* device: fp32 rows X[M, ld], columns [col0, col0+K) -> k-blocks [kb0, kb0+ceil(K/64)) of an image
+ * that has kb_total k-blocks per row-tile; padding rows/columns are written as zeros */
+int pdf_rows_to_image(const float* X, int64_t ld, int64_t M, int col0, int K, void* img, int kb_total, int kb0,
+                      void* stream);
+/* D[m,n] = sum_k Mop[m,k] * Nop[n,k] over KB k-blocks, 128x128 tiles, fp32 accumulate in TMEM.
+ * colmax = 0 (ROW epilogue, thread = M row): y = act(D + bias0[n]); with kb_split > 0 the
+ *   k-blocks below / from kb_split accumulate separately and y = F*(D0+bias0+1) + (D1+bias1)
+ *   (SFT modulation).  Output: fp32 rows out_f32[m, tile_col + n] (m < rows_valid) and/or a bf16
+ *   tile image (out_kb k-blocks per row-tile).  tile_desc_host: int32 [n_tiles][3] =
+ *   {first fp32 column of this N-tile in F/out_f32, valid columns (<=128), first output k-block}.
+ * colmax = 1: M operand = weights (rows = channels), N operand = activations, one N-tile = the
+ *   128 points of one cloud: out_max[n_tile, m] = relu(max_n D[m,n] + bias0[m]). */
+int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const void* n_img, int n_tiles, int n_kb, int KB,
+                  int kb_split, int colmax, const float* bias0, const float* bias1, int act, float* out_f32,
+                  int64_t ld_out, int64_t rows_valid, const float* F, int64_t ldf, void* out_img, int out_kb,
+                  const int32_t* tile_desc_host, float* out_max, int64_t ld_max, void* stream);
+/* SFT on the three xyz channels of level 1 in full fp32 (they feed the level-2 neighbour
+ * search): x[m,c] = x[m,c]*(scale_c+1)+shift_c for c < 3; cond fp32 [M,cc]; conv weights as in
+ * SFTLayer ([out,in] row-major; only rows 0..2 of the second convs are read). cc must be 64. */
+int pdf_sft_xyz_f32(const float* cond, int64_t M, int cc, const float* w0s, const float* b0s, const float* w1s,
+                    const float* b1s, const float* w0h, const float* b0h, const float* w1h, const float* b1h,
+                    float* x, int64_t ldx, void* stream);
+
 /* Depth back-projection xyz[b,:,v,u] = (Kinv[b] * [u,v,1]) * depth[b,v,u].
  * Replaces get_points_coordinate (lib/utils/utils.py:251-262).  depth fp32
  * [B,H,W], Kinv fp32 [B,3,3] (inverse intrinsics, computed by the caller as the

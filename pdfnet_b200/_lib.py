@@ -26,12 +26,18 @@ SIGNATURES = {
     "pdf_sa_mlp_max_bf16": [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _i32,
                             _vp],
     "pdf_sa_pack_weights_host": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "pdf_pack_image_host": [_vp, _i64, _i32, _i64, _vp],
+    "pdf_rows_to_image": [_vp, _i64, _i64, _i32, _i32, _vp, _i32, _i32, _vp],
+    "pdf_gemm_bf16": [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _i64, _vp, _i64,
+                      _vp, _i32, _vp, _vp, _i64, _vp],
+    "pdf_sft_xyz_f32": [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "pdf_backproject": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
     "pdf_depth2pcl": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "pdf_mano_lbs": [_vp] * 11 + [_i64, _vp, _i32, _i32, _vp, _vp, _vp],
     "pdf_split_coeff": [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
 }
-EXPORTS = sorted(list(SIGNATURES) + ["pdf_version", "pdf_last_error", "pdf_launch_count", "pdf_sa_pack_size"])
+EXPORTS = sorted(list(SIGNATURES) + ["pdf_version", "pdf_last_error", "pdf_launch_count", "pdf_sa_pack_size",
+                                     "pdf_image_bytes"])
 
 ACT_NONE, ACT_RELU, ACT_LEAKY01 = 0, 1, 2
 EPI_STORE, EPI_SFT_SCALE, EPI_ACCUM, EPI_GROUP_MAX = 0, 1, 2, 3
@@ -58,6 +64,8 @@ def load():
     lib.pdf_launch_count.restype = ctypes.c_int64
     lib.pdf_sa_pack_size.argtypes = [_i32, _i32, _i32, _i32]
     lib.pdf_sa_pack_size.restype = ctypes.c_int64
+    lib.pdf_image_bytes.argtypes = [_i64, _i32]
+    lib.pdf_image_bytes.restype = ctypes.c_int64
     _lib = lib
     return lib
 

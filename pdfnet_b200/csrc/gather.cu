@@ -164,6 +164,7 @@ static inline unsigned grid_for(int64_t total, int block, int max_blocks = 148 *
 
 extern "C" int pdf_gather_nchw(const float* feat, int64_t n_clouds, int clouds_per_frame, int C, int64_t HW,
                                const int64_t* ind, int n, int64_t ind_stride, float* out, void* stream) {
+  if (n_clouds == 0 || n == 0) return PDF_OK;
   PDF_REQUIRE(feat && ind && out, PDF_ERR_BAD_ARG, "pdf_gather_nchw: null pointer");
   PDF_REQUIRE(n_clouds >= 0 && clouds_per_frame > 0 && C > 0 && HW > 0 && n >= 0, PDF_ERR_BAD_ARG,
               "pdf_gather_nchw: bad size");
@@ -192,6 +193,7 @@ extern "C" int pdf_pyramid_gather(const float* xyz, const int64_t* choose, int64
 extern "C" int pdf_group_gather(const float* pts, int64_t n_clouds, int n_centroids, int k, int C,
                                 int64_t stride_cloud, int64_t stride_point, int64_t stride_ch, const int32_t* idx,
                                 float* out, int64_t ld_out, float* center, void* stream) {
+  if (n_clouds == 0) return PDF_OK;
   PDF_REQUIRE(pts && idx && out, PDF_ERR_BAD_ARG, "pdf_group_gather: null pointer");
   PDF_REQUIRE(n_clouds >= 0 && n_centroids > 0 && k > 0 && C >= 3 && ld_out >= C, PDF_ERR_BAD_ARG,
               "pdf_group_gather: bad size");

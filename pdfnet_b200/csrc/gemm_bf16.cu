@@ -1,0 +1,382 @@
+// Streaming bf16 GEMM on tcgen05 for the dense layers that follow the set-abstraction
+// stages: SFT 1x1 convs, the global point-MLP (netR_3) and the fusion SFT(1024,1024).
+//
+// Both operands are "tile images": a matrix [rows, K] in bf16 stored as
+// [row-tile (128 rows)][k-block (64 columns)] blocks of 16 KB, each block already in the
+// K-major / 128-byte-swizzle layout the tensor core reads from shared memory.  A block is
+// therefore ONE contiguous cp.async.bulk (TMA engine, no tensor map), and the epilogue of
+// one layer writes the operand image of the next layer directly.
+//
+// Persistent warp-specialised kernel, one CTA per SM, 192 threads:
+//   warp 0  : producer  - bulk copies of (M-operand block, N-operand block) into a 4-stage ring
+//   warp 1  : MMA issue - 4 x tcgen05.mma (128x128x16) per k-block, commit frees the stage
+//   warps 2-5: epilogue - drain one of two TMEM accumulator stages while the other fills
+// Epilogues (thread = TMEM lane):
+//   ROW   : lane = activation row.  y = act(D + bias[n]) or, with two accumulators (k-blocks
+//           below / above kb_split accumulate separately), the SFT modulation
+//           y = F*(D0 + b0 + 1) + (D1 + b1)  (intaghand_encoder.py:217-219).  Output as fp32
+//           rows and/or as the bf16 image of the next layer.
+//   COLMAX: lane = output channel (weights are the M operand), columns = the 128 points of
+//           one cloud: y[cloud, c] = relu(max_p D[c,p] + bias[c])   (netR_3 + MaxPool, :86-103).
+#include "pdf_common.cuh"
+#include "umma.cuh"
+
+namespace pdf {
+using namespace umma;
+
+constexpr int G_STAGES = 4;
+constexpr int G_BLOCK = 16384;                 // one 128 x 64 bf16 block
+constexpr int G_THREADS = 192;
+constexpr int G_SMEM = G_STAGES * 2 * G_BLOCK + 1024 + 256;
+constexpr int G_MAX_NT = 16;
+
+struct GemmParams {
+  const uint8_t* m_img; const uint8_t* n_img;
+  int m_kb, n_kb;                // k-blocks per row-tile in each image
+  int m_tiles, n_tiles, KB, kb_split;
+  const float* bias0; const float* bias1;
+  int act;
+  float* out_f32; int64_t ld_out; int64_t rows_valid;
+  const float* F; int64_t ldf;
+  uint8_t* out_img; int out_kb;
+  float* out_max; int64_t ld_max;
+  int tile_col[G_MAX_NT];        // ROW mode, per N-tile: first fp32 column (F and out_f32)
+  int tile_nvalid[G_MAX_NT];     //   valid output columns of this N-tile (others are written as 0 / skipped)
+  int tile_okb[G_MAX_NT];        //   first k-block of this N-tile in the output image
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t saddr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(saddr) : "memory");
+}
+
+template <bool COLMAX>
+__global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_STAGES * 2 * G_BLOCK);
+  // bars: [0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * G_STAGES + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool dual = P.kb_split > 0;
+  const int acc_cols = dual ? 256 : 128;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < G_STAGES; ++s) { mbar_init(smem_u32(&bars[s]), 1); mbar_init(smem_u32(&bars[G_STAGES + s]), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bars[2 * G_STAGES + a]), 1); mbar_init(smem_u32(&bars[2 * G_STAGES + 2 + a]), 4); }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(s_tmem);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  const int n_work = P.m_tiles * P.n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int mt = w / P.n_tiles, nt = w % P.n_tiles;
+        const uint8_t* mb = P.m_img + (size_t)mt * P.m_kb * G_BLOCK;
+        const uint8_t* nb = P.n_img + (size_t)nt * P.n_kb * G_BLOCK;
+        for (int kb = 0; kb < P.KB; ++kb) {
+          mbar_wait(smem_u32(&bars[G_STAGES + stage]), phase ^ 1);
+          const uint32_t full = smem_u32(&bars[stage]);
+          mbar_expect_tx(full, 2 * G_BLOCK);
+          bulk_g2s(smem_u32(smem + stage * 2 * G_BLOCK), mb + (size_t)kb * G_BLOCK, G_BLOCK, full);
+          bulk_g2s(smem_u32(smem + stage * 2 * G_BLOCK + G_BLOCK), nb + (size_t)kb * G_BLOCK, G_BLOCK, full);
+          if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+      const uint32_t idesc = idesc_bf16(128, 128);
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        mbar_wait(smem_u32(&bars[2 * G_STAGES + 2 + as]), aphase ^ 1);
+        fence_after_sync();
+        const uint32_t acc = tmem_base + as * acc_cols;
+        for (int kb = 0; kb < P.KB; ++kb) {
+          mbar_wait(smem_u32(&bars[stage]), phase);
+          fence_after_sync();
+          const uint32_t sm = smem_u32(smem + stage * 2 * G_BLOCK), sn = sm + G_BLOCK;
+          const bool second = dual && kb >= P.kb_split;
+          const uint32_t d = acc + (second ? 128 : 0);
+          const bool first_kb = second ? (kb == P.kb_split) : (kb == 0);
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16)
+            mma_bf16(d, desc_sw128(sm + k16 * 32), desc_sw128(sn + k16 * 32), idesc, !(first_kb && k16 == 0));
+          commit(smem_u32(&bars[G_STAGES + stage]));
+          if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+        }
+        commit(smem_u32(&bars[2 * G_STAGES + as]));
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    const int q4 = warp & 3;                               // TMEM lane quarter of this warp
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_off = ((uint32_t)(q4 * 32)) << 16;
+    int as = 0; uint32_t aphase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int mt = w / P.n_tiles, nt = w % P.n_tiles;
+      mbar_wait(smem_u32(&bars[2 * G_STAGES + as]), aphase);
+      fence_after_sync();
+      const uint32_t acc = tmem_base + as * acc_cols + lane_off;
+      if (COLMAX) {
+        float mx = -3.0e38f;
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(acc + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) mx = max3(mx, __uint_as_float(v[q]), __uint_as_float(v[q + 1]));
+        }
+        const int ch = mt * 128 + row;
+        P.out_max[(int64_t)nt * P.ld_max + ch] = fmaxf(mx + P.bias0[ch], 0.f);
+      } else {
+        const int64_t m = (int64_t)mt * 128 + row;
+        const bool row_ok = m < P.rows_valid;
+        const int col0 = P.tile_col[nt], nvalid = P.tile_nvalid[nt], okb = P.tile_okb[nt];
+        const float* b0 = P.bias0 + nt * 128;
+        const float* b1 = dual ? P.bias1 + nt * 128 : nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32], u[32];
+          tmem_ld32(acc + c0, v);
+          if (dual) tmem_ld32(acc + 128 + c0, u);
+          tmem_ld_wait();
+          float y[32];
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            float f[4] = {0.f, 0.f, 0.f, 0.f};
+            if (dual && row_ok && c0 + q < nvalid) {
+              const float4 t = *reinterpret_cast<const float4*>(P.F + m * P.ldf + col0 + c0 + q);
+              f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int n = c0 + q + e;
+              float r = __uint_as_float(v[q + e]) + __ldg(b0 + n);
+              if (dual) r = fmaf(f[e], r + 1.f, __uint_as_float(u[q + e]) + __ldg(b1 + n));
+              else if (P.act == PDF_ACT_RELU) r = fmaxf(r, 0.f);
+              else if (P.act == PDF_ACT_LEAKY01) r = r > 0.f ? r : 0.1f * r;
+              y[q + e] = (n < nvalid && row_ok) ? r : 0.f;
+            }
+          }
+          if (P.out_f32 != nullptr && row_ok) {
+            float* o = P.out_f32 + m * P.ld_out + col0 + c0;
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) {
+              if (c0 + q + 3 < nvalid) *reinterpret_cast<float4*>(o + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
+              else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (c0 + q + e < nvalid) o[q + e] = y[q + e];
+              }
+            }
+          }
+          if (P.out_img != nullptr) {
+            uint8_t* blk = P.out_img + ((size_t)mt * P.out_kb + okb + (c0 >> 6)) * G_BLOCK;
+#pragma unroll
+            for (int q = 0; q < 32; q += 8) {
+              uint4 wv;
+              wv.x = pack_bf16(y[q], y[q + 1]); wv.y = pack_bf16(y[q + 2], y[q + 3]);
+              wv.z = pack_bf16(y[q + 4], y[q + 5]); wv.w = pack_bf16(y[q + 6], y[q + 7]);
+              *reinterpret_cast<uint4*>(blk + sw128_off(row, (c0 + q) & 63)) = wv;
+            }
+          }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars[2 * G_STAGES + 2 + as]));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+// fp32 rows [M, ld] columns [col0, col0+K) -> bf16 image k-blocks [kb0, kb0 + ceil(K/64)) of every
+// row-tile; rows >= M and columns >= K are written as zeros.  One thread per 16-byte chunk.
+__global__ void rows_to_image_kernel(const float* __restrict__ X, int64_t ld, int64_t M, int col0, int K,
+                                     uint8_t* __restrict__ img, int kb_total, int kb0, int nkb, int64_t n_chunks) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_chunks;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(e & 7);                         // 16 B chunk inside a 64-column block row
+    const int64_t r_all = e >> 3;
+    const int kb = (int)(r_all % nkb);
+    const int64_t m = r_all / nkb;
+    const int k = kb * 64 + ch * 8;
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = (m < M && k + i < K) ? X[m * ld + col0 + k + i] : 0.f;
+    uint4 w;
+    w.x = pack_bf16(f[0], f[1]); w.y = pack_bf16(f[2], f[3]); w.z = pack_bf16(f[4], f[5]); w.w = pack_bf16(f[6], f[7]);
+    const int64_t mt = m >> 7;
+    *reinterpret_cast<uint4*>(img + ((size_t)mt * kb_total + kb0 + kb) * G_BLOCK + sw128_off((uint32_t)(m & 127), ch * 8)) = w;
+  }
+}
+
+// SFT on the three xyz channels in full fp32 (they feed the level-2 neighbour search):
+// x[m,c] = x[m,c]*(scale_c+1)+shift_c, scale/shift = conv1(lrelu(conv0(cond))) restricted to c<3.
+// Thread per row; conv0 weights (2 x [CC,CC]) broadcast from shared memory.
+template <int CC>
+__global__ void __launch_bounds__(128) sft_xyz_kernel(const float* __restrict__ cond, int64_t M,
+                                                      const float* __restrict__ w0s, const float* __restrict__ b0s,
+                                                      const float* __restrict__ w1s, const float* __restrict__ b1s,
+                                                      const float* __restrict__ w0h, const float* __restrict__ b0h,
+                                                      const float* __restrict__ w1h, const float* __restrict__ b1h,
+                                                      float* __restrict__ x, int64_t ldx) {
+  extern __shared__ float sw[];                            // [2][CC*CC] conv0, [2][CC] bias0, [2][3*CC] conv1 rows
+  float* s_w0 = sw; float* s_b0 = s_w0 + 2 * CC * CC; float* s_w1 = s_b0 + 2 * CC;
+  for (int i = threadIdx.x; i < CC * CC; i += blockDim.x) { s_w0[i] = w0s[i]; s_w0[CC * CC + i] = w0h[i]; }
+  for (int i = threadIdx.x; i < CC; i += blockDim.x) { s_b0[i] = b0s[i]; s_b0[CC + i] = b0h[i]; }
+  for (int i = threadIdx.x; i < 3 * CC; i += blockDim.x) { s_w1[i] = w1s[i]; s_w1[3 * CC + i] = w1h[i]; }
+  __syncthreads();
+  const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float c[CC];
+#pragma unroll
+  for (int i = 0; i < CC; i += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(cond + m * CC + i);
+    c[i] = t.x; c[i + 1] = t.y; c[i + 2] = t.z; c[i + 3] = t.w;
+  }
+  float out[2][3];
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+    const float* W0 = s_w0 + br * CC * CC;
+    const float* W1 = s_w1 + br * 3 * CC;
+#pragma unroll 4
+    for (int j = 0; j < CC; ++j) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < CC; i += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(W0 + j * CC + i);
+        a0 = fmaf(wv.x, c[i], a0); a1 = fmaf(wv.y, c[i + 1], a1);
+        a0 = fmaf(wv.z, c[i + 2], a0); a1 = fmaf(wv.w, c[i + 3], a1);
+      }
+      float h = (a0 + a1) + s_b0[br * CC + j];
+      h = h > 0.f ? h : 0.1f * h;
+      o0 = fmaf(W1[j], h, o0); o1 = fmaf(W1[CC + j], h, o1); o2 = fmaf(W1[2 * CC + j], h, o2);
+    }
+    const float* b1 = br == 0 ? b1s : b1h;
+    out[br][0] = o0 + b1[0]; out[br][1] = o1 + b1[1]; out[br][2] = o2 + b1[2];
+  }
+  float* xr = x + m * ldx;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) xr[k] = __fadd_rn(__fmul_rn(xr[k], __fadd_rn(out[0][k], 1.f)), out[1][k]);
+}
+
+static inline uint16_t f2bf_host(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+}  // namespace pdf
+
+extern "C" int64_t pdf_image_bytes(int64_t rows, int cols) {
+  if (rows < 0 || cols <= 0) return -1;
+  return ((rows + 127) / 128) * (int64_t)((cols + 63) / 64) * pdf::G_BLOCK;
+}
+
+extern "C" int pdf_pack_image_host(const float* W, int64_t rows, int cols, int64_t ld, void* out_host) {
+  PDF_REQUIRE(W && out_host && rows > 0 && cols > 0 && ld >= cols, PDF_ERR_BAD_ARG, "pdf_pack_image_host: bad argument");
+  const int kbt = (cols + 63) / 64;
+  uint8_t* out = (uint8_t*)out_host;
+  memset(out, 0, (size_t)pdf_image_bytes(rows, cols));
+  for (int64_t r = 0; r < rows; ++r)
+    for (int k = 0; k < cols; ++k) {
+      const uint16_t h = pdf::f2bf_host(W[r * ld + k]);
+      memcpy(out + ((size_t)(r >> 7) * kbt + (k >> 6)) * pdf::G_BLOCK + pdf::umma::sw128_off((uint32_t)(r & 127), k & 63), &h, 2);
+    }
+  return PDF_OK;
+}
+
+extern "C" int pdf_rows_to_image(const float* X, int64_t ld, int64_t M, int col0, int K, void* img, int kb_total,
+                                 int kb0, void* stream) {
+  if (M == 0) return PDF_OK;
+  PDF_REQUIRE(X && img, PDF_ERR_BAD_ARG, "pdf_rows_to_image: null pointer");
+  PDF_REQUIRE(M > 0 && K > 0 && col0 >= 0 && ld >= col0 + K && kb0 >= 0 && kb0 + (K + 63) / 64 <= kb_total,
+              PDF_ERR_BAD_ARG, "pdf_rows_to_image: bad size");
+  const int nkb = (K + 63) / 64;
+  const int64_t rows_pad = ((M + 127) / 128) * 128;
+  const int64_t chunks = rows_pad * nkb * 8;
+  int64_t grid = (chunks + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  pdf::rows_to_image_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(X, ld, M, col0, K, (uint8_t*)img,
+                                                                              kb_total, kb0, nkb, chunks);
+  return pdf::check_launch("pdf_rows_to_image");
+}
+
+extern "C" int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const void* n_img, int n_tiles, int n_kb,
+                             int KB, int kb_split, int colmax, const float* bias0, const float* bias1, int act,
+                             float* out_f32, int64_t ld_out, int64_t rows_valid, const float* F, int64_t ldf,
+                             void* out_img, int out_kb, const int32_t* tile_desc_host, float* out_max,
+                             int64_t ld_max, void* stream) {
+  using namespace pdf;
+  if (m_tiles == 0 || n_tiles == 0) return PDF_OK;
+  PDF_REQUIRE(m_img && n_img && bias0, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: null pointer");
+  PDF_REQUIRE(m_tiles > 0 && n_tiles > 0 && KB > 0 && KB <= m_kb && KB <= n_kb && kb_split >= 0 && kb_split < KB,
+              PDF_ERR_BAD_ARG, "pdf_gemm_bf16: bad size");
+  PDF_REQUIRE(act >= 0 && act <= 2, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: bad activation");
+  GemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.m_img = (const uint8_t*)m_img; P.n_img = (const uint8_t*)n_img;
+  P.m_kb = m_kb; P.n_kb = n_kb; P.m_tiles = m_tiles; P.n_tiles = n_tiles; P.KB = KB; P.kb_split = kb_split;
+  P.bias0 = bias0; P.bias1 = bias1; P.act = act;
+  P.out_f32 = out_f32; P.ld_out = ld_out; P.rows_valid = rows_valid; P.F = F; P.ldf = ldf;
+  P.out_img = (uint8_t*)out_img; P.out_kb = out_kb; P.out_max = out_max; P.ld_max = ld_max;
+  if (colmax) {
+    PDF_REQUIRE(out_max && kb_split == 0, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: COLMAX needs out_max and one accumulator");
+  } else {
+    PDF_REQUIRE(n_tiles <= G_MAX_NT && tile_desc_host, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: ROW mode needs <= %d N tiles and tile_desc", G_MAX_NT);
+    PDF_REQUIRE(out_f32 || out_img, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: no output");
+    PDF_REQUIRE(kb_split == 0 || (F && bias1), PDF_ERR_BAD_ARG, "pdf_gemm_bf16: SFT mode needs F and bias1");
+    for (int i = 0; i < n_tiles; ++i) {
+      P.tile_col[i] = tile_desc_host[3 * i]; P.tile_nvalid[i] = tile_desc_host[3 * i + 1]; P.tile_okb[i] = tile_desc_host[3 * i + 2];
+      PDF_REQUIRE(P.tile_nvalid[i] >= 0 && P.tile_nvalid[i] <= 128 && (P.tile_col[i] % 4) == 0, PDF_ERR_BAD_ARG,
+                  "pdf_gemm_bf16: bad tile descriptor %d", i);
+      PDF_REQUIRE(!out_img || P.tile_okb[i] + 2 <= out_kb, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: output image too narrow");
+    }
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(gemm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
+    cudaFuncSetAttribute(gemm_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
+    configured = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = m_tiles * n_tiles;
+  if (grid > sms) grid = sms;
+  if (colmax) gemm_bf16_kernel<true><<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(P);
+  else gemm_bf16_kernel<false><<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(P);
+  return check_launch("pdf_gemm_bf16");
+}
+
+extern "C" int pdf_sft_xyz_f32(const float* cond, int64_t M, int cc, const float* w0s, const float* b0s,
+                               const float* w1s, const float* b1s, const float* w0h, const float* b0h,
+                               const float* w1h, const float* b1h, float* x, int64_t ldx, void* stream) {
+  if (M == 0) return PDF_OK;
+  PDF_REQUIRE(cond && w0s && b0s && w1s && b1s && w0h && b0h && w1h && b1h && x, PDF_ERR_BAD_ARG,
+              "pdf_sft_xyz_f32: null pointer");
+  PDF_REQUIRE(cc == 64, PDF_ERR_UNSUPPORTED, "pdf_sft_xyz_f32: only 64 condition channels (level 1) are built");
+  const size_t smem = (size_t)(2 * cc * cc + 2 * cc + 6 * cc) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(pdf::sft_xyz_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  pdf::sft_xyz_kernel<64><<<(unsigned)((M + 127) / 128), 128, smem, (cudaStream_t)stream>>>(
+      cond, M, w0s, b0s, w1s, b1s, w0h, b0h, w1h, b1h, x, ldx);
+  return pdf::check_launch("pdf_sft_xyz_f32");
+}

@@ -12,7 +12,7 @@ namespace pdf {
 // redux.sync per bit, early exit when a prefix splits off exactly k points.
 // ---------------------------------------------------------------------------------
 template <int T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 knn_ball_kernel(const float* __restrict__ xyz, int n_points, int n_centroids, int k, float r2,
                 int64_t stride_cloud, int64_t stride_point, int64_t stride_ch,
                 int32_t* __restrict__ idx_out, int chunks_per_cloud, int centroids_per_cta) {
@@ -44,16 +44,36 @@ knn_ball_kernel(const float* __restrict__ xyz, int n_points, int n_centroids, in
       const int j = t * 32 + lane;
       d[t] = __float_as_uint(sqdist_rn(sx[j], sy[j], sz[j], cx, cy, cz));
     }
-    // radix descent for the k-th smallest bit pattern
+    // radix descent for the k-th smallest bit pattern.  Counting uses four independent
+    // partial sums (setp + predicated add) so the per-bit latency is T/4 dependent adds.
     uint32_t prefix = 0, limit = 0;
     bool split = false;
-#pragma unroll 1
-    for (int bit = 30; bit >= 0; --bit) {
-      const uint32_t cand = prefix | (1u << bit);
-      int cnt = 0;
+    // bits on which every distance agrees need no vote: start below the common prefix
+    uint32_t all_or = 0, all_and = 0xffffffffu;
 #pragma unroll
-      for (int t = 0; t < T; ++t) cnt += (d[t] < cand) ? 1 : 0;
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
+    for (int t = 0; t < T; ++t) {
+      if (t * 32 < n_points) { all_or |= d[t]; all_and &= d[t]; }
+    }
+    all_or = __reduce_or_sync(0xffffffffu, all_or);
+    all_and = __reduce_and_sync(0xffffffffu, all_and);
+    int bit = 31 - __clz((all_or ^ all_and) | 1u);        // highest bit that differs (>= 0)
+    prefix = (bit >= 30) ? 0u : (all_and & ~((2u << bit) - 1u));
+    if (bit > 30) bit = 30;
+#pragma unroll 1
+    for (; bit >= 0; --bit) {
+      const uint32_t cand = prefix | (1u << bit);
+      int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+      for (int t = 0; t < T; t += 4) {
+        asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+            "setp.lt.u32 p0, %4, %8;\n\tsetp.lt.u32 p1, %5, %8;\n\t"
+            "setp.lt.u32 p2, %6, %8;\n\tsetp.lt.u32 p3, %7, %8;\n\t"
+            "@p0 add.s32 %0, %0, 1;\n\t@p1 add.s32 %1, %1, 1;\n\t"
+            "@p2 add.s32 %2, %2, 1;\n\t@p3 add.s32 %3, %3, 1;\n\t}"
+            : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3)
+            : "r"(d[t]), "r"(d[t + 1]), "r"(d[t + 2]), "r"(d[t + 3]), "r"(cand));
+      }
+      const int cnt = __reduce_add_sync(0xffffffffu, (c0 + c1) + (c2 + c3));
       if (cnt == k) { limit = cand; split = true; break; }
       if (cnt < k) prefix = cand;
     }
@@ -162,6 +182,7 @@ fps_kernel(const float* __restrict__ xyz, int n_points, int n_sample, const int3
 extern "C" int pdf_knn_ball(const float* xyz, int64_t n_clouds, int n_points, int n_centroids, int k, float r2,
                             int64_t stride_cloud, int64_t stride_point, int64_t stride_ch,
                             int32_t* idx_out, void* stream) {
+  if (n_clouds == 0) return PDF_OK;
   PDF_REQUIRE(xyz && idx_out, PDF_ERR_BAD_ARG, "pdf_knn_ball: null pointer");
   PDF_REQUIRE(n_clouds >= 0 && n_points > 0 && n_centroids > 0 && k > 0, PDF_ERR_BAD_ARG,
               "pdf_knn_ball: non-positive size");
@@ -188,6 +209,7 @@ extern "C" int pdf_knn_ball(const float* xyz, int64_t n_clouds, int n_points, in
 extern "C" int pdf_fps(const float* xyz, int64_t n_clouds, int n_points, int n_sample, const int32_t* start_idx,
                        int64_t stride_cloud, int64_t stride_point, int64_t stride_ch,
                        int32_t* idx_out, void* stream) {
+  if (n_clouds == 0) return PDF_OK;
   PDF_REQUIRE(xyz && idx_out && start_idx, PDF_ERR_BAD_ARG, "pdf_fps: null pointer");
   PDF_REQUIRE(n_clouds >= 0 && n_points > 0 && n_sample > 0, PDF_ERR_BAD_ARG, "pdf_fps: non-positive size");
   PDF_REQUIRE(n_points <= 4096 && n_sample <= n_points, PDF_ERR_UNSUPPORTED,
@@ -201,7 +223,14 @@ extern "C" int pdf_fps(const float* xyz, int64_t n_clouds, int n_points, int n_s
   if (n_points <= 512) LAUNCH(2);
   else if (n_points <= 1024) LAUNCH(4);
   else if (n_points <= 2048) LAUNCH(8);
-  else LAUNCH(16);
+  else {
+    static bool attr = false;   // 48 KB of coordinates + static barriers exceeds the default dynamic limit
+    if (!attr) {
+      cudaFuncSetAttribute(pdf::fps_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 16 * 256 * 4);
+      attr = true;
+    }
+    LAUNCH(16);
+  }
 #undef LAUNCH
   return pdf::check_launch("pdf_fps");
 }

@@ -125,6 +125,7 @@ extern "C" int pdf_linear_f32(const float* X, int64_t lda, const float* W, int64
                               int64_t M, int N, int K, int act, int epilogue, int group, const float* F,
                               int64_t ldf, float* Y, int64_t ldy, void* stream) {
   using namespace pdf;
+  if (M == 0) return PDF_OK;
   PDF_REQUIRE(X && W && Y, PDF_ERR_BAD_ARG, "pdf_linear_f32: null pointer");
   PDF_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K, PDF_ERR_BAD_ARG, "pdf_linear_f32: bad size");
   PDF_REQUIRE(act >= 0 && act <= 2 && epilogue >= 0 && epilogue <= 3, PDF_ERR_BAD_ARG, "pdf_linear_f32: bad enum");

@@ -184,6 +184,7 @@ extern "C" int pdf_mano_lbs(const float* v_template, const float* shapedirs_t, c
                             int new_skel, float* v, float* j, void* stream) {
   PDF_REQUIRE(v_template && shapedirs_t && posedirs_t && j_template && j_shapedirs && weights_t, PDF_ERR_BAD_ARG,
               "pdf_mano_lbs: null table pointer");
+  if (n == 0) return PDF_OK;
   PDF_REQUIRE(root && pose && shape && v && j && tip_idx_host, PDF_ERR_BAD_ARG, "pdf_mano_lbs: null pointer");
   PDF_REQUIRE(n >= 0 && center_idx < 21, PDF_ERR_BAD_ARG, "pdf_mano_lbs: bad size");
   pdf::Tips tips;

@@ -347,6 +347,7 @@ extern "C" int pdf_sa_pack_weights_host(const float* W1, const float* b1, const 
 extern "C" int pdf_sa_mlp_max_bf16(const float* pts, int64_t n_clouds, int n_src, int64_t ld_pts, int c_in,
                                    const int32_t* idx, int n_centroids, int k, const void* wpack, int c1, int c2,
                                    int c3, float* out, int64_t ld_out, int out_col0, void* stream) {
+  if (n_clouds == 0) return PDF_OK;
   PDF_REQUIRE(pts && idx && wpack && out, PDF_ERR_BAD_ARG, "pdf_sa_mlp_max_bf16: null pointer");
   PDF_REQUIRE(n_clouds >= 0 && n_src > 0 && n_centroids > 0 && out_col0 >= 0 && out_col0 <= 4, PDF_ERR_BAD_ARG,
               "pdf_sa_mlp_max_bf16: bad size");

@@ -160,8 +160,34 @@ class PointNet_Plus(nn.Module):
                 for name in ("netR_1", "netR_2"):
                     (w1, b1), (w2, b2), (w3, b3) = f[name]
                     f[name + "_pack"] = ops.sa_pack_weights(w1, b1, w2, b2, w3, b3).to(dev)
+                f["tc"] = self._tensor_core_images(f, dev)
             self._folded, self._folded_key = f, key
         return self._folded
+
+    def _tensor_core_images(self, f, dev):
+        """bf16 tile images (pdf_pack_image_host) of the dense layers that run on the streaming
+        tcgen05 GEMM.  Channel order inside the images: [features..., xyz, zero pad]."""
+        img = lambda w: ops.pack_image(w).to(dev)
+        z = lambda n, like: torch.zeros((n,) + tuple(like.shape[1:]), dtype=like.dtype, device=like.device)
+        tc = {}
+        # SFT1: hidden = lrelu([Ws0;Wh0] cond), features 3..130 modulated on tensor cores (xyz in fp32)
+        ws0, bs0, ws1, bs1, wh0, bh0, wh1, bh1 = self.sft1.weights()
+        tc["sft1_plain"] = (ws0, bs0, ws1, bs1, wh0, bh0, wh1, bh1)
+        tc["sft1_w0"], tc["sft1_b0"] = img(torch.cat([ws0, wh0], 0)), torch.cat([bs0, bh0]).contiguous()
+        tc["sft1_w1"] = img(torch.cat([ws1[3:], wh1[3:]], 1))
+        tc["sft1_b1s"], tc["sft1_b1h"] = bs1[3:].contiguous(), bh1[3:].contiguous()
+        # SFT2: N-tiles = features 0..127 | features 128..255 | [xyz, pad]
+        ws0, bs0, ws1, bs1, wh0, bh0, wh1, bh1 = self.sft2.weights()
+        tc["sft2_w0"], tc["sft2_b0"] = img(torch.cat([ws0, wh0], 0)), torch.cat([bs0, bh0]).contiguous()
+        reorder = lambda t: torch.cat([t[3:], t[:3], z(125, t)], 0)
+        tc["sft2_w1"] = img(torch.cat([reorder(ws1), reorder(wh1)], 1))
+        tc["sft2_b1s"], tc["sft2_b1h"] = reorder(bs1).contiguous(), reorder(bh1).contiguous()
+        # netR_3: layer-1 columns follow the image written by SFT2 ([256 features, xyz])
+        (w1, b1), (w2, b2), (w3, b3) = f["netR_3"]
+        tc["n3_w1"], tc["n3_b1"] = img(torch.cat([w1[:, 3:], w1[:, :3]], 1)), b1
+        tc["n3_w2"], tc["n3_b2"] = img(w2), b2
+        tc["n3_w3"], tc["n3_b3"] = img(w3), b3
+        return tc
 
     def forward(self, points, emb, choose, clouds_per_frame=1):
         if self.training:
@@ -179,6 +205,8 @@ class PointNet_Plus(nn.Module):
             return torch.cat(outs, 0)
 
     def _forward_chunk(self, points, emb, choose, cpf, frame0):
+        if self.precision == "bf16":
+            return self._forward_chunk_bf16(points, emb, choose, cpf, frame0)
         opt, f = self.opt, self.folded()
         N1, N2, K = self.sample_num_level1, self.sample_num_level2, self.knn_K
         B, N = points.shape[0], points.shape[1]
@@ -222,6 +250,68 @@ class PointNet_Plus(nn.Module):
             out = ops.linear(h, w3, b3, act=L.ACT_RELU, epilogue=L.EPI_GROUP_MAX, group=N2)
         return out.view(B, 1, nstates_plus_3[2])
 
+    def _forward_chunk_bf16(self, points, emb, choose, cpf, frame0):
+        """Tensor-core pipeline: fused tcgen05 set-abstraction kernels + streaming tcgen05 GEMMs over
+        bf16 tile images for SFT1 / SFT2 / netR_3.  Everything that decides neighbour indices (SFT0,
+        the xyz channels of SFT1, both neighbour searches) stays fp32."""
+        opt, f = self.opt, self.folded()
+        tc = f["tc"]
+        N1, N2, K = self.sample_num_level1, self.sample_num_level2, self.knn_K
+        if N2 != 128 or N1 % 128 != 0 or K != 64:
+            raise RuntimeError("PointNet_Plus(precision='bf16') is built for K=64, N2=128, N1 %% 128 == 0 "
+                               "(got K=%d N1=%d N2=%d); use precision='fp32'" % (K, N1, N2))
+        B = points.shape[0]
+        dev = points.device
+        if frame0:
+            nf = (B + cpf - 1) // cpf
+            emb = [e[frame0:frame0 + nf] for e in emb]
+        u8 = lambda n: torch.empty((n,), dtype=torch.uint8, device=dev)
+        RELU, LEAKY, BLK = L.ACT_RELU, L.ACT_LEAKY01, 16384
+        with stage("pyramid_gather"):
+            pts0, cond1, cond2 = ops.pyramid_gather(points, choose, emb, f["sft0"], N1, N2, opt.default_resolution,
+                                                    cpf)
+        with stage("knn1"):
+            idx1 = ops.knn_ball(pts0, N1, K, opt.ball_radius)
+        x1 = torch.empty((B, N1, 132), dtype=torch.float32, device=dev)
+        with stage("sa1"):
+            self._sa(pts0, idx1, "netR_1", f, x1, None)
+        M1, M2 = B * N1, B * N2
+        t1, t2 = M1 // 128, M2 // 128
+        x1r, c1r = x1.view(M1, 132), cond1.view(M1, 64)
+        with stage("sft1"):
+            c1img = ops.rows_to_image(c1r, 0, 64)
+            h1img = u8(t1 * 2 * BLK)
+            ops.gemm_bf16(c1img, t1, 1, tc["sft1_w0"], 1, 1, 1, tc["sft1_b0"], act=LEAKY, out_img=h1img, out_kb=2,
+                          rows_valid=M1, tile_desc=[(0, 128, 0)])
+            ops.gemm_bf16(h1img, t1, 2, tc["sft1_w1"], 1, 2, 2, tc["sft1_b1s"], kb_split=1, bias1=tc["sft1_b1h"],
+                          F=x1r, out_f32=x1r, rows_valid=M1, tile_desc=[(4, 128, 0)])
+            ops.sft_xyz(c1r, tc["sft1_plain"], x1r)
+        with stage("knn2"):
+            idx2 = ops.knn_ball(x1, N2, K, self.ball_radius2)
+        x2 = torch.empty((B, N2, 260), dtype=torch.float32, device=dev)
+        with stage("sa2"):
+            self._sa(x1, idx2, "netR_2", f, x2, None)
+        x2r = x2.view(M2, 260)
+        four = [(0, 128, 0), (0, 128, 2), (0, 128, 4), (0, 128, 6)]
+        with stage("sft2"):
+            c2img = ops.rows_to_image(cond2.view(M2, 256), 0, 256)
+            h2img = u8(t2 * 8 * BLK)
+            ops.gemm_bf16(c2img, t2, 4, tc["sft2_w0"], 4, 4, 4, tc["sft2_b0"], act=LEAKY, out_img=h2img, out_kb=8,
+                          rows_valid=M2, tile_desc=four)
+            x3img = u8(t2 * 6 * BLK)
+            ops.gemm_bf16(h2img, t2, 8, tc["sft2_w1"], 3, 8, 8, tc["sft2_b1s"], kb_split=4, bias1=tc["sft2_b1h"],
+                          F=x2r, out_img=x3img, out_kb=6, rows_valid=M2,
+                          tile_desc=[(4, 128, 0), (132, 128, 2), (0, 4, 4)])
+        with stage("global_mlp"):
+            g1img, g2img = u8(t2 * 8 * BLK), u8(t2 * 8 * BLK)
+            ops.gemm_bf16(x3img, t2, 6, tc["n3_w1"], 4, 5, 5, tc["n3_b1"], act=RELU, out_img=g1img, out_kb=8,
+                          rows_valid=M2, tile_desc=four)
+            ops.gemm_bf16(g1img, t2, 8, tc["n3_w2"], 4, 8, 8, tc["n3_b2"], act=RELU, out_img=g2img, out_kb=8,
+                          rows_valid=M2, tile_desc=four)
+            out = torch.empty((B, nstates_plus_3[2]), dtype=torch.float32, device=dev)
+            ops.gemm_bf16(tc["n3_w3"], 8, 8, g2img, t2, 8, 8, tc["n3_b3"], out_max=out)
+        return out.view(B, 1, nstates_plus_3[2])
+
     def _sa(self, pts, idx, name, f, xout, w1pad):
         """One set-abstraction stage: max-pooled features to xout[:, :, 4:], centroid xyz to
         xout[:, :, 0:3] (written here by the tensor-core kernel, by the caller in fp32 mode)."""
@@ -263,12 +353,40 @@ class HandFusion(nn.Module):
         rows = feat.view(B * H, 1024)
         with torch.no_grad():
             with stage("fusion_sft"):
-                fused = self.sft.apply_rows(rows, L.f32c(center_features).view(B * H, 1024)).view(B, H, 1024)
+                cen = L.f32c(center_features).view(B * H, 1024)
+                if self.pointnet_plus.precision == "bf16":
+                    fused = self._fusion_sft_bf16(rows, cen).view(B, H, 1024)
+                else:
+                    fused = self.sft.apply_rows(rows, cen).view(B, H, 1024)
             if not with_mano:
                 return fused
             with stage("mano_head"):
                 theta = self.mano_head_forward(rows).view(B, H, 122)
             return fused, theta
+
+    def _fusion_sft_bf16(self, rows, cen):
+        """SFTLayer(1024,1024) (:809) on the streaming tcgen05 GEMM: hidden = lrelu([Ws0;Wh0] c) as a
+        bf16 image, then the dual-accumulator SFT epilogue writes fp32 rows."""
+        key = tuple((p.data_ptr(), p._version) for p in self.sft.parameters())
+        if getattr(self, "_sft_tc_key", None) != key:
+            ws0, bs0, ws1, bs1, wh0, bh0, wh1, bh1 = self.sft.weights()
+            dev = rows.device
+            self._sft_tc = dict(w0=ops.pack_image(torch.cat([ws0, wh0], 0)).to(dev),
+                                b0=torch.cat([bs0, bh0]).contiguous(),
+                                w1=ops.pack_image(torch.cat([ws1, wh1], 1)).to(dev), b1s=bs1.contiguous(),
+                                b1h=bh1.contiguous())
+            self._sft_tc_key = key
+        t = self._sft_tc
+        M = rows.shape[0]
+        mt = (M + 127) // 128
+        cimg = ops.rows_to_image(cen, 0, 1024)
+        himg = torch.empty((mt * 32 * 16384,), dtype=torch.uint8, device=rows.device)
+        ops.gemm_bf16(cimg, mt, 16, t["w0"], 16, 16, 16, t["b0"], act=L.ACT_LEAKY01, out_img=himg, out_kb=32,
+                      rows_valid=M, tile_desc=[(0, 128, 2 * i) for i in range(16)])
+        out = torch.empty((M, 1024), dtype=torch.float32, device=rows.device)
+        ops.gemm_bf16(himg, mt, 32, t["w1"], 8, 32, 32, t["b1s"], kb_split=16, bias1=t["b1h"], F=rows, out_f32=out,
+                      rows_valid=M, tile_desc=[(128 * i, 128, 0) for i in range(8)])
+        return out
 
     def mano_head_forward(self, x):
         """mano_head (:630-643) in eval mode: Linear+BN1d folded, ReLU, on the FFMA linear kernel."""

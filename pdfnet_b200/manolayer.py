@@ -92,7 +92,7 @@ class ManoLayer(Module):
         self.new_skel = new_skel
         data = manoPath if isinstance(manoPath, dict) else load_mano_data(manoPath)
         self.new_order = list(NEW_ORDER)
-        g = lambda k: torch.as_tensor(np.asarray(data[k]), dtype=torch.float32)
+        g = lambda k: torch.tensor(np.asarray(data[k]), dtype=torch.float32)   # copy: never alias caller arrays
         if "hands_components" in data:
             self.register_buffer("hands_components", g("hands_components"))
             self.register_buffer("hands_components_inv", torch.inverse(self.hands_components))

@@ -145,6 +145,60 @@ def sa_mlp_max_bf16(pts, idx, wpack, c_in, c1, c2, c3, out, out_col0=0):
     return out
 
 
+def image_bytes(rows, cols):
+    return int(L.load().pdf_image_bytes(rows, cols))
+
+
+def pack_image(w):
+    """Host-side packing of an fp32 matrix [rows, cols] into a bf16 tile image (uint8 CPU tensor)."""
+    w = w.detach().cpu().float().contiguous()
+    rows, cols = w.shape
+    buf = torch.empty((image_bytes(rows, cols),), dtype=torch.uint8)
+    L.call("pdf_pack_image_host", ctypes.c_void_p(w.data_ptr()), rows, cols, w.stride(0),
+           ctypes.c_void_p(buf.data_ptr()))
+    return buf
+
+
+def rows_to_image(x, col0, K, img=None, kb_total=None, kb0=0):
+    """fp32 rows x[M, ld] columns [col0, col0+K) -> bf16 tile image (uint8 device tensor)."""
+    L.require_cuda(x, img)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32
+    M = x.shape[0]
+    nkb = (K + 63) // 64
+    if kb_total is None:
+        kb_total = nkb
+    if img is None:
+        img = torch.empty((((M + 127) // 128) * kb_total * 16384,), dtype=torch.uint8, device=x.device)
+    L.call("pdf_rows_to_image", L.ptr(x), x.stride(0), M, col0, K, L.ptr(img), kb_total, kb0, L.stream())
+    return img
+
+
+def gemm_bf16(m_img, m_tiles, m_kb, n_img, n_tiles, n_kb, KB, bias0, kb_split=0, bias1=None, act=L.ACT_NONE,
+              out_f32=None, rows_valid=0, F=None, out_img=None, out_kb=0, tile_desc=None, out_max=None):
+    """Streaming tcgen05 GEMM over tile images (see pdf_gemm_bf16)."""
+    L.require_cuda(m_img, n_img, bias0, bias1, out_f32, F, out_img, out_max)
+    colmax = out_max is not None
+    desc = None
+    if tile_desc is not None:
+        flat = [int(v) for t in tile_desc for v in t]
+        desc = (ctypes.c_int32 * len(flat))(*flat)
+    L.call("pdf_gemm_bf16", L.ptr(m_img), m_tiles, m_kb, L.ptr(n_img), n_tiles, n_kb, KB, kb_split, 1 if colmax else 0,
+           L.ptr(bias0), L.ptr(bias1), act, L.ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0, rows_valid,
+           L.ptr(F), F.stride(0) if F is not None else 0, L.ptr(out_img), out_kb,
+           ctypes.cast(desc, ctypes.c_void_p) if desc is not None else None, L.ptr(out_max),
+           out_max.stride(0) if colmax else 0, L.stream())
+
+
+def sft_xyz(cond_rows, weights, x_rows):
+    """fp32 SFT on columns 0..2 of x_rows (in place); weights = SFTLayer.weights() tuple."""
+    L.require_cuda(cond_rows, x_rows)
+    ws0, bs0, ws1, bs1, wh0, bh0, wh1, bh1 = weights
+    assert cond_rows.is_contiguous() and x_rows.stride(1) == 1
+    L.call("pdf_sft_xyz_f32", L.ptr(cond_rows), cond_rows.shape[0], cond_rows.shape[1], L.ptr(ws0), L.ptr(bs0),
+           L.ptr(ws1), L.ptr(bs1), L.ptr(wh0), L.ptr(bh0), L.ptr(wh1), L.ptr(bh1), L.ptr(x_rows), x_rows.stride(0),
+           L.stream())
+
+
 def backproject(depth, Kinv):
     """xyz [B,3,H,W] = (Kinv @ [u,v,1]) * depth ; depth [B,H,W] fp32, Kinv [B,3,3] fp32."""
     L.require_cuda(depth, Kinv)

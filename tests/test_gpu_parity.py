@@ -353,7 +353,7 @@ def test_mano_lbs_vs_reference_golden():
 
 def test_mano_lbs_batch_vs_oracle_and_fix_shape():
     from pdfnet_b200 import ManoLayer
-    T = mano_tables("left")
+    T = {k: np.array(v) for k, v in mano_tables("left").items()}
     rot, pose, shape, trans = synth.mano_inputs(256, seed=5)
     layer = ManoLayer(T, center_idx=None)
     v, j = layer(rot.to(DEV), pose.to(DEV), shape.to(DEV), trans.to(DEV), side="left")
@@ -422,3 +422,91 @@ def test_errors_are_loud():
     with pytest.raises(NotImplementedError):
         m.train()(torch.zeros((1, 1024, 3), device=DEV), [None] * 3, torch.zeros((1, 1024), device=DEV))
     assert ops.knn_ball(torch.zeros((0, 1024, 3), device=DEV), 512, 64, 0.01).shape == (0, 512, 64)
+
+
+# ----------------------------------------------------------------------------- streaming tcgen05 GEMM
+
+def _decode_image(img, rows, cols):
+    """bf16 tile image (uint8 numpy) -> float32 [rows, cols] using the documented SW128 offsets."""
+    kbt = (cols + 63) // 64
+    r = np.arange(rows)[:, None]
+    k = np.arange(cols)[None, :]
+    off = ((r >> 7) * kbt + (k >> 6)) * 16384 + ((r & 127) >> 3) * 1024 + (r & 7) * 128 \
+        + ((((k & 63) >> 3) ^ (r & 7)) << 4) + (k & 7) * 2
+    u16 = img[off].astype(np.uint32) | (img[off + 1].astype(np.uint32) << 8)
+    return (u16 << 16).view(np.float32)
+
+
+def _bf(t):
+    return t.bfloat16().float()
+
+
+def test_gemm_bf16_row_modes():
+    from pdfnet_b200 import _lib as L
+    from pdfnet_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    M, K, N = 300, 200, 200
+    x, w, b = torch.randn((M, K), generator=g), torch.randn((N, K), generator=g) * 0.1, torch.randn((N,), generator=g)
+    ximg = ops.rows_to_image(x.to(DEV), 0, K)
+    assert (_decode_image(ximg.cpu().numpy(), M, K) == _bf(x).numpy()).all()
+    wimg = ops.pack_image(w).to(DEV)
+    assert (_decode_image(wimg.cpu().numpy(), N, K) == _bf(w).numpy()).all()
+    ref = _bf(x).double() @ _bf(w).double().t() + b.double()
+    out = torch.full((M, 208), -7.0, device=DEV)
+    oimg = torch.zeros((3 * 4 * 16384,), dtype=torch.uint8, device=DEV)
+    bias = torch.cat([b, torch.zeros(56)]).to(DEV)
+    ops.gemm_bf16(ximg, 3, 4, wimg, 2, 4, 4, bias, act=L.ACT_LEAKY01, out_f32=out, rows_valid=M, out_img=oimg,
+                  out_kb=4, tile_desc=[(0, 128, 0), (128, 72, 2)])
+    want = torch.where(ref > 0, ref, 0.1 * ref)
+    assert rel_err(out[:, :200].cpu(), want) < 1e-5
+    assert bool((out[:, 200:] == -7.0).all())                         # columns beyond nvalid untouched
+    dec = _decode_image(oimg.cpu().numpy(), 384, 256)
+    assert rel_err(dec[:M, :200], _bf(want.float()).numpy()) < 1e-2 and (dec[M:] == 0).all() and (dec[:, 200:] == 0).all()
+    # SFT (dual accumulator) mode: y = F*(X0 W0^T + b0 + 1) + (X1 W1^T + b1)
+    K2 = 128
+    h = torch.randn((M, 2 * K2), generator=g)
+    w0, w1 = torch.randn((N, K2), generator=g) * 0.1, torch.randn((N, K2), generator=g) * 0.1
+    b0, b1 = torch.randn((N,), generator=g), torch.randn((N,), generator=g)
+    F = torch.randn((M, 212), generator=g)
+    himg = ops.rows_to_image(h.to(DEV), 0, 2 * K2)
+    wimg = ops.pack_image(torch.cat([w0, w1], 1)).to(DEV)
+    Fd = F.to(DEV)
+    pad = torch.zeros(56)
+    ops.gemm_bf16(himg, 3, 4, wimg, 2, 4, 4, torch.cat([b0, pad]).to(DEV), kb_split=2,
+                  bias1=torch.cat([b1, pad]).to(DEV), F=Fd, out_f32=Fd, rows_valid=M,
+                  tile_desc=[(4, 128, 0), (132, 72, 0)])
+    s0 = _bf(h[:, :K2]).double() @ _bf(w0).double().t() + b0.double()
+    s1 = _bf(h[:, K2:]).double() @ _bf(w1).double().t() + b1.double()
+    want = F[:, 4:204].double() * (s0 + 1) + s1
+    assert rel_err(Fd[:, 4:204].cpu(), want) < 1e-5
+    assert torch.equal(Fd[:, :4].cpu(), F[:, :4]) and torch.equal(Fd[:, 204:].cpu(), F[:, 204:])
+
+
+def test_gemm_bf16_colmax_and_many_tiles():
+    from pdfnet_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    clouds, C, K = 300, 256, 512                          # > 148 x 2 work items: exercises the persistent loop
+    h = torch.randn((clouds * 128, K), generator=g)
+    w, b = torch.randn((C, K), generator=g) * 0.05, torch.randn((C,), generator=g)
+    himg = ops.rows_to_image(h.to(DEV), 0, K)
+    wimg = ops.pack_image(w).to(DEV)
+    out = torch.empty((clouds, C), device=DEV)
+    ops.gemm_bf16(wimg, 2, 8, himg, clouds, 8, 8, b.to(DEV), out_max=out)
+    ref = (_bf(h).to(DEV) @ _bf(w).to(DEV).t() + b.to(DEV)).view(clouds, 128, C).max(1)[0].clamp(min=0)
+    assert rel_err(out.cpu(), ref.cpu()) < 1e-4
+
+
+def test_sft_xyz_fp32():
+    from pdfnet_b200 import SFTLayer, ops
+    g = torch.Generator().manual_seed(9)
+    m = SFTLayer(131, 64)
+    m.load_state_dict(synth.sft_state("", 131, 64, seed=20))
+    m = m.to(DEV).eval()
+    M = 1000
+    x = torch.randn((M, 132), generator=g).to(DEV)
+    cond = torch.randn((M, 64), generator=g).to(DEV)
+    ref = m.apply_rows(x[:, :3].contiguous(), cond, weights=tuple(t[:3] if i in (2, 3, 6, 7) else t
+                                                                for i, t in enumerate(m.weights())))
+    y = x.clone()
+    ops.sft_xyz(cond, m.weights(), y)
+    assert rel_err(y[:, :3].cpu(), ref.cpu()) < 1e-5 and torch.equal(y[:, 3:], x[:, 3:])

@@ -53,6 +53,7 @@ def test_no_cpu_fallback(lib):
 def test_bad_arguments_return_errors_not_crashes(lib):
     # argument validation happens before any CUDA call, so it is testable without a GPU
     assert lib.pdf_knn_ball(None, 1, 1024, 512, 64, 0.01, 0, 0, 0, None, None) == -1
+    assert lib.pdf_knn_ball(None, 0, 1024, 512, 64, 0.01, 0, 0, 0, None, None) == 0     # empty batch: no-op
     assert b"null" in lib.pdf_last_error()
     assert lib.pdf_linear_f32(None, 0, None, 0, None, 1, 1, 1, 0, 0, 0, None, 0, None, 0, None) == -1
     assert lib.pdf_sa_pack_weights_host(None, None, None, None, None, None, 3, 64, 64, 128, None) == -1
