@@ -119,12 +119,14 @@ int pdf_linear_f32(const float* X, int64_t lda, const float* W, int64_t ldw, con
  * point-MLP (folded BN, ReLU) + max over the k neighbours, one pass, no
  * intermediate in HBM.  Replaces utils.py:153-158/181-186 + netR_1 / netR_2
  * (intaghand_encoder.py:48-84,132,143).
- * pts fp32 [n_clouds, n_src, ld_pts] (xyz = columns 0..2, c_in columns used);
+ * pts fp32 [n_clouds, n_src, ld_pts] (xyz = columns 0..2; for c_in = 131 the 128 feature
+ * columns start at column 4, or, when feat_bf16 is non-null, are read from it instead:
+ * bf16 rows [n_clouds, n_src, 128] copied with cp.async straight into the operand tile);
  * idx int32 [n_clouds, n_centroids, 64]; wpack = pdf_sa_pack_weights image;
  * out fp32 [n_clouds, n_centroids, ld_out] columns out_col0 .. out_col0+c3-1.
  * Supported (c_in,c1,c2,c3): (3,64,64,128) and (131,128,128,256); k = 64. */
 int pdf_sa_mlp_max_bf16(const float* pts, int64_t n_clouds, int n_src, int64_t ld_pts, int c_in,
-                        const int32_t* idx, int n_centroids, int k,
+                        const void* feat_bf16, const int32_t* idx, int n_centroids, int k,
                         const void* wpack, int c1, int c2, int c3,
                         float* out, int64_t ld_out, int out_col0, void* stream);
 /* Size in bytes of, and host-side packer for, the weight image above: folded
@@ -153,14 +155,16 @@ int pdf_rows_to_image(const float* X, int64_t ld, int64_t M, int col0, int K, vo
  * colmax = 0 (ROW epilogue, thread = M row): y = act(D + bias0[n]); with kb_split > 0 the
  *   k-blocks below / from kb_split accumulate separately and y = F*(D0+bias0+1) + (D1+bias1)
  *   (SFT modulation).  Output: fp32 rows out_f32[m, tile_col + n] (m < rows_valid) and/or a bf16
- *   tile image (out_kb k-blocks per row-tile).  tile_desc_host: int32 [n_tiles][3] =
+ *   tile image (out_kb k-blocks per row-tile) and/or bf16 rows out_bf16[m, tile_col -
+ *   bf16_col_off + n] (row pitch ld_bf16 elements).  tile_desc_host: int32 [n_tiles][3] =
  *   {first fp32 column of this N-tile in F/out_f32, valid columns (<=128), first output k-block}.
  * colmax = 1: M operand = weights (rows = channels), N operand = activations, one N-tile = the
  *   128 points of one cloud: out_max[n_tile, m] = relu(max_n D[m,n] + bias0[m]). */
 int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const void* n_img, int n_tiles, int n_kb, int KB,
                   int kb_split, int colmax, const float* bias0, const float* bias1, int act, float* out_f32,
                   int64_t ld_out, int64_t rows_valid, const float* F, int64_t ldf, void* out_img, int out_kb,
-                  const int32_t* tile_desc_host, float* out_max, int64_t ld_max, void* stream);
+                  void* out_bf16, int64_t ld_bf16, int bf16_col_off, const int32_t* tile_desc_host, float* out_max,
+                  int64_t ld_max, void* stream);
 /* SFT on the three xyz channels of level 1 in full fp32 (they feed the level-2 neighbour
  * search): x[m,c] = x[m,c]*(scale_c+1)+shift_c for c < 3; cond fp32 [M,cc]; conv weights as in
  * SFTLayer ([out,in] row-major; only rows 0..2 of the second convs are read). cc must be 64. */

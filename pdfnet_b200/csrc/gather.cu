@@ -43,47 +43,70 @@ __device__ __forceinline__ void sft0_apply(const float* __restrict__ P, const fl
   for (int o = 0; o < 3; ++o) xyz[o] = __fadd_rn(__fmul_rn(xyz[o], __fadd_rn(out[0][o], 1.f)), out[1][o]);
 }
 
-// grid.x = cloud; three sections handled by the same CTA:
-//   (1) points 0..n_points-1: gather 3 channels of l0, SFT0, write pts0
-//   (2) n1 x C1 elements of l1 at choose_1_2 ; (3) n2 x C2 elements of l2 at choose_1_4
+// grid = (cloud, 1 + 2*PG_SPLIT): blockIdx.y == 0 handles level 0 (3 channels + SFT0 for every
+// point); the next PG_SPLIT blocks gather level 1, the last PG_SPLIT level 2.  Every thread keeps
+// PG_UNROLL independent scattered loads in flight (each one is a separate 32 B sector of an NCHW
+// plane), stores are coalesced ([cloud, point, channel], channel fastest).
+constexpr int PG_SPLIT = 8, PG_UNROLL = 8;
+
+__device__ __forceinline__ void gather_level(const float* __restrict__ plane0, int C, int64_t HW, int R, int Rl,
+                                             int div, const int64_t* __restrict__ ch, int n,
+                                             float* __restrict__ out, int part) {
+  const int total = n * C;
+  const int per = (total + PG_SPLIT - 1) / PG_SPLIT;
+  const int lo = part * per, hi = min(total, lo + per);
+  for (int e0 = lo + threadIdx.x; e0 < hi; e0 += blockDim.x * PG_UNROLL) {
+    float v[PG_UNROLL];
+#pragma unroll
+    for (int u = 0; u < PG_UNROLL; ++u) {
+      const int e = e0 + u * blockDim.x;
+      if (e < hi) {
+        const int i = e / C, c = e - i * C;
+        const int pix = (int)ch[i];
+        const int pl = (pix / R / div) * Rl + (pix % R) / div;       // intaghand_encoder.py:125-126
+        v[u] = __ldg(plane0 + (int64_t)c * HW + pl);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PG_UNROLL; ++u) {
+      const int e = e0 + u * blockDim.x;
+      if (e < hi) out[e] = v[u];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 pyramid_gather_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ choose, int clouds_per_frame,
                       int n_points, int n1, int n2, int R,
                       const float* __restrict__ l0, const float* __restrict__ l1, int C1,
                       const float* __restrict__ l2, int C2, const float* __restrict__ sft0,
                       float* __restrict__ pts0, float* __restrict__ cond1, float* __restrict__ cond2) {
-  __shared__ float P[48];
   const int64_t b = blockIdx.x;
   const int64_t f = b / clouds_per_frame;
-  if (threadIdx.x < 48) P[threadIdx.x] = sft0[threadIdx.x];
-  __syncthreads();
   const int64_t* ch = choose + b * n_points;
-  const int64_t RR = (int64_t)R * R;
-  for (int i = threadIdx.x; i < n_points; i += blockDim.x) {
-    const int64_t pix = ch[i];
-    float e[3], p[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      e[c] = __ldg(l0 + (f * 3 + c) * RR + pix);
-      p[c] = xyz[(b * n_points + i) * 3 + c];
-    }
-    sft0_apply(P, e, p);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) pts0[(b * n_points + i) * 3 + c] = p[c];
-  }
   const int R2 = R / 2, R4 = R / 4;
-  const int64_t HW2 = (int64_t)R2 * R2, HW4 = (int64_t)R4 * R4;
-  for (int e = threadIdx.x; e < n1 * C1; e += blockDim.x) {
-    const int i = e / C1, c = e % C1;
-    const int64_t pix = ch[i];
-    const int64_t p2 = (pix / R / 2) * R2 + (pix % R) / 2;     // intaghand_encoder.py:125
-    cond1[(b * n1 + i) * C1 + c] = __ldg(l1 + (f * C1 + c) * HW2 + p2);
-  }
-  for (int e = threadIdx.x; e < n2 * C2; e += blockDim.x) {
-    const int i = e / C2, c = e % C2;
-    const int64_t pix = ch[i];
-    const int64_t p4 = (pix / R / 4) * R4 + (pix % R) / 4;     // intaghand_encoder.py:126
-    cond2[(b * n2 + i) * C2 + c] = __ldg(l2 + (f * C2 + c) * HW4 + p4);
+  const int64_t RR = (int64_t)R * R, HW2 = (int64_t)R2 * R2, HW4 = (int64_t)R4 * R4;
+  if (blockIdx.y == 0) {
+    __shared__ float P[48];
+    if (threadIdx.x < 48) P[threadIdx.x] = sft0[threadIdx.x];
+    __syncthreads();
+    const float* base = l0 + f * 3 * RR;
+    for (int i = threadIdx.x; i < n_points; i += blockDim.x) {
+      const int64_t pix = ch[i];
+      float e[3], p[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        e[c] = __ldg(base + c * RR + pix);
+        p[c] = xyz[(b * n_points + i) * 3 + c];
+      }
+      sft0_apply(P, e, p);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) pts0[(b * n_points + i) * 3 + c] = p[c];
+    }
+  } else if (blockIdx.y <= PG_SPLIT) {
+    gather_level(l1 + f * C1 * HW2, C1, HW2, R, R2, 2, ch, n1, cond1 + b * n1 * C1, blockIdx.y - 1);
+  } else {
+    gather_level(l2 + f * C2 * HW4, C2, HW4, R, R4, 4, ch, n2, cond2 + b * n2 * C2, blockIdx.y - 1 - PG_SPLIT);
   }
 }
 
@@ -185,7 +208,8 @@ extern "C" int pdf_pyramid_gather(const float* xyz, const int64_t* choose, int64
                   n2 <= n_points && R >= 4 && C1 > 0 && C2 > 0,
               PDF_ERR_BAD_ARG, "pdf_pyramid_gather: bad size");
   if (n_clouds == 0) return PDF_OK;
-  pdf::pyramid_gather_kernel<<<(unsigned)n_clouds, 256, 0, (cudaStream_t)stream>>>(
+  PDF_REQUIRE(n_clouds < (1ll << 31) && (int64_t)R * R < (1ll << 31), PDF_ERR_UNSUPPORTED, "pdf_pyramid_gather: too large");
+  pdf::pyramid_gather_kernel<<<dim3((unsigned)n_clouds, 1 + 2 * pdf::PG_SPLIT), 256, 0, (cudaStream_t)stream>>>(
       xyz, choose, clouds_per_frame, n_points, n1, n2, R, l0, l1, C1, l2, C2, sft0_params, pts0, cond1, cond2);
   return pdf::check_launch("pdf_pyramid_gather");
 }

@@ -7,10 +7,11 @@
 // therefore ONE contiguous cp.async.bulk (TMA engine, no tensor map), and the epilogue of
 // one layer writes the operand image of the next layer directly.
 //
-// Persistent warp-specialised kernel, one CTA per SM, 192 threads:
+// Persistent warp-specialised kernel, one CTA per SM, 320 threads:
 //   warp 0  : producer  - bulk copies of (M-operand block, N-operand block) into a 4-stage ring
 //   warp 1  : MMA issue - 4 x tcgen05.mma (128x128x16) per k-block, commit frees the stage
-//   warps 2-5: epilogue - drain one of two TMEM accumulator stages while the other fills
+//   warps 2-9: epilogue - drain one of two TMEM accumulator stages while the other fills
+//              (two warps per TMEM lane quarter, 64 columns each; biases staged in smem)
 // Epilogues (thread = TMEM lane):
 //   ROW   : lane = activation row.  y = act(D + bias[n]) or, with two accumulators (k-blocks
 //           below / above kb_split accumulate separately), the SFT modulation
@@ -26,8 +27,8 @@ using namespace umma;
 
 constexpr int G_STAGES = 4;
 constexpr int G_BLOCK = 16384;                 // one 128 x 64 bf16 block
-constexpr int G_THREADS = 192;
-constexpr int G_SMEM = G_STAGES * 2 * G_BLOCK + 1024 + 256;
+constexpr int G_THREADS = 320;                // producer warp + MMA warp + 8 epilogue warps
+constexpr int G_SMEM = G_STAGES * 2 * G_BLOCK + 1024 + 256 + 2 * 16 * 128 * 4;   // + staged biases
 constexpr int G_MAX_NT = 16;
 
 struct GemmParams {
@@ -39,6 +40,8 @@ struct GemmParams {
   float* out_f32; int64_t ld_out; int64_t rows_valid;
   const float* F; int64_t ldf;
   uint8_t* out_img; int out_kb;
+  uint16_t* out_bf16; int64_t ld_bf16;   // optional bf16 ROW-major output (same columns as out_f32, minus bf16_col_off)
+  int bf16_col_off;
   float* out_max; int64_t ld_max;
   int tile_col[G_MAX_NT];        // ROW mode, per N-tile: first fp32 column (F and out_f32)
   int tile_nvalid[G_MAX_NT];     //   valid output columns of this N-tile (others are written as 0 / skipped)
@@ -62,10 +65,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < G_STAGES; ++s) { mbar_init(smem_u32(&bars[s]), 1); mbar_init(smem_u32(&bars[G_STAGES + s]), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bars[2 * G_STAGES + a]), 1); mbar_init(smem_u32(&bars[2 * G_STAGES + 2 + a]), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bars[2 * G_STAGES + a]), 1); mbar_init(smem_u32(&bars[2 * G_STAGES + 2 + a]), COLMAX ? 4 : 8); }
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<512>(s_tmem);
+  float* s_bias = reinterpret_cast<float*>(smem + G_STAGES * 2 * G_BLOCK + 256);   // [2][n_tiles*128]
+  if (!COLMAX) {
+    for (int i = threadIdx.x; i < P.n_tiles * 128; i += G_THREADS) {
+      s_bias[i] = P.bias0[i];
+      s_bias[G_MAX_NT * 128 + i] = dual ? P.bias1[i] : 0.f;
+    }
+  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -114,8 +124,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-  } else {
+  } else if (!COLMAX || warp < 6) {
     const int q4 = warp & 3;                               // TMEM lane quarter of this warp
+    const int half = (warp - 2) >> 2;                      // ROW mode: which 64 columns this warp drains
     const int row = q4 * 32 + lane;
     const uint32_t lane_off = ((uint32_t)(q4 * 32)) << 16;
     int as = 0; uint32_t aphase = 0;
@@ -140,10 +151,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
         const int64_t m = (int64_t)mt * 128 + row;
         const bool row_ok = m < P.rows_valid;
         const int col0 = P.tile_col[nt], nvalid = P.tile_nvalid[nt], okb = P.tile_okb[nt];
-        const float* b0 = P.bias0 + nt * 128;
-        const float* b1 = dual ? P.bias1 + nt * 128 : nullptr;
+        const float* b0 = s_bias + nt * 128;
+        const float* b1 = s_bias + G_MAX_NT * 128 + nt * 128;
+        const bool full = row_ok && nvalid == 128;           // fast path: no per-element masking
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
+        for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
           uint32_t v[32], u[32];
           tmem_ld32(acc + c0, v);
           if (dual) tmem_ld32(acc + 128 + c0, u);
@@ -151,20 +163,29 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
           float y[32];
 #pragma unroll
           for (int q = 0; q < 32; q += 4) {
-            float f[4] = {0.f, 0.f, 0.f, 0.f};
-            if (dual && row_ok && c0 + q < nvalid) {
-              const float4 t = *reinterpret_cast<const float4*>(P.F + m * P.ldf + col0 + c0 + q);
-              f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
-            }
+            const float4 bb = *reinterpret_cast<const float4*>(b0 + c0 + q);
+            float r[4] = {__uint_as_float(v[q]) + bb.x, __uint_as_float(v[q + 1]) + bb.y,
+                          __uint_as_float(v[q + 2]) + bb.z, __uint_as_float(v[q + 3]) + bb.w};
+            if (dual) {
+              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row_ok && c0 + q < nvalid) t = *reinterpret_cast<const float4*>(P.F + m * P.ldf + col0 + c0 + q);
+              const float4 b2 = *reinterpret_cast<const float4*>(b1 + c0 + q);
+              r[0] = fmaf(t.x, r[0] + 1.f, __uint_as_float(u[q]) + b2.x);
+              r[1] = fmaf(t.y, r[1] + 1.f, __uint_as_float(u[q + 1]) + b2.y);
+              r[2] = fmaf(t.z, r[2] + 1.f, __uint_as_float(u[q + 2]) + b2.z);
+              r[3] = fmaf(t.w, r[3] + 1.f, __uint_as_float(u[q + 3]) + b2.w);
+            } else if (P.act == PDF_ACT_RELU) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int n = c0 + q + e;
-              float r = __uint_as_float(v[q + e]) + __ldg(b0 + n);
-              if (dual) r = fmaf(f[e], r + 1.f, __uint_as_float(u[q + e]) + __ldg(b1 + n));
-              else if (P.act == PDF_ACT_RELU) r = fmaxf(r, 0.f);
-              else if (P.act == PDF_ACT_LEAKY01) r = r > 0.f ? r : 0.1f * r;
-              y[q + e] = (n < nvalid && row_ok) ? r : 0.f;
+              for (int e = 0; e < 4; ++e) r[e] = fmaxf(r[e], 0.f);
+            } else if (P.act == PDF_ACT_LEAKY01) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) r[e] = fmaxf(r[e], 0.1f * r[e]);
             }
+            if (!full) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) r[e] = (row_ok && c0 + q + e < nvalid) ? r[e] : 0.f;
+            }
+            y[q] = r[0]; y[q + 1] = r[1]; y[q + 2] = r[2]; y[q + 3] = r[3];
           }
           if (P.out_f32 != nullptr && row_ok) {
             float* o = P.out_f32 + m * P.ld_out + col0 + c0;
@@ -174,6 +195,18 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
               else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) if (c0 + q + e < nvalid) o[q + e] = y[q + e];
+              }
+            }
+          }
+          if (P.out_bf16 != nullptr && row_ok) {
+            uint16_t* o = P.out_bf16 + m * P.ld_bf16 + (col0 - P.bf16_col_off) + c0;
+#pragma unroll
+            for (int q = 0; q < 32; q += 8) {
+              if (c0 + q + 7 < nvalid) {
+                uint4 wv;
+                wv.x = pack_bf16(y[q], y[q + 1]); wv.y = pack_bf16(y[q + 2], y[q + 3]);
+                wv.z = pack_bf16(y[q + 4], y[q + 5]); wv.w = pack_bf16(y[q + 6], y[q + 7]);
+                *reinterpret_cast<uint4*>(o + q) = wv;
               }
             }
           }
@@ -319,8 +352,8 @@ extern "C" int pdf_rows_to_image(const float* X, int64_t ld, int64_t M, int col0
 extern "C" int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const void* n_img, int n_tiles, int n_kb,
                              int KB, int kb_split, int colmax, const float* bias0, const float* bias1, int act,
                              float* out_f32, int64_t ld_out, int64_t rows_valid, const float* F, int64_t ldf,
-                             void* out_img, int out_kb, const int32_t* tile_desc_host, float* out_max,
-                             int64_t ld_max, void* stream) {
+                             void* out_img, int out_kb, void* out_bf16, int64_t ld_bf16, int bf16_col_off,
+                             const int32_t* tile_desc_host, float* out_max, int64_t ld_max, void* stream) {
   using namespace pdf;
   if (m_tiles == 0 || n_tiles == 0) return PDF_OK;
   PDF_REQUIRE(m_img && n_img && bias0, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: null pointer");
@@ -334,17 +367,22 @@ extern "C" int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const voi
   P.bias0 = bias0; P.bias1 = bias1; P.act = act;
   P.out_f32 = out_f32; P.ld_out = ld_out; P.rows_valid = rows_valid; P.F = F; P.ldf = ldf;
   P.out_img = (uint8_t*)out_img; P.out_kb = out_kb; P.out_max = out_max; P.ld_max = ld_max;
+  P.out_bf16 = (uint16_t*)out_bf16; P.ld_bf16 = ld_bf16; P.bf16_col_off = bf16_col_off;
   if (colmax) {
     PDF_REQUIRE(out_max && kb_split == 0, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: COLMAX needs out_max and one accumulator");
   } else {
     PDF_REQUIRE(n_tiles <= G_MAX_NT && tile_desc_host, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: ROW mode needs <= %d N tiles and tile_desc", G_MAX_NT);
-    PDF_REQUIRE(out_f32 || out_img, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: no output");
+    PDF_REQUIRE(out_f32 || out_img || out_bf16, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: no output");
+    PDF_REQUIRE(!out_bf16 || ((ld_bf16 % 8) == 0 && (bf16_col_off % 4) == 0), PDF_ERR_BAD_ARG,
+                "pdf_gemm_bf16: bf16 rows need 16-byte aligned pitch");
     PDF_REQUIRE(kb_split == 0 || (F && bias1), PDF_ERR_BAD_ARG, "pdf_gemm_bf16: SFT mode needs F and bias1");
     for (int i = 0; i < n_tiles; ++i) {
       P.tile_col[i] = tile_desc_host[3 * i]; P.tile_nvalid[i] = tile_desc_host[3 * i + 1]; P.tile_okb[i] = tile_desc_host[3 * i + 2];
       PDF_REQUIRE(P.tile_nvalid[i] >= 0 && P.tile_nvalid[i] <= 128 && (P.tile_col[i] % 4) == 0, PDF_ERR_BAD_ARG,
                   "pdf_gemm_bf16: bad tile descriptor %d", i);
       PDF_REQUIRE(!out_img || P.tile_okb[i] + 2 <= out_kb, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: output image too narrow");
+      PDF_REQUIRE(!out_bf16 || ((P.tile_col[i] - bf16_col_off) % 8 == 0 && P.tile_nvalid[i] % 8 == 0), PDF_ERR_BAD_ARG,
+                  "pdf_gemm_bf16: bf16 row output needs 8-column aligned tiles");
     }
   }
   static bool configured = false;

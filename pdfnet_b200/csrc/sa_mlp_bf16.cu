@@ -90,9 +90,9 @@ __device__ __forceinline__ void epilogue_repack(uint32_t tmem_row, uint8_t* feat
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
-sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, const int32_t* __restrict__ idx,
-                  int n_centroids, const uint8_t* __restrict__ wpack, float* __restrict__ out, int64_t ld_out,
-                  int out_col0, int64_t n_tiles) {
+sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, const uint16_t* __restrict__ feat_bf16,
+                  const int32_t* __restrict__ idx, int n_centroids, const uint8_t* __restrict__ wpack,
+                  float* __restrict__ out, int64_t ld_out, int out_col0, int64_t n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_w = smem;
@@ -136,19 +136,30 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
 
   mbar_wait(smem_u32(&s_bar[0]), 0);                     // weights resident
 
-  for (int64_t t = (int64_t)blockIdx.x * Cfg::SLOTS + slot; t < n_tiles; t += (int64_t)gridDim.x * Cfg::SLOTS) {
+  // relative coordinates of this thread's row for a tile (fp32, exactly p_j - c_i as the reference)
+  auto load_geom = [&](int64_t t, float& rx, float& ry, float& rz) {
+    const int64_t b = t / tiles_per_cloud;
+    const int g0 = (int)(t % tiles_per_cloud) * 2;
+    const float* cloud = pts + b * n_src * ld_pts;
+    const int j = __ldg(idx + (b * n_centroids + g0) * 64 + p);
+    const float* src = cloud + (int64_t)j * ld_pts;
+    const float* cen = cloud + (int64_t)(g0 + (p >> 6)) * ld_pts;
+    rx = __fsub_rn(__ldg(src), __ldg(cen));
+    ry = __fsub_rn(__ldg(src + 1), __ldg(cen + 1));
+    rz = __fsub_rn(__ldg(src + 2), __ldg(cen + 2));
+  };
+  const int64_t t_first = (int64_t)blockIdx.x * Cfg::SLOTS + slot, t_step = (int64_t)gridDim.x * Cfg::SLOTS;
+  float rx = 0.f, ry = 0.f, rz = 0.f;
+  if (t_first < n_tiles) load_geom(t_first, rx, ry, rz);
+
+  for (int64_t t = t_first; t < n_tiles; t += t_step) {
     const int64_t b = t / tiles_per_cloud;
     const int g0 = (int)(t % tiles_per_cloud) * 2;
     const float* cloud = pts + b * n_src * ld_pts;
     const int32_t* tidx = idx + (b * n_centroids + g0) * 64;
 
-    // ---- gather: geometry/bias block (thread = row), feature block (warp per row) ----
+    // ---- gather: geometry/bias block (thread = row, prefetched one tile ahead) ----
     {
-      const int g = g0 + (p >> 6);
-      const int j = tidx[p];
-      const float* src = cloud + (int64_t)j * ld_pts;
-      const float* cen = cloud + (int64_t)g * ld_pts;
-      const float rx = __fsub_rn(src[0], cen[0]), ry = __fsub_rn(src[1], cen[1]), rz = __fsub_rn(src[2], cen[2]);
       const float hx = __uint_as_float(pack_bf16(rx, 0.f) << 16), hy = __uint_as_float(pack_bf16(ry, 0.f) << 16),
                   hz = __uint_as_float(pack_bf16(rz, 0.f) << 16);
       uint4 w;
@@ -160,19 +171,35 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
       *reinterpret_cast<uint4*>(my_aux + aux_off(p, 8)) = make_uint4(0, 0, 0, 0);
     }
     if (Cfg::CF > 0) {
-      // 128 feature floats per row at column 4 of the source row: one warp per row,
-      // lane l loads float4 #l (coalesced 512 B), stores 4 bf16 into the SW128 tile.
-      const int w4 = warp & 3;
-#pragma unroll 4
-      for (int r = 0; r < 32; ++r) {
-        const int row = w4 * 32 + r;
-        const int j = tidx[row];
-        const float4 f = __ldg(reinterpret_cast<const float4*>(cloud + (int64_t)j * ld_pts + 4) + lane);
-        uint2 w;
-        w.x = pack_bf16(f.x, f.y);
-        w.y = pack_bf16(f.z, f.w);
-        const int col = lane * 4;
-        *reinterpret_cast<uint2*>(my_feat + (col >> 6) * (128 * 128) + sw128_off(row, col & 63)) = w;
+      if (feat_bf16 != nullptr) {
+        // bf16 feature rows (256 B each): 16 consecutive threads copy one row with cp.async
+        // (LDGSTS, no register staging), 8 rows per step, straight into the SW128 tile.
+        const uint16_t* fcloud = feat_bf16 + b * n_src * (int64_t)Cfg::CF;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int row = i * 8 + (p >> 4), ch = p & 15;           // 16-byte chunk ch of row
+          const int j = __ldg(tidx + row);
+          const uint32_t dst = sa_feat + (ch >> 3) * (128 * 128) + sw128_off(row, (ch & 7) * 8);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(fcloud + (int64_t)j * Cfg::CF + ch * 8)
+                       : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      } else {
+        // fp32 source rows [xyz, pad, 128 features]: one warp per row, lane l loads float4 #l
+        // (coalesced 512 B) and stores 4 bf16 into the SW128 tile.
+        const int w4 = warp & 3;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const int row = w4 * 32 + r;
+          const int j = tidx[row];
+          const float4 f = __ldg(reinterpret_cast<const float4*>(cloud + (int64_t)j * ld_pts + 4) + lane);
+          uint2 w;
+          w.x = pack_bf16(f.x, f.y);
+          w.y = pack_bf16(f.z, f.w);
+          const int col = lane * 4;
+          *reinterpret_cast<uint2*>(my_feat + (col >> 6) * (128 * 128) + sw128_off(row, col & 63)) = w;
+        }
       }
     }
     fence_async_smem();
@@ -186,6 +213,7 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
                             idesc_bf16(128, Cfg::C1));
       commit(bar);
     }
+    if (t + t_step < n_tiles) load_geom(t + t_step, rx, ry, rz);   // in flight during the three MMA phases
     mbar_wait(bar, phase); phase ^= 1;
     fence_after_sync();
     epilogue_repack<Cfg::C1>(d1 + lane_off, my_feat, p);
@@ -297,8 +325,8 @@ static void pack_weights(const float* W1, const float* b1, const float* W2, cons
 }
 
 template <class Cfg>
-static int launch_sa(const float* pts, int64_t n_clouds, int n_src, int64_t ld_pts, const int32_t* idx,
-                     int n_centroids, const void* wpack, float* out, int64_t ld_out, int out_col0,
+static int launch_sa(const float* pts, int64_t n_clouds, int n_src, int64_t ld_pts, const void* feat_bf16,
+                     const int32_t* idx, int n_centroids, const void* wpack, float* out, int64_t ld_out, int out_col0,
                      cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
@@ -317,7 +345,8 @@ static int launch_sa(const float* pts, int64_t n_clouds, int n_src, int64_t ld_p
   int64_t grid = (n_tiles + Cfg::SLOTS - 1) / Cfg::SLOTS;
   if (grid > sms) grid = sms;
   sa_mlp_max_kernel<Cfg><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(
-      pts, n_src, ld_pts, idx, n_centroids, reinterpret_cast<const uint8_t*>(wpack), out, ld_out, out_col0, n_tiles);
+      pts, n_src, ld_pts, reinterpret_cast<const uint16_t*>(feat_bf16), idx, n_centroids,
+      reinterpret_cast<const uint8_t*>(wpack), out, ld_out, out_col0, n_tiles);
   return check_launch("pdf_sa_mlp_max_bf16");
 }
 
@@ -345,8 +374,9 @@ extern "C" int pdf_sa_pack_weights_host(const float* W1, const float* b1, const 
 }
 
 extern "C" int pdf_sa_mlp_max_bf16(const float* pts, int64_t n_clouds, int n_src, int64_t ld_pts, int c_in,
-                                   const int32_t* idx, int n_centroids, int k, const void* wpack, int c1, int c2,
-                                   int c3, float* out, int64_t ld_out, int out_col0, void* stream) {
+                                   const void* feat_bf16, const int32_t* idx, int n_centroids, int k,
+                                   const void* wpack, int c1, int c2, int c3, float* out, int64_t ld_out,
+                                   int out_col0, void* stream) {
   if (n_clouds == 0) return PDF_OK;
   PDF_REQUIRE(pts && idx && wpack && out, PDF_ERR_BAD_ARG, "pdf_sa_mlp_max_bf16: null pointer");
   PDF_REQUIRE(n_clouds >= 0 && n_src > 0 && n_centroids > 0 && out_col0 >= 0 && out_col0 <= 4, PDF_ERR_BAD_ARG,
@@ -358,12 +388,15 @@ extern "C" int pdf_sa_mlp_max_bf16(const float* pts, int64_t n_clouds, int n_src
   cudaStream_t s = (cudaStream_t)stream;
   if (c_in == 3 && c1 == 64 && c2 == 64 && c3 == 128) {
     PDF_REQUIRE(ld_pts >= 3, PDF_ERR_BAD_ARG, "pdf_sa_mlp_max_bf16: ld_pts too small");
-    return pdf::launch_sa<pdf::Sa1Cfg>(pts, n_clouds, n_src, ld_pts, idx, n_centroids, wpack, out, ld_out, out_col0, s);
+    return pdf::launch_sa<pdf::Sa1Cfg>(pts, n_clouds, n_src, ld_pts, nullptr, idx, n_centroids, wpack, out, ld_out,
+                                       out_col0, s);
   }
   if (c_in == 131 && c1 == 128 && c2 == 128 && c3 == 256) {
-    PDF_REQUIRE(ld_pts >= 132 && (ld_pts % 4) == 0, PDF_ERR_UNSUPPORTED,
-                "pdf_sa_mlp_max_bf16: level-2 source rows must be [xyz,pad,128 features] with pitch %% 4 == 0");
-    return pdf::launch_sa<pdf::Sa2Cfg>(pts, n_clouds, n_src, ld_pts, idx, n_centroids, wpack, out, ld_out, out_col0, s);
+    PDF_REQUIRE(feat_bf16 != nullptr ? ld_pts >= 3 : (ld_pts >= 132 && (ld_pts % 4) == 0), PDF_ERR_UNSUPPORTED,
+                "pdf_sa_mlp_max_bf16: level-2 source rows must be [xyz,pad,128 features] with pitch %% 4 == 0 "
+                "unless the features are given as bf16 rows");
+    return pdf::launch_sa<pdf::Sa2Cfg>(pts, n_clouds, n_src, ld_pts, feat_bf16, idx, n_centroids, wpack, out, ld_out,
+                                       out_col0, s);
   }
   pdf::set_error("pdf_sa_mlp_max_bf16: unsupported channel plan (%d,%d,%d,%d)", c_in, c1, c2, c3);
   return PDF_ERR_UNSUPPORTED;

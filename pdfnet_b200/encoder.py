@@ -283,14 +283,19 @@ class PointNet_Plus(nn.Module):
             h1img = u8(t1 * 2 * BLK)
             ops.gemm_bf16(c1img, t1, 1, tc["sft1_w0"], 1, 1, 1, tc["sft1_b0"], act=LEAKY, out_img=h1img, out_kb=2,
                           rows_valid=M1, tile_desc=[(0, 128, 0)])
+            # modulated features leave as bf16 rows (the level-2 gather copies them with cp.async);
+            # the xyz channels stay fp32 in x1 (they drive the level-2 neighbour search)
+            x1h = torch.empty((M1, 128), dtype=torch.bfloat16, device=dev)
             ops.gemm_bf16(h1img, t1, 2, tc["sft1_w1"], 1, 2, 2, tc["sft1_b1s"], kb_split=1, bias1=tc["sft1_b1h"],
-                          F=x1r, out_f32=x1r, rows_valid=M1, tile_desc=[(4, 128, 0)])
+                          F=x1r, out_bf16=x1h, bf16_col_off=4, rows_valid=M1, tile_desc=[(4, 128, 0)])
             ops.sft_xyz(c1r, tc["sft1_plain"], x1r)
         with stage("knn2"):
             idx2 = ops.knn_ball(x1, N2, K, self.ball_radius2)
         x2 = torch.empty((B, N2, 260), dtype=torch.float32, device=dev)
         with stage("sa2"):
-            self._sa(x1, idx2, "netR_2", f, x2, None)
+            (w1, _), (w2, _), (w3, _) = f["netR_2"]
+            ops.sa_mlp_max_bf16(x1, idx2, f["netR_2_pack"], w1.shape[1], w1.shape[0], w2.shape[0], w3.shape[0], x2, 4,
+                                feat_bf16=x1h.view(B, N1, 128))
         x2r = x2.view(M2, 260)
         four = [(0, 128, 0), (0, 128, 2), (0, 128, 4), (0, 128, 6)]
         with stage("sft2"):
@@ -391,8 +396,11 @@ class HandFusion(nn.Module):
     def mano_head_forward(self, x):
         """mano_head (:630-643) in eval mode: Linear+BN1d folded, ReLU, on the FFMA linear kernel."""
         m = self.mano_head
-        w1, b1 = _fold_bn_linear(m[0], m[1])
-        w2, b2 = _fold_bn_linear(m[3], m[4])
+        key = tuple((t.data_ptr(), t._version) for t in list(m.parameters()) + list(m.buffers()))
+        if getattr(self, "_mano_fold_key", None) != key:
+            self._mano_fold = _fold_bn_linear(m[0], m[1]) + _fold_bn_linear(m[3], m[4])
+            self._mano_fold_key = key
+        w1, b1, w2, b2 = self._mano_fold
         h = ops.linear(x, w1, b1, act=L.ACT_RELU)
         h = ops.linear(h, w2, b2, act=L.ACT_RELU)
         return ops.linear(h, m[6].weight.detach(), m[6].bias.detach())

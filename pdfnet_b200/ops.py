@@ -132,15 +132,17 @@ def sa_pack_weights(w1, b1, w2, b2, w3, b3):
     return buf
 
 
-def sa_mlp_max_bf16(pts, idx, wpack, c_in, c1, c2, c3, out, out_col0=0):
+def sa_mlp_max_bf16(pts, idx, wpack, c_in, c1, c2, c3, out, out_col0=0, feat_bf16=None):
     """Fused gather + 3-layer point-MLP + max over k on tcgen05 (see pdf_sa_mlp_max_bf16).
     pts fp32 [B,n_src,ld] contiguous, idx int32 [B,N1,k]; writes out[:, :, out_col0:out_col0+c3]."""
-    L.require_cuda(pts, idx, wpack, out)
+    L.require_cuda(pts, idx, wpack, out, feat_bf16)
     assert pts.dtype == torch.float32 and pts.is_contiguous() and idx.dtype == torch.int32 and idx.is_contiguous()
+    assert feat_bf16 is None or (feat_bf16.dtype == torch.bfloat16 and feat_bf16.is_contiguous()
+                                 and feat_bf16.shape[-1] == 128)
     assert out.dtype == torch.float32 and out.stride(2) == 1
     B, n_src, ld = pts.shape
     _, N1, k = idx.shape
-    L.call("pdf_sa_mlp_max_bf16", L.ptr(pts), B, n_src, ld, c_in, L.ptr(idx), N1, k, L.ptr(wpack), c1, c2, c3,
+    L.call("pdf_sa_mlp_max_bf16", L.ptr(pts), B, n_src, ld, c_in, L.ptr(feat_bf16), L.ptr(idx), N1, k, L.ptr(wpack), c1, c2, c3,
            L.ptr(out), out.stride(1), out_col0, L.stream())
     return out
 
@@ -174,9 +176,10 @@ def rows_to_image(x, col0, K, img=None, kb_total=None, kb0=0):
 
 
 def gemm_bf16(m_img, m_tiles, m_kb, n_img, n_tiles, n_kb, KB, bias0, kb_split=0, bias1=None, act=L.ACT_NONE,
-              out_f32=None, rows_valid=0, F=None, out_img=None, out_kb=0, tile_desc=None, out_max=None):
+              out_f32=None, rows_valid=0, F=None, out_img=None, out_kb=0, tile_desc=None, out_max=None,
+              out_bf16=None, bf16_col_off=0):
     """Streaming tcgen05 GEMM over tile images (see pdf_gemm_bf16)."""
-    L.require_cuda(m_img, n_img, bias0, bias1, out_f32, F, out_img, out_max)
+    L.require_cuda(m_img, n_img, bias0, bias1, out_f32, F, out_img, out_max, out_bf16)
     colmax = out_max is not None
     desc = None
     if tile_desc is not None:
@@ -184,7 +187,8 @@ def gemm_bf16(m_img, m_tiles, m_kb, n_img, n_tiles, n_kb, KB, bias0, kb_split=0,
         desc = (ctypes.c_int32 * len(flat))(*flat)
     L.call("pdf_gemm_bf16", L.ptr(m_img), m_tiles, m_kb, L.ptr(n_img), n_tiles, n_kb, KB, kb_split, 1 if colmax else 0,
            L.ptr(bias0), L.ptr(bias1), act, L.ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0, rows_valid,
-           L.ptr(F), F.stride(0) if F is not None else 0, L.ptr(out_img), out_kb,
+           L.ptr(F), F.stride(0) if F is not None else 0, L.ptr(out_img), out_kb, L.ptr(out_bf16),
+           out_bf16.stride(0) if out_bf16 is not None else 0, bf16_col_off,
            ctypes.cast(desc, ctypes.c_void_p) if desc is not None else None, L.ptr(out_max),
            out_max.stride(0) if colmax else 0, L.stream())
 
