@@ -253,23 +253,42 @@ def run_ours(args):
 
     # ---- end to end through the public API with HOST buffers ----
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
+    # The batch is cut into chunks: chunk i+1 crosses PCIe on a copy stream while chunk i computes.
+    n_chunks = max(1, min(args.e2e_chunks, B))
+    bounds = [parallel.shard_range(B, c, n_chunks) for c in range(n_chunks)]
+    copy_stream = torch.cuda.Stream(device=dev)
     out_host = {}
 
+    staging = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in pinned.items()}
+
     def e2e_step():
-        d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
-        fused, verts, joints = hot_path(d)
-        for name, t in (("fused", fused), ("verts", verts), ("joints", joints)):
-            if name not in out_host:
-                out_host[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-            out_host[name].copy_(t, non_blocking=True)
+        main = torch.cuda.current_stream()
+        copy_stream.wait_stream(main)                 # previous step has consumed the staging buffers
+        events = []
+        with torch.cuda.stream(copy_stream):
+            for lo, hi in bounds:
+                for k, v in pinned.items():
+                    staging[k][lo:hi].copy_(v[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                events.append(ev)
+        for (lo, hi), ev in zip(bounds, events):
+            main.wait_event(ev)
+            fused, verts, joints = hot_path({k: v[lo:hi] for k, v in staging.items()})
+            for name, t in (("fused", fused), ("verts", verts), ("joints", joints)):
+                if name not in out_host:
+                    out_host[name] = torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
+                out_host[name][lo:hi].copy_(t, non_blocking=True)
 
     ms_e2e = timed_loop(e2e_step, args.steps, args.warmup)
     torch.cuda.synchronize()
     d2h_bytes = sum(v.numel() * v.element_size() for v in out_host.values())
 
     # ---- per-stage timing (roofline of the dominant kernel), same inputs, L2 flushed ----
+    for _ in range(2):
+        hot_path(resident)
     profiling.enable(True)
-    for _ in range(max(3, min(args.steps, 10))):
+    for _ in range(max(5, min(args.steps, 11))):
         flush.fill_(1)
         hot_path(resident)
     stages = profiling.summary()
@@ -287,7 +306,7 @@ def run_ours(args):
         j = json.load(open(pk))
         peaks = {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops"], "source": "measured"}
     n_clouds = 2 * B
-    stage_ms = {k: t / c for k, (c, t) in stages.items()}
+    stage_ms = {k: t for k, (c, t) in stages.items()}
     flops = {"sa1": FLOP_SA1 * n_clouds, "sa2": FLOP_SA2 * n_clouds, "global_mlp": FLOP_GLOBAL * n_clouds,
              "sft1": FLOP_SFT1 * n_clouds, "sft2": FLOP_SFT2 * n_clouds}
     dom = max(flops, key=lambda k: stage_ms.get(k, 0.0))
@@ -317,8 +336,10 @@ def run_ours(args):
                    "randomness": "subset keys / permutations injected as inputs (reference uses np.random)"},
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e,
+                "chunks": n_chunks,
                 "note": "all hot-path inputs (depth, masks, K, fp32 feature pyramid, centre features, keys) copied "
-                        "from pinned host memory every step; fused features + MANO verts/joints copied back"},
+                        "from pinned host memory every step (chunked, copy stream overlapped with compute); fused "
+                        "features + MANO verts/joints copied back"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "stages_ms": stage_report, "stages_tflops": stage_tflops,
         "cpu_baseline": cpu_baseline,
@@ -339,6 +360,7 @@ def main():
     ap.add_argument("--frames", type=int, default=128, help="frames per GPU per step")
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--cpu-sample-frames", type=int, default=4)
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="H2D/compute overlap chunks in the e2e measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -207,12 +207,17 @@ int pdf_depth2pcl(const float* depth, const float* mask, const float* Kinv, cons
  * Inputs: root [n,3] and pose [n,45] axis-angle, shape [n,10], trans [n,3] or
  * null, scale [n] or null.  tip_idx_host: the 5 finger-tip vertex ids (:305-308).
  * center_idx < 0 disables centring (:313-316).  new_skel as :328-332.
+ * v_tpose (optional, may be null): blend-shaped rest vertices [n,778*3] computed beforehand as ONE
+ * dense GEMM over all hands (pdf_mano_pose_feature + pdf_linear_f32); when null the kernel
+ * evaluates the blend shapes itself.
  * Outputs v [n,778,3], j [n,21,3] (joints in the reference's new_order, :110-115). */
 int pdf_mano_lbs(const float* v_template, const float* shapedirs_t, const float* posedirs_t,
                  const float* j_template, const float* j_shapedirs, const float* weights_t,
                  const float* root, const float* pose, const float* shape, const float* trans,
                  const float* scale, int64_t n, const int32_t* tip_idx_host, int center_idx, int new_skel,
-                 float* v, float* j, void* stream);
+                 const float* v_tpose, float* v, float* j, void* stream);
+/* X[h] = [shape(10) | (rodrigues(pose_j) - I) for the 15 joints (135)], fp32 [n,145] (manolayer.py:274-281) */
+int pdf_mano_pose_feature(const float* pose, const float* shape, int64_t n, float* X, void* stream);
 
 /* Split_coeff (lib/models/hand3d/Mano_render.py:160-194, non-PCA) for one hand:
  * theta [n,ld_theta] (61 used columns starting at col0), index int64 [n], K [n,3,3];

@@ -47,7 +47,7 @@ __device__ __forceinline__ void sft0_apply(const float* __restrict__ P, const fl
 // point); the next PG_SPLIT blocks gather level 1, the last PG_SPLIT level 2.  Every thread keeps
 // PG_UNROLL independent scattered loads in flight (each one is a separate 32 B sector of an NCHW
 // plane), stores are coalesced ([cloud, point, channel], channel fastest).
-constexpr int PG_SPLIT = 8, PG_UNROLL = 8;
+constexpr int PG_SPLIT = 4, PG_UNROLL = 8;
 
 __device__ __forceinline__ void gather_level(const float* __restrict__ plane0, int C, int64_t HW, int R, int Rl,
                                              int div, const int64_t* __restrict__ ch, int n,
@@ -75,19 +75,45 @@ __device__ __forceinline__ void gather_level(const float* __restrict__ plane0, i
   }
 }
 
+// Plane-local variant for n % 32 == 0 and C % 32 == 0 (the reference shapes): a warp gathers a
+// 32-point x 32-channel tile with lanes = points, so every load instruction of the warp stays
+// inside ONE channel plane (one DRAM page neighbourhood, the hand's pixel window) instead of 32
+// different planes; the tile is transposed through shared memory so stores stay coalesced.
+__device__ __forceinline__ void gather_level_tiled(const float* __restrict__ plane0, int C, int64_t HW, int R, int Rl,
+                                                   int div, const int64_t* __restrict__ ch, int n,
+                                                   float* __restrict__ out, int part, float (*tile)[33]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int ct = C / 32, n_tiles = (n / 32) * ct;
+  for (int t = part * nwarps + warp; t < n_tiles; t += PG_SPLIT * nwarps) {
+    const int i0 = (t / ct) * 32, c0 = (t % ct) * 32;
+    const int pix = (int)ch[i0 + lane];
+    const float* src = plane0 + (int64_t)c0 * HW + ((pix / R / div) * Rl + (pix % R) / div);
+    float v[32];
+#pragma unroll
+    for (int cc = 0; cc < 32; ++cc) v[cc] = __ldg(src + (int64_t)cc * HW);
+#pragma unroll
+    for (int cc = 0; cc < 32; ++cc) tile[cc][lane] = v[cc];
+    __syncwarp();
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) out[(int64_t)(i0 + r) * C + c0 + lane] = tile[lane][r];
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(256)
 pyramid_gather_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ choose, int clouds_per_frame,
                       int n_points, int n1, int n2, int R,
                       const float* __restrict__ l0, const float* __restrict__ l1, int C1,
                       const float* __restrict__ l2, int C2, const float* __restrict__ sft0,
                       float* __restrict__ pts0, float* __restrict__ cond1, float* __restrict__ cond2) {
+  __shared__ float s_tile[8][32][33];
   const int64_t b = blockIdx.x;
   const int64_t f = b / clouds_per_frame;
   const int64_t* ch = choose + b * n_points;
   const int R2 = R / 2, R4 = R / 4;
   const int64_t RR = (int64_t)R * R, HW2 = (int64_t)R2 * R2, HW4 = (int64_t)R4 * R4;
   if (blockIdx.y == 0) {
-    __shared__ float P[48];
+    float* P = &s_tile[0][0][0];
     if (threadIdx.x < 48) P[threadIdx.x] = sft0[threadIdx.x];
     __syncthreads();
     const float* base = l0 + f * 3 * RR;
@@ -104,9 +130,15 @@ pyramid_gather_kernel(const float* __restrict__ xyz, const int64_t* __restrict__
       for (int c = 0; c < 3; ++c) pts0[(b * n_points + i) * 3 + c] = p[c];
     }
   } else if (blockIdx.y <= PG_SPLIT) {
-    gather_level(l1 + f * C1 * HW2, C1, HW2, R, R2, 2, ch, n1, cond1 + b * n1 * C1, blockIdx.y - 1);
+    const int part = blockIdx.y - 1;
+    if ((n1 & 31) == 0 && (C1 & 31) == 0)
+      gather_level_tiled(l1 + f * C1 * HW2, C1, HW2, R, R2, 2, ch, n1, cond1 + b * n1 * C1, part, s_tile[threadIdx.x >> 5]);
+    else gather_level(l1 + f * C1 * HW2, C1, HW2, R, R2, 2, ch, n1, cond1 + b * n1 * C1, part);
   } else {
-    gather_level(l2 + f * C2 * HW4, C2, HW4, R, R4, 4, ch, n2, cond2 + b * n2 * C2, blockIdx.y - 1 - PG_SPLIT);
+    const int part = blockIdx.y - 1 - PG_SPLIT;
+    if ((n2 & 31) == 0 && (C2 & 31) == 0)
+      gather_level_tiled(l2 + f * C2 * HW4, C2, HW4, R, R4, 4, ch, n2, cond2 + b * n2 * C2, part, s_tile[threadIdx.x >> 5]);
+    else gather_level(l2 + f * C2 * HW4, C2, HW4, R, R4, 4, ch, n2, cond2 + b * n2 * C2, part);
   }
 }
 

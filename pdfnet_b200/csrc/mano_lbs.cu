@@ -1,4 +1,4 @@
-// MANO linear blend skinning, one hand per CTA, fp32 end to end (the 1e-5 m
+// MANO linear blend skinning, four hands per CTA, fp32 end to end (the 1e-5 m
 // tolerance rules out bf16 bases, SURVEY.md section 7 "LBS precision").
 // The whole op is 1.17 MFLOP per hand and a 16-step dependent chain: it is
 // latency bound, so the kernel keeps everything of one hand in shared memory and
@@ -14,31 +14,44 @@ __constant__ int c_new_order[21] = {0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18,
 
 struct Tips { int v[5]; };
 
+// HPC hands per CTA (1: the kernel is latency bound; the blend-shape contraction can be taken out of
+// it entirely, see v_tpose_in / pdf_mano_pose_feature).
+constexpr int HPC = 1;
+
 __global__ void __launch_bounds__(256)
 mano_lbs_kernel(const float* __restrict__ v_template, const float* __restrict__ shapedirs_t,
                 const float* __restrict__ posedirs_t, const float* __restrict__ j_template,
                 const float* __restrict__ j_shapedirs, const float* __restrict__ weights_t,
                 const float* __restrict__ root, const float* __restrict__ pose, const float* __restrict__ shape,
-                const float* __restrict__ trans, const float* __restrict__ scale, Tips tips, int center_idx,
-                int new_skel, float* __restrict__ v_out, float* __restrict__ j_out) {
-  __shared__ float s_aa[48];          // axis-angle: root + 15 joints
-  __shared__ float s_beta[10];
-  __shared__ float s_R[16][9];
-  __shared__ float s_pf[135];         // pose feature R - I
-  __shared__ float s_jt[16][3];       // rest joints
-  __shared__ float s_G[16][12];       // global 3x4 transforms
-  __shared__ float s_v[NE];           // v_tpose, then posed vertices
-  __shared__ float s_j[21][3];
-  const int64_t h = blockIdx.x;
+                const float* __restrict__ trans, const float* __restrict__ scale, int64_t n_hands, Tips tips,
+                int center_idx, int new_skel, const float* __restrict__ v_tpose_in, float* __restrict__ v_out,
+                float* __restrict__ j_out) {
+  __shared__ float s_aa[HPC][48];          // axis-angle: root + 15 joints
+  __shared__ float s_beta[HPC][10];
+  __shared__ float s_R[HPC][16][9];
+  __shared__ float s_pf[HPC][135];         // pose feature R - I
+  __shared__ float s_jt[HPC][16][3];       // rest joints
+  __shared__ float s_G[HPC][16][12];       // global 3x4 transforms
+  __shared__ float s_v[HPC][NE];           // v_tpose, then posed vertices
+  __shared__ float s_j[HPC][21][3];
+  const int64_t h0 = (int64_t)blockIdx.x * HPC;
+  const int nh = (int)min((int64_t)HPC, n_hands - h0);
   const int tid = threadIdx.x;
 
-  if (tid < 3) s_aa[tid] = root[h * 3 + tid];
-  else if (tid < 48) s_aa[tid] = pose[h * 45 + tid - 3];
-  else if (tid < 58) s_beta[tid - 48] = shape[h * 10 + tid - 48];
+  for (int i = tid; i < HPC * 58; i += 256) {
+    const int hh = i / 58, k = i % 58;
+    float val = 0.f;
+    if (hh < nh) {
+      const int64_t h = h0 + hh;
+      val = k < 3 ? root[h * 3 + k] : (k < 48 ? pose[h * 45 + k - 3] : shape[h * 10 + k - 48]);
+    }
+    if (k < 48) s_aa[hh][k] = val; else s_beta[hh][k - 48] = val;
+  }
   __syncthreads();
 
-  if (tid < 16) {                     // rodrigues_batch, manolayer.py:32-48
-    const float ax = s_aa[tid * 3], ay = s_aa[tid * 3 + 1], az = s_aa[tid * 3 + 2];
+  if (tid < HPC * 16) {                     // rodrigues_batch, manolayer.py:32-48
+    const int hh = tid >> 4, jn = tid & 15;
+    const float ax = s_aa[hh][jn * 3], ay = s_aa[hh][jn * 3 + 1], az = s_aa[hh][jn * 3 + 2];
     const float angle = sqrtf(ax * ax + ay * ay + az * az) + 1e-8f;
     const float x = ax / angle, y = ay / angle, z = az / angle;
     const float sn = sinf(angle), cs = cosf(angle);
@@ -50,57 +63,71 @@ mano_lbs_kernel(const float* __restrict__ v_template, const float* __restrict__ 
       for (int c = 0; c < 3; ++c) {
         const float ll = L[r * 3] * L[c] + L[r * 3 + 1] * L[3 + c] + L[r * 3 + 2] * L[6 + c];
         const float v = (r == c ? 1.f : 0.f) + sn * L[r * 3 + c] + oc * ll;
-        s_R[tid][r * 3 + c] = v;
-        if (tid > 0) s_pf[(tid - 1) * 9 + r * 3 + c] = v - (r == c ? 1.f : 0.f);
+        s_R[hh][jn][r * 3 + c] = v;
+        if (jn > 0) s_pf[hh][(jn - 1) * 9 + r * 3 + c] = v - (r == c ? 1.f : 0.f);
       }
-  } else if (tid >= 32 && tid < 80) { // rest joints = J_regressor (v_template + shapedirs beta)
-    const int e = tid - 32;
+  } else if (tid >= 64 && tid < 64 + HPC * 48) {   // rest joints = J_regressor (v_template + shapedirs beta)
+    const int hh = (tid - 64) / 48, e = (tid - 64) % 48;
     float a = j_template[e];
 #pragma unroll
-    for (int k = 0; k < 10; ++k) a = fmaf(j_shapedirs[e * 10 + k], s_beta[k], a);
-    s_jt[e / 3][e % 3] = a;
+    for (int k = 0; k < 10; ++k) a = fmaf(j_shapedirs[e * 10 + k], s_beta[hh][k], a);
+    s_jt[hh][e / 3][e % 3] = a;
   }
   __syncthreads();
 
   // blend shapes: v_tpose = v_template + shapedirs beta + posedirs (R - I)   (:274-282)
+  if (v_tpose_in != nullptr) {              // contraction already done as one [n,145]x[145,2334] GEMM
+    for (int i = tid; i < nh * NE; i += 256) s_v[i / NE][i % NE] = v_tpose_in[h0 * NE + i];
+  } else
   for (int e = tid; e < NE; e += 256) {
-    float a = 0.f;
+    float a[HPC], p0[HPC], p1[HPC];
 #pragma unroll
-    for (int k = 0; k < 10; ++k) a = fmaf(__ldg(shapedirs_t + k * NE + e), s_beta[k], a);
-    a += __ldg(v_template + e);
-    float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-#pragma unroll 9
-    for (int k = 0; k < 135; k += 3) {
-      p0 = fmaf(__ldg(posedirs_t + (k + 0) * NE + e), s_pf[k + 0], p0);
-      p1 = fmaf(__ldg(posedirs_t + (k + 1) * NE + e), s_pf[k + 1], p1);
-      p2 = fmaf(__ldg(posedirs_t + (k + 2) * NE + e), s_pf[k + 2], p2);
+    for (int hh = 0; hh < HPC; ++hh) { a[hh] = 0.f; p0[hh] = 0.f; p1[hh] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      const float w = __ldg(shapedirs_t + k * NE + e);
+#pragma unroll
+      for (int hh = 0; hh < HPC; ++hh) a[hh] = fmaf(w, s_beta[hh][k], a[hh]);
     }
-    s_v[e] = a + ((p0 + p1) + p2);
+    const float vt = __ldg(v_template + e);
+#pragma unroll 5
+    for (int k = 0; k < 134; k += 2) {
+      const float w0 = __ldg(posedirs_t + k * NE + e), w1 = __ldg(posedirs_t + (k + 1) * NE + e);
+#pragma unroll
+      for (int hh = 0; hh < HPC; ++hh) {
+        p0[hh] = fmaf(w0, s_pf[hh][k], p0[hh]);
+        p1[hh] = fmaf(w1, s_pf[hh][k + 1], p1[hh]);
+      }
+    }
+    const float wl = __ldg(posedirs_t + 134 * NE + e);
+#pragma unroll
+    for (int hh = 0; hh < HPC; ++hh) s_v[hh][e] = (a[hh] + vt) + (fmaf(wl, s_pf[hh][134], p0[hh]) + p1[hh]);
   }
 
-  // kinematic chain (:284-293): G_i = G_parent * [R_i | (I - R_i) j_i], warp 0 only
-  if (tid < 32) {
-    const int r = tid / 4, c = tid % 4;           // lanes 0..11 hold one 3x4 entry
+  // kinematic chain (:284-293): G_i = G_parent * [R_i | (I - R_i) j_i]; warp hh handles hand hh
+  if (tid < HPC * 32) {
+    const int hh = tid >> 5, l = tid & 31;
+    const int r = l / 4, c = l % 4;               // lanes 0..11 hold one 3x4 entry
     for (int i = 0; i < 16; ++i) {
-      if (tid < 12) {
-        float l[4];                               // column c of the local transform (rows 0..2)
+      if (l < 12) {
+        float lc[3];                              // column c of the local transform (rows 0..2)
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          if (c < 3) l[k] = s_R[i][k * 3 + c];
+          if (c < 3) lc[k] = s_R[hh][i][k * 3 + c];
           else {
             float t = 0.f;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) t = fmaf(((k == q) ? 1.f : 0.f) - s_R[i][k * 3 + q], s_jt[i][q], t);
-            l[k] = t;
+            for (int q = 0; q < 3; ++q) t = fmaf(((k == q) ? 1.f : 0.f) - s_R[hh][i][k * 3 + q], s_jt[hh][i][q], t);
+            lc[k] = t;
           }
         }
         float g;
-        if (i == 0) g = l[r];
+        if (i == 0) g = lc[r];
         else {
-          const float* P = s_G[c_parent[i]];
-          g = P[r * 4] * l[0] + P[r * 4 + 1] * l[1] + P[r * 4 + 2] * l[2] + (c == 3 ? P[r * 4 + 3] : 0.f);
+          const float* P = s_G[hh][c_parent[i]];
+          g = P[r * 4] * lc[0] + P[r * 4 + 1] * lc[1] + P[r * 4 + 2] * lc[2] + (c == 3 ? P[r * 4 + 3] : 0.f);
         }
-        s_G[i][r * 4 + c] = g;
+        s_G[hh][i][r * 4 + c] = g;
       }
       __syncwarp();
     }
@@ -109,70 +136,103 @@ mano_lbs_kernel(const float* __restrict__ v_template, const float* __restrict__ 
 
   // skinning (:301-304)
   for (int v = tid; v < NV; v += 256) {
-    float g[12];
+    float w[16];
 #pragma unroll
-    for (int q = 0; q < 12; ++q) g[q] = 0.f;
+    for (int jn = 0; jn < 16; ++jn) w[jn] = __ldg(weights_t + jn * NV + v);
+#pragma unroll 1
+    for (int hh = 0; hh < HPC; ++hh) {
+      float g[12];
 #pragma unroll
-    for (int jn = 0; jn < 16; ++jn) {
-      const float w = __ldg(weights_t + jn * NV + v);
+      for (int q = 0; q < 12; ++q) g[q] = 0.f;
 #pragma unroll
-      for (int q = 0; q < 12; ++q) g[q] = fmaf(w, s_G[jn][q], g[q]);
+      for (int jn = 0; jn < 16; ++jn)
+#pragma unroll
+        for (int q = 0; q < 12; ++q) g[q] = fmaf(w[jn], s_G[hh][jn][q], g[q]);
+      const float x = s_v[hh][v * 3], y = s_v[hh][v * 3 + 1], z = s_v[hh][v * 3 + 2];
+      s_v[hh][v * 3] = g[0] * x + g[1] * y + g[2] * z + g[3];
+      s_v[hh][v * 3 + 1] = g[4] * x + g[5] * y + g[6] * z + g[7];
+      s_v[hh][v * 3 + 2] = g[8] * x + g[9] * y + g[10] * z + g[11];
     }
-    const float x = s_v[v * 3], y = s_v[v * 3 + 1], z = s_v[v * 3 + 2];
-    const float ox = g[0] * x + g[1] * y + g[2] * z + g[3];
-    const float oy = g[4] * x + g[5] * y + g[6] * z + g[7];
-    const float oz = g[8] * x + g[9] * y + g[10] * z + g[11];
-    s_v[v * 3] = ox; s_v[v * 3 + 1] = oy; s_v[v * 3 + 2] = oz;
   }
   __syncthreads();
 
   // joints: 16 posed joints + 5 tips, reordered (:295-311)
-  if (tid < 21 * 3) {
-    const int jo = tid / 3, c = tid % 3;
+  for (int i = tid; i < HPC * 63; i += 256) {
+    const int hh = i / 63, jo = (i % 63) / 3, c = i % 3;
     const int src = c_new_order[jo];
     float val;
-    if (src == 0) val = s_jt[0][c];
+    if (src == 0) val = s_jt[hh][0][c];
     else if (src < 16) {
-      const float* P = s_G[c_parent[src]];
-      val = P[c * 4] * s_jt[src][0] + P[c * 4 + 1] * s_jt[src][1] + P[c * 4 + 2] * s_jt[src][2] + P[c * 4 + 3];
-    } else val = s_v[tips.v[src - 16] * 3 + c];
-    s_j[jo][c] = val;
+      const float* P = s_G[hh][c_parent[src]];
+      val = P[c * 4] * s_jt[hh][src][0] + P[c * 4 + 1] * s_jt[hh][src][1] + P[c * 4 + 2] * s_jt[hh][src][2] + P[c * 4 + 3];
+    } else val = s_v[hh][tips.v[src - 16] * 3 + c];
+    s_j[hh][jo][c] = val;
   }
   __syncthreads();
 
-  float cen[3] = {0.f, 0.f, 0.f};
-  if (center_idx >= 0) { cen[0] = s_j[center_idx][0]; cen[1] = s_j[center_idx][1]; cen[2] = s_j[center_idx][2]; }
-  const float sc = scale ? scale[h] : 1.f;
-  float tr[3] = {0.f, 0.f, 0.f};
-  if (trans) { tr[0] = trans[h * 3]; tr[1] = trans[h * 3 + 1]; tr[2] = trans[h * 3 + 2]; }
-  __syncthreads();
-  for (int e = tid; e < NE; e += 256) {
-    float val = s_v[e];
-    if (center_idx >= 0) val = val - cen[e % 3];
-    if (scale) val = val * sc;
-    if (trans) val = val + tr[e % 3];
-    s_v[e] = val;
-    v_out[h * NE + e] = val;
-  }
-  if (tid < 63) {
-    float val = s_j[tid / 3][tid % 3];
-    if (center_idx >= 0) val = val - cen[tid % 3];
-    if (scale) val = val * sc;
-    if (trans) val = val + tr[tid % 3];
-    s_j[tid / 3][tid % 3] = val;
-  }
-  __syncthreads();
-  if (tid < 63) {
-    const int jo = tid / 3, c = tid % 3;
-    float val = s_j[jo][c];
-    if (new_skel) {                                 // :328-332
-      if (jo == 5) val = (s_v[63 * 3 + c] + s_v[144 * 3 + c]) / 2.f;
-      else if (jo == 9) val = (s_v[271 * 3 + c] + s_v[220 * 3 + c]) / 2.f;
-      else if (jo == 13) val = (s_v[148 * 3 + c] + s_v[290 * 3 + c]) / 2.f;
-      else if (jo == 17) val = (s_v[770 * 3 + c] + s_v[83 * 3 + c]) / 2.f;
+  for (int hh = 0; hh < nh; ++hh) {
+    const int64_t h = h0 + hh;
+    float cen[3] = {0.f, 0.f, 0.f};
+    if (center_idx >= 0) { cen[0] = s_j[hh][center_idx][0]; cen[1] = s_j[hh][center_idx][1]; cen[2] = s_j[hh][center_idx][2]; }
+    const float sc = scale ? scale[h] : 1.f;
+    float tr[3] = {0.f, 0.f, 0.f};
+    if (trans) { tr[0] = trans[h * 3]; tr[1] = trans[h * 3 + 1]; tr[2] = trans[h * 3 + 2]; }
+    __syncthreads();
+    for (int e = tid; e < NE; e += 256) {
+      float val = s_v[hh][e];
+      if (center_idx >= 0) val = val - cen[e % 3];
+      if (scale) val = val * sc;
+      if (trans) val = val + tr[e % 3];
+      s_v[hh][e] = val;
+      v_out[h * NE + e] = val;
     }
-    j_out[h * 63 + tid] = val;
+    if (tid < 63) {
+      float val = s_j[hh][tid / 3][tid % 3];
+      if (center_idx >= 0) val = val - cen[tid % 3];
+      if (scale) val = val * sc;
+      if (trans) val = val + tr[tid % 3];
+      s_j[hh][tid / 3][tid % 3] = val;
+    }
+    __syncthreads();
+    if (tid < 63) {
+      const int jo = tid / 3, c = tid % 3;
+      float val = s_j[hh][jo][c];
+      if (new_skel) {                                 // :328-332
+        if (jo == 5) val = (s_v[hh][63 * 3 + c] + s_v[hh][144 * 3 + c]) / 2.f;
+        else if (jo == 9) val = (s_v[hh][271 * 3 + c] + s_v[hh][220 * 3 + c]) / 2.f;
+        else if (jo == 13) val = (s_v[hh][148 * 3 + c] + s_v[hh][290 * 3 + c]) / 2.f;
+        else if (jo == 17) val = (s_v[hh][770 * 3 + c] + s_v[hh][83 * 3 + c]) / 2.f;
+      }
+      j_out[h * 63 + tid] = val;
+    }
   }
+}
+
+// Blend-shape coefficients of every hand: X[h] = [beta(10) | (R_1..R_15 - I)(135)]  (:274-281), so that
+// v_tpose = X * [shapedirs | posedirs]^T + v_template is a single dense GEMM over all hands.
+__global__ void mano_pose_feature_kernel(const float* __restrict__ pose, const float* __restrict__ shape,
+                                         int64_t n, float* __restrict__ X) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * 16) return;
+  const int64_t h = i >> 4;
+  const int jn = (int)(i & 15);
+  float* x = X + h * 145;
+  if (jn == 0) {
+    for (int k = 0; k < 10; ++k) x[k] = shape[h * 10 + k];
+    return;
+  }
+  const float ax = pose[h * 45 + (jn - 1) * 3], ay = pose[h * 45 + (jn - 1) * 3 + 1], az = pose[h * 45 + (jn - 1) * 3 + 2];
+  const float angle = sqrtf(ax * ax + ay * ay + az * az) + 1e-8f;
+  const float xx = ax / angle, yy = ay / angle, zz = az / angle;
+  const float sn = sinf(angle), oc = 1.f - cosf(angle);
+  const float L[9] = {0.f, -zz, yy, zz, 0.f, -xx, -yy, xx, 0.f};
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float ll = L[r * 3] * L[c] + L[r * 3 + 1] * L[3 + c] + L[r * 3 + 2] * L[6 + c];
+      x[10 + (jn - 1) * 9 + r * 3 + c] = ((r == c ? 1.f : 0.f) + sn * L[r * 3 + c] + oc * ll) - (r == c ? 1.f : 0.f);
+    }
 }
 
 }  // namespace pdf
@@ -181,7 +241,7 @@ extern "C" int pdf_mano_lbs(const float* v_template, const float* shapedirs_t, c
                             const float* j_template, const float* j_shapedirs, const float* weights_t,
                             const float* root, const float* pose, const float* shape, const float* trans,
                             const float* scale, int64_t n, const int32_t* tip_idx_host, int center_idx,
-                            int new_skel, float* v, float* j, void* stream) {
+                            int new_skel, const float* v_tpose, float* v, float* j, void* stream) {
   PDF_REQUIRE(v_template && shapedirs_t && posedirs_t && j_template && j_shapedirs && weights_t, PDF_ERR_BAD_ARG,
               "pdf_mano_lbs: null table pointer");
   if (n == 0) return PDF_OK;
@@ -193,8 +253,15 @@ extern "C" int pdf_mano_lbs(const float* v_template, const float* shapedirs_t, c
     tips.v[i] = tip_idx_host[i];
   }
   if (n == 0) return PDF_OK;
-  pdf::mano_lbs_kernel<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(
-      v_template, shapedirs_t, posedirs_t, j_template, j_shapedirs, weights_t, root, pose, shape, trans, scale, tips,
-      center_idx, new_skel, v, j);
+  pdf::mano_lbs_kernel<<<(unsigned)((n + pdf::HPC - 1) / pdf::HPC), 256, 0, (cudaStream_t)stream>>>(
+      v_template, shapedirs_t, posedirs_t, j_template, j_shapedirs, weights_t, root, pose, shape, trans, scale, n, tips,
+      center_idx, new_skel, v_tpose, v, j);
   return pdf::check_launch("pdf_mano_lbs");
+}
+
+extern "C" int pdf_mano_pose_feature(const float* pose, const float* shape, int64_t n, float* X, void* stream) {
+  if (n == 0) return PDF_OK;
+  PDF_REQUIRE(pose && shape && X, PDF_ERR_BAD_ARG, "pdf_mano_pose_feature: null pointer");
+  pdf::mano_pose_feature_kernel<<<(unsigned)((n * 16 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(pose, shape, n, X);
+  return pdf::check_launch("pdf_mano_pose_feature");
 }

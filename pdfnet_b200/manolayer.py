@@ -75,6 +75,8 @@ def kernel_tables(v_template, shapedirs, posedirs, J_regressor, weights, device)
         j_template=(Jr @ vt).reshape(-1).float(),
         j_shapedirs=torch.einsum("jv,vck->jck", Jr, sd).reshape(48, 10).contiguous().float(),
         weights_t=weights.float().reshape(778, 16).t().contiguous(),
+        # [2334, 145] = [shapedirs | posedirs]: the blend shapes of a batch of hands are one GEMM
+        blend_w=torch.cat([sd.reshape(2334, 10).float(), posedirs.float().reshape(2334, 135)], 1).contiguous(),
     )
     return {k: v.contiguous().to(device) for k, v in t.items()}
 

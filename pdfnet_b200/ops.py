@@ -242,10 +242,17 @@ def mano_lbs(tables, root, pose, shape, trans, scale, tips, center_idx, new_skel
     v = torch.empty((n, 778, 3), dtype=torch.float32, device=root.device)
     j = torch.empty((n, 21, 3), dtype=torch.float32, device=root.device)
     tip_arr = (ctypes.c_int32 * 5)(*[int(t) for t in tips])
+    v_tpose = None
+    if n >= 16 and "blend_w" in tables:
+        # blend shapes of all hands as one dense fp32 GEMM [n,145] x [145,2334] (+ v_template as bias)
+        X = torch.empty((n, 145), dtype=torch.float32, device=root.device)
+        L.call("pdf_mano_pose_feature", L.ptr(pose), L.ptr(shape), n, L.ptr(X), L.stream())
+        v_tpose = linear(X, tables["blend_w"], tables["v_template"])
     L.call("pdf_mano_lbs", L.ptr(tables["v_template"]), L.ptr(tables["shapedirs_t"]), L.ptr(tables["posedirs_t"]),
            L.ptr(tables["j_template"]), L.ptr(tables["j_shapedirs"]), L.ptr(tables["weights_t"]), L.ptr(root),
            L.ptr(pose), L.ptr(shape), L.ptr(trans), L.ptr(scale), n, ctypes.cast(tip_arr, ctypes.c_void_p),
-           -1 if center_idx is None else int(center_idx), 1 if new_skel else 0, L.ptr(v), L.ptr(j), L.stream())
+           -1 if center_idx is None else int(center_idx), 1 if new_skel else 0, L.ptr(v_tpose), L.ptr(v), L.ptr(j),
+           L.stream())
     return v, j
 
 

@@ -3,7 +3,7 @@
 Disabled by default: ``stage(name)`` is then a no-op context manager.  When enabled,
 each stage records a start/stop event pair on torch's current stream (the stream the
 C-ABI kernels are enqueued on); ``summary()`` synchronises once and returns
-{name: (calls, total_ms)}.
+{name: (calls, median_ms)}.
 """
 import contextlib
 
@@ -34,10 +34,14 @@ def stage(name):
 
 
 def summary():
+    """{stage: (calls, median_ms)} — the median is robust against one-off allocator / first-touch stalls."""
     torch.cuda.synchronize()
-    out = {}
+    per = {}
     for name, a, b in _events:
-        c, t = out.get(name, (0, 0.0))
-        out[name] = (c + 1, t + a.elapsed_time(b))
+        per.setdefault(name, []).append(a.elapsed_time(b))
     _events.clear()
+    out = {}
+    for name, ts in per.items():
+        ts.sort()
+        out[name] = (len(ts), ts[len(ts) // 2])
     return out
