@@ -56,9 +56,9 @@ int64_t pdf_launch_count(void);
  * replaced by the centroid's own index.  Centroids are points 0..n_centroids-1.
  * xyz element (cloud b, point j, channel c) is xyz[b*stride_cloud + j*stride_point
  * + c*stride_ch] so both [B,N,C] and channel-major [B,C,N] inputs work.
- * idx_out: int32 [n_clouds, n_centroids, k], each group in ascending point order,
- * exact distance ties at the k-th neighbour resolved towards the lower index.
- * Supported: n_points in [k, 1024] and a multiple of 32, k <= 128. */
+ * idx_out: int32 [n_clouds, n_centroids, k]; the order inside a group is unspecified (as with the
+ * reference's topk(sorted=False)) but deterministic; exact distance ties at the k-th neighbour
+ * are resolved towards the lower index.  Supported: k <= n_points <= 1024, r2 >= 0. */
 int pdf_knn_ball(const float* xyz, int64_t n_clouds, int n_points, int n_centroids, int k, float r2,
                  int64_t stride_cloud, int64_t stride_point, int64_t stride_ch,
                  int32_t* idx_out, void* stream);

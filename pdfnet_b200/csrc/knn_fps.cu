@@ -6,23 +6,39 @@
 namespace pdf {
 
 // ---------------------------------------------------------------------------------
-// kNN + ball mask.  One warp per centroid; lane l owns points j = 32 t + l.
-// The k-th smallest distance is found by a bitwise radix descent over the fp32 bit
-// pattern (distances are >= 0, so unsigned order == float order); one
-// redux.sync per bit, early exit when a prefix splits off exactly k points.
+// kNN + ball mask.  One warp per centroid; lane l owns the 32 points j = 32 t + l.
+// Selection of the k smallest distances is a BIT-SLICED radix descent: the 32 distance
+// bit patterns of a lane (non-negative floats order as unsigned integers) are transposed
+// in registers into 31 bit planes (plane[b] bit t = bit b of d[t]); per bit the lane's
+// contribution to "how many still-active candidates have a 0 here" is one LOP3 + POPC,
+// summed across the warp with one redux.sync.  ~8 instructions per bit instead of one
+// compare per point per bit.  Ties at the k-th distance go to the lowest index.
 // ---------------------------------------------------------------------------------
-template <int T>
+__device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
+  // Hacker's Delight 7-3: afterwards a[r] bit c == old a[31-c] bit (31-r)
+  uint32_t m = 0x0000FFFFu;
+#pragma unroll
+  for (int j = 16; j != 0; j >>= 1, m ^= (m << j)) {
+#pragma unroll
+    for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
+      const uint32_t t = (a[k] ^ (a[k + j] >> j)) & m;
+      a[k] ^= t;
+      a[k + j] ^= (t << j);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256, 2)
 knn_ball_kernel(const float* __restrict__ xyz, int n_points, int n_centroids, int k, float r2,
                 int64_t stride_cloud, int64_t stride_point, int64_t stride_ch,
                 int32_t* __restrict__ idx_out, int chunks_per_cloud, int centroids_per_cta) {
-  constexpr int NP = T * 32;
+  constexpr int NP = 1024;
   __shared__ float sx[NP], sy[NP], sz[NP];
   const int b = blockIdx.x / chunks_per_cloud;
   const int chunk = blockIdx.x % chunks_per_cloud;
   const float* base = xyz + (int64_t)b * stride_cloud;
   for (int j = threadIdx.x; j < NP; j += blockDim.x) {
-    float x = __int_as_float(0x7f800000), y = x, z = x;   // padding: +inf, never selected
+    float x = 0.f, y = 0.f, z = 0.f;
     if (j < n_points) {
       const float* p = base + (int64_t)j * stride_point;
       x = p[0]; y = p[stride_ch]; z = p[2 * stride_ch];
@@ -35,72 +51,61 @@ knn_ball_kernel(const float* __restrict__ xyz, int n_points, int n_centroids, in
   const unsigned lt_mask = (1u << lane) - 1u;
   const int c_begin = chunk * centroids_per_cta;
   const int c_end = min(n_centroids, c_begin + centroids_per_cta);
+  const uint32_t r2b = __float_as_uint(fmaxf(r2, 0.f));
+  // bit t set <=> point 32 t + lane exists
+  uint32_t valid = 0;
+#pragma unroll
+  for (int t = 0; t < 32; ++t) valid |= (t * 32 + lane < n_points) ? (1u << t) : 0u;
 
   for (int i = c_begin + warp; i < c_end; i += nwarps) {
     const float cx = sx[i], cy = sy[i], cz = sz[i];
-    uint32_t d[T];
+    uint32_t a[32];                                   // a[31 - t] = bits of d(point 32 t + lane)
+    uint32_t far = 0;                                 // bit t <=> d > r2 (radius mask, utils.py:149-151)
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
+    for (int t = 31; t >= 0; --t) {
       const int j = t * 32 + lane;
-      d[t] = __float_as_uint(sqdist_rn(sx[j], sy[j], sz[j], cx, cy, cz));
+      const uint32_t d = __float_as_uint(sqdist_rn(sx[j], sy[j], sz[j], cx, cy, cz));
+      a[31 - t] = d;
+      far = __funnelshift_l(r2b - d, far, 1);         // shifts in the sign of (r2 - d): 1 <=> d > r2
     }
-    // radix descent for the k-th smallest bit pattern.  Counting uses four independent
-    // partial sums (setp + predicated add) so the per-bit latency is T/4 dependent adds.
-    uint32_t prefix = 0, limit = 0;
-    bool split = false;
-    // bits on which every distance agrees need no vote: start below the common prefix
-    uint32_t all_or = 0, all_and = 0xffffffffu;
+    transpose32(a);                                   // now a[31 - B] bit t = bit B of d(point 32 t + lane)
+
+    uint32_t active = valid, sel = 0;
+    int kr = k;                                       // how many of the active set are still to be taken
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      if (t * 32 < n_points) { all_or |= d[t]; all_and &= d[t]; }
+    for (int B = 30; B >= 0; --B) {
+      const uint32_t z = active & ~a[31 - B];         // active candidates with a 0 at this bit (the smaller ones)
+      const int c = __reduce_add_sync(0xffffffffu, __popc(z));
+      if (c >= kr) active = z;                        // the k-th smallest has a 0 here
+      else { sel |= z; kr -= c; active &= a[31 - B]; }
     }
-    all_or = __reduce_or_sync(0xffffffffu, all_or);
-    all_and = __reduce_and_sync(0xffffffffu, all_and);
-    int bit = 31 - __clz((all_or ^ all_and) | 1u);        // highest bit that differs (>= 0)
-    prefix = (bit >= 30) ? 0u : (all_and & ~((2u << bit) - 1u));
-    if (bit > 30) bit = 30;
+    // `active` now holds the candidates EQUAL to the k-th smallest value; kr >= 1 of them are needed
+    const int n_eq = __reduce_add_sync(0xffffffffu, __popc(active));
+    if (n_eq == kr) sel |= active;
+    else {                                            // exact ties: lowest index first (index = 32 t + lane)
 #pragma unroll 1
-    for (; bit >= 0; --bit) {
-      const uint32_t cand = prefix | (1u << bit);
-      int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-#pragma unroll
-      for (int t = 0; t < T; t += 4) {
-        asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
-            "setp.lt.u32 p0, %4, %8;\n\tsetp.lt.u32 p1, %5, %8;\n\t"
-            "setp.lt.u32 p2, %6, %8;\n\tsetp.lt.u32 p3, %7, %8;\n\t"
-            "@p0 add.s32 %0, %0, 1;\n\t@p1 add.s32 %1, %1, 1;\n\t"
-            "@p2 add.s32 %2, %2, 1;\n\t@p3 add.s32 %3, %3, 1;\n\t}"
-            : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3)
-            : "r"(d[t]), "r"(d[t + 1]), "r"(d[t + 2]), "r"(d[t + 3]), "r"(cand));
+      for (int t = 0; t < 32 && kr > 0; ++t) {
+        const bool mine = (active >> t) & 1u;
+        const unsigned bt = __ballot_sync(0xffffffffu, mine);
+        const int cnt = __popc(bt);
+        if (mine && (cnt <= kr || __popc(bt & lt_mask) < kr)) sel |= 1u << t;
+        kr -= min(cnt, kr);
       }
-      const int cnt = __reduce_add_sync(0xffffffffu, (c0 + c1) + (c2 + c3));
-      if (cnt == k) { limit = cand; split = true; break; }
-      if (cnt < k) prefix = cand;
     }
-    int need_eq = 0;
-    if (!split) {
-      limit = prefix;                       // == the k-th smallest value
-      int cnt = 0;
+    // each lane appends its selected points; order inside a group is irrelevant to every consumer
+    int pos = __popc(sel);
 #pragma unroll
-      for (int t = 0; t < T; ++t) cnt += (d[t] < limit) ? 1 : 0;
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-      need_eq = k - cnt;                    // ties at the k-th distance: lowest index first
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, pos, o);
+      if (lane >= o) pos += v;
     }
-    int32_t* out = idx_out + ((int64_t)b * n_centroids + i) * k;
-    int written = 0, eq_seen = 0;
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const bool lt = d[t] < limit;
-      const bool eq = (need_eq > 0) && (d[t] == limit);
-      const unsigned beq = __ballot_sync(0xffffffffu, eq);
-      const bool sel = lt || (eq && (eq_seen + __popc(beq & lt_mask)) < need_eq);
-      const unsigned bs = __ballot_sync(0xffffffffu, sel);
-      if (sel) {
-        const int pos = written + __popc(bs & lt_mask);
-        out[pos] = (__uint_as_float(d[t]) > r2) ? i : (t * 32 + lane);
-      }
-      written += __popc(bs);
-      eq_seen += __popc(beq);
+    pos -= __popc(sel);
+    int32_t* out = idx_out + ((int64_t)b * n_centroids + i) * k + pos;
+    uint32_t m = sel;
+    while (m) {
+      const int t = __ffs(m) - 1;
+      m &= m - 1;
+      *out++ = ((far >> t) & 1u) ? i : (t * 32 + lane);
     }
   }
 }
@@ -195,14 +200,8 @@ extern "C" int pdf_knn_ball(const float* xyz, int64_t n_clouds, int n_points, in
   PDF_REQUIRE(n_clouds * chunks < (1ll << 31), PDF_ERR_UNSUPPORTED, "pdf_knn_ball: grid too large");
   dim3 grid((unsigned)(n_clouds * chunks));
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH(T)                                                                                   \
-  pdf::knn_ball_kernel<T><<<grid, 256, 0, s>>>(xyz, n_points, n_centroids, k, r2, stride_cloud,     \
-                                               stride_point, stride_ch, idx_out, chunks, per_cta)
-  if (n_points <= 128) LAUNCH(4);
-  else if (n_points <= 256) LAUNCH(8);
-  else if (n_points <= 512) LAUNCH(16);
-  else LAUNCH(32);
-#undef LAUNCH
+  pdf::knn_ball_kernel<<<grid, 256, 0, s>>>(xyz, n_points, n_centroids, k, r2, stride_cloud, stride_point,
+                                            stride_ch, idx_out, chunks, per_cta);
   return pdf::check_launch("pdf_knn_ball");
 }
 

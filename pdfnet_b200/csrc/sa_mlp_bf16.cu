@@ -136,27 +136,36 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
 
   mbar_wait(smem_u32(&s_bar[0]), 0);                     // weights resident
 
-  // relative coordinates of this thread's row for a tile (fp32, exactly p_j - c_i as the reference)
-  auto load_geom = [&](int64_t t, float& rx, float& ry, float& rz) {
+  // Two-deep software prefetch of the geometry (warps issue in order, so a load only overlaps
+  // with other work if its first USE is an iteration away): the neighbour index of tile t+2 and the
+  // raw coordinates of tile t+1 are in flight while tile t runs its three MMA phases.
+  auto load_idx = [&](int64_t t) -> int {
+    const int64_t b = t / tiles_per_cloud;
+    const int g0 = (int)(t % tiles_per_cloud) * 2;
+    return __ldg(idx + (b * n_centroids + g0) * 64 + p);
+  };
+  auto load_raw = [&](int64_t t, int j, float (&sp)[3], float (&cp)[3]) {
     const int64_t b = t / tiles_per_cloud;
     const int g0 = (int)(t % tiles_per_cloud) * 2;
     const float* cloud = pts + b * n_src * ld_pts;
-    const int j = __ldg(idx + (b * n_centroids + g0) * 64 + p);
     const float* src = cloud + (int64_t)j * ld_pts;
     const float* cen = cloud + (int64_t)(g0 + (p >> 6)) * ld_pts;
-    rx = __fsub_rn(__ldg(src), __ldg(cen));
-    ry = __fsub_rn(__ldg(src + 1), __ldg(cen + 1));
-    rz = __fsub_rn(__ldg(src + 2), __ldg(cen + 2));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { sp[c] = __ldg(src + c); cp[c] = __ldg(cen + c); }
   };
   const int64_t t_first = (int64_t)blockIdx.x * Cfg::SLOTS + slot, t_step = (int64_t)gridDim.x * Cfg::SLOTS;
-  float rx = 0.f, ry = 0.f, rz = 0.f;
-  if (t_first < n_tiles) load_geom(t_first, rx, ry, rz);
+  float sp[3] = {0.f, 0.f, 0.f}, cp[3] = {0.f, 0.f, 0.f};
+  int j_next = 0;
+  if (t_first < n_tiles) load_raw(t_first, load_idx(t_first), sp, cp);
+  if (t_first + t_step < n_tiles) j_next = load_idx(t_first + t_step);
 
   for (int64_t t = t_first; t < n_tiles; t += t_step) {
     const int64_t b = t / tiles_per_cloud;
     const int g0 = (int)(t % tiles_per_cloud) * 2;
     const float* cloud = pts + b * n_src * ld_pts;
     const int32_t* tidx = idx + (b * n_centroids + g0) * 64;
+    // p_j - c_i in fp32, the reference's operand order (utils.py:142-143)
+    const float rx = __fsub_rn(sp[0], cp[0]), ry = __fsub_rn(sp[1], cp[1]), rz = __fsub_rn(sp[2], cp[2]);
 
     // ---- gather: geometry/bias block (thread = row, prefetched one tile ahead) ----
     {
@@ -213,7 +222,8 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
                             idesc_bf16(128, Cfg::C1));
       commit(bar);
     }
-    if (t + t_step < n_tiles) load_geom(t + t_step, rx, ry, rz);   // in flight during the three MMA phases
+    if (t + t_step < n_tiles) load_raw(t + t_step, j_next, sp, cp);       // first use: next iteration
+    if (t + 2 * t_step < n_tiles) j_next = load_idx(t + 2 * t_step);      // first use: next iteration
     mbar_wait(bar, phase); phase ^= 1;
     fence_after_sync();
     epilogue_repack<Cfg::C1>(d1 + lane_off, my_feat, p);
