@@ -145,12 +145,15 @@ int pdf_sa_pack_weights_host(const float* W1, const float* b1, const float* W2, 
  * (intaghand_encoder.py:205-219), netR_3 + MaxPool (:86-103,152-154) and the fusion
  * SFT(1024,1024) (:809). */
 int64_t pdf_image_bytes(int64_t rows, int cols);
-/* host-side packer: fp32 W[rows, cols] (row pitch ld) -> bf16 tile image (pure host code) */
-int pdf_pack_image_host(const float* W, int64_t rows, int cols, int64_t ld, void* out_host);
+/* host-side packer: fp32 W[rows, cols] (row pitch ld) -> bf16 tile image (pure host code).
+ * split != 0 packs [hi | lo | hi] (3x the k-blocks, 3x pdf_image_bytes): against an activation
+ * image written with split != 0 ([hi | hi | lo]) the GEMM then accumulates a_hi*w_hi + a_hi*w_lo +
+ * a_lo*w_hi, i.e. fp32-accurate products (error ~2^-16 relative) on the bf16 tensor cores. */
+int pdf_pack_image_host(const float* W, int64_t rows, int cols, int64_t ld, int split, void* out_host);
 /* device: fp32 rows X[M, ld], columns [col0, col0+K) -> k-blocks [kb0, kb0+ceil(K/64)) of an image
  * that has kb_total k-blocks per row-tile; padding rows/columns are written as zeros */
 int pdf_rows_to_image(const float* X, int64_t ld, int64_t M, int col0, int K, void* img, int kb_total, int kb0,
-                      void* stream);
+                      int split, void* stream);
 /* D[m,n] = sum_k Mop[m,k] * Nop[n,k] over KB k-blocks, 128x128 tiles, fp32 accumulate in TMEM.
  * colmax = 0 (ROW epilogue, thread = M row): y = act(D + bias0[n]); with kb_split > 0 the
  *   k-blocks below / from kb_split accumulate separately and y = F*(D0+bias0+1) + (D1+bias1)
@@ -159,12 +162,16 @@ int pdf_rows_to_image(const float* X, int64_t ld, int64_t M, int col0, int K, vo
  *   bf16_col_off + n] (row pitch ld_bf16 elements).  tile_desc_host: int32 [n_tiles][3] =
  *   {first fp32 column of this N-tile in F/out_f32, valid columns (<=128), first output k-block}.
  * colmax = 1: M operand = weights (rows = channels), N operand = activations, one N-tile = the
- *   128 points of one cloud: out_max[n_tile, m] = relu(max_n D[m,n] + bias0[m]). */
+ *   128 points of one cloud: out_max[n_tile, m] = relu(max_n D[m,n] + bias0[m]).
+ * xyz_w != NULL (XYZ mode, one N-tile whose 128 columns are [64 scale-hidden | 64 shift-hidden] of
+ *   an SFTLayer): besides the regular outputs the epilogue applies the SFT modulation to the 3 xyz
+ *   channels in fp32, x[m,c] = x[m,c]*(w1s[c].h_s + b1s[c] + 1) + (w1h[c].h_h + b1h[c]) with
+ *   xyz_w = {w1s[3][64], w1h[3][64], b1s[3], b1h[3]} and x = xyz_x[m*xyz_ld + c]. */
 int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const void* n_img, int n_tiles, int n_kb, int KB,
                   int kb_split, int colmax, const float* bias0, const float* bias1, int act, float* out_f32,
                   int64_t ld_out, int64_t rows_valid, const float* F, int64_t ldf, void* out_img, int out_kb,
                   void* out_bf16, int64_t ld_bf16, int bf16_col_off, const int32_t* tile_desc_host, float* out_max,
-                  int64_t ld_max, void* stream);
+                  int64_t ld_max, const float* xyz_w, float* xyz_x, int64_t xyz_ld, void* stream);
 /* SFT on the three xyz channels of level 1 in full fp32 (they feed the level-2 neighbour
  * search): x[m,c] = x[m,c]*(scale_c+1)+shift_c for c < 3; cond fp32 [M,cc]; conv weights as in
  * SFTLayer ([out,in] row-major; only rows 0..2 of the second convs are read). cc must be 64. */

@@ -26,10 +26,10 @@ SIGNATURES = {
     "pdf_sa_mlp_max_bf16": [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _i32,
                             _vp],
     "pdf_sa_pack_weights_host": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
-    "pdf_pack_image_host": [_vp, _i64, _i32, _i64, _vp],
-    "pdf_rows_to_image": [_vp, _i64, _i64, _i32, _i32, _vp, _i32, _i32, _vp],
+    "pdf_pack_image_host": [_vp, _i64, _i32, _i64, _i32, _vp],
+    "pdf_rows_to_image": [_vp, _i64, _i64, _i32, _i32, _vp, _i32, _i32, _i32, _vp],
     "pdf_gemm_bf16": [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _i64, _vp, _i64,
-                      _vp, _i32, _vp, _i64, _i32, _vp, _vp, _i64, _vp],
+                      _vp, _i32, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp],
     "pdf_sft_xyz_f32": [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "pdf_backproject": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
     "pdf_depth2pcl": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],

@@ -28,7 +28,7 @@ using namespace umma;
 constexpr int G_STAGES = 4;
 constexpr int G_BLOCK = 16384;                 // one 128 x 64 bf16 block
 constexpr int G_THREADS = 320;                // producer warp + MMA warp + 8 epilogue warps
-constexpr int G_SMEM = G_STAGES * 2 * G_BLOCK + 1024 + 256 + 2 * 16 * 128 * 4;   // + staged biases
+constexpr int G_SMEM = G_STAGES * 2 * G_BLOCK + 1024 + 256 + 2 * 16 * 128 * 4 + 400 * 4;   // + staged biases, xyz weights
 constexpr int G_MAX_NT = 16;
 
 struct GemmParams {
@@ -43,6 +43,10 @@ struct GemmParams {
   uint16_t* out_bf16; int64_t ld_bf16;   // optional bf16 ROW-major output (same columns as out_f32, minus bf16_col_off)
   int bf16_col_off;
   float* out_max; int64_t ld_max;
+  // XYZ mode (SFT1 hidden layer): the 128 columns are [64 scale-hidden | 64 shift-hidden]; besides the
+  // bf16 image of lrelu(D+b) the epilogue applies the SFT modulation to the 3 xyz channels in fp32:
+  // x[m,c] = x[m,c]*(w1s[c].h_s + b1s[c] + 1) + (w1h[c].h_h + b1h[c]).  xyz_w = [2][3][64] then [2][3].
+  const float* xyz_w; float* xyz_x; int64_t xyz_ld;
   int tile_col[G_MAX_NT];        // ROW mode, per N-tile: first fp32 column (F and out_f32)
   int tile_nvalid[G_MAX_NT];     //   valid output columns of this N-tile (others are written as 0 / skipped)
   int tile_okb[G_MAX_NT];        //   first k-block of this N-tile in the output image
@@ -70,11 +74,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
   }
   if (warp == 0) tmem_alloc<512>(s_tmem);
   float* s_bias = reinterpret_cast<float*>(smem + G_STAGES * 2 * G_BLOCK + 256);   // [2][n_tiles*128]
+  float* s_xyz = s_bias + 2 * G_MAX_NT * 128;                                     // [390]
+  const bool xyz = !COLMAX && P.xyz_w != nullptr;
   if (!COLMAX) {
     for (int i = threadIdx.x; i < P.n_tiles * 128; i += G_THREADS) {
       s_bias[i] = P.bias0[i];
       s_bias[G_MAX_NT * 128 + i] = dual ? P.bias1[i] : 0.f;
     }
+    if (xyz) for (int i = threadIdx.x; i < 390; i += G_THREADS) s_xyz[i] = P.xyz_w[i];
   }
   fence_before_sync();
   __syncthreads();
@@ -154,8 +161,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
         const float* b0 = s_bias + nt * 128;
         const float* b1 = s_bias + G_MAX_NT * 128 + nt * 128;
         const bool full = row_ok && nvalid == 128;           // fast path: no per-element masking
+        float xo[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+        const int c_begin = xyz ? (half == 0 ? 0 : 128) : half * 64, c_end = xyz ? 128 : half * 64 + 64;
 #pragma unroll 1
-        for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t v[32], u[32];
           tmem_ld32(acc + c0, v);
           if (dual) tmem_ld32(acc + 128 + c0, u);
@@ -186,6 +195,18 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
               for (int e = 0; e < 4; ++e) r[e] = (row_ok && c0 + q + e < nvalid) ? r[e] : 0.f;
             }
             y[q] = r[0]; y[q + 1] = r[1]; y[q + 2] = r[2]; y[q + 3] = r[3];
+          }
+          if (xyz) {                                         // fp32 dots with the 3 xyz rows of the second conv
+            const int br = c0 >> 6;
+            const float* w = s_xyz + br * 192 + (c0 & 63);
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                const float4 wv = *reinterpret_cast<const float4*>(w + c * 64 + q);
+                xo[br][c] = fmaf(wv.x, y[q], fmaf(wv.y, y[q + 1], fmaf(wv.z, y[q + 2], fmaf(wv.w, y[q + 3], xo[br][c]))));
+              }
+            }
           }
           if (P.out_f32 != nullptr && row_ok) {
             float* o = P.out_f32 + m * P.ld_out + col0 + c0;
@@ -221,6 +242,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
             }
           }
         }
+        if (xyz && half == 0 && row_ok) {
+          float* xr = P.xyz_x + m * P.xyz_ld;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            xr[c] = __fadd_rn(__fmul_rn(xr[c], __fadd_rn(xo[0][c] + s_xyz[384 + c], 1.f)), xo[1][c] + s_xyz[387 + c]);
+        }
       }
       fence_before_sync();
       __syncwarp();
@@ -236,7 +263,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
 // fp32 rows [M, ld] columns [col0, col0+K) -> bf16 image k-blocks [kb0, kb0 + ceil(K/64)) of every
 // row-tile; rows >= M and columns >= K are written as zeros.  One thread per 16-byte chunk.
 __global__ void rows_to_image_kernel(const float* __restrict__ X, int64_t ld, int64_t M, int col0, int K,
-                                     uint8_t* __restrict__ img, int kb_total, int kb0, int nkb, int64_t n_chunks) {
+                                     uint8_t* __restrict__ img, int kb_total, int kb0, int nkb, int64_t n_chunks,
+                                     int split) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_chunks;
        e += (int64_t)gridDim.x * blockDim.x) {
     const int ch = (int)(e & 7);                         // 16 B chunk inside a 64-column block row
@@ -250,7 +278,22 @@ __global__ void rows_to_image_kernel(const float* __restrict__ X, int64_t ld, in
     uint4 w;
     w.x = pack_bf16(f[0], f[1]); w.y = pack_bf16(f[2], f[3]); w.z = pack_bf16(f[4], f[5]); w.w = pack_bf16(f[6], f[7]);
     const int64_t mt = m >> 7;
-    *reinterpret_cast<uint4*>(img + ((size_t)mt * kb_total + kb0 + kb) * G_BLOCK + sw128_off((uint32_t)(m & 127), ch * 8)) = w;
+    const uint32_t off = sw128_off((uint32_t)(m & 127), ch * 8);
+    uint8_t* tile = img + ((size_t)mt * kb_total + kb0) * G_BLOCK;
+    *reinterpret_cast<uint4*>(tile + (size_t)kb * G_BLOCK + off) = w;
+    if (split) {                                         // [hi | hi | lo]: fp32-accurate products on bf16 tensor cores
+      *reinterpret_cast<uint4*>(tile + (size_t)(nkb + kb) * G_BLOCK + off) = w;
+      float l[8];
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const uint32_t pk = i == 0 ? w.x : (i == 2 ? w.y : (i == 4 ? w.z : w.w));
+        l[i] = f[i] - __uint_as_float(pk << 16);
+        l[i + 1] = f[i + 1] - __uint_as_float(pk & 0xffff0000u);
+      }
+      uint4 wl;
+      wl.x = pack_bf16(l[0], l[1]); wl.y = pack_bf16(l[2], l[3]); wl.z = pack_bf16(l[4], l[5]); wl.w = pack_bf16(l[6], l[7]);
+      *reinterpret_cast<uint4*>(tile + (size_t)(2 * nkb + kb) * G_BLOCK + off) = wl;
+    }
   }
 }
 
@@ -320,24 +363,36 @@ extern "C" int64_t pdf_image_bytes(int64_t rows, int cols) {
   return ((rows + 127) / 128) * (int64_t)((cols + 63) / 64) * pdf::G_BLOCK;
 }
 
-extern "C" int pdf_pack_image_host(const float* W, int64_t rows, int cols, int64_t ld, void* out_host) {
+extern "C" int pdf_pack_image_host(const float* W, int64_t rows, int cols, int64_t ld, int split, void* out_host) {
   PDF_REQUIRE(W && out_host && rows > 0 && cols > 0 && ld >= cols, PDF_ERR_BAD_ARG, "pdf_pack_image_host: bad argument");
-  const int kbt = (cols + 63) / 64;
+  const int nkb = (cols + 63) / 64, kbt = split ? 3 * nkb : nkb;
   uint8_t* out = (uint8_t*)out_host;
-  memset(out, 0, (size_t)pdf_image_bytes(rows, cols));
+  memset(out, 0, (size_t)pdf_image_bytes(rows, cols) * (split ? 3 : 1));
   for (int64_t r = 0; r < rows; ++r)
     for (int k = 0; k < cols; ++k) {
-      const uint16_t h = pdf::f2bf_host(W[r * ld + k]);
-      memcpy(out + ((size_t)(r >> 7) * kbt + (k >> 6)) * pdf::G_BLOCK + pdf::umma::sw128_off((uint32_t)(r & 127), k & 63), &h, 2);
+      const float v = W[r * ld + k];
+      const uint16_t h = pdf::f2bf_host(v);
+      const uint32_t off = pdf::umma::sw128_off((uint32_t)(r & 127), k & 63);
+      uint8_t* tile = out + (size_t)(r >> 7) * kbt * pdf::G_BLOCK;
+      memcpy(tile + (size_t)(k >> 6) * pdf::G_BLOCK + off, &h, 2);
+      if (split) {                                       // [hi | lo | hi], the mirror of the activation split
+        uint32_t hb = (uint32_t)h << 16;
+        float hf;
+        memcpy(&hf, &hb, 4);
+        const uint16_t l = pdf::f2bf_host(v - hf);
+        memcpy(tile + (size_t)(nkb + (k >> 6)) * pdf::G_BLOCK + off, &l, 2);
+        memcpy(tile + (size_t)(2 * nkb + (k >> 6)) * pdf::G_BLOCK + off, &h, 2);
+      }
     }
   return PDF_OK;
 }
 
 extern "C" int pdf_rows_to_image(const float* X, int64_t ld, int64_t M, int col0, int K, void* img, int kb_total,
-                                 int kb0, void* stream) {
+                                 int kb0, int split, void* stream) {
   if (M == 0) return PDF_OK;
   PDF_REQUIRE(X && img, PDF_ERR_BAD_ARG, "pdf_rows_to_image: null pointer");
-  PDF_REQUIRE(M > 0 && K > 0 && col0 >= 0 && ld >= col0 + K && kb0 >= 0 && kb0 + (K + 63) / 64 <= kb_total,
+  PDF_REQUIRE(M > 0 && K > 0 && col0 >= 0 && ld >= col0 + K && kb0 >= 0 &&
+                  kb0 + (split ? 3 : 1) * ((K + 63) / 64) <= kb_total,
               PDF_ERR_BAD_ARG, "pdf_rows_to_image: bad size");
   const int nkb = (K + 63) / 64;
   const int64_t rows_pad = ((M + 127) / 128) * 128;
@@ -345,7 +400,7 @@ extern "C" int pdf_rows_to_image(const float* X, int64_t ld, int64_t M, int col0
   int64_t grid = (chunks + 255) / 256;
   if (grid > 148 * 32) grid = 148 * 32;
   pdf::rows_to_image_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(X, ld, M, col0, K, (uint8_t*)img,
-                                                                              kb_total, kb0, nkb, chunks);
+                                                                              kb_total, kb0, nkb, chunks, split);
   return pdf::check_launch("pdf_rows_to_image");
 }
 
@@ -353,7 +408,8 @@ extern "C" int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const voi
                              int KB, int kb_split, int colmax, const float* bias0, const float* bias1, int act,
                              float* out_f32, int64_t ld_out, int64_t rows_valid, const float* F, int64_t ldf,
                              void* out_img, int out_kb, void* out_bf16, int64_t ld_bf16, int bf16_col_off,
-                             const int32_t* tile_desc_host, float* out_max, int64_t ld_max, void* stream) {
+                             const int32_t* tile_desc_host, float* out_max, int64_t ld_max, const float* xyz_w,
+                             float* xyz_x, int64_t xyz_ld, void* stream) {
   using namespace pdf;
   if (m_tiles == 0 || n_tiles == 0) return PDF_OK;
   PDF_REQUIRE(m_img && n_img && bias0, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: null pointer");
@@ -368,11 +424,16 @@ extern "C" int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const voi
   P.out_f32 = out_f32; P.ld_out = ld_out; P.rows_valid = rows_valid; P.F = F; P.ldf = ldf;
   P.out_img = (uint8_t*)out_img; P.out_kb = out_kb; P.out_max = out_max; P.ld_max = ld_max;
   P.out_bf16 = (uint16_t*)out_bf16; P.ld_bf16 = ld_bf16; P.bf16_col_off = bf16_col_off;
+  P.xyz_w = xyz_w; P.xyz_x = xyz_x; P.xyz_ld = xyz_ld;
+  PDF_REQUIRE(!xyz_w || (!colmax && n_tiles == 1 && kb_split == 0 && xyz_x), PDF_ERR_BAD_ARG,
+              "pdf_gemm_bf16: XYZ mode needs one N tile, one accumulator and xyz_x");
   if (colmax) {
     PDF_REQUIRE(out_max && kb_split == 0, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: COLMAX needs out_max and one accumulator");
   } else {
     PDF_REQUIRE(n_tiles <= G_MAX_NT && tile_desc_host, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: ROW mode needs <= %d N tiles and tile_desc", G_MAX_NT);
     PDF_REQUIRE(out_f32 || out_img || out_bf16, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: no output");
+    PDF_REQUIRE((!out_f32 || ld_out % 4 == 0) && (!F || ldf % 4 == 0), PDF_ERR_BAD_ARG,
+                "pdf_gemm_bf16: fp32 row pitches must be multiples of 4 (16-byte vector access)");
     PDF_REQUIRE(!out_bf16 || ((ld_bf16 % 8) == 0 && (bf16_col_off % 4) == 0), PDF_ERR_BAD_ARG,
                 "pdf_gemm_bf16: bf16 rows need 16-byte aligned pitch");
     PDF_REQUIRE(kb_split == 0 || (F && bias1), PDF_ERR_BAD_ARG, "pdf_gemm_bf16: SFT mode needs F and bias1");

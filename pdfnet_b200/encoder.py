@@ -173,7 +173,10 @@ class PointNet_Plus(nn.Module):
         # SFT1: hidden = lrelu([Ws0;Wh0] cond), features 3..130 modulated on tensor cores (xyz in fp32)
         ws0, bs0, ws1, bs1, wh0, bh0, wh1, bh1 = self.sft1.weights()
         tc["sft1_plain"] = (ws0, bs0, ws1, bs1, wh0, bh0, wh1, bh1)
-        tc["sft1_w0"], tc["sft1_b0"] = img(torch.cat([ws0, wh0], 0)), torch.cat([bs0, bh0]).contiguous()
+        # hidden layer as a split (fp32-accurate) GEMM: its fp32 accumulator also feeds the xyz channels
+        tc["sft1_w0"] = ops.pack_image(torch.cat([ws0, wh0], 0), split=True).to(dev)
+        tc["sft1_b0"] = torch.cat([bs0, bh0]).contiguous()
+        tc["sft1_xyz"] = torch.cat([ws1[:3].reshape(-1), wh1[:3].reshape(-1), bs1[:3], bh1[:3]]).contiguous()
         tc["sft1_w1"] = img(torch.cat([ws1[3:], wh1[3:]], 1))
         tc["sft1_b1s"], tc["sft1_b1h"] = bs1[3:].contiguous(), bh1[3:].contiguous()
         # SFT2: N-tiles = features 0..127 | features 128..255 | [xyz, pad]
@@ -279,16 +282,17 @@ class PointNet_Plus(nn.Module):
         t1, t2 = M1 // 128, M2 // 128
         x1r, c1r = x1.view(M1, 132), cond1.view(M1, 64)
         with stage("sft1"):
-            c1img = ops.rows_to_image(c1r, 0, 64)
+            # hidden = lrelu([Ws0;Wh0] cond): split-bf16 GEMM (fp32-accurate); the same epilogue modulates
+            # the 3 xyz channels of x1 in fp32 (they drive the level-2 neighbour search)
+            c1img = ops.rows_to_image(c1r, 0, 64, split=True)
             h1img = u8(t1 * 2 * BLK)
-            ops.gemm_bf16(c1img, t1, 1, tc["sft1_w0"], 1, 1, 1, tc["sft1_b0"], act=LEAKY, out_img=h1img, out_kb=2,
-                          rows_valid=M1, tile_desc=[(0, 128, 0)])
+            ops.gemm_bf16(c1img, t1, 3, tc["sft1_w0"], 1, 3, 3, tc["sft1_b0"], act=LEAKY, out_img=h1img, out_kb=2,
+                          rows_valid=M1, tile_desc=[(0, 128, 0)], xyz_w=tc["sft1_xyz"], xyz_x=x1r)
             # modulated features leave as bf16 rows (the level-2 gather copies them with cp.async);
             # the xyz channels stay fp32 in x1 (they drive the level-2 neighbour search)
             x1h = torch.empty((M1, 128), dtype=torch.bfloat16, device=dev)
             ops.gemm_bf16(h1img, t1, 2, tc["sft1_w1"], 1, 2, 2, tc["sft1_b1s"], kb_split=1, bias1=tc["sft1_b1h"],
                           F=x1r, out_bf16=x1h, bf16_col_off=4, rows_valid=M1, tile_desc=[(4, 128, 0)])
-            ops.sft_xyz(c1r, tc["sft1_plain"], x1r)
         with stage("knn2"):
             idx2 = ops.knn_ball(x1, N2, K, self.ball_radius2)
         x2 = torch.empty((B, N2, 260), dtype=torch.float32, device=dev)
@@ -366,7 +370,7 @@ class HandFusion(nn.Module):
             if not with_mano:
                 return fused
             with stage("mano_head"):
-                theta = self.mano_head_forward(rows).view(B, H, 122)
+                theta = self.mano_head_forward(rows).reshape(B, H, 122)
             return fused, theta
 
     def _fusion_sft_bf16(self, rows, cen):
@@ -401,9 +405,41 @@ class HandFusion(nn.Module):
             self._mano_fold = _fold_bn_linear(m[0], m[1]) + _fold_bn_linear(m[3], m[4])
             self._mano_fold_key = key
         w1, b1, w2, b2 = self._mano_fold
+        if self.pointnet_plus.precision == "bf16":
+            return self._mano_head_tc(x, key, (w1, b1, w2, b2, m[6].weight.detach(), m[6].bias.detach()))
         h = ops.linear(x, w1, b1, act=L.ACT_RELU)
         h = ops.linear(h, w2, b2, act=L.ACT_RELU)
         return ops.linear(h, m[6].weight.detach(), m[6].bias.detach())
+
+
+def _mano_head_tc_impl(self, x, key, w):
+    """mano_head on the streaming tcgen05 GEMM with split-bf16 operands ([hi|hi|lo] x [hi|lo|hi]):
+    fp32-accurate products (the MANO pose parameters feed rotations), fp32 accumulate."""
+    if getattr(self, "_mano_tc_key", None) != key:
+        w1, b1, w2, b2, w3, b3 = w
+        dev = x.device
+        pad = lambda b: torch.cat([b, torch.zeros(128 - b.shape[0] % 128 if b.shape[0] % 128 else 0, device=b.device)])
+        self._mano_tc = dict(w1=ops.pack_image(w1, split=True).to(dev), b1=b1.contiguous(),
+                             w2=ops.pack_image(w2, split=True).to(dev), b2=b2.contiguous(),
+                             w3=ops.pack_image(w3, split=True).to(dev), b3=pad(b3.float()).contiguous())
+        self._mano_tc_key = key
+    t = self._mano_tc
+    M = x.shape[0]
+    mt = (M + 127) // 128
+    dev = x.device
+    h1 = torch.empty((M, 512), dtype=torch.float32, device=dev)
+    ops.gemm_bf16(ops.rows_to_image(x, 0, 1024, split=True), mt, 48, t["w1"], 4, 48, 48, t["b1"], act=L.ACT_RELU,
+                  out_f32=h1, rows_valid=M, tile_desc=[(128 * i, 128, 0) for i in range(4)])
+    h2 = torch.empty((M, 256), dtype=torch.float32, device=dev)
+    ops.gemm_bf16(ops.rows_to_image(h1, 0, 512, split=True), mt, 24, t["w2"], 2, 24, 24, t["b2"], act=L.ACT_RELU,
+                  out_f32=h2, rows_valid=M, tile_desc=[(128 * i, 128, 0) for i in range(2)])
+    theta = torch.empty((M, 124), dtype=torch.float32, device=dev)
+    ops.gemm_bf16(ops.rows_to_image(h2, 0, 256, split=True), mt, 12, t["w3"], 1, 12, 12, t["b3"], out_f32=theta,
+                  rows_valid=M, tile_desc=[(0, 122, 0)])
+    return theta[:, :122]
+
+
+HandFusion._mano_head_tc = _mano_head_tc_impl
 
 
 def _fold_bn_linear(fc, bn):

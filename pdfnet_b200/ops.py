@@ -151,35 +151,38 @@ def image_bytes(rows, cols):
     return int(L.load().pdf_image_bytes(rows, cols))
 
 
-def pack_image(w):
-    """Host-side packing of an fp32 matrix [rows, cols] into a bf16 tile image (uint8 CPU tensor)."""
+def pack_image(w, split=False):
+    """Host-side packing of an fp32 matrix [rows, cols] into a bf16 tile image (uint8 CPU tensor).
+    split=True packs [hi | lo | hi] (3x k-blocks) for fp32-accurate GEMMs against a split activation image."""
     w = w.detach().cpu().float().contiguous()
     rows, cols = w.shape
-    buf = torch.empty((image_bytes(rows, cols),), dtype=torch.uint8)
-    L.call("pdf_pack_image_host", ctypes.c_void_p(w.data_ptr()), rows, cols, w.stride(0),
+    buf = torch.empty((image_bytes(rows, cols) * (3 if split else 1),), dtype=torch.uint8)
+    L.call("pdf_pack_image_host", ctypes.c_void_p(w.data_ptr()), rows, cols, w.stride(0), 1 if split else 0,
            ctypes.c_void_p(buf.data_ptr()))
     return buf
 
 
-def rows_to_image(x, col0, K, img=None, kb_total=None, kb0=0):
-    """fp32 rows x[M, ld] columns [col0, col0+K) -> bf16 tile image (uint8 device tensor)."""
+def rows_to_image(x, col0, K, img=None, kb_total=None, kb0=0, split=False):
+    """fp32 rows x[M, ld] columns [col0, col0+K) -> bf16 tile image (uint8 device tensor).
+    split=True writes [hi | hi | lo] (3x k-blocks)."""
     L.require_cuda(x, img)
     assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32
     M = x.shape[0]
-    nkb = (K + 63) // 64
+    nkb = (K + 63) // 64 * (3 if split else 1)
     if kb_total is None:
         kb_total = nkb
     if img is None:
         img = torch.empty((((M + 127) // 128) * kb_total * 16384,), dtype=torch.uint8, device=x.device)
-    L.call("pdf_rows_to_image", L.ptr(x), x.stride(0), M, col0, K, L.ptr(img), kb_total, kb0, L.stream())
+    L.call("pdf_rows_to_image", L.ptr(x), x.stride(0), M, col0, K, L.ptr(img), kb_total, kb0, 1 if split else 0,
+           L.stream())
     return img
 
 
 def gemm_bf16(m_img, m_tiles, m_kb, n_img, n_tiles, n_kb, KB, bias0, kb_split=0, bias1=None, act=L.ACT_NONE,
               out_f32=None, rows_valid=0, F=None, out_img=None, out_kb=0, tile_desc=None, out_max=None,
-              out_bf16=None, bf16_col_off=0):
+              out_bf16=None, bf16_col_off=0, xyz_w=None, xyz_x=None):
     """Streaming tcgen05 GEMM over tile images (see pdf_gemm_bf16)."""
-    L.require_cuda(m_img, n_img, bias0, bias1, out_f32, F, out_img, out_max, out_bf16)
+    L.require_cuda(m_img, n_img, bias0, bias1, out_f32, F, out_img, out_max, out_bf16, xyz_w, xyz_x)
     colmax = out_max is not None
     desc = None
     if tile_desc is not None:
@@ -190,7 +193,8 @@ def gemm_bf16(m_img, m_tiles, m_kb, n_img, n_tiles, n_kb, KB, bias0, kb_split=0,
            L.ptr(F), F.stride(0) if F is not None else 0, L.ptr(out_img), out_kb, L.ptr(out_bf16),
            out_bf16.stride(0) if out_bf16 is not None else 0, bf16_col_off,
            ctypes.cast(desc, ctypes.c_void_p) if desc is not None else None, L.ptr(out_max),
-           out_max.stride(0) if colmax else 0, L.stream())
+           out_max.stride(0) if colmax else 0, L.ptr(xyz_w), L.ptr(xyz_x),
+           xyz_x.stride(0) if xyz_x is not None else 0, L.stream())
 
 
 def sft_xyz(cond_rows, weights, x_rows):

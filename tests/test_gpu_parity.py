@@ -510,3 +510,48 @@ def test_sft_xyz_fp32():
     y = x.clone()
     ops.sft_xyz(cond, m.weights(), y)
     assert rel_err(y[:, :3].cpu(), ref.cpu()) < 1e-5 and torch.equal(y[:, 3:], x[:, 3:])
+
+
+def test_gemm_split_bf16_is_fp32_accurate():
+    """[hi|hi|lo] x [hi|lo|hi] operand images: fp32-accurate products on the bf16 tensor cores."""
+    from pdfnet_b200 import _lib as L
+    from pdfnet_b200 import ops
+    g = torch.Generator().manual_seed(10)
+    M, K, N = 200, 300, 130
+    x, w, b = torch.randn((M, K), generator=g), torch.randn((N, K), generator=g), torch.randn((N,), generator=g)
+    ximg = ops.rows_to_image(x.to(DEV), 0, K, split=True)
+    wimg = ops.pack_image(w, split=True).to(DEV)
+    out = torch.zeros((M, 132), device=DEV)
+    bias = torch.cat([b, torch.zeros(126)]).to(DEV)
+    ops.gemm_bf16(ximg, 2, 15, wimg, 2, 15, 15, bias, out_f32=out, rows_valid=M, tile_desc=[(0, 128, 0), (128, 2, 0)])
+    ref = x.double() @ w.double().t() + b.double()
+    assert rel_err(out[:, :130].cpu(), ref) < 3e-5
+    plain = _bf(x).double() @ _bf(w).double().t() + b.double()
+    assert rel_err(plain, ref) > 20 * rel_err(out[:, :130].cpu(), ref)      # far better than plain bf16
+
+
+def test_gemm_xyz_mode_matches_fp32_sft():
+    """SFT1 hidden layer in XYZ mode: bf16 hidden image + fp32 modulation of the 3 xyz channels."""
+    from pdfnet_b200 import _lib as L
+    from pdfnet_b200 import SFTLayer, ops
+    g = torch.Generator().manual_seed(11)
+    m = SFTLayer(131, 64)
+    m.load_state_dict(synth.sft_state("", 131, 64, seed=20))
+    m = m.to(DEV).eval()
+    M = 1000
+    x = torch.randn((M, 132), generator=g).to(DEV)
+    cond = torch.randn((M, 64), generator=g).to(DEV)
+    ws0, bs0, ws1, bs1, wh0, bh0, wh1, bh1 = m.weights()
+    ref = m.apply_rows(x[:, :3].contiguous(), cond, weights=(ws0, bs0, ws1[:3], bs1[:3], wh0, bh0, wh1[:3], bh1[:3]))
+    hid_ref = torch.cat([torch.nn.functional.leaky_relu(cond @ ws0.t() + bs0, 0.1),
+                         torch.nn.functional.leaky_relu(cond @ wh0.t() + bh0, 0.1)], 1)
+    y = x.clone()
+    cimg = ops.rows_to_image(cond, 0, 64, split=True)
+    wimg = ops.pack_image(torch.cat([ws0, wh0], 0), split=True).to(DEV)
+    himg = torch.zeros((8 * 2 * 16384,), dtype=torch.uint8, device=DEV)
+    xyz_w = torch.cat([ws1[:3].reshape(-1), wh1[:3].reshape(-1), bs1[:3], bh1[:3]]).contiguous()
+    ops.gemm_bf16(cimg, 8, 3, wimg, 1, 3, 3, torch.cat([bs0, bh0]).contiguous(), act=L.ACT_LEAKY01, out_img=himg,
+                  out_kb=2, rows_valid=M, tile_desc=[(0, 128, 0)], xyz_w=xyz_w, xyz_x=y)
+    assert rel_err(y[:, :3].cpu(), ref.cpu()) < 2e-5 and torch.equal(y[:, 3:], x[:, 3:])
+    dec = _decode_image(himg.cpu().numpy(), 1024, 128)
+    assert rel_err(dec[:M], hid_ref.cpu().numpy()) < 1e-2 and (dec[M:] == 0).all()
