@@ -199,7 +199,7 @@ int pdf_backproject(const float* depth, const float* Kinv, int64_t B, int H, int
  * exceed n_points); perm int32 [B,2,n_points] (null = identity).
  * choose int64 [B,2,n_points] (row 0 = left), cloud fp32 [B,2,n_points,3],
  * n_cand int32 [B,2] (number of candidate pixels, for diagnostics).
- * Supported: n_points == 1024. */
+ * Supported: n_points == 1024, H*W <= 640*640. */
 int pdf_depth2pcl(const float* depth, const float* mask, const float* Kinv, const float* valid,
                   const int32_t* subset_keys, const int32_t* perm, int64_t B, int H, int W,
                   int n_points, int min_pixels, int64_t* choose, float* cloud, int32_t* n_cand, void* stream);

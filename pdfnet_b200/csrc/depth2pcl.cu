@@ -77,17 +77,25 @@ depth2pcl_kernel(const float* __restrict__ depth, const float* __restrict__ mask
     const bool keep = (0.2f < d) && (2.5f > d) && (msk[pix] > 0.5f);
     return keep ? d : 0.f;
   };
-  auto z_of = [&](int pix, float zm) -> float {
-    const float u = (float)(pix % W), v = (float)(pix / W);
-    return __fmul_rn(fmaf(k21, v, fmaf(k20, u, k22)), zm);
+  auto z_uv = [&](float u, float v, float zm) -> float { return __fmul_rn(fmaf(k21, v, fmaf(k20, u, k22)), zm); };
+  // pixel coordinates of lane `lane` of 32-pixel word w0 without a per-pixel division when W % 32 == 0
+  const int wpr = (W & 31) == 0 ? (W >> 5) : 0;
+  auto word_uv = [&](int w0, float& u, float& v) {
+    if (wpr) { const int row = w0 / wpr; u = (float)(((w0 - row * wpr) << 5) + lane); v = (float)row; }
+    else { const int pix = w0 * 32 + lane; u = (float)(pix % W); v = (float)(pix / W); }
   };
 
   // pass A: mean z over non-zero pixels (:407)
   double sum = 0.0;
   int cnt = 0;
-  for (int pix = tid; pix < npx; pix += D2P_THREADS) {
-    const float z = z_of(pix, masked_depth(pix));
-    if (z != 0.f) { sum += (double)z; ++cnt; }
+  for (int w0 = warp; w0 < nwords; w0 += 32) {
+    const int pix = w0 * 32 + lane;
+    if (pix < npx) {
+      float u, v;
+      word_uv(w0, u, v);
+      const float z = z_uv(u, v, masked_depth(pix));
+      if (z != 0.f) { sum += (double)z; ++cnt; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -121,7 +129,9 @@ depth2pcl_kernel(const float* __restrict__ depth, const float* __restrict__ mask
     const int pix = w0 * 32 + lane;
     bool c = false;
     if (pix < npx && n_nonzero > 0) {
-      const float z = z_of(pix, masked_depth(pix));
+      float u, v;
+      word_uv(w0, u, v);
+      const float z = z_uv(u, v, masked_depth(pix));
       c = (z > lo) && (z < hi);
     }
     const unsigned b = __ballot_sync(0xffffffffu, c);
@@ -148,68 +158,75 @@ depth2pcl_kernel(const float* __restrict__ depth, const float* __restrict__ mask
     }
     n_sel = n_cand;
   } else if (n_cand > n_points) {
-    // random subset (:418-422): the n_points candidates with the smallest keys
+    // random subset (:418-422): the n_points candidates with the smallest keys.  Every pass walks the
+    // frame one 32-pixel word per warp iteration (lane = pixel): balanced, coalesced key loads.
     const int32_t* keys = subset_keys + (f * 2 + hand) * (int64_t)npx;
+    uint32_t* s_lt = s_bits + nwords;              // selected (key < threshold) bitmask
+    uint32_t* s_eq = s_bits + 2 * nwords;          // key == threshold bitmask
     uint32_t prefix = 0;
     int remaining = n_points;                      // rank (1-based) of the threshold inside the prefix bucket
     for (int shift = 24; shift >= 0; shift -= 8) {
       if (tid < 256) s_hist[tid] = 0;
       __syncthreads();
       const uint32_t hmask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
-      for (int w = wbeg; w < wend; ++w) {
-        unsigned b = s_bits[w];
-        while (b) {
-          const int bit = __ffs(b) - 1; b &= b - 1;
-          const uint32_t kx = (uint32_t)keys[w * 32 + bit] ^ 0x80000000u;   // signed order -> unsigned
+      for (int w0 = warp; w0 < nwords; w0 += 32) {
+        const unsigned bw = s_bits[w0];
+        if (bw == 0) continue;
+        const int pix = w0 * 32 + lane;
+        if ((bw >> lane) & 1u) {
+          const uint32_t kx = (uint32_t)__ldg(keys + pix) ^ 0x80000000u;     // signed order -> unsigned
           if ((kx & hmask) == prefix) atomicAdd(&s_hist[(kx >> shift) & 255], 1);
         }
       }
       __syncthreads();
-      if (tid == 0) {
-        int acc = 0, d = 0;
-        for (; d < 256; ++d) { if (acc + s_hist[d] >= remaining) break; acc += s_hist[d]; }
-        s_misc[1] = d; s_misc[2] = remaining - acc;
+      if (warp == 0) {                             // find the bucket holding the `remaining`-th key: warp scan over 256 bins
+        int h[8], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { h[q] = s_hist[lane * 8 + q]; sum += h[q]; }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        int acc = inc - sum;                       // keys in lower bins
+        const bool here = acc < remaining && remaining <= inc;
+        if (here) {
+          int d = 0;
+          for (; d < 8; ++d) { if (acc + h[d] >= remaining) break; acc += h[d]; }
+          s_misc[1] = lane * 8 + d; s_misc[2] = remaining - acc;
+        }
       }
       __syncthreads();
       prefix |= ((uint32_t)s_misc[1]) << shift;
       remaining = s_misc[2];
       __syncthreads();
     }
-    const uint32_t thr = prefix;                   // n_points-th smallest key; `remaining` ties allowed
-    // ordered enumeration: first rank the ties, then the selected set
+    const uint32_t thr = prefix;                   // n_points-th smallest key; `remaining` ties are taken
+    for (int w0 = warp; w0 < nwords; w0 += 32) {
+      const unsigned bw = s_bits[w0];
+      bool lt = false, eq = false;
+      if ((bw >> lane) & 1u) {
+        const uint32_t kx = (uint32_t)__ldg(keys + w0 * 32 + lane) ^ 0x80000000u;
+        lt = kx < thr; eq = kx == thr;
+      }
+      const unsigned blt = __ballot_sync(0xffffffffu, lt), beq = __ballot_sync(0xffffffffu, eq);
+      if (lane == 0) { s_lt[w0] = blt; s_eq[w0] = beq; }
+    }
+    __syncthreads();
+    // ties at the threshold: the first `remaining` in pixel order join the selection
     int c_eq = 0;
-    for (int w = wbeg; w < wend; ++w) {
-      unsigned b = s_bits[w];
-      while (b) {
-        const int bit = __ffs(b) - 1; b &= b - 1;
-        c_eq += (((uint32_t)keys[w * 32 + bit] ^ 0x80000000u) == thr) ? 1 : 0;
-      }
-    }
+    for (int w = wbeg; w < wend; ++w) c_eq += __popc(s_eq[w]);
     int tot;
-    int eq_rank = block_exclusive_scan(c_eq, s_warp, tot);
-    int c_sel = 0;
-    {
-      int er = eq_rank;
-      for (int w = wbeg; w < wend; ++w) {
-        unsigned b = s_bits[w];
-        while (b) {
-          const int bit = __ffs(b) - 1; b &= b - 1;
-          const uint32_t kx = (uint32_t)keys[w * 32 + bit] ^ 0x80000000u;
-          if (kx < thr || (kx == thr && er++ < remaining)) ++c_sel;
-        }
-      }
+    int er = block_exclusive_scan(c_eq, s_warp, tot);
+    for (int w = wbeg; w < wend; ++w) {
+      unsigned bq = s_eq[w], add = 0;
+      while (bq && er < remaining) { add |= bq & (0u - bq); bq &= bq - 1; ++er; }
+      s_lt[w] |= add;
     }
+    int c_sel = 0;
+    for (int w = wbeg; w < wend; ++w) c_sel += __popc(s_lt[w]);
     int r = block_exclusive_scan(c_sel, s_warp, tot);
-    {
-      int er = eq_rank;
-      for (int w = wbeg; w < wend; ++w) {
-        unsigned b = s_bits[w];
-        while (b) {
-          const int bit = __ffs(b) - 1; b &= b - 1;
-          const uint32_t kx = (uint32_t)keys[w * 32 + bit] ^ 0x80000000u;
-          if (kx < thr || (kx == thr && er++ < remaining)) { if (r < 1024) s_sel[r] = w * 32 + bit; ++r; }
-        }
-      }
+    for (int w = wbeg; w < wend; ++w) {
+      unsigned bsel = s_lt[w];
+      while (bsel) { const int bit = __ffs(bsel) - 1; bsel &= bsel - 1; if (r < 1024) s_sel[r] = w * 32 + bit; ++r; }
     }
     n_sel = n_points;
   }
@@ -239,11 +256,11 @@ extern "C" int pdf_depth2pcl(const float* depth, const float* mask, const float*
               "pdf_depth2pcl: null pointer");
   PDF_REQUIRE(B >= 0 && H > 0 && W > 0 && min_pixels >= 1, PDF_ERR_BAD_ARG, "pdf_depth2pcl: bad size");
   PDF_REQUIRE(n_points == 1024, PDF_ERR_UNSUPPORTED, "pdf_depth2pcl: n_points must be 1024 (got %d)", n_points);
-  PDF_REQUIRE((int64_t)H * W <= 1024 * 1024, PDF_ERR_UNSUPPORTED, "pdf_depth2pcl: frame larger than 1024x1024");
+  PDF_REQUIRE((int64_t)H * W <= 640 * 640, PDF_ERR_UNSUPPORTED, "pdf_depth2pcl: frame larger than 640x640");
   PDF_REQUIRE(subset_keys != nullptr || (int64_t)H * W <= n_points, PDF_ERR_BAD_ARG,
               "pdf_depth2pcl: subset_keys required when a hand can exceed n_points pixels");
   if (B == 0) return PDF_OK;
-  const size_t smem = (size_t)(((int64_t)H * W + 31) / 32) * 4;
+  const size_t smem = (size_t)(((int64_t)H * W + 31) / 32) * 4 * 3;      // candidate / selected / tie bitmasks
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(pdf::depth2pcl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);

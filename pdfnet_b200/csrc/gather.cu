@@ -75,45 +75,95 @@ __device__ __forceinline__ void gather_level(const float* __restrict__ plane0, i
   }
 }
 
-// Plane-local variant for n % 32 == 0 and C % 32 == 0 (the reference shapes): a warp gathers a
-// 32-point x 32-channel tile with lanes = points, so every load instruction of the warp stays
-// inside ONE channel plane (one DRAM page neighbourhood, the hand's pixel window) instead of 32
-// different planes; the tile is transposed through shared memory so stores stay coalesced.
-__device__ __forceinline__ void gather_level_tiled(const float* __restrict__ plane0, int C, int64_t HW, int R, int Rl,
-                                                   int div, const int64_t* __restrict__ ch, int n,
-                                                   float* __restrict__ out, int part, float (*tile)[33]) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int ct = C / 32, n_tiles = (n / 32) * ct;
-  for (int t = part * nwarps + warp; t < n_tiles; t += PG_SPLIT * nwarps) {
-    const int i0 = (t / ct) * 32, c0 = (t % ct) * 32;
-    const int pix = (int)ch[i0 + lane];
-    const float* src = plane0 + (int64_t)c0 * HW + ((pix / R / div) * Rl + (pix % R) / div);
-    float v[32];
+// Window variant (levels 1 and 2).  HBM serves 64 B per access, so a point-wise NCHW gather moves
+// 64 B per 4 B element.  The pixels of one hand are spatially compact, so a CTA instead loads the
+// BOUNDING WINDOW of the cloud's pixels for CG channel planes with coalesced 16 B loads into shared
+// memory and gathers from there; stores are CG contiguous floats per point.  Falls back to the
+// point-wise gather when the window does not fit the shared-memory budget.
+constexpr int PG_WIN_BYTES = 64 * 1024;
+
+template <int CG>
+__device__ __forceinline__ void gather_level_window(const float* __restrict__ plane0, int C, int64_t HW, int R,
+                                                    int Rl, int div, const int64_t* __restrict__ ch, int n,
+                                                    float* __restrict__ out, int c0, float* win, int* s_red) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int x0 = 1 << 30, x1 = -1, y0 = 1 << 30, y1 = -1;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int pix = (int)ch[i];
+    const int px = (pix % R) / div, py = pix / R / div;
+    x0 = min(x0, px); x1 = max(x1, px); y0 = min(y0, py); y1 = max(y1, py);
+  }
+  x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
+  y0 = __reduce_min_sync(0xffffffffu, y0); y1 = __reduce_max_sync(0xffffffffu, y1);
+  if (lane == 0) { s_red[warp * 4] = x0; s_red[warp * 4 + 1] = x1; s_red[warp * 4 + 2] = y0; s_red[warp * 4 + 3] = y1; }
+  __syncthreads();
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+    x0 = min(x0, s_red[w * 4]); x1 = max(x1, s_red[w * 4 + 1]);
+    y0 = min(y0, s_red[w * 4 + 2]); y1 = max(y1, s_red[w * 4 + 3]);
+  }
+  const int x0a = x0 & ~15;                                    // 64 B aligned start
+  const int Wa = min(((x1 - x0a + 1) + 15) & ~15, ((Rl - x0a) + 3) & ~3);
+  const int H = y1 - y0 + 1;
+  const bool fits = (Rl % 4 == 0) && (x0a + Wa <= Rl) && ((int64_t)CG * H * Wa * 4 <= PG_WIN_BYTES);
+  if (fits) {
+    const int wq = Wa >> 2, per_plane = H * wq;                // float4 units
+    constexpr int U = 8;                                       // independent 16 B loads in flight per thread
+    const int total = CG * per_plane;
+    for (int e0 = tid; e0 < total; e0 += blockDim.x * U) {
+      float4 v[U];
 #pragma unroll
-    for (int cc = 0; cc < 32; ++cc) v[cc] = __ldg(src + (int64_t)cc * HW);
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * blockDim.x;
+        if (e < total) {
+          const int c = e / per_plane, r = (e - c * per_plane) / wq, q = e - c * per_plane - r * wq;
+          v[u] = __ldg(reinterpret_cast<const float4*>(plane0 + (int64_t)(c0 + c) * HW + (int64_t)(y0 + r) * Rl + x0a) + q);
+        }
+      }
 #pragma unroll
-    for (int cc = 0; cc < 32; ++cc) tile[cc][lane] = v[cc];
-    __syncwarp();
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) out[(int64_t)(i0 + r) * C + c0 + lane] = tile[lane][r];
-    __syncwarp();
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * blockDim.x;
+        if (e < total) reinterpret_cast<float4*>(win)[e] = v[u];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int pix = (int)ch[i];
+      const int off = (pix / R / div - y0) * Wa + ((pix % R) / div - x0a);
+      float v[CG];
+#pragma unroll
+      for (int c = 0; c < CG; ++c) v[c] = win[c * H * Wa + off];
+      float4* o = reinterpret_cast<float4*>(out + (int64_t)i * C + c0);
+#pragma unroll
+      for (int c = 0; c < CG; c += 4) o[c >> 2] = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    }
+  } else {
+    for (int e = tid; e < n * CG; e += blockDim.x) {
+      const int i = e / CG, c = e - i * CG;
+      const int pix = (int)ch[i];
+      out[(int64_t)i * C + c0 + c] = __ldg(plane0 + (int64_t)(c0 + c) * HW + (pix / R / div) * Rl + (pix % R) / div);
+    }
   }
 }
+
+constexpr int PG_CG1 = 4, PG_CG2 = 16;                         // channels per CTA at level 1 / level 2
 
 __global__ void __launch_bounds__(256)
 pyramid_gather_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ choose, int clouds_per_frame,
                       int n_points, int n1, int n2, int R,
                       const float* __restrict__ l0, const float* __restrict__ l1, int C1,
                       const float* __restrict__ l2, int C2, const float* __restrict__ sft0,
-                      float* __restrict__ pts0, float* __restrict__ cond1, float* __restrict__ cond2) {
-  __shared__ float s_tile[8][32][33];
+                      float* __restrict__ pts0, float* __restrict__ cond1, float* __restrict__ cond2,
+                      int groups1, int groups2, int windowed) {
+  extern __shared__ __align__(16) float win[];
+  __shared__ int s_red[32];
+  __shared__ float P[48];
   const int64_t b = blockIdx.x;
   const int64_t f = b / clouds_per_frame;
   const int64_t* ch = choose + b * n_points;
   const int R2 = R / 2, R4 = R / 4;
   const int64_t RR = (int64_t)R * R, HW2 = (int64_t)R2 * R2, HW4 = (int64_t)R4 * R4;
-  if (blockIdx.y == 0) {
-    float* P = &s_tile[0][0][0];
+  const int y = blockIdx.y;
+  if (y == 0) {
     if (threadIdx.x < 48) P[threadIdx.x] = sft0[threadIdx.x];
     __syncthreads();
     const float* base = l0 + f * 3 * RR;
@@ -129,16 +179,15 @@ pyramid_gather_kernel(const float* __restrict__ xyz, const int64_t* __restrict__
 #pragma unroll
       for (int c = 0; c < 3; ++c) pts0[(b * n_points + i) * 3 + c] = p[c];
     }
-  } else if (blockIdx.y <= PG_SPLIT) {
-    const int part = blockIdx.y - 1;
-    if ((n1 & 31) == 0 && (C1 & 31) == 0)
-      gather_level_tiled(l1 + f * C1 * HW2, C1, HW2, R, R2, 2, ch, n1, cond1 + b * n1 * C1, part, s_tile[threadIdx.x >> 5]);
-    else gather_level(l1 + f * C1 * HW2, C1, HW2, R, R2, 2, ch, n1, cond1 + b * n1 * C1, part);
+  } else if (y <= groups1) {
+    if (windowed)
+      gather_level_window<PG_CG1>(l1 + f * C1 * HW2, C1, HW2, R, R2, 2, ch, n1, cond1 + b * n1 * C1, (y - 1) * PG_CG1, win, s_red);
+    else gather_level(l1 + f * C1 * HW2, C1, HW2, R, R2, 2, ch, n1, cond1 + b * n1 * C1, y - 1);
   } else {
-    const int part = blockIdx.y - 1 - PG_SPLIT;
-    if ((n2 & 31) == 0 && (C2 & 31) == 0)
-      gather_level_tiled(l2 + f * C2 * HW4, C2, HW4, R, R4, 4, ch, n2, cond2 + b * n2 * C2, part, s_tile[threadIdx.x >> 5]);
-    else gather_level(l2 + f * C2 * HW4, C2, HW4, R, R4, 4, ch, n2, cond2 + b * n2 * C2, part);
+    const int g = y - 1 - groups1;
+    if (windowed)
+      gather_level_window<PG_CG2>(l2 + f * C2 * HW4, C2, HW4, R, R4, 4, ch, n2, cond2 + b * n2 * C2, g * PG_CG2, win, s_red);
+    else gather_level(l2 + f * C2 * HW4, C2, HW4, R, R4, 4, ch, n2, cond2 + b * n2 * C2, g);
   }
 }
 
@@ -241,8 +290,18 @@ extern "C" int pdf_pyramid_gather(const float* xyz, const int64_t* choose, int64
               PDF_ERR_BAD_ARG, "pdf_pyramid_gather: bad size");
   if (n_clouds == 0) return PDF_OK;
   PDF_REQUIRE(n_clouds < (1ll << 31) && (int64_t)R * R < (1ll << 31), PDF_ERR_UNSUPPORTED, "pdf_pyramid_gather: too large");
-  pdf::pyramid_gather_kernel<<<dim3((unsigned)n_clouds, 1 + 2 * pdf::PG_SPLIT), 256, 0, (cudaStream_t)stream>>>(
-      xyz, choose, clouds_per_frame, n_points, n1, n2, R, l0, l1, C1, l2, C2, sft0_params, pts0, cond1, cond2);
+  // window variant needs whole channel groups and 16-byte aligned output rows
+  const int windowed = (C1 % pdf::PG_CG1 == 0) && (C2 % pdf::PG_CG2 == 0) && (R % 16 == 0);
+  const int groups1 = windowed ? C1 / pdf::PG_CG1 : pdf::PG_SPLIT, groups2 = windowed ? C2 / pdf::PG_CG2 : pdf::PG_SPLIT;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(pdf::pyramid_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pdf::PG_WIN_BYTES);
+    configured = true;
+  }
+  pdf::pyramid_gather_kernel<<<dim3((unsigned)n_clouds, 1 + groups1 + groups2), 256,
+                               windowed ? pdf::PG_WIN_BYTES : 0, (cudaStream_t)stream>>>(
+      xyz, choose, clouds_per_frame, n_points, n1, n2, R, l0, l1, C1, l2, C2, sft0_params, pts0, cond1, cond2,
+      groups1, groups2, windowed);
   return pdf::check_launch("pdf_pyramid_gather");
 }
 

@@ -25,10 +25,14 @@
 namespace pdf {
 using namespace umma;
 
-template <int CF_, int C1_, int C2_, int C3_, int SLOTS_>
+template <int CF_, int C1_, int C2_, int C3_, int SLOTS_, bool COMPACT_ = false>
 struct SaCfg {
   static constexpr int CF = CF_;        // feature channels gathered with each neighbour (0 or 128)
   static constexpr int C1 = C1_, C2 = C2_, C3 = C3_, SLOTS = SLOTS_;
+  // COMPACT: every accumulator of a tile (D1, D2, and layer 3 one 64-point group at a time) reuses
+  // the SAME 64 TMEM columns, so twice as many tiles are in flight per SM (TMEM, not issue slots or
+  // tensor throughput, is what limits the number of concurrent tiles); costs one more MMA phase.
+  static constexpr bool COMPACT = COMPACT_;
   static constexpr int KB1 = CF / 64, KB2 = C1 / 64, KB3 = C2 / 64;       // 64-wide SW128 K blocks per layer
   // weight image (bytes): [W1 feat blocks][W1 aux][W2 feat][W2 aux][W3 feat][W3 aux]
   static constexpr int W1_FEAT = KB1 * C1 * 128, W1_AUX = C1 * 32;
@@ -41,13 +45,16 @@ struct SaCfg {
   static constexpr int SLOT_FEAT = KBMAX * 128 * 128;                     // activation tile, in place
   static constexpr int SLOT_BYTES = SLOT_FEAT + 128 * 32;                 // + geometry/bias aux block
   static constexpr int SMEM_BYTES = W_BYTES + SLOTS * SLOT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int TMEM_PER_SLOT = (C3 > C1 + C2) ? C3 : ((C1 + C2) > 128 ? C1 + C2 : 128);
+  static constexpr int TMEM_PER_SLOT = COMPACT ? 64 : ((C3 > C1 + C2) ? C3 : ((C1 + C2) > 128 ? C1 + C2 : 128));
+  static_assert(!COMPACT || (C1 <= 64 && C2 <= 64 && C3 == 128), "COMPACT is the level-1 plan");
   static constexpr int THREADS = SLOTS * 128;
   static_assert(SLOTS * TMEM_PER_SLOT <= 512, "TMEM budget");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-using Sa1Cfg = SaCfg<0, 64, 64, 128, 4>;
+// (the COMPACT 8-slot plan measured slower on B200: level 1 is bound by shared-memory operand
+// bandwidth, not by the number of tiles in flight — see DESIGN.md section 3.1)
+using Sa1Cfg = SaCfg<0, 64, 64, 128, 4, false>;
 using Sa2Cfg = SaCfg<128, 128, 128, 256, 2>;
 
 // One layer = (KB SW128 K-blocks x 4 K-steps) + 1 aux K-step, accumulating into d_tmem.
@@ -130,7 +137,7 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
   const uint32_t bar = smem_u32(&s_bar[1 + slot]);
   const uint32_t d_base = tmem_base + slot * Cfg::TMEM_PER_SLOT;
   const uint32_t lane_off = ((uint32_t)(wslot * 32)) << 16;
-  const uint32_t d1 = d_base, d2 = d_base + Cfg::C1, d3 = d_base;
+  const uint32_t d1 = d_base, d2 = Cfg::COMPACT ? d_base : d_base + Cfg::C1, d3 = d_base;
   uint32_t phase = 0;
   const int tiles_per_cloud = n_centroids >> 1;
 
@@ -246,6 +253,34 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
     named_bar_sync(1 + slot, 128);
 
     // ---- layer 3 (transposed): D3[c3, p] = W3[c3, :] . H2[p, :] ; max over each 64-point group ----
+    if (Cfg::COMPACT) {
+      // one group (64 points = 8 row-groups of the H2 tile) per MMA phase, same 64 TMEM columns
+#pragma unroll 1
+      for (int grp = 0; grp < 2; ++grp) {
+        if (p == 0) {
+          fence_after_sync();
+          issue_layer<Cfg::KB3>(sw + Cfg::OFF_W3, Cfg::C3 * 128, sw + Cfg::OFF_W3A, sa_feat + grp * (64 * 128),
+                                128 * 128, sa_aux + grp * (64 * 32), d3, idesc_bf16(128, 64));
+          commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        fence_after_sync();
+        float mm = 0.f;                                  // ReLU floor
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(d3 + lane_off + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) mm = max3(mm, __uint_as_float(v[q]), __uint_as_float(v[q + 1]));
+        }
+        out[(b * n_centroids + g0 + grp) * ld_out + out_col0 + p] = mm;
+        if (grp == 0) {                                  // D3 of group 1 overwrites the columns just read
+          fence_before_sync();
+          named_bar_sync(1 + slot, 128);
+        }
+      }
+    } else {
     if (p == 0) {
       fence_after_sync();
 #pragma unroll
@@ -273,6 +308,7 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
       float* o = out + (b * n_centroids + g0) * ld_out + out_col0 + ch;
       o[0] = m[0];
       o[ld_out] = m[1];
+    }
     }
     if (p < 8) {                                         // centroid xyz + zero pad in the leading columns
       const int g = g0 + (p >> 2), c = p & 3;
