@@ -85,15 +85,29 @@ depth2pcl_kernel(const float* __restrict__ depth, const float* __restrict__ mask
     else { const int pix = w0 * 32 + lane; u = (float)(pix % W); v = (float)(pix / W); }
   };
 
+  // Every pass walks the frame one 32-pixel word per warp and keeps U words (U independent loads per
+  // thread) in flight: the kernel is otherwise bound by the latency of one load per iteration.
+  constexpr int U = 8;
   // pass A: mean z over non-zero pixels (:407)
   double sum = 0.0;
   int cnt = 0;
-  for (int w0 = warp; w0 < nwords; w0 += 32) {
-    const int pix = w0 * 32 + lane;
-    if (pix < npx) {
+  for (int wb = warp * U; wb < nwords; wb += 32 * U) {        // U consecutive words per warp batch
+    float d[U], m[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int pix = (wb + q) * 32 + lane;
+      const bool ok = pix < npx;
+      d[q] = ok ? __ldg(dep + pix) : 0.f;
+      m[q] = ok ? __ldg(msk + pix) : 0.f;
+    }
+    int row = wpr ? wb / wpr : 0, wcol = wpr ? wb - row * wpr : 0;   // one division per batch
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
       float u, v;
-      word_uv(w0, u, v);
-      const float z = z_uv(u, v, masked_depth(pix));
+      if (wpr) { u = (float)((wcol << 5) + lane); v = (float)row; if (++wcol == wpr) { wcol = 0; ++row; } }
+      else { const int pix = (wb + q) * 32 + lane; u = (float)(pix % W); v = (float)(pix / W); }
+      const bool keep = (0.2f < d[q]) && (2.5f > d[q]) && (m[q] > 0.5f);
+      const float z = z_uv(u, v, keep ? d[q] : 0.f);
       if (z != 0.f) { sum += (double)z; ++cnt; }
     }
   }
@@ -117,25 +131,43 @@ depth2pcl_kernel(const float* __restrict__ depth, const float* __restrict__ mask
       s_lohi[0] = fmaxf(0.2f, __fsub_rn(mean, 0.08f));     // :408
       s_lohi[1] = fminf(2.5f, __fadd_rn(mean, 0.08f));
       s_misc[0] = c;
+      s_misc[3] = 0;
     }
   }
   __syncthreads();
   const int n_nonzero = s_misc[0];
   const float lo = s_lohi[0], hi = s_lohi[1];
+  uint32_t* s_wlist = s_bits + 3 * nwords;
 
-  // pass B: candidate bitmask (:409), one word per warp iteration (coalesced)
+  // pass B: candidate bitmask (:409)
   int my_cand = 0;
-  for (int w0 = warp; w0 < nwords; w0 += 32) {
-    const int pix = w0 * 32 + lane;
-    bool c = false;
-    if (pix < npx && n_nonzero > 0) {
-      float u, v;
-      word_uv(w0, u, v);
-      const float z = z_uv(u, v, masked_depth(pix));
-      c = (z > lo) && (z < hi);
+  for (int wb = warp * U; wb < nwords; wb += 32 * U) {
+    float d[U], m[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int pix = (wb + q) * 32 + lane;
+      const bool ok = pix < npx;
+      d[q] = ok ? __ldg(dep + pix) : 0.f;
+      m[q] = ok ? __ldg(msk + pix) : 0.f;
     }
-    const unsigned b = __ballot_sync(0xffffffffu, c);
-    if (lane == 0) { s_bits[w0] = b; my_cand += __popc(b); }
+    int row = wpr ? wb / wpr : 0, wcol = wpr ? wb - row * wpr : 0;
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int w0 = wb + q;
+      float u, v;
+      if (wpr) { u = (float)((wcol << 5) + lane); v = (float)row; if (++wcol == wpr) { wcol = 0; ++row; } }
+      else { const int pix = w0 * 32 + lane; u = (float)(pix % W); v = (float)(pix / W); }
+      if (w0 < nwords) {                               // warp-uniform
+        const bool keep = (0.2f < d[q]) && (2.5f > d[q]) && (m[q] > 0.5f);
+        const float z = z_uv(u, v, keep ? d[q] : 0.f);
+        const bool c = n_nonzero > 0 && (z > lo) && (z < hi);
+        const unsigned b = __ballot_sync(0xffffffffu, c);
+        if (lane == 0) {
+          s_bits[w0] = b; my_cand += __popc(b);
+          if (b) s_wlist[atomicAdd(&s_misc[3], 1)] = w0;   // non-empty words (unordered) for the key passes
+        }
+      }
+    }
   }
   int n_cand;
   (void)block_exclusive_scan(my_cand, s_warp, n_cand);
@@ -163,20 +195,26 @@ depth2pcl_kernel(const float* __restrict__ depth, const float* __restrict__ mask
     const int32_t* keys = subset_keys + (f * 2 + hand) * (int64_t)npx;
     uint32_t* s_lt = s_bits + nwords;              // selected (key < threshold) bitmask
     uint32_t* s_eq = s_bits + 2 * nwords;          // key == threshold bitmask
+    const int n_words_used = s_misc[3];
     uint32_t prefix = 0;
     int remaining = n_points;                      // rank (1-based) of the threshold inside the prefix bucket
     for (int shift = 24; shift >= 0; shift -= 8) {
       if (tid < 256) s_hist[tid] = 0;
       __syncthreads();
       const uint32_t hmask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
-      for (int w0 = warp; w0 < nwords; w0 += 32) {
-        const unsigned bw = s_bits[w0];
-        if (bw == 0) continue;
-        const int pix = w0 * 32 + lane;
-        if ((bw >> lane) & 1u) {
-          const uint32_t kx = (uint32_t)__ldg(keys + pix) ^ 0x80000000u;     // signed order -> unsigned
-          if ((kx & hmask) == prefix) atomicAdd(&s_hist[(kx >> shift) & 255], 1);
+      for (int wb = warp; wb < n_words_used; wb += 32 * U) {
+        uint32_t kx[U];
+        bool on[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+          const int li = wb + q * 32;
+          const int w0 = li < n_words_used ? (int)s_wlist[li] : 0;
+          on[q] = li < n_words_used && ((s_bits[w0] >> lane) & 1u);
+          kx[q] = on[q] ? ((uint32_t)__ldg(keys + w0 * 32 + lane) ^ 0x80000000u) : 0u;   // signed order -> unsigned
         }
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+          if (on[q] && (kx[q] & hmask) == prefix) atomicAdd(&s_hist[(kx[q] >> shift) & 255], 1);
       }
       __syncthreads();
       if (warp == 0) {                             // find the bucket holding the `remaining`-th key: warp scan over 256 bins
@@ -200,15 +238,27 @@ depth2pcl_kernel(const float* __restrict__ depth, const float* __restrict__ mask
       __syncthreads();
     }
     const uint32_t thr = prefix;                   // n_points-th smallest key; `remaining` ties are taken
-    for (int w0 = warp; w0 < nwords; w0 += 32) {
-      const unsigned bw = s_bits[w0];
-      bool lt = false, eq = false;
-      if ((bw >> lane) & 1u) {
-        const uint32_t kx = (uint32_t)__ldg(keys + w0 * 32 + lane) ^ 0x80000000u;
-        lt = kx < thr; eq = kx == thr;
+    for (int w = tid; w < nwords; w += D2P_THREADS) { s_lt[w] = 0; s_eq[w] = 0; }
+    __syncthreads();
+    for (int wb = warp; wb < n_words_used; wb += 32 * U) {
+      uint32_t kx[U];
+      bool on[U];
+      int wq[U];
+#pragma unroll
+      for (int q = 0; q < U; ++q) {
+        const int li = wb + q * 32;
+        wq[q] = li < n_words_used ? (int)s_wlist[li] : -1;
+        on[q] = wq[q] >= 0 && ((s_bits[wq[q]] >> lane) & 1u);
+        kx[q] = on[q] ? ((uint32_t)__ldg(keys + wq[q] * 32 + lane) ^ 0x80000000u) : 0u;
       }
-      const unsigned blt = __ballot_sync(0xffffffffu, lt), beq = __ballot_sync(0xffffffffu, eq);
-      if (lane == 0) { s_lt[w0] = blt; s_eq[w0] = beq; }
+#pragma unroll
+      for (int q = 0; q < U; ++q) {
+        if (wq[q] >= 0) {                              // warp-uniform
+          const unsigned blt = __ballot_sync(0xffffffffu, on[q] && kx[q] < thr);
+          const unsigned beq = __ballot_sync(0xffffffffu, on[q] && kx[q] == thr);
+          if (lane == 0) { s_lt[wq[q]] = blt; s_eq[wq[q]] = beq; }
+        }
+      }
     }
     __syncthreads();
     // ties at the threshold: the first `remaining` in pixel order join the selection
@@ -260,10 +310,10 @@ extern "C" int pdf_depth2pcl(const float* depth, const float* mask, const float*
   PDF_REQUIRE(subset_keys != nullptr || (int64_t)H * W <= n_points, PDF_ERR_BAD_ARG,
               "pdf_depth2pcl: subset_keys required when a hand can exceed n_points pixels");
   if (B == 0) return PDF_OK;
-  const size_t smem = (size_t)(((int64_t)H * W + 31) / 32) * 4 * 3;      // candidate / selected / tie bitmasks
+  const size_t smem = (size_t)(((int64_t)H * W + 31) / 32) * 4 * 4;      // candidate / selected / tie bitmasks + word list
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(pdf::depth2pcl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(pdf::depth2pcl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     attr_set = true;
   }
   pdf::depth2pcl_kernel<<<(unsigned)(B * 2), pdf::D2P_THREADS, smem, (cudaStream_t)stream>>>(
