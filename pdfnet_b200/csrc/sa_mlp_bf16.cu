@@ -147,13 +147,13 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
   // with other work if its first USE is an iteration away): the neighbour index of tile t+2 and the
   // raw coordinates of tile t+1 are in flight while tile t runs its three MMA phases.
   auto load_idx = [&](int64_t t) -> int {
-    const int64_t b = t / tiles_per_cloud;
-    const int g0 = (int)(t % tiles_per_cloud) * 2;
+    const int64_t b = (uint32_t)t / (uint32_t)tiles_per_cloud;        // n_tiles < 2^31 (checked by the launcher)
+    const int g0 = (int)((uint32_t)t % (uint32_t)tiles_per_cloud) * 2;
     return __ldg(idx + (b * n_centroids + g0) * 64 + p);
   };
   auto load_raw = [&](int64_t t, int j, float (&sp)[3], float (&cp)[3]) {
-    const int64_t b = t / tiles_per_cloud;
-    const int g0 = (int)(t % tiles_per_cloud) * 2;
+    const int64_t b = (uint32_t)t / (uint32_t)tiles_per_cloud;
+    const int g0 = (int)((uint32_t)t % (uint32_t)tiles_per_cloud) * 2;
     const float* cloud = pts + b * n_src * ld_pts;
     const float* src = cloud + (int64_t)j * ld_pts;
     const float* cen = cloud + (int64_t)(g0 + (p >> 6)) * ld_pts;
@@ -167,12 +167,16 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
   if (t_first + t_step < n_tiles) j_next = load_idx(t_first + t_step);
 
   for (int64_t t = t_first; t < n_tiles; t += t_step) {
-    const int64_t b = t / tiles_per_cloud;
-    const int g0 = (int)(t % tiles_per_cloud) * 2;
+    const int64_t b = (uint32_t)t / (uint32_t)tiles_per_cloud;
+    const int g0 = (int)((uint32_t)t % (uint32_t)tiles_per_cloud) * 2;
     const float* cloud = pts + b * n_src * ld_pts;
     const int32_t* tidx = idx + (b * n_centroids + g0) * 64;
     // p_j - c_i in fp32, the reference's operand order (utils.py:142-143)
     const float rx = __fsub_rn(sp[0], cp[0]), ry = __fsub_rn(sp[1], cp[1]), rz = __fsub_rn(sp[2], cp[2]);
+    if ((p & 63) == 0 && out_col0 > 0) {                   // centroid xyz (+ zero pad) into the leading columns,
+      float* o = out + (b * n_centroids + g0 + (p >> 6)) * ld_out;   // straight from the prefetched registers
+      for (int c = 0; c < out_col0; ++c) o[c] = c < 3 ? cp[c] : 0.f;
+    }
 
     // ---- gather: geometry/bias block (thread = row, prefetched one tile ahead) ----
     {
@@ -310,11 +314,6 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
       o[ld_out] = m[1];
     }
     }
-    if (p < 8) {                                         // centroid xyz + zero pad in the leading columns
-      const int g = g0 + (p >> 2), c = p & 3;
-      if (c < out_col0)
-        out[(b * n_centroids + g) * ld_out + c] = (c < 3) ? cloud[(int64_t)g * ld_pts + c] : 0.f;
-    }
   }
 
   fence_before_sync();
@@ -388,6 +387,10 @@ static int launch_sa(const float* pts, int64_t n_clouds, int n_src, int64_t ld_p
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t n_tiles = n_clouds * (n_centroids / 2);
+  if (n_tiles >= (1ll << 31)) {
+    set_error("pdf_sa_mlp_max_bf16: too many tiles (%lld)", (long long)n_tiles);
+    return PDF_ERR_UNSUPPORTED;
+  }
   int64_t grid = (n_tiles + Cfg::SLOTS - 1) / Cfg::SLOTS;
   if (grid > sms) grid = sms;
   sa_mlp_max_kernel<Cfg><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(

@@ -134,6 +134,7 @@ class PointNet_Plus(nn.Module):
             nn.Linear(nstates_plus_3[4], self.num_outputs))
         self._folded = None
         self._folded_key = None
+        self.chunk_clouds = None      # clouds per internal pass (None: 256 in fp32 mode, 2048 in bf16 mode)
 
     # -- folded / packed parameters, rebuilt when any parameter or buffer changes --
     def _params_key(self):
@@ -199,7 +200,7 @@ class PointNet_Plus(nn.Module):
         L.require_cuda(points, choose, *emb)
         with torch.no_grad():
             B = points.shape[0]
-            chunk = 256 if self.precision == "fp32" else 2048
+            chunk = self.chunk_clouds or (256 if self.precision == "fp32" else 2048)
             if B <= chunk:
                 return self._forward_chunk(points, emb, choose, clouds_per_frame, 0)
             assert chunk % clouds_per_frame == 0

@@ -1,18 +1,23 @@
 #!/bin/bash
-# Full GPU test-suite + bench + ncu launch list + one full ncu capture of the tensor-core kernels.
+# Round profile: full GPU test-suite, smoke, bench (both precisions), ncu launch list of the bench command,
+# and one `ncu --set full` capture of every kernel of one step.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_gpu.log 2>&1
 echo "exit $?" >> gpurun_out/pytest_gpu.log
-tail -8 gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -3 gpurun_out/smoke.log
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
-tail -c 2500 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
-# launch list of one bench (device-resident loop): warmup 3 + 2 steps
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+tail -c 600 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+timeout 600 python bench.py --steps 10 --warmup 3 --precision fp32 > gpurun_out/bench_fp32.json 2> gpurun_out/bench_fp32.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/smi.txt 2>&1
+# launch list of the bench command (warm-up 3 + 2 steps)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
    --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_bench.log 2>&1
 echo "launch rows: $(wc -l < gpurun_out/launches.csv)"
-# full capture of the dominant kernels
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${PDF_NCU_KERNELS:-sa_mlp_max_kernel}" -s 6 -c 2 \
-   -f -o gpurun_out/prof_sa python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1
+# full capture of one step of our kernels (4th step)
+timeout 1200 ncu --set full --clock-control none --import-source on \
+   -k regex:"^(sa_mlp|gemm_bf16|knn_ball|pyramid|rows_to|depth2pcl|mano|linear_f32|split_coeff)" -s 96 -c 32 \
+   -f -o gpurun_out/prof_step python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out/*.ncu-rep

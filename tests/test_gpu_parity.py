@@ -555,3 +555,71 @@ def test_gemm_xyz_mode_matches_fp32_sft():
     assert rel_err(y[:, :3].cpu(), ref.cpu()) < 2e-5 and torch.equal(y[:, 3:], x[:, 3:])
     dec = _decode_image(himg.cpu().numpy(), 1024, 128)
     assert rel_err(dec[:M], hid_ref.cpu().numpy()) < 1e-2 and (dec[M:] == 0).all()
+
+
+# ----------------------------------------------------------------------------- edge cases
+
+def test_knn_degenerate_clouds():
+    from pdfnet_b200 import ops
+    # all points identical: every distance ties at 0 -> the 64 lowest indices, nothing masked
+    pts = torch.full((2, 1024, 3), 0.25)
+    idx = ops.knn_ball(pts.to(DEV), 512, 64, 0.01).cpu().numpy()
+    assert (np.sort(idx, -1) == np.arange(64)[None, None, :]).all()
+    # k == n_points: every point is a neighbour; beyond the radius -> centroid index
+    pts = synth.clouds(2, n_points=64, seed=3, sigma=0.2)
+    idx = ops.knn_ball(pts.to(DEV), 64, 64, 0.01).cpu().numpy()
+    assert (np.sort(idx, -1) == O.knn_ball_indices(pts.numpy(), 64, 64, 0.01)).all()
+    # radius 0: only exact duplicates of the centroid survive, all others collapse to the centroid index
+    pts = synth.clouds(1, seed=4, wrap_from=600)
+    idx = ops.knn_ball(pts.to(DEV), 512, 64, 0.0).cpu().numpy()
+    assert (np.sort(idx, -1) == O.knn_ball_indices(pts.numpy(), 512, 64, 0.0)).all()
+    # huge coordinates / large radius
+    pts = synth.clouds(1, seed=5) * 1000.0
+    idx = ops.knn_ball(pts.to(DEV), 512, 64, 1e12).cpu().numpy()
+    assert (np.sort(idx, -1) == O.knn_ball_indices(pts.numpy(), 512, 64, 1e12)).all()
+
+
+def test_depth2pcl_edge_cases():
+    from pdfnet_b200 import ops
+    R = 64
+    depth, mask, K, valid = synth.rgbd_frames(3, R, seed=8)
+    mask[0] = 0                                       # frame 0: no hand pixels at all -> zeros / pixel-0 cloud
+    depth[1] = 5.0                                    # frame 1: everything beyond Z_max -> gated out
+    Kinv = torch.linalg.inv(K)
+    keys = torch.zeros((3, 2, R * R), dtype=torch.int32)       # constant keys: every candidate ties
+    perm = torch.arange(1024, dtype=torch.int32).flip(0).expand(3, 2, 1024).contiguous()
+    choose, cloud, n_cand = ops.depth2pcl(depth.to(DEV), mask.to(DEV), Kinv.to(DEV), valid.to(DEV), keys.to(DEV),
+                                          perm.to(DEV))
+    assert int(n_cand[0].sum()) == 0 and int(choose[0].abs().sum()) == 0 and float(cloud[0].abs().sum()) == 0
+    assert int(n_cand[1].sum()) == 0 and int(choose[1].abs().sum()) == 0
+    for b in range(3):
+        ch, cl = O.depth2pcl(depth[b].numpy(), mask[b:b + 1].numpy(), K[b].numpy(), valid[b:b + 1].numpy(),
+                             keys[b].numpy(), perm[b].numpy())
+        assert (choose[b].cpu().numpy() == ch).all(), b
+        assert rel_err(cloud[b].cpu().numpy(), cl) < 1e-6 or np.abs(cl).max() == 0
+    # identity permutation / no keys needed when no hand can exceed 1024 pixels
+    d2, m2, K2, v2 = synth.rgbd_frames(1, 32, seed=9)
+    c2, _, _ = ops.depth2pcl(d2.to(DEV), m2.to(DEV), torch.linalg.inv(K2).to(DEV), v2.to(DEV), None, None)
+    ch, _ = O.depth2pcl(d2[0].numpy(), m2.numpy(), K2[0].numpy(), v2.numpy(), np.zeros((2, 1024), np.int32),
+                        np.stack([np.arange(1024)] * 2))
+    assert (c2[0].cpu().numpy() == ch).all()
+
+
+def test_pointnet_plus_chunking_and_two_hand_batching():
+    """Internal chunking over clouds and the clouds_per_frame=2 batching give identical results."""
+    from pdfnet_b200 import PointNet_Plus
+    R, B = 64, 3
+    emb = [e.to(DEV) for e in synth.pyramid(B, R, seed=21)]
+    pts = synth.clouds(2 * B, seed=21).to(DEV)
+    choose = synth.choose_indices(2 * B, R, seed=21).to(DEV)
+    for prec in ("fp32", "bf16"):
+        m = PointNet_Plus(_opt(default_resolution=R), precision=prec)
+        m.load_state_dict(synth.pointnet_plus_state(seed=317), strict=False)
+        m = m.to(DEV).eval()
+        full = m(pts, emb, choose, clouds_per_frame=2)
+        m.chunk_clouds = 2
+        chunked = m(pts, emb, choose, clouds_per_frame=2)
+        assert torch.equal(full, chunked)
+        m.chunk_clouds = None
+        left = m(pts[0::2].contiguous(), emb, choose[0::2].contiguous())        # the reference's per-hand call
+        assert torch.equal(left, full[0::2])
