@@ -179,6 +179,16 @@ int pdf_sft_xyz_f32(const float* cond, int64_t M, int cc, const float* w0s, cons
                     const float* b1s, const float* w0h, const float* b0h, const float* w1h, const float* b1h,
                     float* x, int64_t ldx, void* stream);
 
+/* Centre features evaluated only where they are used.  The reference runs two 3x3
+ * convolutions over the whole (R/4)^2 map, center_feat_up1(center_feat_up0(x0)), and then keeps the
+ * 2 pixels at `ind` (intaghand_encoder.py:627-628,790-792).  This builds, for every (frame, hand),
+ * the im2col rows of the 3x3 conv0 outputs that conv1 needs at the centre pixel:
+ * rows fp32 [B*2*9, 9*C], row (b,hand,pos) = 3x3xC input patch around output position pos (K order:
+ * tap-major, channel-minor; zero padding; all-zero rows for positions outside the map).  The two
+ * convolutions are then two GEMMs (pdf_linear_f32 / pdf_gemm_bf16) with re-laid weights.
+ * x0 fp32 [B,C,H,W]; ind int64 [B,2] flat index on the HxW map. */
+int pdf_center_im2col(const float* x0, const int64_t* ind, int64_t B, int C, int H, int W, float* rows, void* stream);
+
 /* Depth back-projection xyz[b,:,v,u] = (Kinv[b] * [u,v,1]) * depth[b,v,u].
  * Replaces get_points_coordinate (lib/utils/utils.py:251-262).  depth fp32
  * [B,H,W], Kinv fp32 [B,3,3] (inverse intrinsics, computed by the caller as the

@@ -197,6 +197,15 @@ def fusion_tail(sd_pointnet, sd_sft, cloud, emb, choose, center_features, opt):
         return sft_layer(fuse.transpose(1, 2).contiguous(), torch.as_tensor(center_features), sd_sft, "")
 
 
+def center_features(x0, w_up0, w_up1, ind):
+    """ResNetSimple.forward centre features, intaghand_encoder.py:790-792:
+    x0_up1 = center_feat_up1(center_feat_up0(x0)) (3x3, pad 1, no bias) over the WHOLE map, then
+    _tranpose_and_gather_feat(x0_up1, ind).  x0 [B,C,H,W], ind [B,2] -> [B,2,1024]."""
+    with torch.no_grad():
+        up1 = F.conv2d(F.conv2d(torch.as_tensor(x0), w_up0, padding=1), w_up1, padding=1)
+        return tranpose_and_gather_feat(up1, ind)
+
+
 # ----------------------------------------------------------------------------
 # farthest point sampling
 # ----------------------------------------------------------------------------

@@ -14,7 +14,7 @@ _COMPUTE = {
     "group_points": "grouping", "group_points_2": "grouping", "farthest_point_sample": "grouping",
     "query_ball_point": "grouping", "index_points": "grouping", "sample_and_group": "grouping",
     "_tranpose_and_gather_feat": "encoder", "SFTLayer": "encoder", "PointNet_Plus": "encoder",
-    "HandFusion": "encoder", "depth2pcl": "encoder", "depth2pcl_batched": "encoder",
+    "HandFusion": "encoder", "CenterFeatures": "encoder", "depth2pcl": "encoder", "depth2pcl_batched": "encoder",
     "get_points_coordinate": "encoder", "ManoLayer": "manolayer", "Split_coeff": "manolayer",
     "mano_tail": "manolayer", "patch_reference": "patch",
 }

@@ -31,6 +31,7 @@ SIGNATURES = {
     "pdf_gemm_bf16": [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _i64, _vp, _i64,
                       _vp, _i32, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp],
     "pdf_sft_xyz_f32": [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "pdf_center_im2col": [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp],
     "pdf_backproject": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
     "pdf_depth2pcl": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "pdf_mano_lbs": [_vp] * 11 + [_i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],

@@ -257,6 +257,31 @@ __global__ void split_coeff_kernel(const float* __restrict__ theta, int64_t ld, 
   trans[i * 3 + 2] = tz;
 }
 
+// im2col of the 3x3 neighbourhood of outputs around each centre pixel, for evaluating
+// center_feat_up1(center_feat_up0(x0)) ONLY at `ind` (intaghand_encoder.py:790-792):
+// row (b, hand, pos) holds the 3x3x C input patch of conv0 output position pos (K order: tap-major,
+// channel-minor); positions outside the map are all-zero rows (zero padding of the INTERMEDIATE).
+__global__ void center_im2col_kernel(const float* __restrict__ x0, const int64_t* __restrict__ ind, int C, int H,
+                                     int W, float* __restrict__ rows, int64_t total) {
+  const int K = 9 * C;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(e % K);
+    const int64_t row = e / K;
+    const int pos = (int)(row % 9);
+    const int64_t bh = row / 9;                        // b * 2 + hand
+    const int64_t b = bh >> 1;
+    const int centre = (int)ind[bh];
+    const int py = centre / W + pos / 3 - 1, px = centre % W + pos % 3 - 1;
+    const int tap = k / C, c = k - tap * C;
+    const int y = py + tap / 3 - 1, x = px + tap % 3 - 1;
+    float v = 0.f;
+    if (py >= 0 && py < H && px >= 0 && px < W && y >= 0 && y < H && x >= 0 && x < W)
+      v = __ldg(x0 + ((b * C + c) * H + y) * (int64_t)W + x);
+    rows[e] = v;
+  }
+}
+
 static inline unsigned grid_for(int64_t total, int block, int max_blocks = 148 * 16) {
   int64_t g = (total + block - 1) / block;
   if (g > max_blocks) g = max_blocks;
@@ -340,4 +365,15 @@ extern "C" int pdf_split_coeff(const float* theta, int64_t ld_theta, int col0, c
   pdf::split_coeff_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       theta, ld_theta, col0, index, K, n, input_res, down_ratio, root, pose, shape, trans);
   return pdf::check_launch("pdf_split_coeff");
+}
+
+extern "C" int pdf_center_im2col(const float* x0, const int64_t* ind, int64_t B, int C, int H, int W, float* rows,
+                                 void* stream) {
+  if (B == 0) return PDF_OK;
+  PDF_REQUIRE(x0 && ind && rows, PDF_ERR_BAD_ARG, "pdf_center_im2col: null pointer");
+  PDF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, PDF_ERR_BAD_ARG, "pdf_center_im2col: bad size");
+  const int64_t total = B * 2 * 9 * 9 * C;
+  pdf::center_im2col_kernel<<<pdf::grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(x0, ind, C, H, W,
+                                                                                                  rows, total);
+  return pdf::check_launch("pdf_center_im2col");
 }

@@ -443,6 +443,59 @@ def _mano_head_tc_impl(self, x, key, w):
 HandFusion._mano_head_tc = _mano_head_tc_impl
 
 
+class CenterFeatures(nn.Module):
+    """center_feat_up0 / center_feat_up1 + the centre gather of ResNetSimple.forward
+    (intaghand_encoder.py:627-628, 790-792), evaluated only at ``ind``: numerically the
+    same as convolving the whole map and gathering 2 pixels, at 1/2000 of the work.  Parameter names
+    follow ResNetSimple (``center_feat_up0.weight`` [512,256,3,3], ``center_feat_up1.weight`` [1024,512,3,3])."""
+
+    def __init__(self, c_in=256, c_mid=512, c_out=1024, precision="fp32"):
+        super(CenterFeatures, self).__init__()
+        self.center_feat_up0 = nn.Conv2d(c_in, c_mid, kernel_size=3, stride=1, padding=1, bias=False)
+        self.center_feat_up1 = nn.Conv2d(c_mid, c_out, kernel_size=3, stride=1, padding=1, bias=False)
+        self.precision = precision
+        self._key = None
+
+    def _weights(self, dev):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (self.precision, str(dev))
+        if self._key != key:
+            # K order of the im2col rows: tap-major, channel-minor
+            w0 = self.center_feat_up0.weight.detach().permute(0, 2, 3, 1).reshape(self.center_feat_up0.out_channels, -1)
+            w1 = self.center_feat_up1.weight.detach().permute(0, 2, 3, 1).reshape(self.center_feat_up1.out_channels, -1)
+            if self.precision == "bf16":
+                self._w = (ops.pack_image(w0, split=True).to(dev), ops.pack_image(w1, split=True).to(dev))
+            else:
+                self._w = (w0.contiguous().to(dev), w1.contiguous().to(dev))
+            self._zero = torch.zeros((max(w0.shape[0], w1.shape[0]),), dtype=torch.float32, device=dev)
+            self._key = key
+        return self._w
+
+    def forward(self, x0, ind):
+        """x0 [B,C,H,W] fp32 (the 1/4-resolution feature map), ind [B,2] -> center_features [B,2,c_out]."""
+        L.require_cuda(x0, ind)
+        with torch.no_grad():
+            B = x0.shape[0]
+            w0, w1 = self._weights(x0.device)
+            cm, co = self.center_feat_up0.out_channels, self.center_feat_up1.out_channels
+            rows = ops.center_im2col(x0, ind)                                  # [B*18, 9*C]
+            if self.precision != "bf16":
+                mid = ops.linear(rows, w0)                                     # conv0 at the 9 positions
+                return ops.linear(mid.view(B * 2, 9 * cm), w1).view(B, 2, co)  # conv1 at the centre
+            # split-bf16 tensor-core GEMMs (fp32-accurate products, fp32 accumulate)
+            M0, K0 = rows.shape
+            kb0 = (K0 + 63) // 64 * 3
+            mid = torch.empty((M0, cm), dtype=torch.float32, device=x0.device)
+            ops.gemm_bf16(ops.rows_to_image(rows, 0, K0, split=True), (M0 + 127) // 128, kb0, w0, cm // 128, kb0, kb0,
+                          self._zero, out_f32=mid, rows_valid=M0, tile_desc=[(128 * i, 128, 0) for i in range(cm // 128)])
+            mid2 = mid.view(B * 2, 9 * cm)
+            M1, K1 = mid2.shape
+            kb1 = (K1 + 63) // 64 * 3
+            out = torch.empty((M1, co), dtype=torch.float32, device=x0.device)
+            ops.gemm_bf16(ops.rows_to_image(mid2, 0, K1, split=True), (M1 + 127) // 128, kb1, w1, co // 128, kb1, kb1,
+                          self._zero, out_f32=out, rows_valid=M1, tile_desc=[(128 * i, 128, 0) for i in range(co // 128)])
+            return out.view(B, 2, co)
+
+
 def _fold_bn_linear(fc, bn):
     s = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
     w = (fc.weight.detach().double() * s[:, None]).float().contiguous()

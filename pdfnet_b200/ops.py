@@ -207,6 +207,17 @@ def sft_xyz(cond_rows, weights, x_rows):
            L.stream())
 
 
+def center_im2col(x0, ind):
+    """im2col rows [B*2*9, 9*C] of the conv0 outputs that conv1 needs at the centre pixels (pdf_center_im2col)."""
+    L.require_cuda(x0, ind)
+    x0 = L.f32c(x0)
+    ind = ind.long().contiguous()
+    B, C, H, W = x0.shape
+    rows = torch.empty((B * 2 * 9, 9 * C), dtype=torch.float32, device=x0.device)
+    L.call("pdf_center_im2col", L.ptr(x0), L.ptr(ind), B, C, H, W, L.ptr(rows), L.stream())
+    return rows
+
+
 def backproject(depth, Kinv):
     """xyz [B,3,H,W] = (Kinv @ [u,v,1]) * depth ; depth [B,H,W] fp32, Kinv [B,3,3] fp32."""
     L.require_cuda(depth, Kinv)

@@ -623,3 +623,22 @@ def test_pointnet_plus_chunking_and_two_hand_batching():
         m.chunk_clouds = None
         left = m(pts[0::2].contiguous(), emb, choose[0::2].contiguous())        # the reference's per-hand call
         assert torch.equal(left, full[0::2])
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 1e-4)])
+def test_center_features_only_at_ind(precision, tol):
+    """two 3x3 convs evaluated only at `ind` == full-map convs + gather (incl. border pixels)."""
+    from pdfnet_b200 import CenterFeatures
+    g = torch.Generator().manual_seed(13)
+    B, C, H, W = 5, 256, 16, 16
+    x0 = torch.relu(torch.randn((B, C, H, W), generator=g))
+    m = CenterFeatures(precision=precision)
+    w0 = torch.randn((512, 256, 3, 3), generator=g) * 0.02
+    w1 = torch.randn((1024, 512, 3, 3), generator=g) * 0.02
+    m.load_state_dict({"center_feat_up0.weight": w0, "center_feat_up1.weight": w1})
+    m = m.to(DEV).eval()
+    ind = torch.tensor([[0, W - 1], [(H - 1) * W, H * W - 1], [5 * W + 7, 1], [W, 2 * W - 1], [8 * W + 8, 15 * W + 3]])
+    out = m(x0.to(DEV), ind.to(DEV))
+    ref = O.center_features(x0, w0, w1, ind)
+    assert out.shape == (B, 2, 1024)
+    assert rel_err(out.cpu(), ref) < tol
