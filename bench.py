@@ -311,9 +311,17 @@ def run_ours(args):
              "sft1": FLOP_SFT1 * n_clouds, "sft2": FLOP_SFT2 * n_clouds}
     dom = max(flops, key=lambda k: stage_ms.get(k, 0.0))
     ach = flops[dom] / (stage_ms[dom] * 1e-3) / 1e12
-    tensor_stage = args.precision == "bf16" and dom in ("sa1", "sa2")
+    tensor_stage = args.precision == "bf16" and dom in ("sa1", "sa2", "global_mlp")
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/), if any
+    traffic = None
+    for cand in sorted((f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_dram_traffic.json")),
+                       reverse=True) if os.path.isdir(os.path.join(ROOT, "profiles")) else []:
+        tj = json.load(open(os.path.join(ROOT, "profiles", cand)))
+        if dom in tj and args.precision == "bf16" and B == 128:
+            traffic = tj[dom]
+        break
     roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peaks["source"],
                 "pipe": "tcgen05 bf16" if tensor_stage else "FFMA fp32 (stage not yet on tensor cores)",
                 "launch_ms": stage_ms[dom]}
     stage_report = {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}

@@ -15,10 +15,23 @@ namespace pdf {
 // compare per point per bit.  Ties at the k-th distance go to the lowest index.
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
-  // Hacker's Delight 7-3: afterwards a[r] bit c == old a[31-c] bit (31-r)
-  uint32_t m = 0x0000FFFFu;
+  // Hacker's Delight 7-3: afterwards a[r] bit c == old a[31-c] bit (31-r).
+  // The 16- and 8-bit stages are pure byte permutes (2 PRMT per register pair instead of 5 ALU ops).
 #pragma unroll
-  for (int j = 16; j != 0; j >>= 1, m ^= (m << j)) {
+  for (int k = 0; k < 16; ++k) {
+    const uint32_t lo = a[k], hi = a[k + 16];
+    a[k] = __byte_perm(lo, hi, 0x3276);        // (lo & 0xffff0000) | (hi >> 16)
+    a[k + 16] = __byte_perm(lo, hi, 0x1054);   // (hi & 0x0000ffff) | (lo << 16)
+  }
+#pragma unroll
+  for (int k = 0; k < 32; k = (k + 8 + 1) & ~8) {
+    const uint32_t lo = a[k], hi = a[k + 8];
+    a[k] = __byte_perm(lo, hi, 0x3715);        // bytes 0,2 of lo <- bytes 1,3 of hi
+    a[k + 8] = __byte_perm(lo, hi, 0x2604);    // bytes 1,3 of hi <- bytes 0,2 of lo
+  }
+  uint32_t m = 0x0F0F0F0Fu;
+#pragma unroll
+  for (int j = 4; j != 0; j >>= 1, m ^= (m << j)) {
 #pragma unroll
     for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
       const uint32_t t = (a[k] ^ (a[k + j] >> j)) & m;
@@ -28,11 +41,12 @@ __device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
   }
 }
 
+template <int T>   // T = rows of 32 points actually present (16 for n_points <= 512): the rest folds away at compile time
 __global__ void __launch_bounds__(256, 2)
 knn_ball_kernel(const float* __restrict__ xyz, int n_points, int n_centroids, int k, float r2,
                 int64_t stride_cloud, int64_t stride_point, int64_t stride_ch,
                 int32_t* __restrict__ idx_out, int chunks_per_cloud, int centroids_per_cta) {
-  constexpr int NP = 1024;
+  constexpr int NP = T * 32;
   __shared__ float sx[NP], sy[NP], sz[NP];
   const int b = blockIdx.x / chunks_per_cloud;
   const int chunk = blockIdx.x % chunks_per_cloud;
@@ -55,7 +69,7 @@ knn_ball_kernel(const float* __restrict__ xyz, int n_points, int n_centroids, in
   // bit t set <=> point 32 t + lane exists
   uint32_t valid = 0;
 #pragma unroll
-  for (int t = 0; t < 32; ++t) valid |= (t * 32 + lane < n_points) ? (1u << t) : 0u;
+  for (int t = 0; t < T; ++t) valid |= (t * 32 + lane < n_points) ? (1u << t) : 0u;
 
   for (int i = c_begin + warp; i < c_end; i += nwarps) {
     const float cx = sx[i], cy = sy[i], cz = sz[i];
@@ -63,6 +77,7 @@ knn_ball_kernel(const float* __restrict__ xyz, int n_points, int n_centroids, in
     uint32_t far = 0;                                 // bit t <=> d > r2 (radius mask, utils.py:149-151)
 #pragma unroll
     for (int t = 31; t >= 0; --t) {
+      if (t >= T) { a[31 - t] = 0; continue; }        // rows that do not exist: compile-time zeros
       const int j = t * 32 + lane;
       const uint32_t d = __float_as_uint(sqdist_rn(sx[j], sy[j], sz[j], cx, cy, cz));
       a[31 - t] = d;
@@ -200,8 +215,12 @@ extern "C" int pdf_knn_ball(const float* xyz, int64_t n_clouds, int n_points, in
   PDF_REQUIRE(n_clouds * chunks < (1ll << 31), PDF_ERR_UNSUPPORTED, "pdf_knn_ball: grid too large");
   dim3 grid((unsigned)(n_clouds * chunks));
   cudaStream_t s = (cudaStream_t)stream;
-  pdf::knn_ball_kernel<<<grid, 256, 0, s>>>(xyz, n_points, n_centroids, k, r2, stride_cloud, stride_point,
-                                            stride_ch, idx_out, chunks, per_cta);
+  if (n_points <= 512)
+    pdf::knn_ball_kernel<16><<<grid, 256, 0, s>>>(xyz, n_points, n_centroids, k, r2, stride_cloud, stride_point,
+                                                  stride_ch, idx_out, chunks, per_cta);
+  else
+    pdf::knn_ball_kernel<32><<<grid, 256, 0, s>>>(xyz, n_points, n_centroids, k, r2, stride_cloud, stride_point,
+                                                  stride_ch, idx_out, chunks, per_cta);
   return pdf::check_launch("pdf_knn_ball");
 }
 
