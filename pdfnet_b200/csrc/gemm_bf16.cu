@@ -166,6 +166,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t v[32], u[32];
+          float4 fin[8];                                   // all eight F loads of this chunk in flight at once
+          if (dual) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              fin[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row_ok && c0 + 4 * q < nvalid)
+                fin[q] = __ldg(reinterpret_cast<const float4*>(P.F + m * P.ldf + col0 + c0) + q);
+            }
+          }
           tmem_ld32(acc + c0, v);
           if (dual) tmem_ld32(acc + 128 + c0, u);
           tmem_ld_wait();
@@ -176,8 +185,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
             float r[4] = {__uint_as_float(v[q]) + bb.x, __uint_as_float(v[q + 1]) + bb.y,
                           __uint_as_float(v[q + 2]) + bb.z, __uint_as_float(v[q + 3]) + bb.w};
             if (dual) {
-              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (row_ok && c0 + q < nvalid) t = *reinterpret_cast<const float4*>(P.F + m * P.ldf + col0 + c0 + q);
+              const float4 t = fin[q >> 2];
               const float4 b2 = *reinterpret_cast<const float4*>(b1 + c0 + q);
               r[0] = fmaf(t.x, r[0] + 1.f, __uint_as_float(u[q]) + b2.x);
               r[1] = fmaf(t.y, r[1] + 1.f, __uint_as_float(u[q + 1]) + b2.y);
