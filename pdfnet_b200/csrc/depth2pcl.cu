@@ -311,10 +311,9 @@ extern "C" int pdf_depth2pcl(const float* depth, const float* mask, const float*
               "pdf_depth2pcl: subset_keys required when a hand can exceed n_points pixels");
   if (B == 0) return PDF_OK;
   const size_t smem = (size_t)(((int64_t)H * W + 31) / 32) * 4 * 4;      // candidate / selected / tie bitmasks + word list
-  static bool attr_set = false;
-  if (!attr_set) {
+  static pdf::PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(pdf::depth2pcl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
-    attr_set = true;
   }
   pdf::depth2pcl_kernel<<<(unsigned)(B * 2), pdf::D2P_THREADS, smem, (cudaStream_t)stream>>>(
       depth, mask, Kinv, valid, subset_keys, perm, H, W, n_points, min_pixels, choose, cloud, n_cand);

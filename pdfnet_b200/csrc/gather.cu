@@ -80,7 +80,7 @@ __device__ __forceinline__ void gather_level(const float* __restrict__ plane0, i
 // BOUNDING WINDOW of the cloud's pixels for CG channel planes with coalesced 16 B loads into shared
 // memory and gathers from there; stores are CG contiguous floats per point.  Falls back to the
 // point-wise gather when the window does not fit the shared-memory budget.
-constexpr int PG_WIN_BYTES = 64 * 1024;
+constexpr int PG_WIN_BYTES = 48 * 1024;
 
 template <int CG>
 __device__ __forceinline__ void gather_level_window(const float* __restrict__ plane0, int C, int64_t HW, int R,
@@ -318,10 +318,9 @@ extern "C" int pdf_pyramid_gather(const float* xyz, const int64_t* choose, int64
   // window variant needs whole channel groups and 16-byte aligned output rows
   const int windowed = (C1 % pdf::PG_CG1 == 0) && (C2 % pdf::PG_CG2 == 0) && (R % 16 == 0);
   const int groups1 = windowed ? C1 / pdf::PG_CG1 : pdf::PG_SPLIT, groups2 = windowed ? C2 / pdf::PG_CG2 : pdf::PG_SPLIT;
-  static bool configured = false;
-  if (!configured) {
+  static pdf::PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(pdf::pyramid_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pdf::PG_WIN_BYTES);
-    configured = true;
   }
   pdf::pyramid_gather_kernel<<<dim3((unsigned)n_clouds, 1 + groups1 + groups2), 256,
                                windowed ? pdf::PG_WIN_BYTES : 0, (cudaStream_t)stream>>>(

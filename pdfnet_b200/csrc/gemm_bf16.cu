@@ -454,11 +454,10 @@ extern "C" int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const voi
                   "pdf_gemm_bf16: bf16 row output needs 8-column aligned tiles");
     }
   }
-  static bool configured = false;
-  if (!configured) {
+  static pdf::PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(gemm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
     cudaFuncSetAttribute(gemm_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
-    configured = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -478,10 +477,9 @@ extern "C" int pdf_sft_xyz_f32(const float* cond, int64_t M, int cc, const float
               "pdf_sft_xyz_f32: null pointer");
   PDF_REQUIRE(cc == 64, PDF_ERR_UNSUPPORTED, "pdf_sft_xyz_f32: only 64 condition channels (level 1) are built");
   const size_t smem = (size_t)(2 * cc * cc + 2 * cc + 6 * cc) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static pdf::PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(pdf::sft_xyz_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
   }
   pdf::sft_xyz_kernel<64><<<(unsigned)((M + 127) / 128), 128, smem, (cudaStream_t)stream>>>(
       cond, M, w0s, b0s, w1s, b1s, w0h, b0h, w1h, b1h, x, ldx);

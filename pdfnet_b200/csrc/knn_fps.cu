@@ -242,10 +242,9 @@ extern "C" int pdf_fps(const float* xyz, int64_t n_clouds, int n_points, int n_s
   else if (n_points <= 1024) LAUNCH(4);
   else if (n_points <= 2048) LAUNCH(8);
   else {
-    static bool attr = false;   // 48 KB of coordinates + static barriers exceeds the default dynamic limit
-    if (!attr) {
+    static pdf::PerDeviceOnce once;   // 48 KB of coordinates + static barriers exceeds the default dynamic limit
+    if (once.first()) {
       cudaFuncSetAttribute(pdf::fps_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 16 * 256 * 4);
-      attr = true;
     }
     LAUNCH(16);
   }

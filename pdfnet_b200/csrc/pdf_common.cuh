@@ -22,6 +22,20 @@ inline int check_launch(const char* what) {
   return PDF_OK;
 }
 
+// cudaFuncSetAttribute is per device: returns true the first time it is called for the current
+// device with this flag array (one process may drive several GPUs).
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 #define PDF_REQUIRE(cond, code, ...)            \
   do {                                          \
     if (!(cond)) {                              \

@@ -373,15 +373,14 @@ template <class Cfg>
 static int launch_sa(const float* pts, int64_t n_clouds, int n_src, int64_t ld_pts, const void* feat_bf16,
                      const int32_t* idx, int n_centroids, const void* wpack, float* out, int64_t ld_out, int out_col0,
                      cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;            // one flag array per template instantiation
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(sa_mlp_max_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("pdf_sa_mlp_max_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return PDF_ERR_CUDA;
     }
-    configured = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
