@@ -193,7 +193,7 @@ def run_ours(args):
     rank, world, local = parallel.init_distributed("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    from pdfnet_b200 import HandFusion, ManoLayer, _lib, depth2pcl_batched, mano_tail, ops, profiling
+    from pdfnet_b200 import HandFusion, ManoLayer, _lib, mano_tail_pair, ops, profiling
 
     R, B = args.res, args.frames                      # frames per GPU (weak scaling)
     opt = make_opt(R)
@@ -217,8 +217,7 @@ def run_ours(args):
             choose, cloud, _ = ops.depth2pcl(d["depth"], d["mask"], d["Kinv"], d["valid"], d["keys"], d["perm"])
         fused, theta = model(cloud, [d["l0"], d["l1"], d["l2"]], choose, d["center"], with_mano=True)
         with profiling.stage("mano_tail"):
-            verts, joints, tl, tr = mano_tail(theta[:, 0].contiguous(), theta[:, 1].contiguous(), d["ind"][:, 0],
-                                              d["ind"][:, 1], d["K"], mano_l, mano_r, input_res=R)
+            verts, joints, _ = mano_tail_pair(theta, d["ind"], d["K"], mano_l, mano_r, input_res=R)
         return fused, verts, joints
 
     def barrier():

@@ -233,13 +233,24 @@ int pdf_mano_lbs(const float* v_template, const float* shapedirs_t, const float*
                  const float* root, const float* pose, const float* shape, const float* trans,
                  const float* scale, int64_t n, const int32_t* tip_idx_host, int center_idx, int new_skel,
                  const float* v_tpose, float* v, float* j, void* stream);
+/* Both hands of every frame in ONE launch: hands laid out (frame, side), even = left, odd = right.
+ * tables_left / tables_right: host arrays of the 6 device table pointers in the order of
+ * pdf_mano_lbs (v_template, shapedirs_t, posedirs_t, j_template, j_shapedirs, weights_t).
+ * Replaces the two per-side ManoLayer calls of CtdetLoss.origforward (lib/trains/simplified.py:733-736). */
+int pdf_mano_lbs_pair(const float* const* tables_left, const float* const* tables_right, const float* root,
+                      const float* pose, const float* shape, const float* trans, const float* scale, int64_t n,
+                      const int32_t* tips_left_host, const int32_t* tips_right_host, int center_idx, int new_skel,
+                      const float* v_tpose, float* v, float* j, void* stream);
 /* X[h] = [shape(10) | (rodrigues(pose_j) - I) for the 15 joints (135)], fp32 [n,145] (manolayer.py:274-281) */
 int pdf_mano_pose_feature(const float* pose, const float* shape, int64_t n, float* X, void* stream);
 
 /* Split_coeff (lib/models/hand3d/Mano_render.py:160-194, non-PCA) for one hand:
  * theta [n,ld_theta] (61 used columns starting at col0), index int64 [n], K [n,3,3];
- * writes root [n,3], pose [n,45], shape [n,10] (zeros: betas*0), trans [n,3]. */
-int pdf_split_coeff(const float* theta, int64_t ld_theta, int col0, const int64_t* index, const float* K,
+ * writes root [n,3], pose [n,45], shape [n,10] (zeros: betas*0), trans [n,3].
+ * pair != 0: rows are (frame, side) with one 122-vector per row (point2mano_left / point2mano_right,
+ * simplified.py:722-732): even rows read the left slice [0,61), odd rows the right slice [61,122),
+ * and K is indexed per frame (K [n/2,3,3]). */
+int pdf_split_coeff(const float* theta, int64_t ld_theta, int col0, int pair, const int64_t* index, const float* K,
                     int64_t n, int input_res, int down_ratio,
                     float* root, float* pose, float* shape, float* trans, void* stream);
 

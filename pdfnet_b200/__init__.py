@@ -16,7 +16,7 @@ _COMPUTE = {
     "_tranpose_and_gather_feat": "encoder", "SFTLayer": "encoder", "PointNet_Plus": "encoder",
     "HandFusion": "encoder", "CenterFeatures": "encoder", "depth2pcl": "encoder", "depth2pcl_batched": "encoder",
     "get_points_coordinate": "encoder", "ManoLayer": "manolayer", "Split_coeff": "manolayer",
-    "mano_tail": "manolayer", "patch_reference": "patch",
+    "mano_tail": "manolayer", "mano_tail_pair": "manolayer", "patch_reference": "patch",
 }
 
 

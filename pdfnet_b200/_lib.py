@@ -36,7 +36,8 @@ SIGNATURES = {
     "pdf_depth2pcl": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "pdf_mano_lbs": [_vp] * 11 + [_i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "pdf_mano_pose_feature": [_vp, _vp, _i64, _vp, _vp],
-    "pdf_split_coeff": [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "pdf_split_coeff": [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "pdf_mano_lbs_pair": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
 }
 EXPORTS = sorted(list(SIGNATURES) + ["pdf_version", "pdf_last_error", "pdf_launch_count", "pdf_sa_pack_size",
                                      "pdf_image_bytes"])

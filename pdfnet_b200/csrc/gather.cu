@@ -238,17 +238,18 @@ __global__ void backproject_kernel(const float* __restrict__ depth, const float*
 }
 
 // Split_coeff, one thread per hand row (Mano_render.py:160-194).
-__global__ void split_coeff_kernel(const float* __restrict__ theta, int64_t ld, int col0,
+__global__ void split_coeff_kernel(const float* __restrict__ theta, int64_t ld, int col0, int pair,
                                    const int64_t* __restrict__ index, const float* __restrict__ K, int64_t n,
                                    int input_res, int down_ratio, float* __restrict__ root,
                                    float* __restrict__ pose, float* __restrict__ shape, float* __restrict__ trans) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float* t = theta + i * ld + col0;
+  // pair mode: rows are (frame, hand); hand 0 reads the left slice [0,61), hand 1 the right slice [61,122)
+  const float* t = theta + i * ld + (pair ? 61 * (int)(i & 1) : col0);
   for (int c = 0; c < 3; ++c) root[i * 3 + c] = t[c];
   for (int c = 0; c < 45; ++c) pose[i * 45 + c] = t[3 + c];
   for (int c = 0; c < 10; ++c) shape[i * 10 + c] = t[48 + c] * 0.f;
-  const float* Ki = K + i * 9;
+  const float* Ki = K + (pair ? (i >> 1) : i) * 9;
   const int g = input_res / down_ratio;
   const float cx = (float)((index[i] % g) * down_ratio), cy = (float)((index[i] / g) * down_ratio);
   const float tz = __fadd_rn(t[60], 0.6f);
@@ -354,15 +355,15 @@ extern "C" int pdf_backproject(const float* depth, const float* Kinv, int64_t B,
   return pdf::check_launch("pdf_backproject");
 }
 
-extern "C" int pdf_split_coeff(const float* theta, int64_t ld_theta, int col0, const int64_t* index, const float* K,
-                               int64_t n, int input_res, int down_ratio, float* root, float* pose, float* shape,
-                               float* trans, void* stream) {
+extern "C" int pdf_split_coeff(const float* theta, int64_t ld_theta, int col0, int pair, const int64_t* index,
+                               const float* K, int64_t n, int input_res, int down_ratio, float* root, float* pose,
+                               float* shape, float* trans, void* stream) {
   PDF_REQUIRE(theta && index && K && root && pose && shape && trans, PDF_ERR_BAD_ARG, "pdf_split_coeff: null pointer");
-  PDF_REQUIRE(n >= 0 && input_res > 0 && down_ratio > 0 && col0 >= 0 && ld_theta >= col0 + 61, PDF_ERR_BAD_ARG,
-              "pdf_split_coeff: bad size");
+  PDF_REQUIRE(n >= 0 && input_res > 0 && down_ratio > 0 && col0 >= 0 && ld_theta >= (pair ? 122 : col0 + 61),
+              PDF_ERR_BAD_ARG, "pdf_split_coeff: bad size");
   if (n == 0) return PDF_OK;
   pdf::split_coeff_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      theta, ld_theta, col0, index, K, n, input_res, down_ratio, root, pose, shape, trans);
+      theta, ld_theta, col0, pair, index, K, n, input_res, down_ratio, root, pose, shape, trans);
   return pdf::check_launch("pdf_split_coeff");
 }
 

@@ -13,19 +13,30 @@ __constant__ int c_parent[16] = {-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 0, 10, 11, 0, 13
 __constant__ int c_new_order[21] = {0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20};
 
 struct Tips { int v[5]; };
+struct ManoTables {                      // one side's constants (see include/pdfnet_b200.h)
+  const float *v_template, *shapedirs_t, *posedirs_t, *j_template, *j_shapedirs, *weights_t;
+};
 
 // HPC hands per CTA (1: the kernel is latency bound; the blend-shape contraction can be taken out of
 // it entirely, see v_tpose_in / pdf_mano_pose_feature).
 constexpr int HPC = 1;
 
 __global__ void __launch_bounds__(256)
-mano_lbs_kernel(const float* __restrict__ v_template, const float* __restrict__ shapedirs_t,
-                const float* __restrict__ posedirs_t, const float* __restrict__ j_template,
-                const float* __restrict__ j_shapedirs, const float* __restrict__ weights_t,
+mano_lbs_kernel(ManoTables T0, ManoTables T1, int pair,
                 const float* __restrict__ root, const float* __restrict__ pose, const float* __restrict__ shape,
-                const float* __restrict__ trans, const float* __restrict__ scale, int64_t n_hands, Tips tips,
-                int center_idx, int new_skel, const float* __restrict__ v_tpose_in, float* __restrict__ v_out,
-                float* __restrict__ j_out) {
+                const float* __restrict__ trans, const float* __restrict__ scale, int64_t n_hands, Tips tips0,
+                Tips tips1, int center_idx, int new_skel, const float* __restrict__ v_tpose_in,
+                float* __restrict__ v_out, float* __restrict__ j_out) {
+  // pair mode: hands are laid out (frame, side); even hands use table set 0 (left), odd hands set 1 (right)
+  const bool alt = pair && (blockIdx.x & 1);
+  const ManoTables& T = alt ? T1 : T0;
+  const Tips tips = alt ? tips1 : tips0;
+  const float* __restrict__ v_template = T.v_template;
+  const float* __restrict__ shapedirs_t = T.shapedirs_t;
+  const float* __restrict__ posedirs_t = T.posedirs_t;
+  const float* __restrict__ j_template = T.j_template;
+  const float* __restrict__ j_shapedirs = T.j_shapedirs;
+  const float* __restrict__ weights_t = T.weights_t;
   __shared__ float s_aa[HPC][48];          // axis-angle: root + 15 joints
   __shared__ float s_beta[HPC][10];
   __shared__ float s_R[HPC][16][9];
@@ -237,6 +248,11 @@ __global__ void mano_pose_feature_kernel(const float* __restrict__ pose, const f
 
 }  // namespace pdf
 
+static int mano_lbs_launch(const pdf::ManoTables& T0, const pdf::ManoTables& T1, int pair, const float* root,
+                           const float* pose, const float* shape, const float* trans, const float* scale, int64_t n,
+                           const int32_t* tip0, const int32_t* tip1, int center_idx, int new_skel,
+                           const float* v_tpose, float* v, float* j, void* stream);
+
 extern "C" int pdf_mano_lbs(const float* v_template, const float* shapedirs_t, const float* posedirs_t,
                             const float* j_template, const float* j_shapedirs, const float* weights_t,
                             const float* root, const float* pose, const float* shape, const float* trans,
@@ -244,18 +260,43 @@ extern "C" int pdf_mano_lbs(const float* v_template, const float* shapedirs_t, c
                             int new_skel, const float* v_tpose, float* v, float* j, void* stream) {
   PDF_REQUIRE(v_template && shapedirs_t && posedirs_t && j_template && j_shapedirs && weights_t, PDF_ERR_BAD_ARG,
               "pdf_mano_lbs: null table pointer");
+  pdf::ManoTables T{v_template, shapedirs_t, posedirs_t, j_template, j_shapedirs, weights_t};
+  return mano_lbs_launch(T, T, 0, root, pose, shape, trans, scale, n, tip_idx_host, tip_idx_host, center_idx, new_skel,
+                         v_tpose, v, j, stream);
+}
+
+extern "C" int pdf_mano_lbs_pair(const float* const* tables_left, const float* const* tables_right, const float* root,
+                                 const float* pose, const float* shape, const float* trans, const float* scale,
+                                 int64_t n, const int32_t* tips_left_host, const int32_t* tips_right_host,
+                                 int center_idx, int new_skel, const float* v_tpose, float* v, float* j, void* stream) {
+  PDF_REQUIRE(tables_left && tables_right, PDF_ERR_BAD_ARG, "pdf_mano_lbs_pair: null table array");
+  for (int i = 0; i < 6; ++i)
+    PDF_REQUIRE(tables_left[i] && tables_right[i], PDF_ERR_BAD_ARG, "pdf_mano_lbs_pair: null table pointer");
+  PDF_REQUIRE((n & 1) == 0, PDF_ERR_BAD_ARG, "pdf_mano_lbs_pair: n must be even ((frame, side) layout)");
+  pdf::ManoTables L{tables_left[0], tables_left[1], tables_left[2], tables_left[3], tables_left[4], tables_left[5]};
+  pdf::ManoTables R{tables_right[0], tables_right[1], tables_right[2], tables_right[3], tables_right[4], tables_right[5]};
+  return mano_lbs_launch(L, R, 1, root, pose, shape, trans, scale, n, tips_left_host, tips_right_host, center_idx,
+                         new_skel, v_tpose, v, j, stream);
+}
+
+static int mano_lbs_launch(const pdf::ManoTables& T0, const pdf::ManoTables& T1, int pair, const float* root,
+                           const float* pose, const float* shape, const float* trans, const float* scale, int64_t n,
+                           const int32_t* tip_idx_host, const int32_t* tip1_host, int center_idx, int new_skel,
+                           const float* v_tpose, float* v, float* j, void* stream) {
   if (n == 0) return PDF_OK;
   PDF_REQUIRE(root && pose && shape && v && j && tip_idx_host, PDF_ERR_BAD_ARG, "pdf_mano_lbs: null pointer");
   PDF_REQUIRE(n >= 0 && center_idx < 21, PDF_ERR_BAD_ARG, "pdf_mano_lbs: bad size");
-  pdf::Tips tips;
+  PDF_REQUIRE(tip1_host != nullptr, PDF_ERR_BAD_ARG, "pdf_mano_lbs: null pointer");
+  pdf::Tips tips, tips1;
   for (int i = 0; i < 5; ++i) {
-    PDF_REQUIRE(tip_idx_host[i] >= 0 && tip_idx_host[i] < pdf::NV, PDF_ERR_BAD_ARG, "pdf_mano_lbs: tip index");
+    PDF_REQUIRE(tip_idx_host[i] >= 0 && tip_idx_host[i] < pdf::NV && tip1_host[i] >= 0 && tip1_host[i] < pdf::NV,
+                PDF_ERR_BAD_ARG, "pdf_mano_lbs: tip index");
     tips.v[i] = tip_idx_host[i];
+    tips1.v[i] = tip1_host[i];
   }
   if (n == 0) return PDF_OK;
   pdf::mano_lbs_kernel<<<(unsigned)((n + pdf::HPC - 1) / pdf::HPC), 256, 0, (cudaStream_t)stream>>>(
-      v_template, shapedirs_t, posedirs_t, j_template, j_shapedirs, weights_t, root, pose, shape, trans, scale, n, tips,
-      center_idx, new_skel, v_tpose, v, j);
+      T0, T1, pair, root, pose, shape, trans, scale, n, tips, tips1, center_idx, new_skel, v_tpose, v, j);
   return pdf::check_launch("pdf_mano_lbs");
 }
 

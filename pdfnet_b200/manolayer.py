@@ -159,6 +159,19 @@ def Split_coeff(theta, index, K, input_res=384, down_ratio=4):
     return left + right
 
 
+def mano_tail_pair(theta, ind, K, layer_left, layer_right, input_res=384, down_ratio=4):
+    """Same as ``mano_tail`` for theta [B,2,122] / ind [B,2] ((frame, side) layout) with ONE launch per
+    stage for both hands: Split_coeff, blend-shape coefficients and skinning.  Returns verts [B,2,778,3],
+    joints [B,2,21,3], trans [B,2,3]."""
+    if layer_left.use_pca or layer_right.use_pca or layer_left.center_idx != layer_right.center_idx:
+        raise RuntimeError("mano_tail_pair: both layers must be axis-angle layers with the same center_idx")
+    root, pose, shape, trans = ops.split_coeff_pair(theta, ind, K, input_res, down_ratio)
+    dev = theta.device
+    v, j = ops.mano_lbs_pair(layer_left._kernel_tables(dev), layer_right._kernel_tables(dev), root, pose, shape, None,
+                             None, TIPS["left"], TIPS["right"], layer_left.center_idx, layer_left.new_skel)
+    return v, j, trans
+
+
 def mano_tail(theta_left, theta_right, ind_left, ind_right, K, layer_left, layer_right, input_res=384,
               down_ratio=4):
     """MANO tail as CtdetLoss.origforward runs it (lib/trains/simplified.py:722-736): each hand has

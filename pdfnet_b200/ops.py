@@ -271,6 +271,54 @@ def mano_lbs(tables, root, pose, shape, trans, scale, tips, center_idx, new_skel
     return v, j
 
 
+def mano_lbs_pair(tables_l, tables_r, root, pose, shape, trans, scale, tips_l, tips_r, center_idx, new_skel):
+    """Both hands of every frame in one launch; inputs [B,2,...] ((frame, side), side 0 = left)."""
+    L.require_cuda(root, pose, shape, trans, scale)
+    B = root.shape[0]
+    n = 2 * B
+    root, pose, shape = L.f32c(root).view(n, 3), L.f32c(pose).view(n, 45), L.f32c(shape).view(n, 10)
+    trans = L.f32c(trans).view(n, 3) if trans is not None else None
+    scale = L.f32c(scale).view(n) if scale is not None else None
+    dev = root.device
+    v = torch.empty((B, 2, 778, 3), dtype=torch.float32, device=dev)
+    j = torch.empty((B, 2, 21, 3), dtype=torch.float32, device=dev)
+    names = ("v_template", "shapedirs_t", "posedirs_t", "j_template", "j_shapedirs", "weights_t")
+    tl = (ctypes.c_void_p * 6)(*[tables_l[k].data_ptr() for k in names])
+    tr = (ctypes.c_void_p * 6)(*[tables_r[k].data_ptr() for k in names])
+    tipl = (ctypes.c_int32 * 5)(*[int(t) for t in tips_l])
+    tipr = (ctypes.c_int32 * 5)(*[int(t) for t in tips_r])
+    v_tpose = None
+    if n >= 16:
+        # blend shapes: one [n,145] coefficient matrix, then one fp32 GEMM per side on strided rows
+        X = torch.empty((n, 145), dtype=torch.float32, device=dev)
+        L.call("pdf_mano_pose_feature", L.ptr(pose), L.ptr(shape), n, L.ptr(X), L.stream())
+        v_tpose = torch.empty((n, 2334), dtype=torch.float32, device=dev)
+        linear(X[0::2], tables_l["blend_w"], tables_l["v_template"], out=v_tpose[0::2])
+        linear(X[1::2], tables_r["blend_w"], tables_r["v_template"], out=v_tpose[1::2])
+    L.call("pdf_mano_lbs_pair", ctypes.cast(tl, ctypes.c_void_p), ctypes.cast(tr, ctypes.c_void_p), L.ptr(root),
+           L.ptr(pose), L.ptr(shape), L.ptr(trans), L.ptr(scale), n, ctypes.cast(tipl, ctypes.c_void_p),
+           ctypes.cast(tipr, ctypes.c_void_p), -1 if center_idx is None else int(center_idx), 1 if new_skel else 0,
+           L.ptr(v_tpose), L.ptr(v), L.ptr(j), L.stream())
+    return v, j
+
+
+def split_coeff_pair(theta, index, K, input_res, down_ratio):
+    """theta [B,2,122] (row (b,0) = point2mano_left, (b,1) = point2mano_right), index [B,2], K [B,3,3] ->
+    root [B,2,3], pose [B,2,45], shape [B,2,10], trans [B,2,3] in one launch."""
+    L.require_cuda(theta, index, K)
+    theta, K = L.f32c(theta), L.f32c(K)
+    index = index.long().contiguous()
+    B = theta.shape[0]
+    dev = theta.device
+    root = torch.empty((B, 2, 3), dtype=torch.float32, device=dev)
+    pose = torch.empty((B, 2, 45), dtype=torch.float32, device=dev)
+    shape = torch.empty((B, 2, 10), dtype=torch.float32, device=dev)
+    trans = torch.empty((B, 2, 3), dtype=torch.float32, device=dev)
+    L.call("pdf_split_coeff", L.ptr(theta), 122, 0, 1, L.ptr(index), L.ptr(K), 2 * B, input_res, down_ratio,
+           L.ptr(root), L.ptr(pose), L.ptr(shape), L.ptr(trans), L.stream())
+    return root, pose, shape, trans
+
+
 def split_coeff(theta, col0, index, K, input_res, down_ratio):
     """One hand's slice of Split_coeff; returns root [n,3], pose [n,45], shape [n,10], trans [n,3]."""
     L.require_cuda(theta, index, K)
@@ -282,6 +330,6 @@ def split_coeff(theta, col0, index, K, input_res, down_ratio):
     pose = torch.empty((n, 45), dtype=torch.float32, device=dev)
     shape = torch.empty((n, 10), dtype=torch.float32, device=dev)
     trans = torch.empty((n, 3), dtype=torch.float32, device=dev)
-    L.call("pdf_split_coeff", L.ptr(theta), theta.stride(0), col0, L.ptr(index), L.ptr(K), n, input_res, down_ratio,
+    L.call("pdf_split_coeff", L.ptr(theta), theta.stride(0), col0, 0, L.ptr(index), L.ptr(K), n, input_res, down_ratio,
            L.ptr(root), L.ptr(pose), L.ptr(shape), L.ptr(trans), L.stream())
     return root, pose, shape, trans

@@ -642,3 +642,18 @@ def test_center_features_only_at_ind(precision, tol):
     ref = O.center_features(x0, w0, w1, ind)
     assert out.shape == (B, 2, 1024)
     assert rel_err(out.cpu(), ref) < tol
+
+
+def test_mano_tail_pair_matches_per_side_tail():
+    from pdfnet_b200 import ManoLayer, mano_tail, mano_tail_pair
+    g = torch.Generator().manual_seed(14)
+    B = 20
+    theta = (torch.randn((B, 2, 122), generator=g) * 0.2).to(DEV)
+    ind = torch.randint(0, 96 * 96, (B, 2), generator=g).to(DEV)
+    K = torch.tensor([[300.0, 0, 192.0], [0, 310.0, 190.0], [0, 0, 1]]).repeat(B, 1, 1).to(DEV)
+    ll, lr = ManoLayer(mano_tables("left"), center_idx=None), ManoLayer(mano_tables("right"), center_idx=None)
+    v, j, t = mano_tail_pair(theta, ind, K, ll, lr)
+    v2, j2, tl, tr = mano_tail(theta[:, 0].contiguous(), theta[:, 1].contiguous(), ind[:, 0].contiguous(),
+                               ind[:, 1].contiguous(), K, ll, lr)
+    assert float((v - v2).abs().max()) < 1e-6 and float((j - j2).abs().max()) < 1e-6
+    assert torch.equal(t[:, 0], tl) and torch.equal(t[:, 1], tr)
