@@ -76,7 +76,7 @@ __device__ __forceinline__ void issue_layer(uint32_t a_feat, uint32_t a_blk, uin
 
 // Epilogue of layers 1/2: TMEM row (this thread's point) -> ReLU -> bf16 -> SW128 tile row.
 template <int C>
-__device__ __forceinline__ void epilogue_repack(uint32_t tmem_row, uint8_t* feat, int p) {
+__device__ __forceinline__ void epilogue_repack(uint32_t tmem_row, uint32_t feat, int p) {   // feat: shared address
 #pragma unroll
   for (int c0 = 0; c0 < C; c0 += 32) {
     uint32_t v[32];
@@ -90,7 +90,7 @@ __device__ __forceinline__ void epilogue_repack(uint32_t tmem_row, uint8_t* feat
       w.y = pack_relu_bf16(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
       w.z = pack_relu_bf16(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
       w.w = pack_relu_bf16(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
-      *reinterpret_cast<uint4*>(feat + (col >> 6) * (128 * 128) + sw128_off(p, col & 63)) = w;
+      st_shared_v4(feat + (col >> 6) * (128 * 128) + sw128_off(p, col & 63), w);
     }
   }
 }
@@ -187,8 +187,8 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
       w.y = pack_bf16(hz, 1.f);
       w.z = pack_bf16(rx - hx, ry - hy);
       w.w = pack_bf16(rz - hz, 1.f);
-      *reinterpret_cast<uint4*>(my_aux + aux_off(p, 0)) = w;
-      *reinterpret_cast<uint4*>(my_aux + aux_off(p, 8)) = make_uint4(0, 0, 0, 0);
+      st_shared_v4(sa_aux + aux_off(p, 0), w);
+      st_shared_v4(sa_aux + aux_off(p, 8), make_uint4(0, 0, 0, 0));
     }
     if (Cfg::CF > 0) {
       if (feat_bf16 != nullptr) {
@@ -218,7 +218,7 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
           w.x = pack_bf16(f.x, f.y);
           w.y = pack_bf16(f.z, f.w);
           const int col = lane * 4;
-          *reinterpret_cast<uint2*>(my_feat + (col >> 6) * (128 * 128) + sw128_off(row, col & 63)) = w;
+          st_shared_v2(sa_feat + (col >> 6) * (128 * 128) + sw128_off(row, col & 63), w);
         }
       }
     }
@@ -233,11 +233,9 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
                             idesc_bf16(128, Cfg::C1));
       commit(bar);
     }
-    if (t + t_step < n_tiles) load_raw(t + t_step, j_next, sp, cp);       // first use: next iteration
-    if (t + 2 * t_step < n_tiles) j_next = load_idx(t + 2 * t_step);      // first use: next iteration
     mbar_wait(bar, phase); phase ^= 1;
     fence_after_sync();
-    epilogue_repack<Cfg::C1>(d1 + lane_off, my_feat, p);
+    epilogue_repack<Cfg::C1>(d1 + lane_off, sa_feat, p);
     fence_async_smem();
     fence_before_sync();
     named_bar_sync(1 + slot, 128);
@@ -251,7 +249,7 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
     }
     mbar_wait(bar, phase); phase ^= 1;
     fence_after_sync();
-    epilogue_repack<Cfg::C2>(d2 + lane_off, my_feat, p);
+    epilogue_repack<Cfg::C2>(d2 + lane_off, sa_feat, p);
     fence_async_smem();
     fence_before_sync();
     named_bar_sync(1 + slot, 128);
@@ -293,6 +291,10 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
                               sa_feat, 128 * 128, sa_aux, d3 + h * 128, idesc_bf16(128, 128));
       commit(bar);
     }
+    // prefetch for the next tiles, issued AFTER the last proxy fence of this tile (the fence is a
+    // MEMBAR and would otherwise wait for these loads): first use is the top of the next iteration
+    if (t + t_step < n_tiles) load_raw(t + t_step, j_next, sp, cp);
+    if (t + 2 * t_step < n_tiles) j_next = load_idx(t + 2 * t_step);
     mbar_wait(bar, phase); phase ^= 1;
     fence_after_sync();
 #pragma unroll

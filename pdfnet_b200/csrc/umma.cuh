@@ -100,6 +100,15 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// explicit shared-space stores (a generic uint8_t* makes the compiler emit generic ST.E, which is
+// slower and turns the following proxy fence into a full MEMBAR)
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_shared_v2(uint32_t saddr, uint2 v) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(v.x), "r"(v.y) : "memory");
+}
+
 // two fp32 -> packed bf16x2 with ReLU (lo = first element)
 __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
   uint32_t r;
