@@ -158,8 +158,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
         const int64_t m = (int64_t)mt * 128 + row;
         const bool row_ok = m < P.rows_valid;
         const int col0 = P.tile_col[nt], nvalid = P.tile_nvalid[nt], okb = P.tile_okb[nt];
-        const float* b0 = s_bias + nt * 128;
-        const float* b1 = s_bias + G_MAX_NT * 128 + nt * 128;
+        const uint32_t b0 = smem_u32(s_bias) + nt * 512;                    // shared addresses (explicit LDS)
+        const uint32_t b1 = b0 + G_MAX_NT * 512;
+        const uint32_t sxyz = smem_u32(s_xyz);
         const bool full = row_ok && nvalid == 128;           // fast path: no per-element masking
         float xo[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
         const int c_begin = xyz ? (half == 0 ? 0 : 128) : half * 64, c_end = xyz ? 128 : half * 64 + 64;
@@ -181,12 +182,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
           float y[32];
 #pragma unroll
           for (int q = 0; q < 32; q += 4) {
-            const float4 bb = *reinterpret_cast<const float4*>(b0 + c0 + q);
+            const float4 bb = ld_shared_f4(b0 + (c0 + q) * 4);
             float r[4] = {__uint_as_float(v[q]) + bb.x, __uint_as_float(v[q + 1]) + bb.y,
                           __uint_as_float(v[q + 2]) + bb.z, __uint_as_float(v[q + 3]) + bb.w};
             if (dual) {
               const float4 t = fin[q >> 2];
-              const float4 b2 = *reinterpret_cast<const float4*>(b1 + c0 + q);
+              const float4 b2 = ld_shared_f4(b1 + (c0 + q) * 4);
               r[0] = fmaf(t.x, r[0] + 1.f, __uint_as_float(u[q]) + b2.x);
               r[1] = fmaf(t.y, r[1] + 1.f, __uint_as_float(u[q + 1]) + b2.y);
               r[2] = fmaf(t.z, r[2] + 1.f, __uint_as_float(u[q + 2]) + b2.z);
@@ -206,12 +207,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
           }
           if (xyz) {                                         // fp32 dots with the 3 xyz rows of the second conv
             const int br = c0 >> 6;
-            const float* w = s_xyz + br * 192 + (c0 & 63);
+            const uint32_t w = sxyz + (br * 192 + (c0 & 63)) * 4;
 #pragma unroll
             for (int q = 0; q < 32; q += 4) {
 #pragma unroll
               for (int c = 0; c < 3; ++c) {
-                const float4 wv = *reinterpret_cast<const float4*>(w + c * 64 + q);
+                const float4 wv = ld_shared_f4(w + (c * 64 + q) * 4);
                 xo[br][c] = fmaf(wv.x, y[q], fmaf(wv.y, y[q + 1], fmaf(wv.z, y[q + 2], fmaf(wv.w, y[q + 3], xo[br][c]))));
               }
             }
@@ -254,7 +255,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
           float* xr = P.xyz_x + m * P.xyz_ld;
 #pragma unroll
           for (int c = 0; c < 3; ++c)
-            xr[c] = __fadd_rn(__fmul_rn(xr[c], __fadd_rn(xo[0][c] + s_xyz[384 + c], 1.f)), xo[1][c] + s_xyz[387 + c]);
+            xr[c] = __fadd_rn(__fmul_rn(xr[c], __fadd_rn(xo[0][c] + ld_shared_f1(sxyz + (384 + c) * 4), 1.f)),
+                              xo[1][c] + ld_shared_f1(sxyz + (387 + c) * 4));
         }
       }
       fence_before_sync();

@@ -109,6 +109,17 @@ __device__ __forceinline__ void st_shared_v2(uint32_t saddr, uint2 v) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(v.x), "r"(v.y) : "memory");
 }
 
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float ld_shared_f1(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+
 // two fp32 -> packed bf16x2 with ReLU (lo = first element)
 __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
   uint32_t r;
