@@ -254,6 +254,59 @@ int pdf_split_coeff(const float* theta, int64_t ld_theta, int col0, int pair, co
                     int64_t n, int input_res, int down_ratio,
                     float* root, float* pose, float* shape, float* trans, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training-mode (BASELINE cfg5) entry points: fp32, rows [M, C] with a free row pitch.
+ * Together with pdf_linear_f32 (data gradient: dX = dY * W, call it with W^T) these are the
+ * backward of PointNet_Plus.forward / SFTLayer.forward (intaghand_encoder.py:118-159, 205-219)
+ * that the reference gets from torch.autograd.  `sums` buffers are caller-owned fp64 scratch.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Per-channel shifted sums over the M rows, d = x - x[0,c]: sums[0:C] = sum d, sums[C:2C] = sum d^2
+ * (nn.BatchNorm2d batch statistics, intaghand_encoder.py:52,57,62 ...; the shift keeps the
+ * variance free of cancellation). */
+int pdf_bn_stats(const float* X, int64_t ldx, int64_t M, int C, double* sums, void* stream);
+/* mean / rstd from pdf_bn_stats of the same X (biased variance, eps inside the sqrt) and the
+ * running-stat update running = (1-momentum)*running + momentum*batch (unbiased variance), as
+ * torch.nn.functional.batch_norm(training=True).  running_* may be null. */
+int pdf_bn_finalize(const double* sums, const float* X, int64_t M, int C, float eps, float momentum,
+                    float* running_mean, float* running_var, float* mean, float* rstd, void* stream);
+/* Y = [relu]((X - mean) * rstd * gamma + beta) */
+int pdf_bn_act_fwd(const float* X, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
+                   const float* beta, int relu, int64_t M, int C, float* Y, int64_t ldy, void* stream);
+/* Backward of pdf_bn_act_fwd: g = dY * [Y > 0]; sums[0:C] = dbeta = sum g, sums[C:2C] = dgamma =
+ * sum g*xhat; dX = gamma*rstd*(g - dbeta/M - xhat*dgamma/M).  dX may alias dY. */
+int pdf_bn_act_bwd(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* X, int64_t ldx,
+                   const float* mean, const float* rstd, const float* gamma, int relu, int64_t M, int C,
+                   double* sums, float* dX, int64_t lddx, void* stream);
+/* sums[0:C] = column sums of A (bias gradients) */
+int pdf_col_sum(const float* A, int64_t lda, int64_t M, int C, double* sums, void* stream);
+/* dX = dY * act'(Y) for the PDF_ACT_* enum (Y is the activation OUTPUT); dX may alias dY */
+int pdf_act_bwd(const float* dY, int64_t lddy, const float* Y, int64_t ldy, int act, int64_t M, int C, float* dX,
+                int64_t lddx, void* stream);
+/* out = fea * (scale + 1) + shift (SFTLayer.forward :219) and its backward:
+ * dfea = dout*(scale+1), dscale = dout*fea (dshift = dout). */
+int pdf_sft_modulate(const float* fea, int64_t ldf, const float* scale, int64_t lds, const float* shift, int64_t ldh,
+                     int64_t M, int C, float* out, int64_t ldo, void* stream);
+int pdf_sft_modulate_bwd(const float* dout, int64_t ldd, const float* fea, int64_t ldf, const float* scale,
+                         int64_t lds, int64_t M, int C, float* dfea, int64_t lddf, float* dscale, int64_t ldds,
+                         void* stream);
+/* Weight gradient C[N,K] = A[M,N]^T * B[M,K] (A = dY, B = layer input); C is overwritten. */
+int pdf_linear_tn_f32(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int N, int K, float* C,
+                      int64_t ldc, void* stream);
+/* nn.MaxPool2d over groups of G consecutive rows (intaghand_encoder.py:63,81,99) and its
+ * backward: the FIRST maximum of each (group, channel) receives dOut, all other rows 0. */
+int pdf_group_max(const float* Y, int64_t ldy, int G, int64_t groups, int C, float* out, int64_t ldo, void* stream);
+int pdf_group_max_bwd(const float* Y, int64_t ldy, const float* dOut, int64_t lddo, int G, int64_t groups, int C,
+                      float* dY, int64_t lddy, void* stream);
+/* Backward of pdf_group_gather: dPts[b, idx[b,g,j], c] += dG[b,g,j,c]; dPts[b,g,c<3] -= dG[b,g,j,c].
+ * dG fp32 [n_clouds, n_centroids, k, C] contiguous; dPts [n_clouds, n_points, ld] pre-zeroed by the caller. */
+int pdf_group_scatter_add(const float* dG, const int32_t* idx, int64_t n_clouds, int n_points, int n_centroids, int k,
+                          int C, float* dPts, int64_t ldp, void* stream);
+/* Backward of pdf_gather_nchw (one cloud per frame): dFeat[b, c, ind[b,i]] += dOut[b,i,c];
+ * dFeat [n_clouds, C, HW] pre-zeroed by the caller. */
+int pdf_gather_nchw_bwd(const float* dOut, const int64_t* ind, int64_t n_clouds, int C, int64_t HW, int n,
+                        float* dFeat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

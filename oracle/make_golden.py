@@ -281,6 +281,49 @@ def golden_mano_head(ref):
     save("mano_head", x=x.numpy(), y=y.numpy())
 
 
+def grad_digest(name, g):
+    """Full tensor when small, otherwise (sum, L2 norm, every 97th element)."""
+    g = g.detach().reshape(-1).double()
+    if g.numel() <= 20000:
+        return {name: g.numpy()}
+    return {name + "@sum": np.float64(g.sum().item()), name + "@norm": np.float64(g.norm().item()),
+            name + "@s97": g[::97].numpy()}
+
+
+def golden_train_step(ref):
+    """One training-mode forward + backward of the UNMODIFIED reference PointNet_Plus
+    (intaghand_encoder.py:118-159, nn.BatchNorm2d batch statistics, torch.autograd):
+    loss = sum(out * gdir).  Records the output, every parameter gradient, the gradients of
+    the three pyramid maps and the updated BatchNorm running buffers.  The module is run in
+    float64 (``m.double()``): in fp32 the early-layer gradients of this network carry ~1 %
+    rounding noise, which would hide semantic differences; the fp32 forward output is kept too."""
+    R, B = 64, 2
+    opt = ref_import.default_opt(default_resolution=R)
+    m = ref.PointNet_Plus(opt)
+    m.load_state_dict(synth.pointnet_plus_state(seed=317), strict=False)
+    m.train()
+    pts, choose, emb, gdir = synth.train_inputs(B, R)
+    with torch.no_grad():
+        out32 = m(pts.clone(), [e.clone() for e in emb], choose).numpy()
+    m.load_state_dict(synth.pointnet_plus_state(seed=317), strict=False)     # undo the running-stat update
+    m.double()
+    emb = [e.double().requires_grad_(True) for e in emb]
+    out = m(pts.double(), emb, choose)
+    (out * gdir.double()).sum().backward()
+    rec = dict(out=out.detach().numpy(), out_fp32=out32, R=np.int64(R), B=np.int64(B))
+    for k, p in m.named_parameters():
+        if k.startswith("netR_FC"):
+            continue
+        rec.update(grad_digest("grad:" + k, p.grad))
+    for i, e in enumerate(emb):
+        rec.update(grad_digest("grad:emb%d" % i, e.grad))
+    for k, b in m.named_buffers():
+        if k.startswith("netR_FC") or k.endswith("num_batches_tracked"):
+            continue
+        rec["buf:" + k] = b.detach().numpy()
+    save("train_step", **rec)
+
+
 def main():
     ref = ref_import.load_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -296,6 +339,7 @@ def main():
     golden_mano(ref)
     golden_split_coeff(ref)
     golden_mano_head(ref)
+    golden_train_step(ref)
 
 
 if __name__ == "__main__":

@@ -187,6 +187,63 @@ def pointnet_plus_forward(sd, points, emb, choose, opt, return_intermediates=Fal
         return out
 
 
+# ----------------------------------------------------------------------------
+# training mode (BASELINE cfg5): the same forward with batch-statistic BatchNorm,
+# written with differentiable torch-CPU ops so torch.autograd yields the gradients
+# the reference's autograd yields.  Pinned by tests/golden/train_step.npz (the
+# unmodified reference PointNet_Plus in .train() mode, loss.backward()).
+# ----------------------------------------------------------------------------
+
+
+def _group_rows_torch(pts, idx):
+    """Differentiable form of the gathers in utils.py:153-158 / :181-186.
+    pts [B,N,C] tensor, idx [B,N1,K] int64 -> [B,N1,K,C] with centroid-relative xyz."""
+    B, N, C = pts.shape
+    N1, K = idx.shape[1], idx.shape[2]
+    g = torch.gather(pts, 1, idx.reshape(B, N1 * K, 1).expand(B, N1 * K, C)).view(B, N1, K, C)
+    center = pts[:, :N1, None, 0:3]
+    return torch.cat((g[..., 0:3] - center, g[..., 3:]), -1)
+
+
+def _mlp_max_train(x, sd, prefix, pool_dim, momentum=0.1, eps=1e-5):
+    for i_conv, i_bn in ((0, 1), (3, 4), (6, 7)):
+        x = F.conv2d(x, sd["%s.%d.weight" % (prefix, i_conv)], sd["%s.%d.bias" % (prefix, i_conv)])
+        x = F.batch_norm(x, sd["%s.%d.running_mean" % (prefix, i_bn)], sd["%s.%d.running_var" % (prefix, i_bn)],
+                         sd["%s.%d.weight" % (prefix, i_bn)], sd["%s.%d.bias" % (prefix, i_bn)], True, momentum, eps)
+        x = F.relu(x)
+    return x.max(dim=pool_dim, keepdim=True)[0]
+
+
+def pointnet_plus_train(sd, points, emb, choose, opt, dtype=torch.float32):
+    """PointNet_Plus.forward (intaghand_encoder.py:118-159) in .train() mode.  ``sd`` maps
+    state-dict names to tensors (parameters with requires_grad=True; running buffers are
+    updated in place as nn.BatchNorm2d does); ``emb`` tensors may require grad.  -> [B,1,1024].
+    ``dtype=torch.float64`` (all tensors double) is the form the golden pins: fp32 autograd of
+    this network carries ~1 % rounding noise in the early-layer gradients, fp64 does not."""
+    points = torch.as_tensor(points, dtype=dtype)
+    choose = torch.as_tensor(choose).long()
+    R = opt.default_resolution
+    N1, N2, K = opt.sample_num_level1, opt.sample_num_level2, opt.knn_K
+    e0 = tranpose_and_gather_feat(emb[0], choose)
+    pts0 = sft_layer(points.transpose(1, 2), e0, sd, "sft0.")                      # [B,N,3]
+    idx1 = torch.from_numpy(knn_ball_indices(pts0.detach().numpy(), N1, K, opt.ball_radius))
+    g1 = _group_rows_torch(pts0, idx1).permute(0, 3, 1, 2)                         # [B,3,N1,K]
+    y = pts0[:, :N1, 0:3].transpose(1, 2).unsqueeze(-1)                            # [B,3,N1,1]
+    c2, c4 = pyramid_index(choose, R)
+    e1 = tranpose_and_gather_feat(emb[1], c2[:, :N1])
+    e2 = tranpose_and_gather_feat(emb[2], c4[:, :N2])
+    f1 = _mlp_max_train(g1, sd, "netR_1", 3)
+    x1 = torch.cat((y, f1), 1).squeeze(-1)                                         # [B,131,N1]
+    pts1 = sft_layer(x1, e1, sd, "sft1.")                                          # [B,N1,131]
+    idx2 = torch.from_numpy(knn_ball_indices(pts1.detach().numpy()[:, :, 0:3], N2, K, opt.ball_radius2))
+    g2 = _group_rows_torch(pts1, idx2).permute(0, 3, 1, 2)                         # [B,131,N2,K]
+    c2xyz = pts1[:, :N2, 0:3].transpose(1, 2).unsqueeze(-1)
+    f2 = _mlp_max_train(g2, sd, "netR_2", 3)
+    x2 = torch.cat((c2xyz, f2), 1).squeeze(-1)                                     # [B,259,N2]
+    pts2 = sft_layer(x2, e2, sd, "sft2.").transpose(1, 2).unsqueeze(3)
+    return _mlp_max_train(pts2, sd, "netR_3", 2).view(-1, 1, 1024)
+
+
 def fusion_tail(sd_pointnet, sd_sft, cloud, emb, choose, center_features, opt):
     """ResNetSimple.forward fusion tail, intaghand_encoder.py:805-809.
     cloud [B,2,N,3], choose [B,2,N], center_features [B,2,1024] -> fuse_feat [B,2,1024]."""

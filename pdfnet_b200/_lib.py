@@ -37,6 +37,19 @@ SIGNATURES = {
     "pdf_mano_lbs": [_vp] * 11 + [_i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "pdf_mano_pose_feature": [_vp, _vp, _i64, _vp, _vp],
     "pdf_split_coeff": [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "pdf_bn_stats": [_vp, _i64, _i64, _i32, _vp, _vp],
+    "pdf_bn_finalize": [_vp, _vp, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp],
+    "pdf_bn_act_fwd": [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _i64, _vp],
+    "pdf_bn_act_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _i64, _vp],
+    "pdf_col_sum": [_vp, _i64, _i64, _i32, _vp, _vp],
+    "pdf_act_bwd": [_vp, _i64, _vp, _i64, _i32, _i64, _i32, _vp, _i64, _vp],
+    "pdf_sft_modulate": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _vp],
+    "pdf_sft_modulate_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _i64, _vp],
+    "pdf_linear_tn_f32": [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _i64, _vp],
+    "pdf_group_max": [_vp, _i64, _i32, _i64, _i32, _vp, _i64, _vp],
+    "pdf_group_max_bwd": [_vp, _i64, _vp, _i64, _i32, _i64, _i32, _vp, _i64, _vp],
+    "pdf_group_scatter_add": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp],
+    "pdf_gather_nchw_bwd": [_vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp],
     "pdf_mano_lbs_pair": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
 }
 EXPORTS = sorted(list(SIGNATURES) + ["pdf_version", "pdf_last_error", "pdf_launch_count", "pdf_sa_pack_size",

@@ -1,0 +1,419 @@
+// Training-mode (cfg5) kernels of the fusion path, fp32: train-mode BatchNorm over rows,
+// the weight-gradient GEMM (reduction over rows), max-pool / grouping / pixel-gather
+// backward scatters and the SFT modulation backward.  The data-gradient GEMM reuses
+// pdf_linear_f32 with the transposed weight.  Everything is row-major [rows, channels] with a
+// free row pitch, the layout the inference path already uses.
+//
+// Reference semantics: nn.BatchNorm2d(train) inside netR_1/2/3 (intaghand_encoder.py:52-99:
+// biased variance for the normalisation, unbiased for running_var, momentum 0.1),
+// nn.MaxPool2d backward (first maximum of the window receives the gradient), and autograd
+// of group_points / group_points_2 (utils.py:134-191), _tranpose_and_gather_feat
+// (models/utils.py:22-26) and SFTLayer.forward (intaghand_encoder.py:213-219).
+#include "pdf_common.cuh"
+
+namespace pdf {
+
+// ---------------------------------------------------------------------------------------------
+// column reductions over rows: two sums per channel, accumulated in double with atomics.
+// block (32 channels x 8 row lanes); each thread walks rows with a grid stride.
+enum { RED_STATS = 0, RED_COLSUM = 1, RED_BN_BWD = 2 };
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+col_reduce_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ Yp, int64_t ldy,
+                  const float* __restrict__ X, int64_t ldx, const float* __restrict__ mean,
+                  const float* __restrict__ rstd, int relu, int64_t M, int C, double* __restrict__ sums) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < C;
+  float s0 = 0.f, s1 = 0.f;
+  float mu = 0.f, rs = 0.f;
+  if (MODE == RED_BN_BWD && ok) { mu = mean[c]; rs = rstd[c]; }
+  // statistics are accumulated about the channel's first row (shifted sums): the variance
+  // sum d^2 - (sum d)^2 / M then has no catastrophic cancellation when |mean| >> std
+  if (MODE == RED_STATS && ok && M > 0) mu = A[c];
+  // two-level accumulation keeps fp32 partial sums short (<= 64 terms) before going to double
+  double d0 = 0.0, d1 = 0.0;
+  int n = 0;
+  for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < M; r += (int64_t)gridDim.y * 8) {
+    if (ok) {
+      const float a = A[r * lda + c];
+      if (MODE == RED_STATS) { const float d = a - mu; s0 += d; s1 = fmaf(d, d, s1); }
+      else if (MODE == RED_COLSUM) { s0 += a; }
+      else {
+        const float g = (!relu || Yp[r * ldy + c] > 0.f) ? a : 0.f;
+        s0 += g;
+        s1 = fmaf(g, (X[r * ldx + c] - mu) * rs, s1);
+      }
+    }
+    if (++n == 64) { d0 += s0; d1 += s1; s0 = s1 = 0.f; n = 0; }
+  }
+  d0 += s0; d1 += s1;
+  __shared__ double sh[2][8][32];
+  sh[0][threadIdx.y][threadIdx.x] = d0;
+  sh[1][threadIdx.y][threadIdx.x] = d1;
+  __syncthreads();
+  if (threadIdx.y == 0 && ok) {
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t0 += sh[0][i][threadIdx.x]; t1 += sh[1][i][threadIdx.x]; }
+    atomicAdd(&sums[c], t0);
+    if (MODE != RED_COLSUM) atomicAdd(&sums[C + c], t1);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ X, int64_t M, int C,
+                                   float eps, float momentum, float* running_mean, float* running_var,
+                                   float* __restrict__ mean, float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double md = sums[c] / (double)M;                 // mean of (x - x[0,c])
+  const double m = md + (double)X[c];
+  double var = sums[C + c] / (double)M - md * md;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+  if (running_var) {
+    const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// element-wise passes over [M, C] row-major matrices (grid-stride, channel fastest)
+enum { EW_BN_FWD = 0, EW_BN_BWD = 1, EW_ACT_BWD = 2, EW_SFT_FWD = 3, EW_SFT_BWD = 4 };
+
+struct EwArgs {
+  const float* a; int64_t lda;      // BN_FWD: X      BN_BWD: dY    ACT_BWD: dY    SFT_FWD: fea    SFT_BWD: dout
+  const float* b; int64_t ldb;      // BN_BWD: Y      ACT_BWD: Y    SFT_FWD: scale SFT_BWD: fea
+  const float* c; int64_t ldc;      // BN_BWD: X      SFT_FWD: shift SFT_BWD: scale
+  const float* v0; const float* v1; const float* v2; const float* v3;   // per-channel vectors
+  const double* sums;               // BN_BWD: [sum g | sum g*xhat]
+  float* o0; int64_t ldo0;          // primary output
+  float* o1; int64_t ldo1;          // SFT_BWD: dscale
+  int64_t M; int C; int flag;       // flag: relu (BN) / activation enum (ACT_BWD)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) elementwise_kernel(EwArgs p) {
+  const int64_t total = p.M * (int64_t)p.C;
+  const float invM = 1.f / (float)p.M;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / p.C;
+    const int c = (int)(i - r * p.C);
+    if (MODE == EW_BN_FWD) {            // v0 mean, v1 rstd, v2 gamma, v3 beta
+      float y = fmaf((p.a[r * p.lda + c] - p.v0[c]) * p.v1[c], p.v2[c], p.v3[c]);
+      if (p.flag) y = fmaxf(y, 0.f);
+      p.o0[r * p.ldo0 + c] = y;
+    } else if (MODE == EW_BN_BWD) {     // v0 mean, v1 rstd, v2 gamma
+      const float dy = p.a[r * p.lda + c];
+      const float g = (!p.flag || p.b[r * p.ldb + c] > 0.f) ? dy : 0.f;
+      const float xhat = (p.c[r * p.ldc + c] - p.v0[c]) * p.v1[c];
+      const float dbeta = (float)p.sums[c], dgamma = (float)p.sums[p.C + c];
+      p.o0[r * p.ldo0 + c] = p.v2[c] * p.v1[c] * (g - dbeta * invM - xhat * dgamma * invM);
+    } else if (MODE == EW_ACT_BWD) {
+      const float y = p.b[r * p.ldb + c];
+      const float d = p.a[r * p.lda + c];
+      const float s = p.flag == PDF_ACT_RELU ? (y > 0.f ? 1.f : 0.f) : (p.flag == PDF_ACT_LEAKY01 ? (y > 0.f ? 1.f : 0.1f) : 1.f);
+      p.o0[r * p.ldo0 + c] = d * s;
+    } else if (MODE == EW_SFT_FWD) {    // fea * (scale + 1) + shift, rounded like the reference (mul, then add)
+      p.o0[r * p.ldo0 + c] = __fadd_rn(__fmul_rn(p.a[r * p.lda + c], __fadd_rn(p.b[r * p.ldb + c], 1.f)),
+                                       p.c[r * p.ldc + c]);
+    } else {                            // SFT_BWD: dfea = dout*(scale+1), dscale = dout*fea  (dshift = dout)
+      const float d = p.a[r * p.lda + c];
+      const float fea = p.b[r * p.ldb + c];
+      p.o1[r * p.ldo1 + c] = d * fea;
+      p.o0[r * p.ldo0 + c] = d * (p.c[r * p.ldc + c] + 1.f);
+    }
+  }
+}
+
+template <int MODE>
+static int launch_ew(const EwArgs& p, cudaStream_t s, const char* what) {
+  const int64_t total = p.M * (int64_t)p.C;
+  if (total == 0) return PDF_OK;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  elementwise_kernel<MODE><<<(unsigned)blocks, 256, 0, s>>>(p);
+  return check_launch(what);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient: Cout[N, K] += sum_r A[r, n] * B[r, k]   (A = dY, B = layer input)
+// 64 x 64 output tile per CTA over a chunk of rows, 4x4 micro-tile per thread, fp32 atomics.
+constexpr int TN_ROWS = 16;
+
+__global__ void __launch_bounds__(256)
+linear_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int64_t M, int N,
+                 int K, int64_t rows_per_cta, float* __restrict__ Cout, int64_t ldc) {
+  __shared__ float As[TN_ROWS][64 + 4];
+  __shared__ float Bs[TN_ROWS][64 + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+  const int64_t r_begin = (int64_t)blockIdx.z * rows_per_cta;
+  const int64_t r_end = r_begin + rows_per_cta < M ? r_begin + rows_per_cta : M;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int lr = tid >> 4, lc = (tid & 15) * 4;        // loader: 16 rows x 64 columns, 4 columns per thread
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += TN_ROWS) {
+    const int64_t r = r0 + lr;
+    float a[4], b[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      a[q] = (r < r_end && n0 + lc + q < N) ? A[r * lda + n0 + lc + q] : 0.f;
+      b[q] = (r < r_end && k0 + lc + q < K) ? B[r * ldb + k0 + lc + q] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { As[lr][lc + q] = a[q]; Bs[lr][lc + q] = b[q]; }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < TN_ROWS; ++rr) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[rr][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[rr][tx * 4]);
+      const float ar[4] = {av.x, av.y, av.z, av.w};
+      const float br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < K) atomicAdd(Cout + (int64_t)n * ldc + k, acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// max over groups of G consecutive rows, and its backward (gradient to the FIRST maximum)
+__global__ void group_max_kernel(const float* __restrict__ Y, int64_t ldy, int G, int64_t groups, int C,
+                                 float* __restrict__ out, int64_t ldo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups * C) return;
+  const int64_t g = i / C;
+  const int c = (int)(i - g * C);
+  const float* y = Y + g * G * ldy + c;
+  float m = y[0];
+  for (int r = 1; r < G; ++r) m = fmaxf(m, y[(int64_t)r * ldy]);
+  out[g * ldo + c] = m;
+}
+
+__global__ void group_max_bwd_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ dOut,
+                                     int64_t lddo, int G, int64_t groups, int C, float* __restrict__ dY,
+                                     int64_t lddy) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups * C) return;
+  const int64_t g = i / C;
+  const int c = (int)(i - g * C);
+  const float* y = Y + g * G * ldy + c;
+  float m = y[0];
+  int arg = 0;
+  for (int r = 1; r < G; ++r) {
+    const float v = y[(int64_t)r * ldy];
+    if (v > m) { m = v; arg = r; }
+  }
+  const float d = dOut[g * lddo + c];
+  float* dy = dY + g * G * lddy + c;
+  for (int r = 0; r < G; ++r) dy[(int64_t)r * lddy] = r == arg ? d : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward of the grouping gather: dG [B, N1, K, C] -> dPts [B, N, C] (+= neighbour rows,
+// -= the xyz columns at the centroid, which is source point g)
+__global__ void group_scatter_add_kernel(const float* __restrict__ dG, const int* __restrict__ idx, int64_t B, int N,
+                                         int N1, int K, int C, float* __restrict__ dPts, int64_t ldp) {
+  const int64_t total = B * N1 * (int64_t)K * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t row = i / C;                 // (b, g, k)
+    const int64_t bg = row / K;
+    const int64_t b = bg / N1;
+    const int g = (int)(bg - b * N1);
+    const float d = dG[i];
+    if (d == 0.f) continue;
+    const int j = idx[row];
+    atomicAdd(dPts + (b * N + j) * ldp + c, d);
+    if (c < 3) atomicAdd(dPts + (b * N + g) * ldp + c, -d);
+  }
+}
+
+// backward of the pixel->point gather: dOut [B, n, C] -> dFeat [B, C, HW] (+=)
+__global__ void gather_nchw_bwd_kernel(const float* __restrict__ dOut, const int64_t* __restrict__ ind, int64_t B,
+                                       int C, int64_t HW, int n, float* __restrict__ dFeat) {
+  const int64_t total = B * n * (int64_t)C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t bp = i / C;
+    const int64_t b = bp / n;
+    const int64_t pix = ind[bp];
+    atomicAdd(dFeat + (b * C + c) * HW + pix, dOut[i]);
+  }
+}
+
+static unsigned grid_for(int64_t total) {
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+template <int MODE>
+static int launch_reduce(const float* A, int64_t lda, const float* Y, int64_t ldy, const float* X, int64_t ldx,
+                         const float* mean, const float* rstd, int relu, int64_t M, int C, double* sums,
+                         cudaStream_t s, const char* what) {
+  const int nsum = MODE == RED_COLSUM ? C : 2 * C;
+  cudaMemsetAsync(sums, 0, sizeof(double) * nsum, s);
+  if (M == 0) return PDF_OK;
+  int64_t gy = (M + 8 * 64 - 1) / (8 * 64);
+  const int gx = (C + 31) / 32;
+  const int64_t cap = (148 * 16 + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  dim3 grid((unsigned)gx, (unsigned)gy), block(32, 8);
+  col_reduce_kernel<MODE><<<grid, block, 0, s>>>(A, lda, Y, ldy, X, ldx, mean, rstd, relu, M, C, sums);
+  return check_launch(what);
+}
+
+}  // namespace pdf
+
+using namespace pdf;
+
+extern "C" int pdf_bn_stats(const float* X, int64_t ldx, int64_t M, int C, double* sums, void* stream) {
+  PDF_REQUIRE(X && sums && M >= 0 && C > 0 && ldx >= C, PDF_ERR_BAD_ARG, "pdf_bn_stats: bad argument");
+  return launch_reduce<RED_STATS>(X, ldx, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, M, C, sums,
+                                  (cudaStream_t)stream, "pdf_bn_stats");
+}
+
+extern "C" int pdf_col_sum(const float* A, int64_t lda, int64_t M, int C, double* sums, void* stream) {
+  PDF_REQUIRE(A && sums && M >= 0 && C > 0 && lda >= C, PDF_ERR_BAD_ARG, "pdf_col_sum: bad argument");
+  return launch_reduce<RED_COLSUM>(A, lda, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, M, C, sums,
+                                   (cudaStream_t)stream, "pdf_col_sum");
+}
+
+extern "C" int pdf_bn_finalize(const double* sums, const float* X, int64_t M, int C, float eps, float momentum,
+                               float* running_mean, float* running_var, float* mean, float* rstd, void* stream) {
+  PDF_REQUIRE(sums && X && mean && rstd && M > 0 && C > 0, PDF_ERR_BAD_ARG, "pdf_bn_finalize: bad argument");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, X, M, C, eps, momentum, running_mean,
+                                                                         running_var, mean, rstd);
+  return check_launch("pdf_bn_finalize");
+}
+
+extern "C" int pdf_bn_act_fwd(const float* X, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, int relu, int64_t M, int C, float* Y, int64_t ldy, void* stream) {
+  PDF_REQUIRE(X && mean && rstd && gamma && beta && Y && M >= 0 && C > 0, PDF_ERR_BAD_ARG,
+              "pdf_bn_act_fwd: bad argument");
+  EwArgs p = {};
+  p.a = X; p.lda = ldx; p.v0 = mean; p.v1 = rstd; p.v2 = gamma; p.v3 = beta;
+  p.o0 = Y; p.ldo0 = ldy; p.M = M; p.C = C; p.flag = relu;
+  return launch_ew<EW_BN_FWD>(p, (cudaStream_t)stream, "pdf_bn_act_fwd");
+}
+
+extern "C" int pdf_bn_act_bwd(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* X, int64_t ldx,
+                              const float* mean, const float* rstd, const float* gamma, int relu, int64_t M, int C,
+                              double* sums, float* dX, int64_t lddx, void* stream) {
+  PDF_REQUIRE(dY && Y && X && mean && rstd && gamma && sums && dX && M >= 0 && C > 0, PDF_ERR_BAD_ARG,
+              "pdf_bn_act_bwd: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = launch_reduce<RED_BN_BWD>(dY, lddy, Y, ldy, X, ldx, mean, rstd, relu, M, C, sums, s, "pdf_bn_act_bwd");
+  if (rc != PDF_OK) return rc;
+  EwArgs p = {};
+  p.a = dY; p.lda = lddy; p.b = Y; p.ldb = ldy; p.c = X; p.ldc = ldx;
+  p.v0 = mean; p.v1 = rstd; p.v2 = gamma; p.sums = sums;
+  p.o0 = dX; p.ldo0 = lddx; p.M = M; p.C = C; p.flag = relu;
+  return launch_ew<EW_BN_BWD>(p, s, "pdf_bn_act_bwd");
+}
+
+extern "C" int pdf_act_bwd(const float* dY, int64_t lddy, const float* Y, int64_t ldy, int act, int64_t M, int C,
+                           float* dX, int64_t lddx, void* stream) {
+  PDF_REQUIRE(dY && Y && dX && M >= 0 && C > 0 && act >= 0 && act <= 2, PDF_ERR_BAD_ARG, "pdf_act_bwd: bad argument");
+  EwArgs p = {};
+  p.a = dY; p.lda = lddy; p.b = Y; p.ldb = ldy; p.o0 = dX; p.ldo0 = lddx; p.M = M; p.C = C; p.flag = act;
+  return launch_ew<EW_ACT_BWD>(p, (cudaStream_t)stream, "pdf_act_bwd");
+}
+
+extern "C" int pdf_sft_modulate(const float* fea, int64_t ldf, const float* scale, int64_t lds, const float* shift,
+                                int64_t ldh, int64_t M, int C, float* out, int64_t ldo, void* stream) {
+  PDF_REQUIRE(fea && scale && shift && out && M >= 0 && C > 0, PDF_ERR_BAD_ARG, "pdf_sft_modulate: bad argument");
+  EwArgs p = {};
+  p.a = fea; p.lda = ldf; p.b = scale; p.ldb = lds; p.c = shift; p.ldc = ldh;
+  p.o0 = out; p.ldo0 = ldo; p.M = M; p.C = C;
+  return launch_ew<EW_SFT_FWD>(p, (cudaStream_t)stream, "pdf_sft_modulate");
+}
+
+extern "C" int pdf_sft_modulate_bwd(const float* dout, int64_t ldd, const float* fea, int64_t ldf, const float* scale,
+                                    int64_t lds, int64_t M, int C, float* dfea, int64_t lddf, float* dscale,
+                                    int64_t ldds, void* stream) {
+  PDF_REQUIRE(dout && fea && scale && dfea && dscale && M >= 0 && C > 0, PDF_ERR_BAD_ARG,
+              "pdf_sft_modulate_bwd: bad argument");
+  EwArgs p = {};
+  p.a = dout; p.lda = ldd; p.b = fea; p.ldb = ldf; p.c = scale; p.ldc = lds;
+  p.o0 = dfea; p.ldo0 = lddf; p.o1 = dscale; p.ldo1 = ldds; p.M = M; p.C = C;
+  return launch_ew<EW_SFT_BWD>(p, (cudaStream_t)stream, "pdf_sft_modulate_bwd");
+}
+
+extern "C" int pdf_linear_tn_f32(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int N, int K,
+                                 float* C, int64_t ldc, void* stream) {
+  PDF_REQUIRE(A && B && C && M >= 0 && N > 0 && K > 0 && lda >= N && ldb >= K && ldc >= K, PDF_ERR_BAD_ARG,
+              "pdf_linear_tn_f32: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * K, N, s);
+  if (M == 0) return PDF_OK;
+  const int gx = (N + 63) / 64, gy = (K + 63) / 64;
+  // enough row chunks to fill the machine a few times over, each at least 256 rows
+  int64_t chunks = (148 * 8 + gx * gy - 1) / (gx * gy);
+  int64_t rows = (M + chunks - 1) / chunks;
+  if (rows < 256) rows = 256;
+  rows = (rows + TN_ROWS - 1) / TN_ROWS * TN_ROWS;
+  chunks = (M + rows - 1) / rows;
+  PDF_REQUIRE(chunks <= 65535, PDF_ERR_UNSUPPORTED, "pdf_linear_tn_f32: too many row chunks");
+  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)chunks);
+  linear_tn_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, M, N, K, rows, C, ldc);
+  return check_launch("pdf_linear_tn_f32");
+}
+
+extern "C" int pdf_group_max(const float* Y, int64_t ldy, int G, int64_t groups, int C, float* out, int64_t ldo,
+                             void* stream) {
+  PDF_REQUIRE(Y && out && G > 0 && groups >= 0 && C > 0, PDF_ERR_BAD_ARG, "pdf_group_max: bad argument");
+  if (groups == 0) return PDF_OK;
+  const int64_t total = groups * C;
+  group_max_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(Y, ldy, G, groups, C, out, ldo);
+  return check_launch("pdf_group_max");
+}
+
+extern "C" int pdf_group_max_bwd(const float* Y, int64_t ldy, const float* dOut, int64_t lddo, int G, int64_t groups,
+                                 int C, float* dY, int64_t lddy, void* stream) {
+  PDF_REQUIRE(Y && dOut && dY && G > 0 && groups >= 0 && C > 0, PDF_ERR_BAD_ARG, "pdf_group_max_bwd: bad argument");
+  if (groups == 0) return PDF_OK;
+  const int64_t total = groups * C;
+  group_max_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(Y, ldy, dOut, lddo, G,
+                                                                                           groups, C, dY, lddy);
+  return check_launch("pdf_group_max_bwd");
+}
+
+extern "C" int pdf_group_scatter_add(const float* dG, const int* idx, int64_t B, int N, int N1, int K, int C,
+                                     float* dPts, int64_t ldp, void* stream) {
+  PDF_REQUIRE(dG && idx && dPts && B >= 0 && N > 0 && N1 > 0 && N1 <= N && K > 0 && C >= 3 && ldp >= C,
+              PDF_ERR_BAD_ARG, "pdf_group_scatter_add: bad argument");
+  if (B == 0) return PDF_OK;
+  const int64_t total = B * N1 * (int64_t)K * C;
+  group_scatter_add_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(dG, idx, B, N, N1, K, C, dPts, ldp);
+  return check_launch("pdf_group_scatter_add");
+}
+
+extern "C" int pdf_gather_nchw_bwd(const float* dOut, const int64_t* ind, int64_t B, int C, int64_t HW, int n,
+                                   float* dFeat, void* stream) {
+  PDF_REQUIRE(dOut && ind && dFeat && B >= 0 && C > 0 && HW > 0 && n > 0, PDF_ERR_BAD_ARG,
+              "pdf_gather_nchw_bwd: bad argument");
+  if (B == 0) return PDF_OK;
+  const int64_t total = B * n * (int64_t)C;
+  gather_nchw_bwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(dOut, ind, B, C, HW, n, dFeat);
+  return check_launch("pdf_gather_nchw_bwd");
+}

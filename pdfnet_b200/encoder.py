@@ -78,6 +78,9 @@ class SFTLayer(nn.Module):
         B, Cf, n = fea.shape
         fea_rows = L.f32c(fea.transpose(1, 2)).view(B * n, Cf)
         cond_rows = L.f32c(cond).view(B * n, -1)
+        if self.training and torch.is_grad_enabled():
+            from .training import sft_rows
+            return sft_rows(self, fea_rows, cond_rows).view(B, n, Cf)
         return self.apply_rows(fea_rows, cond_rows).view(B, n, Cf)
 
     def packed_sft0(self):
@@ -195,8 +198,12 @@ class PointNet_Plus(nn.Module):
 
     def forward(self, points, emb, choose, clouds_per_frame=1):
         if self.training:
-            raise NotImplementedError("pdfnet_b200.PointNet_Plus: inference only (call .eval()); "
-                                      "train-mode BatchNorm is not built in this round")
+            # train-mode BatchNorm + autograd through every stage (fp32 kernels, training.py)
+            from .training import pointnet_plus_train
+            if clouds_per_frame != 1:
+                raise RuntimeError("PointNet_Plus (training): one cloud per frame per call, as the reference "
+                                   "(intaghand_encoder.py:805-806); BatchNorm statistics are per call")
+            return pointnet_plus_train(self, points, emb, choose)
         L.require_cuda(points, choose, *emb)
         with torch.no_grad():
             B = points.shape[0]
@@ -358,6 +365,11 @@ class HandFusion(nn.Module):
         """cloud [B,2,N,3], choose [B,2,N], center_features [B,2,1024] ->
         fuse_feat [B,2,1024] (and theta [B,2,122] = (point2mano_left, point2mano_right))."""
         B, H, N, _ = cloud.shape
+        if self.training:
+            from .training import hand_fusion_train
+            if with_mano:
+                raise RuntimeError("HandFusion (training): the MANO head branch is inference only")
+            return hand_fusion_train(self, cloud, point_wise_emb, choose, center_features)
         feat = self.pointnet_plus(cloud.reshape(B * H, N, 3), point_wise_emb, choose.reshape(B * H, N),
                                   clouds_per_frame=H)                       # [2B,1,1024]
         rows = feat.view(B * H, 1024)

@@ -333,3 +333,127 @@ def split_coeff(theta, col0, index, K, input_res, down_ratio):
     L.call("pdf_split_coeff", L.ptr(theta), theta.stride(0), col0, 0, L.ptr(index), L.ptr(K), n, input_res, down_ratio,
            L.ptr(root), L.ptr(pose), L.ptr(shape), L.ptr(trans), L.stream())
     return root, pose, shape, trans
+
+
+# ------------------------------------------------------------------------------------------------
+# training-mode (cfg5) primitives: thin wrappers over the pdf_* entry points in train_f32.cu
+def _rows(t):
+    assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == torch.float32, "fp32 rows with unit column stride"
+    return t
+
+
+def bn_batch_stats(x, eps, momentum, running_mean=None, running_var=None):
+    """Train-mode BatchNorm statistics of rows x [M,C]: (mean, rstd); updates the running buffers."""
+    L.require_cuda(x, running_mean, running_var)
+    M, C = _rows(x).shape
+    sums = torch.empty((2 * C,), dtype=torch.float64, device=x.device)
+    L.call("pdf_bn_stats", L.ptr(x), x.stride(0), M, C, L.ptr(sums), L.stream())
+    mean = torch.empty((C,), dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    L.call("pdf_bn_finalize", L.ptr(sums), L.ptr(x), M, C, float(eps), float(momentum), L.ptr(running_mean),
+           L.ptr(running_var), L.ptr(mean), L.ptr(rstd), L.stream())
+    return mean, rstd
+
+
+def bn_act_fwd(x, mean, rstd, gamma, beta, relu=True):
+    M, C = _rows(x).shape
+    y = torch.empty((M, C), dtype=torch.float32, device=x.device)
+    L.call("pdf_bn_act_fwd", L.ptr(x), x.stride(0), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), int(relu), M,
+           C, L.ptr(y), y.stride(0), L.stream())
+    return y
+
+
+def bn_act_bwd(dy, y, x, mean, rstd, gamma, relu=True):
+    """-> (dx, dgamma, dbeta)"""
+    M, C = _rows(x).shape
+    dy = _rows(dy if dy.stride(1) == 1 else dy.contiguous())
+    sums = torch.empty((2 * C,), dtype=torch.float64, device=x.device)
+    dx = torch.empty((M, C), dtype=torch.float32, device=x.device)
+    L.call("pdf_bn_act_bwd", L.ptr(dy), dy.stride(0), L.ptr(y), y.stride(0), L.ptr(x), x.stride(0), L.ptr(mean),
+           L.ptr(rstd), L.ptr(gamma), int(relu), M, C, L.ptr(sums), L.ptr(dx), dx.stride(0), L.stream())
+    return dx, sums[C:].float(), sums[:C].float()
+
+
+def col_sum(a):
+    M, C = _rows(a).shape
+    sums = torch.empty((C,), dtype=torch.float64, device=a.device)
+    L.call("pdf_col_sum", L.ptr(a), a.stride(0), M, C, L.ptr(sums), L.stream())
+    return sums.float()
+
+
+def act_bwd(dy, y, act):
+    M, C = _rows(y).shape
+    dy = _rows(dy if dy.stride(1) == 1 else dy.contiguous())
+    dx = torch.empty((M, C), dtype=torch.float32, device=y.device)
+    L.call("pdf_act_bwd", L.ptr(dy), dy.stride(0), L.ptr(y), y.stride(0), int(act), M, C, L.ptr(dx), dx.stride(0),
+           L.stream())
+    return dx
+
+
+def sft_modulate(fea, scale, shift):
+    M, C = _rows(fea).shape
+    out = torch.empty((M, C), dtype=torch.float32, device=fea.device)
+    L.call("pdf_sft_modulate", L.ptr(fea), fea.stride(0), L.ptr(_rows(scale)), scale.stride(0), L.ptr(_rows(shift)),
+           shift.stride(0), M, C, L.ptr(out), out.stride(0), L.stream())
+    return out
+
+
+def sft_modulate_bwd(dout, fea, scale):
+    """-> (dfea, dscale); dshift is dout itself."""
+    M, C = _rows(fea).shape
+    dout = _rows(dout if dout.stride(1) == 1 else dout.contiguous())
+    dfea = torch.empty((M, C), dtype=torch.float32, device=fea.device)
+    dscale = torch.empty_like(dfea)
+    L.call("pdf_sft_modulate_bwd", L.ptr(dout), dout.stride(0), L.ptr(fea), fea.stride(0), L.ptr(scale),
+           scale.stride(0), M, C, L.ptr(dfea), dfea.stride(0), L.ptr(dscale), dscale.stride(0), L.stream())
+    return dfea, dscale
+
+
+def linear_tn(a, b):
+    """a [M,N], b [M,K] -> a^T b [N,K]  (weight gradient: a = dY, b = layer input)."""
+    L.require_cuda(a, b)
+    M, N = _rows(a).shape
+    K = _rows(b).shape[1]
+    assert b.shape[0] == M
+    c = torch.empty((N, K), dtype=torch.float32, device=a.device)
+    L.call("pdf_linear_tn_f32", L.ptr(a), a.stride(0), L.ptr(b), b.stride(0), M, N, K, L.ptr(c), c.stride(0),
+           L.stream())
+    return c
+
+
+def group_max(y, G):
+    M, C = _rows(y).shape
+    assert M % G == 0
+    out = torch.empty((M // G, C), dtype=torch.float32, device=y.device)
+    L.call("pdf_group_max", L.ptr(y), y.stride(0), G, M // G, C, L.ptr(out), out.stride(0), L.stream())
+    return out
+
+
+def group_max_bwd(y, dout, G):
+    M, C = _rows(y).shape
+    dout = _rows(dout if dout.stride(1) == 1 else dout.contiguous())
+    dy = torch.empty((M, C), dtype=torch.float32, device=y.device)
+    L.call("pdf_group_max_bwd", L.ptr(y), y.stride(0), L.ptr(dout), dout.stride(0), G, M // G, C, L.ptr(dy),
+           dy.stride(0), L.stream())
+    return dy
+
+
+def group_scatter_add(dg, idx, n_points):
+    """dg [B,N1,K,C] contiguous, idx int32 [B,N1,K] -> dpts [B,n_points,C]."""
+    L.require_cuda(dg, idx)
+    dg = L.f32c(dg)
+    B, N1, K, C = dg.shape
+    dpts = torch.zeros((B, n_points, C), dtype=torch.float32, device=dg.device)
+    L.call("pdf_group_scatter_add", L.ptr(dg), L.ptr(idx), B, n_points, N1, K, C, L.ptr(dpts), C, L.stream())
+    return dpts
+
+
+def gather_nchw_bwd(dout, ind, shape):
+    """dout [B,n,C], ind int64 [B,n] -> dfeat of ``shape`` [B,C,H,W]."""
+    L.require_cuda(dout, ind)
+    dout = L.f32c(dout)
+    ind = ind.long().contiguous()
+    B, n, C = dout.shape
+    dfeat = torch.zeros(tuple(shape), dtype=torch.float32, device=dout.device)
+    L.call("pdf_gather_nchw_bwd", L.ptr(dout), L.ptr(ind), B, C, dfeat[0, 0].numel(), n, L.ptr(dfeat), L.stream())
+    return dfeat

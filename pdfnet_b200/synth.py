@@ -126,6 +126,13 @@ def pyramid(n_frames, R, seed=317, dtype=torch.float32):
     return out
 
 
+def train_inputs(B=2, R=64, seed=41):
+    """Inputs of the training-step golden (tests/golden/train_step.npz): clouds, choose,
+    pyramid maps and the direction ``gdir`` of the scalar loss sum(out * gdir)."""
+    gdir = torch.randn((B, 1, 1024), generator=_gen("gdir", seed))
+    return clouds(B, seed=seed), choose_indices(B, R, seed=seed), pyramid(B, R, seed=seed), gdir
+
+
 def rgbd_frames(n_frames, R, seed=317):
     """Synthetic depth [B,R,R] f32 metres (0.5 m + 2 cm noise inside two disjoint hand
     rectangles, 0 elsewhere), masks [B,2,R,R] f32 (channel 0 = right, 1 = left as

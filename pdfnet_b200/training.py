@@ -1,0 +1,225 @@
+"""Training-mode forward + backward of the fusion path (BASELINE cfg5), fp32.
+
+The reference trains this path through torch.autograd over PointNet_Plus.forward
+(intaghand_encoder.py:118-159) with the DDP gradient all-reduce of main.py:44-73.  Here every
+differentiable stage is a ``torch.autograd.Function`` whose forward AND backward run on the
+hand-written kernels of csrc/train_f32.cu / linear_f32.cu / gather.cu / knn_fps.cu; autograd only
+chains them (and does the concatenations), so the module drops into the reference's training loop,
+its optimizer and its DistributedDataParallel wrapper unchanged.
+
+Semantics kept from the reference: train-mode BatchNorm2d over all rows of ONE call (the reference
+calls PointNet_Plus once per hand, :805-806, so statistics are per hand and the running buffers are
+updated twice per step); neighbour indices are constants of the graph; max-pool gradient goes to the
+first maximum; gradients flow into the pyramid maps l0/l1/l2, the SFT and MLP parameters, but not
+into the input cloud.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+from . import ops
+
+
+def _c(t):
+    return t if t.stride(-1) == 1 and t.dtype == torch.float32 else t.float().contiguous()
+
+
+class LinearFn(Function):
+    """y = act(x @ w.T + b);  x [M,K], w [N,K]."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        x, w = _c(x), _c(w)
+        y = ops.linear(x, w, b, act=act)
+        ctx.act = act
+        ctx.save_for_backward(x, w, y if act != L.ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = _c(dy)
+        if ctx.act != L.ACT_NONE:
+            dy = ops.act_bwd(dy, y, ctx.act)
+        dx = ops.linear(dy, w.t().contiguous()) if ctx.needs_input_grad[0] else None
+        dw = ops.linear_tn(dy, x) if ctx.needs_input_grad[1] else None
+        db = ops.col_sum(dy) if ctx.needs_input_grad[2] else None
+        return dx, dw, db, None
+
+
+class BatchNormActFn(Function):
+    """Train-mode BatchNorm over rows + optional ReLU; updates running_mean / running_var in place."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu):
+        x = _c(x)
+        mean, rstd = ops.bn_batch_stats(x, eps, momentum, running_mean, running_var)
+        y = ops.bn_act_fwd(x, mean, rstd, gamma, beta, relu)
+        ctx.relu = relu
+        ctx.save_for_backward(x, y, mean, rstd, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, rstd, gamma = ctx.saved_tensors
+        dx, dgamma, dbeta = ops.bn_act_bwd(_c(dy), y, x, mean, rstd, gamma, ctx.relu)
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
+class GroupMaxFn(Function):
+    """nn.MaxPool2d over groups of G consecutive rows."""
+
+    @staticmethod
+    def forward(ctx, y, G):
+        y = _c(y)
+        ctx.G = G
+        ctx.save_for_backward(y)
+        return ops.group_max(y, G)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (y,) = ctx.saved_tensors
+        return ops.group_max_bwd(y, _c(dout), ctx.G), None
+
+
+class GroupGatherFn(Function):
+    """group_points / group_points_2 gather (utils.py:153-158, :181-186) with constant indices."""
+
+    @staticmethod
+    def forward(ctx, pts, idx):
+        g, _ = ops.group_gather(pts, idx, want_center=False)
+        ctx.n_points = pts.shape[1]
+        ctx.save_for_backward(idx)
+        return g
+
+    @staticmethod
+    def backward(ctx, dg):
+        (idx,) = ctx.saved_tensors
+        return ops.group_scatter_add(dg, idx, ctx.n_points), None
+
+
+class SFTModulateFn(Function):
+    """fea * (scale + 1) + shift (intaghand_encoder.py:219)."""
+
+    @staticmethod
+    def forward(ctx, fea, scale, shift):
+        fea, scale, shift = _c(fea), _c(scale), _c(shift)
+        ctx.save_for_backward(fea, scale)
+        return ops.sft_modulate(fea, scale, shift)
+
+    @staticmethod
+    def backward(ctx, dout):
+        fea, scale = ctx.saved_tensors
+        dout = _c(dout)
+        dfea, dscale = ops.sft_modulate_bwd(dout, fea, scale)
+        return dfea, dscale, dout
+
+
+class GatherNCHWFn(Function):
+    """_tranpose_and_gather_feat (models/utils.py:22-26): feat [B,C,H,W], ind [B,n] -> [B,n,C]."""
+
+    @staticmethod
+    def forward(ctx, feat, ind):
+        ctx.shape = feat.shape
+        ctx.save_for_backward(ind)
+        return ops.gather_nchw(feat, ind)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ind,) = ctx.saved_tensors
+        return ops.gather_nchw_bwd(dout, ind, ctx.shape), None
+
+
+def _conv_w(conv):
+    return conv.weight.view(conv.out_channels, conv.in_channels)
+
+
+def sft_rows(sft, fea_rows, cond_rows):
+    """SFTLayer on rows: fea [M,Cf], cond [M,Cc] -> [M,Cf] (differentiable)."""
+    hs = LinearFn.apply(cond_rows, _conv_w(sft.SFT_scale_conv0), sft.SFT_scale_conv0.bias, L.ACT_LEAKY01)
+    scale = LinearFn.apply(hs, _conv_w(sft.SFT_scale_conv1), sft.SFT_scale_conv1.bias, L.ACT_NONE)
+    hh = LinearFn.apply(cond_rows, _conv_w(sft.SFT_shift_conv0), sft.SFT_shift_conv0.bias, L.ACT_LEAKY01)
+    shift = LinearFn.apply(hh, _conv_w(sft.SFT_shift_conv1), sft.SFT_shift_conv1.bias, L.ACT_NONE)
+    return SFTModulateFn.apply(fea_rows, scale, shift)
+
+
+def mlp_max_rows(net, rows, group):
+    """(Conv1x1 -> BatchNorm2d(train) -> ReLU) x3 -> max over ``group`` consecutive rows."""
+    h = rows
+    for i in (0, 3, 6):
+        conv, bn = net[i], net[i + 1]
+        h = LinearFn.apply(h, _conv_w(conv), conv.bias, L.ACT_NONE)
+        momentum = bn.momentum if bn.momentum is not None else 0.1
+        if bn.training:
+            h = BatchNormActFn.apply(h, bn.weight, bn.bias, bn.running_mean, bn.running_var, momentum, bn.eps, True)
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+        else:
+            raise RuntimeError("mlp_max_rows is the train-mode path")
+    return GroupMaxFn.apply(h, group)
+
+
+def pyramid_indices(choose, R):
+    """intaghand_encoder.py:125-126"""
+    c2 = (choose // R // 2) * (R // 2) + choose % R // 2
+    c4 = (choose // R // 4) * (R // 4) + choose % R // 4
+    return c2, c4
+
+
+def pointnet_plus_train(net, points, emb, choose):
+    """PointNet_Plus.forward in training mode: points [B,N,3], emb [l0,l1,l2], choose [B,N]
+    -> [B,1,1024] with an autograd graph through every stage."""
+    L.require_cuda(points, choose, *emb)
+    opt = net.opt
+    N1, N2, K = net.sample_num_level1, net.sample_num_level2, net.knn_K
+    B, N, _ = points.shape
+    choose = choose.long()
+    points = _c(points)
+    e0 = GatherNCHWFn.apply(_c(emb[0]), choose)                                         # [B,N,3]
+    pts0 = sft_rows(net.sft0, points.reshape(B * N, 3), e0.reshape(B * N, 3)).view(B, N, 3)
+    idx1 = ops.knn_ball(pts0.detach(), N1, K, opt.ball_radius)
+    g1 = GroupGatherFn.apply(pts0, idx1)                                                # [B,N1,K,3]
+    c2, c4 = pyramid_indices(choose, opt.default_resolution)
+    e1 = GatherNCHWFn.apply(_c(emb[1]), c2[:, :N1].contiguous())
+    e2 = GatherNCHWFn.apply(_c(emb[2]), c4[:, :N2].contiguous())
+    f1 = mlp_max_rows(net.netR_1, g1.view(B * N1 * K, -1), K)                           # [B*N1,128]
+    x1 = torch.cat((pts0[:, :N1].reshape(B * N1, 3), f1), 1)                            # cat((y, x), 1) (:134)
+    x1 = sft_rows(net.sft1, x1, e1.reshape(B * N1, -1))
+    C1 = x1.shape[1]
+    x1b = x1.view(B, N1, C1)
+    idx2 = ops.knn_ball(x1b.detach(), N2, K, net.ball_radius2)
+    g2 = GroupGatherFn.apply(x1b, idx2)                                                 # [B,N2,K,131]
+    f2 = mlp_max_rows(net.netR_2, g2.view(B * N2 * K, C1), K)                           # [B*N2,256]
+    x2 = torch.cat((x1b[:, :N2, :3].reshape(B * N2, 3), f2), 1)
+    x2 = sft_rows(net.sft2, x2, e2.reshape(B * N2, -1))
+    out = mlp_max_rows(net.netR_3, x2, N2)                                              # [B,1024]
+    return out.view(B, 1, -1)
+
+
+def hand_fusion_train(fusion, cloud, point_wise_emb, choose, center_features):
+    """ResNetSimple.forward :805-809 in training mode: one PointNet_Plus call per hand (per-hand
+    BatchNorm statistics, as in the reference), concatenation, final SFTLayer(1024,1024)."""
+    B = cloud.shape[0]
+    left = pointnet_plus_train(fusion.pointnet_plus, cloud[:, 0], point_wise_emb, choose[:, 0])
+    right = pointnet_plus_train(fusion.pointnet_plus, cloud[:, 1], point_wise_emb, choose[:, 1])
+    feat = torch.cat((left, right), 1)                                                  # [B,2,1024]
+    fused = sft_rows(fusion.sft, feat.reshape(B * 2, -1), _c(center_features).reshape(B * 2, -1))
+    return fused.view(B, 2, -1)
+
+
+def allreduce_gradients(params, world_size, group=None):
+    """DDP's exchange step (main.py:44-73): SUM over ranks then divide by world size, one flat
+    bucket over NCCL / NVLink.  No-op outside an initialised process group."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads or world_size <= 1 or not dist.is_initialized():
+        return 0
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(world_size)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+    return flat.numel() * 4

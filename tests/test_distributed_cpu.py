@@ -47,3 +47,38 @@ def test_two_rank_sharding(tmp_path):
     for r in res:
         assert torch.equal(r["full"], ref)
         assert r["t"] == 2.0
+
+
+def _grad_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from pdfnet_b200 import parallel, training
+    parallel.init_distributed("gloo")
+    g = torch.Generator().manual_seed(100 + rank)
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in ((3, 5), (7,), (2, 2, 2))]
+    params.append(torch.nn.Parameter(torch.zeros(4)))               # no gradient: skipped, like unused heads
+    for p in params[:3]:
+        p.grad = torch.randn(p.shape, generator=g)
+    nbytes = training.allreduce_gradients(params, world)
+    torch.save(dict(grads=[p.grad for p in params[:3]], nbytes=nbytes, none=params[3].grad is None),
+               os.path.join(out_dir, "g%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce(tmp_path):
+    """The cfg5 exchange step (DDP semantics, main.py:44-73): every rank ends with the MEAN gradient."""
+    world = 2
+    mp.spawn(_grad_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(os.path.join(str(tmp_path), "g%d.pt" % r)) for r in range(world)]
+    shapes = ((3, 5), (7,), (2, 2, 2))
+    expect = []
+    gens = [torch.Generator().manual_seed(100 + r) for r in range(world)]
+    for s in shapes:
+        expect.append(sum(torch.randn(s, generator=g) for g in gens) / world)
+    for r in res:
+        assert r["none"] and r["nbytes"] == 4 * (15 + 7 + 8)
+        for got, want in zip(r["grads"], expect):
+            torch.testing.assert_close(got, want)

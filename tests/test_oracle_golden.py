@@ -140,3 +140,41 @@ def test_mano_head():
     g = load_golden("mano_head")
     y = O.mano_head(torch.from_numpy(g["x"]), synth.mano_head_state(seed=317, std=0.05))
     np.testing.assert_allclose(y.numpy(), g["y"], rtol=1e-5, atol=1e-6)
+
+
+def _train_state(dtype=torch.float64):
+    sd = {k: (v.clone().to(dtype) if v.is_floating_point() else v.clone())
+          for k, v in synth.pointnet_plus_state(seed=317).items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    return sd
+
+
+def test_train_step_oracle_vs_reference_autograd():
+    """The train-mode restatement reproduces the reference's output, every parameter gradient,
+    the pyramid-map gradients and the BatchNorm running-buffer updates (cfg5 semantics).
+    Compared in float64, where autograd rounding noise does not mask semantic differences."""
+    from conftest import check_grad_digest
+    g = load_golden("train_step")
+    B, R = int(g["B"]), int(g["R"])
+    opt = _opt(default_resolution=R)
+    pts, choose, emb, gdir = synth.train_inputs(B, R)
+    out32 = O.pointnet_plus_train(_train_state(torch.float32), pts, emb, choose, opt)
+    np.testing.assert_allclose(out32.detach().numpy(), g["out_fp32"], rtol=1e-4, atol=1e-5)
+    emb = [e.double().requires_grad_(True) for e in emb]
+    sd = _train_state()
+    out = O.pointnet_plus_train(sd, pts.double(), emb, choose, opt, dtype=torch.float64)
+    np.testing.assert_allclose(out.detach().numpy(), g["out"], rtol=1e-9, atol=1e-10)
+    (out * gdir.double()).sum().backward()
+    n = 0
+    for k, v in sd.items():
+        if v.requires_grad:
+            check_grad_digest(g, "grad:" + k, v.grad.numpy(), rtol=1e-6)
+            n += 1
+    assert n == 3 * 8 + 3 * 3 * 4          # 3 SFT layers x 8 tensors + 9 conv/BN pairs x 4 tensors
+    for i, e in enumerate(emb):
+        check_grad_digest(g, "grad:emb%d" % i, e.grad.numpy(), rtol=1e-6)
+    for k, v in sd.items():
+        if "running_" in k:
+            np.testing.assert_allclose(v.numpy(), g["buf:" + k], rtol=1e-9, atol=1e-12)
