@@ -426,6 +426,169 @@ def run_cfg2(args):
     }))
 
 
+def cfg5_workload(args):
+    return ("cfg5-train-hotpath: %d frames/GPU x 2 hands, %dx%d pyramid, 1024-pt clouds; train-mode forward "
+            "(batch-stat BatchNorm, per hand) + backward of pyramid gather/SFT0+SA1+SFT1+SA2+SFT2+global MLP+"
+            "fusion SFT, gradient all-reduce (mean), Adam step" % (args.frames, args.res, args.res))
+
+
+def cfg5_inputs(B, R, seed):
+    from pdfnet_b200 import synth
+    g = torch.Generator().manual_seed(seed)
+    return dict(cloud=synth.clouds(2 * B, seed=seed).view(B, 2, 1024, 3),
+                choose=synth.choose_indices(2 * B, R, seed=seed).view(B, 2, 1024),
+                l0=synth.pyramid(B, R, seed=seed)[0], l1=synth.pyramid(B, R, seed=seed)[1],
+                l2=synth.pyramid(B, R, seed=seed)[2], center=torch.randn((B, 2, 1024), generator=g),
+                target=torch.randn((B, 2, 1024), generator=g))
+
+
+def run_cfg5_reference(args):
+    """CPU arm of cfg5: the oracle's train-mode restatement (torch-CPU autograd, fp32, all host
+    threads) + Adam on a bounded sample of the same workload; rank 0 only."""
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    from oracle import pdf_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    R, B = args.res, args.cpu_sample_frames
+    opt = make_opt(R)
+    inp = cfg5_inputs(B, R, 317)
+    st = load_states()
+    sd = {k: v.clone() for k, v in st["pointnet"].items()}
+    sft = {k: v.clone().requires_grad_(True) for k, v in st["sft"].items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    params = [v for v in list(sd.values()) + list(sft.values()) if v.requires_grad]
+    optim = torch.optim.Adam(params, lr=1e-4)
+    emb = [inp["l0"], inp["l1"], inp["l2"]]
+
+    def step():
+        optim.zero_grad(set_to_none=True)
+        l = O.pointnet_plus_train(sd, inp["cloud"][:, 0], emb, inp["choose"][:, 0], opt)
+        r = O.pointnet_plus_train(sd, inp["cloud"][:, 1], emb, inp["choose"][:, 1], opt)
+        fused = O.sft_layer(torch.cat((l, r), 1).transpose(1, 2), inp["center"], sft)
+        loss = ((fused - inp["target"]) ** 2).mean()
+        loss.backward()
+        optim.step()
+        return float(loss.detach())
+
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        step()
+    ts = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(ts) / len(ts)
+    val = B / (ms / 1e3)
+    cores = os.cpu_count() or 1
+    print(json.dumps({
+        "impl": "reference", "metric": "train_frames_per_sec_hot_path", "value": val, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg5_workload(args), "sample_frames_per_step": B, "resolution": R},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d frames/step, oracle train-mode port (torch CPU autograd fp32, %d threads)"
+                                   % (B, cores)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def run_cfg5(args):
+    """BASELINE.json configs[4] restricted to the hot path: one training step = train-mode forward +
+    backward on this repo's kernels, ONE flat-bucket gradient all-reduce over NCCL, Adam update."""
+    from pdfnet_b200 import parallel
+    rank, world, local = parallel.init_distributed("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    from pdfnet_b200 import HandFusion, _lib, training
+    R, B = args.res, args.frames
+    model = HandFusion(make_opt(R), precision="fp32")
+    st = load_states()
+    sd = {"pointnet_plus." + k: v for k, v in st["pointnet"].items()}
+    sd.update({"sft." + k: v for k, v in st["sft"].items()})
+    model.load_state_dict(sd, strict=False)
+    model = model.to(dev).train()
+    params = [p for n, p in model.named_parameters() if not n.startswith("mano_head") and "netR_FC" not in n]
+    optim = torch.optim.Adam(params, lr=1e-4, fused=True)
+    host = cfg5_inputs(B, R, 317 + rank)
+    pinned = {k: v.contiguous().pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    staging = {k: torch.empty_like(v) for k, v in resident.items()}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    comm_bytes = [0]
+
+    def train_step(d):
+        optim.zero_grad(set_to_none=True)
+        fused = model(d["cloud"], [d["l0"], d["l1"], d["l2"]], d["choose"], d["center"])
+        loss = ((fused - d["target"]) ** 2).mean()
+        loss.backward()
+        comm_bytes[0] = training.allreduce_gradients(params, world)
+        optim.step()
+        return loss
+
+    def e2e_step():
+        for k, v in pinned.items():
+            staging[k].copy_(v, non_blocking=True)
+        return float(train_step(staging).detach())           # device -> host read of the loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        return parallel.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / steps, dev)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms_dev = timed_loop(lambda: train_step(resident), args.steps, args.warmup)
+    launches = (_lib.launch_count() - l0) // (args.steps + args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed_loop(e2e_step, args.steps, args.warmup)
+    loss = float(train_step(resident).detach())
+    peak_mem = torch.cuda.max_memory_allocated(dev)
+    if rank == 0:
+        n_clouds = 2 * B
+        fwd = (FLOP_SA1 + FLOP_SA2 + FLOP_GLOBAL + FLOP_SFT1 + FLOP_SFT2) * n_clouds
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+        ach = 3 * fwd / (ms_dev * 1e-3) / 1e12                 # forward + data-gradient + weight-gradient GEMMs
+        print(json.dumps({
+            "metric": "train_frames_per_sec_hot_path", "value": world * B / (ms_dev * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg5_workload(args), "frames_per_gpu": B, "resolution": R, "precision": "fp32",
+                       "parallelism": "dp%d" % world, "l2": "256 MiB flush write between timed iterations",
+                       "optimizer": "Adam (torch fused), lr 1e-4; loss = MSE(fused, target)"},
+            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pinned.values()),
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"kernel": "whole step (FFMA fp32 GEMMs)", "bound": "tensor", "achieved": ach,
+                         "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+                         "traffic": None, "pipe": "FFMA fp32 (training GEMMs are not on tensor cores yet)"},
+            "allreduce_bytes_per_step": comm_bytes[0], "final_loss": loss, "peak_mem_gb": peak_mem / 2 ** 30,
+            "cpu_baseline": None}))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -433,16 +596,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--frames", type=int, default=128, help="frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (cfg3: 128, cfg5: 64)")
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--cpu-sample-frames", type=int, default=4)
     ap.add_argument("--e2e-chunks", type=int, default=4, help="H2D/compute overlap chunks in the e2e measurement")
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2"],
-                    help="cfg3 = hot path at 128 frames/GPU (default, the driver's contract); cfg2 = SA microbench")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5"],
+                    help="cfg3 = hot path at 128 frames/GPU (default, the driver's contract); cfg2 = SA microbench; "
+                         "cfg5 = training step (use --frames 64)")
     ap.add_argument("--clouds", type=int, default=64, help="cfg2: number of clouds")
     args = ap.parse_args()
+    if args.frames is None:
+        args.frames = 64 if args.workload == "cfg5" else 128
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.workload == "cfg5":
+        (run_cfg5_reference if args.impl == "reference" else run_cfg5)(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.workload == "cfg2":
         run_cfg2(args)
