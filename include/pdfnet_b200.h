@@ -172,6 +172,20 @@ int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const void* n_img, i
                   int64_t ld_out, int64_t rows_valid, const float* F, int64_t ldf, void* out_img, int out_kb,
                   void* out_bf16, int64_t ld_bf16, int bf16_col_off, const int32_t* tile_desc_host, float* out_max,
                   int64_t ld_max, const float* xyz_w, float* xyz_x, int64_t xyz_ld, void* stream);
+/* Transposed tile image for reductions over rows (weight gradients): X[M, ld] columns
+ * [col0, col0+C) -> bf16 image of X^T cut into batches of Mc rows of X (Mc % 64 == 0): layout
+ * [batch][row-tile of 128 channels][k-block of 64 rows], zero padded; split as in pdf_rows_to_image
+ * (1 = [hi|hi|lo], 2 = [hi|lo|hi], tripling the k-blocks).  pdf_rows_to_image accepts split = 2 too. */
+int pdf_rows_to_image_t(const float* X, int64_t ld, int64_t M, int col0, int C, void* img, int64_t Mc, int split,
+                        void* stream);
+/* Batched ROW-mode GEMM without bias/activation: for every batch b, out[b][m, n] = sum_k Mop_b[m,k] *
+ * Nop_b[n,k]; operands advance by *_batch_stride bytes, the fp32 output by out_batch_stride floats.
+ * With pdf_rows_to_image_t images this is the split-K weight gradient dW = dY^T X (autograd of the
+ * 1x1 convs, intaghand_encoder.py:48-103,205-219); the caller sums the per-batch partials. */
+int pdf_gemm_bf16_batched(const void* m_img, int m_tiles, int m_kb, int64_t m_batch_stride, const void* n_img,
+                          int n_tiles, int n_kb, int64_t n_batch_stride, int KB, int batches, float* out_f32,
+                          int64_t ld_out, int64_t out_batch_stride, int64_t rows_valid,
+                          const int32_t* tile_desc_host, void* stream);
 /* SFT on the three xyz channels of level 1 in full fp32 (they feed the level-2 neighbour
  * search): x[m,c] = x[m,c]*(scale_c+1)+shift_c for c < 3; cond fp32 [M,cc]; conv weights as in
  * SFTLayer ([out,in] row-major; only rows 0..2 of the second convs are read). cc must be 64. */

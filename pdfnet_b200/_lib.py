@@ -37,6 +37,8 @@ SIGNATURES = {
     "pdf_mano_lbs": [_vp] * 11 + [_i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "pdf_mano_pose_feature": [_vp, _vp, _i64, _vp, _vp],
     "pdf_split_coeff": [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "pdf_rows_to_image_t": [_vp, _i64, _i64, _i32, _i32, _vp, _i64, _i32, _vp],
+    "pdf_gemm_bf16_batched": [_vp, _i32, _i32, _i64, _vp, _i32, _i32, _i64, _i32, _i32, _vp, _i64, _i64, _i64, _vp, _vp],
     "pdf_bn_stats": [_vp, _i64, _i64, _i32, _vp, _vp],
     "pdf_bn_finalize": [_vp, _vp, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp],
     "pdf_bn_act_fwd": [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _i64, _vp],

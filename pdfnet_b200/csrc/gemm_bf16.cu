@@ -47,6 +47,9 @@ struct GemmParams {
   // bf16 image of lrelu(D+b) the epilogue applies the SFT modulation to the 3 xyz channels in fp32:
   // x[m,c] = x[m,c]*(w1s[c].h_s + b1s[c] + 1) + (w1h[c].h_h + b1h[c]).  xyz_w = [2][3][64] then [2][3].
   const float* xyz_w; float* xyz_x; int64_t xyz_ld;
+  // batched mode (split-K weight gradients): work item = (batch, m-tile, n-tile); operands and the
+  // fp32 output advance by these strides per batch (bytes / floats)
+  int batches; int64_t m_batch_stride, n_batch_stride, out_batch_stride;
   int tile_col[G_MAX_NT];        // ROW mode, per N-tile: first fp32 column (F and out_f32)
   int tile_nvalid[G_MAX_NT];     //   valid output columns of this N-tile (others are written as 0 / skipped)
   int tile_okb[G_MAX_NT];        //   first k-block of this N-tile in the output image
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
   const bool xyz = !COLMAX && P.xyz_w != nullptr;
   if (!COLMAX) {
     for (int i = threadIdx.x; i < P.n_tiles * 128; i += G_THREADS) {
-      s_bias[i] = P.bias0[i];
+      s_bias[i] = P.bias0 ? P.bias0[i] : 0.f;
       s_bias[G_MAX_NT * 128 + i] = dual ? P.bias1[i] : 0.f;
     }
     if (xyz) for (int i = threadIdx.x; i < 390; i += G_THREADS) s_xyz[i] = P.xyz_w[i];
@@ -87,15 +90,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
-  const int n_work = P.m_tiles * P.n_tiles;
+  const int per_batch = P.m_tiles * P.n_tiles;
+  const int n_work = per_batch * P.batches;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int mt = w / P.n_tiles, nt = w % P.n_tiles;
-        const uint8_t* mb = P.m_img + (size_t)mt * P.m_kb * G_BLOCK;
-        const uint8_t* nb = P.n_img + (size_t)nt * P.n_kb * G_BLOCK;
+        const int bt = w / per_batch, wr = w - bt * per_batch;
+        const int mt = wr / P.n_tiles, nt = wr % P.n_tiles;
+        const uint8_t* mb = P.m_img + (size_t)bt * P.m_batch_stride + (size_t)mt * P.m_kb * G_BLOCK;
+        const uint8_t* nb = P.n_img + (size_t)bt * P.n_batch_stride + (size_t)nt * P.n_kb * G_BLOCK;
         for (int kb = 0; kb < P.KB; ++kb) {
           mbar_wait(smem_u32(&bars[G_STAGES + stage]), phase ^ 1);
           const uint32_t full = smem_u32(&bars[stage]);
@@ -138,7 +143,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
     const uint32_t lane_off = ((uint32_t)(q4 * 32)) << 16;
     int as = 0; uint32_t aphase = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int mt = w / P.n_tiles, nt = w % P.n_tiles;
+      const int bt = w / per_batch, wr = w - bt * per_batch;
+      const int mt = wr / P.n_tiles, nt = wr % P.n_tiles;
       mbar_wait(smem_u32(&bars[2 * G_STAGES + as]), aphase);
       fence_after_sync();
       const uint32_t acc = tmem_base + as * acc_cols + lane_off;
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
             }
           }
           if (P.out_f32 != nullptr && row_ok) {
-            float* o = P.out_f32 + m * P.ld_out + col0 + c0;
+            float* o = P.out_f32 + (int64_t)bt * P.out_batch_stride + m * P.ld_out + col0 + c0;
 #pragma unroll
             for (int q = 0; q < 32; q += 4) {
               if (c0 + q + 3 < nvalid) *reinterpret_cast<float4*>(o + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
@@ -291,8 +297,52 @@ __global__ void rows_to_image_kernel(const float* __restrict__ X, int64_t ld, in
     const uint32_t off = sw128_off((uint32_t)(m & 127), ch * 8);
     uint8_t* tile = img + ((size_t)mt * kb_total + kb0) * G_BLOCK;
     *reinterpret_cast<uint4*>(tile + (size_t)kb * G_BLOCK + off) = w;
-    if (split) {                                         // [hi | hi | lo]: fp32-accurate products on bf16 tensor cores
-      *reinterpret_cast<uint4*>(tile + (size_t)(nkb + kb) * G_BLOCK + off) = w;
+    if (split) {                                         // fp32-accurate products on bf16 tensor cores:
+      float l[8];                                        // split 1 = [hi | hi | lo], split 2 = [hi | lo | hi]
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const uint32_t pk = i == 0 ? w.x : (i == 2 ? w.y : (i == 4 ? w.z : w.w));
+        l[i] = f[i] - __uint_as_float(pk << 16);
+        l[i + 1] = f[i + 1] - __uint_as_float(pk & 0xffff0000u);
+      }
+      uint4 wl;
+      wl.x = pack_bf16(l[0], l[1]); wl.y = pack_bf16(l[2], l[3]); wl.z = pack_bf16(l[4], l[5]); wl.w = pack_bf16(l[6], l[7]);
+      *reinterpret_cast<uint4*>(tile + (size_t)(nkb + kb) * G_BLOCK + off) = split == 2 ? wl : w;
+      *reinterpret_cast<uint4*>(tile + (size_t)(2 * nkb + kb) * G_BLOCK + off) = split == 2 ? w : wl;
+    }
+  }
+}
+
+// Transposed image: fp32 rows X[M, ld], columns [col0, col0+C) -> bf16 image of X^T cut into batches of
+// Mc rows of X (Mc % 64 == 0): image rows = channels (zero-padded to 128), k = row index inside the batch.
+// Layout [batch][row-tile][k-block]; with split the k-blocks are tripled ([hi|hi|lo] or [hi|lo|hi]).
+// One CTA = 64 rows of X x 128 channels, transposed through shared memory.
+__global__ void __launch_bounds__(256)
+rows_to_image_t_kernel(const float* __restrict__ X, int64_t ld, int64_t M, int col0, int C, uint8_t* __restrict__ img,
+                       int64_t Mc, int split) {
+  __shared__ float s[64][129];
+  const int64_t m0 = (int64_t)blockIdx.x * 64;
+  const int rt = blockIdx.y, ch0 = rt * 128;
+  for (int e = threadIdx.x; e < 64 * 128; e += 256) {
+    const int r = e >> 7, c = e & 127;
+    const int64_t m = m0 + r;
+    s[r][c] = (m < M && ch0 + c < C) ? X[m * ld + col0 + ch0 + c] : 0.f;
+  }
+  __syncthreads();
+  const int nkb = (int)(Mc / 64), parts = split ? 3 : 1, n_rt = (C + 127) / 128;
+  const int64_t bt = m0 / Mc;
+  const int kb = (int)((m0 - bt * Mc) / 64);
+  uint8_t* base = img + (((size_t)bt * n_rt + rt) * (size_t)(nkb * parts)) * G_BLOCK;
+  for (int e = threadIdx.x; e < 128 * 8; e += 256) {
+    const int c = e & 127, chunk = e >> 7;               // consecutive threads -> consecutive channels
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = s[chunk * 8 + i][c];
+    uint4 w;
+    w.x = pack_bf16(f[0], f[1]); w.y = pack_bf16(f[2], f[3]); w.z = pack_bf16(f[4], f[5]); w.w = pack_bf16(f[6], f[7]);
+    const uint32_t off = sw128_off((uint32_t)c, chunk * 8);
+    *reinterpret_cast<uint4*>(base + (size_t)kb * G_BLOCK + off) = w;
+    if (split) {
       float l[8];
 #pragma unroll
       for (int i = 0; i < 8; i += 2) {
@@ -302,7 +352,8 @@ __global__ void rows_to_image_kernel(const float* __restrict__ X, int64_t ld, in
       }
       uint4 wl;
       wl.x = pack_bf16(l[0], l[1]); wl.y = pack_bf16(l[2], l[3]); wl.z = pack_bf16(l[4], l[5]); wl.w = pack_bf16(l[6], l[7]);
-      *reinterpret_cast<uint4*>(tile + (size_t)(2 * nkb + kb) * G_BLOCK + off) = wl;
+      *reinterpret_cast<uint4*>(base + (size_t)(nkb + kb) * G_BLOCK + off) = split == 2 ? wl : w;
+      *reinterpret_cast<uint4*>(base + (size_t)(2 * nkb + kb) * G_BLOCK + off) = split == 2 ? w : wl;
     }
   }
 }
@@ -435,6 +486,7 @@ extern "C" int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const voi
   P.out_img = (uint8_t*)out_img; P.out_kb = out_kb; P.out_max = out_max; P.ld_max = ld_max;
   P.out_bf16 = (uint16_t*)out_bf16; P.ld_bf16 = ld_bf16; P.bf16_col_off = bf16_col_off;
   P.xyz_w = xyz_w; P.xyz_x = xyz_x; P.xyz_ld = xyz_ld;
+  P.batches = 1;
   PDF_REQUIRE(!xyz_w || (!colmax && n_tiles == 1 && kb_split == 0 && xyz_x), PDF_ERR_BAD_ARG,
               "pdf_gemm_bf16: XYZ mode needs one N tile, one accumulator and xyz_x");
   if (colmax) {
@@ -486,4 +538,53 @@ extern "C" int pdf_sft_xyz_f32(const float* cond, int64_t M, int cc, const float
   pdf::sft_xyz_kernel<64><<<(unsigned)((M + 127) / 128), 128, smem, (cudaStream_t)stream>>>(
       cond, M, w0s, b0s, w1s, b1s, w0h, b0h, w1h, b1h, x, ldx);
   return pdf::check_launch("pdf_sft_xyz_f32");
+}
+
+
+extern "C" int pdf_rows_to_image_t(const float* X, int64_t ld, int64_t M, int col0, int C, void* img, int64_t Mc,
+                                   int split, void* stream) {
+  if (M == 0) return PDF_OK;
+  PDF_REQUIRE(X && img && M > 0 && C > 0 && col0 >= 0 && ld >= col0 + C && Mc > 0 && Mc % 64 == 0 && split >= 0 &&
+                  split <= 2,
+              PDF_ERR_BAD_ARG, "pdf_rows_to_image_t: bad argument");
+  const int64_t batches = (M + Mc - 1) / Mc;
+  const int64_t gx = batches * (Mc / 64);                 // padded: every k-block of every batch is written
+  PDF_REQUIRE(gx < (1ll << 31), PDF_ERR_UNSUPPORTED, "pdf_rows_to_image_t: too many rows");
+  dim3 grid((unsigned)gx, (unsigned)((C + 127) / 128));
+  pdf::rows_to_image_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ld, M, col0, C, (uint8_t*)img, Mc, split);
+  return pdf::check_launch("pdf_rows_to_image_t");
+}
+
+extern "C" int pdf_gemm_bf16_batched(const void* m_img, int m_tiles, int m_kb, int64_t m_batch_stride, const void* n_img,
+                                     int n_tiles, int n_kb, int64_t n_batch_stride, int KB, int batches,
+                                     float* out_f32, int64_t ld_out, int64_t out_batch_stride, int64_t rows_valid,
+                                     const int32_t* tile_desc_host, void* stream) {
+  using namespace pdf;
+  if (m_tiles == 0 || n_tiles == 0 || batches == 0) return PDF_OK;
+  PDF_REQUIRE(m_img && n_img && out_f32 && tile_desc_host, PDF_ERR_BAD_ARG, "pdf_gemm_bf16_batched: null pointer");
+  PDF_REQUIRE(m_tiles > 0 && n_tiles > 0 && n_tiles <= G_MAX_NT && batches > 0 && KB > 0 && KB <= m_kb && KB <= n_kb &&
+                  ld_out % 4 == 0 && out_batch_stride % 4 == 0,
+              PDF_ERR_BAD_ARG, "pdf_gemm_bf16_batched: bad size");
+  PDF_REQUIRE((int64_t)m_tiles * n_tiles * batches < (1ll << 31), PDF_ERR_UNSUPPORTED, "pdf_gemm_bf16_batched: too much work");
+  GemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.m_img = (const uint8_t*)m_img; P.n_img = (const uint8_t*)n_img;
+  P.m_kb = m_kb; P.n_kb = n_kb; P.m_tiles = m_tiles; P.n_tiles = n_tiles; P.KB = KB;
+  P.out_f32 = out_f32; P.ld_out = ld_out; P.rows_valid = rows_valid;
+  P.batches = batches; P.m_batch_stride = m_batch_stride; P.n_batch_stride = n_batch_stride;
+  P.out_batch_stride = out_batch_stride;
+  for (int i = 0; i < n_tiles; ++i) {
+    P.tile_col[i] = tile_desc_host[3 * i]; P.tile_nvalid[i] = tile_desc_host[3 * i + 1]; P.tile_okb[i] = tile_desc_host[3 * i + 2];
+    PDF_REQUIRE(P.tile_nvalid[i] >= 0 && P.tile_nvalid[i] <= 128 && (P.tile_col[i] % 4) == 0, PDF_ERR_BAD_ARG,
+                "pdf_gemm_bf16_batched: bad tile descriptor %d", i);
+  }
+  static pdf::PerDeviceOnce once;
+  if (once.first()) cudaFuncSetAttribute(gemm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t n_work = (int64_t)m_tiles * n_tiles * batches;
+  const int grid = (int)(n_work < sms ? n_work : sms);
+  gemm_bf16_kernel<false><<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(P);
+  return check_launch("pdf_gemm_bf16_batched");
 }

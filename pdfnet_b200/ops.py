@@ -164,7 +164,7 @@ def pack_image(w, split=False):
 
 def rows_to_image(x, col0, K, img=None, kb_total=None, kb0=0, split=False):
     """fp32 rows x[M, ld] columns [col0, col0+K) -> bf16 tile image (uint8 device tensor).
-    split=True writes [hi | hi | lo] (3x k-blocks)."""
+    split=True/1 writes [hi | hi | lo], split=2 writes [hi | lo | hi] (3x k-blocks)."""
     L.require_cuda(x, img)
     assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32
     M = x.shape[0]
@@ -173,7 +173,7 @@ def rows_to_image(x, col0, K, img=None, kb_total=None, kb0=0, split=False):
         kb_total = nkb
     if img is None:
         img = torch.empty((((M + 127) // 128) * kb_total * 16384,), dtype=torch.uint8, device=x.device)
-    L.call("pdf_rows_to_image", L.ptr(x), x.stride(0), M, col0, K, L.ptr(img), kb_total, kb0, 1 if split else 0,
+    L.call("pdf_rows_to_image", L.ptr(x), x.stride(0), M, col0, K, L.ptr(img), kb_total, kb0, int(split),
            L.stream())
     return img
 
@@ -457,3 +457,58 @@ def gather_nchw_bwd(dout, ind, shape):
     dfeat = torch.zeros(tuple(shape), dtype=torch.float32, device=dout.device)
     L.call("pdf_gather_nchw_bwd", L.ptr(dout), L.ptr(ind), B, C, dfeat[0, 0].numel(), n, L.ptr(dfeat), L.stream())
     return dfeat
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+def _tile_desc(n):
+    return [(128 * i, min(128, n - 128 * i), 0) for i in range((n + 127) // 128)]
+
+
+def linear_tc(x, w, bias=None, act=L.ACT_NONE):
+    """act(x @ w.T + bias) on the tcgen05 GEMM with split-bf16 operands (three bf16 products per
+    fp32 product: fp32-accurate, ~2^-16 relative).  x [M,K] fp32 rows, w [N,K] fp32 (device).
+    Returns a [M,N] view of a buffer whose row pitch is padded to a multiple of 4."""
+    L.require_cuda(x, w, bias)
+    M, K = _rows(x).shape
+    N = _rows(w).shape[0]
+    kb = 3 * ((K + 63) // 64)
+    nt = (N + 127) // 128
+    x_img = rows_to_image(x, 0, K, split=1)
+    w_img = rows_to_image(w, 0, K, split=2)
+    b = torch.zeros((nt * 128,), dtype=torch.float32, device=x.device)
+    if bias is not None:
+        b[:N] = bias
+    out = torch.empty((M, _pad4(N)), dtype=torch.float32, device=x.device)
+    gemm_bf16(x_img, (M + 127) // 128, kb, w_img, nt, kb, kb, b, act=act, out_f32=out, rows_valid=M,
+              tile_desc=_tile_desc(N))
+    return out[:, :N]
+
+
+def linear_tn_tc(a, b):
+    """a [M,N], b [M,K] -> a^T b [N,K] on the tcgen05 GEMM: split-K over batches of rows
+    (pdf_rows_to_image_t + pdf_gemm_bf16_batched, split-bf16 operands), partials summed in fp64."""
+    L.require_cuda(a, b)
+    M, N = _rows(a).shape
+    K = _rows(b).shape[1]
+    mt, nt = (N + 127) // 128, (K + 127) // 128
+    want = max(1, (2 * 148 + mt * nt - 1) // (mt * nt))                 # batches: about two waves of work items
+    Mc = max(512, ((M + want - 1) // want + 63) // 64 * 64)
+    batches = (M + Mc - 1) // Mc
+    kb = 3 * (Mc // 64)
+    dev = a.device
+    a_img = torch.empty((batches * mt * kb * 16384,), dtype=torch.uint8, device=dev)
+    b_img = torch.empty((batches * nt * kb * 16384,), dtype=torch.uint8, device=dev)
+    L.call("pdf_rows_to_image_t", L.ptr(a), a.stride(0), M, 0, N, L.ptr(a_img), Mc, 1, L.stream())
+    L.call("pdf_rows_to_image_t", L.ptr(b), b.stride(0), M, 0, K, L.ptr(b_img), Mc, 2, L.stream())
+    ldk = _pad4(K)
+    part = torch.zeros((batches, N, ldk), dtype=torch.float32, device=dev)
+    flat = [int(v) for t in _tile_desc(K) for v in t]
+    desc = (ctypes.c_int32 * len(flat))(*flat)
+    L.call("pdf_gemm_bf16_batched", L.ptr(a_img), mt, kb, mt * kb * 16384, L.ptr(b_img), nt, kb, nt * kb * 16384, kb,
+           batches, L.ptr(part), ldk, N * ldk, N, ctypes.cast(desc, ctypes.c_void_p), L.stream())
+    if batches == 1:
+        return part[0, :, :K]
+    return col_sum(part.view(batches, N * ldk)).view(N, ldk)[:, :K]

@@ -24,14 +24,24 @@ def _c(t):
     return t if t.stride(-1) == 1 and t.dtype == torch.float32 else t.float().contiguous()
 
 
+def _use_tc(M, N, K):
+    """Dense layers large enough for the tensor-core path; tiny ones (SFT0's 3x3 convs, the K=3 first
+    layer) stay on the FFMA kernels."""
+    return TENSOR_CORE_GEMMS and M >= 1024 and min(N, K) >= 16
+
+
+TENSOR_CORE_GEMMS = True     # split-bf16 tcgen05 GEMMs (fp32-accurate) for forward, dX and dW
+
+
 class LinearFn(Function):
     """y = act(x @ w.T + b);  x [M,K], w [N,K]."""
 
     @staticmethod
     def forward(ctx, x, w, b, act):
         x, w = _c(x), _c(w)
-        y = ops.linear(x, w, b, act=act)
-        ctx.act = act
+        tc = _use_tc(x.shape[0], w.shape[0], w.shape[1])
+        y = ops.linear_tc(x, w, b, act=act) if tc else ops.linear(x, w, b, act=act)
+        ctx.act, ctx.tc = act, tc
         ctx.save_for_backward(x, w, y if act != L.ACT_NONE else None)
         return y
 
@@ -41,8 +51,9 @@ class LinearFn(Function):
         dy = _c(dy)
         if ctx.act != L.ACT_NONE:
             dy = ops.act_bwd(dy, y, ctx.act)
-        dx = ops.linear(dy, w.t().contiguous()) if ctx.needs_input_grad[0] else None
-        dw = ops.linear_tn(dy, x) if ctx.needs_input_grad[1] else None
+        lin, lin_tn = (ops.linear_tc, ops.linear_tn_tc) if ctx.tc else (ops.linear, ops.linear_tn)
+        dx = lin(dy, w.t().contiguous()) if ctx.needs_input_grad[0] else None
+        dw = lin_tn(dy, x) if ctx.needs_input_grad[1] else None
         db = ops.col_sum(dy) if ctx.needs_input_grad[2] else None
         return dx, dw, db, None
 

@@ -862,3 +862,28 @@ def test_train_hand_fusion_and_optimizer_step():
     with torch.no_grad():
         after = m(cloud.to(DEV), [e.to(DEV) for e in emb], choose.to(DEV), cen.to(DEV))
     assert torch.isfinite(after).all() and not torch.equal(before, after)
+
+
+def test_train_tensor_core_gemms_are_fp32_accurate():
+    """Split-bf16 tcgen05 GEMMs used by the training path (forward / dX via pdf_gemm_bf16, dW via
+    pdf_rows_to_image_t + pdf_gemm_bf16_batched) against float64, ragged sizes."""
+    from pdfnet_b200 import ops
+    from pdfnet_b200 import _lib as L
+    gen = torch.Generator().manual_seed(11)
+    for M, K, N in ((5000, 131, 259), (1024, 64, 64), (70000, 128, 40)):
+        x = torch.randn((M, K), generator=gen)
+        w = torch.randn((N, K), generator=gen) / K ** 0.5
+        b = torch.randn((N,), generator=gen)
+        dy = torch.randn((M, N), generator=gen)
+        ref = x.double() @ w.double().t() + b.double()
+        y = ops.linear_tc(x.to(DEV), w.to(DEV), b.to(DEV)).cpu().double()
+        assert rel_err(y, ref) < 2e-5, (M, K, N, rel_err(y, ref))
+        yl = ops.linear_tc(x.to(DEV), w.to(DEV), b.to(DEV), act=L.ACT_LEAKY01).cpu().double()
+        assert rel_err(yl, torch.where(ref > 0, ref, 0.1 * ref)) < 2e-5
+        dw_ref = dy.double().t() @ x.double()
+        dw = ops.linear_tn_tc(dy.to(DEV), x.to(DEV)).cpu().double()
+        assert dw.shape == (N, K) and rel_err(dw, dw_ref) < 2e-5, (M, K, N, rel_err(dw, dw_ref))
+        # strided inputs (row pitch > columns), as autograd hands them over
+        xs = torch.zeros((M, K + 5)); xs[:, :K] = x
+        dws = ops.linear_tn_tc(dy.to(DEV), xs.to(DEV)[:, :K]).cpu().double()
+        assert rel_err(dws, dw_ref) < 2e-5
