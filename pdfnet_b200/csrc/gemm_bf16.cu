@@ -334,7 +334,7 @@ rows_to_image_t_kernel(const float* __restrict__ X, int64_t ld, int64_t M, int c
   const int kb = (int)((m0 - bt * Mc) / 64);
   uint8_t* base = img + (((size_t)bt * n_rt + rt) * (size_t)(nkb * parts)) * G_BLOCK;
   for (int e = threadIdx.x; e < 128 * 8; e += 256) {
-    const int c = e & 127, chunk = e >> 7;               // consecutive threads -> consecutive channels
+    const int chunk = e & 7, c = e >> 3;                 // consecutive threads fill one 128 B image row
     float f[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = s[chunk * 8 + i][c];

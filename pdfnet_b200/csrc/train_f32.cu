@@ -31,21 +31,34 @@ col_reduce_kernel(const float* __restrict__ A, int64_t lda, const float* __restr
   // statistics are accumulated about the channel's first row (shifted sums): the variance
   // sum d^2 - (sum d)^2 / M then has no catastrophic cancellation when |mean| >> std
   if (MODE == RED_STATS && ok && M > 0) mu = A[c];
-  // two-level accumulation keeps fp32 partial sums short (<= 64 terms) before going to double
+  // two-level accumulation keeps fp32 partial sums short (<= 64 terms) before going to double;
+  // four rows per iteration keep four independent loads in flight per thread
   double d0 = 0.0, d1 = 0.0;
   int n = 0;
-  for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < M; r += (int64_t)gridDim.y * 8) {
-    if (ok) {
-      const float a = A[r * lda + c];
-      if (MODE == RED_STATS) { const float d = a - mu; s0 += d; s1 = fmaf(d, d, s1); }
-      else if (MODE == RED_COLSUM) { s0 += a; }
-      else {
-        const float g = (!relu || Yp[r * ldy + c] > 0.f) ? a : 0.f;
-        s0 += g;
-        s1 = fmaf(g, (X[r * ldx + c] - mu) * rs, s1);
+  const int64_t stride = (int64_t)gridDim.y * 8;
+  for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < M; r += 4 * stride) {
+    float a[4], y[4], x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t ru = r + u * stride;
+      const bool in = ok && ru < M;
+      a[u] = in ? A[ru * lda + c] : (MODE == RED_STATS ? mu : 0.f);
+      if (MODE == RED_BN_BWD) {
+        y[u] = in ? Yp[ru * ldy + c] : 0.f;
+        x[u] = in ? X[ru * ldx + c] : 0.f;
       }
     }
-    if (++n == 64) { d0 += s0; d1 += s1; s0 = s1 = 0.f; n = 0; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (MODE == RED_STATS) { const float d = a[u] - mu; s0 += d; s1 = fmaf(d, d, s1); }
+      else if (MODE == RED_COLSUM) { s0 += a[u]; }
+      else {
+        const float g = (!relu || y[u] > 0.f) ? a[u] : 0.f;
+        s0 += g;
+        s1 = fmaf(g, (x[u] - mu) * rs, s1);
+      }
+    }
+    if (++n == 16) { d0 += s0; d1 += s1; s0 = s1 = 0.f; n = 0; }
   }
   d0 += s0; d1 += s1;
   __shared__ double sh[2][8][32];
@@ -94,47 +107,98 @@ struct EwArgs {
   int64_t M; int C; int flag;       // flag: relu (BN) / activation enum (ACT_BWD)
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(256) elementwise_kernel(EwArgs p) {
-  const int64_t total = p.M * (int64_t)p.C;
-  const float invM = 1.f / (float)p.M;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / p.C;
-    const int c = (int)(i - r * p.C);
-    if (MODE == EW_BN_FWD) {            // v0 mean, v1 rstd, v2 gamma, v3 beta
-      float y = fmaf((p.a[r * p.lda + c] - p.v0[c]) * p.v1[c], p.v2[c], p.v3[c]);
-      if (p.flag) y = fmaxf(y, 0.f);
-      p.o0[r * p.ldo0 + c] = y;
-    } else if (MODE == EW_BN_BWD) {     // v0 mean, v1 rstd, v2 gamma
-      const float dy = p.a[r * p.lda + c];
-      const float g = (!p.flag || p.b[r * p.ldb + c] > 0.f) ? dy : 0.f;
-      const float xhat = (p.c[r * p.ldc + c] - p.v0[c]) * p.v1[c];
-      const float dbeta = (float)p.sums[c], dgamma = (float)p.sums[p.C + c];
-      p.o0[r * p.ldo0 + c] = p.v2[c] * p.v1[c] * (g - dbeta * invM - xhat * dgamma * invM);
-    } else if (MODE == EW_ACT_BWD) {
-      const float y = p.b[r * p.ldb + c];
-      const float d = p.a[r * p.lda + c];
-      const float s = p.flag == PDF_ACT_RELU ? (y > 0.f ? 1.f : 0.f) : (p.flag == PDF_ACT_LEAKY01 ? (y > 0.f ? 1.f : 0.1f) : 1.f);
-      p.o0[r * p.ldo0 + c] = d * s;
-    } else if (MODE == EW_SFT_FWD) {    // fea * (scale + 1) + shift, rounded like the reference (mul, then add)
-      p.o0[r * p.ldo0 + c] = __fadd_rn(__fmul_rn(p.a[r * p.lda + c], __fadd_rn(p.b[r * p.ldb + c], 1.f)),
-                                       p.c[r * p.ldc + c]);
-    } else {                            // SFT_BWD: dfea = dout*(scale+1), dscale = dout*fea  (dshift = dout)
-      const float d = p.a[r * p.lda + c];
-      const float fea = p.b[r * p.ldb + c];
-      p.o1[r * p.ldo1 + c] = d * fea;
-      p.o0[r * p.ldo0 + c] = d * (p.c[r * p.ldc + c] + 1.f);
-    }
+template <int V>
+struct Vec {
+  float v[V];
+};
+template <int V>
+__device__ __forceinline__ Vec<V> vload(const float* p) {
+  Vec<V> r;
+  if (V == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) r.v[i] = p[i];
+  }
+  return r;
+}
+template <int V>
+__device__ __forceinline__ void vstore(float* p, const Vec<V>& r) {
+  if (V == 4) *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) p[i] = r.v[i];
   }
 }
 
+// V = 4: C and every row pitch are multiples of 4 and all pointers 16-byte aligned (checked on the host)
+template <int MODE, int V>
+__global__ void __launch_bounds__(256) elementwise_kernel(EwArgs p) {
+  const int cv = p.C / V;
+  const int64_t total = p.M * (int64_t)cv;
+  const float invM = 1.f / (float)p.M;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cv;
+    const int c = (int)(i - r * cv) * V;
+    Vec<V> o;
+    if (MODE == EW_BN_FWD) {            // v0 mean, v1 rstd, v2 gamma, v3 beta
+      const Vec<V> x = vload<V>(p.a + r * p.lda + c), mu = vload<V>(p.v0 + c), rs = vload<V>(p.v1 + c),
+                   ga = vload<V>(p.v2 + c), be = vload<V>(p.v3 + c);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float y = fmaf((x.v[e] - mu.v[e]) * rs.v[e], ga.v[e], be.v[e]);
+        o.v[e] = p.flag ? fmaxf(y, 0.f) : y;
+      }
+    } else if (MODE == EW_BN_BWD) {     // v0 mean, v1 rstd, v2 gamma
+      const Vec<V> dy = vload<V>(p.a + r * p.lda + c), y = vload<V>(p.b + r * p.ldb + c),
+                   x = vload<V>(p.c + r * p.ldc + c), mu = vload<V>(p.v0 + c), rs = vload<V>(p.v1 + c),
+                   ga = vload<V>(p.v2 + c);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float g = (!p.flag || y.v[e] > 0.f) ? dy.v[e] : 0.f;
+        const float xhat = (x.v[e] - mu.v[e]) * rs.v[e];
+        const float dbeta = (float)p.sums[c + e], dgamma = (float)p.sums[p.C + c + e];
+        o.v[e] = ga.v[e] * rs.v[e] * (g - dbeta * invM - xhat * dgamma * invM);
+      }
+    } else if (MODE == EW_ACT_BWD) {
+      const Vec<V> d = vload<V>(p.a + r * p.lda + c), y = vload<V>(p.b + r * p.ldb + c);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float s = p.flag == PDF_ACT_RELU ? (y.v[e] > 0.f ? 1.f : 0.f)
+                                               : (p.flag == PDF_ACT_LEAKY01 ? (y.v[e] > 0.f ? 1.f : 0.1f) : 1.f);
+        o.v[e] = d.v[e] * s;
+      }
+    } else if (MODE == EW_SFT_FWD) {    // fea * (scale + 1) + shift, rounded like the reference (mul, then add)
+      const Vec<V> f = vload<V>(p.a + r * p.lda + c), sc = vload<V>(p.b + r * p.ldb + c),
+                   sh = vload<V>(p.c + r * p.ldc + c);
+#pragma unroll
+      for (int e = 0; e < V; ++e) o.v[e] = __fadd_rn(__fmul_rn(f.v[e], __fadd_rn(sc.v[e], 1.f)), sh.v[e]);
+    } else {                            // SFT_BWD: dfea = dout*(scale+1), dscale = dout*fea  (dshift = dout)
+      const Vec<V> d = vload<V>(p.a + r * p.lda + c), f = vload<V>(p.b + r * p.ldb + c),
+                   sc = vload<V>(p.c + r * p.ldc + c);
+      Vec<V> o1;
+#pragma unroll
+      for (int e = 0; e < V; ++e) { o1.v[e] = d.v[e] * f.v[e]; o.v[e] = d.v[e] * (sc.v[e] + 1.f); }
+      vstore<V>(p.o1 + r * p.ldo1 + c, o1);
+    }
+    vstore<V>(p.o0 + r * p.ldo0 + c, o);
+  }
+}
+
+static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
 template <int MODE>
 static int launch_ew(const EwArgs& p, cudaStream_t s, const char* what) {
-  const int64_t total = p.M * (int64_t)p.C;
-  if (total == 0) return PDF_OK;
+  if (p.M * (int64_t)p.C == 0) return PDF_OK;
+  const bool vec = p.C % 4 == 0 && p.lda % 4 == 0 && p.ldb % 4 == 0 && p.ldc % 4 == 0 && p.ldo0 % 4 == 0 &&
+                   p.ldo1 % 4 == 0 && aligned16(p.a) && aligned16(p.b) && aligned16(p.c) && aligned16(p.o0) &&
+                   aligned16(p.o1) && aligned16(p.v0) && aligned16(p.v1) && aligned16(p.v2) && aligned16(p.v3);
+  const int64_t total = p.M * (int64_t)(vec ? p.C / 4 : p.C);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  elementwise_kernel<MODE><<<(unsigned)blocks, 256, 0, s>>>(p);
+  if (vec) elementwise_kernel<MODE, 4><<<(unsigned)blocks, 256, 0, s>>>(p);
+  else elementwise_kernel<MODE, 1><<<(unsigned)blocks, 256, 0, s>>>(p);
   return check_launch(what);
 }
 

@@ -37,11 +37,11 @@ class LinearFn(Function):
     """y = act(x @ w.T + b);  x [M,K], w [N,K]."""
 
     @staticmethod
-    def forward(ctx, x, w, b, act):
+    def forward(ctx, x, w, b, act, bias_before_bn=False):
         x, w = _c(x), _c(w)
         tc = _use_tc(x.shape[0], w.shape[0], w.shape[1])
         y = ops.linear_tc(x, w, b, act=act) if tc else ops.linear(x, w, b, act=act)
-        ctx.act, ctx.tc = act, tc
+        ctx.act, ctx.tc, ctx.bias_before_bn = act, tc, bias_before_bn
         ctx.save_for_backward(x, w, y if act != L.ACT_NONE else None)
         return y
 
@@ -54,8 +54,13 @@ class LinearFn(Function):
         lin, lin_tn = (ops.linear_tc, ops.linear_tn_tc) if ctx.tc else (ops.linear, ops.linear_tn)
         dx = lin(dy, w.t().contiguous()) if ctx.needs_input_grad[0] else None
         dw = lin_tn(dy, x) if ctx.needs_input_grad[1] else None
-        db = ops.col_sum(dy) if ctx.needs_input_grad[2] else None
-        return dx, dw, db, None
+        db = None
+        if ctx.needs_input_grad[2]:
+            # a bias in front of train-mode BatchNorm has an identically zero gradient (BatchNorm removes
+            # the mean); autograd would return the rounding residue of sum(dy), we return the exact zeros
+            db = torch.zeros((w.shape[0],), dtype=torch.float32, device=w.device) if ctx.bias_before_bn \
+                else ops.col_sum(dy)
+        return dx, dw, db, None, None
 
 
 class BatchNormActFn(Function):
@@ -159,7 +164,7 @@ def mlp_max_rows(net, rows, group):
     h = rows
     for i in (0, 3, 6):
         conv, bn = net[i], net[i + 1]
-        h = LinearFn.apply(h, _conv_w(conv), conv.bias, L.ACT_NONE)
+        h = LinearFn.apply(h, _conv_w(conv), conv.bias, L.ACT_NONE, True)
         momentum = bn.momentum if bn.momentum is not None else 0.1
         if bn.training:
             h = BatchNormActFn.apply(h, bn.weight, bn.bias, bn.running_mean, bn.running_var, momentum, bn.eps, True)
