@@ -18,59 +18,98 @@ namespace pdf {
 // block (32 channels x 8 row lanes); each thread walks rows with a grid stride.
 enum { RED_STATS = 0, RED_COLSUM = 1, RED_BN_BWD = 2 };
 
-template <int MODE>
+template <int V>
+struct Vec {
+  float v[V];
+};
+template <int V>
+__device__ __forceinline__ Vec<V> vload(const float* p) {
+  Vec<V> r;
+  if (V == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) r.v[i] = p[i];
+  }
+  return r;
+}
+template <int V>
+__device__ __forceinline__ void vstore(float* p, const Vec<V>& r) {
+  if (V == 4) *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) p[i] = r.v[i];
+  }
+}
+
+// 256 threads = LX channel-vectors (V channels each) x 256/LX row lanes; V = 4 needs C % 4 == 0,
+// row pitches % 4 == 0 and 16-byte aligned bases (checked on the host).
+template <int MODE, int V>
 __global__ void __launch_bounds__(256)
 col_reduce_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ Yp, int64_t ldy,
                   const float* __restrict__ X, int64_t ldx, const float* __restrict__ mean,
-                  const float* __restrict__ rstd, int relu, int64_t M, int C, double* __restrict__ sums) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
+                  const float* __restrict__ rstd, int relu, int64_t M, int C, int LX, double* __restrict__ sums) {
+  const int cx = threadIdx.x % LX, ry = threadIdx.x / LX, RY = 256 / LX;
+  const int c = (blockIdx.x * LX + cx) * V;
   const bool ok = c < C;
-  float s0 = 0.f, s1 = 0.f;
-  float mu = 0.f, rs = 0.f;
-  if (MODE == RED_BN_BWD && ok) { mu = mean[c]; rs = rstd[c]; }
-  // statistics are accumulated about the channel's first row (shifted sums): the variance
-  // sum d^2 - (sum d)^2 / M then has no catastrophic cancellation when |mean| >> std
-  if (MODE == RED_STATS && ok && M > 0) mu = A[c];
-  // two-level accumulation keeps fp32 partial sums short (<= 64 terms) before going to double;
-  // four rows per iteration keep four independent loads in flight per thread
-  double d0 = 0.0, d1 = 0.0;
-  int n = 0;
-  const int64_t stride = (int64_t)gridDim.y * 8;
-  for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < M; r += 4 * stride) {
-    float a[4], y[4], x[4];
+  float s0[V], s1[V], mu[V], rs[V];
+  double d0[V], d1[V];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t ru = r + u * stride;
-      const bool in = ok && ru < M;
-      a[u] = in ? A[ru * lda + c] : (MODE == RED_STATS ? mu : 0.f);
-      if (MODE == RED_BN_BWD) {
-        y[u] = in ? Yp[ru * ldy + c] : 0.f;
-        x[u] = in ? X[ru * ldx + c] : 0.f;
-      }
-    }
+  for (int e = 0; e < V; ++e) { s0[e] = s1[e] = 0.f; d0[e] = d1[e] = 0.0; mu[e] = rs[e] = 0.f; }
+  if (ok) {
+    // statistics are accumulated about the channel's first row (shifted sums): the variance
+    // sum d^2 - (sum d)^2 / M then has no catastrophic cancellation when |mean| >> std
+    if (MODE == RED_STATS && M > 0) { const Vec<V> t = vload<V>(A + c);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (MODE == RED_STATS) { const float d = a[u] - mu; s0 += d; s1 = fmaf(d, d, s1); }
-      else if (MODE == RED_COLSUM) { s0 += a[u]; }
-      else {
-        const float g = (!relu || y[u] > 0.f) ? a[u] : 0.f;
-        s0 += g;
-        s1 = fmaf(g, (x[u] - mu) * rs, s1);
-      }
+      for (int e = 0; e < V; ++e) mu[e] = t.v[e]; }
+    if (MODE == RED_BN_BWD) {
+      const Vec<V> t = vload<V>(mean + c), u = vload<V>(rstd + c);
+#pragma unroll
+      for (int e = 0; e < V; ++e) { mu[e] = t.v[e]; rs[e] = u.v[e]; }
     }
-    if (++n == 16) { d0 += s0; d1 += s1; s0 = s1 = 0.f; n = 0; }
   }
-  d0 += s0; d1 += s1;
-  __shared__ double sh[2][8][32];
-  sh[0][threadIdx.y][threadIdx.x] = d0;
-  sh[1][threadIdx.y][threadIdx.x] = d1;
-  __syncthreads();
-  if (threadIdx.y == 0 && ok) {
-    double t0 = 0.0, t1 = 0.0;
+  // two-level accumulation keeps fp32 partial sums short (<= 64 terms) before going to double
+  int n = 0;
+  const int64_t stride = (int64_t)gridDim.y * RY;
+  if (ok) {
+    for (int64_t r = (int64_t)blockIdx.y * RY + ry; r < M; r += stride) {
+      const Vec<V> a = vload<V>(A + r * lda + c);
+      if (MODE == RED_STATS) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { t0 += sh[0][i][threadIdx.x]; t1 += sh[1][i][threadIdx.x]; }
-    atomicAdd(&sums[c], t0);
-    if (MODE != RED_COLSUM) atomicAdd(&sums[C + c], t1);
+        for (int e = 0; e < V; ++e) { const float d = a.v[e] - mu[e]; s0[e] += d; s1[e] = fmaf(d, d, s1[e]); }
+      } else if (MODE == RED_COLSUM) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) s0[e] += a.v[e];
+      } else {
+        const Vec<V> y = vload<V>(Yp + r * ldy + c), x = vload<V>(X + r * ldx + c);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float g = (!relu || y.v[e] > 0.f) ? a.v[e] : 0.f;
+          s0[e] += g;
+          s1[e] = fmaf(g, (x.v[e] - mu[e]) * rs[e], s1[e]);
+        }
+      }
+      if (++n == 64) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) { d0[e] += s0[e]; d1[e] += s1[e]; s0[e] = s1[e] = 0.f; }
+        n = 0;
+      }
+    }
+  }
+  __shared__ double sh[2][256][V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) { sh[0][threadIdx.x][e] = d0[e] + s0[e]; sh[1][threadIdx.x][e] = d1[e] + s1[e]; }
+  __syncthreads();
+  if (ry == 0 && ok) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      if (c + e >= C) break;
+      double t0 = 0.0, t1 = 0.0;
+      for (int i = 0; i < RY; ++i) { t0 += sh[0][i * LX + cx][e]; t1 += sh[1][i * LX + cx][e]; }
+      atomicAdd(&sums[c + e], t0);
+      if (MODE != RED_COLSUM) atomicAdd(&sums[C + c + e], t1);
+    }
   }
 }
 
@@ -106,31 +145,6 @@ struct EwArgs {
   float* o1; int64_t ldo1;          // SFT_BWD: dscale
   int64_t M; int C; int flag;       // flag: relu (BN) / activation enum (ACT_BWD)
 };
-
-template <int V>
-struct Vec {
-  float v[V];
-};
-template <int V>
-__device__ __forceinline__ Vec<V> vload(const float* p) {
-  Vec<V> r;
-  if (V == 4) {
-    const float4 t = *reinterpret_cast<const float4*>(p);
-    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
-  } else {
-#pragma unroll
-    for (int i = 0; i < V; ++i) r.v[i] = p[i];
-  }
-  return r;
-}
-template <int V>
-__device__ __forceinline__ void vstore(float* p, const Vec<V>& r) {
-  if (V == 4) *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
-  else {
-#pragma unroll
-    for (int i = 0; i < V; ++i) p[i] = r.v[i];
-  }
-}
 
 // V = 4: C and every row pitch are multiples of 4 and all pointers 16-byte aligned (checked on the host)
 template <int MODE, int V>
@@ -337,12 +351,20 @@ static int launch_reduce(const float* A, int64_t lda, const float* Y, int64_t ld
   const int nsum = MODE == RED_COLSUM ? C : 2 * C;
   cudaMemsetAsync(sums, 0, sizeof(double) * nsum, s);
   if (M == 0) return PDF_OK;
-  int64_t gy = (M + 8 * 64 - 1) / (8 * 64);
-  const int gx = (C + 31) / 32;
-  const int64_t cap = (148 * 16 + gx - 1) / gx;
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool vec = C % 4 == 0 && lda % 4 == 0 && ldy % 4 == 0 && ldx % 4 == 0 && al(A) && al(Y) && al(X) &&
+                   al(mean) && al(rstd);
+  const int cv = vec ? C / 4 : C;                       // channel-vectors per row
+  int LX = 1;
+  while (LX < cv && LX < 32) LX <<= 1;
+  const int RY = 256 / LX;
+  const int gx = (cv + LX - 1) / LX;
+  int64_t gy = (M + (int64_t)RY * 16 - 1) / ((int64_t)RY * 16);
+  const int64_t cap = (148 * 8 + gx - 1) / gx;
   if (gy > cap) gy = cap;
-  dim3 grid((unsigned)gx, (unsigned)gy), block(32, 8);
-  col_reduce_kernel<MODE><<<grid, block, 0, s>>>(A, lda, Y, ldy, X, ldx, mean, rstd, relu, M, C, sums);
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  if (vec) col_reduce_kernel<MODE, 4><<<grid, 256, 0, s>>>(A, lda, Y, ldy, X, ldx, mean, rstd, relu, M, C, LX, sums);
+  else col_reduce_kernel<MODE, 1><<<grid, 256, 0, s>>>(A, lda, Y, ldy, X, ldx, mean, rstd, relu, M, C, LX, sums);
   return check_launch(what);
 }
 
