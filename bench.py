@@ -246,8 +246,15 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count()
-    ms_dev = timed_loop(lambda: hot_path(resident), args.steps, args.warmup)
+    ms_eager = timed_loop(lambda: hot_path(resident), args.steps, args.warmup)
     launches = (_lib.launch_count() - l0) // (args.steps + args.warmup)
+    ms_dev, graphed = ms_eager, False
+    if not args.no_graph:
+        # the same ~30 kernels replayed as one CUDA graph (no Python / ctypes launch cost in the step)
+        from pdfnet_b200.graph import CapturedStep
+        step = CapturedStep(lambda: hot_path(resident))
+        assert step.launches == launches, (step.launches, launches)
+        ms_dev, graphed = timed_loop(step.replay, args.steps, args.warmup), True
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the public API with HOST buffers ----
@@ -340,6 +347,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "frames_per_gpu": B, "resolution": R, "precision": args.precision,
                    "parallelism": "dp%d" % world, "l2": "256 MiB flush write between timed iterations; inputs 1.2 GB > L2",
+                   "launch": "one CUDA-graph replay per step" if graphed else "eager (one ctypes call per kernel)",
                    "randomness": "subset keys / permutations injected as inputs (reference uses np.random)"},
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e,
@@ -347,7 +355,7 @@ def run_ours(args):
                 "note": "all hot-path inputs (depth, masks, K, fp32 feature pyramid, centre features, keys) copied "
                         "from pinned host memory every step (chunked, copy stream overlapped with compute); fused "
                         "features + MANO verts/joints copied back"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "gpu_launches": int(launches), "eager_ms_per_step": ms_eager, "clocks": clocks, "roofline": roofline,
         "stages_ms": stage_report, "stages_tflops": stage_tflops,
         "cpu_baseline": cpu_baseline,
     }
@@ -599,6 +607,7 @@ def main():
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (cfg3: 128, cfg5: 64)")
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--cpu-sample-frames", type=int, default=4)
+    ap.add_argument("--no-graph", action="store_true", help="time the eager launch path instead of a CUDA-graph replay")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="H2D/compute overlap chunks in the e2e measurement")
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5"],
                     help="cfg3 = hot path at 128 frames/GPU (default, the driver's contract); cfg2 = SA microbench; "
