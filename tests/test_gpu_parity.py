@@ -887,3 +887,28 @@ def test_train_tensor_core_gemms_are_fp32_accurate():
         xs = torch.zeros((M, K + 5)); xs[:, :K] = x
         dws = ops.linear_tn_tc(dy.to(DEV), xs.to(DEV)[:, :K]).cpu().double()
         assert rel_err(dws, dw_ref) < 2e-5
+
+
+def test_captured_step_replays_the_hot_path_bit_exactly():
+    """pdfnet_b200.graph.CapturedStep: the eager step and its CUDA-graph replay give identical bits,
+    also after the input buffers are overwritten in place."""
+    from pdfnet_b200 import HandFusion
+    from pdfnet_b200.graph import CapturedStep
+    R, B = 64, 4
+    opt = _opt(default_resolution=R)
+    m = HandFusion(opt, "bf16")
+    m.pointnet_plus.load_state_dict(synth.pointnet_plus_state(seed=317), strict=False)
+    m.sft.load_state_dict(synth.fusion_sft_state(seed=317))
+    m = m.to(DEV).eval()
+    cloud = synth.clouds(2 * B, seed=51).view(B, 2, 1024, 3).to(DEV)
+    choose = synth.choose_indices(2 * B, R, seed=51).view(B, 2, 1024).to(DEV)
+    emb = [e.to(DEV) for e in synth.pyramid(B, R, seed=51)]
+    cen = torch.randn((B, 2, 1024), generator=torch.Generator().manual_seed(51)).to(DEV)
+    step = CapturedStep(lambda: m(cloud, emb, choose, cen))
+    assert step.launches > 10
+    eager = m(cloud, emb, choose, cen).clone()
+    assert torch.equal(step.replay(), eager)
+    cloud.copy_(synth.clouds(2 * B, seed=52).view(B, 2, 1024, 3))          # new inputs, same buffers
+    eager2 = m(cloud, emb, choose, cen).clone()
+    out2 = step.replay()
+    assert torch.equal(out2, eager2) and not torch.equal(eager2, eager)
