@@ -200,6 +200,10 @@ def run_ours(args):
     host = make_inputs(B, R, seed=317 + rank)
     pinned = {k: v.contiguous().pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
+    if args.pyramid_layout == "nhwc":                 # channels-last hand-off from the RGB neck
+        for k in ("l0", "l1", "l2"):
+            resident[k] = resident[k].contiguous(memory_format=torch.channels_last)
+            pinned[k] = host[k].contiguous(memory_format=torch.channels_last).pin_memory()
     state = load_states()
     tables = load_mano_tables()
     model = HandFusion(opt, precision=args.precision)
@@ -265,7 +269,7 @@ def run_ours(args):
     copy_stream = torch.cuda.Stream(device=dev)
     out_host = {}
 
-    staging = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in pinned.items()}
+    staging = {k: torch.empty_like(resident[k]) for k in pinned}
 
     def e2e_step():
         main = torch.cuda.current_stream()
@@ -347,6 +351,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "frames_per_gpu": B, "resolution": R, "precision": args.precision,
                    "parallelism": "dp%d" % world, "l2": "256 MiB flush write between timed iterations; inputs 1.2 GB > L2",
+                   "pyramid_layout": args.pyramid_layout,
                    "launch": "one CUDA-graph replay per step" if graphed else "eager (one ctypes call per kernel)",
                    "randomness": "subset keys / permutations injected as inputs (reference uses np.random)"},
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
@@ -607,6 +612,9 @@ def main():
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (cfg3: 128, cfg5: 64)")
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--cpu-sample-frames", type=int, default=4)
+    ap.add_argument("--pyramid-layout", default="nchw", choices=["nchw", "nhwc"],
+                    help="memory format of the RGB feature pyramid inputs (nchw = what the reference neck emits; "
+                         "nhwc = torch.channels_last hand-off, SURVEY 8f row f4)")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch path instead of a CUDA-graph replay")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="H2D/compute overlap chunks in the e2e measurement")
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5"],

@@ -96,6 +96,16 @@ int pdf_pyramid_gather(const float* xyz, const int64_t* choose, int64_t n_clouds
                        const float* l0, const float* l1, int C1, const float* l2, int C2,
                        const float* sft0_params, float* pts0, float* cond1, float* cond2, void* stream);
 
+/* Channels-last (NHWC) forms of the two gathers above (hand-off from the RGB neck,
+ * intaghand_encoder.py:711,715,741-744, in torch.channels_last memory format): feat / l0 / l1 / l2 are
+ * [F, H, W, C] so each point reads C contiguous floats.  Results are bit-identical to the NCHW forms. */
+int pdf_gather_nhwc(const float* feat, int64_t n_clouds, int clouds_per_frame, int C, int64_t HW,
+                    const int64_t* ind, int n, int64_t ind_stride, float* out, void* stream);
+int pdf_pyramid_gather_nhwc(const float* xyz, const int64_t* choose, int64_t n_clouds, int clouds_per_frame,
+                            int n_points, int n1, int n2, int R,
+                            const float* l0, const float* l1, int C1, const float* l2, int C2,
+                            const float* sft0_params, float* pts0, float* cond1, float* cond2, void* stream);
+
 /* Grouping gather: out[b,g,j,c] = pts[b, idx[b,g,j], c] - (c < 3 ? pts[b,g,c] : 0).
  * Replaces lib/utils/utils.py:153-158 and :181-186.  pts addressed with
  * (stride_cloud, stride_point, stride_ch) as in pdf_knn_ball; out fp32

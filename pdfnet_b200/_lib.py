@@ -21,6 +21,9 @@ SIGNATURES = {
     "pdf_gather_nchw": [_vp, _i64, _i32, _i32, _i64, _vp, _i32, _i64, _vp, _vp],
     "pdf_pyramid_gather": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp,
                            _vp, _vp],
+    "pdf_gather_nhwc": [_vp, _i64, _i32, _i32, _i64, _vp, _i32, _i64, _vp, _vp],
+    "pdf_pyramid_gather_nhwc": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp,
+                                _vp, _vp, _vp],
     "pdf_group_gather": [_vp, _i64, _i32, _i32, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp],
     "pdf_linear_f32": [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _vp],
     "pdf_sa_mlp_max_bf16": [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _i32,

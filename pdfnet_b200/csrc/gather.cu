@@ -191,6 +191,98 @@ pyramid_gather_kernel(const float* __restrict__ xyz, const int64_t* __restrict__
   }
 }
 
+// ---- channels-last (NHWC) variants: the RGB neck hands over [F, H, W, C] maps, so a
+// point's C features are one contiguous run and the gather reads exactly the algorithmic bytes. ----
+// rows [lo, hi) x C of one level; thread = one 16 B chunk, 8 independent loads in flight.
+__device__ __forceinline__ void gather_rows_nhwc(const float* __restrict__ src, int C, int R, int Rl, int div,
+                                                 const int64_t* __restrict__ ch, float* __restrict__ out,
+                                                 int lo, int hi) {
+  if ((C & 3) == 0) {
+    const int cq = C >> 2;
+    constexpr int U = 8;
+    const int e_lo = lo * cq, e_hi = hi * cq;
+    for (int e0 = e_lo + threadIdx.x; e0 < e_hi; e0 += blockDim.x * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * blockDim.x;
+        if (e < e_hi) {
+          const int i = e / cq, q = e - i * cq;
+          const int pix = (int)ch[i];
+          const int64_t p = (int64_t)(pix / R / div) * Rl + (pix % R) / div;
+          v[u] = __ldg(reinterpret_cast<const float4*>(src + p * C) + q);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * blockDim.x;
+        if (e < e_hi) reinterpret_cast<float4*>(out)[e] = v[u];
+      }
+    }
+  } else {
+    for (int e = lo * C + threadIdx.x; e < hi * C; e += blockDim.x) {
+      const int i = e / C, c = e - i * C;
+      const int pix = (int)ch[i];
+      const int64_t p = (int64_t)(pix / R / div) * Rl + (pix % R) / div;
+      out[e] = __ldg(src + p * C + c);
+    }
+  }
+}
+
+constexpr int PG_NHWC_PARTS = 4;                               // CTAs per cloud and level
+
+__global__ void __launch_bounds__(256)
+pyramid_gather_nhwc_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ choose, int clouds_per_frame,
+                           int n_points, int n1, int n2, int R, const float* __restrict__ l0,
+                           const float* __restrict__ l1, int C1, const float* __restrict__ l2, int C2,
+                           const float* __restrict__ sft0, float* __restrict__ pts0, float* __restrict__ cond1,
+                           float* __restrict__ cond2) {
+  __shared__ float P[48];
+  const int64_t b = blockIdx.x;
+  const int64_t f = b / clouds_per_frame;
+  const int64_t* ch = choose + b * n_points;
+  const int R2 = R / 2, R4 = R / 4;
+  const int y = blockIdx.y;
+  if (y == 0) {
+    if (threadIdx.x < 48) P[threadIdx.x] = sft0[threadIdx.x];
+    __syncthreads();
+    const float* base = l0 + f * 3 * (int64_t)R * R;
+    for (int i = threadIdx.x; i < n_points; i += blockDim.x) {
+      const int64_t pix = ch[i];
+      float e[3], p[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        e[c] = __ldg(base + pix * 3 + c);
+        p[c] = xyz[(b * n_points + i) * 3 + c];
+      }
+      sft0_apply(P, e, p);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) pts0[(b * n_points + i) * 3 + c] = p[c];
+    }
+  } else if (y <= PG_NHWC_PARTS) {
+    const int part = y - 1, per = (n1 + PG_NHWC_PARTS - 1) / PG_NHWC_PARTS;
+    gather_rows_nhwc(l1 + f * C1 * (int64_t)R2 * R2, C1, R, R2, 2, ch, cond1 + b * n1 * C1, min(n1, part * per),
+                     min(n1, (part + 1) * per));
+  } else {
+    const int part = y - 1 - PG_NHWC_PARTS, per = (n2 + PG_NHWC_PARTS - 1) / PG_NHWC_PARTS;
+    gather_rows_nhwc(l2 + f * C2 * (int64_t)R4 * R4, C2, R, R4, 4, ch, cond2 + b * n2 * C2, min(n2, part * per),
+                     min(n2, (part + 1) * per));
+  }
+}
+
+// out[b,i,:] = feat[b / clouds_per_frame, ind[b,i], :]   (feat [F, HW, C] channels-last)
+__global__ void gather_nhwc_kernel(const float* __restrict__ feat, int clouds_per_frame, int C, int64_t HW,
+                                   const int64_t* __restrict__ ind, int n, int64_t ind_stride,
+                                   float* __restrict__ out, int64_t total) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const int64_t bi = e / C;
+    const int64_t b = bi / n;
+    const int i = (int)(bi - b * n);
+    out[e] = __ldg(feat + ((b / clouds_per_frame) * HW + ind[b * ind_stride + i]) * C + c);
+  }
+}
+
 // out[b,g,j,c] = pts[b,idx[b,g,j],c] - (c<3 ? pts[b,g,c] : 0).  One warp per output
 // row; lanes stride over channels (coalesced for point-major sources).
 __global__ void __launch_bounds__(256)
@@ -328,6 +420,36 @@ extern "C" int pdf_pyramid_gather(const float* xyz, const int64_t* choose, int64
       xyz, choose, clouds_per_frame, n_points, n1, n2, R, l0, l1, C1, l2, C2, sft0_params, pts0, cond1, cond2,
       groups1, groups2, windowed);
   return pdf::check_launch("pdf_pyramid_gather");
+}
+
+extern "C" int pdf_gather_nhwc(const float* feat, int64_t n_clouds, int clouds_per_frame, int C, int64_t HW,
+                               const int64_t* ind, int n, int64_t ind_stride, float* out, void* stream) {
+  if (n_clouds == 0 || n == 0) return PDF_OK;
+  PDF_REQUIRE(feat && ind && out, PDF_ERR_BAD_ARG, "pdf_gather_nhwc: null pointer");
+  PDF_REQUIRE(n_clouds >= 0 && clouds_per_frame > 0 && C > 0 && HW > 0 && n >= 0, PDF_ERR_BAD_ARG,
+              "pdf_gather_nhwc: bad size");
+  const int64_t total = n_clouds * n * C;
+  pdf::gather_nhwc_kernel<<<pdf::grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      feat, clouds_per_frame, C, HW, ind, n, ind_stride, out, total);
+  return pdf::check_launch("pdf_gather_nhwc");
+}
+
+extern "C" int pdf_pyramid_gather_nhwc(const float* xyz, const int64_t* choose, int64_t n_clouds, int clouds_per_frame,
+                                       int n_points, int n1, int n2, int R, const float* l0, const float* l1, int C1,
+                                       const float* l2, int C2, const float* sft0_params, float* pts0, float* cond1,
+                                       float* cond2, void* stream) {
+  PDF_REQUIRE(xyz && choose && l0 && l1 && l2 && sft0_params && pts0 && cond1 && cond2, PDF_ERR_BAD_ARG,
+              "pdf_pyramid_gather_nhwc: null pointer");
+  PDF_REQUIRE(n_clouds >= 0 && clouds_per_frame > 0 && n_points > 0 && n1 >= 0 && n2 >= 0 && n1 <= n_points &&
+                  n2 <= n_points && R >= 4 && C1 > 0 && C2 > 0,
+              PDF_ERR_BAD_ARG, "pdf_pyramid_gather_nhwc: bad size");
+  if (n_clouds == 0) return PDF_OK;
+  PDF_REQUIRE(n_clouds < (1ll << 31) && (int64_t)R * R < (1ll << 31), PDF_ERR_UNSUPPORTED,
+              "pdf_pyramid_gather_nhwc: too large");
+  pdf::pyramid_gather_nhwc_kernel<<<dim3((unsigned)n_clouds, 1 + 2 * pdf::PG_NHWC_PARTS), 256, 0,
+                                    (cudaStream_t)stream>>>(xyz, choose, clouds_per_frame, n_points, n1, n2, R, l0, l1,
+                                                            C1, l2, C2, sft0_params, pts0, cond1, cond2);
+  return pdf::check_launch("pdf_pyramid_gather_nhwc");
 }
 
 extern "C" int pdf_group_gather(const float* pts, int64_t n_clouds, int n_centroids, int k, int C,

@@ -45,10 +45,19 @@ def fps(xyz, n_sample, start_idx):
     return out
 
 
+def _is_nhwc(t):
+    """[F,C,H,W] tensor stored channels-last (and not also plain-contiguous, as C == 1 or H*W == 1 would be)."""
+    return (t.dim() == 4 and t.dtype == torch.float32 and not t.is_contiguous()
+            and t.is_contiguous(memory_format=torch.channels_last))
+
+
 def gather_nchw(feat, ind, clouds_per_frame=1):
-    """out[b,i,:] = feat[b // clouds_per_frame, :, ind[b,i]] ; feat [F,C,H,W] fp32, ind [B,n] int64."""
+    """out[b,i,:] = feat[b // clouds_per_frame, :, ind[b,i]] ; feat [F,C,H,W] fp32, ind [B,n] int64.
+    A channels-last ``feat`` is gathered in place (pdf_gather_nhwc), no layout conversion."""
     L.require_cuda(feat, ind)
-    feat = L.f32c(feat)
+    nhwc = _is_nhwc(feat)
+    if not nhwc:
+        feat = L.f32c(feat)
     ind = ind.long()
     if ind.stride(-1) != 1:
         ind = ind.contiguous()
@@ -56,8 +65,8 @@ def gather_nchw(feat, ind, clouds_per_frame=1):
     HW = feat[0, 0].numel()
     B, n = ind.shape
     out = torch.empty((B, n, C), dtype=torch.float32, device=feat.device)
-    L.call("pdf_gather_nchw", L.ptr(feat), B, clouds_per_frame, C, HW, L.ptr(ind), n, ind.stride(0), L.ptr(out),
-           L.stream())
+    L.call("pdf_gather_nhwc" if nhwc else "pdf_gather_nchw", L.ptr(feat), B, clouds_per_frame, C, HW, L.ptr(ind), n,
+           ind.stride(0), L.ptr(out), L.stream())
     return out
 
 
@@ -67,15 +76,17 @@ def pyramid_gather(xyz, choose, emb, sft0_params, n1, n2, R, clouds_per_frame=1)
     L.require_cuda(xyz, choose, emb[0], emb[1], emb[2], sft0_params)
     xyz = L.f32c(xyz)
     choose = choose.long().contiguous()
-    l0, l1, l2 = (L.f32c(e) for e in emb)
+    nhwc = all(_is_nhwc(e) for e in emb)                 # channels-last hand-off from the RGB neck (f4)
+    l0, l1, l2 = emb if nhwc else (L.f32c(e) for e in emb)
     B, N, _ = xyz.shape
     C1, C2 = l1.shape[1], l2.shape[1]
     dev = xyz.device
     pts0 = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
     cond1 = torch.empty((B, n1, C1), dtype=torch.float32, device=dev)
     cond2 = torch.empty((B, n2, C2), dtype=torch.float32, device=dev)
-    L.call("pdf_pyramid_gather", L.ptr(xyz), L.ptr(choose), B, clouds_per_frame, N, n1, n2, R, L.ptr(l0), L.ptr(l1),
-           C1, L.ptr(l2), C2, L.ptr(sft0_params), L.ptr(pts0), L.ptr(cond1), L.ptr(cond2), L.stream())
+    L.call("pdf_pyramid_gather_nhwc" if nhwc else "pdf_pyramid_gather", L.ptr(xyz), L.ptr(choose), B, clouds_per_frame,
+           N, n1, n2, R, L.ptr(l0), L.ptr(l1), C1, L.ptr(l2), C2, L.ptr(sft0_params), L.ptr(pts0), L.ptr(cond1),
+           L.ptr(cond2), L.stream())
     return pts0, cond1, cond2
 
 

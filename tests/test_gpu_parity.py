@@ -912,3 +912,27 @@ def test_captured_step_replays_the_hot_path_bit_exactly():
     eager2 = m(cloud, emb, choose, cen).clone()
     out2 = step.replay()
     assert torch.equal(out2, eager2) and not torch.equal(eager2, eager)
+
+
+def test_channels_last_pyramid_is_bit_identical():
+    """pyramid maps handed over in torch.channels_last are gathered in place
+    (pdf_pyramid_gather_nhwc / pdf_gather_nhwc); every result equals the NCHW path bit for bit."""
+    from pdfnet_b200 import HandFusion, ops
+    R, B = 64, 3
+    opt = _opt(default_resolution=R)
+    emb = [e.to(DEV) for e in synth.pyramid(B, R, seed=61)]
+    emb_cl = [e.contiguous(memory_format=torch.channels_last) for e in emb]
+    assert all(ops._is_nhwc(e) for e in emb_cl) and not any(ops._is_nhwc(e) for e in emb)
+    ind = synth.choose_indices(B, R // 2, n_points=100, seed=61).to(DEV)
+    assert torch.equal(ops.gather_nchw(emb[1], ind), ops.gather_nchw(emb_cl[1], ind))
+    ind2 = synth.choose_indices(2 * B, R // 4, n_points=7, seed=62).to(DEV)       # two clouds per frame, ragged n
+    assert torch.equal(ops.gather_nchw(emb[2], ind2, 2), ops.gather_nchw(emb_cl[2], ind2, 2))
+    for prec in ("fp32", "bf16"):
+        m = HandFusion(opt, prec)
+        m.pointnet_plus.load_state_dict(synth.pointnet_plus_state(seed=317), strict=False)
+        m.sft.load_state_dict(synth.fusion_sft_state(seed=317))
+        m = m.to(DEV).eval()
+        cloud = synth.clouds(2 * B, seed=61).view(B, 2, 1024, 3).to(DEV)
+        choose = synth.choose_indices(2 * B, R, seed=61).view(B, 2, 1024).to(DEV)
+        cen = torch.randn((B, 2, 1024), generator=torch.Generator().manual_seed(61)).to(DEV)
+        assert torch.equal(m(cloud, emb, choose, cen), m(cloud, emb_cl, choose, cen)), prec
