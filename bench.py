@@ -516,7 +516,7 @@ def run_cfg5(args):
     dev = torch.device("cuda", local)
     from pdfnet_b200 import HandFusion, _lib, training
     R, B = args.res, args.frames
-    model = HandFusion(make_opt(R), precision="fp32")
+    model = HandFusion(make_opt(R), precision=args.precision)
     st = load_states()
     sd = {"pointnet_plus." + k: v for k, v in st["pointnet"].items()}
     sd.update({"sft." + k: v for k, v in st["sft"].items()})
@@ -584,17 +584,21 @@ def run_cfg5(args):
         print(json.dumps({
             "metric": "train_frames_per_sec_hot_path", "value": world * B / (ms_dev * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg5_workload(args), "frames_per_gpu": B, "resolution": R, "precision": "fp32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (split operands, fp32-accurate)", "data": "synthetic",
+            "config": {"workload": cfg5_workload(args), "frames_per_gpu": B, "resolution": R,
+                       "precision": args.precision + (" GEMM operands (fp32 activations, fp32 accumulate)"
+                                                      if args.precision == "bf16" else " (split-bf16 tensor-core GEMMs)"),
                        "parallelism": "dp%d" % world, "l2": "256 MiB flush write between timed iterations",
                        "optimizer": "Adam (torch fused), lr 1e-4; loss = MSE(fused, target)"},
             "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pinned.values()),
                     "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"kernel": "whole step (FFMA fp32 GEMMs)", "bound": "tensor", "achieved": ach,
-                         "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-                         "traffic": None, "pipe": "FFMA fp32 (training GEMMs are not on tensor cores yet)"},
+            "roofline": {"kernel": "whole step (forward + dX + dW GEMM flops over the step time)", "bound": "tensor",
+                         "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": ach / peaks["bf16_tflops"], "traffic": None,
+                         "pipe": "tcgen05 bf16; the step is dominated by HBM-bound staging / BatchNorm passes"},
             "allreduce_bytes_per_step": comm_bytes[0], "final_loss": loss, "peak_mem_gb": peak_mem / 2 ** 30,
             "cpu_baseline": None}))
     if world > 1:
@@ -608,7 +612,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=None, choices=["bf16", "fp32"],
+                    help="cfg3 default bf16; cfg5 default fp32 = split-bf16 (3-pass, fp32-accurate) tensor-core GEMMs, "
+                         "bf16 = plain bf16 operands for forward / dW")
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (cfg3: 128, cfg5: 64)")
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--cpu-sample-frames", type=int, default=4)
@@ -624,6 +630,8 @@ def main():
     args = ap.parse_args()
     if args.frames is None:
         args.frames = 64 if args.workload == "cfg5" else 128
+    if args.precision is None:
+        args.precision = "fp32" if args.workload == "cfg5" else "bf16"
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.workload == "cfg5":
         (run_cfg5_reference if args.impl == "reference" else run_cfg5)(args)

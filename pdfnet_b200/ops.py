@@ -478,17 +478,18 @@ def _tile_desc(n):
     return [(128 * i, min(128, n - 128 * i), 0) for i in range((n + 127) // 128)]
 
 
-def linear_tc(x, w, bias=None, act=L.ACT_NONE):
-    """act(x @ w.T + bias) on the tcgen05 GEMM with split-bf16 operands (three bf16 products per
-    fp32 product: fp32-accurate, ~2^-16 relative).  x [M,K] fp32 rows, w [N,K] fp32 (device).
+def linear_tc(x, w, bias=None, act=L.ACT_NONE, split=True):
+    """act(x @ w.T + bias) on the tcgen05 GEMM.  split=True: split-bf16 operands (three bf16 products
+    per fp32 product: fp32-accurate, ~2^-16 relative); split=False: plain bf16 operands, fp32
+    accumulate.  x [M,K] fp32 rows, w [N,K] fp32 (device).
     Returns a [M,N] view of a buffer whose row pitch is padded to a multiple of 4."""
     L.require_cuda(x, w, bias)
     M, K = _rows(x).shape
     N = _rows(w).shape[0]
-    kb = 3 * ((K + 63) // 64)
+    kb = (3 if split else 1) * ((K + 63) // 64)
     nt = (N + 127) // 128
-    x_img = rows_to_image(x, 0, K, split=1)
-    w_img = rows_to_image(w, 0, K, split=2)
+    x_img = rows_to_image(x, 0, K, split=1 if split else 0)
+    w_img = rows_to_image(w, 0, K, split=2 if split else 0)
     b = torch.zeros((nt * 128,), dtype=torch.float32, device=x.device)
     if bias is not None:
         b[:N] = bias
@@ -498,9 +499,10 @@ def linear_tc(x, w, bias=None, act=L.ACT_NONE):
     return out[:, :N]
 
 
-def linear_tn_tc(a, b):
+def linear_tn_tc(a, b, split=True):
     """a [M,N], b [M,K] -> a^T b [N,K] on the tcgen05 GEMM: split-K over batches of rows
-    (pdf_rows_to_image_t + pdf_gemm_bf16_batched, split-bf16 operands), partials summed in fp64."""
+    (pdf_rows_to_image_t + pdf_gemm_bf16_batched; split-bf16 or plain bf16 operands), partials
+    summed in fp64."""
     L.require_cuda(a, b)
     M, N = _rows(a).shape
     K = _rows(b).shape[1]
@@ -508,12 +510,12 @@ def linear_tn_tc(a, b):
     want = max(1, (2 * 148 + mt * nt - 1) // (mt * nt))                 # batches: about two waves of work items
     Mc = max(512, ((M + want - 1) // want + 63) // 64 * 64)
     batches = (M + Mc - 1) // Mc
-    kb = 3 * (Mc // 64)
+    kb = (3 if split else 1) * (Mc // 64)
     dev = a.device
     a_img = torch.empty((batches * mt * kb * 16384,), dtype=torch.uint8, device=dev)
     b_img = torch.empty((batches * nt * kb * 16384,), dtype=torch.uint8, device=dev)
-    L.call("pdf_rows_to_image_t", L.ptr(a), a.stride(0), M, 0, N, L.ptr(a_img), Mc, 1, L.stream())
-    L.call("pdf_rows_to_image_t", L.ptr(b), b.stride(0), M, 0, K, L.ptr(b_img), Mc, 2, L.stream())
+    L.call("pdf_rows_to_image_t", L.ptr(a), a.stride(0), M, 0, N, L.ptr(a_img), Mc, 1 if split else 0, L.stream())
+    L.call("pdf_rows_to_image_t", L.ptr(b), b.stride(0), M, 0, K, L.ptr(b_img), Mc, 2 if split else 0, L.stream())
     ldk = _pad4(K)
     part = torch.zeros((batches, N, ldk), dtype=torch.float32, device=dev)
     flat = [int(v) for t in _tile_desc(K) for v in t]

@@ -30,18 +30,24 @@ def _use_tc(M, N, K):
     return TENSOR_CORE_GEMMS and M >= 1024 and min(N, K) >= 16
 
 
-TENSOR_CORE_GEMMS = True     # split-bf16 tcgen05 GEMMs (fp32-accurate) for forward, dX and dW
+TENSOR_CORE_GEMMS = True     # tcgen05 GEMMs for forward, dX and dW (False: FFMA kernels everywhere)
+
+# GEMM operand precision per mode: "fp32" -> split-bf16 (fp32-accurate), "bf16" -> plain bf16 operands
+# with fp32 accumulation (BASELINE cfg5 "training step bf16").  The layers that decide neighbour
+# indices (SFT0 and the xyz channels through SFT1) are small / FFMA or split in both modes.
+FP32, BF16 = "fp32", "bf16"
 
 
 class LinearFn(Function):
     """y = act(x @ w.T + b);  x [M,K], w [N,K]."""
 
     @staticmethod
-    def forward(ctx, x, w, b, act, bias_before_bn=False):
+    def forward(ctx, x, w, b, act, bias_before_bn=False, precision=FP32):
         x, w = _c(x), _c(w)
         tc = _use_tc(x.shape[0], w.shape[0], w.shape[1])
-        y = ops.linear_tc(x, w, b, act=act) if tc else ops.linear(x, w, b, act=act)
-        ctx.act, ctx.tc, ctx.bias_before_bn = act, tc, bias_before_bn
+        split = precision != BF16
+        y = ops.linear_tc(x, w, b, act=act, split=split) if tc else ops.linear(x, w, b, act=act)
+        ctx.act, ctx.tc, ctx.bias_before_bn, ctx.split = act, tc, bias_before_bn, split
         ctx.save_for_backward(x, w, y if act != L.ACT_NONE else None)
         return y
 
@@ -51,16 +57,21 @@ class LinearFn(Function):
         dy = _c(dy)
         if ctx.act != L.ACT_NONE:
             dy = ops.act_bwd(dy, y, ctx.act)
-        lin, lin_tn = (ops.linear_tc, ops.linear_tn_tc) if ctx.tc else (ops.linear, ops.linear_tn)
-        dx = lin(dy, w.t().contiguous()) if ctx.needs_input_grad[0] else None
-        dw = lin_tn(dy, x) if ctx.needs_input_grad[1] else None
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            wt = w.t().contiguous()
+            # the data gradient is the chain that carries every upstream gradient (and ends in the xyz
+            # coordinates, where centroid-relative differences cancel): always fp32-accurate
+            dx = ops.linear_tc(dy, wt, split=True) if ctx.tc else ops.linear(dy, wt)
+        if ctx.needs_input_grad[1]:
+            dw = ops.linear_tn_tc(dy, x, split=ctx.split) if ctx.tc else ops.linear_tn(dy, x)
         db = None
         if ctx.needs_input_grad[2]:
             # a bias in front of train-mode BatchNorm has an identically zero gradient (BatchNorm removes
             # the mean); autograd would return the rounding residue of sum(dy), we return the exact zeros
             db = torch.zeros((w.shape[0],), dtype=torch.float32, device=w.device) if ctx.bias_before_bn \
                 else ops.col_sum(dy)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 class BatchNormActFn(Function):
@@ -150,21 +161,20 @@ def _conv_w(conv):
     return conv.weight.view(conv.out_channels, conv.in_channels)
 
 
-def sft_rows(sft, fea_rows, cond_rows):
+def sft_rows(sft, fea_rows, cond_rows, precision=FP32):
     """SFTLayer on rows: fea [M,Cf], cond [M,Cc] -> [M,Cf] (differentiable)."""
-    hs = LinearFn.apply(cond_rows, _conv_w(sft.SFT_scale_conv0), sft.SFT_scale_conv0.bias, L.ACT_LEAKY01)
-    scale = LinearFn.apply(hs, _conv_w(sft.SFT_scale_conv1), sft.SFT_scale_conv1.bias, L.ACT_NONE)
-    hh = LinearFn.apply(cond_rows, _conv_w(sft.SFT_shift_conv0), sft.SFT_shift_conv0.bias, L.ACT_LEAKY01)
-    shift = LinearFn.apply(hh, _conv_w(sft.SFT_shift_conv1), sft.SFT_shift_conv1.bias, L.ACT_NONE)
+    lin = lambda x, conv, act: LinearFn.apply(x, _conv_w(conv), conv.bias, act, False, precision)
+    scale = lin(lin(cond_rows, sft.SFT_scale_conv0, L.ACT_LEAKY01), sft.SFT_scale_conv1, L.ACT_NONE)
+    shift = lin(lin(cond_rows, sft.SFT_shift_conv0, L.ACT_LEAKY01), sft.SFT_shift_conv1, L.ACT_NONE)
     return SFTModulateFn.apply(fea_rows, scale, shift)
 
 
-def mlp_max_rows(net, rows, group):
+def mlp_max_rows(net, rows, group, precision=FP32):
     """(Conv1x1 -> BatchNorm2d(train) -> ReLU) x3 -> max over ``group`` consecutive rows."""
     h = rows
     for i in (0, 3, 6):
         conv, bn = net[i], net[i + 1]
-        h = LinearFn.apply(h, _conv_w(conv), conv.bias, L.ACT_NONE, True)
+        h = LinearFn.apply(h, _conv_w(conv), conv.bias, L.ACT_NONE, True, precision)
         momentum = bn.momentum if bn.momentum is not None else 0.1
         if bn.training:
             h = BatchNormActFn.apply(h, bn.weight, bn.bias, bn.running_mean, bn.running_var, momentum, bn.eps, True)
@@ -187,6 +197,7 @@ def pointnet_plus_train(net, points, emb, choose):
     -> [B,1,1024] with an autograd graph through every stage."""
     L.require_cuda(points, choose, *emb)
     opt = net.opt
+    prec = BF16 if getattr(net, "precision", FP32) == BF16 else FP32
     N1, N2, K = net.sample_num_level1, net.sample_num_level2, net.knn_K
     B, N, _ = points.shape
     choose = choose.long()
@@ -198,17 +209,17 @@ def pointnet_plus_train(net, points, emb, choose):
     c2, c4 = pyramid_indices(choose, opt.default_resolution)
     e1 = GatherNCHWFn.apply(_c(emb[1]), c2[:, :N1].contiguous())
     e2 = GatherNCHWFn.apply(_c(emb[2]), c4[:, :N2].contiguous())
-    f1 = mlp_max_rows(net.netR_1, g1.view(B * N1 * K, -1), K)                           # [B*N1,128]
+    f1 = mlp_max_rows(net.netR_1, g1.view(B * N1 * K, -1), K, prec)                     # [B*N1,128]
     x1 = torch.cat((pts0[:, :N1].reshape(B * N1, 3), f1), 1)                            # cat((y, x), 1) (:134)
-    x1 = sft_rows(net.sft1, x1, e1.reshape(B * N1, -1))
+    x1 = sft_rows(net.sft1, x1, e1.reshape(B * N1, -1))          # fp32-accurate: its xyz channels pick level-2 neighbours
     C1 = x1.shape[1]
     x1b = x1.view(B, N1, C1)
     idx2 = ops.knn_ball(x1b.detach(), N2, K, net.ball_radius2)
     g2 = GroupGatherFn.apply(x1b, idx2)                                                 # [B,N2,K,131]
-    f2 = mlp_max_rows(net.netR_2, g2.view(B * N2 * K, C1), K)                           # [B*N2,256]
+    f2 = mlp_max_rows(net.netR_2, g2.view(B * N2 * K, C1), K, prec)                     # [B*N2,256]
     x2 = torch.cat((x1b[:, :N2, :3].reshape(B * N2, 3), f2), 1)
-    x2 = sft_rows(net.sft2, x2, e2.reshape(B * N2, -1))
-    out = mlp_max_rows(net.netR_3, x2, N2)                                              # [B,1024]
+    x2 = sft_rows(net.sft2, x2, e2.reshape(B * N2, -1), prec)
+    out = mlp_max_rows(net.netR_3, x2, N2, prec)                                        # [B,1024]
     return out.view(B, 1, -1)
 
 
@@ -219,7 +230,8 @@ def hand_fusion_train(fusion, cloud, point_wise_emb, choose, center_features):
     left = pointnet_plus_train(fusion.pointnet_plus, cloud[:, 0], point_wise_emb, choose[:, 0])
     right = pointnet_plus_train(fusion.pointnet_plus, cloud[:, 1], point_wise_emb, choose[:, 1])
     feat = torch.cat((left, right), 1)                                                  # [B,2,1024]
-    fused = sft_rows(fusion.sft, feat.reshape(B * 2, -1), _c(center_features).reshape(B * 2, -1))
+    prec = BF16 if fusion.pointnet_plus.precision == BF16 else FP32
+    fused = sft_rows(fusion.sft, feat.reshape(B * 2, -1), _c(center_features).reshape(B * 2, -1), prec)
     return fused.view(B, 2, -1)
 
 
