@@ -324,6 +324,53 @@ def golden_train_step(ref):
     save("train_step", **rec)
 
 
+def export_gcn_assets(ref_dec):
+    """Graph assets of the GCN decoder (lib/models/networks/gcn_core/*.pkl) as plain arrays: the three
+    coarsened Laplacians per hand (dense, as GCN_ResBlock registers them, gcn.py:83-87), the vertex
+    permutations, the dense colour table and the 252 -> 778 upsampling matrix.  Data, not code."""
+    m, _ = ref_dec
+    rec = {"dense_coor": m.dense_coor.numpy(), "upsample": m.unsample_layer.weight.detach().numpy()}
+    for side in ("left", "right"):
+        rec["graph_perm_" + side] = np.asarray(m.converter[side].graph_perm, dtype=np.int64)
+        rec["graph_perm_reverse_" + side] = np.asarray(m.converter[side].graph_perm_reverse, dtype=np.int64)
+        for i in range(3):
+            blk = getattr(m.dual_gcn.layers[i], "graph_" + side).GCN_blocks[0]
+            rec["L_%s_%d" % (side, i)] = blk.graph_L.numpy()
+    save("gcn_assets", **rec)
+    return rec
+
+
+def golden_gcn_decoder(ref_dec):
+    """decoder.forward (intaghand_decoder.py:180-242) of the UNMODIFIED reference, eval mode, synthetic
+    weights from pdfnet_b200.synth.decoder_state loaded into the reference module (strict for every
+    parameter forward uses), driven the way HandNET_GCN.forward drives it: global features =
+    fuse_feat[:, 0] / fuse_feat[:, 1] (intaghand_encoder.py:873-874), fmaps = zero placeholders (shape-checked, never read)."""
+    m, dec = ref_dec
+    state = synth.decoder_state(seed=317, upsample_weight=m.unsample_layer.weight.detach())
+    res = m.load_state_dict(state, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all("img_ex" in k or k == "dense_coor" for k in res.missing_keys), res.missing_keys      # buffer: an asset
+    m.eval()
+    B = 3
+    fuse = torch.randn((B, 2, 1024), generator=torch.Generator().manual_seed(71))
+    with torch.no_grad():
+        # fmaps only pass DualGraphLayer's shape asserts (DualGraph.py:69-73); their values are never read
+        fmaps = [torch.zeros((B, 256, r, r)) for r in (12, 24, 48)] + [None]
+        result, params, hand_list, other = m(fuse[:, 0], fuse[:, 1], fmaps)
+    rec = {"fuse_feat": fuse.numpy(), "img_size": np.int64(dec.IMG_SIZE)}
+    for side in ("left", "right"):
+        rec["verts3d_" + side] = result["verts3d"][side].numpy()
+        rec["verts2d_" + side] = result["verts2d"][side].numpy()
+        rec["verts3d_gcn_" + side] = hand_list[0]["verts3d"][side].numpy()
+        rec["verts2d_gcn_" + side] = hand_list[0]["verts2d"][side].numpy()
+        rec["scale_" + side] = params["scale"][side].numpy()
+        rec["trans2d_" + side] = params["trans2d"][side].numpy()
+        rec["root_" + side] = params["root"][side].numpy()
+        rec["verts3d_mano_" + side] = other["verts3d_MANO_list"][side][0].numpy()
+        rec["verts2d_mano_" + side] = other["verts2d_MANO_list"][side][0].numpy()
+    save("gcn_decoder", **rec)
+
+
 def main():
     ref = ref_import.load_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -340,6 +387,9 @@ def main():
     golden_split_coeff(ref)
     golden_mano_head(ref)
     golden_train_step(ref)
+    ref_dec = ref_import.load_decoder()
+    export_gcn_assets(ref_dec)
+    golden_gcn_decoder(ref_dec)
 
 
 if __name__ == "__main__":

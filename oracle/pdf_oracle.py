@@ -489,3 +489,128 @@ def mano_lbs(tables, root_rotation, pose, shape, trans=None, scale=None, side="l
         j[:, 13] = (v[:, 148] + v[:, 290]) / 2
         j[:, 17] = (v[:, 770] + v[:, 83]) / 2
     return v, j
+
+
+# ----------------------------------------------------------------------------
+# GCN decoder: the consumer of fuse_feat.  resnet_mid hands
+# fuse_feat[:, 0] / fuse_feat[:, 1] over as the per-hand global features
+# (intaghand_encoder.py:873-874) and decoder.forward never touches fmaps (the
+# img_ex calls are commented out, DualGraph.py:84-85), so the decoder is a pure
+# function of fuse_feat, its parameters and the graph assets.
+# ----------------------------------------------------------------------------
+
+
+def _lin(x, sd, p):
+    return F.linear(x, sd[p + ".weight"], sd.get(p + ".bias"))
+
+
+def _ln(x, sd, p):
+    return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-6)
+
+
+def graph_conv_cheby(x, sd, p, L):
+    """model_attn/gcn.py:34-69 for K = 2: features [x, Lx] interleaved (k fastest, :62-64) -> Linear."""
+    B, V, Fin = x.shape
+    x1 = torch.einsum("vu,buf->bvf", L, x)
+    return _lin(torch.stack((x, x1), -1).reshape(B, V, Fin * 2), sd, p)
+
+
+def gcn_resblock(x, sd, p, L):
+    """GCN_ResBlock.forward, gcn.py:100-110 (eval: dropout = identity; the norm1/ReLU result of :104 is
+    overwritten by :105, which convolves the un-normalised x)."""
+    x1 = graph_conv_cheby(x, sd, p + ".fc1", L)
+    x1 = F.relu(_ln(x1, sd, p + ".norm2"))
+    x1 = graph_conv_cheby(x1, sd, p + ".fc2", L)
+    return _ln(x1 + _lin(x, sd, p + ".shortcut"), sd, p + ".norm3")
+
+
+def graph_layer(x, sd, p, L, n_blocks=4):
+    """GraphLayer.forward, gcn.py:131-137."""
+    for i in range(n_blocks):
+        x = gcn_resblock(x, sd, "%s.GCN_blocks.%d" % (p, i), L)
+        if i != n_blocks - 1:
+            x = F.relu(x)
+    return x
+
+
+def _mlp_res(x, sd, p):
+    """MLP_res_block, self_attn.py:17-33."""
+    return x + _lin(F.relu(_lin(_ln(x, sd, p + ".layer_norm"), sd, p + ".fc1")), sd, p + ".fc2")
+
+
+def _mha(xq, xkv, sd, p, heads=4):
+    """softmax(q k^T / sqrt(d)) v with the projections of ``p`` (self_attn.py:60-72, inter_attn.py:84-108)."""
+    B, V, f = xq.shape
+    d = f // heads
+    q = _lin(xq, sd, p + ".w_qs").view(B, V, heads, d).transpose(1, 2)
+    k = _lin(xkv, sd, p + ".w_ks").view(B, V, heads, d).transpose(1, 2)
+    v = _lin(xkv, sd, p + ".w_vs").view(B, V, heads, d).transpose(1, 2)
+    a = F.softmax(torch.matmul(q, k.transpose(-1, -2)) / d ** 0.5, dim=-1)
+    return _lin(torch.matmul(a, v).transpose(1, 2).reshape(B, V, f), sd, p + ".fc")
+
+
+def self_attn(x, sd, p):
+    """SelfAttn.forward, self_attn.py:75-84."""
+    h = _ln(x, sd, p + ".layer_norm")
+    return _mlp_res(x + _mha(h, h, sd, p), sd, p + ".ff")
+
+
+def inter_attn(Lf, Rf, sd, p):
+    """inter_attn.forward, inter_attn.py:113-125 (+ :72-111): two self-attention blocks, then the two
+    cross-attention directions share w_qs / w_ks / w_vs / fc."""
+    Lf = self_attn(Lf, sd, p + ".L_self_attn_layer")
+    Rf = self_attn(Rf, sd, p + ".R_self_attn_layer")
+    L2, R2 = _ln(Lf, sd, p + ".layer_norm1"), _ln(Rf, sd, p + ".layer_norm2")
+    feat_R2L = _mha(L2, R2, sd, p)            # queries from the left hand, keys / values from the right
+    feat_L2R = _mha(R2, L2, sd, p)
+    return _mlp_res(Lf + feat_R2L, sd, p + ".ffL"), _mlp_res(Rf + feat_L2R, sd, p + ".ffR")
+
+
+def hand_position_encoding(assets, side, n):
+    """decoder.get_hand_pe, intaghand_decoder.py:169-178: dense colours -> GCN order -> average pool."""
+    pe = torch.as_tensor(assets["dense_coor"], dtype=torch.float32) * 2 - 1
+    pe = pe[torch.as_tensor(assets["graph_perm_" + side]).long()]
+    return pe.view(n, pe.shape[0] // n, 3).mean(1)
+
+
+def projection_batch(scale, trans2d, v, img_size):
+    """lib/utils/utils.py:231-249."""
+    return (scale * img_size)[:, None, None] * v[..., :2] + (trans2d * img_size / 2 + img_size / 2)[:, None]
+
+
+def gcn_decoder_forward(sd, assets, fuse_feat, img_size=384):
+    """decoder.forward, intaghand_decoder.py:180-242, fed as HandNET_GCN.forward does
+    (intaghand_model.py:30-31 with resnet_mid.forward :873-874): fuse_feat [B,2,1024] ->
+    dict(verts3d_{left,right} [B,778,3], verts2d_*, verts3d_gcn_* [B,252,3], verts2d_gcn_*,
+    scale_*, trans2d_*, root_*, verts3d_mano_* / verts2d_mano_* [B,778,*])."""
+    fuse_feat = torch.as_tensor(fuse_feat)
+    dt = fuse_feat.dtype
+    out = {}
+    feats = {}
+    for h, side in enumerate(("left", "right")):
+        g = _ln(_lin(fuse_feat[:, h], sd, "gf_layer_%s.0" % side), sd, "gf_layer_%s.1" % side)
+        pe = hand_position_encoding(assets, side, 63).to(dt)
+        feats[side] = torch.cat((g[:, None, :].expand(-1, 63, -1), pe[None].expand(g.shape[0], -1, -1)), -1)
+    Lf, Rf = feats["left"], feats["right"]
+    for i in range(3):
+        p = "dual_gcn.layers.%d" % i
+        pos = sd[p + ".position_embeddings.weight"]
+        Lf = graph_layer(Lf + pos, sd, p + ".graph_left", torch.as_tensor(assets["L_left_%d" % i]).to(dt))
+        Rf = graph_layer(Rf + pos, sd, p + ".graph_right", torch.as_tensor(assets["L_right_%d" % i]).to(dt))
+        Lf, Rf = inter_attn(Lf, Rf, sd, p + ".attn")
+        if i != 2:
+            Lf, Rf = Lf.repeat_interleave(2, dim=1), Rf.repeat_interleave(2, dim=1)    # graph_upsample(., 2)
+    for side, f in (("left", Lf), ("right", Rf)):
+        temp = _lin(f.transpose(-1, -2), sd, "avg_head")[..., 0]
+        params, root = _lin(temp, sd, "params_head"), _lin(temp, sd, "root_head")
+        v252 = _lin(f, sd, "coord_head")
+        v778 = _lin(v252.transpose(1, 2), sd, "unsample_layer").transpose(1, 2)
+        scale, trans2d = params[:, 0], params[:, 1:]
+        rev = torch.as_tensor(assets["graph_perm_reverse_" + side]).long()[:778]
+        up = lambda t: t.repeat_interleave(1008 // t.shape[1], dim=1)[:, rev]             # graph_upsample + GCN_to_vert
+        v2_252 = projection_batch(scale, trans2d, v252, img_size)
+        out.update({"verts3d_" + side: v778, "verts2d_" + side: projection_batch(scale, trans2d, v778, img_size),
+                    "verts3d_gcn_" + side: v252, "verts2d_gcn_" + side: v2_252, "scale_" + side: scale,
+                    "trans2d_" + side: trans2d, "root_" + side: root, "verts3d_mano_" + side: up(v252),
+                    "verts2d_mano_" + side: up(v2_252)})
+    return out

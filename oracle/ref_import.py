@@ -180,3 +180,18 @@ def default_opt(**over):
     for k, v in over.items():
         setattr(opt, k, v)
     return opt
+
+
+def load_decoder(cfg=None, global_feature_dim=1024):
+    """The reference's GCN decoder (lib/models/networks/intaghand_decoder.py:244-277, load_decoder)
+    built exactly as load_model_intag does: cfg defaults from lib/opts.py:235-239, encoder_info from
+    resnet_mid.get_info (global_feature_dim 1024, intaghand_encoder.py:851).  Returns (module, dec_mod)."""
+    load_reference()
+    import importlib
+
+    dec = importlib.import_module("lib.models.networks.intaghand_decoder")
+    if cfg is None:
+        cfg = types.SimpleNamespace(IMG_DIMS=[256, 128, 64], GCN_IN_DIM=[512, 256, 128], GCN_OUT_DIM=[256, 128, 64],
+                                    graph_k=2, graph_layer_num=4)
+    model = dec.load_decoder(cfg, {"global_feature_dim": global_feature_dim, "fmaps_dim": [256, 256, 256, 256]})
+    return model, dec

@@ -177,3 +177,73 @@ def synthetic_mano_tables(seed=317):
 
 def to_numpy(d):
     return {k: (v.numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in d.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# GCN decoder: deterministic stand-ins for a trained checkpoint
+GCN_IN_DIM, GCN_OUT_DIM, GCN_VERTS = (512, 256, 128), (256, 128, 64), (63, 126, 252)
+
+
+def decoder_param_shapes(gf_dim=1024, graph_k=2, n_blocks=4):
+    """(name, shape) of every parameter decoder.forward uses (intaghand_decoder.py:74-147; the img_ex_*
+    sub-modules exist in the reference state dict but their call is commented out, DualGraph.py:84-85)."""
+    out = []
+    lin = lambda n, o, i, bias=True: out.extend([(n + ".weight", (o, i))] + ([(n + ".bias", (o,))] if bias else []))
+    ln = lambda n, c: out.extend([(n + ".weight", (c,)), (n + ".bias", (c,))])
+    for li, (cin, cout, V) in enumerate(zip(GCN_IN_DIM, GCN_OUT_DIM, GCN_VERTS)):
+        base = "dual_gcn.layers.%d." % li
+        out.append((base + "position_embeddings.weight", (V, cin)))
+        for side in ("graph_left", "graph_right"):
+            for b in range(n_blocks):
+                p = "%s%s.GCN_blocks.%d." % (base, side, b)
+                ci = cin if b == 0 else cout
+                ln(p + "norm1", ci)
+                lin(p + "fc1", cout, ci * graph_k)
+                ln(p + "norm2", cout)
+                lin(p + "fc2", cout, cout * graph_k)
+                lin(p + "shortcut", cout, ci)
+                ln(p + "norm3", cout)
+        a = base + "attn."
+        for sa in ("L_self_attn_layer.", "R_self_attn_layer."):
+            for w in ("w_qs", "w_ks", "w_vs"):
+                lin(a + sa + w, cout, cout)
+            ln(a + sa + "layer_norm", cout)
+            lin(a + sa + "fc", cout, cout)
+            ln(a + sa + "ff.layer_norm", cout)
+            lin(a + sa + "ff.fc1", cout, cout)
+            lin(a + sa + "ff.fc2", cout, cout)
+        for w in ("w_qs", "w_ks", "w_vs", "fc"):
+            lin(a + w, cout, cout)
+        ln(a + "layer_norm1", cout)
+        ln(a + "layer_norm2", cout)
+        for ff in ("ffL.", "ffR."):
+            ln(a + ff + "layer_norm", cout)
+            lin(a + ff + "fc1", cout, cout)
+            lin(a + ff + "fc2", cout, cout)
+    for side in ("left", "right"):
+        lin("gf_layer_%s.0" % side, GCN_IN_DIM[0] - 3, gf_dim)
+        ln("gf_layer_%s.1" % side, GCN_IN_DIM[0] - 3)
+    lin("unsample_layer", 778, GCN_VERTS[-1], bias=False)
+    lin("coord_head", 3, GCN_OUT_DIM[-1])
+    lin("avg_head", 1, GCN_VERTS[-1])
+    lin("params_head", 3, GCN_OUT_DIM[-1])
+    lin("root_head", 3, GCN_OUT_DIM[-1])
+    return out
+
+
+def decoder_state(seed=317, upsample_weight=None):
+    """Synthetic decoder weights with the reference's state-dict keys: Xavier-uniform Linear weights
+    (gcn.py:8-16), small non-zero biases, LayerNorm gains around 1, N(0,1) position embeddings."""
+    sd = {}
+    for name, shape in decoder_param_shapes():
+        if name == "unsample_layer.weight" and upsample_weight is not None:
+            sd[name] = torch.as_tensor(upsample_weight, dtype=torch.float32).clone()
+        elif name.endswith("position_embeddings.weight"):
+            sd[name] = _normal(name, shape, 1.0, seed)
+        elif len(shape) == 2:
+            sd[name] = _uniform(name, shape, math.sqrt(6.0 / (shape[0] + shape[1])), seed)
+        elif "norm" in name or (name.startswith("gf_layer") and name.split(".")[1] == "1"):
+            sd[name] = (1.0 + _uniform(name, shape, 0.1, seed)) if name.endswith("weight") else _uniform(name, shape, 0.1, seed)
+        else:
+            sd[name] = _uniform(name, shape, 0.05, seed)
+    return sd

@@ -178,3 +178,14 @@ def test_train_step_oracle_vs_reference_autograd():
     for k, v in sd.items():
         if "running_" in k:
             np.testing.assert_allclose(v.numpy(), g["buf:" + k], rtol=1e-9, atol=1e-12)
+
+
+def test_gcn_decoder_oracle_vs_reference():
+    """the decoder restatement against the unmodified reference decoder.forward."""
+    g, assets = load_golden("gcn_decoder"), load_golden("gcn_assets")
+    sd = synth.decoder_state(seed=317, upsample_weight=assets["upsample"])
+    with torch.no_grad():
+        out = O.gcn_decoder_forward(sd, assets, torch.from_numpy(g["fuse_feat"]), int(g["img_size"]))
+    assert out["verts3d_left"].shape == (3, 778, 3)
+    for k, v in out.items():
+        np.testing.assert_allclose(v.numpy(), g[k], rtol=1e-4, atol=2e-5 * max(1.0, np.abs(g[k]).max()), err_msg=k)
