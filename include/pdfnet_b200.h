@@ -331,6 +331,39 @@ int pdf_group_scatter_add(const float* dG, const int32_t* idx, int64_t n_clouds,
 int pdf_gather_nchw_bwd(const float* dOut, const int64_t* ind, int64_t n_clouds, int C, int64_t HW, int n,
                         float* dFeat, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * GCN decoder (lib/models/networks/intaghand_decoder.py:180-242): everything
+ * between two dense layers of decoder.forward.  Activations are fp32 rows [n_samples * V, C].
+ * ------------------------------------------------------------------------------------------- */
+
+/* t = a[src] (+ b[src]) (+ rowvec[v]) for output row (sample, v), src = sample*(V_out/up) + v/up
+ * (up = 2 is graph_upsample, DualGraph.py:11-18; rowvec is the position embedding, :76-80);
+ * writes t to sum_out and/or LayerNorm(t)*gamma+beta (+ReLU) to ln_out (nn.LayerNorm, eps inside the
+ * sqrt; gcn.py:92-98, self_attn.py:20,55).  C <= 1024. */
+int pdf_row_combine(const float* a, int64_t lda, const float* b, int64_t ldb, const float* rowvec, int64_t ldr,
+                    int V_out, int up, int C, int64_t rows_out, const float* gamma, const float* beta, float eps,
+                    int relu, float* sum_out, int64_t lds, float* ln_out, int64_t ldl, void* stream);
+/* Second half of a K = 2 Chebyshev graph convolution fused with the LayerNorm that follows
+ * (graph_conv_cheby gcn.py:34-69, GCN_ResBlock.forward :100-110): with U = x [W0;W1]^T already
+ * computed by a GEMM (W0 = fc.weight[:, 0::2], W1 = fc.weight[:, 1::2]),
+ *   t = U0 + bias + L.U1 (+ R + bias_r),  out = LayerNorm(t) (+ReLU);
+ * L [V,V] in CSR (rowptr int32 [V+1], colidx, vals); R is the shortcut branch (:108). */
+int pdf_graph_cheby_ln(const float* U0, const float* U1, int64_t ldu, const float* bias, const float* R, int64_t ldr,
+                       const float* bias_r, const int32_t* rowptr, const int32_t* colidx, const float* vals, int V,
+                       int C, int64_t rows, const float* gamma, const float* beta, float eps, int relu, float* out,
+                       int64_t ldo, void* stream);
+/* softmax(q k^T / sqrt(d)) v per (sample, head) (self_attn.py:60-72, inter_attn.py:84-108); q/k/v/out
+ * rows [n_samples*V, heads*d] with free pitches (q and k/v may come from different hands).
+ * V <= 256, d <= 64. */
+int pdf_mha(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* Vv, int64_t ldv,
+            int64_t n_samples, int V, int heads, int d, float* out, int64_t ldo, void* stream);
+/* projection_batch (lib/utils/utils.py:231-249) of the coarse [B,Vc,3] and dense [B,Vd,3] meshes with
+ * params [B, >=3] = (scale, tx, ty), and the MANO-order lists of intaghand_decoder.py:231-240:
+ * mano[b,i] = coarse[b, rev[i] / rep] (graph_upsample by rep, then GCN_to_vert). */
+int pdf_decoder_project(const float* v_coarse, int Vc, const float* v_dense, int Vd, const float* params, int64_t ldp,
+                        float img_size, const int64_t* rev, int rep, int64_t B, float* coarse2d, float* dense2d,
+                        float* mano3d, float* mano2d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,298 @@
+// GCN decoder kernels: the consumer of fuse_feat.
+// Reference: lib/models/networks/intaghand_decoder.py:180-242 (decoder.forward),
+// model_attn/gcn.py:34-110 (Chebyshev graph conv + GCN_ResBlock), self_attn.py:60-84,
+// inter_attn.py:72-125.  The dense layers run on the GEMM kernels (linear_f32.cu / gemm_bf16.cu);
+// everything between two GEMMs is ONE of the kernels below, activations are fp32 rows [B*V, C]:
+//   row_combine   : t = a (+ b) (+ per-vertex row) with optional x2 vertex up-sampling, writes t and/or
+//                   LayerNorm(t) (+ReLU)          -> residual adds, LayerNorms, position embeddings
+//   graph_cheby_ln: t = U0 + L.U1 + bias (+ R + bias_r), LayerNorm(t) (+ReLU), L sparse (CSR)
+//                   -> the second half of a K = 2 Chebyshev conv, fused with the norm that follows
+//   mha           : softmax(q k^T / sqrt(d)) v for one (sample, head) per CTA, V <= 256 tokens
+//   decoder_project: orthographic projection + GCN -> MANO vertex order (graph_upsample + GCN_to_vert)
+#include "pdf_common.cuh"
+
+#include <type_traits>
+
+namespace pdf {
+
+constexpr int DEC_MAX_C = 1024;          // channels per row handled by one warp (32 per lane)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// LayerNorm of the lane-distributed row t[0..n) (element i of lane l is channel l + 32 i), two-pass
+template <int NPL>
+__device__ __forceinline__ void layer_norm_row(float (&t)[NPL], int C, int lane, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, float eps, int relu,
+                                               float* __restrict__ out) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) if (lane + 32 * i < C) s += t[i];
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) if (lane + 32 * i < C) { const float d = t[i] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C) {
+      float y = fmaf((t[i] - mean) * rstd, gamma[c], beta[c]);
+      if (relu) y = fmaxf(y, 0.f);
+      out[c] = y;
+    }
+  }
+}
+
+// one warp per output row r' = (sample, v'); source row = sample * (V_out / up) + v' / up
+template <int NPL>
+__global__ void __launch_bounds__(256)
+row_combine_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
+                   const float* __restrict__ rowvec, int64_t ldr, int V_out, int up, int C, int64_t rows_out,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
+                   float* __restrict__ sum_out, int64_t lds, float* __restrict__ ln_out, int64_t ldl) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows_out) return;
+  const int64_t smp = r / V_out;
+  const int v = (int)(r - smp * V_out);
+  const int64_t src = smp * (V_out / up) + v / up;
+  float t[NPL];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int c = lane + 32 * i;
+    t[i] = 0.f;
+    if (c < C) {
+      float x = a[src * lda + c];
+      if (b) x += b[src * ldb + c];
+      if (rowvec) x += rowvec[(int64_t)v * ldr + c];
+      t[i] = x;
+      if (sum_out) sum_out[r * lds + c] = x;
+    }
+  }
+  if (ln_out) layer_norm_row<NPL>(t, C, lane, gamma, beta, eps, relu, ln_out + r * ldl);
+}
+
+// t = U0[row] + bias + sum_u L[v,u] U1[sample, u] (+ R[row] + bias_r); out = LayerNorm(t) (+ReLU)
+template <int NPL>
+__global__ void __launch_bounds__(256)
+graph_cheby_ln_kernel(const float* __restrict__ U0, const float* __restrict__ U1, int64_t ldu,
+                      const float* __restrict__ bias, const float* __restrict__ R, int64_t ldr,
+                      const float* __restrict__ bias_r, const int* __restrict__ rowptr,
+                      const int* __restrict__ colidx, const float* __restrict__ vals, int V, int C, int64_t rows,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
+                      float* __restrict__ out, int64_t ldo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const int64_t smp = r / V;
+  const int v = (int)(r - smp * V);
+  float t[NPL];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int c = lane + 32 * i;
+    t[i] = 0.f;
+    if (c < C) {
+      float x = U0[r * ldu + c] + bias[c];
+      if (R) x += R[r * ldr + c] + (bias_r ? bias_r[c] : 0.f);
+      t[i] = x;
+    }
+  }
+  const int e0 = rowptr[v], e1 = rowptr[v + 1];
+  for (int e = e0; e < e1; ++e) {
+    const float w = vals[e];
+    const float* u = U1 + (smp * V + colidx[e]) * ldu;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) t[i] = fmaf(w, u[c], t[i]);
+    }
+  }
+  layer_norm_row<NPL>(t, C, lane, gamma, beta, eps, relu, out + r * ldo);
+}
+
+// one CTA per (sample, head): K and V of that head in shared memory, one warp per query row
+__global__ void __launch_bounds__(256)
+mha_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, int64_t ldk,
+           const float* __restrict__ Vv, int64_t ldv, int V, int heads, int d, float inv_norm,
+           float* __restrict__ out, int64_t ldo) {
+  extern __shared__ float sm[];
+  const int pitch = d + 1;                       // odd pitch: lanes reading different keys hit different banks
+  float* sK = sm;
+  float* sV = sm + (size_t)V * pitch;
+  const int smp = blockIdx.x / heads, h = blockIdx.x - smp * heads;
+  const int64_t row0 = (int64_t)smp * V;
+  for (int e = threadIdx.x; e < V * d; e += blockDim.x) {
+    const int j = e / d, c = e - j * d;
+    sK[j * pitch + c] = K[(row0 + j) * ldk + h * d + c];
+    sV[j * pitch + c] = Vv[(row0 + j) * ldv + h * d + c];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i = warp; i < V; i += nwarps) {
+    const float* q = Q + (row0 + i) * ldq + h * d;
+    float p[8];                                   // keys lane, lane+32, ... (V <= 256)
+    float mx = -3.0e38f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int j = lane + 32 * t;
+      float s = -3.0e38f;
+      if (j < V) {
+        s = 0.f;
+        for (int c = 0; c < d; ++c) s = fmaf(__ldg(q + c), sK[j * pitch + c], s);
+        s *= inv_norm;
+      }
+      p[t] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float den = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int j = lane + 32 * t;
+      p[t] = j < V ? expf(p[t] - mx) : 0.f;
+      den += p[t];
+    }
+    den = warp_sum(den);
+    const float inv = 1.f / den;
+    // out[c] = sum_j p_j V[j][c]; lane owns channels lane, lane + 32
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int jbase = 32 * t;
+      if (jbase >= V) break;
+      for (int l = 0; l < 32; ++l) {
+        const int j = jbase + l;
+        if (j >= V) break;
+        const float pj = __shfl_sync(0xffffffffu, p[t], l);
+        if (lane < d) o0 = fmaf(pj, sV[j * pitch + lane], o0);
+        if (lane + 32 < d) o1 = fmaf(pj, sV[j * pitch + lane + 32], o1);
+      }
+    }
+    float* o = out + (row0 + i) * ldo + h * d;
+    if (lane < d) o[lane] = o0 * inv;
+    if (lane + 32 < d) o[lane + 32] = o1 * inv;
+  }
+}
+
+// verts2d = scale*img * v[..., :2] + (trans2d*img/2 + img/2) for the coarse (Vc) and dense (Vd) meshes, and the
+// MANO-order lists: mano[b, i] = coarse[b, rev[i] / rep]  (graph_upsample by rep = Vall / Vc, then GCN_to_vert)
+__global__ void decoder_project_kernel(const float* __restrict__ vc, int Vc, const float* __restrict__ vd, int Vd,
+                                       const float* __restrict__ params, int64_t ldp, float img,
+                                       const int64_t* __restrict__ rev, int rep, int64_t B,
+                                       float* __restrict__ vc2d, float* __restrict__ vd2d,
+                                       float* __restrict__ mano3d, float* __restrict__ mano2d) {
+  const int64_t total = B * (Vc + 2 * Vd);
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = e / (Vc + 2 * Vd);
+    const int k = (int)(e - b * (Vc + 2 * Vd));
+    const float s = params[b * ldp] * img;
+    const float tx = params[b * ldp + 1] * img / 2 + img / 2, ty = params[b * ldp + 2] * img / 2 + img / 2;
+    if (k < Vc) {
+      const float* p = vc + (b * Vc + k) * 3;
+      vc2d[(b * Vc + k) * 2] = s * p[0] + tx;
+      vc2d[(b * Vc + k) * 2 + 1] = s * p[1] + ty;
+    } else if (k < Vc + Vd) {
+      const int i = k - Vc;
+      const float* p = vd + (b * Vd + i) * 3;
+      vd2d[(b * Vd + i) * 2] = s * p[0] + tx;
+      vd2d[(b * Vd + i) * 2 + 1] = s * p[1] + ty;
+    } else {
+      const int i = k - Vc - Vd;
+      const float* p = vc + (b * Vc + (int)(rev[i] / rep)) * 3;
+      float* m3 = mano3d + (b * Vd + i) * 3;
+      m3[0] = p[0]; m3[1] = p[1]; m3[2] = p[2];
+      mano2d[(b * Vd + i) * 2] = s * p[0] + tx;
+      mano2d[(b * Vd + i) * 2 + 1] = s * p[1] + ty;
+    }
+  }
+}
+
+template <typename F>
+static int dispatch_npl(int C, F&& f) {
+  if (C <= 128) return f(std::integral_constant<int, 4>());
+  if (C <= 256) return f(std::integral_constant<int, 8>());
+  if (C <= 512) return f(std::integral_constant<int, 16>());
+  return f(std::integral_constant<int, 32>());
+}
+
+}  // namespace pdf
+
+using namespace pdf;
+
+extern "C" int pdf_row_combine(const float* a, int64_t lda, const float* b, int64_t ldb, const float* rowvec,
+                               int64_t ldr, int V_out, int up, int C, int64_t rows_out, const float* gamma,
+                               const float* beta, float eps, int relu, float* sum_out, int64_t lds, float* ln_out,
+                               int64_t ldl, void* stream) {
+  if (rows_out == 0) return PDF_OK;
+  PDF_REQUIRE(a && (sum_out || ln_out), PDF_ERR_BAD_ARG, "pdf_row_combine: null pointer");
+  PDF_REQUIRE(rows_out > 0 && C > 0 && C <= DEC_MAX_C && V_out > 0 && up >= 1 && V_out % up == 0 &&
+                  rows_out % V_out == 0 && (!ln_out || (gamma && beta)),
+              PDF_ERR_BAD_ARG, "pdf_row_combine: bad argument");
+  const unsigned grid = (unsigned)((rows_out * 32 + 255) / 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  dispatch_npl(C, [&](auto npl) {
+    row_combine_kernel<decltype(npl)::value><<<grid, 256, 0, s>>>(a, lda, b, ldb, rowvec, ldr, V_out, up, C, rows_out,
+                                                                   gamma, beta, eps, relu, sum_out, lds, ln_out, ldl);
+    return 0;
+  });
+  return check_launch("pdf_row_combine");
+}
+
+extern "C" int pdf_graph_cheby_ln(const float* U0, const float* U1, int64_t ldu, const float* bias, const float* R,
+                                  int64_t ldr, const float* bias_r, const int32_t* rowptr, const int32_t* colidx,
+                                  const float* vals, int V, int C, int64_t rows, const float* gamma,
+                                  const float* beta, float eps, int relu, float* out, int64_t ldo, void* stream) {
+  if (rows == 0) return PDF_OK;
+  PDF_REQUIRE(U0 && U1 && bias && rowptr && colidx && vals && gamma && beta && out, PDF_ERR_BAD_ARG,
+              "pdf_graph_cheby_ln: null pointer");
+  PDF_REQUIRE(rows > 0 && V > 0 && rows % V == 0 && C > 0 && C <= DEC_MAX_C, PDF_ERR_BAD_ARG,
+              "pdf_graph_cheby_ln: bad argument");
+  const unsigned grid = (unsigned)((rows * 32 + 255) / 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  dispatch_npl(C, [&](auto npl) {
+    graph_cheby_ln_kernel<decltype(npl)::value><<<grid, 256, 0, s>>>(U0, U1, ldu, bias, R, ldr, bias_r, rowptr, colidx,
+                                                                      vals, V, C, rows, gamma, beta, eps, relu, out,
+                                                                      ldo);
+    return 0;
+  });
+  return check_launch("pdf_graph_cheby_ln");
+}
+
+extern "C" int pdf_mha(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* Vv, int64_t ldv,
+                       int64_t n_samples, int V, int heads, int d, float* out, int64_t ldo, void* stream) {
+  if (n_samples == 0) return PDF_OK;
+  PDF_REQUIRE(Q && K && Vv && out, PDF_ERR_BAD_ARG, "pdf_mha: null pointer");
+  PDF_REQUIRE(n_samples > 0 && V > 0 && V <= 256 && heads > 0 && d > 0 && d <= 64 && n_samples * heads < (1ll << 31),
+              PDF_ERR_UNSUPPORTED, "pdf_mha: supports <= 256 tokens and head dim <= 64");
+  const size_t smem = (size_t)2 * V * (d + 1) * sizeof(float);
+  static pdf::PerDeviceOnce once;
+  if (once.first()) cudaFuncSetAttribute(mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 65 * 4);
+  mha_kernel<<<(unsigned)(n_samples * heads), 256, smem, (cudaStream_t)stream>>>(Q, ldq, K, ldk, Vv, ldv, V, heads, d,
+                                                                                  1.f / sqrtf((float)d), out, ldo);
+  return check_launch("pdf_mha");
+}
+
+extern "C" int pdf_decoder_project(const float* v_coarse, int Vc, const float* v_dense, int Vd, const float* params,
+                                   int64_t ldp, float img_size, const int64_t* rev, int rep, int64_t B,
+                                   float* coarse2d, float* dense2d, float* mano3d, float* mano2d, void* stream) {
+  if (B == 0) return PDF_OK;
+  PDF_REQUIRE(v_coarse && v_dense && params && rev && coarse2d && dense2d && mano3d && mano2d, PDF_ERR_BAD_ARG,
+              "pdf_decoder_project: null pointer");
+  PDF_REQUIRE(B > 0 && Vc > 0 && Vd > 0 && rep > 0 && ldp >= 3, PDF_ERR_BAD_ARG, "pdf_decoder_project: bad argument");
+  const int64_t total = B * (Vc + 2 * Vd);
+  int64_t grid = (total + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  decoder_project_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(v_coarse, Vc, v_dense, Vd, params, ldp,
+                                                                            img_size, rev, rep, B, coarse2d, dense2d,
+                                                                            mano3d, mano2d);
+  return check_launch("pdf_decoder_project");
+}

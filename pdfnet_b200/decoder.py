@@ -1,0 +1,302 @@
+"""GCN decoder - the consumer of fuse_feat in the reference's live path.
+
+Mirrors ``lib/models/networks/intaghand_decoder.py:74-242`` (class ``decoder``) with the same
+state-dict keys (``dual_gcn.layers.{i}.graph_{left,right}.GCN_blocks.{j}.*``,
+``dual_gcn.layers.{i}.attn.*``, ``gf_layer_{left,right}.*``, ``unsample_layer``, ``coord_head``,
+``avg_head``, ``params_head``, ``root_head``) and the same call:
+
+    result, paramsDict, handDictList, otherInfo = decoder(global_feature_left, global_feature_right, fmaps)
+
+``fmaps`` is accepted and ignored, as in the reference (the ``img_ex`` calls are commented out,
+``model_attn/DualGraph.py:84-85``; the ``img_ex_*`` parameters of a reference checkpoint are skipped
+on load).  Dense layers run on the GEMM kernels (``precision='fp32'``: FFMA; ``'bf16x3'``: tcgen05 with
+split-bf16 operands, fp32-accurate - both hold the 1e-4 parity; ``'bf16'``: tcgen05 with plain bf16
+operands, a few % on the projected 2-D vertices after ~40 chained layers); each run of glue between two GEMMs is one fused kernel
+(``csrc/gcn_decoder.cu``): Chebyshev graph term (sparse L) + bias + shortcut + LayerNorm + ReLU,
+residual + LayerNorm, attention, projection.  Inference only.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+
+IMG_SIZE = 384                                             # intaghand_decoder.py:17
+
+
+class GCN_vert_convert(object):
+    """intaghand_decoder.py:32-43"""
+
+    def __init__(self, vertex_num=1, graph_perm_reverse=(0,), graph_perm=(0,)):
+        self.graph_perm_reverse = graph_perm_reverse[:vertex_num]
+        self.graph_perm = graph_perm
+
+    def vert_to_GCN(self, x):
+        return x[:, self.graph_perm]
+
+    def GCN_to_vert(self, x):
+        return x[:, self.graph_perm_reverse]
+
+
+class _GCNResBlock(nn.Module):
+    def __init__(self, cin, cout, k):
+        super(_GCNResBlock, self).__init__()
+        self.norm1 = nn.LayerNorm(cin, eps=1e-6)               # present in checkpoints; its output is discarded (gcn.py:104-105)
+        self.fc1 = nn.Linear(cin * k, cout)
+        self.norm2 = nn.LayerNorm(cout, eps=1e-6)
+        self.fc2 = nn.Linear(cout * k, cout)
+        self.shortcut = nn.Linear(cin, cout)
+        self.norm3 = nn.LayerNorm(cout, eps=1e-6)
+
+
+class _GraphLayer(nn.Module):
+    def __init__(self, cin, cout, k, n):
+        super(_GraphLayer, self).__init__()
+        self.GCN_blocks = nn.ModuleList([_GCNResBlock(cin if i == 0 else cout, cout, k) for i in range(n)])
+
+
+class _MLPRes(nn.Module):
+    def __init__(self, f):
+        super(_MLPRes, self).__init__()
+        self.layer_norm = nn.LayerNorm(f, eps=1e-6)
+        self.fc1 = nn.Linear(f, f)
+        self.fc2 = nn.Linear(f, f)
+
+
+class _SelfAttn(nn.Module):
+    def __init__(self, f):
+        super(_SelfAttn, self).__init__()
+        self.w_qs, self.w_ks, self.w_vs = nn.Linear(f, f), nn.Linear(f, f), nn.Linear(f, f)
+        self.layer_norm = nn.LayerNorm(f, eps=1e-6)
+        self.fc = nn.Linear(f, f)
+        self.ff = _MLPRes(f)
+
+
+class _InterAttn(nn.Module):
+    def __init__(self, f):
+        super(_InterAttn, self).__init__()
+        self.L_self_attn_layer, self.R_self_attn_layer = _SelfAttn(f), _SelfAttn(f)
+        self.w_qs, self.w_ks, self.w_vs, self.fc = nn.Linear(f, f), nn.Linear(f, f), nn.Linear(f, f), nn.Linear(f, f)
+        self.layer_norm1, self.layer_norm2 = nn.LayerNorm(f, eps=1e-6), nn.LayerNorm(f, eps=1e-6)
+        self.ffL, self.ffR = _MLPRes(f), _MLPRes(f)
+
+
+class _DualGraphLayer(nn.Module):
+    def __init__(self, V, cin, cout, k, n):
+        super(_DualGraphLayer, self).__init__()
+        self.position_embeddings = nn.Embedding(V, cin)
+        self.graph_left, self.graph_right = _GraphLayer(cin, cout, k, n), _GraphLayer(cin, cout, k, n)
+        self.attn = _InterAttn(cout)
+
+
+class _DualGraph(nn.Module):
+    def __init__(self, verts, cins, couts, k, n):
+        super(_DualGraph, self).__init__()
+        self.layers = nn.ModuleList([_DualGraphLayer(V, ci, co, k, n) for V, ci, co in zip(verts, cins, couts)])
+
+
+def _csr(dense):
+    """Dense Laplacian (as GCN_ResBlock registers it, gcn.py:83-87) -> (rowptr, colidx, vals) int32/int32/fp32."""
+    dense = np.asarray(dense, dtype=np.float32)
+    rows, cols = np.nonzero(dense)
+    rowptr = np.zeros(dense.shape[0] + 1, dtype=np.int32)
+    np.add.at(rowptr, rows + 1, 1)
+    return (torch.from_numpy(np.cumsum(rowptr).astype(np.int32)), torch.from_numpy(cols.astype(np.int32)),
+            torch.from_numpy(dense[rows, cols].copy()))
+
+
+class decoder(nn.Module):
+    """``assets``: dict with L_{left,right}_{0,1,2} (dense Laplacians, coarse to fine), graph_perm_{side},
+    graph_perm_reverse_{side}, dense_coor [778,3], upsample [778,252] - the contents of
+    ``gcn_core/*.pkl`` (``oracle/make_golden.export_gcn_assets`` writes them as ``gcn_assets.npz``)."""
+
+    def __init__(self, assets, global_feature_dim=1024, gcn_in_dim=(512, 256, 128), gcn_out_dim=(256, 128, 64),
+                 graph_k=2, graph_layer_num=4, vertex_num=778, num_attn_heads=4, precision="fp32"):
+        super(decoder, self).__init__()
+        if precision not in ("fp32", "bf16x3", "bf16"):
+            raise ValueError("decoder: precision must be 'fp32', 'bf16x3' or 'bf16'")
+        if graph_k != 2:
+            raise NotImplementedError("decoder: only Chebyshev order graph_k=2 (the reference default) is built")
+        self.precision = precision
+        self.heads = num_attn_heads
+        self.verts = [int(np.asarray(assets["L_left_%d" % i]).shape[0]) for i in range(3)]
+        self.vNum_in, self.vNum_out = self.verts[0], self.verts[2]
+        self.vNum_all = len(assets["graph_perm_left"])
+        self.vNum_mano = vertex_num
+        self.gf_dim = global_feature_dim
+        self.gcn_in_dim, self.gcn_out_dim = list(gcn_in_dim), list(gcn_out_dim)
+        self.register_buffer("dense_coor", torch.as_tensor(np.asarray(assets["dense_coor"]), dtype=torch.float32))
+        self.converter = {}
+        for side in ("left", "right"):
+            perm = np.asarray(assets["graph_perm_" + side]).astype(np.int64)
+            rev = np.asarray(assets["graph_perm_reverse_" + side]).astype(np.int64)
+            self.converter[side] = GCN_vert_convert(vertex_num, rev, perm)
+            self.register_buffer("_rev_" + side, torch.from_numpy(rev[:vertex_num].copy()), persistent=False)
+            pe = (self.dense_coor * 2 - 1)[torch.from_numpy(perm)]                     # get_hand_pe (:169-178)
+            self.register_buffer("_pe_" + side, pe.view(self.vNum_in, -1, 3).mean(1), persistent=False)
+            for i in range(3):
+                for name, t in zip(("rowptr", "colidx", "vals"), _csr(assets["L_%s_%d" % (side, i)])):
+                    self.register_buffer("_L_%s_%d_%s" % (side, i, name), t, persistent=False)
+        self.dual_gcn = _DualGraph(self.verts, gcn_in_dim, gcn_out_dim, graph_k, graph_layer_num)
+        for side in ("left", "right"):
+            setattr(self, "gf_layer_" + side, nn.Sequential(nn.Linear(global_feature_dim, gcn_in_dim[0] - 3),
+                                                            nn.LayerNorm(gcn_in_dim[0] - 3, eps=1e-6)))
+        self.unsample_layer = nn.Linear(self.vNum_out, vertex_num, bias=False)
+        self.coord_head = nn.Linear(gcn_out_dim[-1], 3)
+        self.avg_head = nn.Linear(self.vNum_out, 1)
+        self.params_head = nn.Linear(gcn_out_dim[-1], 3)
+        self.root_head = nn.Linear(gcn_out_dim[-1], 3)
+        if "upsample" in assets:
+            self.unsample_layer.weight.data.copy_(torch.as_tensor(np.asarray(assets["upsample"])))
+        self._cache, self._cache_key = {}, None
+
+    def get_upsample_weight(self):
+        return self.unsample_layer.weight.data
+
+    def get_converter(self):
+        return self.converter
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        # a reference checkpoint also holds the img_ex_* sub-modules whose call is commented out
+        state_dict = {k: v for k, v in state_dict.items() if "img_ex_" not in k}
+        state_dict.setdefault("dense_coor", self.dense_coor)        # an asset, already set by the constructor
+        return super(decoder, self).load_state_dict(state_dict, strict=strict, **kw)
+
+    # -- concatenated / re-laid weights, rebuilt when a parameter changes --
+    def _weights(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if key == self._cache_key:
+            return self._cache
+        c = {}
+        w = lambda m: m.weight.detach()
+        for li, layer in enumerate(self.dual_gcn.layers):
+            for side in ("left", "right"):
+                for bi, blk in enumerate(getattr(layer, "graph_" + side).GCN_blocks):
+                    # Chebyshev features are interleaved (x_k fastest, gcn.py:62-64): W0 = even, W1 = odd columns
+                    c[(li, side, bi, "in")] = torch.cat([w(blk.fc1)[:, 0::2], w(blk.fc1)[:, 1::2], w(blk.shortcut)], 0).contiguous()
+                    c[(li, side, bi, "mid")] = torch.cat([w(blk.fc2)[:, 0::2], w(blk.fc2)[:, 1::2]], 0).contiguous()
+            a = layer.attn
+            for name, m in (("L", a.L_self_attn_layer), ("R", a.R_self_attn_layer), ("X", a)):
+                c[(li, name, "qkv_w")] = torch.cat([w(m.w_qs), w(m.w_ks), w(m.w_vs)], 0).contiguous()
+                c[(li, name, "qkv_b")] = torch.cat([m.w_qs.bias, m.w_ks.bias, m.w_vs.bias]).detach().contiguous()
+        for side in ("left", "right"):
+            pos0 = self.dual_gcn.layers[0].position_embeddings.weight.detach()
+            row0 = pos0.clone()
+            row0[:, -3:] += getattr(self, "_pe_" + side)          # cat([g, pe]) + pos = pad(g) + (pos + [0 | pe])
+            c[("row0", side)] = row0.contiguous()
+        self._cache, self._cache_key = c, key
+        return c
+
+    def _linear(self, x, w, b=None, act=L.ACT_NONE):
+        if self.precision != "fp32" and x.shape[0] >= 1024 and min(w.shape) >= 16:
+            return ops.linear_tc(x, w, b, act=act, split=self.precision == "bf16x3")
+        return ops.linear(x, w, b, act=act)
+
+    def _graph_layer(self, x, li, side, V):
+        c = self._weights()
+        layer = getattr(self.dual_gcn.layers[li], "graph_" + side)
+        csr = tuple(getattr(self, "_L_%s_%d_%s" % (side, li, n)) for n in ("rowptr", "colidx", "vals"))
+        nb = len(layer.GCN_blocks)
+        for bi, blk in enumerate(layer.GCN_blocks):
+            co = blk.fc1.out_features
+            U = self._linear(x, c[(li, side, bi, "in")])                                    # [M, 3*co] = [U0 | U1 | shortcut]
+            y = ops.graph_cheby_ln(U[:, :co], U[:, co:2 * co], blk.fc1.bias.detach(), csr, V,
+                                   (blk.norm2.weight.detach(), blk.norm2.bias.detach()), True)
+            U2 = self._linear(y, c[(li, side, bi, "mid")])                                  # [M, 2*co]
+            x = ops.graph_cheby_ln(U2[:, :co], U2[:, co:], blk.fc2.bias.detach(), csr, V,
+                                   (blk.norm3.weight.detach(), blk.norm3.bias.detach()), bi != nb - 1,
+                                   R=U[:, 2 * co:], bias_r=blk.shortcut.bias.detach())
+        return x
+
+    @staticmethod
+    def _ln(m):
+        return (m.weight.detach(), m.bias.detach())
+
+    def _mlp(self, h, ff):
+        f1 = self._linear(h, ff.fc1.weight.detach(), ff.fc1.bias.detach(), L.ACT_RELU)
+        return self._linear(f1, ff.fc2.weight.detach(), ff.fc2.bias.detach())
+
+    def _self_attn(self, x, li, name, sa, n, V):
+        """-> (x2, f2) with SelfAttn(x) = x2 + f2; the add is fused into the caller's next kernel."""
+        c = self._weights()
+        f = x.shape[1]
+        _, h = ops.row_combine(x, ln=self._ln(sa.layer_norm))
+        qkv = self._linear(h, c[(li, name, "qkv_w")], c[(li, name, "qkv_b")])
+        a = ops.mha(qkv[:, :f], qkv[:, f:2 * f], qkv[:, 2 * f:], n, V, self.heads)
+        g = self._linear(a, sa.fc.weight.detach(), sa.fc.bias.detach())
+        x2, h2 = ops.row_combine(x, g, ln=self._ln(sa.ff.layer_norm), want_sum=True)
+        return x2, self._mlp(h2, sa.ff)
+
+    def _inter_attn(self, xl, xr, li, n, V):
+        """-> ((xL, fL), (xR, fR)) with outputs Lf = xL + fL, Rf = xR + fR (adds deferred)."""
+        c = self._weights()
+        a = self.dual_gcn.layers[li].attn
+        f, M = xl.shape[1], xl.shape[0]
+        l2, lf = self._self_attn(xl, li, "L", a.L_self_attn_layer, n, V)
+        r2, rf = self._self_attn(xr, li, "R", a.R_self_attn_layer, n, V)
+        both = torch.empty((2 * M, f), dtype=torch.float32, device=xl.device)               # [LN1(Lf) ; LN2(Rf)]
+        Lf, _ = ops.row_combine(l2, lf, ln=self._ln(a.layer_norm1), want_sum=True, ln_out=both[:M])
+        Rf, _ = ops.row_combine(r2, rf, ln=self._ln(a.layer_norm2), want_sum=True, ln_out=both[M:])
+        qkv = self._linear(both, c[(li, "X", "qkv_w")], c[(li, "X", "qkv_b")])            # shared projections
+        q, k, v = qkv[:, :f], qkv[:, f:2 * f], qkv[:, 2 * f:]
+        att = torch.empty((2 * M, f), dtype=torch.float32, device=xl.device)
+        ops.mha(q[:M], k[M:], v[M:], n, V, self.heads, out=att[:M])                         # R2L: left queries, right keys/values
+        ops.mha(q[M:], k[:M], v[:M], n, V, self.heads, out=att[M:])                         # L2R
+        feat = self._linear(att, a.fc.weight.detach(), a.fc.bias.detach())
+        x4l, h4l = ops.row_combine(Lf, feat[:M], ln=self._ln(a.ffL.layer_norm), want_sum=True)
+        x4r, h4r = ops.row_combine(Rf, feat[M:], ln=self._ln(a.ffR.layer_norm), want_sum=True)
+        return (x4l, self._mlp(h4l, a.ffL)), (x4r, self._mlp(h4r, a.ffR))
+
+    def forward(self, global_feature_left, global_feature_right, fmaps=None):
+        if self.training:
+            raise NotImplementedError("pdfnet_b200.decoder: inference only (call .eval())")
+        L.require_cuda(global_feature_left, global_feature_right)
+        with torch.no_grad():
+            c = self._weights()
+            B = global_feature_left.shape[0]
+            assert global_feature_left.shape[1] == self.gf_dim and global_feature_right.shape[1] == self.gf_dim
+            cin0 = self.gcn_in_dim[0]
+            x = {}
+            for side, gfeat in (("left", global_feature_left), ("right", global_feature_right)):
+                gf = getattr(self, "gf_layer_" + side)
+                g = self._linear(L.f32c(gfeat), gf[0].weight.detach(), gf[0].bias.detach())
+                gpad = torch.zeros((B, cin0), dtype=torch.float32, device=g.device)
+                ops.row_combine(g, ln=self._ln(gf[1]), ln_out=gpad[:, :cin0 - 3])
+                # Lf = cat([g repeated over the 63 vertices, pe], -1) + position embedding (:197-198, DualGraph.py:76-80)
+                x[side], _ = ops.row_combine(gpad, rowvec=c[("row0", side)], V_out=self.verts[0], up=self.verts[0],
+                                             want_sum=True)
+            for li, V in enumerate(self.verts):
+                xl = self._graph_layer(x["left"], li, "left", V)
+                xr = self._graph_layer(x["right"], li, "right", V)
+                (al, bl), (ar, br) = self._inter_attn(xl, xr, li, B, V)
+                if li != 2:                                    # add + graph_upsample(., 2) + next position embedding
+                    pos = self.dual_gcn.layers[li + 1].position_embeddings.weight.detach()
+                    x["left"], _ = ops.row_combine(al, bl, rowvec=pos, V_out=2 * V, up=2, want_sum=True)
+                    x["right"], _ = ops.row_combine(ar, br, rowvec=pos, V_out=2 * V, up=2, want_sum=True)
+                else:
+                    x["left"], _ = ops.row_combine(al, bl, V_out=V, want_sum=True)
+                    x["right"], _ = ops.row_combine(ar, br, V_out=V, want_sum=True)
+            V, fo = self.verts[2], self.gcn_out_dim[-1]
+            scale, trans2d, root, verts3d, verts2d = {}, {}, {}, {}, {}
+            result = {"verts3d": {}, "verts2d": {}}
+            other = {"verts3d_MANO_list": {"left": [], "right": []}, "verts2d_MANO_list": {"left": [], "right": []}}
+            for side in ("left", "right"):
+                f = x[side]                                                                  # [B*252, 64]
+                ft = f.view(B, V, fo).transpose(1, 2).contiguous().view(B * fo, V)
+                temp = ops.linear(ft, self.avg_head.weight.detach(), self.avg_head.bias.detach()).view(B, fo)
+                params = ops.linear(temp, self.params_head.weight.detach(), self.params_head.bias.detach())
+                root[side] = ops.linear(temp, self.root_head.weight.detach(), self.root_head.bias.detach())
+                v252 = ops.linear(f, self.coord_head.weight.detach(), self.coord_head.bias.detach()).view(B, V, 3)
+                vt = v252.transpose(1, 2).contiguous().view(B * 3, V)
+                v778 = ops.linear(vt, self.unsample_layer.weight.detach()).view(B, 3, -1).transpose(1, 2).contiguous()
+                c2, d2, m3, m2 = ops.decoder_project(v252, v778, params, IMG_SIZE, getattr(self, "_rev_" + side),
+                                                     self.vNum_all // V)
+                scale[side], trans2d[side] = params[:, 0], params[:, 1:]
+                verts3d[side], verts2d[side] = v252, c2
+                result["verts3d"][side], result["verts2d"][side] = v778, d2
+                other["verts3d_MANO_list"][side].append(m3)
+                other["verts2d_MANO_list"][side].append(m2)
+            paramsDict = {"scale": scale, "trans2d": trans2d, "root": root}
+            handDictList = [{"verts3d": verts3d, "verts2d": verts2d}]
+            return result, paramsDict, handDictList, other

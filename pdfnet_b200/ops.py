@@ -525,3 +525,66 @@ def linear_tn_tc(a, b, split=True):
     if batches == 1:
         return part[0, :, :K]
     return col_sum(part.view(batches, N * ldk)).view(N, ldk)[:, :K]
+
+
+# ------------------------------------------------------------------------------------------------
+# GCN decoder primitives (gcn_decoder.cu)
+def row_combine(a, b=None, rowvec=None, V_out=None, up=1, ln=None, relu=False, want_sum=False, eps=1e-6,
+                ln_out=None):
+    """t = a[src] (+ b[src]) (+ rowvec[v]); returns (t or None, LayerNorm(t) or None); see pdf_row_combine.
+    ``ln`` = (gamma, beta).  Output rows = a.shape[0] * up."""
+    L.require_cuda(a, b, rowvec, ln_out)
+    Ma, C = _rows(a).shape
+    rows = Ma * up
+    if V_out is None:
+        V_out = up
+    dev = a.device
+    s_out = torch.empty((rows, C), dtype=torch.float32, device=dev) if want_sum else None
+    if ln is not None and ln_out is None:
+        ln_out = torch.empty((rows, C), dtype=torch.float32, device=dev)
+    gamma, beta = ln if ln is not None else (None, None)
+    L.call("pdf_row_combine", L.ptr(a), a.stride(0), L.ptr(b), b.stride(0) if b is not None else 0, L.ptr(rowvec),
+           rowvec.stride(0) if rowvec is not None else 0, V_out, up, C, rows, L.ptr(gamma), L.ptr(beta), float(eps),
+           int(relu), L.ptr(s_out), C, L.ptr(ln_out), ln_out.stride(0) if ln_out is not None else 0, L.stream())
+    return s_out, ln_out
+
+
+def graph_cheby_ln(U0, U1, bias, csr, V, ln, relu, R=None, bias_r=None, eps=1e-6):
+    """LayerNorm(U0 + bias + L.U1 (+ R + bias_r)) (+ReLU); U0/U1 (and R) are column slices of GEMM outputs."""
+    L.require_cuda(U0, U1, bias, R)
+    rows, C = _rows(U0).shape
+    assert U1.stride(0) == U0.stride(0) and U1.shape == U0.shape
+    rowptr, colidx, vals = csr
+    out = torch.empty((rows, C), dtype=torch.float32, device=U0.device)
+    L.call("pdf_graph_cheby_ln", L.ptr(U0), L.ptr(U1), U0.stride(0), L.ptr(bias), L.ptr(R),
+           R.stride(0) if R is not None else 0, L.ptr(bias_r), L.ptr(rowptr), L.ptr(colidx), L.ptr(vals), V, C, rows,
+           L.ptr(ln[0]), L.ptr(ln[1]), float(eps), int(relu), L.ptr(out), C, L.stream())
+    return out
+
+
+def mha(q, k, v, n_samples, V, heads, out=None):
+    """softmax(q k^T / sqrt(d)) v per (sample, head); q/k/v [n_samples*V, heads*d] column slices."""
+    L.require_cuda(q, k, v, out)
+    M, f = _rows(q).shape
+    assert M == n_samples * V and f % heads == 0
+    if out is None:
+        out = torch.empty((M, f), dtype=torch.float32, device=q.device)
+    L.call("pdf_mha", L.ptr(q), q.stride(0), L.ptr(_rows(k)), k.stride(0), L.ptr(_rows(v)), v.stride(0), n_samples, V,
+           heads, f // heads, L.ptr(out), out.stride(0), L.stream())
+    return out
+
+
+def decoder_project(v_coarse, v_dense, params, img_size, rev, rep):
+    """-> (coarse2d [B,Vc,2], dense2d [B,Vd,2], mano3d [B,Vd,3], mano2d [B,Vd,2]); see pdf_decoder_project."""
+    L.require_cuda(v_coarse, v_dense, params, rev)
+    B, Vc, _ = v_coarse.shape
+    Vd = v_dense.shape[1]
+    assert v_coarse.is_contiguous() and v_dense.is_contiguous() and params.stride(1) == 1 and rev.dtype == torch.int64
+    dev = v_coarse.device
+    c2 = torch.empty((B, Vc, 2), dtype=torch.float32, device=dev)
+    d2 = torch.empty((B, Vd, 2), dtype=torch.float32, device=dev)
+    m3 = torch.empty((B, Vd, 3), dtype=torch.float32, device=dev)
+    m2 = torch.empty((B, Vd, 2), dtype=torch.float32, device=dev)
+    L.call("pdf_decoder_project", L.ptr(v_coarse), Vc, L.ptr(v_dense), Vd, L.ptr(params), params.stride(0),
+           float(img_size), L.ptr(rev), rep, B, L.ptr(c2), L.ptr(d2), L.ptr(m3), L.ptr(m2), L.stream())
+    return c2, d2, m3, m2

@@ -997,3 +997,63 @@ def test_train_step_fp32_gradients_are_aligned():
             continue
         cos = float(np.dot(got, ref) / (np.linalg.norm(got) * np.linalg.norm(ref)))
         assert cos >= 0.999, (k, cos)
+
+
+# ----------------------------------------------------------------------------- GCN decoder (f3)
+
+def _decoder(precision):
+    from pdfnet_b200.decoder import decoder
+    assets = load_golden("gcn_assets")
+    m = decoder(assets, precision=precision)
+    m.load_state_dict(synth.decoder_state(seed=317, upsample_weight=assets["upsample"]), strict=True)
+    return m.to(DEV).eval(), assets
+
+
+def _decoder_outputs(res):
+    result, params, hands, other = res
+    out = {}
+    for side in ("left", "right"):
+        out["verts3d_" + side], out["verts2d_" + side] = result["verts3d"][side], result["verts2d"][side]
+        out["verts3d_gcn_" + side], out["verts2d_gcn_" + side] = hands[0]["verts3d"][side], hands[0]["verts2d"][side]
+        out["scale_" + side], out["trans2d_" + side], out["root_" + side] = (params["scale"][side], params["trans2d"][side],
+                                                                             params["root"][side])
+        out["verts3d_mano_" + side] = other["verts3d_MANO_list"][side][0]
+        out["verts2d_mano_" + side] = other["verts2d_MANO_list"][side][0]
+    return out
+
+
+def test_gcn_decoder_vs_reference_golden():
+    """decoder.forward (intaghand_decoder.py:180-242) against the unmodified reference: every returned
+    tensor, fp32 path 1e-4 of each tensor's scale."""
+    g = load_golden("gcn_decoder")
+    m, _ = _decoder("fp32")
+    fuse = torch.from_numpy(g["fuse_feat"]).to(DEV)
+    out = _decoder_outputs(m(fuse[:, 0], fuse[:, 1], None))
+    for k, v in out.items():
+        assert tuple(v.shape) == g[k].shape, k
+        assert rel_err(v.cpu().numpy(), g[k]) < 1e-4, (k, rel_err(v.cpu().numpy(), g[k]))
+
+
+def test_gcn_decoder_tensor_core_and_batch():
+    """Tensor-core paths at a batch large enough to take them (rows >= 1024): split-bf16 operands hold the
+    fp32 tolerance (2e-4 vs the oracle), plain bf16 stays within 8e-2 on every output (2-D vertices are
+    scale/translation amplified by the 384 px image size); deterministic; batch-independent."""
+    B = 24
+    fuse = torch.randn((B, 2, 1024), generator=torch.Generator().manual_seed(72))
+    fl, fr = fuse[:, 0].to(DEV), fuse[:, 1].to(DEV)
+    assets = load_golden("gcn_assets")
+    sd = synth.decoder_state(seed=317, upsample_weight=assets["upsample"])
+    with torch.no_grad():
+        ref = O.gcn_decoder_forward(sd, assets, fuse)
+    for prec, tol in (("bf16x3", 2e-4), ("bf16", 8e-2)):
+        m, _ = _decoder(prec)
+        out = _decoder_outputs(m(fl, fr, None))
+        for k, v in out.items():
+            assert rel_err(v.cpu().numpy(), ref[k].numpy()) < tol, (prec, k, rel_err(v.cpu().numpy(), ref[k].numpy()))
+        again = _decoder_outputs(m(fl, fr, None))
+        assert all(torch.equal(out[k], again[k]) for k in out)
+    m32, _ = _decoder("fp32")
+    full = _decoder_outputs(m32(fl, fr, None))
+    part = _decoder_outputs(m32(fl[5:9], fr[5:9], None))
+    for k in full:
+        assert rel_err(part[k].cpu().numpy(), full[k][5:9].cpu().numpy()) < 1e-5, k
