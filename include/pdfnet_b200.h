@@ -354,7 +354,7 @@ int pdf_graph_cheby_ln(const float* U0, const float* U1, int64_t ldu, const floa
                        int64_t ldo, void* stream);
 /* softmax(q k^T / sqrt(d)) v per (sample, head) (self_attn.py:60-72, inter_attn.py:84-108); q/k/v/out
  * rows [n_samples*V, heads*d] with free pitches (q and k/v may come from different hands).
- * V <= 256, d <= 64. */
+ * V <= 256, d in {16, 32, 64}. */
 int pdf_mha(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* Vv, int64_t ldv,
             int64_t n_samples, int V, int heads, int d, float* out, int64_t ldo, void* stream);
 /* projection_batch (lib/utils/utils.py:231-249) of the coarse [B,Vc,3] and dense [B,Vd,3] meshes with

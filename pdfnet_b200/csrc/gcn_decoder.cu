@@ -119,67 +119,107 @@ graph_cheby_ln_kernel(const float* __restrict__ U0, const float* __restrict__ U1
   layer_norm_row<NPL>(t, C, lane, gamma, beta, eps, relu, out + r * ldo);
 }
 
-// one CTA per (sample, head): K and V of that head in shared memory, one warp per query row
-__global__ void __launch_bounds__(256)
+// one CTA per (sample, head): K and V of that head in shared memory; each warp takes FOUR query rows at a
+// time: scores with lane = key (8 keys per lane, 32 FMAs per 9 shared loads), softmax by warp shuffles,
+// probabilities through a per-warp shared tile, then P.V with lane = output channel.
+constexpr int MHA_WARPS = 8, MHA_R = 4, MHA_MAXV = 256;
+
+template <int D>
+__global__ void __launch_bounds__(MHA_WARPS * 32)
 mha_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ K, int64_t ldk,
-           const float* __restrict__ Vv, int64_t ldv, int V, int heads, int d, float inv_norm,
+           const float* __restrict__ Vv, int64_t ldv, int V, int heads, float inv_norm,
            float* __restrict__ out, int64_t ldo) {
-  extern __shared__ float sm[];
-  const int pitch = d + 1;                       // odd pitch: lanes reading different keys hit different banks
-  float* sK = sm;
-  float* sV = sm + (size_t)V * pitch;
+  extern __shared__ __align__(16) float sm[];
+  constexpr int PITCH = D + 1;                   // odd pitch: lanes reading different keys hit different banks
+  float* sP = sm;                                // [warps][MAXV][4]  (query fastest: one 16 B load = 4 rows)
+  float* sQ = sP + MHA_WARPS * MHA_MAXV * MHA_R; // [warps][D][4]
+  float* sV = sQ + MHA_WARPS * D * MHA_R;        // [V][D]
+  float* sK = sV + (size_t)V * D;                // [V][D+1]
   const int smp = blockIdx.x / heads, h = blockIdx.x - smp * heads;
   const int64_t row0 = (int64_t)smp * V;
-  for (int e = threadIdx.x; e < V * d; e += blockDim.x) {
-    const int j = e / d, c = e - j * d;
-    sK[j * pitch + c] = K[(row0 + j) * ldk + h * d + c];
-    sV[j * pitch + c] = Vv[(row0 + j) * ldv + h * d + c];
+  for (int e = threadIdx.x; e < V * D; e += blockDim.x) {
+    const int j = e / D, c = e - j * D;
+    sK[j * PITCH + c] = K[(row0 + j) * ldk + h * D + c];
+    sV[j * D + c] = Vv[(row0 + j) * ldv + h * D + c];
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int i = warp; i < V; i += nwarps) {
-    const float* q = Q + (row0 + i) * ldq + h * d;
-    float p[8];                                   // keys lane, lane+32, ... (V <= 256)
-    float mx = -3.0e38f;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int j = lane + 32 * t;
-      float s = -3.0e38f;
-      if (j < V) {
-        s = 0.f;
-        for (int c = 0; c < d; ++c) s = fmaf(__ldg(q + c), sK[j * pitch + c], s);
-        s *= inv_norm;
-      }
-      p[t] = s;
-      mx = fmaxf(mx, s);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* wP = sP + warp * MHA_MAXV * MHA_R;
+  float* wQ = sQ + warp * D * MHA_R;
+  for (int i0 = warp * MHA_R; i0 < V; i0 += MHA_WARPS * MHA_R) {
+    // stage the four query rows, pre-scaled by 1/sqrt(d)
+    for (int e = lane; e < D * MHA_R; e += 32) {
+      const int r = e / D, c = e - r * D;
+      wQ[c * MHA_R + r] = (i0 + r < V) ? Q[(row0 + i0 + r) * ldq + h * D + c] * inv_norm : 0.f;
     }
-    mx = warp_max(mx);
-    float den = 0.f;
+    __syncwarp();
+    float s[MHA_R][8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int j = lane + 32 * t;
-      p[t] = j < V ? expf(p[t] - mx) : 0.f;
-      den += p[t];
-    }
-    den = warp_sum(den);
-    const float inv = 1.f / den;
-    // out[c] = sum_j p_j V[j][c]; lane owns channels lane, lane + 32
-    float o0 = 0.f, o1 = 0.f;
+    for (int r = 0; r < MHA_R; ++r)
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int jbase = 32 * t;
-      if (jbase >= V) break;
-      for (int l = 0; l < 32; ++l) {
-        const int j = jbase + l;
-        if (j >= V) break;
-        const float pj = __shfl_sync(0xffffffffu, p[t], l);
-        if (lane < d) o0 = fmaf(pj, sV[j * pitch + lane], o0);
-        if (lane + 32 < d) o1 = fmaf(pj, sV[j * pitch + lane + 32], o1);
+      for (int t = 0; t < 8; ++t) s[r][t] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < D; ++c) {
+      const float4 q = *reinterpret_cast<const float4*>(wQ + c * MHA_R);
+      float kc[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { const int j = lane + 32 * t; kc[t] = j < V ? sK[j * PITCH + c] : 0.f; }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        s[0][t] = fmaf(q.x, kc[t], s[0][t]); s[1][t] = fmaf(q.y, kc[t], s[1][t]);
+        s[2][t] = fmaf(q.z, kc[t], s[2][t]); s[3][t] = fmaf(q.w, kc[t], s[3][t]);
       }
     }
-    float* o = out + (row0 + i) * ldo + h * d;
-    if (lane < d) o[lane] = o0 * inv;
-    if (lane + 32 < d) o[lane + 32] = o1 * inv;
+#pragma unroll
+    for (int r = 0; r < MHA_R; ++r) {
+      float mx = -3.0e38f;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) if (lane + 32 * t < V) mx = fmaxf(mx, s[r][t]);
+      mx = warp_max(mx);
+      float den = 0.f;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { s[r][t] = (lane + 32 * t < V) ? expf(s[r][t] - mx) : 0.f; den += s[r][t]; }
+      const float inv = 1.f / warp_sum(den);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) if (lane + 32 * t < V) wP[(lane + 32 * t) * MHA_R + r] = s[r][t] * inv;
+    }
+    __syncwarp();
+    // out[r][c] = sum_j P[j][r] V[j][c]
+    if (D >= 32) {
+      float o0[MHA_R] = {0.f, 0.f, 0.f, 0.f}, o1[MHA_R] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int j = 0; j < V; ++j) {
+        const float4 pj = *reinterpret_cast<const float4*>(wP + j * MHA_R);
+        const float v0 = sV[j * D + lane];
+        o0[0] = fmaf(pj.x, v0, o0[0]); o0[1] = fmaf(pj.y, v0, o0[1]); o0[2] = fmaf(pj.z, v0, o0[2]); o0[3] = fmaf(pj.w, v0, o0[3]);
+        if (D == 64) {
+          const float v1 = sV[j * D + lane + 32];
+          o1[0] = fmaf(pj.x, v1, o1[0]); o1[1] = fmaf(pj.y, v1, o1[1]); o1[2] = fmaf(pj.z, v1, o1[2]); o1[3] = fmaf(pj.w, v1, o1[3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < MHA_R; ++r) {
+        if (i0 + r < V) {
+          float* o = out + (row0 + i0 + r) * ldo + h * D;
+          o[lane] = o0[r];
+          if (D == 64) o[lane + 32] = o1[r];
+        }
+      }
+    } else {                                     // D == 16: two key groups per warp, combined by one shuffle
+      const int c = lane & 15, g = lane >> 4;
+      float o[MHA_R] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = g; j < V; j += 2) {
+        const float4 pj = *reinterpret_cast<const float4*>(wP + j * MHA_R);
+        const float v0 = sV[j * D + c];
+        o[0] = fmaf(pj.x, v0, o[0]); o[1] = fmaf(pj.y, v0, o[1]); o[2] = fmaf(pj.z, v0, o[2]); o[3] = fmaf(pj.w, v0, o[3]);
+      }
+#pragma unroll
+      for (int r = 0; r < MHA_R; ++r) {
+        o[r] += __shfl_xor_sync(0xffffffffu, o[r], 16);
+        if (g == 0 && i0 + r < V) out[(row0 + i0 + r) * ldo + h * D + c] = o[r];
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -271,13 +311,24 @@ extern "C" int pdf_mha(const float* Q, int64_t ldq, const float* K, int64_t ldk,
                        int64_t n_samples, int V, int heads, int d, float* out, int64_t ldo, void* stream) {
   if (n_samples == 0) return PDF_OK;
   PDF_REQUIRE(Q && K && Vv && out, PDF_ERR_BAD_ARG, "pdf_mha: null pointer");
-  PDF_REQUIRE(n_samples > 0 && V > 0 && V <= 256 && heads > 0 && d > 0 && d <= 64 && n_samples * heads < (1ll << 31),
-              PDF_ERR_UNSUPPORTED, "pdf_mha: supports <= 256 tokens and head dim <= 64");
-  const size_t smem = (size_t)2 * V * (d + 1) * sizeof(float);
+  PDF_REQUIRE(n_samples > 0 && V > 0 && V <= MHA_MAXV && heads > 0 && (d == 16 || d == 32 || d == 64) &&
+                  n_samples * heads < (1ll << 31),
+              PDF_ERR_UNSUPPORTED, "pdf_mha: supports <= 256 tokens and head dim 16 / 32 / 64");
+  const size_t smem = sizeof(float) * ((size_t)MHA_WARPS * MHA_MAXV * MHA_R + (size_t)MHA_WARPS * d * MHA_R +
+                                       (size_t)V * d + (size_t)V * (d + 1));
   static pdf::PerDeviceOnce once;
-  if (once.first()) cudaFuncSetAttribute(mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 65 * 4);
-  mha_kernel<<<(unsigned)(n_samples * heads), 256, smem, (cudaStream_t)stream>>>(Q, ldq, K, ldk, Vv, ldv, V, heads, d,
-                                                                                  1.f / sqrtf((float)d), out, ldo);
+  if (once.first()) {
+    const int mx = (int)(sizeof(float) * (MHA_WARPS * MHA_MAXV * MHA_R + MHA_WARPS * 64 * MHA_R + 256 * 64 + 256 * 65));
+    cudaFuncSetAttribute(mha_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(mha_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(mha_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  }
+  const unsigned grid = (unsigned)(n_samples * heads);
+  const float inv_norm = 1.f / sqrtf((float)d);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (d == 16) mha_kernel<16><<<grid, MHA_WARPS * 32, smem, s>>>(Q, ldq, K, ldk, Vv, ldv, V, heads, inv_norm, out, ldo);
+  else if (d == 32) mha_kernel<32><<<grid, MHA_WARPS * 32, smem, s>>>(Q, ldq, K, ldk, Vv, ldv, V, heads, inv_norm, out, ldo);
+  else mha_kernel<64><<<grid, MHA_WARPS * 32, smem, s>>>(Q, ldq, K, ldk, Vv, ldv, V, heads, inv_norm, out, ldo);
   return check_launch("pdf_mha");
 }
 

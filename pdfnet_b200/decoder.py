@@ -9,9 +9,10 @@ state-dict keys (``dual_gcn.layers.{i}.graph_{left,right}.GCN_blocks.{j}.*``,
 
 ``fmaps`` is accepted and ignored, as in the reference (the ``img_ex`` calls are commented out,
 ``model_attn/DualGraph.py:84-85``; the ``img_ex_*`` parameters of a reference checkpoint are skipped
-on load).  Dense layers run on the GEMM kernels (``precision='fp32'``: FFMA; ``'bf16x3'``: tcgen05 with
-split-bf16 operands, fp32-accurate - both hold the 1e-4 parity; ``'bf16'``: tcgen05 with plain bf16
-operands, a few % on the projected 2-D vertices after ~40 chained layers); each run of glue between two GEMMs is one fused kernel
+on load).  Dense layers run on the GEMM kernels (``precision='fp32'``: FFMA; ``'bf16x3'`` (alias
+``'bf16'``): tcgen05 with split-bf16 operands, fp32-accurate - both hold the 1e-4 parity.  Plain bf16
+operands were measured and dropped: after ~40 chained layers the scale / translation heads drift by
+5-9 % for a 5 % shorter step); each run of glue between two GEMMs is one fused kernel
 (``csrc/gcn_decoder.cu``): Chebyshev graph term (sparse L) + bias + shortcut + LayerNorm + ReLU,
 residual + LayerNorm, attention, projection.  Inference only.
 """
@@ -115,7 +116,7 @@ class decoder(nn.Module):
                  graph_k=2, graph_layer_num=4, vertex_num=778, num_attn_heads=4, precision="fp32"):
         super(decoder, self).__init__()
         if precision not in ("fp32", "bf16x3", "bf16"):
-            raise ValueError("decoder: precision must be 'fp32', 'bf16x3' or 'bf16'")
+            raise ValueError("decoder: precision must be 'fp32' or 'bf16x3' ('bf16' is an alias of the latter)")
         if graph_k != 2:
             raise NotImplementedError("decoder: only Chebyshev order graph_k=2 (the reference default) is built")
         self.precision = precision
@@ -190,7 +191,7 @@ class decoder(nn.Module):
 
     def _linear(self, x, w, b=None, act=L.ACT_NONE):
         if self.precision != "fp32" and x.shape[0] >= 1024 and min(w.shape) >= 16:
-            return ops.linear_tc(x, w, b, act=act, split=self.precision == "bf16x3")
+            return ops.linear_tc(x, w, b, act=act, split=True)
         return ops.linear(x, w, b, act=act)
 
     def _graph_layer(self, x, li, side, V):

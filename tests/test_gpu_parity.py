@@ -1035,9 +1035,8 @@ def test_gcn_decoder_vs_reference_golden():
 
 
 def test_gcn_decoder_tensor_core_and_batch():
-    """Tensor-core paths at a batch large enough to take them (rows >= 1024): split-bf16 operands hold the
-    fp32 tolerance (2e-4 vs the oracle), plain bf16 stays within 8e-2 on every output (2-D vertices are
-    scale/translation amplified by the 384 px image size); deterministic; batch-independent."""
+    """Tensor-core path at a batch large enough to take it (rows >= 1024): split-bf16 operands hold the
+    fp32 tolerance (2e-4 vs the oracle); deterministic; batch-independent."""
     B = 24
     fuse = torch.randn((B, 2, 1024), generator=torch.Generator().manual_seed(72))
     fl, fr = fuse[:, 0].to(DEV), fuse[:, 1].to(DEV)
@@ -1045,7 +1044,7 @@ def test_gcn_decoder_tensor_core_and_batch():
     sd = synth.decoder_state(seed=317, upsample_weight=assets["upsample"])
     with torch.no_grad():
         ref = O.gcn_decoder_forward(sd, assets, fuse)
-    for prec, tol in (("bf16x3", 2e-4), ("bf16", 8e-2)):
+    for prec, tol in (("bf16x3", 2e-4),):
         m, _ = _decoder(prec)
         out = _decoder_outputs(m(fl, fr, None))
         for k, v in out.items():
