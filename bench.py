@@ -606,6 +606,120 @@ def run_cfg5(args):
         torch.distributed.destroy_process_group()
 
 
+def decoder_flops_per_frame():
+    """Dense-layer + attention FLOPs of decoder.forward for one frame (two hands)."""
+    cins, couts, verts = (512, 256, 128), (256, 128, 64), (63, 126, 252)
+    fl = 2 * 1024 * 509                                                  # gf_layer
+    for ci, co, V in zip(cins, couts, verts):
+        g = 0
+        for b in range(4):
+            c0 = ci if b == 0 else co
+            g += 2 * V * (c0 * 3 * co + co * 2 * co)                       # [W0;W1;shortcut], [W0';W1']
+        sa = 2 * V * (3 * co * co + co * co + 2 * co * co) + 4 * V * V * co  # qkv, fc, ff + QK^T, PV
+        ia = 2 * V * (3 * co * co + co * co + 2 * co * co) + 4 * V * V * co
+        fl += g + sa + ia
+    fl += 2 * 252 * 64 * 3 + 2 * 3 * 252 * 778
+    return 2 * fl
+
+
+def run_decoder(args):
+    """the GCN decoder that consumes fuse_feat (the reference's live path after the
+    fusion tail).  One step = decoder.forward for ``--frames`` frames (both hands), replayed as a CUDA graph."""
+    from pdfnet_b200 import parallel
+    rank, world, local = parallel.init_distributed("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    from pdfnet_b200 import _lib, synth
+    from pdfnet_b200.decoder import decoder
+    from pdfnet_b200.graph import CapturedStep
+    assets = dict(np.load(os.path.join(ROOT, "tests", "golden", "gcn_assets.npz")))
+    B = args.frames
+    prec = "fp32" if args.precision == "fp32" else "bf16x3"
+    m = decoder(assets, precision=prec)
+    state = synth.decoder_state(317, assets["upsample"])
+    m.load_state_dict(state)
+    m = m.to(dev).eval()
+    fuse_host = torch.randn((B, 2, 1024), generator=torch.Generator().manual_seed(317 + rank)).pin_memory()
+    fuse = fuse_host.to(dev)
+    fl, fr = fuse[:, 0].contiguous(), fuse[:, 1].contiguous()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def fwd():
+        result, params, _, _ = m(fl, fr, None)
+        return result["verts3d"]["left"], result["verts3d"]["right"], params["root"]["left"], params["root"]["right"]
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        return parallel.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / steps, dev)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_eager = timed(fwd, args.steps, args.warmup)
+    step = CapturedStep(fwd)
+    ms_dev = timed(step.replay, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    out_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in step.outputs]
+
+    def e2e():
+        fuse.copy_(fuse_host, non_blocking=True)
+        fl.copy_(fuse[:, 0]); fr.copy_(fuse[:, 1])
+        outs = step.replay()
+        for h, t in zip(out_host, outs):
+            h.copy_(t, non_blocking=True)
+
+    ms_e2e = timed(e2e, args.steps, args.warmup)
+    if rank == 0:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+        flops = decoder_flops_per_frame() * B
+        ach = flops / (ms_dev * 1e-3) / 1e12
+        from oracle import pdf_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        ns = args.cpu_sample_frames
+        sd = state
+        with torch.no_grad():
+            O.gcn_decoder_forward(sd, assets, fuse_host[:ns])
+            t0 = time.perf_counter(); O.gcn_decoder_forward(sd, assets, fuse_host[:ns]); t_cpu = time.perf_counter() - t0
+        cores = os.cpu_count() or 1
+        print(json.dumps({
+            "metric": "decoder_frames_per_sec", "value": world * B / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "eager_ms_per_step": ms_eager,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if prec == "fp32" else "bf16x3 (split operands, fp32-accurate)", "data": "synthetic",
+            "config": {"workload": "f3-gcn-decoder: %d frames/GPU x 2 hands, fuse_feat [B,2,1024] -> 3 DualGraph levels "
+                                   "(63/126/252 vertices, 4 GCN blocks + self/inter attention each) -> 778-vertex meshes"
+                                   % B, "precision": prec, "launch": "one CUDA-graph replay per step",
+                       "l2": "256 MiB flush write between timed iterations"},
+            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": fuse_host.numel() * 4,
+                    "d2h_bytes_per_step": sum(h.numel() * 4 for h in out_host)},
+            "gpu_launches": int(step.launches), "clocks": clocks,
+            "roofline": {"kernel": "whole decoder step (%.2f GFLOP/frame of dense + attention math)"
+                                   % (decoder_flops_per_frame() / 1e9), "bound": "tensor", "achieved": ach,
+                         "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+                         "traffic": None,
+                         "pipe": "latency / launch-count bound: ~290 small kernels per step, none larger than 30 us"},
+            "cpu_baseline": {"value": ns / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d frames, oracle port of decoder.forward (torch CPU fp32, %d threads)" % (ns, cores)}}))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -623,7 +737,7 @@ def main():
                          "nhwc = torch.channels_last hand-off, SURVEY 8f row f4)")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch path instead of a CUDA-graph replay")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="H2D/compute overlap chunks in the e2e measurement")
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5"],
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5", "decoder"],
                     help="cfg3 = hot path at 128 frames/GPU (default, the driver's contract); cfg2 = SA microbench; "
                          "cfg5 = training step (use --frames 64)")
     ap.add_argument("--clouds", type=int, default=64, help="cfg2: number of clouds")
@@ -639,6 +753,8 @@ def main():
         run_reference(args)
     elif args.workload == "cfg2":
         run_cfg2(args)
+    elif args.workload == "decoder":
+        run_decoder(args)
     else:
         run_ours(args)
 

@@ -191,7 +191,11 @@ class decoder(nn.Module):
 
     def _linear(self, x, w, b=None, act=L.ACT_NONE):
         if self.precision != "fp32" and x.shape[0] >= 1024 and min(w.shape) >= 16:
-            return ops.linear_tc(x, w, b, act=act, split=True)
+            key = ("tc", w.data_ptr(), b.data_ptr() if b is not None else 0)     # weight image packed once
+            packed = self._cache.get(key)
+            if packed is None:
+                packed = self._cache[key] = ops.pack_linear_tc(w, b, split=True) + (w, b)   # keep w / b alive
+            return ops.linear_tc(x, None, None, act=act, packed=packed[:5])
         return ops.linear(x, w, b, act=act)
 
     def _graph_layer(self, x, li, side, V):

@@ -478,21 +478,32 @@ def _tile_desc(n):
     return [(128 * i, min(128, n - 128 * i), 0) for i in range((n + 127) // 128)]
 
 
-def linear_tc(x, w, bias=None, act=L.ACT_NONE, split=True):
+def pack_linear_tc(w, bias=None, split=True):
+    """Pre-pack a weight [N,K] (device, fp32) for linear_tc: (bf16 tile image, bias padded to whole
+    N-tiles, N, K, split).  Inference code packs once and reuses it; training re-packs every call."""
+    N, K = _rows(w).shape
+    nt = (N + 127) // 128
+    w_img = rows_to_image(w, 0, K, split=2 if split else 0)
+    b = torch.zeros((nt * 128,), dtype=torch.float32, device=w.device)
+    if bias is not None:
+        b[:N] = bias
+    return (w_img, b, N, K, split)
+
+
+def linear_tc(x, w, bias=None, act=L.ACT_NONE, split=True, packed=None):
     """act(x @ w.T + bias) on the tcgen05 GEMM.  split=True: split-bf16 operands (three bf16 products
     per fp32 product: fp32-accurate, ~2^-16 relative); split=False: plain bf16 operands, fp32
-    accumulate.  x [M,K] fp32 rows, w [N,K] fp32 (device).
+    accumulate.  x [M,K] fp32 rows, w [N,K] fp32 (device) or ``packed`` = pack_linear_tc(w, bias, split).
     Returns a [M,N] view of a buffer whose row pitch is padded to a multiple of 4."""
     L.require_cuda(x, w, bias)
-    M, K = _rows(x).shape
-    N = _rows(w).shape[0]
+    if packed is None:
+        packed = pack_linear_tc(w, bias, split)
+    w_img, b, N, K, split = packed
+    M = _rows(x).shape[0]
+    assert x.shape[1] == K
     kb = (3 if split else 1) * ((K + 63) // 64)
     nt = (N + 127) // 128
     x_img = rows_to_image(x, 0, K, split=1 if split else 0)
-    w_img = rows_to_image(w, 0, K, split=2 if split else 0)
-    b = torch.zeros((nt * 128,), dtype=torch.float32, device=x.device)
-    if bias is not None:
-        b[:N] = bias
     out = torch.empty((M, _pad4(N)), dtype=torch.float32, device=x.device)
     gemm_bf16(x_img, (M + 127) // 128, kb, w_img, nt, kb, kb, b, act=act, out_f32=out, rows_valid=M,
               tile_desc=_tile_desc(N))
