@@ -145,8 +145,8 @@ def run_reference(args):
 
 def workload_name(args):
     return ("cfg3-hotpath: %d frames/GPU x 2 hands, %dx%d depth, 1024-pt clouds, N1=512 N2=128 K=64 r2=(0.015,0.04); "
-            "depth2pcl+pyramid gather/SFT+SA1+SA2+global MLP+fusion SFT+mano_head+Split_coeff+LBS"
-            % (args.frames, args.res, args.res))
+            "depth2pcl+pyramid gather/SFT+SA1+SA2+global MLP+fusion SFT+mano_head+Split_coeff+LBS%s"
+            % (args.frames, args.res, args.res, "+GCN decoder" if getattr(args, "with_decoder", False) else ""))
 
 
 class ClockSampler(object):
@@ -215,6 +215,14 @@ def run_ours(args):
     mano_l = ManoLayer(tables["left"], center_idx=None).to(dev)
     mano_r = ManoLayer(tables["right"], center_idx=None).to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    dec = None
+    if args.with_decoder:                             # the GCN decoder consuming fuse_feat
+        from pdfnet_b200.decoder import decoder
+        from pdfnet_b200 import synth
+        assets = dict(np.load(os.path.join(ROOT, "tests", "golden", "gcn_assets.npz")))
+        dec = decoder(assets, precision="fp32" if args.precision == "fp32" else "bf16x3")
+        dec.load_state_dict(synth.decoder_state(317, assets["upsample"]))
+        dec = dec.to(dev).eval()
 
     def hot_path(d):
         with profiling.stage("depth2pcl"):
@@ -222,6 +230,10 @@ def run_ours(args):
         fused, theta = model(cloud, [d["l0"], d["l1"], d["l2"]], choose, d["center"], with_mano=True)
         with profiling.stage("mano_tail"):
             verts, joints, _ = mano_tail_pair(theta, d["ind"], d["K"], mano_l, mano_r, input_res=R)
+        if dec is not None:
+            with profiling.stage("gcn_decoder"):
+                result, _, _, _ = dec(fused[:, 0], fused[:, 1], None)
+            return fused, verts, joints, result["verts3d"]["left"], result["verts3d"]["right"]
         return fused, verts, joints
 
     def barrier():
@@ -257,7 +269,7 @@ def run_ours(args):
         # the same ~30 kernels replayed as one CUDA graph (no Python / ctypes launch cost in the step)
         from pdfnet_b200.graph import CapturedStep
         step = CapturedStep(lambda: hot_path(resident))
-        assert step.launches == launches, (step.launches, launches)
+        launches = step.launches                      # exact: the kernels inside the captured step
         ms_dev, graphed = timed_loop(step.replay, args.steps, args.warmup), True
     clocks = sampler.stop() if rank == 0 else None
 
@@ -271,6 +283,12 @@ def run_ours(args):
 
     staging = {k: torch.empty_like(resident[k]) for k in pinned}
 
+    chunk_steps = None
+    if not args.no_graph:                             # one captured graph per chunk, over slices of the staging buffers
+        from pdfnet_b200.graph import CapturedStep
+        chunk_steps = [CapturedStep(lambda lo=lo, hi=hi: hot_path({k: v[lo:hi] for k, v in staging.items()}), warmup=2)
+                       for lo, hi in bounds]
+
     def e2e_step():
         main = torch.cuda.current_stream()
         copy_stream.wait_stream(main)                 # previous step has consumed the staging buffers
@@ -282,10 +300,10 @@ def run_ours(args):
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 events.append(ev)
-        for (lo, hi), ev in zip(bounds, events):
+        for ci, ((lo, hi), ev) in enumerate(zip(bounds, events)):
             main.wait_event(ev)
-            fused, verts, joints = hot_path({k: v[lo:hi] for k, v in staging.items()})
-            for name, t in (("fused", fused), ("verts", verts), ("joints", joints)):
+            outs = chunk_steps[ci].replay() if chunk_steps else hot_path({k: v[lo:hi] for k, v in staging.items()})
+            for name, t in zip(("fused", "verts", "joints", "gcn_left", "gcn_right"), outs):
                 if name not in out_host:
                     out_host[name] = torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
                 out_host[name][lo:hi].copy_(t, non_blocking=True)
@@ -735,6 +753,8 @@ def main():
     ap.add_argument("--pyramid-layout", default="nchw", choices=["nchw", "nhwc"],
                     help="memory format of the RGB feature pyramid inputs (nchw = what the reference neck emits; "
                          "nhwc = torch.channels_last hand-off, SURVEY 8f row f4)")
+    ap.add_argument("--with-decoder", action="store_true",
+                    help="cfg3: also run the GCN decoder (SURVEY 8f row f3) on the fused features inside the step")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch path instead of a CUDA-graph replay")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="H2D/compute overlap chunks in the e2e measurement")
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5", "decoder"],
