@@ -305,3 +305,40 @@ class decoder(nn.Module):
             paramsDict = {"scale": scale, "trans2d": trans2d, "root": root}
             handDictList = [{"verts3d": verts3d, "verts2d": verts2d}]
             return result, paramsDict, handDictList, other
+
+
+def assets_from_graph_dicts(left_graph_dict, right_graph_dict, dense_coor, upsample_weight=None, vertex_num=778):
+    """The ``assets`` dict from the objects ``load_decoder`` un-pickles (intaghand_decoder.py:244-258):
+    ``gcn_core/graph_{left,right}.pkl`` dicts (scipy-sparse ``coarsen_graphs_L`` fine-to-coarse,
+    ``graph_perm``, ``graph_perm_reverse``), ``v_color.pkl`` and ``upsample.pkl``."""
+    assets = {"dense_coor": np.asarray(dense_coor, dtype=np.float32)}
+    if upsample_weight is not None:
+        assets["upsample"] = np.asarray(upsample_weight, dtype=np.float32)
+    for side, gd in (("left", left_graph_dict), ("right", right_graph_dict)):
+        coarse_first = list(gd["coarsen_graphs_L"])[::-1]                 # decoder.__init__ reverses the list (:96-97)
+        for i in range(3):
+            Lm = coarse_first[i]
+            assets["L_%s_%d" % (side, i)] = np.asarray(Lm.todense() if hasattr(Lm, "todense") else Lm, dtype=np.float32)
+        assets["graph_perm_" + side] = np.asarray(gd["graph_perm"], dtype=np.int64)
+        assets["graph_perm_reverse_" + side] = np.asarray(gd["graph_perm_reverse"], dtype=np.int64)[:vertex_num]
+    return assets
+
+
+def load_decoder(cfg, encoder_info, precision="bf16x3"):
+    """Drop-in for ``intaghand_decoder.load_decoder(cfg, encoder_info)`` (:244-277): reads the reference's own
+    ``gcn_core`` pickles through the reference module's path helpers and returns the B200 decoder."""
+    import importlib
+    import pickle
+    rdec = importlib.import_module("lib.models.networks.intaghand_decoder")
+    paths = rdec.get_graph_dict_path()
+    with open(paths["left"], "rb") as f:
+        left = pickle.load(f)
+    with open(paths["right"], "rb") as f:
+        right = pickle.load(f)
+    with open(rdec.get_dense_color_path(), "rb") as f:
+        dense = pickle.load(f)
+    with open(rdec.get_upsample_path(), "rb") as f:
+        up = pickle.load(f)
+    return decoder(assets_from_graph_dicts(left, right, dense, up), global_feature_dim=encoder_info["global_feature_dim"],
+                   gcn_in_dim=cfg.GCN_IN_DIM, gcn_out_dim=cfg.GCN_OUT_DIM, graph_k=cfg.graph_k,
+                   graph_layer_num=cfg.graph_layer_num, precision=precision)

@@ -9,13 +9,16 @@ import importlib
 
 def patch_reference():
     """Requires the reference to be importable (``lib`` on sys.path).  Returns the list of patched names."""
-    from . import encoder, grouping, manolayer
+    from . import decoder, encoder, grouping, manolayer
     patched = []
     ru = importlib.import_module("lib.utils.utils")
     rmu = importlib.import_module("lib.models.utils")
     renc = importlib.import_module("lib.models.networks.intaghand_encoder")
     rml = importlib.import_module("lib.models.networks.manolayer")
+    rdec = importlib.import_module("lib.models.networks.intaghand_decoder")
+    rmodel = importlib.import_module("lib.models.networks.intaghand_model")
     for mod, name, new in (
+        (rdec, "load_decoder", decoder.load_decoder), (rmodel, "load_decoder", decoder.load_decoder),
         (ru, "group_points", grouping.group_points), (ru, "group_points_2", grouping.group_points_2),
         (ru, "get_points_coordinate", encoder.get_points_coordinate),
         (rmu, "_tranpose_and_gather_feat", encoder._tranpose_and_gather_feat),

@@ -2,6 +2,7 @@
 host-side logic (BN folding, weight packing, padding, sharding), and loud failure without CUDA."""
 import os
 import re
+import sys
 import types
 
 import numpy as np
@@ -171,3 +172,42 @@ def test_shard_range_covers_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_patch_reference_rebinds_every_boundary_name(monkeypatch):
+    """patch_reference() swaps the names of SURVEY 8b inside (stand-ins for) the reference's modules."""
+    import types
+    import pdfnet_b200
+    names = ["lib", "lib.utils", "lib.utils.utils", "lib.models", "lib.models.utils", "lib.models.networks",
+             "lib.models.networks.intaghand_encoder", "lib.models.networks.manolayer",
+             "lib.models.networks.intaghand_decoder", "lib.models.networks.intaghand_model"]
+    for n in names:
+        monkeypatch.setitem(sys.modules, n, types.ModuleType(n))
+    patched = pdfnet_b200.patch_reference()
+    enc = sys.modules["lib.models.networks.intaghand_encoder"]
+    from pdfnet_b200 import decoder, encoder, grouping, manolayer
+    assert enc.PointNet_Plus is encoder.PointNet_Plus and enc.SFTLayer is encoder.SFTLayer
+    assert enc.group_points is grouping.group_points and enc.depth2pcl is encoder.depth2pcl
+    assert sys.modules["lib.models.networks.manolayer"].ManoLayer is manolayer.ManoLayer
+    assert sys.modules["lib.models.networks.intaghand_model"].load_decoder is decoder.load_decoder
+    assert len(patched) == 13
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/lib/models/networks/gcn_core"), reason="reference assets absent")
+def test_decoder_assets_from_reference_pickles_match_fixture():
+    """assets_from_graph_dicts (what the drop-in load_decoder builds from gcn_core/*.pkl) == tests/golden/gcn_assets.npz."""
+    import pickle
+    import warnings
+    from pdfnet_b200.decoder import assets_from_graph_dicts, decoder
+    base = "/root/reference/lib/models/networks/gcn_core/"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        objs = [pickle.load(open(base + n, "rb")) for n in ("graph_left.pkl", "graph_right.pkl", "v_color.pkl", "upsample.pkl")]
+    assets = assets_from_graph_dicts(*objs)
+    fixture = dict(np.load(os.path.join(ROOT, "tests", "golden", "gcn_assets.npz")))
+    assert sorted(assets) == sorted(fixture)
+    for k in fixture:
+        np.testing.assert_array_equal(assets[k], fixture[k], err_msg=k)
+    m = decoder(assets)
+    assert m.verts == [63, 126, 252] and m.vNum_all == 1008
+    assert int(m._L_left_2_rowptr[-1]) == 1546            # nnz of the 252-vertex Laplacian
