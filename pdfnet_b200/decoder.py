@@ -151,6 +151,7 @@ class decoder(nn.Module):
         if "upsample" in assets:
             self.unsample_layer.weight.data.copy_(torch.as_tensor(np.asarray(assets["upsample"])))
         self._cache, self._cache_key = {}, None
+        self._side = None
 
     def get_upsample_weight(self):
         return self.unsample_layer.weight.data
@@ -233,19 +234,18 @@ class decoder(nn.Module):
         x2, h2 = ops.row_combine(x, g, ln=self._ln(sa.ff.layer_norm), want_sum=True)
         return x2, self._mlp(h2, sa.ff)
 
-    def _inter_attn(self, xl, xr, li, n, V):
-        """-> ((xL, fL), (xR, fR)) with outputs Lf = xL + fL, Rf = xR + fR (adds deferred)."""
+    def _inter_attn(self, l2, lf, r2, rf, li, n, V):
+        """Cross attention after the two SelfAttn blocks (given as deferred sums l2 + lf, r2 + rf)
+        -> ((xL, fL), (xR, fR)) with outputs Lf = xL + fL, Rf = xR + fR (adds deferred)."""
         c = self._weights()
         a = self.dual_gcn.layers[li].attn
-        f, M = xl.shape[1], xl.shape[0]
-        l2, lf = self._self_attn(xl, li, "L", a.L_self_attn_layer, n, V)
-        r2, rf = self._self_attn(xr, li, "R", a.R_self_attn_layer, n, V)
-        both = torch.empty((2 * M, f), dtype=torch.float32, device=xl.device)               # [LN1(Lf) ; LN2(Rf)]
+        f, M = l2.shape[1], l2.shape[0]
+        both = torch.empty((2 * M, f), dtype=torch.float32, device=l2.device)               # [LN1(Lf) ; LN2(Rf)]
         Lf, _ = ops.row_combine(l2, lf, ln=self._ln(a.layer_norm1), want_sum=True, ln_out=both[:M])
         Rf, _ = ops.row_combine(r2, rf, ln=self._ln(a.layer_norm2), want_sum=True, ln_out=both[M:])
         qkv = self._linear(both, c[(li, "X", "qkv_w")], c[(li, "X", "qkv_b")])            # shared projections
         q, k, v = qkv[:, :f], qkv[:, f:2 * f], qkv[:, 2 * f:]
-        att = torch.empty((2 * M, f), dtype=torch.float32, device=xl.device)
+        att = torch.empty((2 * M, f), dtype=torch.float32, device=l2.device)
         ops.mha(q[:M], k[M:], v[M:], n, V, self.heads, out=att[:M])                         # R2L: left queries, right keys/values
         ops.mha(q[M:], k[:M], v[:M], n, V, self.heads, out=att[M:])                         # L2R
         feat = self._linear(att, a.fc.weight.detach(), a.fc.bias.detach())
@@ -271,10 +271,23 @@ class decoder(nn.Module):
                 # Lf = cat([g repeated over the 63 vertices, pe], -1) + position embedding (:197-198, DualGraph.py:76-80)
                 x[side], _ = ops.row_combine(gpad, rowvec=c[("row0", side)], V_out=self.verts[0], up=self.verts[0],
                                              want_sum=True)
+            cur = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream()
             for li, V in enumerate(self.verts):
+                # the two hands are independent up to the cross attention: the right hand's GraphLayer and
+                # SelfAttn run on a second stream (captured as a fork / join inside a CUDA graph)
+                att = self.dual_gcn.layers[li].attn
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    xr = self._graph_layer(x["right"], li, "right", V)
+                    r2, rf = self._self_attn(xr, li, "R", att.R_self_attn_layer, B, V)
                 xl = self._graph_layer(x["left"], li, "left", V)
-                xr = self._graph_layer(x["right"], li, "right", V)
-                (al, bl), (ar, br) = self._inter_attn(xl, xr, li, B, V)
+                l2, lf = self._self_attn(xl, li, "L", att.L_self_attn_layer, B, V)
+                cur.wait_stream(self._side)
+                for t in (r2, rf):
+                    t.record_stream(cur)
+                (al, bl), (ar, br) = self._inter_attn(l2, lf, r2, rf, li, B, V)
                 if li != 2:                                    # add + graph_upsample(., 2) + next position embedding
                     pos = self.dual_gcn.layers[li + 1].position_embeddings.weight.detach()
                     x["left"], _ = ops.row_combine(al, bl, rowvec=pos, V_out=2 * V, up=2, want_sum=True)
