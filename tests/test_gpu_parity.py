@@ -1056,3 +1056,70 @@ def test_gcn_decoder_tensor_core_and_batch():
     part = _decoder_outputs(m32(fl[5:9], fr[5:9], None))
     for k in full:
         assert rel_err(part[k].cpu().numpy(), full[k][5:9].cpu().numpy()) < 1e-5, k
+
+
+def test_decoder_primitives_vs_torch():
+    """row_combine / graph_cheby_ln / mha / decoder_project against torch-CPU on ragged shapes."""
+    import torch.nn.functional as F
+    from pdfnet_b200 import ops
+    from pdfnet_b200.decoder import _csr
+    gen = torch.Generator().manual_seed(21)
+    rnd = lambda *s: torch.randn(s, generator=gen)
+    # residual + row vector + x2 up-sampling + LayerNorm (+ReLU), C not a multiple of 32
+    n, V, C = 5, 6, 70
+    a, b, rv = rnd(n * V, C), rnd(n * V, C), rnd(2 * V, C)
+    gamma, beta = rnd(C), rnd(C)
+    t_ref = (a + b).view(n, V, C).repeat_interleave(2, dim=1) + rv
+    ln_ref = F.relu(F.layer_norm(t_ref, (C,), gamma, beta, 1e-6))
+    s_out, l_out = ops.row_combine(a.to(DEV), b.to(DEV), rowvec=rv.to(DEV), V_out=2 * V, up=2,
+                                   ln=(gamma.to(DEV), beta.to(DEV)), relu=True, want_sum=True)
+    np.testing.assert_allclose(s_out.cpu().numpy(), t_ref.reshape(-1, C).numpy(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(l_out.cpu().numpy(), ln_ref.reshape(-1, C).numpy(), rtol=1e-4, atol=1e-5)
+    # Chebyshev graph term + shortcut + LayerNorm, wide rows (C = 600 > 512), sparse random Laplacian
+    V, C = 17, 600
+    Ld = rnd(V, V) * (torch.rand((V, V), generator=gen) < 0.3)
+    U, R = rnd(n * V, 2 * C), rnd(n * V, C)
+    bias, bias_r, gamma, beta = rnd(C), rnd(C), rnd(C), rnd(C)
+    t_ref = U[:, :C] + bias + torch.einsum("vu,buc->bvc", Ld, U[:, C:].view(n, V, C)).reshape(-1, C) + R + bias_r
+    ref = F.layer_norm(t_ref, (C,), gamma, beta, 1e-6)
+    Ud = U.to(DEV)
+    got = ops.graph_cheby_ln(Ud[:, :C], Ud[:, C:], bias.to(DEV), tuple(t.to(DEV) for t in _csr(Ld.numpy())), V,
+                             (gamma.to(DEV), beta.to(DEV)), False, R=R.to(DEV), bias_r=bias_r.to(DEV))
+    np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=2e-5)
+    # attention: every head size, token counts on both sides of the 32-key lane groups, cross q vs k/v
+    for V, heads, d in ((63, 4, 64), (126, 4, 32), (252, 4, 16), (1, 2, 16), (33, 1, 32)):
+        f = heads * d
+        q, k, v = rnd(n * V, f), rnd(n * V, f), rnd(n * V, f)
+        sh = lambda t: t.view(n, V, heads, d).transpose(1, 2)
+        ref = torch.matmul(F.softmax(torch.matmul(sh(q), sh(k).transpose(-1, -2)) / d ** 0.5, -1), sh(v))
+        ref = ref.transpose(1, 2).reshape(n * V, f)
+        got = ops.mha(q.to(DEV), k.to(DEV), v.to(DEV), n, V, heads)
+        np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=2e-6, err_msg=str((V, heads, d)))
+    with pytest.raises(RuntimeError):
+        ops.mha(rnd(300, 32).to(DEV), rnd(300, 32).to(DEV), rnd(300, 32).to(DEV), 1, 300, 2)     # > 256 tokens
+    # projection + MANO-order lists
+    B, Vc, Vd, rep = 3, 12, 20, 4
+    vc, vd, params = rnd(B, Vc, 3), rnd(B, Vd, 3), rnd(B, 3)
+    rev = torch.randint(0, Vc * rep, (Vd,), generator=gen)
+    c2, d2, m3, m2 = ops.decoder_project(vc.to(DEV), vd.to(DEV), params.to(DEV), 384, rev.to(DEV), rep)
+    proj = lambda v: O.projection_batch(params[:, 0], params[:, 1:], v, 384)
+    up = vc.repeat_interleave(rep, dim=1)[:, rev]
+    for got, want in ((c2, proj(vc)), (d2, proj(vd)), (m3, up), (m2, proj(up))):
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-4)
+
+
+def test_gcn_decoder_single_frame_and_errors():
+    """B = 1 (every GEMM below the tensor-core row threshold even in bf16x3 mode) equals the fp32 path;
+    wrong feature width and train mode fail loudly."""
+    m, _ = _decoder("bf16x3")
+    m32, _ = _decoder("fp32")
+    fuse = torch.randn((1, 2, 1024), generator=torch.Generator().manual_seed(73)).to(DEV)
+    a = _decoder_outputs(m(fuse[:, 0], fuse[:, 1], None))
+    b = _decoder_outputs(m32(fuse[:, 0], fuse[:, 1], None))
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    with pytest.raises(AssertionError):
+        m32(fuse[:, 0, :512], fuse[:, 1, :512], None)
+    with pytest.raises(NotImplementedError):
+        m32.train()(fuse[:, 0], fuse[:, 1], None)
+    with pytest.raises(RuntimeError):
+        m32.eval()(fuse[:, 0].cpu(), fuse[:, 1].cpu(), None)
