@@ -762,6 +762,16 @@ def main():
                          "cfg5 = training step (use --frames 64)")
     ap.add_argument("--clouds", type=int, default=64, help="cfg2: number of clouds")
     args = ap.parse_args()
+    if args.gpus > 1 and "RANK" not in os.environ and args.impl == "ours" and args.workload != "cfg2":
+        # launched without torchrun: start one rank per GPU ourselves (same command line the driver uses)
+        import socket
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
     if args.frames is None:
         args.frames = 64 if args.workload == "cfg5" else 128
     if args.precision is None:
