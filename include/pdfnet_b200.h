@@ -339,19 +339,23 @@ int pdf_gather_nchw_bwd(const float* dOut, const int64_t* ind, int64_t n_clouds,
 /* t = a[src] (+ b[src]) (+ rowvec[v]) for output row (sample, v), src = sample*(V_out/up) + v/up
  * (up = 2 is graph_upsample, DualGraph.py:11-18; rowvec is the position embedding, :76-80);
  * writes t to sum_out and/or LayerNorm(t)*gamma+beta (+ReLU) to ln_out (nn.LayerNorm, eps inside the
- * sqrt; gcn.py:92-98, self_attn.py:20,55).  C <= 1024. */
+ * sqrt; gcn.py:92-98, self_attn.py:20,55).  C <= 1024.  sum_img / ln_img (optional, C % 64 == 0): the
+ * same rows written as a split-bf16 tile image ([hi|hi|lo], 3*C/64 k-blocks per row-tile, as
+ * pdf_rows_to_image(split=1) would produce), i.e. directly as the next GEMM's operand. */
 int pdf_row_combine(const float* a, int64_t lda, const float* b, int64_t ldb, const float* rowvec, int64_t ldr,
                     int V_out, int up, int C, int64_t rows_out, const float* gamma, const float* beta, float eps,
-                    int relu, float* sum_out, int64_t lds, float* ln_out, int64_t ldl, void* stream);
+                    int relu, float* sum_out, int64_t lds, float* ln_out, int64_t ldl, void* sum_img, void* ln_img,
+                    void* stream);
 /* Second half of a K = 2 Chebyshev graph convolution fused with the LayerNorm that follows
  * (graph_conv_cheby gcn.py:34-69, GCN_ResBlock.forward :100-110): with U = x [W0;W1]^T already
  * computed by a GEMM (W0 = fc.weight[:, 0::2], W1 = fc.weight[:, 1::2]),
  *   t = U0 + bias + L.U1 (+ R + bias_r),  out = LayerNorm(t) (+ReLU);
- * L [V,V] in CSR (rowptr int32 [V+1], colidx, vals); R is the shortcut branch (:108). */
+ * L [V,V] in CSR (rowptr int32 [V+1], colidx, vals); R is the shortcut branch (:108).  out (fp32 rows)
+ * and/or out_img (split-bf16 tile image, C % 64 == 0) receive the result. */
 int pdf_graph_cheby_ln(const float* U0, const float* U1, int64_t ldu, const float* bias, const float* R, int64_t ldr,
                        const float* bias_r, const int32_t* rowptr, const int32_t* colidx, const float* vals, int V,
                        int C, int64_t rows, const float* gamma, const float* beta, float eps, int relu, float* out,
-                       int64_t ldo, void* stream);
+                       int64_t ldo, void* out_img, void* stream);
 /* softmax(q k^T / sqrt(d)) v per (sample, head) (self_attn.py:60-72, inter_attn.py:84-108); q/k/v/out
  * rows [n_samples*V, heads*d] with free pitches (q and k/v may come from different hands).
  * V <= 256, d in {16, 32, 64}. */

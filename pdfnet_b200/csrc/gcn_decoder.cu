@@ -10,6 +10,7 @@
 //   mha           : softmax(q k^T / sqrt(d)) v for one (sample, head) per CTA, V <= 256 tokens
 //   decoder_project: orthographic projection + GCN -> MANO vertex order (graph_upsample + GCN_to_vert)
 #include "pdf_common.cuh"
+#include "umma.cuh"
 
 #include <type_traits>
 
@@ -28,11 +29,10 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// LayerNorm of the lane-distributed row t[0..n) (element i of lane l is channel l + 32 i), two-pass
+// LayerNorm (in place) of the lane-distributed row t[0..n) (element i of lane l is channel l + 32 i), two-pass
 template <int NPL>
 __device__ __forceinline__ void layer_norm_row(float (&t)[NPL], int C, int lane, const float* __restrict__ gamma,
-                                               const float* __restrict__ beta, float eps, int relu,
-                                               float* __restrict__ out) {
+                                               const float* __restrict__ beta, float eps, int relu) {
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NPL; ++i) if (lane + 32 * i < C) s += t[i];
@@ -45,11 +45,47 @@ __device__ __forceinline__ void layer_norm_row(float (&t)[NPL], int C, int lane,
   for (int i = 0; i < NPL; ++i) {
     const int c = lane + 32 * i;
     if (c < C) {
-      float y = fmaf((t[i] - mean) * rstd, gamma[c], beta[c]);
-      if (relu) y = fmaxf(y, 0.f);
-      out[c] = y;
+      const float y = fmaf((t[i] - mean) * rstd, gamma[c], beta[c]);
+      t[i] = relu ? fmaxf(y, 0.f) : y;
     }
   }
+}
+
+template <int NPL>
+__device__ __forceinline__ void store_row(const float (&t)[NPL], int C, int lane, float* __restrict__ out) {
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) if (lane + 32 * i < C) out[lane + 32 * i] = t[i];
+}
+
+// Row r of a split-bf16 tile image ([hi | hi | lo] k-blocks, the M operand pdf_gemm_bf16 expects): the producing
+// kernel writes the next GEMM's operand directly instead of fp32 rows + a pdf_rows_to_image pass.
+// C % 64 == 0; stage = this warp's C floats of shared memory.
+template <int NPL>
+__device__ __forceinline__ void store_split_image(const float (&t)[NPL], int C, int lane, float* stage,
+                                                  uint8_t* __restrict__ img, int64_t r) {
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) if (lane + 32 * i < C) stage[lane + 32 * i] = t[i];
+  __syncwarp();
+  const int nkb = C >> 6;
+  uint8_t* base = img + (size_t)(r >> 7) * (size_t)(3 * nkb) * 16384;
+  const uint32_t rr = (uint32_t)(r & 127);
+  for (int q = lane; q < (C >> 3); q += 32) {
+    const float4 a = *reinterpret_cast<const float4*>(stage + q * 8);
+    const float4 b = *reinterpret_cast<const float4*>(stage + q * 8 + 4);
+    uint4 w, wl;
+    w.x = umma::pack_bf16(a.x, a.y); w.y = umma::pack_bf16(a.z, a.w);
+    w.z = umma::pack_bf16(b.x, b.y); w.w = umma::pack_bf16(b.z, b.w);
+    wl.x = umma::pack_bf16(a.x - __uint_as_float(w.x << 16), a.y - __uint_as_float(w.x & 0xffff0000u));
+    wl.y = umma::pack_bf16(a.z - __uint_as_float(w.y << 16), a.w - __uint_as_float(w.y & 0xffff0000u));
+    wl.z = umma::pack_bf16(b.x - __uint_as_float(w.z << 16), b.y - __uint_as_float(w.z & 0xffff0000u));
+    wl.w = umma::pack_bf16(b.z - __uint_as_float(w.w << 16), b.w - __uint_as_float(w.w & 0xffff0000u));
+    const int kb = q >> 3;
+    const uint32_t off = umma::sw128_off(rr, (uint32_t)(q & 7) * 8);
+    *reinterpret_cast<uint4*>(base + (size_t)kb * 16384 + off) = w;
+    *reinterpret_cast<uint4*>(base + (size_t)(nkb + kb) * 16384 + off) = w;
+    *reinterpret_cast<uint4*>(base + (size_t)(2 * nkb + kb) * 16384 + off) = wl;
+  }
+  __syncwarp();
 }
 
 // one warp per output row r' = (sample, v'); source row = sample * (V_out / up) + v' / up
@@ -58,8 +94,11 @@ __global__ void __launch_bounds__(256)
 row_combine_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
                    const float* __restrict__ rowvec, int64_t ldr, int V_out, int up, int C, int64_t rows_out,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
-                   float* __restrict__ sum_out, int64_t lds, float* __restrict__ ln_out, int64_t ldl) {
+                   float* __restrict__ sum_out, int64_t lds, float* __restrict__ ln_out, int64_t ldl,
+                   uint8_t* __restrict__ sum_img, uint8_t* __restrict__ ln_img) {
+  extern __shared__ __align__(16) float stage_all[];
   const int lane = threadIdx.x & 31;
+  float* stage = stage_all + (threadIdx.x >> 5) * C;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (r >= rows_out) return;
   const int64_t smp = r / V_out;
@@ -75,10 +114,15 @@ row_combine_kernel(const float* __restrict__ a, int64_t lda, const float* __rest
       if (b) x += b[src * ldb + c];
       if (rowvec) x += rowvec[(int64_t)v * ldr + c];
       t[i] = x;
-      if (sum_out) sum_out[r * lds + c] = x;
     }
   }
-  if (ln_out) layer_norm_row<NPL>(t, C, lane, gamma, beta, eps, relu, ln_out + r * ldl);
+  if (sum_out) store_row<NPL>(t, C, lane, sum_out + r * lds);
+  if (sum_img) store_split_image<NPL>(t, C, lane, stage, sum_img, r);
+  if (ln_out || ln_img) {
+    layer_norm_row<NPL>(t, C, lane, gamma, beta, eps, relu);
+    if (ln_out) store_row<NPL>(t, C, lane, ln_out + r * ldl);
+    if (ln_img) store_split_image<NPL>(t, C, lane, stage, ln_img, r);
+  }
 }
 
 // t = U0[row] + bias + sum_u L[v,u] U1[sample, u] (+ R[row] + bias_r); out = LayerNorm(t) (+ReLU)
@@ -89,8 +133,10 @@ graph_cheby_ln_kernel(const float* __restrict__ U0, const float* __restrict__ U1
                       const float* __restrict__ bias_r, const int* __restrict__ rowptr,
                       const int* __restrict__ colidx, const float* __restrict__ vals, int V, int C, int64_t rows,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
-                      float* __restrict__ out, int64_t ldo) {
+                      float* __restrict__ out, int64_t ldo, uint8_t* __restrict__ out_img) {
+  extern __shared__ __align__(16) float stage_all[];
   const int lane = threadIdx.x & 31;
+  float* stage = stage_all + (threadIdx.x >> 5) * C;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (r >= rows) return;
   const int64_t smp = r / V;
@@ -116,7 +162,9 @@ graph_cheby_ln_kernel(const float* __restrict__ U0, const float* __restrict__ U1
       if (c < C) t[i] = fmaf(w, u[c], t[i]);
     }
   }
-  layer_norm_row<NPL>(t, C, lane, gamma, beta, eps, relu, out + r * ldo);
+  layer_norm_row<NPL>(t, C, lane, gamma, beta, eps, relu);
+  if (out) store_row<NPL>(t, C, lane, out + r * ldo);
+  if (out_img) store_split_image<NPL>(t, C, lane, stage, out_img, r);
 }
 
 // one CTA per (sample, head): K and V of that head in shared memory; each warp takes FOUR query rows at a
@@ -271,17 +319,20 @@ using namespace pdf;
 extern "C" int pdf_row_combine(const float* a, int64_t lda, const float* b, int64_t ldb, const float* rowvec,
                                int64_t ldr, int V_out, int up, int C, int64_t rows_out, const float* gamma,
                                const float* beta, float eps, int relu, float* sum_out, int64_t lds, float* ln_out,
-                               int64_t ldl, void* stream) {
+                               int64_t ldl, void* sum_img, void* ln_img, void* stream) {
   if (rows_out == 0) return PDF_OK;
-  PDF_REQUIRE(a && (sum_out || ln_out), PDF_ERR_BAD_ARG, "pdf_row_combine: null pointer");
+  PDF_REQUIRE(a && (sum_out || ln_out || sum_img || ln_img), PDF_ERR_BAD_ARG, "pdf_row_combine: null pointer");
   PDF_REQUIRE(rows_out > 0 && C > 0 && C <= DEC_MAX_C && V_out > 0 && up >= 1 && V_out % up == 0 &&
-                  rows_out % V_out == 0 && (!ln_out || (gamma && beta)),
+                  rows_out % V_out == 0 && (!(ln_out || ln_img) || (gamma && beta)) &&
+                  (!(sum_img || ln_img) || C % 64 == 0),
               PDF_ERR_BAD_ARG, "pdf_row_combine: bad argument");
   const unsigned grid = (unsigned)((rows_out * 32 + 255) / 256);
+  const size_t smem = (sum_img || ln_img) ? (size_t)8 * C * sizeof(float) : 0;
   cudaStream_t s = (cudaStream_t)stream;
   dispatch_npl(C, [&](auto npl) {
-    row_combine_kernel<decltype(npl)::value><<<grid, 256, 0, s>>>(a, lda, b, ldb, rowvec, ldr, V_out, up, C, rows_out,
-                                                                   gamma, beta, eps, relu, sum_out, lds, ln_out, ldl);
+    row_combine_kernel<decltype(npl)::value><<<grid, 256, smem, s>>>(a, lda, b, ldb, rowvec, ldr, V_out, up, C, rows_out,
+                                                                      gamma, beta, eps, relu, sum_out, lds, ln_out, ldl,
+                                                                      (uint8_t*)sum_img, (uint8_t*)ln_img);
     return 0;
   });
   return check_launch("pdf_row_combine");
@@ -290,18 +341,20 @@ extern "C" int pdf_row_combine(const float* a, int64_t lda, const float* b, int6
 extern "C" int pdf_graph_cheby_ln(const float* U0, const float* U1, int64_t ldu, const float* bias, const float* R,
                                   int64_t ldr, const float* bias_r, const int32_t* rowptr, const int32_t* colidx,
                                   const float* vals, int V, int C, int64_t rows, const float* gamma,
-                                  const float* beta, float eps, int relu, float* out, int64_t ldo, void* stream) {
+                                  const float* beta, float eps, int relu, float* out, int64_t ldo, void* out_img,
+                                  void* stream) {
   if (rows == 0) return PDF_OK;
-  PDF_REQUIRE(U0 && U1 && bias && rowptr && colidx && vals && gamma && beta && out, PDF_ERR_BAD_ARG,
+  PDF_REQUIRE(U0 && U1 && bias && rowptr && colidx && vals && gamma && beta && (out || out_img), PDF_ERR_BAD_ARG,
               "pdf_graph_cheby_ln: null pointer");
-  PDF_REQUIRE(rows > 0 && V > 0 && rows % V == 0 && C > 0 && C <= DEC_MAX_C, PDF_ERR_BAD_ARG,
-              "pdf_graph_cheby_ln: bad argument");
+  PDF_REQUIRE(rows > 0 && V > 0 && rows % V == 0 && C > 0 && C <= DEC_MAX_C && (!out_img || C % 64 == 0),
+              PDF_ERR_BAD_ARG, "pdf_graph_cheby_ln: bad argument");
   const unsigned grid = (unsigned)((rows * 32 + 255) / 256);
+  const size_t smem = out_img ? (size_t)8 * C * sizeof(float) : 0;
   cudaStream_t s = (cudaStream_t)stream;
   dispatch_npl(C, [&](auto npl) {
-    graph_cheby_ln_kernel<decltype(npl)::value><<<grid, 256, 0, s>>>(U0, U1, ldu, bias, R, ldr, bias_r, rowptr, colidx,
-                                                                      vals, V, C, rows, gamma, beta, eps, relu, out,
-                                                                      ldo);
+    graph_cheby_ln_kernel<decltype(npl)::value><<<grid, 256, smem, s>>>(U0, U1, ldu, bias, R, ldr, bias_r, rowptr,
+                                                                         colidx, vals, V, C, rows, gamma, beta, eps,
+                                                                         relu, out, ldo, (uint8_t*)out_img);
     return 0;
   });
   return check_launch("pdf_graph_cheby_ln");

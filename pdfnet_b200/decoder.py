@@ -190,49 +190,70 @@ class decoder(nn.Module):
         self._cache, self._cache_key = c, key
         return c
 
-    def _linear(self, x, w, b=None, act=L.ACT_NONE):
-        if self.precision != "fp32" and x.shape[0] >= 1024 and min(w.shape) >= 16:
+    def _tc(self, M):
+        """Rows enough for the tensor-core GEMM path (whose operand images the producers write directly)."""
+        return self.precision != "fp32" and M >= 1024
+
+    def _linear(self, x, w, b=None, act=L.ACT_NONE, x_img=None, M=None):
+        M = x.shape[0] if x is not None else M
+        if self._tc(M) and min(w.shape) >= 16:
             key = ("tc", w.data_ptr(), b.data_ptr() if b is not None else 0)     # weight image packed once
             packed = self._cache.get(key)
             if packed is None:
                 packed = self._cache[key] = ops.pack_linear_tc(w, b, split=True) + (w, b)   # keep w / b alive
-            return ops.linear_tc(x, None, None, act=act, packed=packed[:5])
+            return ops.linear_tc(x, None, None, act=act, packed=packed[:5], x_img=x_img, M=M)
         return ops.linear(x, w, b, act=act)
 
-    def _graph_layer(self, x, li, side, V):
+    def _graph_layer(self, x, x_img, li, side, V, M):
+        """x: fp32 rows or None, x_img: split tile image or None (tensor-core path) -> fp32 rows."""
         c = self._weights()
+        tc = self._tc(M)
         layer = getattr(self.dual_gcn.layers[li], "graph_" + side)
         csr = tuple(getattr(self, "_L_%s_%d_%s" % (side, li, n)) for n in ("rowptr", "colidx", "vals"))
         nb = len(layer.GCN_blocks)
         for bi, blk in enumerate(layer.GCN_blocks):
-            co = blk.fc1.out_features
-            U = self._linear(x, c[(li, side, bi, "in")])                                    # [M, 3*co] = [U0 | U1 | shortcut]
-            y = ops.graph_cheby_ln(U[:, :co], U[:, co:2 * co], blk.fc1.bias.detach(), csr, V,
-                                   (blk.norm2.weight.detach(), blk.norm2.bias.detach()), True)
-            U2 = self._linear(y, c[(li, side, bi, "mid")])                                  # [M, 2*co]
-            x = ops.graph_cheby_ln(U2[:, :co], U2[:, co:], blk.fc2.bias.detach(), csr, V,
-                                   (blk.norm3.weight.detach(), blk.norm3.bias.detach()), bi != nb - 1,
-                                   R=U[:, 2 * co:], bias_r=blk.shortcut.bias.detach())
+            co, last = blk.fc1.out_features, bi == nb - 1
+            U = self._linear(x, c[(li, side, bi, "in")], x_img=x_img, M=M)                  # [M, 3*co] = [U0 | U1 | shortcut]
+            res = ops.graph_cheby_ln(U[:, :co], U[:, co:2 * co], blk.fc1.bias.detach(), csr, V,
+                                     (blk.norm2.weight.detach(), blk.norm2.bias.detach()), True, want_rows=not tc,
+                                     want_img=tc)
+            y, y_img = res if tc else (res, None)
+            U2 = self._linear(y, c[(li, side, bi, "mid")], x_img=y_img, M=M)                # [M, 2*co]
+            img = tc and not last                              # the last block feeds the attention residual: fp32 rows
+            res = ops.graph_cheby_ln(U2[:, :co], U2[:, co:], blk.fc2.bias.detach(), csr, V,
+                                     (blk.norm3.weight.detach(), blk.norm3.bias.detach()), not last,
+                                     R=U[:, 2 * co:], bias_r=blk.shortcut.bias.detach(), want_rows=not img,
+                                     want_img=img)
+            x, x_img = res if img else (res, None)
         return x
 
     @staticmethod
     def _ln(m):
         return (m.weight.detach(), m.bias.detach())
 
-    def _mlp(self, h, ff):
-        f1 = self._linear(h, ff.fc1.weight.detach(), ff.fc1.bias.detach(), L.ACT_RELU)
+    def _mlp(self, h, ff, h_img=None, M=None):
+        f1 = self._linear(h, ff.fc1.weight.detach(), ff.fc1.bias.detach(), L.ACT_RELU, x_img=h_img, M=M)
         return self._linear(f1, ff.fc2.weight.detach(), ff.fc2.bias.detach())
+
+    def _ln_for_gemm(self, a, b, ln, want_sum):
+        """row_combine whose LayerNorm output only feeds a GEMM: fp32 rows on the FFMA path, the split tile
+        image on the tensor-core path.  -> (sum rows or None, ln rows or None, ln image or None)"""
+        if self._tc(a.shape[0]):
+            s_out, _, _, l_img = ops.row_combine(a, b, ln=ln, want_sum=want_sum, ln_rows=False, ln_img=True)
+            return s_out, None, l_img
+        s_out, l_out = ops.row_combine(a, b, ln=ln, want_sum=want_sum)
+        return s_out, l_out, None
 
     def _self_attn(self, x, li, name, sa, n, V):
         """-> (x2, f2) with SelfAttn(x) = x2 + f2; the add is fused into the caller's next kernel."""
         c = self._weights()
-        f = x.shape[1]
-        _, h = ops.row_combine(x, ln=self._ln(sa.layer_norm))
-        qkv = self._linear(h, c[(li, name, "qkv_w")], c[(li, name, "qkv_b")])
+        f, M = x.shape[1], x.shape[0]
+        _, h, h_img = self._ln_for_gemm(x, None, self._ln(sa.layer_norm), False)
+        qkv = self._linear(h, c[(li, name, "qkv_w")], c[(li, name, "qkv_b")], x_img=h_img, M=M)
         a = ops.mha(qkv[:, :f], qkv[:, f:2 * f], qkv[:, 2 * f:], n, V, self.heads)
         g = self._linear(a, sa.fc.weight.detach(), sa.fc.bias.detach())
-        x2, h2 = ops.row_combine(x, g, ln=self._ln(sa.ff.layer_norm), want_sum=True)
-        return x2, self._mlp(h2, sa.ff)
+        x2, h2, h2_img = self._ln_for_gemm(x, g, self._ln(sa.ff.layer_norm), True)
+        return x2, self._mlp(h2, sa.ff, h2_img, M)
 
     def _inter_attn(self, l2, lf, r2, rf, li, n, V):
         """Cross attention after the two SelfAttn blocks (given as deferred sums l2 + lf, r2 + rf)
@@ -240,18 +261,33 @@ class decoder(nn.Module):
         c = self._weights()
         a = self.dual_gcn.layers[li].attn
         f, M = l2.shape[1], l2.shape[0]
-        both = torch.empty((2 * M, f), dtype=torch.float32, device=l2.device)               # [LN1(Lf) ; LN2(Rf)]
-        Lf, _ = ops.row_combine(l2, lf, ln=self._ln(a.layer_norm1), want_sum=True, ln_out=both[:M])
-        Rf, _ = ops.row_combine(r2, rf, ln=self._ln(a.layer_norm2), want_sum=True, ln_out=both[M:])
-        qkv = self._linear(both, c[(li, "X", "qkv_w")], c[(li, "X", "qkv_b")])            # shared projections
+        if self._tc(2 * M) and M % 128 == 0:                   # [LN1(Lf) ; LN2(Rf)] written as ONE operand image
+            both_img = ops.split_image_empty(2 * M, f, l2.device)
+            half = (M // 128) * 3 * (f // 64) * 16384
+            Lf = ops.row_combine(l2, lf, ln=self._ln(a.layer_norm1), want_sum=True, ln_rows=False, ln_img=both_img[:half])[0]
+            Rf = ops.row_combine(r2, rf, ln=self._ln(a.layer_norm2), want_sum=True, ln_rows=False, ln_img=both_img[half:])[0]
+            qkv = self._linear(None, c[(li, "X", "qkv_w")], c[(li, "X", "qkv_b")], x_img=both_img, M=2 * M)
+        else:
+            both = torch.empty((2 * M, f), dtype=torch.float32, device=l2.device)
+            Lf, _ = ops.row_combine(l2, lf, ln=self._ln(a.layer_norm1), want_sum=True, ln_out=both[:M])
+            Rf, _ = ops.row_combine(r2, rf, ln=self._ln(a.layer_norm2), want_sum=True, ln_out=both[M:])
+            qkv = self._linear(both, c[(li, "X", "qkv_w")], c[(li, "X", "qkv_b")])        # shared projections
         q, k, v = qkv[:, :f], qkv[:, f:2 * f], qkv[:, 2 * f:]
         att = torch.empty((2 * M, f), dtype=torch.float32, device=l2.device)
         ops.mha(q[:M], k[M:], v[M:], n, V, self.heads, out=att[:M])                         # R2L: left queries, right keys/values
         ops.mha(q[M:], k[:M], v[:M], n, V, self.heads, out=att[M:])                         # L2R
         feat = self._linear(att, a.fc.weight.detach(), a.fc.bias.detach())
-        x4l, h4l = ops.row_combine(Lf, feat[:M], ln=self._ln(a.ffL.layer_norm), want_sum=True)
-        x4r, h4r = ops.row_combine(Rf, feat[M:], ln=self._ln(a.ffR.layer_norm), want_sum=True)
-        return (x4l, self._mlp(h4l, a.ffL)), (x4r, self._mlp(h4r, a.ffR))
+        x4l, h4l, h4l_img = self._ln_for_gemm(Lf, feat[:M], self._ln(a.ffL.layer_norm), True)
+        x4r, h4r, h4r_img = self._ln_for_gemm(Rf, feat[M:], self._ln(a.ffR.layer_norm), True)
+        return (x4l, self._mlp(h4l, a.ffL, h4l_img, M)), (x4r, self._mlp(h4r, a.ffR, h4r_img, M))
+
+    def _level_input(self, a, b, rowvec, V_out, up):
+        """Input of a DualGraph level (sum + position embedding, x2 up-sampled): it only feeds the first GEMM of
+        the level, so on the tensor-core path it is written as that GEMM's operand image.  -> (rows, image)"""
+        if self._tc(a.shape[0] * up):
+            _, _, s_img, _ = ops.row_combine(a, b, rowvec=rowvec, V_out=V_out, up=up, sum_img=True)
+            return None, s_img
+        return ops.row_combine(a, b, rowvec=rowvec, V_out=V_out, up=up, want_sum=True)[0], None
 
     def forward(self, global_feature_left, global_feature_right, fmaps=None):
         if self.training:
@@ -269,8 +305,7 @@ class decoder(nn.Module):
                 gpad = torch.zeros((B, cin0), dtype=torch.float32, device=g.device)
                 ops.row_combine(g, ln=self._ln(gf[1]), ln_out=gpad[:, :cin0 - 3])
                 # Lf = cat([g repeated over the 63 vertices, pe], -1) + position embedding (:197-198, DualGraph.py:76-80)
-                x[side], _ = ops.row_combine(gpad, rowvec=c[("row0", side)], V_out=self.verts[0], up=self.verts[0],
-                                             want_sum=True)
+                x[side] = self._level_input(gpad, None, c[("row0", side)], self.verts[0], self.verts[0])
             cur = torch.cuda.current_stream()
             if self._side is None:
                 self._side = torch.cuda.Stream()
@@ -280,9 +315,9 @@ class decoder(nn.Module):
                 att = self.dual_gcn.layers[li].attn
                 self._side.wait_stream(cur)
                 with torch.cuda.stream(self._side):
-                    xr = self._graph_layer(x["right"], li, "right", V)
+                    xr = self._graph_layer(x["right"][0], x["right"][1], li, "right", V, B * V)
                     r2, rf = self._self_attn(xr, li, "R", att.R_self_attn_layer, B, V)
-                xl = self._graph_layer(x["left"], li, "left", V)
+                xl = self._graph_layer(x["left"][0], x["left"][1], li, "left", V, B * V)
                 l2, lf = self._self_attn(xl, li, "L", att.L_self_attn_layer, B, V)
                 cur.wait_stream(self._side)
                 for t in (r2, rf):
@@ -290,8 +325,8 @@ class decoder(nn.Module):
                 (al, bl), (ar, br) = self._inter_attn(l2, lf, r2, rf, li, B, V)
                 if li != 2:                                    # add + graph_upsample(., 2) + next position embedding
                     pos = self.dual_gcn.layers[li + 1].position_embeddings.weight.detach()
-                    x["left"], _ = ops.row_combine(al, bl, rowvec=pos, V_out=2 * V, up=2, want_sum=True)
-                    x["right"], _ = ops.row_combine(ar, br, rowvec=pos, V_out=2 * V, up=2, want_sum=True)
+                    x["left"] = self._level_input(al, bl, pos, 2 * V, 2)
+                    x["right"] = self._level_input(ar, br, pos, 2 * V, 2)
                 else:
                     x["left"], _ = ops.row_combine(al, bl, V_out=V, want_sum=True)
                     x["right"], _ = ops.row_combine(ar, br, V_out=V, want_sum=True)

@@ -490,21 +490,23 @@ def pack_linear_tc(w, bias=None, split=True):
     return (w_img, b, N, K, split)
 
 
-def linear_tc(x, w, bias=None, act=L.ACT_NONE, split=True, packed=None):
+def linear_tc(x, w, bias=None, act=L.ACT_NONE, split=True, packed=None, x_img=None, M=None):
     """act(x @ w.T + bias) on the tcgen05 GEMM.  split=True: split-bf16 operands (three bf16 products
     per fp32 product: fp32-accurate, ~2^-16 relative); split=False: plain bf16 operands, fp32
-    accumulate.  x [M,K] fp32 rows, w [N,K] fp32 (device) or ``packed`` = pack_linear_tc(w, bias, split).
+    accumulate.  x [M,K] fp32 rows (or ``x_img`` = its tile image and ``M``), w [N,K] fp32 (device) or
+    ``packed`` = pack_linear_tc(w, bias, split).
     Returns a [M,N] view of a buffer whose row pitch is padded to a multiple of 4."""
     L.require_cuda(x, w, bias)
     if packed is None:
         packed = pack_linear_tc(w, bias, split)
     w_img, b, N, K, split = packed
-    M = _rows(x).shape[0]
-    assert x.shape[1] == K
     kb = (3 if split else 1) * ((K + 63) // 64)
     nt = (N + 127) // 128
-    x_img = rows_to_image(x, 0, K, split=1 if split else 0)
-    out = torch.empty((M, _pad4(N)), dtype=torch.float32, device=x.device)
+    if x_img is None:                                   # otherwise the producer already wrote the operand image
+        M = _rows(x).shape[0]
+        assert x.shape[1] == K
+        x_img = rows_to_image(x, 0, K, split=1 if split else 0)
+    out = torch.empty((M, _pad4(N)), dtype=torch.float32, device=x_img.device)
     gemm_bf16(x_img, (M + 127) // 128, kb, w_img, nt, kb, kb, b, act=act, out_f32=out, rows_valid=M,
               tile_desc=_tile_desc(N))
     return out[:, :N]
@@ -540,10 +542,18 @@ def linear_tn_tc(a, b, split=True):
 
 # ------------------------------------------------------------------------------------------------
 # GCN decoder primitives (gcn_decoder.cu)
+def split_image_empty(rows, C, device):
+    """Uninitialised split-bf16 tile image ([hi|hi|lo]) for a [rows, C] matrix, C % 64 == 0."""
+    assert C % 64 == 0
+    return torch.empty((((rows + 127) // 128) * 3 * (C // 64) * 16384,), dtype=torch.uint8, device=device)
+
+
 def row_combine(a, b=None, rowvec=None, V_out=None, up=1, ln=None, relu=False, want_sum=False, eps=1e-6,
-                ln_out=None):
+                ln_out=None, sum_img=False, ln_img=False, ln_rows=True):
     """t = a[src] (+ b[src]) (+ rowvec[v]); returns (t or None, LayerNorm(t) or None); see pdf_row_combine.
-    ``ln`` = (gamma, beta).  Output rows = a.shape[0] * up."""
+    ``ln`` = (gamma, beta).  Output rows = a.shape[0] * up.  sum_img / ln_img: also (or, with
+    want_sum=False / ln_rows=False, only) write the result as a split-bf16 tile image; an image argument
+    may be a preallocated uint8 view; the return value then is (t, ln, t_image, ln_image)."""
     L.require_cuda(a, b, rowvec, ln_out)
     Ma, C = _rows(a).shape
     rows = Ma * up
@@ -551,26 +561,33 @@ def row_combine(a, b=None, rowvec=None, V_out=None, up=1, ln=None, relu=False, w
         V_out = up
     dev = a.device
     s_out = torch.empty((rows, C), dtype=torch.float32, device=dev) if want_sum else None
-    if ln is not None and ln_out is None:
+    if ln is not None and ln_out is None and ln_rows:
         ln_out = torch.empty((rows, C), dtype=torch.float32, device=dev)
+    s_im = split_image_empty(rows, C, dev) if sum_img is True else (sum_img if sum_img is not False else None)
+    l_im = split_image_empty(rows, C, dev) if ln_img is True else (ln_img if ln_img is not False else None)
     gamma, beta = ln if ln is not None else (None, None)
     L.call("pdf_row_combine", L.ptr(a), a.stride(0), L.ptr(b), b.stride(0) if b is not None else 0, L.ptr(rowvec),
            rowvec.stride(0) if rowvec is not None else 0, V_out, up, C, rows, L.ptr(gamma), L.ptr(beta), float(eps),
-           int(relu), L.ptr(s_out), C, L.ptr(ln_out), ln_out.stride(0) if ln_out is not None else 0, L.stream())
-    return s_out, ln_out
+           int(relu), L.ptr(s_out), C, L.ptr(ln_out), ln_out.stride(0) if ln_out is not None else 0, L.ptr(s_im),
+           L.ptr(l_im), L.stream())
+    if s_im is None and l_im is None:
+        return s_out, ln_out
+    return s_out, ln_out, s_im, l_im
 
 
-def graph_cheby_ln(U0, U1, bias, csr, V, ln, relu, R=None, bias_r=None, eps=1e-6):
-    """LayerNorm(U0 + bias + L.U1 (+ R + bias_r)) (+ReLU); U0/U1 (and R) are column slices of GEMM outputs."""
+def graph_cheby_ln(U0, U1, bias, csr, V, ln, relu, R=None, bias_r=None, eps=1e-6, want_rows=True, want_img=False):
+    """LayerNorm(U0 + bias + L.U1 (+ R + bias_r)) (+ReLU); U0/U1 (and R) are column slices of GEMM outputs.
+    Returns fp32 rows, or (rows or None, split-bf16 tile image) with want_img."""
     L.require_cuda(U0, U1, bias, R)
     rows, C = _rows(U0).shape
     assert U1.stride(0) == U0.stride(0) and U1.shape == U0.shape
     rowptr, colidx, vals = csr
-    out = torch.empty((rows, C), dtype=torch.float32, device=U0.device)
+    out = torch.empty((rows, C), dtype=torch.float32, device=U0.device) if want_rows else None
+    img = split_image_empty(rows, C, U0.device) if want_img else None
     L.call("pdf_graph_cheby_ln", L.ptr(U0), L.ptr(U1), U0.stride(0), L.ptr(bias), L.ptr(R),
            R.stride(0) if R is not None else 0, L.ptr(bias_r), L.ptr(rowptr), L.ptr(colidx), L.ptr(vals), V, C, rows,
-           L.ptr(ln[0]), L.ptr(ln[1]), float(eps), int(relu), L.ptr(out), C, L.stream())
-    return out
+           L.ptr(ln[0]), L.ptr(ln[1]), float(eps), int(relu), L.ptr(out), C, L.ptr(img), L.stream())
+    return (out, img) if want_img else out
 
 
 def mha(q, k, v, n_samples, V, heads, out=None):

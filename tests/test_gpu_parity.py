@@ -1051,6 +1051,15 @@ def test_gcn_decoder_tensor_core_and_batch():
             assert rel_err(v.cpu().numpy(), ref[k].numpy()) < tol, (prec, k, rel_err(v.cpu().numpy(), ref[k].numpy()))
         again = _decoder_outputs(m(fl, fr, None))
         assert all(torch.equal(out[k], again[k]) for k in out)
+    # 128 frames: rows per level are multiples of 128, so the cross-attention operand of both hands is written
+    # as ONE tile image by the two LayerNorm kernels (decoder._inter_attn)
+    fuse = torch.randn((128, 2, 1024), generator=torch.Generator().manual_seed(74))
+    with torch.no_grad():
+        ref = O.gcn_decoder_forward(sd, assets, fuse)
+    m, _ = _decoder("bf16x3")
+    out = _decoder_outputs(m(fuse[:, 0].to(DEV), fuse[:, 1].to(DEV), None))
+    for k, v in out.items():
+        assert rel_err(v.cpu().numpy(), ref[k].numpy()) < 2e-4, (k, rel_err(v.cpu().numpy(), ref[k].numpy()))
     m32, _ = _decoder("fp32")
     full = _decoder_outputs(m32(fl, fr, None))
     part = _decoder_outputs(m32(fl[5:9], fr[5:9], None))
