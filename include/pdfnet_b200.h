@@ -317,6 +317,13 @@ int pdf_sft_modulate_bwd(const float* dout, int64_t ldd, const float* fea, int64
 /* Weight gradient C[N,K] = A[M,N]^T * B[M,K] (A = dY, B = layer input); C is overwritten. */
 int pdf_linear_tn_f32(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int N, int K, float* C,
                       int64_t ldc, void* stream);
+/* Streaming forms of a linear layer with K <= 4 input channels (netR_1[0]: 3 -> 64, intaghand_encoder.py:50)
+ * and of its two gradients (12 B in / 4N B out per row; the 64x64-tile kernels waste 95 % of a tile there):
+ *   mode 0: out[M,N] = A[M,K] * B[N,K]^T + bias      (forward; N % 4 == 0, 16-byte aligned output rows)
+ *   mode 1: out[M,K] = A[M,N] * B[N,K]               (data gradient, A = dY, B = W)
+ *   mode 2: out[N,K] = A[M,N]^T * B[M,K]             (weight gradient, A = dY, B = X; out is overwritten) */
+int pdf_linear_smallk_f32(int mode, const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias,
+                          int64_t M, int N, int K, float* out, int64_t ldo, void* stream);
 /* nn.MaxPool2d over groups of G consecutive rows (intaghand_encoder.py:63,81,99) and its
  * backward: the FIRST maximum of each (group, channel) receives dOut, all other rows 0. */
 int pdf_group_max(const float* Y, int64_t ldy, int G, int64_t groups, int C, float* out, int64_t ldo, void* stream);

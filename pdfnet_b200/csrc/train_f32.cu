@@ -503,3 +503,117 @@ extern "C" int pdf_gather_nchw_bwd(const float* dOut, const int64_t* ind, int64_
   gather_nchw_bwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(dOut, ind, B, C, HW, n, dFeat);
   return check_launch("pdf_gather_nchw_bwd");
 }
+
+// ---------------------------------------------------------------------------------------------
+// The K = 3 first layer of the level-1 point-MLP (netR_1[0], intaghand_encoder.py:50) and its two
+// gradients are pure streaming: 12 B in / 4*N B out per row.  The 64x64-tile FFMA kernels waste 95 % of a
+// tile on them, so they get their own bandwidth-shaped kernels (K <= 4).
+namespace pdf {
+
+// Y[m, n] = act(sum_k X[m,k] W[n,k] + b[n]); one thread = one row x 4 consecutive channels (N % 4 == 0)
+__global__ void __launch_bounds__(256)
+linear_smallk_fwd_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ W, int64_t ldw,
+                         const float* __restrict__ bias, int64_t M, int N, int K, float* __restrict__ Y, int64_t ldy) {
+  extern __shared__ float sw[];                      // [N][4] weights (zero padded) then [N] bias
+  for (int i = threadIdx.x; i < N * 4; i += blockDim.x) sw[i] = (i & 3) < K ? W[(int64_t)(i >> 2) * ldw + (i & 3)] : 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sw[N * 4 + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int nq = N >> 2;
+  const int64_t total = M * nq;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = e / nq;
+    const int n0 = (int)(e - m * nq) * 4;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < K; ++k) x[k] = X[m * ldx + k];
+    float y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 w = *reinterpret_cast<const float4*>(sw + (n0 + j) * 4);
+      y[j] = fmaf(w.w, x[3], fmaf(w.z, x[2], fmaf(w.y, x[1], fmaf(w.x, x[0], sw[N * 4 + n0 + j]))));
+    }
+    *reinterpret_cast<float4*>(Y + m * ldy + n0) = make_float4(y[0], y[1], y[2], y[3]);
+  }
+}
+
+// dX[m, k] = sum_n dY[m,n] W[n,k] (k < K <= 4): 16 lanes x float4 per row, two rows per warp (N == 64)
+// generalised: LPR lanes per row, each lane strides over float4 chunks
+__global__ void __launch_bounds__(256)
+linear_smallk_dx_kernel(const float* __restrict__ dY, int64_t lddy, const float* __restrict__ W, int64_t ldw,
+                        int64_t M, int N, int K, float* __restrict__ dX, int64_t lddx) {
+  extern __shared__ float sw[];                      // [N][4]
+  for (int i = threadIdx.x; i < N * 4; i += blockDim.x) sw[i] = (i & 3) < K ? W[(int64_t)(i >> 2) * ldw + (i & 3)] : 0.f;
+  __syncthreads();
+  const int lane16 = threadIdx.x & 15;
+  const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);   // the two 16-lane row groups of a warp may leave the loop apart
+  const int64_t row0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 4;
+  const int64_t rstep = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  for (int64_t m = row0; m < M; m += rstep) {        // the 16 lanes of a row group run the same trip count
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int n0 = lane16 * 4; n0 < N; n0 += 64) {
+      const float4 d = *reinterpret_cast<const float4*>(dY + m * lddy + n0);
+      const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(sw + (n0 + j) * 4);
+        a[0] = fmaf(dv[j], w.x, a[0]); a[1] = fmaf(dv[j], w.y, a[1]); a[2] = fmaf(dv[j], w.z, a[2]); a[3] = fmaf(dv[j], w.w, a[3]);
+      }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[k] += __shfl_xor_sync(hmask, a[k], o, 16);
+    if (lane16 == 0)
+      for (int k = 0; k < K; ++k) dX[m * lddx + k] = a[k];
+  }
+}
+
+// dW[n, k] = sum_m dY[m,n] X[m,k]: block = 64 channels x 4 row lanes, fp32 partials, atomics at the end
+__global__ void __launch_bounds__(256)
+linear_smallk_dw_kernel(const float* __restrict__ dY, int64_t lddy, const float* __restrict__ X, int64_t ldx, int64_t M,
+                        int N, int K, float* __restrict__ dW, int64_t lddw) {
+  const int c = blockIdx.y * 64 + (threadIdx.x & 63), rl = threadIdx.x >> 6;
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < N) {
+    for (int64_t m = (int64_t)blockIdx.x * 4 + rl; m < M; m += (int64_t)gridDim.x * 4) {
+      const float d = dY[m * lddy + c];
+      for (int k = 0; k < K; ++k) a[k] = fmaf(d, X[m * ldx + k], a[k]);
+    }
+  }
+  __shared__ float red[4][64][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) red[rl][threadIdx.x & 63][k] = a[k];
+  __syncthreads();
+  if (rl == 0 && c < N)
+    for (int k = 0; k < K; ++k)
+      atomicAdd(dW + (int64_t)c * lddw + k, red[0][threadIdx.x][k] + red[1][threadIdx.x][k] + red[2][threadIdx.x][k] +
+                                                red[3][threadIdx.x][k]);
+}
+
+}  // namespace pdf
+
+extern "C" int pdf_linear_smallk_f32(int mode, const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias,
+                                     int64_t M, int N, int K, float* out, int64_t ldo, void* stream) {
+  if (M == 0 && mode != 2) return PDF_OK;
+  PDF_REQUIRE(A && B && out && M >= 0 && N > 0 && K > 0 && K <= 4 && mode >= 0 && mode <= 2, PDF_ERR_BAD_ARG,
+              "pdf_linear_smallk_f32: bad argument");
+  PDF_REQUIRE(N % 4 == 0 && N <= 2048, PDF_ERR_UNSUPPORTED, "pdf_linear_smallk_f32: N must be a multiple of 4, <= 2048");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (mode == 0) {                                     // forward: A = X [M,K], B = W [N,K] -> out [M,N]
+    PDF_REQUIRE(ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, PDF_ERR_BAD_ARG,
+                "pdf_linear_smallk_f32: output rows must be 16-byte aligned");
+    const int64_t total = M * (N / 4);
+    linear_smallk_fwd_kernel<<<grid_for(total), 256, (size_t)N * 5 * sizeof(float), s>>>(A, lda, B, ldb, bias, M, N, K,
+                                                                                          out, ldo);
+  } else if (mode == 1) {                              // data gradient: A = dY [M,N], B = W [N,K] -> out [M,K]
+    PDF_REQUIRE(lda % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0, PDF_ERR_BAD_ARG,
+                "pdf_linear_smallk_f32: dY rows must be 16-byte aligned");
+    linear_smallk_dx_kernel<<<grid_for(M * 16), 256, (size_t)N * 4 * sizeof(float), s>>>(A, lda, B, ldb, M, N, K, out, ldo);
+  } else {                                             // weight gradient: A = dY [M,N], B = X [M,K] -> out [N,K]
+    cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * K, N, s);
+    if (M == 0) return PDF_OK;
+    int64_t gx = (M + 4 * 256 - 1) / (4 * 256);
+    if (gx > 148 * 8) gx = 148 * 8;
+    linear_smallk_dw_kernel<<<dim3((unsigned)gx, (unsigned)((N + 63) / 64)), 256, 0, s>>>(A, lda, B, ldb, M, N, K, out, ldo);
+  }
+  return check_launch("pdf_linear_smallk_f32");
+}

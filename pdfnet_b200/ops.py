@@ -432,6 +432,28 @@ def linear_tn(a, b):
     return c
 
 
+def linear_smallk(mode, a, b, bias=None):
+    """K <= 4 streaming linear layer: mode 0 forward (a = x [M,K], b = w [N,K]), 1 data gradient
+    (a = dy [M,N], b = w [N,K] -> [M,K]), 2 weight gradient (a = dy [M,N], b = x [M,K] -> [N,K])."""
+    L.require_cuda(a, b, bias)
+    a, b = _rows(a), _rows(b)
+    if mode == 0:
+        M, K = a.shape
+        N = b.shape[0]
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    elif mode == 1:
+        M, N = a.shape
+        K = b.shape[1]
+        out = torch.empty((M, K), dtype=torch.float32, device=a.device)
+    else:
+        M, N = a.shape
+        K = b.shape[1]
+        out = torch.empty((N, K), dtype=torch.float32, device=a.device)
+    L.call("pdf_linear_smallk_f32", mode, L.ptr(a), a.stride(0), L.ptr(b), b.stride(0), L.ptr(bias), M, N, K, L.ptr(out),
+           out.stride(0), L.stream())
+    return out
+
+
 def group_max(y, G):
     M, C = _rows(y).shape
     assert M % G == 0

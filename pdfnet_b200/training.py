@@ -46,8 +46,16 @@ class LinearFn(Function):
         x, w = _c(x), _c(w)
         tc = _use_tc(x.shape[0], w.shape[0], w.shape[1])
         split = precision != BF16
-        y = ops.linear_tc(x, w, b, act=act, split=split) if tc else ops.linear(x, w, b, act=act)
-        ctx.act, ctx.tc, ctx.bias_before_bn, ctx.split = act, tc, bias_before_bn, split
+        # K <= 4 (netR_1[0]: xyz -> 64) is pure streaming: bandwidth-shaped kernels for the layer and both gradients
+        smallk = (not tc and w.shape[1] <= 4 and w.shape[0] % 4 == 0 and act == L.ACT_NONE and x.shape[0] >= 4096
+                  and w.is_contiguous())
+        if tc:
+            y = ops.linear_tc(x, w, b, act=act, split=split)
+        elif smallk:
+            y = ops.linear_smallk(0, x, w, b)
+        else:
+            y = ops.linear(x, w, b, act=act)
+        ctx.act, ctx.tc, ctx.bias_before_bn, ctx.split, ctx.smallk = act, tc, bias_before_bn, split, smallk
         ctx.save_for_backward(x, w, y if act != L.ACT_NONE else None)
         return y
 
@@ -59,12 +67,18 @@ class LinearFn(Function):
             dy = ops.act_bwd(dy, y, ctx.act)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            wt = w.t().contiguous()
             # the data gradient is the chain that carries every upstream gradient (and ends in the xyz
             # coordinates, where centroid-relative differences cancel): always fp32-accurate
-            dx = ops.linear_tc(dy, wt, split=True) if ctx.tc else ops.linear(dy, wt)
+            if ctx.smallk and dy.stride(0) % 4 == 0 and dy.data_ptr() % 16 == 0:
+                dx = ops.linear_smallk(1, dy, w)
+            else:
+                wt = w.t().contiguous()
+                dx = ops.linear_tc(dy, wt, split=True) if ctx.tc else ops.linear(dy, wt)
         if ctx.needs_input_grad[1]:
-            dw = ops.linear_tn_tc(dy, x, split=ctx.split) if ctx.tc else ops.linear_tn(dy, x)
+            if ctx.smallk:
+                dw = ops.linear_smallk(2, dy, x)
+            else:
+                dw = ops.linear_tn_tc(dy, x, split=ctx.split) if ctx.tc else ops.linear_tn(dy, x)
         db = None
         if ctx.needs_input_grad[2]:
             # a bias in front of train-mode BatchNorm has an identically zero gradient (BatchNorm removes

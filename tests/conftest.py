@@ -33,7 +33,7 @@ def check_grad_digest(golden, name, g, rtol, floor=1e-9, outliers=0.0):
     """Compare a gradient tensor with its record in a golden made by make_golden.grad_digest:
     element-wise within rtol of the tensor's largest magnitude (``floor`` is the absolute
     tolerance for gradients that are analytically zero, e.g. conv biases in front of BatchNorm).
-    ``outliers``: fraction of elements allowed outside that band (but inside 10x of it) - in fp32 a
+    ``outliers``: fraction of elements allowed outside that band (but inside 10x of it / 5 % of the scale) - in fp32 a
     near-tie in a max-pool or a ReLU at 0 can route one gradient differently from the fp64 golden."""
     g = np.asarray(g, dtype=np.float64).reshape(-1)
     full = name in golden
@@ -44,7 +44,9 @@ def check_grad_digest(golden, name, g, rtol, floor=1e-9, outliers=0.0):
     bad = np.abs(got - ref) > atol + rtol * np.abs(ref)
     assert bad.mean() <= outliers, "%s: %d of %d elements outside tolerance (max diff %.3g, atol %.3g)" % (
         name, bad.sum(), bad.size, np.abs(got - ref).max(), atol)
-    assert (np.abs(got - ref) <= 10 * (atol + rtol * np.abs(ref))).all(), name
+    # re-routed elements carry a whole different contribution: bounded by a fraction of the tensor's scale
+    hard = np.maximum(10 * (atol + rtol * np.abs(ref)), 0.05 * max(np.abs(ref).max(), scale))
+    assert (np.abs(got - ref) <= hard).all(), name
     if not full:
         norm = float(golden[name + "@norm"])
         assert abs(np.linalg.norm(g) - norm) <= max(rtol * norm, floor * np.sqrt(g.size)), name
