@@ -510,7 +510,8 @@ extern "C" int pdf_gather_nchw_bwd(const float* dOut, const int64_t* ind, int64_
 // tile on them, so they get their own bandwidth-shaped kernels (K <= 4).
 namespace pdf {
 
-// Y[m, n] = act(sum_k X[m,k] W[n,k] + b[n]); one thread = one row x 4 consecutive channels (N % 4 == 0)
+// Y[m, n] = sum_k X[m,k] W[n,k] + b[n]; one thread = 4 consecutive channels of 4 rows per iteration
+// (N % 4 == 0; blockDim.x = 256 = (N/4 channel groups) x (rows per CTA pass))
 __global__ void __launch_bounds__(256)
 linear_smallk_fwd_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ W, int64_t ldw,
                          const float* __restrict__ bias, int64_t M, int N, int K, float* __restrict__ Y, int64_t ldy) {
@@ -518,25 +519,40 @@ linear_smallk_fwd_kernel(const float* __restrict__ X, int64_t ldx, const float* 
   for (int i = threadIdx.x; i < N * 4; i += blockDim.x) sw[i] = (i & 3) < K ? W[(int64_t)(i >> 2) * ldw + (i & 3)] : 0.f;
   for (int i = threadIdx.x; i < N; i += blockDim.x) sw[N * 4 + i] = bias ? bias[i] : 0.f;
   __syncthreads();
-  const int nq = N >> 2;
-  const int64_t total = M * nq;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = e / nq;
-    const int n0 = (int)(e - m * nq) * 4;
-    float x[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < K; ++k) x[k] = X[m * ldx + k];
-    float y[4];
+  const int nq = N >> 2;                             // channel groups per row
+  const int rows_cta = 256 / nq > 0 ? 256 / nq : 1;  // rows covered by one CTA pass (nq <= 256 by the host check)
+  const int q = threadIdx.x % nq, rl = threadIdx.x / nq;
+  if (rl >= rows_cta) return;
+  const int n0 = q * 4;
+  float4 w[4];
+  float bb[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 w = *reinterpret_cast<const float4*>(sw + (n0 + j) * 4);
-      y[j] = fmaf(w.w, x[3], fmaf(w.z, x[2], fmaf(w.y, x[1], fmaf(w.x, x[0], sw[N * 4 + n0 + j]))));
+  for (int j = 0; j < 4; ++j) { w[j] = *reinterpret_cast<const float4*>(sw + (n0 + j) * 4); bb[j] = sw[N * 4 + n0 + j]; }
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * rows_cta;
+  for (int64_t m0 = (int64_t)blockIdx.x * rows_cta + rl; m0 < M; m0 += U * stride) {
+    float x[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t m = m0 + u * stride;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[u][k] = (m < M && k < K) ? X[m * ldx + k] : 0.f;
     }
-    *reinterpret_cast<float4*>(Y + m * ldy + n0) = make_float4(y[0], y[1], y[2], y[3]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t m = m0 + u * stride;
+      if (m >= M) break;
+      float y[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        y[j] = fmaf(w[j].w, x[u][3], fmaf(w[j].z, x[u][2], fmaf(w[j].y, x[u][1], fmaf(w[j].x, x[u][0], bb[j]))));
+      *reinterpret_cast<float4*>(Y + m * ldy + n0) = make_float4(y[0], y[1], y[2], y[3]);
+    }
   }
 }
 
-// dX[m, k] = sum_n dY[m,n] W[n,k] (k < K <= 4): 16 lanes x float4 per row, two rows per warp (N == 64)
-// generalised: LPR lanes per row, each lane strides over float4 chunks
+// dX[m, k] = sum_n dY[m,n] W[n,k] (k < K <= 4): 16 lanes x float4 per row, two row groups per warp, four rows
+// in flight per group
 __global__ void __launch_bounds__(256)
 linear_smallk_dx_kernel(const float* __restrict__ dY, int64_t lddy, const float* __restrict__ W, int64_t ldw,
                         int64_t M, int N, int K, float* __restrict__ dX, int64_t lddx) {
@@ -547,36 +563,65 @@ linear_smallk_dx_kernel(const float* __restrict__ dY, int64_t lddy, const float*
   const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);   // the two 16-lane row groups of a warp may leave the loop apart
   const int64_t row0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 4;
   const int64_t rstep = ((int64_t)gridDim.x * blockDim.x) >> 4;
-  for (int64_t m = row0; m < M; m += rstep) {        // the 16 lanes of a row group run the same trip count
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
+  constexpr int U = 4;
+  for (int64_t m0 = row0; m0 < M; m0 += U * rstep) {   // the 16 lanes of a row group run the same trip count
+    float a[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u][0] = a[u][1] = a[u][2] = a[u][3] = 0.f;
     for (int n0 = lane16 * 4; n0 < N; n0 += 64) {
-      const float4 d = *reinterpret_cast<const float4*>(dY + m * lddy + n0);
-      const float dv[4] = {d.x, d.y, d.z, d.w};
+      float4 d[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t m = m0 + u * rstep;
+        d[u] = m < M ? *reinterpret_cast<const float4*>(dY + m * lddy + n0) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 w = *reinterpret_cast<const float4*>(sw + (n0 + j) * 4);
-        a[0] = fmaf(dv[j], w.x, a[0]); a[1] = fmaf(dv[j], w.y, a[1]); a[2] = fmaf(dv[j], w.z, a[2]); a[3] = fmaf(dv[j], w.w, a[3]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float dv = j == 0 ? d[u].x : (j == 1 ? d[u].y : (j == 2 ? d[u].z : d[u].w));
+          a[u][0] = fmaf(dv, w.x, a[u][0]); a[u][1] = fmaf(dv, w.y, a[u][1]);
+          a[u][2] = fmaf(dv, w.z, a[u][2]); a[u][3] = fmaf(dv, w.w, a[u][3]);
+        }
       }
     }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1)
+    for (int u = 0; u < U; ++u) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) a[k] += __shfl_xor_sync(hmask, a[k], o, 16);
-    if (lane16 == 0)
-      for (int k = 0; k < K; ++k) dX[m * lddx + k] = a[k];
+      for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[u][k] += __shfl_xor_sync(hmask, a[u][k], o, 16);
+      const int64_t m = m0 + u * rstep;
+      if (lane16 == 0 && m < M)
+        for (int k = 0; k < K; ++k) dX[m * lddx + k] = a[u][k];
+    }
   }
 }
 
-// dW[n, k] = sum_m dY[m,n] X[m,k]: block = 64 channels x 4 row lanes, fp32 partials, atomics at the end
+// dW[n, k] = sum_m dY[m,n] X[m,k]: block = 64 channels x 4 row lanes, eight rows in flight per thread,
+// fp32 partials, atomics at the end
 __global__ void __launch_bounds__(256)
 linear_smallk_dw_kernel(const float* __restrict__ dY, int64_t lddy, const float* __restrict__ X, int64_t ldx, int64_t M,
                         int N, int K, float* __restrict__ dW, int64_t lddw) {
   const int c = blockIdx.y * 64 + (threadIdx.x & 63), rl = threadIdx.x >> 6;
   float a[4] = {0.f, 0.f, 0.f, 0.f};
+  constexpr int U = 8;
+  const int64_t stride = (int64_t)gridDim.x * 4;
   if (c < N) {
-    for (int64_t m = (int64_t)blockIdx.x * 4 + rl; m < M; m += (int64_t)gridDim.x * 4) {
-      const float d = dY[m * lddy + c];
-      for (int k = 0; k < K; ++k) a[k] = fmaf(d, X[m * ldx + k], a[k]);
+    for (int64_t m0 = (int64_t)blockIdx.x * 4 + rl; m0 < M; m0 += U * stride) {
+      float d[U], x[U][4];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t m = m0 + u * stride;
+        d[u] = m < M ? dY[m * lddy + c] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[u][k] = (m < M && k < K) ? X[m * ldx + k] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = fmaf(d[u], x[u][k], a[k]);
     }
   }
   __shared__ float red[4][64][4];
@@ -601,17 +646,20 @@ extern "C" int pdf_linear_smallk_f32(int mode, const float* A, int64_t lda, cons
   if (mode == 0) {                                     // forward: A = X [M,K], B = W [N,K] -> out [M,N]
     PDF_REQUIRE(ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, PDF_ERR_BAD_ARG,
                 "pdf_linear_smallk_f32: output rows must be 16-byte aligned");
-    const int64_t total = M * (N / 4);
-    linear_smallk_fwd_kernel<<<grid_for(total), 256, (size_t)N * 5 * sizeof(float), s>>>(A, lda, B, ldb, bias, M, N, K,
-                                                                                          out, ldo);
+    PDF_REQUIRE(N <= 1024, PDF_ERR_UNSUPPORTED, "pdf_linear_smallk_f32: forward supports N <= 1024");
+    const int rows_cta = 256 / (N / 4);
+    int64_t gx = (M + (int64_t)rows_cta * 4 - 1) / ((int64_t)rows_cta * 4);
+    if (gx > 148 * 16) gx = 148 * 16;
+    linear_smallk_fwd_kernel<<<(unsigned)(gx < 1 ? 1 : gx), 256, (size_t)N * 5 * sizeof(float), s>>>(A, lda, B, ldb, bias,
+                                                                                                     M, N, K, out, ldo);
   } else if (mode == 1) {                              // data gradient: A = dY [M,N], B = W [N,K] -> out [M,K]
     PDF_REQUIRE(lda % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0, PDF_ERR_BAD_ARG,
                 "pdf_linear_smallk_f32: dY rows must be 16-byte aligned");
-    linear_smallk_dx_kernel<<<grid_for(M * 16), 256, (size_t)N * 4 * sizeof(float), s>>>(A, lda, B, ldb, M, N, K, out, ldo);
+    linear_smallk_dx_kernel<<<grid_for(M * 4), 256, (size_t)N * 4 * sizeof(float), s>>>(A, lda, B, ldb, M, N, K, out, ldo);
   } else {                                             // weight gradient: A = dY [M,N], B = X [M,K] -> out [N,K]
     cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * K, N, s);
     if (M == 0) return PDF_OK;
-    int64_t gx = (M + 4 * 256 - 1) / (4 * 256);
+    int64_t gx = (M + 4 * 64 - 1) / (4 * 64);
     if (gx > 148 * 8) gx = 148 * 8;
     linear_smallk_dw_kernel<<<dim3((unsigned)gx, (unsigned)((N + 63) / 64)), 256, 0, s>>>(A, lda, B, ldb, M, N, K, out, ldo);
   }
