@@ -196,6 +196,14 @@ int pdf_gemm_bf16_batched(const void* m_img, int m_tiles, int m_kb, int64_t m_ba
                           int n_tiles, int n_kb, int64_t n_batch_stride, int KB, int batches, float* out_f32,
                           int64_t ld_out, int64_t out_batch_stride, int64_t rows_valid,
                           const int32_t* tile_desc_host, void* stream);
+/* Weight gradient straight from ROW tile images (no transposed copy): out[b][ca, cb] = sum over the rows of
+ * batch b of A[r, ca] * B[r, cb], A / B = images of dY / X as written by pdf_rows_to_image (split = 1:
+ * [hi|hi|lo], three products per fp32 product; split = 0: plain bf16).  The tensor core reads the K-major
+ * blocks as MN-major operands (instruction-descriptor a_major = b_major = 1).  Batches are runs of
+ * tiles_per_batch row tiles (split-K); the caller sums out over b (batch_stride floats apart).
+ * Rows >= `rows` inside the last tile must be zero in both images (pdf_rows_to_image guarantees it). */
+int pdf_gemm_tn_bf16(const void* a_img, int ca, const void* b_img, int cb, int64_t rows, int split,
+                     int tiles_per_batch, float* out, int64_t ld_out, int64_t batch_stride, void* stream);
 /* SFT on the three xyz channels of level 1 in full fp32 (they feed the level-2 neighbour
  * search): x[m,c] = x[m,c]*(scale_c+1)+shift_c for c < 3; cond fp32 [M,cc]; conv weights as in
  * SFTLayer ([out,in] row-major; only rows 0..2 of the second convs are read). cc must be 64. */

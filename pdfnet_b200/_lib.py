@@ -42,6 +42,7 @@ SIGNATURES = {
     "pdf_split_coeff": [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "pdf_rows_to_image_t": [_vp, _i64, _i64, _i32, _i32, _vp, _i64, _i32, _vp],
     "pdf_gemm_bf16_batched": [_vp, _i32, _i32, _i64, _vp, _i32, _i32, _i64, _i32, _i32, _vp, _i64, _i64, _i64, _vp, _vp],
+    "pdf_gemm_tn_bf16": [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _i64, _i64, _vp],
     "pdf_bn_stats": [_vp, _i64, _i64, _i32, _vp, _vp],
     "pdf_bn_finalize": [_vp, _vp, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp],
     "pdf_bn_act_fwd": [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _i64, _vp],

@@ -534,6 +534,25 @@ def linear_tc(x, w, bias=None, act=L.ACT_NONE, split=True, packed=None, x_img=No
     return out[:, :N]
 
 
+def linear_tn_mn(a_img, ca, b_img, cb, M, split=True):
+    """a^T b [ca, cb] from the ROW tile images of a [M,ca] and b [M,cb] (pdf_gemm_tn_bf16: the tensor core
+    reads the K-major blocks as MN-major operands; no transposed copies).  Images as written by
+    rows_to_image(split=1) (or split=0 with split=False)."""
+    L.require_cuda(a_img, b_img)
+    row_tiles = (M + 127) // 128
+    at, bt = (ca + 127) // 128, (cb + 127) // 128
+    want = max(1, (2 * 148 + at * bt - 1) // (at * bt))                  # about two waves of work items
+    tpb = max(4, (row_tiles + want - 1) // want)
+    batches = (row_tiles + tpb - 1) // tpb
+    ld = _pad4(cb)
+    part = torch.zeros((batches, ca, ld), dtype=torch.float32, device=a_img.device)
+    L.call("pdf_gemm_tn_bf16", L.ptr(a_img), ca, L.ptr(b_img), cb, M, 1 if split else 0, tpb, L.ptr(part), ld, ca * ld,
+           L.stream())
+    if batches == 1:
+        return part[0, :, :cb]
+    return col_sum(part.view(batches, ca * ld)).view(ca, ld)[:, :cb]
+
+
 def linear_tn_tc(a, b, split=True):
     """a [M,N], b [M,K] -> a^T b [N,K] on the tcgen05 GEMM: split-K over batches of rows
     (pdf_rows_to_image_t + pdf_gemm_bf16_batched; split-bf16 or plain bf16 operands), partials

@@ -49,23 +49,29 @@ class LinearFn(Function):
         # K <= 4 (netR_1[0]: xyz -> 64) is pure streaming: bandwidth-shaped kernels for the layer and both gradients
         smallk = (not tc and w.shape[1] <= 4 and w.shape[0] % 4 == 0 and act == L.ACT_NONE and x.shape[0] >= 4096
                   and w.is_contiguous())
+        x_img = None
         if tc:
-            y = ops.linear_tc(x, w, b, act=act, split=split)
+            # the operand image of x is built here and kept: the weight gradient reads the same image again
+            # (as an MN-major operand, pdf_gemm_tn_bf16) instead of a transposed copy
+            x_img = ops.rows_to_image(x, 0, x.shape[1], split=1 if split else 0)
+            y = ops.linear_tc(None, w, b, act=act, split=split, x_img=x_img, M=x.shape[0])
         elif smallk:
             y = ops.linear_smallk(0, x, w, b)
         else:
             y = ops.linear(x, w, b, act=act)
         ctx.act, ctx.tc, ctx.bias_before_bn, ctx.split, ctx.smallk = act, tc, bias_before_bn, split, smallk
-        ctx.save_for_backward(x, w, y if act != L.ACT_NONE else None)
+        ctx.save_for_backward(x, w, y if act != L.ACT_NONE else None, x_img if (tc and split) else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, y = ctx.saved_tensors
+        x, w, y, x_img = ctx.saved_tensors
         dy = _c(dy)
         if ctx.act != L.ACT_NONE:
             dy = ops.act_bwd(dy, y, ctx.act)
         dx = dw = None
+        M, N, K = dy.shape[0], w.shape[0], w.shape[1]
+        dy_img = ops.rows_to_image(dy, 0, N, split=1) if ctx.tc else None      # shared by the dX and dW GEMMs
         if ctx.needs_input_grad[0]:
             # the data gradient is the chain that carries every upstream gradient (and ends in the xyz
             # coordinates, where centroid-relative differences cancel): always fp32-accurate
@@ -73,12 +79,17 @@ class LinearFn(Function):
                 dx = ops.linear_smallk(1, dy, w)
             else:
                 wt = w.t().contiguous()
-                dx = ops.linear_tc(dy, wt, split=True) if ctx.tc else ops.linear(dy, wt)
+                dx = ops.linear_tc(None, wt, split=True, x_img=dy_img, M=M) if ctx.tc else ops.linear(dy, wt)
         if ctx.needs_input_grad[1]:
             if ctx.smallk:
                 dw = ops.linear_smallk(2, dy, x)
             else:
-                dw = ops.linear_tn_tc(dy, x, split=ctx.split) if ctx.tc else ops.linear_tn(dy, x)
+                if ctx.tc:
+                    if x_img is None:                   # bf16 mode kept a plain image: the gradient wants the split one
+                        x_img = ops.rows_to_image(x, 0, K, split=1)
+                    dw = ops.linear_tn_mn(dy_img, N, x_img, K, M, split=True)
+                else:
+                    dw = ops.linear_tn(dy, x)
         db = None
         if ctx.needs_input_grad[2]:
             # a bias in front of train-mode BatchNorm has an identically zero gradient (BatchNorm removes

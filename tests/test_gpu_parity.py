@@ -883,6 +883,11 @@ def test_train_tensor_core_gemms_are_fp32_accurate():
         dw_ref = dy.double().t() @ x.double()
         dw = ops.linear_tn_tc(dy.to(DEV), x.to(DEV)).cpu().double()
         assert dw.shape == (N, K) and rel_err(dw, dw_ref) < 2e-5, (M, K, N, rel_err(dw, dw_ref))
+        # the same weight gradient straight from the ROW images (MN-major operand descriptors, no transposed copy)
+        dy_img = ops.rows_to_image(dy.to(DEV), 0, N, split=1)
+        x_img = ops.rows_to_image(x.to(DEV), 0, K, split=1)
+        dwm = ops.linear_tn_mn(dy_img, N, x_img, K, M).cpu().double()
+        assert dwm.shape == (N, K) and rel_err(dwm, dw_ref) < 2e-5, (M, K, N, rel_err(dwm, dw_ref))
         # plain bf16 operands (split=False): exact products of the bf16-rounded operands, fp32 accumulate
         rb = lambda t: t.bfloat16().double()
         yb = ops.linear_tc(x.to(DEV), w.to(DEV), b.to(DEV), split=False).cpu().double()
