@@ -58,6 +58,17 @@ def test_bad_arguments_return_errors_not_crashes(lib):
     assert b"null" in lib.pdf_last_error()
     assert lib.pdf_linear_f32(None, 0, None, 0, None, 1, 1, 1, 0, 0, 0, None, 0, None, 0, None) == -1
     assert lib.pdf_sa_pack_weights_host(None, None, None, None, None, None, 3, 64, 64, 128, None) == -1
+    # training / decoder entry points: null pointers and unsupported shapes are reported, never dereferenced
+    assert lib.pdf_bn_stats(None, 64, 10, 64, None, None) == -1
+    assert lib.pdf_linear_tn_f32(None, 0, None, 0, 10, 4, 4, None, 4, None) == -1
+    assert lib.pdf_gemm_tn_bf16(None, 64, None, 64, 128, 1, 4, None, 64, 0, None) == -1
+    assert lib.pdf_gemm_tn_bf16(None, 64, None, 64, 0, 1, 4, None, 64, 0, None) == 0      # no rows: no-op
+    assert lib.pdf_row_combine(None, 0, None, 0, None, 0, 1, 1, 64, 10, None, None, 1e-6, 0, None, 0, None, 0,
+                               None, None, None) == -1
+    assert lib.pdf_mha(None, 0, None, 0, None, 0, 0, 63, 4, 64, None, 0, None) == 0           # no samples: no-op
+    assert lib.pdf_mha(None, 0, None, 0, None, 0, 1, 63, 4, 64, None, 0, None) == -1
+    assert lib.pdf_linear_smallk_f32(0, None, 0, None, 0, None, 10, 64, 3, None, 64, None) == -1
+    assert lib.pdf_group_scatter_add(None, None, 1, 1024, 512, 64, 3, None, 3, None) == -1
 
 
 def test_state_dict_keys_match_reference_layout(lib):
