@@ -49,14 +49,15 @@ template <int MODE, int V>
 __global__ void __launch_bounds__(256)
 col_reduce_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ Yp, int64_t ldy,
                   const float* __restrict__ X, int64_t ldx, const float* __restrict__ mean,
-                  const float* __restrict__ rstd, int relu, int64_t M, int C, int LX, double* __restrict__ sums) {
+                  const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  int relu, int64_t M, int C, int LX, double* __restrict__ sums) {
   const int cx = threadIdx.x % LX, ry = threadIdx.x / LX, RY = 256 / LX;
   const int c = (blockIdx.x * LX + cx) * V;
   const bool ok = c < C;
-  float s0[V], s1[V], mu[V], rs[V];
+  float s0[V], s1[V], mu[V], rs[V], ga[V], be[V];
   double d0[V], d1[V];
 #pragma unroll
-  for (int e = 0; e < V; ++e) { s0[e] = s1[e] = 0.f; d0[e] = d1[e] = 0.0; mu[e] = rs[e] = 0.f; }
+  for (int e = 0; e < V; ++e) { s0[e] = s1[e] = 0.f; d0[e] = d1[e] = 0.0; mu[e] = rs[e] = ga[e] = be[e] = 0.f; }
   if (ok) {
     // statistics are accumulated about the channel's first row (shifted sums): the variance
     // sum d^2 - (sum d)^2 / M then has no catastrophic cancellation when |mean| >> std
@@ -67,6 +68,11 @@ col_reduce_kernel(const float* __restrict__ A, int64_t lda, const float* __restr
       const Vec<V> t = vload<V>(mean + c), u = vload<V>(rstd + c);
 #pragma unroll
       for (int e = 0; e < V; ++e) { mu[e] = t.v[e]; rs[e] = u.v[e]; }
+      if (!Yp && relu) {                             // ReLU mask recomputed from x instead of read from Y
+        const Vec<V> g2 = vload<V>(gamma + c), b2 = vload<V>(beta + c);
+#pragma unroll
+        for (int e = 0; e < V; ++e) { ga[e] = g2.v[e]; be[e] = b2.v[e]; }
+      }
     }
   }
   // two-level accumulation keeps fp32 partial sums short (<= 64 terms) before going to double
@@ -82,12 +88,17 @@ col_reduce_kernel(const float* __restrict__ A, int64_t lda, const float* __restr
 #pragma unroll
         for (int e = 0; e < V; ++e) s0[e] += a.v[e];
       } else {
-        const Vec<V> y = vload<V>(Yp + r * ldy + c), x = vload<V>(X + r * ldx + c);
+        const Vec<V> x = vload<V>(X + r * ldx + c);
+        Vec<V> y;
+        if (Yp) y = vload<V>(Yp + r * ldy + c);
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-          const float g = (!relu || y.v[e] > 0.f) ? a.v[e] : 0.f;
+          const float xhat = (x.v[e] - mu[e]) * rs[e];
+          // same expression as the forward pass (pdf_bn_act_fwd), so the recomputed mask is bit-identical
+          const bool on = !relu || (Yp ? y.v[e] > 0.f : fmaf(xhat, ga[e], be[e]) > 0.f);
+          const float g = on ? a.v[e] : 0.f;
           s0[e] += g;
-          s1[e] = fmaf(g, (x.v[e] - mu[e]) * rs[e], s1[e]);
+          s1[e] = fmaf(g, xhat, s1[e]);
         }
       }
       if (++n == 64) {
@@ -165,13 +176,16 @@ __global__ void __launch_bounds__(256) elementwise_kernel(EwArgs p) {
         o.v[e] = p.flag ? fmaxf(y, 0.f) : y;
       }
     } else if (MODE == EW_BN_BWD) {     // v0 mean, v1 rstd, v2 gamma
-      const Vec<V> dy = vload<V>(p.a + r * p.lda + c), y = vload<V>(p.b + r * p.ldb + c),
-                   x = vload<V>(p.c + r * p.ldc + c), mu = vload<V>(p.v0 + c), rs = vload<V>(p.v1 + c),
-                   ga = vload<V>(p.v2 + c);
+      const Vec<V> dy = vload<V>(p.a + r * p.lda + c), x = vload<V>(p.c + r * p.ldc + c), mu = vload<V>(p.v0 + c),
+                   rs = vload<V>(p.v1 + c), ga = vload<V>(p.v2 + c);
+      Vec<V> y, be;
+      if (p.b) y = vload<V>(p.b + r * p.ldb + c);
+      else if (p.flag) be = vload<V>(p.v3 + c);
 #pragma unroll
       for (int e = 0; e < V; ++e) {
-        const float g = (!p.flag || y.v[e] > 0.f) ? dy.v[e] : 0.f;
         const float xhat = (x.v[e] - mu.v[e]) * rs.v[e];
+        const bool on = !p.flag || (p.b ? y.v[e] > 0.f : fmaf(xhat, ga.v[e], be.v[e]) > 0.f);
+        const float g = on ? dy.v[e] : 0.f;
         const float dbeta = (float)p.sums[c + e], dgamma = (float)p.sums[p.C + c + e];
         o.v[e] = ga.v[e] * rs.v[e] * (g - dbeta * invM - xhat * dgamma * invM);
       }
@@ -347,13 +361,13 @@ static unsigned grid_for(int64_t total) {
 template <int MODE>
 static int launch_reduce(const float* A, int64_t lda, const float* Y, int64_t ldy, const float* X, int64_t ldx,
                          const float* mean, const float* rstd, int relu, int64_t M, int C, double* sums,
-                         cudaStream_t s, const char* what) {
+                         cudaStream_t s, const char* what, const float* gamma = nullptr, const float* beta = nullptr) {
   const int nsum = MODE == RED_COLSUM ? C : 2 * C;
   cudaMemsetAsync(sums, 0, sizeof(double) * nsum, s);
   if (M == 0) return PDF_OK;
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const bool vec = C % 4 == 0 && lda % 4 == 0 && ldy % 4 == 0 && ldx % 4 == 0 && al(A) && al(Y) && al(X) &&
-                   al(mean) && al(rstd);
+                   al(mean) && al(rstd) && al(gamma) && al(beta);
   const int cv = vec ? C / 4 : C;                       // channel-vectors per row
   int LX = 1;
   while (LX < cv && LX < 32) LX <<= 1;
@@ -363,8 +377,8 @@ static int launch_reduce(const float* A, int64_t lda, const float* Y, int64_t ld
   const int64_t cap = (148 * 8 + gx - 1) / gx;
   if (gy > cap) gy = cap;
   dim3 grid((unsigned)gx, (unsigned)gy);
-  if (vec) col_reduce_kernel<MODE, 4><<<grid, 256, 0, s>>>(A, lda, Y, ldy, X, ldx, mean, rstd, relu, M, C, LX, sums);
-  else col_reduce_kernel<MODE, 1><<<grid, 256, 0, s>>>(A, lda, Y, ldy, X, ldx, mean, rstd, relu, M, C, LX, sums);
+  if (vec) col_reduce_kernel<MODE, 4><<<grid, 256, 0, s>>>(A, lda, Y, ldy, X, ldx, mean, rstd, gamma, beta, relu, M, C, LX, sums);
+  else col_reduce_kernel<MODE, 1><<<grid, 256, 0, s>>>(A, lda, Y, ldy, X, ldx, mean, rstd, gamma, beta, relu, M, C, LX, sums);
   return check_launch(what);
 }
 
@@ -403,16 +417,17 @@ extern "C" int pdf_bn_act_fwd(const float* X, int64_t ldx, const float* mean, co
 }
 
 extern "C" int pdf_bn_act_bwd(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* X, int64_t ldx,
-                              const float* mean, const float* rstd, const float* gamma, int relu, int64_t M, int C,
-                              double* sums, float* dX, int64_t lddx, void* stream) {
-  PDF_REQUIRE(dY && Y && X && mean && rstd && gamma && sums && dX && M >= 0 && C > 0, PDF_ERR_BAD_ARG,
-              "pdf_bn_act_bwd: bad argument");
+                              const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
+                              int64_t M, int C, double* sums, float* dX, int64_t lddx, void* stream) {
+  PDF_REQUIRE(dY && X && mean && rstd && gamma && sums && dX && M >= 0 && C > 0 && (Y || beta || !relu),
+              PDF_ERR_BAD_ARG, "pdf_bn_act_bwd: bad argument");
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = launch_reduce<RED_BN_BWD>(dY, lddy, Y, ldy, X, ldx, mean, rstd, relu, M, C, sums, s, "pdf_bn_act_bwd");
+  int rc = launch_reduce<RED_BN_BWD>(dY, lddy, Y, ldy, X, ldx, mean, rstd, relu, M, C, sums, s, "pdf_bn_act_bwd", gamma,
+                                     beta);
   if (rc != PDF_OK) return rc;
   EwArgs p = {};
   p.a = dY; p.lda = lddy; p.b = Y; p.ldb = ldy; p.c = X; p.ldc = ldx;
-  p.v0 = mean; p.v1 = rstd; p.v2 = gamma; p.sums = sums;
+  p.v0 = mean; p.v1 = rstd; p.v2 = gamma; p.v3 = beta; p.sums = sums;
   p.o0 = dX; p.ldo0 = lddx; p.M = M; p.C = C; p.flag = relu;
   return launch_ew<EW_BN_BWD>(p, s, "pdf_bn_act_bwd");
 }

@@ -374,14 +374,15 @@ def bn_act_fwd(x, mean, rstd, gamma, beta, relu=True):
     return y
 
 
-def bn_act_bwd(dy, y, x, mean, rstd, gamma, relu=True):
-    """-> (dx, dgamma, dbeta)"""
+def bn_act_bwd(dy, y, x, mean, rstd, gamma, relu=True, beta=None):
+    """-> (dx, dgamma, dbeta).  y=None with beta given: the ReLU mask is recomputed from x (no read of y)."""
     M, C = _rows(x).shape
     dy = _rows(dy if dy.stride(1) == 1 else dy.contiguous())
     sums = torch.empty((2 * C,), dtype=torch.float64, device=x.device)
     dx = torch.empty((M, C), dtype=torch.float32, device=x.device)
-    L.call("pdf_bn_act_bwd", L.ptr(dy), dy.stride(0), L.ptr(y), y.stride(0), L.ptr(x), x.stride(0), L.ptr(mean),
-           L.ptr(rstd), L.ptr(gamma), int(relu), M, C, L.ptr(sums), L.ptr(dx), dx.stride(0), L.stream())
+    L.call("pdf_bn_act_bwd", L.ptr(dy), dy.stride(0), L.ptr(y), y.stride(0) if y is not None else 0, L.ptr(x),
+           x.stride(0), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), int(relu), M, C, L.ptr(sums), L.ptr(dx),
+           dx.stride(0), L.stream())
     return dx, sums[C:].float(), sums[:C].float()
 
 

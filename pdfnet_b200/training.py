@@ -108,13 +108,14 @@ class BatchNormActFn(Function):
         mean, rstd = ops.bn_batch_stats(x, eps, momentum, running_mean, running_var)
         y = ops.bn_act_fwd(x, mean, rstd, gamma, beta, relu)
         ctx.relu = relu
-        ctx.save_for_backward(x, y, mean, rstd, gamma)
+        # y is not kept for the backward pass: the ReLU mask is recomputed from x (bit-identical expression)
+        ctx.save_for_backward(x, mean, rstd, gamma, beta)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, mean, rstd, gamma = ctx.saved_tensors
-        dx, dgamma, dbeta = ops.bn_act_bwd(_c(dy), y, x, mean, rstd, gamma, ctx.relu)
+        x, mean, rstd, gamma, beta = ctx.saved_tensors
+        dx, dgamma, dbeta = ops.bn_act_bwd(_c(dy), None, x, mean, rstd, gamma, ctx.relu, beta=beta)
         return dx, dgamma, dbeta, None, None, None, None, None
 
 

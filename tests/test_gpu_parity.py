@@ -726,6 +726,13 @@ def test_train_primitives_vs_torch_autograd():
     np.testing.assert_allclose(dx.cpu().numpy(), xc.grad.numpy(), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(dgamma.cpu().numpy(), gamma.grad.numpy(), rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(dbeta.cpu().numpy(), beta.grad.numpy(), rtol=1e-4, atol=1e-4)
+    # the same backward with the ReLU mask recomputed from x instead of read from y (identical mask; the sums
+    # are accumulated with atomics, so only their last bits may move)
+    dx2, dgamma2, dbeta2 = ops.bn_act_bwd(dy.to(DEV), None, xc.detach().to(DEV), mean, rstd, gamma.detach().to(DEV), True,
+                                          beta=beta.detach().to(DEV))
+    for got, want in ((dx2, dx), (dgamma2, dgamma), (dbeta2, dbeta)):
+        np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    assert torch.equal(dx2 == 0, dx == 0)
     # max over groups: duplicated rows -> the FIRST maximum takes the gradient (nn.MaxPool2d)
     G, groups = 8, 50
     yv = torch.randn((groups, G, C), generator=gen)
