@@ -308,10 +308,12 @@ int pdf_bn_act_fwd(const float* X, int64_t ldx, const float* mean, const float* 
 /* Backward of pdf_bn_act_fwd: g = dY * [Y > 0]; sums[0:C] = dbeta = sum g, sums[C:2C] = dgamma =
  * sum g*xhat; dX = gamma*rstd*(g - dbeta/M - xhat*dgamma/M).  dX may alias dY.  Y may be null when
  * beta is given: the ReLU mask is then recomputed from X with the forward's own expression (bit-identical),
- * which saves reading Y twice. */
+ * which saves reading Y twice.  dX_img (optional; C % 64 == 0, Y null, beta given): dX written as the
+ * split-bf16 tile image the gradient GEMMs read (zero rows up to the next multiple of 128); dX (fp32) may
+ * then be null. */
 int pdf_bn_act_bwd(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* X, int64_t ldx,
                    const float* mean, const float* rstd, const float* gamma, const float* beta, int relu, int64_t M,
-                   int C, double* sums, float* dX, int64_t lddx, void* stream);
+                   int C, double* sums, float* dX, int64_t lddx, void* dX_img, void* stream);
 /* sums[0:C] = column sums of A (bias gradients) */
 int pdf_col_sum(const float* A, int64_t lda, int64_t M, int C, double* sums, void* stream);
 /* dX = dY * act'(Y) for the PDF_ACT_* enum (Y is the activation OUTPUT); dX may alias dY */

@@ -10,6 +10,7 @@
 // of group_points / group_points_2 (utils.py:134-191), _tranpose_and_gather_feat
 // (models/utils.py:22-26) and SFTLayer.forward (intaghand_encoder.py:213-219).
 #include "pdf_common.cuh"
+#include "umma.cuh"
 
 namespace pdf {
 
@@ -211,6 +212,67 @@ __global__ void __launch_bounds__(256) elementwise_kernel(EwArgs p) {
       vstore<V>(p.o1 + r * p.ldo1 + c, o1);
     }
     vstore<V>(p.o0 + r * p.ldo0 + c, o);
+  }
+}
+
+
+// BatchNorm(+ReLU) backward apply writing dX directly as the split-bf16 tile image ([hi|hi|lo]) that the
+// data- and weight-gradient GEMMs read (pdf_gemm_bf16 / pdf_gemm_tn_bf16): one thread = 8 channels of a
+// row = one 16-byte image chunk per part.  Rows >= M of the last row tile are written as zeros (the
+// weight gradient reduces over them).  C % 64 == 0, 16-byte aligned rows.
+__global__ void __launch_bounds__(256)
+bn_bwd_image_kernel(const float* __restrict__ dY, int64_t lddy, const float* __restrict__ X, int64_t ldx,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const double* __restrict__ sums, int relu, int64_t M, int C,
+                    uint8_t* __restrict__ img) {
+  // thread = one 8-channel chunk (fixed for the thread's lifetime, its coefficients live in registers) of a run
+  // of rows: 256 threads = (C/8 chunks) x (256 / (C/8) rows per pass)
+  const int cq = C >> 3, nkb = C >> 6;
+  const int q = threadIdx.x % cq, rl = threadIdx.x / cq, rows_cta = 256 / cq;
+  if (rl >= rows_cta) return;
+  const int c = q * 8;
+  const float invM = 1.f / (float)M;
+  float mu[8], rs[8], ga[8], be[8], k0[8], k1[8], k2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    mu[e] = mean[c + e]; rs[e] = rstd[c + e]; ga[e] = gamma[c + e]; be[e] = beta[c + e];
+    k0[e] = ga[e] * rs[e];
+    k1[e] = (float)sums[c + e] * invM;               // dbeta / M
+    k2[e] = (float)sums[C + c + e] * invM;           // dgamma / M
+  }
+  const int64_t rows_pad = ((M + 127) >> 7) << 7;
+  const int kb = q >> 3;
+  const uint32_t kcol = (uint32_t)(q & 7) * 8;
+  for (int64_t r = (int64_t)blockIdx.x * rows_cta + rl; r < rows_pad; r += (int64_t)gridDim.x * rows_cta) {
+    float d[8];
+    if (r < M) {
+      const float4 a0 = *reinterpret_cast<const float4*>(dY + r * lddy + c), a1 = *reinterpret_cast<const float4*>(dY + r * lddy + c + 4);
+      const float4 x0 = *reinterpret_cast<const float4*>(X + r * ldx + c), x1 = *reinterpret_cast<const float4*>(X + r * ldx + c + 4);
+      const float dy[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xhat = (xv[e] - mu[e]) * rs[e];
+        const bool on = !relu || fmaf(xhat, ga[e], be[e]) > 0.f;
+        const float g = on ? dy[e] : 0.f;
+        d[e] = k0[e] * (g - k1[e] - xhat * k2[e]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[e] = 0.f;
+    }
+    uint4 w, wl;
+    w.x = umma::pack_bf16(d[0], d[1]); w.y = umma::pack_bf16(d[2], d[3]);
+    w.z = umma::pack_bf16(d[4], d[5]); w.w = umma::pack_bf16(d[6], d[7]);
+    wl.x = umma::pack_bf16(d[0] - __uint_as_float(w.x << 16), d[1] - __uint_as_float(w.x & 0xffff0000u));
+    wl.y = umma::pack_bf16(d[2] - __uint_as_float(w.y << 16), d[3] - __uint_as_float(w.y & 0xffff0000u));
+    wl.z = umma::pack_bf16(d[4] - __uint_as_float(w.z << 16), d[5] - __uint_as_float(w.z & 0xffff0000u));
+    wl.w = umma::pack_bf16(d[6] - __uint_as_float(w.w << 16), d[7] - __uint_as_float(w.w & 0xffff0000u));
+    uint8_t* base = img + (size_t)(r >> 7) * (size_t)(3 * nkb) * 16384;
+    const uint32_t off = umma::sw128_off((uint32_t)(r & 127), kcol);
+    *reinterpret_cast<uint4*>(base + (size_t)kb * 16384 + off) = w;
+    *reinterpret_cast<uint4*>(base + (size_t)(nkb + kb) * 16384 + off) = w;
+    *reinterpret_cast<uint4*>(base + (size_t)(2 * nkb + kb) * 16384 + off) = wl;
   }
 }
 
@@ -418,9 +480,11 @@ extern "C" int pdf_bn_act_fwd(const float* X, int64_t ldx, const float* mean, co
 
 extern "C" int pdf_bn_act_bwd(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* X, int64_t ldx,
                               const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
-                              int64_t M, int C, double* sums, float* dX, int64_t lddx, void* stream) {
-  PDF_REQUIRE(dY && X && mean && rstd && gamma && sums && dX && M >= 0 && C > 0 && (Y || beta || !relu),
+                              int64_t M, int C, double* sums, float* dX, int64_t lddx, void* dX_img, void* stream) {
+  PDF_REQUIRE(dY && X && mean && rstd && gamma && sums && (dX || dX_img) && M >= 0 && C > 0 && (Y || beta || !relu),
               PDF_ERR_BAD_ARG, "pdf_bn_act_bwd: bad argument");
+  PDF_REQUIRE(!dX_img || (C % 64 == 0 && beta && !Y && lddy % 4 == 0 && ldx % 4 == 0 && aligned16(dY) && aligned16(X)),
+              PDF_ERR_BAD_ARG, "pdf_bn_act_bwd: the image output needs C %% 64 == 0, beta (mask from x) and aligned rows");
   cudaStream_t s = (cudaStream_t)stream;
   int rc = launch_reduce<RED_BN_BWD>(dY, lddy, Y, ldy, X, ldx, mean, rstd, relu, M, C, sums, s, "pdf_bn_act_bwd", gamma,
                                      beta);
@@ -429,6 +493,16 @@ extern "C" int pdf_bn_act_bwd(const float* dY, int64_t lddy, const float* Y, int
   p.a = dY; p.lda = lddy; p.b = Y; p.ldb = ldy; p.c = X; p.ldc = ldx;
   p.v0 = mean; p.v1 = rstd; p.v2 = gamma; p.v3 = beta; p.sums = sums;
   p.o0 = dX; p.ldo0 = lddx; p.M = M; p.C = C; p.flag = relu;
+  if (dX_img && M > 0) {
+    PDF_REQUIRE(C <= 2048, PDF_ERR_UNSUPPORTED, "pdf_bn_act_bwd: the image output supports C <= 2048");
+    const int rows_cta = 256 / (C >> 3);
+    int64_t gx = ((((M + 127) >> 7) << 7) + rows_cta - 1) / rows_cta;
+    if (gx > 148 * 16) gx = 148 * 16;
+    bn_bwd_image_kernel<<<(unsigned)gx, 256, 0, s>>>(dY, lddy, X, ldx, mean, rstd, gamma, beta, sums, relu, M, C,
+                                                     (uint8_t*)dX_img);
+    rc = check_launch("pdf_bn_act_bwd");
+    if (rc != PDF_OK || !dX) return rc;
+  }
   return launch_ew<EW_BN_BWD>(p, s, "pdf_bn_act_bwd");
 }
 

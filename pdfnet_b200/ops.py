@@ -374,16 +374,19 @@ def bn_act_fwd(x, mean, rstd, gamma, beta, relu=True):
     return y
 
 
-def bn_act_bwd(dy, y, x, mean, rstd, gamma, relu=True, beta=None):
-    """-> (dx, dgamma, dbeta).  y=None with beta given: the ReLU mask is recomputed from x (no read of y)."""
+def bn_act_bwd(dy, y, x, mean, rstd, gamma, relu=True, beta=None, image=False):
+    """-> (dx, dgamma, dbeta).  y=None with beta given: the ReLU mask is recomputed from x (no read of y).
+    image=True (needs y=None, beta, C % 64 == 0): dx is returned as the split-bf16 tile image the gradient
+    GEMMs read instead of fp32 rows."""
     M, C = _rows(x).shape
     dy = _rows(dy if dy.stride(1) == 1 else dy.contiguous())
     sums = torch.empty((2 * C,), dtype=torch.float64, device=x.device)
-    dx = torch.empty((M, C), dtype=torch.float32, device=x.device)
+    dx = None if image else torch.empty((M, C), dtype=torch.float32, device=x.device)
+    img = split_image_empty(M, C, x.device) if image else None
     L.call("pdf_bn_act_bwd", L.ptr(dy), dy.stride(0), L.ptr(y), y.stride(0) if y is not None else 0, L.ptr(x),
            x.stride(0), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), int(relu), M, C, L.ptr(sums), L.ptr(dx),
-           dx.stride(0), L.stream())
-    return dx, sums[C:].float(), sums[:C].float()
+           dx.stride(0) if dx is not None else 0, L.ptr(img), L.stream())
+    return (img if image else dx), sums[C:].float(), sums[:C].float()
 
 
 def col_sum(a):

@@ -119,6 +119,44 @@ class BatchNormActFn(Function):
         return dx, dgamma, dbeta, None, None, None, None, None
 
 
+class LinearBNReLUFn(Function):
+    """Conv1x1 -> BatchNorm2d(train) -> ReLU as ONE autograd node on the tensor-core path, so that the
+    gradient between the BatchNorm and the convolution never exists as fp32 rows: the BatchNorm backward
+    writes it as the split-bf16 tile image which both gradient GEMMs read (dX through pdf_gemm_bf16, dW
+    through pdf_gemm_tn_bf16 together with the image of x kept from the forward pass)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, momentum, eps, precision):
+        x, w = _c(x), _c(w)
+        split = precision != BF16
+        M = x.shape[0]
+        x_img = ops.rows_to_image(x, 0, x.shape[1], split=1 if split else 0)
+        pre = ops.linear_tc(None, w, b, split=split, x_img=x_img, M=M)
+        mean, rstd = ops.bn_batch_stats(pre, eps, momentum, running_mean, running_var)
+        y = ops.bn_act_fwd(pre, mean, rstd, gamma, beta, True)
+        ctx.save_for_backward(x, w, pre, mean, rstd, gamma, beta, x_img if split else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, pre, mean, rstd, gamma, beta, x_img = ctx.saved_tensors
+        M, N, K = pre.shape[0], w.shape[0], w.shape[1]
+        dy = _c(dy)
+        if dy.stride(0) % 4 or dy.data_ptr() % 16:
+            dy = dy.contiguous()
+        dpre_img, dgamma, dbeta = ops.bn_act_bwd(dy, None, pre, mean, rstd, gamma, True, beta=beta, image=True)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.linear_tc(None, w.t().contiguous(), split=True, x_img=dpre_img, M=M)
+        if ctx.needs_input_grad[1]:
+            if x_img is None:                           # bf16 mode kept a plain image: the gradient wants the split one
+                x_img = ops.rows_to_image(x, 0, K, split=1)
+            dw = ops.linear_tn_mn(dpre_img, N, x_img, K, M, split=True)
+        if ctx.needs_input_grad[2]:                     # bias in front of BatchNorm: identically zero gradient
+            db = torch.zeros((N,), dtype=torch.float32, device=w.device)
+        return dx, dw, db, dgamma, dbeta, None, None, None, None, None
+
+
 class GroupMaxFn(Function):
     """nn.MaxPool2d over groups of G consecutive rows."""
 
@@ -200,14 +238,18 @@ def mlp_max_rows(net, rows, group, precision=FP32):
     h = rows
     for i in (0, 3, 6):
         conv, bn = net[i], net[i + 1]
-        h = LinearFn.apply(h, _conv_w(conv), conv.bias, L.ACT_NONE, True, precision)
-        momentum = bn.momentum if bn.momentum is not None else 0.1
-        if bn.training:
-            h = BatchNormActFn.apply(h, bn.weight, bn.bias, bn.running_mean, bn.running_var, momentum, bn.eps, True)
-            if bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += 1
-        else:
+        if not bn.training:
             raise RuntimeError("mlp_max_rows is the train-mode path")
+        momentum = bn.momentum if bn.momentum is not None else 0.1
+        w = _conv_w(conv)
+        if _use_tc(h.shape[0], w.shape[0], w.shape[1]) and w.shape[0] % 64 == 0:
+            h = LinearBNReLUFn.apply(h, w, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, momentum,
+                                     bn.eps, precision)
+        else:
+            h = LinearFn.apply(h, w, conv.bias, L.ACT_NONE, True, precision)
+            h = BatchNormActFn.apply(h, bn.weight, bn.bias, bn.running_mean, bn.running_var, momentum, bn.eps, True)
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
     return GroupMaxFn.apply(h, group)
 
 
