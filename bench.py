@@ -759,7 +759,8 @@ def main():
                          "bf16 = plain bf16 operands for forward / dW")
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (cfg3: 128, cfg5: 64)")
     ap.add_argument("--res", type=int, default=256)
-    ap.add_argument("--cpu-sample-frames", type=int, default=4)
+    ap.add_argument("--cpu-sample-frames", type=int, default=16,
+                    help="frames per CPU step of the reference arm / cpu_baseline leg (about 1.6 s of 16-thread CPU work each)")
     ap.add_argument("--pyramid-layout", default="nchw", choices=["nchw", "nhwc"],
                     help="memory format of the RGB feature pyramid inputs (nchw = what the reference neck emits; "
                          "nhwc = torch.channels_last hand-off, SURVEY 8f row f4)")
