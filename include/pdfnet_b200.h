@@ -337,8 +337,17 @@ int pdf_linear_tn_f32(const float* A, int64_t lda, const float* B, int64_t ldb, 
 int pdf_linear_smallk_f32(int mode, const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias,
                           int64_t M, int N, int K, float* out, int64_t ldo, void* stream);
 /* nn.MaxPool2d over groups of G consecutive rows (intaghand_encoder.py:63,81,99) and its
- * backward: the FIRST maximum of each (group, channel) receives dOut, all other rows 0. */
-int pdf_group_max(const float* Y, int64_t ldy, int G, int64_t groups, int C, float* out, int64_t ldo, void* stream);
+ * backward: the FIRST maximum of each (group, channel) receives dOut, all other rows 0.  arg_out (optional,
+ * uint8 [groups, C], G <= 256): row index of that maximum inside its group. */
+int pdf_group_max(const float* Y, int64_t ldy, int G, int64_t groups, int C, float* out, int64_t ldo,
+                  uint8_t* arg_out, void* stream);
+/* BatchNorm(+ReLU) backward of a layer whose output feeds the max-pool directly (netR_x[6..8] -> MaxPool,
+ * intaghand_encoder.py:60-63,78-81,96-99): the incoming gradient is dOut at the argmax row of each (group,
+ * channel) and zero elsewhere, so it is never materialised; sums (dbeta | dgamma) are reduced over the argmax
+ * rows only and dX is written as the split-bf16 tile image.  arg = pdf_group_max's arg_out (G <= 256). */
+int pdf_bn_maxpool_bwd(const float* dOut, int64_t lddo, const uint8_t* arg, int G, const float* X, int64_t ldx,
+                       const float* mean, const float* rstd, const float* gamma, const float* beta, int relu, int64_t M,
+                       int C, double* sums, void* dX_img, void* stream);
 int pdf_group_max_bwd(const float* Y, int64_t ldy, const float* dOut, int64_t lddo, int G, int64_t groups, int C,
                       float* dY, int64_t lddy, void* stream);
 /* Backward of pdf_group_gather: dPts[b, idx[b,g,j], c] += dG[b,g,j,c]; dPts[b,g,c<3] -= dG[b,g,j,c].

@@ -53,7 +53,8 @@ SIGNATURES = {
     "pdf_sft_modulate_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _i64, _vp],
     "pdf_linear_tn_f32": [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _i64, _vp],
     "pdf_linear_smallk_f32": [_i32, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp],
-    "pdf_group_max": [_vp, _i64, _i32, _i64, _i32, _vp, _i64, _vp],
+    "pdf_group_max": [_vp, _i64, _i32, _i64, _i32, _vp, _i64, _vp, _vp],
+    "pdf_bn_maxpool_bwd": [_vp, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp],
     "pdf_group_max_bwd": [_vp, _i64, _vp, _i64, _i32, _i64, _i32, _vp, _i64, _vp],
     "pdf_group_scatter_add": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp],
     "pdf_gather_nchw_bwd": [_vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp],

@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(256)
 bn_bwd_image_kernel(const float* __restrict__ dY, int64_t lddy, const float* __restrict__ X, int64_t ldx,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const double* __restrict__ sums, int relu, int64_t M, int C,
-                    uint8_t* __restrict__ img) {
+                    uint8_t* __restrict__ img, const float* __restrict__ dOut, int64_t lddo,
+                    const uint8_t* __restrict__ arg, int G) {
   // thread = one 8-channel chunk (fixed for the thread's lifetime, its coefficients live in registers) of a run
   // of rows: 256 threads = (C/8 chunks) x (256 / (C/8) rows per pass)
   const int cq = C >> 3, nkb = C >> 6;
@@ -246,9 +247,23 @@ bn_bwd_image_kernel(const float* __restrict__ dY, int64_t lddy, const float* __r
   for (int64_t r = (int64_t)blockIdx.x * rows_cta + rl; r < rows_pad; r += (int64_t)gridDim.x * rows_cta) {
     float d[8];
     if (r < M) {
-      const float4 a0 = *reinterpret_cast<const float4*>(dY + r * lddy + c), a1 = *reinterpret_cast<const float4*>(dY + r * lddy + c + 4);
+      float dy[8];
+      if (arg) {                                     // gradient of the max-pool: only the argmax row of a group is non-zero
+        const int64_t g = r / G;
+        const int rg = (int)(r - g * G);
+        const uint2 aw = *reinterpret_cast<const uint2*>(arg + g * C + c);
+        const float4 o0 = *reinterpret_cast<const float4*>(dOut + g * lddo + c), o1 = *reinterpret_cast<const float4*>(dOut + g * lddo + c + 4);
+        const float ov[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int a = (int)(((e < 4 ? aw.x : aw.y) >> (8 * (e & 3))) & 0xffu);
+          dy[e] = a == rg ? ov[e] : 0.f;
+        }
+      } else {
+        const float4 a0 = *reinterpret_cast<const float4*>(dY + r * lddy + c), a1 = *reinterpret_cast<const float4*>(dY + r * lddy + c + 4);
+        dy[0] = a0.x; dy[1] = a0.y; dy[2] = a0.z; dy[3] = a0.w; dy[4] = a1.x; dy[5] = a1.y; dy[6] = a1.z; dy[7] = a1.w;
+      }
       const float4 x0 = *reinterpret_cast<const float4*>(X + r * ldx + c), x1 = *reinterpret_cast<const float4*>(X + r * ldx + c + 4);
-      const float dy[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -351,15 +366,53 @@ linear_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
 // ---------------------------------------------------------------------------------------------
 // max over groups of G consecutive rows, and its backward (gradient to the FIRST maximum)
 __global__ void group_max_kernel(const float* __restrict__ Y, int64_t ldy, int G, int64_t groups, int C,
-                                 float* __restrict__ out, int64_t ldo) {
+                                 float* __restrict__ out, int64_t ldo, uint8_t* __restrict__ arg) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= groups * C) return;
   const int64_t g = i / C;
   const int c = (int)(i - g * C);
   const float* y = Y + g * G * ldy + c;
   float m = y[0];
-  for (int r = 1; r < G; ++r) m = fmaxf(m, y[(int64_t)r * ldy]);
+  int a = 0;
+  for (int r = 1; r < G; ++r) {
+    const float v = y[(int64_t)r * ldy];
+    if (v > m) { m = v; a = r; }                      // first maximum, as nn.MaxPool2d
+  }
   out[g * ldo + c] = m;
+  if (arg) arg[g * C + c] = (uint8_t)a;
+}
+
+// BatchNorm(+ReLU) backward for a layer whose output goes straight into the max-pool: the incoming gradient is
+// dY[r, c] = dOut[g, c] if r is the argmax row of (group g = r / G, channel c), else 0.  The two sums then
+// need only the `groups` argmax rows per channel (G times less data than a dense reduction).
+__global__ void __launch_bounds__(256)
+bn_bwd_sparse_reduce_kernel(const float* __restrict__ dOut, int64_t lddo, const uint8_t* __restrict__ arg,
+                            const float* __restrict__ X, int64_t ldx, const float* __restrict__ mean,
+                            const float* __restrict__ rstd, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, int relu, int G, int64_t groups, int C,
+                            double* __restrict__ sums) {
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63), gl = threadIdx.x >> 6;
+  double s0 = 0.0, s1 = 0.0;
+  if (c < C) {
+    const float mu = mean[c], rs = rstd[c], ga = gamma[c], be = beta[c];
+    for (int64_t g = (int64_t)blockIdx.y * 4 + gl; g < groups; g += (int64_t)gridDim.y * 4) {
+      const int64_t r = g * G + arg[g * C + c];
+      const float xhat = (X[r * ldx + c] - mu) * rs;
+      const bool on = !relu || fmaf(xhat, ga, be) > 0.f;
+      const float d = on ? dOut[g * lddo + c] : 0.f;
+      s0 += d;
+      s1 += (double)d * xhat;
+    }
+  }
+  __shared__ double red[2][4][64];
+  red[0][gl][threadIdx.x & 63] = s0;
+  red[1][gl][threadIdx.x & 63] = s1;
+  __syncthreads();
+  if (gl == 0 && c < C) {
+    const int t = threadIdx.x;
+    atomicAdd(&sums[c], red[0][0][t] + red[0][1][t] + red[0][2][t] + red[0][3][t]);
+    atomicAdd(&sums[C + c], red[1][0][t] + red[1][1][t] + red[1][2][t] + red[1][3][t]);
+  }
 }
 
 __global__ void group_max_bwd_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ dOut,
@@ -499,7 +552,7 @@ extern "C" int pdf_bn_act_bwd(const float* dY, int64_t lddy, const float* Y, int
     int64_t gx = ((((M + 127) >> 7) << 7) + rows_cta - 1) / rows_cta;
     if (gx > 148 * 16) gx = 148 * 16;
     bn_bwd_image_kernel<<<(unsigned)gx, 256, 0, s>>>(dY, lddy, X, ldx, mean, rstd, gamma, beta, sums, relu, M, C,
-                                                     (uint8_t*)dX_img);
+                                                     (uint8_t*)dX_img, nullptr, 0, nullptr, 1);
     rc = check_launch("pdf_bn_act_bwd");
     if (rc != PDF_OK || !dX) return rc;
   }
@@ -555,12 +608,43 @@ extern "C" int pdf_linear_tn_f32(const float* A, int64_t lda, const float* B, in
 }
 
 extern "C" int pdf_group_max(const float* Y, int64_t ldy, int G, int64_t groups, int C, float* out, int64_t ldo,
-                             void* stream) {
-  PDF_REQUIRE(Y && out && G > 0 && groups >= 0 && C > 0, PDF_ERR_BAD_ARG, "pdf_group_max: bad argument");
+                             uint8_t* arg_out, void* stream) {
+  PDF_REQUIRE(Y && out && G > 0 && groups >= 0 && C > 0 && (!arg_out || G <= 256), PDF_ERR_BAD_ARG,
+              "pdf_group_max: bad argument");
   if (groups == 0) return PDF_OK;
   const int64_t total = groups * C;
-  group_max_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(Y, ldy, G, groups, C, out, ldo);
+  group_max_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(Y, ldy, G, groups, C, out, ldo,
+                                                                                       arg_out);
   return check_launch("pdf_group_max");
+}
+
+extern "C" int pdf_bn_maxpool_bwd(const float* dOut, int64_t lddo, const uint8_t* arg, int G, const float* X, int64_t ldx,
+                                  const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
+                                  int64_t M, int C, double* sums, void* dX_img, void* stream) {
+  PDF_REQUIRE(dOut && arg && X && mean && rstd && gamma && beta && sums && dX_img && M >= 0 && C > 0 && G > 0 &&
+                  G <= 256 && M % G == 0,
+              PDF_ERR_BAD_ARG, "pdf_bn_maxpool_bwd: bad argument");
+  PDF_REQUIRE(C % 64 == 0 && C <= 2048 && lddo % 4 == 0 && ldx % 4 == 0 && aligned16(dOut) && aligned16(X) &&
+                  (reinterpret_cast<uintptr_t>(arg) & 7) == 0,
+              PDF_ERR_BAD_ARG, "pdf_bn_maxpool_bwd: needs C %% 64 == 0 and aligned rows");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s);
+  if (M == 0) return PDF_OK;
+  const int64_t groups = M / G;
+  int64_t gy = (groups + 4 * 32 - 1) / (4 * 32);
+  const int gx = (C + 63) / 64;
+  const int64_t cap = (148 * 8 + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  bn_bwd_sparse_reduce_kernel<<<dim3((unsigned)gx, (unsigned)(gy < 1 ? 1 : gy)), 256, 0, s>>>(
+      dOut, lddo, arg, X, ldx, mean, rstd, gamma, beta, relu, G, groups, C, sums);
+  int rc = check_launch("pdf_bn_maxpool_bwd");
+  if (rc != PDF_OK) return rc;
+  const int rows_cta = 256 / (C >> 3);
+  int64_t gxi = ((((M + 127) >> 7) << 7) + rows_cta - 1) / rows_cta;
+  if (gxi > 148 * 16) gxi = 148 * 16;
+  bn_bwd_image_kernel<<<(unsigned)gxi, 256, 0, s>>>(nullptr, 0, X, ldx, mean, rstd, gamma, beta, sums, relu, M, C,
+                                                    (uint8_t*)dX_img, dOut, lddo, arg, G);
+  return check_launch("pdf_bn_maxpool_bwd");
 }
 
 extern "C" int pdf_group_max_bwd(const float* Y, int64_t ldy, const float* dOut, int64_t lddo, int G, int64_t groups,

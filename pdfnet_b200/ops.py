@@ -458,12 +458,26 @@ def linear_smallk(mode, a, b, bias=None):
     return out
 
 
-def group_max(y, G):
+def group_max(y, G, want_arg=False):
+    """max over groups of G consecutive rows; want_arg: also the uint8 row index of the (first) maximum."""
     M, C = _rows(y).shape
     assert M % G == 0
     out = torch.empty((M // G, C), dtype=torch.float32, device=y.device)
-    L.call("pdf_group_max", L.ptr(y), y.stride(0), G, M // G, C, L.ptr(out), out.stride(0), L.stream())
-    return out
+    arg = torch.empty((M // G, C), dtype=torch.uint8, device=y.device) if want_arg else None
+    L.call("pdf_group_max", L.ptr(y), y.stride(0), G, M // G, C, L.ptr(out), out.stride(0), L.ptr(arg), L.stream())
+    return (out, arg) if want_arg else out
+
+
+def bn_maxpool_bwd(dout, arg, G, x, mean, rstd, gamma, beta, relu=True):
+    """BatchNorm(+ReLU) backward fed by the max-pool gradient (never materialised): -> (dx split tile image,
+    dgamma, dbeta); see pdf_bn_maxpool_bwd."""
+    M, C = _rows(x).shape
+    dout = _rows(dout if dout.stride(1) == 1 else dout.contiguous())
+    sums = torch.empty((2 * C,), dtype=torch.float64, device=x.device)
+    img = split_image_empty(M, C, x.device)
+    L.call("pdf_bn_maxpool_bwd", L.ptr(dout), dout.stride(0), L.ptr(arg), G, L.ptr(x), x.stride(0), L.ptr(mean),
+           L.ptr(rstd), L.ptr(gamma), L.ptr(beta), int(relu), M, C, L.ptr(sums), L.ptr(img), L.stream())
+    return img, sums[C:].float(), sums[:C].float()
 
 
 def group_max_bwd(y, dout, G):

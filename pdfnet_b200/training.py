@@ -126,7 +126,9 @@ class LinearBNReLUFn(Function):
     through pdf_gemm_tn_bf16 together with the image of x kept from the forward pass)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, momentum, eps, precision):
+    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, momentum, eps, precision, group=0):
+        """group > 0: the nn.MaxPool2d over ``group`` consecutive rows that ends the stack is part of the node;
+        its gradient (dOut at the argmax row, zero elsewhere) is then never materialised."""
         x, w = _c(x), _c(w)
         split = precision != BF16
         M = x.shape[0]
@@ -134,17 +136,24 @@ class LinearBNReLUFn(Function):
         pre = ops.linear_tc(None, w, b, split=split, x_img=x_img, M=M)
         mean, rstd = ops.bn_batch_stats(pre, eps, momentum, running_mean, running_var)
         y = ops.bn_act_fwd(pre, mean, rstd, gamma, beta, True)
-        ctx.save_for_backward(x, w, pre, mean, rstd, gamma, beta, x_img if split else None)
+        arg = None
+        if group:
+            y, arg = ops.group_max(y, group, want_arg=True)
+        ctx.group = group
+        ctx.save_for_backward(x, w, pre, mean, rstd, gamma, beta, x_img if split else None, arg)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, pre, mean, rstd, gamma, beta, x_img = ctx.saved_tensors
+        x, w, pre, mean, rstd, gamma, beta, x_img, arg = ctx.saved_tensors
         M, N, K = pre.shape[0], w.shape[0], w.shape[1]
         dy = _c(dy)
         if dy.stride(0) % 4 or dy.data_ptr() % 16:
             dy = dy.contiguous()
-        dpre_img, dgamma, dbeta = ops.bn_act_bwd(dy, None, pre, mean, rstd, gamma, True, beta=beta, image=True)
+        if ctx.group:
+            dpre_img, dgamma, dbeta = ops.bn_maxpool_bwd(dy, arg, ctx.group, pre, mean, rstd, gamma, beta, True)
+        else:
+            dpre_img, dgamma, dbeta = ops.bn_act_bwd(dy, None, pre, mean, rstd, gamma, True, beta=beta, image=True)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = ops.linear_tc(None, w.t().contiguous(), split=True, x_img=dpre_img, M=M)
@@ -154,7 +163,7 @@ class LinearBNReLUFn(Function):
             dw = ops.linear_tn_mn(dpre_img, N, x_img, K, M, split=True)
         if ctx.needs_input_grad[2]:                     # bias in front of BatchNorm: identically zero gradient
             db = torch.zeros((N,), dtype=torch.float32, device=w.device)
-        return dx, dw, db, dgamma, dbeta, None, None, None, None, None
+        return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None
 
 
 class GroupMaxFn(Function):
@@ -243,14 +252,17 @@ def mlp_max_rows(net, rows, group, precision=FP32):
         momentum = bn.momentum if bn.momentum is not None else 0.1
         w = _conv_w(conv)
         if _use_tc(h.shape[0], w.shape[0], w.shape[1]) and w.shape[0] % 64 == 0:
+            pool = group if (i == 6 and group <= 256 and h.shape[0] % group == 0) else 0
             h = LinearBNReLUFn.apply(h, w, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, momentum,
-                                     bn.eps, precision)
+                                     bn.eps, precision, pool)
+            pooled = pool > 0
         else:
+            pooled = False
             h = LinearFn.apply(h, w, conv.bias, L.ACT_NONE, True, precision)
             h = BatchNormActFn.apply(h, bn.weight, bn.bias, bn.running_mean, bn.running_var, momentum, bn.eps, True)
         if bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
-    return GroupMaxFn.apply(h, group)
+    return h if pooled else GroupMaxFn.apply(h, group)
 
 
 def pyramid_indices(choose, R):

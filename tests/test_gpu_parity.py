@@ -1160,3 +1160,37 @@ def test_linear_smallk_streaming_kernels():
         assert dx.shape == (M, K) and rel_err(dx, dy.double() @ w.double()) < 1e-5
         dw = ops.linear_smallk(2, dy.to(DEV), x.to(DEV)).cpu().double()
         assert dw.shape == (N, K) and rel_err(dw, dy.double().t() @ x.double()) < 1e-4
+
+
+def test_bn_backward_image_and_maxpool_forms():
+    """pdf_bn_act_bwd(image) and pdf_bn_maxpool_bwd write dX as the split tile image: decoded (hi + lo) it equals
+    the fp32-row form to 2^-16, pad rows of the last tile are zero, and the max-pool form (gradient never
+    materialised, sums over the argmax rows only) matches the dense form fed with pdf_group_max_bwd's output."""
+    from pdfnet_b200 import ops
+    gen = torch.Generator().manual_seed(41)
+    G, groups, C = 64, 37, 128                                   # 2368 rows: the last row tile is ragged
+    M = G * groups
+    pre = (torch.randn((M, C), generator=gen) * 2 + 0.3).to(DEV)
+    gamma, beta = (torch.rand(C, generator=gen) + 0.5).to(DEV), torch.randn(C, generator=gen).to(DEV)
+    mean, rstd = ops.bn_batch_stats(pre, 1e-5, 0.1)
+    y = ops.bn_act_fwd(pre, mean, rstd, gamma, beta, True)
+    pooled, arg = ops.group_max(y, G, want_arg=True)
+    assert torch.equal(pooled, ops.group_max(y, G))
+    dout = torch.randn((groups, C), generator=gen).to(DEV)
+    dy = ops.group_max_bwd(y, dout, G)
+    assert torch.equal(dy.view(groups, G, C).gather(1, arg.long()[:, None, :])[:, 0], dout)   # arg marks the routed rows
+    dx, dgamma, dbeta = ops.bn_act_bwd(dy, None, pre, mean, rstd, gamma, True, beta=beta)
+
+    def decode(img):
+        full = _decode_image(img.cpu().numpy(), ((M + 127) // 128) * 128, 3 * C)
+        return full[:, :C] + full[:, 2 * C:], full[:, :C], full[:, C:2 * C]
+
+    scale = float(dx.abs().max())
+    for img, dg, db in (ops.bn_act_bwd(dy, None, pre, mean, rstd, gamma, True, beta=beta, image=True),
+                        ops.bn_maxpool_bwd(dout, arg, G, pre, mean, rstd, gamma, beta, True)):
+        val, hi, hi2 = decode(img)
+        assert np.array_equal(hi, hi2)                                        # [hi | hi | lo]
+        assert np.abs(val[:M] - dx.cpu().numpy()).max() < 3e-5 * scale
+        assert not val[M:].any()                                              # zero pad rows: dW reduces over them
+        np.testing.assert_allclose(dg.cpu().numpy(), dgamma.cpu().numpy(), rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(db.cpu().numpy(), dbeta.cpu().numpy(), rtol=1e-4, atol=1e-4)
