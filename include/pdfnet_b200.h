@@ -302,9 +302,10 @@ int pdf_bn_stats(const float* X, int64_t ldx, int64_t M, int C, double* sums, vo
  * torch.nn.functional.batch_norm(training=True).  running_* may be null. */
 int pdf_bn_finalize(const double* sums, const float* X, int64_t M, int C, float eps, float momentum,
                     float* running_mean, float* running_var, float* mean, float* rstd, void* stream);
-/* Y = [relu]((X - mean) * rstd * gamma + beta) */
+/* Y = [relu]((X - mean) * rstd * gamma + beta).  Y_img (optional, C % 64 == 0): Y written as the split-bf16 tile
+ * image of the next layer's GEMM (zero rows up to the next multiple of 128); Y (fp32 rows) may then be null. */
 int pdf_bn_act_fwd(const float* X, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
-                   const float* beta, int relu, int64_t M, int C, float* Y, int64_t ldy, void* stream);
+                   const float* beta, int relu, int64_t M, int C, float* Y, int64_t ldy, void* Y_img, void* stream);
 /* Backward of pdf_bn_act_fwd: g = dY * [Y > 0]; sums[0:C] = dbeta = sum g, sums[C:2C] = dgamma =
  * sum g*xhat; dX = gamma*rstd*(g - dbeta/M - xhat*dgamma/M).  dX may alias dY.  Y may be null when
  * beta is given: the ReLU mask is then recomputed from X with the forward's own expression (bit-identical),

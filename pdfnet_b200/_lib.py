@@ -45,7 +45,7 @@ SIGNATURES = {
     "pdf_gemm_tn_bf16": [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _i64, _i64, _vp],
     "pdf_bn_stats": [_vp, _i64, _i64, _i32, _vp, _vp],
     "pdf_bn_finalize": [_vp, _vp, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp],
-    "pdf_bn_act_fwd": [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _i64, _vp],
+    "pdf_bn_act_fwd": [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _i64, _vp, _vp],
     "pdf_bn_act_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _i64, _vp, _vp],
     "pdf_col_sum": [_vp, _i64, _i64, _i32, _vp, _vp],
     "pdf_act_bwd": [_vp, _i64, _vp, _i64, _i32, _i64, _i32, _vp, _i64, _vp],

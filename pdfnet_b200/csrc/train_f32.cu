@@ -291,6 +291,55 @@ bn_bwd_image_kernel(const float* __restrict__ dY, int64_t lddy, const float* __r
   }
 }
 
+// BatchNorm(+ReLU) forward apply writing Y directly as the split-bf16 tile image of the NEXT layer's GEMM (and,
+// optionally, as fp32 rows): thread = one 8-channel chunk of a run of rows, zero pad rows up to the tile edge.
+__global__ void __launch_bounds__(256)
+bn_fwd_image_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    int relu, int64_t M, int C, float* __restrict__ Y, int64_t ldy, uint8_t* __restrict__ img) {
+  const int cq = C >> 3, nkb = C >> 6;
+  const int q = threadIdx.x % cq, rl = threadIdx.x / cq, rows_cta = 256 / cq;
+  if (rl >= rows_cta) return;
+  const int c = q * 8;
+  float mu[8], rs[8], ga[8], be[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { mu[e] = mean[c + e]; rs[e] = rstd[c + e]; ga[e] = gamma[c + e]; be[e] = beta[c + e]; }
+  const int64_t rows_pad = ((M + 127) >> 7) << 7;
+  const int kb = q >> 3;
+  const uint32_t kcol = (uint32_t)(q & 7) * 8;
+  for (int64_t r = (int64_t)blockIdx.x * rows_cta + rl; r < rows_pad; r += (int64_t)gridDim.x * rows_cta) {
+    float d[8];
+    if (r < M) {
+      const float4 x0 = *reinterpret_cast<const float4*>(X + r * ldx + c), x1 = *reinterpret_cast<const float4*>(X + r * ldx + c + 4);
+      const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float y = fmaf((xv[e] - mu[e]) * rs[e], ga[e], be[e]);       // same expression as elementwise BN_FWD
+        d[e] = relu ? fmaxf(y, 0.f) : y;
+      }
+      if (Y) {
+        *reinterpret_cast<float4*>(Y + r * ldy + c) = make_float4(d[0], d[1], d[2], d[3]);
+        *reinterpret_cast<float4*>(Y + r * ldy + c + 4) = make_float4(d[4], d[5], d[6], d[7]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[e] = 0.f;
+    }
+    uint4 w, wl;
+    w.x = umma::pack_bf16(d[0], d[1]); w.y = umma::pack_bf16(d[2], d[3]);
+    w.z = umma::pack_bf16(d[4], d[5]); w.w = umma::pack_bf16(d[6], d[7]);
+    wl.x = umma::pack_bf16(d[0] - __uint_as_float(w.x << 16), d[1] - __uint_as_float(w.x & 0xffff0000u));
+    wl.y = umma::pack_bf16(d[2] - __uint_as_float(w.y << 16), d[3] - __uint_as_float(w.y & 0xffff0000u));
+    wl.z = umma::pack_bf16(d[4] - __uint_as_float(w.z << 16), d[5] - __uint_as_float(w.z & 0xffff0000u));
+    wl.w = umma::pack_bf16(d[6] - __uint_as_float(w.w << 16), d[7] - __uint_as_float(w.w & 0xffff0000u));
+    uint8_t* base = img + (size_t)(r >> 7) * (size_t)(3 * nkb) * 16384;
+    const uint32_t off = umma::sw128_off((uint32_t)(r & 127), kcol);
+    *reinterpret_cast<uint4*>(base + (size_t)kb * 16384 + off) = w;
+    *reinterpret_cast<uint4*>(base + (size_t)(nkb + kb) * 16384 + off) = w;
+    *reinterpret_cast<uint4*>(base + (size_t)(2 * nkb + kb) * 16384 + off) = wl;
+  }
+}
+
 static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
 template <int MODE>
@@ -522,9 +571,21 @@ extern "C" int pdf_bn_finalize(const double* sums, const float* X, int64_t M, in
 }
 
 extern "C" int pdf_bn_act_fwd(const float* X, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
-                              const float* beta, int relu, int64_t M, int C, float* Y, int64_t ldy, void* stream) {
-  PDF_REQUIRE(X && mean && rstd && gamma && beta && Y && M >= 0 && C > 0, PDF_ERR_BAD_ARG,
+                              const float* beta, int relu, int64_t M, int C, float* Y, int64_t ldy, void* Y_img,
+                              void* stream) {
+  PDF_REQUIRE(X && mean && rstd && gamma && beta && (Y || Y_img) && M >= 0 && C > 0, PDF_ERR_BAD_ARG,
               "pdf_bn_act_fwd: bad argument");
+  if (Y_img) {
+    PDF_REQUIRE(C % 64 == 0 && C <= 2048 && ldx % 4 == 0 && aligned16(X) && (!Y || (ldy % 4 == 0 && aligned16(Y))),
+                PDF_ERR_BAD_ARG, "pdf_bn_act_fwd: the image output needs C %% 64 == 0 and 16-byte aligned rows");
+    if (M == 0) return PDF_OK;
+    const int rows_cta = 256 / (C >> 3);
+    int64_t gx = ((((M + 127) >> 7) << 7) + rows_cta - 1) / rows_cta;
+    if (gx > 148 * 16) gx = 148 * 16;
+    bn_fwd_image_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(X, ldx, mean, rstd, gamma, beta, relu, M, C, Y,
+                                                                         ldy, (uint8_t*)Y_img);
+    return check_launch("pdf_bn_act_fwd");
+  }
   EwArgs p = {};
   p.a = X; p.lda = ldx; p.v0 = mean; p.v1 = rstd; p.v2 = gamma; p.v3 = beta;
   p.o0 = Y; p.ldo0 = ldy; p.M = M; p.C = C; p.flag = relu;

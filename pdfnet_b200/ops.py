@@ -366,12 +366,15 @@ def bn_batch_stats(x, eps, momentum, running_mean=None, running_var=None):
     return mean, rstd
 
 
-def bn_act_fwd(x, mean, rstd, gamma, beta, relu=True):
+def bn_act_fwd(x, mean, rstd, gamma, beta, relu=True, rows=True, image=False):
+    """[relu](BatchNorm(x)) as fp32 rows and/or (image=True, C % 64 == 0) as the split-bf16 tile image of the
+    next layer's GEMM.  Returns rows, or (rows or None, image)."""
     M, C = _rows(x).shape
-    y = torch.empty((M, C), dtype=torch.float32, device=x.device)
+    y = torch.empty((M, C), dtype=torch.float32, device=x.device) if rows else None
+    img = split_image_empty(M, C, x.device) if image else None
     L.call("pdf_bn_act_fwd", L.ptr(x), x.stride(0), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), int(relu), M,
-           C, L.ptr(y), y.stride(0), L.stream())
-    return y
+           C, L.ptr(y), y.stride(0) if y is not None else 0, L.ptr(img), L.stream())
+    return (y, img) if image else y
 
 
 def bn_act_bwd(dy, y, x, mean, rstd, gamma, relu=True, beta=None, image=False):

@@ -125,22 +125,38 @@ class LinearBNReLUFn(Function):
     writes it as the split-bf16 tile image which both gradient GEMMs read (dX through pdf_gemm_bf16, dW
     through pdf_gemm_tn_bf16 together with the image of x kept from the forward pass)."""
 
+    handoff = None
+
     @staticmethod
-    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, momentum, eps, precision, group=0):
+    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, momentum, eps, precision, group=0,
+                image_only=False):
         """group > 0: the nn.MaxPool2d over ``group`` consecutive rows that ends the stack is part of the node;
-        its gradient (dOut at the argmax row, zero elsewhere) is then never materialised."""
-        x, w = _c(x), _c(w)
+        its gradient (dOut at the argmax row, zero elsewhere) is then never materialised.
+        image_only: the output is consumed by another node of this kind only, so it is written ONLY as that
+        node's operand image (handed to the caller through ``LinearBNReLUFn.handoff``; the returned fp32 tensor
+        is a one-element placeholder expanded to the right shape)."""
+        w = _c(w)
         split = precision != BF16
         M = x.shape[0]
-        x_img = ops.rows_to_image(x, 0, x.shape[1], split=1 if split else 0)
+        x_img = getattr(x, "_pdf_split_img", None) if split else None
+        if x_img is None:
+            x = _c(x)
+            x_img = ops.rows_to_image(x, 0, x.shape[1], split=1 if split else 0)
         pre = ops.linear_tc(None, w, b, split=split, x_img=x_img, M=M)
         mean, rstd = ops.bn_batch_stats(pre, eps, momentum, running_mean, running_var)
-        y = ops.bn_act_fwd(pre, mean, rstd, gamma, beta, True)
         arg = None
-        if group:
-            y, arg = ops.group_max(y, group, want_arg=True)
+        if image_only and split and not group:
+            _, y_img = ops.bn_act_fwd(pre, mean, rstd, gamma, beta, True, rows=False, image=True)
+            y = torch.empty((1, 1), dtype=torch.float32, device=pre.device).expand(M, w.shape[0])
+        else:
+            y_img = None
+            y = ops.bn_act_fwd(pre, mean, rstd, gamma, beta, True)
+            if group:
+                y, arg = ops.group_max(y, group, want_arg=True)
         ctx.group = group
-        ctx.save_for_backward(x, w, pre, mean, rstd, gamma, beta, x_img if split else None, arg)
+        ctx.save_for_backward(x if x.stride(-1) == 1 else None, w, pre, mean, rstd, gamma, beta,
+                              x_img if split else None, arg)
+        LinearBNReLUFn.handoff = y_img                  # picked up by mlp_max_rows right after apply()
         return y
 
     @staticmethod
@@ -163,7 +179,7 @@ class LinearBNReLUFn(Function):
             dw = ops.linear_tn_mn(dpre_img, N, x_img, K, M, split=True)
         if ctx.needs_input_grad[2]:                     # bias in front of BatchNorm: identically zero gradient
             db = torch.zeros((N,), dtype=torch.float32, device=w.device)
-        return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None
+        return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None, None
 
 
 class GroupMaxFn(Function):
@@ -245,16 +261,23 @@ def sft_rows(sft, fea_rows, cond_rows, precision=FP32):
 def mlp_max_rows(net, rows, group, precision=FP32):
     """(Conv1x1 -> BatchNorm2d(train) -> ReLU) x3 -> max over ``group`` consecutive rows."""
     h = rows
-    for i in (0, 3, 6):
+    M = rows.shape[0]
+    fused = [_use_tc(M, _conv_w(net[i]).shape[0], _conv_w(net[i]).shape[1]) and net[i].out_channels % 64 == 0
+             for i in (0, 3, 6)]
+    for li, i in enumerate((0, 3, 6)):
         conv, bn = net[i], net[i + 1]
         if not bn.training:
             raise RuntimeError("mlp_max_rows is the train-mode path")
         momentum = bn.momentum if bn.momentum is not None else 0.1
         w = _conv_w(conv)
-        if _use_tc(h.shape[0], w.shape[0], w.shape[1]) and w.shape[0] % 64 == 0:
-            pool = group if (i == 6 and group <= 256 and h.shape[0] % group == 0) else 0
+        if fused[li]:
+            pool = group if (i == 6 and group <= 256 and M % group == 0) else 0
+            # an intermediate layer whose only consumer is the next fused node hands over its operand image
+            image_only = li < 2 and fused[li + 1] and precision != BF16
             h = LinearBNReLUFn.apply(h, w, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, momentum,
-                                     bn.eps, precision, pool)
+                                     bn.eps, precision, pool, image_only)
+            if LinearBNReLUFn.handoff is not None:      # h's fp32 storage is a placeholder: the values live in the image
+                h._pdf_split_img, LinearBNReLUFn.handoff = LinearBNReLUFn.handoff, None
             pooled = pool > 0
         else:
             pooled = False
