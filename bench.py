@@ -190,6 +190,7 @@ class ClockSampler(object):
 
 def run_ours(args):
     from pdfnet_b200 import parallel
+    torch.set_grad_enabled(False)         # inference workload: fused kernels (a graph would select training.py)
     rank, world, local = parallel.init_distributed("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -404,6 +405,7 @@ def run_cfg2(args):
     ball query (r = 0.1 => r2 = 0.01, k = 64) -> fused point-MLP 3->64->64->128 + max (tcgen05).
     Reports per-kernel time, achieved algorithmic HBM GB/s (SURVEY 8d bytes) and TFLOP/s."""
     from pdfnet_b200 import PointNet_Plus, ops, synth
+    torch.set_grad_enabled(False)
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     B, N, N1, K = args.clouds, 1024, 512, 64
@@ -654,6 +656,7 @@ def run_decoder(args):
     """the GCN decoder that consumes fuse_feat (the reference's live path after the
     fusion tail).  One step = decoder.forward for ``--frames`` frames (both hands), replayed as a CUDA graph."""
     from pdfnet_b200 import parallel
+    torch.set_grad_enabled(False)
     rank, world, local = parallel.init_distributed("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

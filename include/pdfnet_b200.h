@@ -265,6 +265,21 @@ int pdf_mano_lbs(const float* v_template, const float* shapedirs_t, const float*
                  const float* root, const float* pose, const float* shape, const float* trans,
                  const float* scale, int64_t n, const int32_t* tip_idx_host, int center_idx, int new_skel,
                  const float* v_tpose, float* v, float* j, void* stream);
+/* Same, for layers built with use_pca=True (manolayer.py:266-267, the dataset layers of
+ * interhand.py:192,220-223): the root rotation arrives as a 3x3 MATRIX root_mat [n,9] and is used as is
+ * (:285); pose is the axis-angle vector after pca2axis (:159-162, a [n,ncomps]x[ncomps,45] product done by
+ * the caller). */
+int pdf_mano_lbs_rootmat(const float* v_template, const float* shapedirs_t, const float* posedirs_t,
+                         const float* j_template, const float* j_shapedirs, const float* weights_t,
+                         const float* root_mat, const float* pose, const float* shape, const float* trans,
+                         const float* scale, int64_t n, const int32_t* tip_idx_host, int center_idx, int new_skel,
+                         const float* v_tpose, float* v, float* j, void* stream);
+/* rodrigues_batch (manolayer.py:32-48): axis [n,3] -> rot [n,3,3], theta = |a| + 1e-8. */
+int pdf_rodrigues(const float* axis, int64_t n, float* rot, void* stream);
+/* joints = full_regressor @ verts (Mano_model.py:246-247,309-323; demo.py:217-218, simplified.py:431-434):
+ * reg [n_joints,778] dense fp32 (J_regressor + one-hot tip rows, reordered), verts [n,778,3] ->
+ * joints [n,n_joints,3]. */
+int pdf_joint_regress(const float* reg, int n_joints, const float* verts, int64_t n, float* joints, void* stream);
 /* Both hands of every frame in ONE launch: hands laid out (frame, side), even = left, odd = right.
  * tables_left / tables_right: host arrays of the 6 device table pointers in the order of
  * pdf_mano_lbs (v_template, shapedirs_t, posedirs_t, j_template, j_shapedirs, weights_t).

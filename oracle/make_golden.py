@@ -371,9 +371,60 @@ def golden_gcn_decoder(ref_dec):
     save("gcn_decoder", **rec)
 
 
+def golden_mano_extra(ref):
+    """Round-2 additions, all from the UNMODIFIED reference:
+    * rodrigues_batch (manolayer.py:32-48) stand-alone, incl. a zero and a tiny rotation;
+    * ManoLayer(use_pca=True): root rotation as a 3x3 matrix, pose as PCA coefficients (:266-267), the way
+      the InterHand dataset drives it (interhand.py:192,220-223), 45 and 30 components;
+    * ManoModel (lib/models/hand3d/Mano_model.py): full_regressor (:309-323), joints = full_regressor @ verts
+      (demo.py:217-218) and the second LBS implementation (``lbs``, :560-647) on the mano_lbs.npz inputs."""
+    import importlib
+    ref_import.load_split_coeff()                       # installs the pytorch3d import stubs Mano_model needs
+    MM = importlib.import_module("lib.models.hand3d.Mano_model")
+    out = {}
+    g = torch.Generator().manual_seed(101)
+    axis = torch.randn((64, 3), generator=g) * 0.8
+    axis[0] = 0.0
+    axis[1] = torch.tensor([1e-6, -2e-6, 5e-7])
+    axis[2] = torch.tensor([3.1, 0.0, 0.0])
+    out["rod_axis"] = axis.numpy()
+    out["rod_R"] = ref.rodrigues_batch(axis.clone()).numpy()
+    for side in ("left", "right"):
+        path = os.path.join(ref.mano_dir, "MANO_%s.pkl" % side.upper())
+        rot, pose, shape, trans = synth.mano_inputs(6, seed=171 if side == "left" else 172)
+        Rroot = ref.rodrigues_batch(rot.clone())
+        scale = torch.rand((6,), generator=torch.Generator().manual_seed(173)) + 0.5
+        out.update({"pca_root_" + side: Rroot.numpy(), "pca_shape_" + side: shape.numpy(),
+                    "pca_trans_" + side: trans.numpy(), "pca_scale_" + side: scale.numpy()})
+        for nc in (45, 30):
+            coef = torch.randn((6, nc), generator=torch.Generator().manual_seed(180 + nc)) * 0.7
+            out["pca_coef%d_%s" % (nc, side)] = coef.numpy()
+            for tag, kw, ci in (("plain", {}, None), ("full", dict(trans=trans, scale=scale), 9)):
+                m = ref.ManoLayer(path, center_idx=ci, use_pca=True)
+                with torch.no_grad():
+                    v, j = m(Rroot.clone(), coef.clone(), shape.clone(), side=side, **kw)
+                out["pca_v%d_%s_%s" % (nc, tag, side)] = v.numpy()
+                out["pca_j%d_%s_%s" % (nc, tag, side)] = j.numpy()
+        mm = MM.ManoModel(model_path=path, is_rhand=(side == "right"), use_pca=False, flat_hand_mean=True,
+                          num_pca_comps=45)
+        out["full_regressor_" + side] = mm.full_regressor.numpy()
+        rot2, pose2, shape2, trans2 = synth.mano_inputs(6, seed=71 if side == "left" else 72)   # = mano_lbs.npz inputs
+        with torch.no_grad():
+            o = mm(betas=shape2.clone(), global_orient=rot2.clone(), hand_pose=pose2.clone(), transl=trans2.clone(),
+                   using_wrist_rotate=True)
+            out["model_v_" + side] = o.vertices.numpy()
+            out["model_j16_" + side] = o.joints.numpy()
+            out["model_j21_" + side] = torch.matmul(mm.full_regressor, o.vertices).numpy()
+    save("mano_extra", **out)
+
+
 def main():
     ref = ref_import.load_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if len(sys.argv) > 1:                               # python oracle/make_golden.py mano_extra ...
+        for name in sys.argv[1:]:
+            globals()["golden_" + name](ref)
+        return
     golden_knn_level1(ref)
     golden_knn_level2(ref)
     golden_gather(ref)
@@ -390,6 +441,7 @@ def main():
     ref_dec = ref_import.load_decoder()
     export_gcn_assets(ref_dec)
     golden_gcn_decoder(ref_dec)
+    golden_mano_extra(ref)
 
 
 if __name__ == "__main__":

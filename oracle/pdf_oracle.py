@@ -437,18 +437,24 @@ MANO_TIPS = {"left": [745, 317, 445, 556, 673], "right": [745, 317, 444, 556, 67
 
 
 def mano_lbs(tables, root_rotation, pose, shape, trans=None, scale=None, side="left",
-             center_idx=None, new_skel=False):
-    """ManoLayer.forward with use_pca=False, lib/models/networks/manolayer.py:257-334.
+             center_idx=None, new_skel=False, use_pca=False):
+    """ManoLayer.forward, lib/models/networks/manolayer.py:257-334.
     tables: dict with v_template [778,3], shapedirs [778,3,10], posedirs [778,3,135],
-    J_regressor [16,778] dense, weights [778,16] (f32).  Inputs are axis-angle
-    root [B,3], pose [B,45], shape [B,10].  Returns (v [B,778,3], j [B,21,3])."""
+    J_regressor [16,778] dense, weights [778,16] (f32) (+ hands_components [45,45], hands_mean [45]
+    for use_pca).  use_pca=False (:268-272): axis-angle root [B,3] and pose [B,45].  use_pca=True
+    (:266-267): root is a rotation MATRIX [B,3,3] used as is (:285) and pose holds PCA coefficients
+    [B,ncomps] (pca2axis, :159-162).  shape [B,10].  Returns (v [B,778,3], j [B,21,3])."""
     T = {k: torch.as_tensor(np.asarray(v), dtype=torch.float32) for k, v in tables.items()
-         if k in ("v_template", "shapedirs", "posedirs", "J_regressor", "weights")}
+         if k in ("v_template", "shapedirs", "posedirs", "J_regressor", "weights", "hands_components", "hands_mean")}
     root_rotation = torch.as_tensor(root_rotation, dtype=torch.float32)
     pose = torch.as_tensor(pose, dtype=torch.float32)
     shape = torch.as_tensor(shape, dtype=torch.float32)
     bs = root_rotation.shape[0]
-    Rroot = rodrigues(root_rotation.reshape(-1, 3)).view(bs, 3, 3)
+    if use_pca:
+        pose = pose.mm(T["hands_components"][:pose.shape[1]]) + T["hands_mean"]
+        Rroot = root_rotation.reshape(bs, 3, 3)
+    else:
+        Rroot = rodrigues(root_rotation.reshape(-1, 3)).view(bs, 3, 3)
     Rpose = rodrigues(pose.reshape(-1, 3)).view(bs, 15, 3, 3)
     v_shaped = T["v_template"] + torch.matmul(T["shapedirs"], shape.permute(1, 0)).permute(2, 0, 1)
     j_tpose = torch.matmul(T["J_regressor"], v_shaped)
@@ -489,6 +495,22 @@ def mano_lbs(tables, root_rotation, pose, shape, trans=None, scale=None, side="l
         j[:, 13] = (v[:, 148] + v[:, 290]) / 2
         j[:, 17] = (v[:, 770] + v[:, 83]) / 2
     return v, j
+
+
+def full_regressor(J_regressor):
+    """ManoModel.process_J_regressor, lib/models/hand3d/Mano_model.py:309-323: the 16-row rest-joint
+    regressor plus one-hot rows for the five finger-tip vertices (745, 317, 444, 556, 673 - the SAME
+    indices for both hands, unlike ManoLayer's tips), reordered to the 21-joint convention.  [21,778]."""
+    J = torch.as_tensor(np.asarray(J_regressor), dtype=torch.float32)
+    tips = torch.zeros((5, J.shape[1]))
+    for r, v in enumerate((745, 317, 444, 556, 673)):
+        tips[r, v] = 1.0
+    return torch.cat([J, tips], 0)[MANO_NEW_ORDER].contiguous()
+
+
+def regress_joints(reg, verts):
+    """joints = full_regressor @ verts (demo.py:217-218, simplified.py:431-434): [21,778] x [B,778,3]."""
+    return torch.matmul(torch.as_tensor(reg, dtype=torch.float32), torch.as_tensor(verts, dtype=torch.float32))
 
 
 # ----------------------------------------------------------------------------

@@ -66,7 +66,8 @@ class _StubModule(types.ModuleType):
     def __getattr__(self, name):
         if name.startswith("__"):
             raise AttributeError(name)
-        cls = type(name, (_ChStub,), {})
+        # __module__ = the stubbed package: Mano_model.to_np (:543) recognises chumpy objects by their type string
+        cls = type(name, (_ChStub,), {"__module__": self.__name__})
         setattr(self, name, cls)
         return cls
 

@@ -18,6 +18,7 @@ _COMPUTE = {
     "HandFusion": "encoder", "CenterFeatures": "encoder", "depth2pcl": "encoder", "depth2pcl_batched": "encoder",
     "get_points_coordinate": "encoder", "ManoLayer": "manolayer", "Split_coeff": "manolayer",
     "mano_tail": "manolayer", "mano_tail_pair": "manolayer", "patch_reference": "patch",
+    "rodrigues_batch": "manolayer", "process_J_regressor": "manolayer", "regress_joints": "manolayer",
     "decoder": "decoder", "load_decoder": "decoder", "CapturedStep": "graph", "pointnet_plus_train": "training", "hand_fusion_train": "training",
     "allreduce_gradients": "training",
 }

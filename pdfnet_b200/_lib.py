@@ -6,6 +6,7 @@ non-CUDA tensor.
 """
 import ctypes
 import os
+import threading
 
 import torch
 
@@ -38,6 +39,9 @@ SIGNATURES = {
     "pdf_backproject": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
     "pdf_depth2pcl": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "pdf_mano_lbs": [_vp] * 11 + [_i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
+    "pdf_mano_lbs_rootmat": [_vp] * 11 + [_i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
+    "pdf_rodrigues": [_vp, _i64, _vp, _vp],
+    "pdf_joint_regress": [_vp, _i32, _vp, _i64, _vp, _vp],
     "pdf_mano_pose_feature": [_vp, _vp, _i64, _vp, _vp],
     "pdf_split_coeff": [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "pdf_rows_to_image_t": [_vp, _i64, _i64, _i32, _i32, _vp, _i64, _i32, _vp],
@@ -104,23 +108,45 @@ def launch_count():
     return int(load().pdf_launch_count())
 
 
+_tls = threading.local()      # device index of the CUDA tensors whose pointers ptr() handed out for the pending call
+
+
 def call(name, *args):
+    """Run one C-ABI entry point.  The kernel is enqueued on the device that owns the tensors passed through
+    ptr() (not on whatever device happens to be current) and on that device's current stream (see stream())."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    dev = getattr(_tls, "dev", None)
+    _tls.dev = None
+    if dev is not None and dev != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            rc = getattr(lib, name)(*args)
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.pdf_last_error().decode("utf-8", "replace")
         raise RuntimeError("%s failed (%d): %s" % (name, rc, msg))
 
 
 def ptr(t):
-    """Device pointer of a tensor (None -> NULL)."""
+    """Device pointer of a tensor (None -> NULL).  All CUDA tensors of one call must live on one device."""
     if t is None:
         return None
+    if t.is_cuda:
+        dev = getattr(_tls, "dev", None)
+        if dev is None:
+            _tls.dev = t.device.index
+        elif dev != t.device.index:
+            _tls.dev = None
+            raise RuntimeError("pdfnet_b200: tensors of one call live on different devices (cuda:%d and %s)"
+                               % (dev, t.device))
     return ctypes.c_void_p(t.data_ptr())
 
 
 def stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Current stream of the device of the tensors already passed through ptr() (the stream argument is the
+    last one of every entry point), else of the current device."""
+    dev = getattr(_tls, "dev", None)
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 def require_cuda(*tensors):

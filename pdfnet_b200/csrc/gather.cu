@@ -4,6 +4,10 @@
 
 namespace pdf {
 
+// A gather index outside the map never touches memory outside it (the reference's torch.gather raises a
+// device assert instead; PDF_CHECK_INDICES=1 on the Python side reproduces that).
+__device__ __forceinline__ int64_t clamp_index(int64_t i, int64_t n) { return i < 0 ? 0 : (i >= n ? n - 1 : i); }
+
 // out[b,i,c] = feat[b/cpf, c, ind[b,i]] ; thread per output element, c fastest so
 // stores are coalesced; loads hit one 32 B sector each (NCHW hand-off).
 __global__ void gather_nchw_kernel(const float* __restrict__ feat, int clouds_per_frame, int C, int64_t HW,
@@ -15,7 +19,7 @@ __global__ void gather_nchw_kernel(const float* __restrict__ feat, int clouds_pe
     const int64_t bi = e / C;
     const int i = (int)(bi % n);
     const int64_t b = bi / n;
-    const int64_t pix = ind[b * ind_stride + i];
+    const int64_t pix = clamp_index(ind[b * ind_stride + i], HW);
     out[e] = __ldg(feat + ((b / clouds_per_frame) * C + c) * HW + pix);
   }
 }
@@ -62,7 +66,7 @@ __device__ __forceinline__ void gather_level(const float* __restrict__ plane0, i
       const int e = e0 + u * blockDim.x;
       if (e < hi) {
         const int i = e / C, c = e - i * C;
-        const int pix = (int)ch[i];
+        const int pix = (int)clamp_index(ch[i], (int64_t)R * R);
         const int pl = (pix / R / div) * Rl + (pix % R) / div;       // intaghand_encoder.py:125-126
         v[u] = __ldg(plane0 + (int64_t)c * HW + pl);
       }
@@ -89,7 +93,7 @@ __device__ __forceinline__ void gather_level_window(const float* __restrict__ pl
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int x0 = 1 << 30, x1 = -1, y0 = 1 << 30, y1 = -1;
   for (int i = tid; i < n; i += blockDim.x) {
-    const int pix = (int)ch[i];
+    const int pix = (int)clamp_index(ch[i], (int64_t)R * R);
     const int px = (pix % R) / div, py = pix / R / div;
     x0 = min(x0, px); x1 = max(x1, px); y0 = min(y0, py); y1 = max(y1, py);
   }
@@ -127,7 +131,7 @@ __device__ __forceinline__ void gather_level_window(const float* __restrict__ pl
     }
     __syncthreads();
     for (int i = tid; i < n; i += blockDim.x) {
-      const int pix = (int)ch[i];
+      const int pix = (int)clamp_index(ch[i], (int64_t)R * R);
       const int off = (pix / R / div - y0) * Wa + ((pix % R) / div - x0a);
       float v[CG];
 #pragma unroll
@@ -139,7 +143,7 @@ __device__ __forceinline__ void gather_level_window(const float* __restrict__ pl
   } else {
     for (int e = tid; e < n * CG; e += blockDim.x) {
       const int i = e / CG, c = e - i * CG;
-      const int pix = (int)ch[i];
+      const int pix = (int)clamp_index(ch[i], (int64_t)R * R);
       out[(int64_t)i * C + c0 + c] = __ldg(plane0 + (int64_t)(c0 + c) * HW + (pix / R / div) * Rl + (pix % R) / div);
     }
   }
@@ -168,7 +172,7 @@ pyramid_gather_kernel(const float* __restrict__ xyz, const int64_t* __restrict__
     __syncthreads();
     const float* base = l0 + f * 3 * RR;
     for (int i = threadIdx.x; i < n_points; i += blockDim.x) {
-      const int64_t pix = ch[i];
+      const int64_t pix = clamp_index(ch[i], RR);
       float e[3], p[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -208,7 +212,7 @@ __device__ __forceinline__ void gather_rows_nhwc(const float* __restrict__ src, 
         const int e = e0 + u * blockDim.x;
         if (e < e_hi) {
           const int i = e / cq, q = e - i * cq;
-          const int pix = (int)ch[i];
+          const int pix = (int)clamp_index(ch[i], (int64_t)R * R);
           const int64_t p = (int64_t)(pix / R / div) * Rl + (pix % R) / div;
           v[u] = __ldg(reinterpret_cast<const float4*>(src + p * C) + q);
         }
@@ -222,7 +226,7 @@ __device__ __forceinline__ void gather_rows_nhwc(const float* __restrict__ src, 
   } else {
     for (int e = lo * C + threadIdx.x; e < hi * C; e += blockDim.x) {
       const int i = e / C, c = e - i * C;
-      const int pix = (int)ch[i];
+      const int pix = (int)clamp_index(ch[i], (int64_t)R * R);
       const int64_t p = (int64_t)(pix / R / div) * Rl + (pix % R) / div;
       out[e] = __ldg(src + p * C + c);
     }
@@ -248,7 +252,7 @@ pyramid_gather_nhwc_kernel(const float* __restrict__ xyz, const int64_t* __restr
     __syncthreads();
     const float* base = l0 + f * 3 * (int64_t)R * R;
     for (int i = threadIdx.x; i < n_points; i += blockDim.x) {
-      const int64_t pix = ch[i];
+      const int64_t pix = clamp_index(ch[i], (int64_t)R * R);
       float e[3], p[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -279,7 +283,7 @@ __global__ void gather_nhwc_kernel(const float* __restrict__ feat, int clouds_pe
     const int64_t bi = e / C;
     const int64_t b = bi / n;
     const int i = (int)(bi - b * n);
-    out[e] = __ldg(feat + ((b / clouds_per_frame) * HW + ind[b * ind_stride + i]) * C + c);
+    out[e] = __ldg(feat + ((b / clouds_per_frame) * HW + clamp_index(ind[b * ind_stride + i], HW)) * C + c);
   }
 }
 
@@ -364,7 +368,7 @@ __global__ void center_im2col_kernel(const float* __restrict__ x0, const int64_t
     const int pos = (int)(row % 9);
     const int64_t bh = row / 9;                        // b * 2 + hand
     const int64_t b = bh >> 1;
-    const int centre = (int)ind[bh];
+    const int centre = (int)clamp_index(ind[bh], (int64_t)H * W);
     const int py = centre / W + pos / 3 - 1, px = centre % W + pos % 3 - 1;
     const int tap = k / C, c = k - tap * C;
     const int y = py + tap / 3 - 1, x = px + tap % 3 - 1;

@@ -22,7 +22,7 @@ struct ManoTables {                      // one side's constants (see include/pd
 constexpr int HPC = 1;
 
 __global__ void __launch_bounds__(256)
-mano_lbs_kernel(ManoTables T0, ManoTables T1, int pair,
+mano_lbs_kernel(ManoTables T0, ManoTables T1, int pair, int root_is_mat,
                 const float* __restrict__ root, const float* __restrict__ pose, const float* __restrict__ shape,
                 const float* __restrict__ trans, const float* __restrict__ scale, int64_t n_hands, Tips tips0,
                 Tips tips1, int center_idx, int new_skel, const float* __restrict__ v_tpose_in,
@@ -54,7 +54,7 @@ mano_lbs_kernel(ManoTables T0, ManoTables T1, int pair,
     float val = 0.f;
     if (hh < nh) {
       const int64_t h = h0 + hh;
-      val = k < 3 ? root[h * 3 + k] : (k < 48 ? pose[h * 45 + k - 3] : shape[h * 10 + k - 48]);
+      val = k < 3 ? (root_is_mat ? 0.f : root[h * 3 + k]) : (k < 48 ? pose[h * 45 + k - 3] : shape[h * 10 + k - 48]);
     }
     if (k < 48) s_aa[hh][k] = val; else s_beta[hh][k - 48] = val;
   }
@@ -73,7 +73,9 @@ mano_lbs_kernel(ManoTables T0, ManoTables T1, int pair,
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float ll = L[r * 3] * L[c] + L[r * 3 + 1] * L[3 + c] + L[r * 3 + 2] * L[6 + c];
-        const float v = (r == c ? 1.f : 0.f) + sn * L[r * 3 + c] + oc * ll;
+        float v = (r == c ? 1.f : 0.f) + sn * L[r * 3 + c] + oc * ll;
+        // use_pca layers receive the root rotation as a 3x3 matrix and use it as is (manolayer.py:266-267,285)
+        if (jn == 0 && root_is_mat) v = root[(h0 + hh) * 9 + r * 3 + c];
         s_R[hh][jn][r * 3 + c] = v;
         if (jn > 0) s_pf[hh][(jn - 1) * 9 + r * 3 + c] = v - (r == c ? 1.f : 0.f);
       }
@@ -246,12 +248,67 @@ __global__ void mano_pose_feature_kernel(const float* __restrict__ pose, const f
     }
 }
 
+// rodrigues_batch (manolayer.py:32-48): axis-angle [n,3] -> rotation matrices [n,3,3]; one thread per rotation.
+__global__ void rodrigues_kernel(const float* __restrict__ axis, int64_t n, float* __restrict__ Rm) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float ax = axis[i * 3], ay = axis[i * 3 + 1], az = axis[i * 3 + 2];
+  const float angle = sqrtf(ax * ax + ay * ay + az * az) + 1e-8f;
+  const float x = ax / angle, y = ay / angle, z = az / angle;
+  const float sn = sinf(angle), oc = 1.f - cosf(angle);
+  const float L[9] = {0.f, -z, y, z, 0.f, -x, -y, x, 0.f};
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float ll = L[r * 3] * L[c] + L[r * 3 + 1] * L[3 + c] + L[r * 3 + 2] * L[6 + c];
+      Rm[i * 9 + r * 3 + c] = (r == c ? 1.f : 0.f) + sn * L[r * 3 + c] + oc * ll;
+    }
+}
+
+// joints[h, j, c] = sum_v reg[j, v] * verts[h, v, c]   (full_regressor @ verts, Mano_model.py:309-323,
+// demo.py:217-218).  One CTA per mesh: the 778x3 vertices are staged in shared memory, one warp per output
+// (j, c), lanes stride over the vertices of the dense (L2-resident, 65 KB) regressor row.
+__global__ void __launch_bounds__(256)
+joint_regress_kernel(const float* __restrict__ reg, int n_joints, const float* __restrict__ verts,
+                     float* __restrict__ joints) {
+  __shared__ float s_v[NE];
+  const int64_t h = blockIdx.x;
+  for (int e = threadIdx.x; e < NE; e += 256) s_v[e] = verts[h * NE + e];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = warp; o < n_joints * 3; o += 8) {
+    const int jn = o / 3, c = o - jn * 3;
+    float a = 0.f;
+    for (int v = lane; v < NV; v += 32) a = fmaf(__ldg(reg + jn * NV + v), s_v[v * 3 + c], a);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+    if (lane == 0) joints[(h * n_joints + jn) * 3 + c] = a;
+  }
+}
+
 }  // namespace pdf
+
+extern "C" int pdf_rodrigues(const float* axis, int64_t n, float* rot, void* stream) {
+  if (n == 0) return PDF_OK;
+  PDF_REQUIRE(axis && rot && n > 0, PDF_ERR_BAD_ARG, "pdf_rodrigues: null pointer / bad size");
+  pdf::rodrigues_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(axis, n, rot);
+  return pdf::check_launch("pdf_rodrigues");
+}
+
+extern "C" int pdf_joint_regress(const float* reg, int n_joints, const float* verts, int64_t n, float* joints,
+                                 void* stream) {
+  if (n == 0) return PDF_OK;
+  PDF_REQUIRE(reg && verts && joints, PDF_ERR_BAD_ARG, "pdf_joint_regress: null pointer");
+  PDF_REQUIRE(n > 0 && n_joints > 0 && n_joints <= 64, PDF_ERR_BAD_ARG, "pdf_joint_regress: bad size");
+  pdf::joint_regress_kernel<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(reg, n_joints, verts, joints);
+  return pdf::check_launch("pdf_joint_regress");
+}
 
 static int mano_lbs_launch(const pdf::ManoTables& T0, const pdf::ManoTables& T1, int pair, const float* root,
                            const float* pose, const float* shape, const float* trans, const float* scale, int64_t n,
                            const int32_t* tip0, const int32_t* tip1, int center_idx, int new_skel,
-                           const float* v_tpose, float* v, float* j, void* stream);
+                           const float* v_tpose, float* v, float* j, void* stream, int root_is_mat = 0);
 
 extern "C" int pdf_mano_lbs(const float* v_template, const float* shapedirs_t, const float* posedirs_t,
                             const float* j_template, const float* j_shapedirs, const float* weights_t,
@@ -263,6 +320,18 @@ extern "C" int pdf_mano_lbs(const float* v_template, const float* shapedirs_t, c
   pdf::ManoTables T{v_template, shapedirs_t, posedirs_t, j_template, j_shapedirs, weights_t};
   return mano_lbs_launch(T, T, 0, root, pose, shape, trans, scale, n, tip_idx_host, tip_idx_host, center_idx, new_skel,
                          v_tpose, v, j, stream);
+}
+
+extern "C" int pdf_mano_lbs_rootmat(const float* v_template, const float* shapedirs_t, const float* posedirs_t,
+                                    const float* j_template, const float* j_shapedirs, const float* weights_t,
+                                    const float* root_mat, const float* pose, const float* shape, const float* trans,
+                                    const float* scale, int64_t n, const int32_t* tip_idx_host, int center_idx,
+                                    int new_skel, const float* v_tpose, float* v, float* j, void* stream) {
+  PDF_REQUIRE(v_template && shapedirs_t && posedirs_t && j_template && j_shapedirs && weights_t, PDF_ERR_BAD_ARG,
+              "pdf_mano_lbs_rootmat: null table pointer");
+  pdf::ManoTables T{v_template, shapedirs_t, posedirs_t, j_template, j_shapedirs, weights_t};
+  return mano_lbs_launch(T, T, 0, root_mat, pose, shape, trans, scale, n, tip_idx_host, tip_idx_host, center_idx,
+                         new_skel, v_tpose, v, j, stream, 1);
 }
 
 extern "C" int pdf_mano_lbs_pair(const float* const* tables_left, const float* const* tables_right, const float* root,
@@ -282,7 +351,7 @@ extern "C" int pdf_mano_lbs_pair(const float* const* tables_left, const float* c
 static int mano_lbs_launch(const pdf::ManoTables& T0, const pdf::ManoTables& T1, int pair, const float* root,
                            const float* pose, const float* shape, const float* trans, const float* scale, int64_t n,
                            const int32_t* tip_idx_host, const int32_t* tip1_host, int center_idx, int new_skel,
-                           const float* v_tpose, float* v, float* j, void* stream) {
+                           const float* v_tpose, float* v, float* j, void* stream, int root_is_mat) {
   if (n == 0) return PDF_OK;
   PDF_REQUIRE(root && pose && shape && v && j && tip_idx_host, PDF_ERR_BAD_ARG, "pdf_mano_lbs: null pointer");
   PDF_REQUIRE(n >= 0 && center_idx < 21, PDF_ERR_BAD_ARG, "pdf_mano_lbs: bad size");
@@ -296,7 +365,7 @@ static int mano_lbs_launch(const pdf::ManoTables& T0, const pdf::ManoTables& T1,
   }
   if (n == 0) return PDF_OK;
   pdf::mano_lbs_kernel<<<(unsigned)((n + pdf::HPC - 1) / pdf::HPC), 256, 0, (cudaStream_t)stream>>>(
-      T0, T1, pair, root, pose, shape, trans, scale, n, tips, tips1, center_idx, new_skel, v_tpose, v, j);
+      T0, T1, pair, root_is_mat, root, pose, shape, trans, scale, n, tips, tips1, center_idx, new_skel, v_tpose, v, j);
   return pdf::check_launch("pdf_mano_lbs");
 }
 

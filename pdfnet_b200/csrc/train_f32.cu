@@ -497,7 +497,8 @@ __global__ void group_scatter_add_kernel(const float* __restrict__ dG, const int
     const int g = (int)(bg - b * N1);
     const float d = dG[i];
     if (d == 0.f) continue;
-    const int j = idx[row];
+    int j = idx[row];
+    j = j < 0 ? 0 : (j >= N ? N - 1 : j);        // never scatter outside the cloud
     atomicAdd(dPts + (b * N + j) * ldp + c, d);
     if (c < 3) atomicAdd(dPts + (b * N + g) * ldp + c, -d);
   }
@@ -511,7 +512,8 @@ __global__ void gather_nchw_bwd_kernel(const float* __restrict__ dOut, const int
     const int c = (int)(i % C);
     const int64_t bp = i / C;
     const int64_t b = bp / n;
-    const int64_t pix = ind[bp];
+    int64_t pix = ind[bp];
+    pix = pix < 0 ? 0 : (pix >= HW ? HW - 1 : pix);   // never scatter outside the map (see gather.cu: clamp_index)
     atomicAdd(dFeat + (b * C + c) * HW + pix, dOut[i]);
   }
 }

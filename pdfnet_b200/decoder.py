@@ -8,8 +8,8 @@ state-dict keys (``dual_gcn.layers.{i}.graph_{left,right}.GCN_blocks.{j}.*``,
     result, paramsDict, handDictList, otherInfo = decoder(global_feature_left, global_feature_right, fmaps)
 
 ``fmaps`` is accepted and ignored, as in the reference (the ``img_ex`` calls are commented out,
-``model_attn/DualGraph.py:84-85``; the ``img_ex_*`` parameters of a reference checkpoint are skipped
-on load).  Dense layers run on the GEMM kernels (``precision='fp32'``: FFMA; ``'bf16x3'`` (alias
+``model_attn/DualGraph.py:84-85``; the ``img_ex_*`` parameters of a reference checkpoint are carried as
+inert holders so state dicts round-trip between the two models).  Dense layers run on the GEMM kernels (``precision='fp32'``: FFMA; ``'bf16x3'`` (alias
 ``'bf16'``): tcgen05 with split-bf16 operands, fp32-accurate - both hold the 1e-4 parity.  Plain bf16
 operands were measured and dropped: after ~40 chained layers the scale / translation heads drift by
 5-9 % for a 5 % shorter step); each run of glue between two GEMMs is one fused kernel
@@ -83,18 +83,54 @@ class _InterAttn(nn.Module):
         self.ffL, self.ffR = _MLPRes(f), _MLPRes(f)
 
 
+class _ImgFeatToGrid(nn.Module):
+    """model_attn/img_attn.py:38-51 - parameters only (see _ImgEx)."""
+
+    def __init__(self, img_size, img_f_dim, grid_size, grid_f_dim):
+        super(_ImgFeatToGrid, self).__init__()
+        self.position_embeddings = nn.Embedding(grid_size * grid_size, grid_f_dim)
+        patch = img_size // grid_size
+        self.proj = nn.Conv2d(img_f_dim, grid_f_dim, kernel_size=patch, stride=patch)
+        self.self_attn = _SelfAttn(grid_f_dim)
+
+
+class _ImgAttn(nn.Module):
+    """model_attn/img_attn.py:72-79 - parameters only."""
+
+    def __init__(self, verts_f_dim, img_f_dim):
+        super(_ImgAttn, self).__init__()
+        self.fc = nn.Linear(img_f_dim, verts_f_dim)
+        self.Attn = _SelfAttn(verts_f_dim)
+
+
+class _ImgEx(nn.Module):
+    """model_attn/img_attn.py:97-111.  The reference constructs ``img_ex_left`` / ``img_ex_right`` in every
+    DualGraphLayer but never calls them (DualGraph.py:84-85), so their tensors live in every reference checkpoint.
+    They are kept here as inert parameter holders: a state dict saved from either model loads into the other
+    with no missing or unexpected key."""
+
+    def __init__(self, img_size, img_f_dim, grid_size, grid_f_dim, verts_f_dim):
+        super(_ImgEx, self).__init__()
+        self.encoder = _ImgFeatToGrid(img_size, img_f_dim, grid_size, grid_f_dim)
+        self.attn = _ImgAttn(verts_f_dim, grid_f_dim)
+
+
 class _DualGraphLayer(nn.Module):
-    def __init__(self, V, cin, cout, k, n):
+    def __init__(self, V, cin, cout, k, n, img=None):
         super(_DualGraphLayer, self).__init__()
         self.position_embeddings = nn.Embedding(V, cin)
         self.graph_left, self.graph_right = _GraphLayer(cin, cout, k, n), _GraphLayer(cin, cout, k, n)
+        if img is not None:                                    # (img_size, img_f_dim, grid_size, grid_f_dim)
+            self.img_ex_left, self.img_ex_right = _ImgEx(*img, cout), _ImgEx(*img, cout)
         self.attn = _InterAttn(cout)
 
 
 class _DualGraph(nn.Module):
-    def __init__(self, verts, cins, couts, k, n):
+    def __init__(self, verts, cins, couts, k, n, img=None):
         super(_DualGraph, self).__init__()
-        self.layers = nn.ModuleList([_DualGraphLayer(V, ci, co, k, n) for V, ci, co in zip(verts, cins, couts)])
+        img = img or [None] * len(verts)
+        self.layers = nn.ModuleList([_DualGraphLayer(V, ci, co, k, n, im)
+                                     for V, ci, co, im in zip(verts, cins, couts, img)])
 
 
 def _csr(dense):
@@ -113,7 +149,8 @@ class decoder(nn.Module):
     ``gcn_core/*.pkl`` (``oracle/make_golden.export_gcn_assets`` writes them as ``gcn_assets.npz``)."""
 
     def __init__(self, assets, global_feature_dim=1024, gcn_in_dim=(512, 256, 128), gcn_out_dim=(256, 128, 64),
-                 graph_k=2, graph_layer_num=4, vertex_num=778, num_attn_heads=4, precision="fp32"):
+                 graph_k=2, graph_layer_num=4, vertex_num=778, num_attn_heads=4, precision="fp32",
+                 f_in_Dim=(256, 256, 256, 256), f_out_Dim=(256, 128, 64), img_ex_params=True):
         super(decoder, self).__init__()
         if precision not in ("fp32", "bf16x3", "bf16"):
             raise ValueError("decoder: precision must be 'fp32' or 'bf16x3' ('bf16' is an alias of the latter)")
@@ -139,7 +176,10 @@ class decoder(nn.Module):
             for i in range(3):
                 for name, t in zip(("rowptr", "colidx", "vals"), _csr(assets["L_%s_%d" % (side, i)])):
                     self.register_buffer("_L_%s_%d_%s" % (side, i, name), t, persistent=False)
-        self.dual_gcn = _DualGraph(self.verts, gcn_in_dim, gcn_out_dim, graph_k, graph_layer_num)
+        # inert img_ex_* parameter holders with the reference's shapes (intaghand_decoder.py:121-138:
+        # img_size [12,24,48], grid_size 6, img_f_dim = f_in_Dim[:3], grid_f_dim = f_out_Dim)
+        img = [(s, fi, 6, fo) for s, fi, fo in zip((12, 24, 48), list(f_in_Dim)[:3], f_out_Dim)] if img_ex_params else None
+        self.dual_gcn = _DualGraph(self.verts, gcn_in_dim, gcn_out_dim, graph_k, graph_layer_num, img)
         for side in ("left", "right"):
             setattr(self, "gf_layer_" + side, nn.Sequential(nn.Linear(global_feature_dim, gcn_in_dim[0] - 3),
                                                             nn.LayerNorm(gcn_in_dim[0] - 3, eps=1e-6)))
@@ -160,14 +200,18 @@ class decoder(nn.Module):
         return self.converter
 
     def load_state_dict(self, state_dict, strict=True, **kw):
-        # a reference checkpoint also holds the img_ex_* sub-modules whose call is commented out
-        state_dict = {k: v for k, v in state_dict.items() if "img_ex_" not in k}
+        state_dict = dict(state_dict)
+        have = any("img_ex_" in k for k in self.state_dict())
+        if not have:                                                # built with img_ex_params=False
+            state_dict = {k: v for k, v in state_dict.items() if "img_ex_" not in k}
+        elif not any("img_ex_" in k for k in state_dict):           # a hot-path-only state: keep the inert holders
+            state_dict.update({k: v for k, v in self.state_dict().items() if "img_ex_" in k})
         state_dict.setdefault("dense_coor", self.dense_coor)        # an asset, already set by the constructor
         return super(decoder, self).load_state_dict(state_dict, strict=strict, **kw)
 
     # -- concatenated / re-laid weights, rebuilt when a parameter changes --
     def _weights(self):
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = tuple((p.data_ptr(), p._version) for n, p in self.named_parameters() if "img_ex_" not in n)
         if key == self._cache_key:
             return self._cache
         c = {}
@@ -291,7 +335,11 @@ class decoder(nn.Module):
 
     def forward(self, global_feature_left, global_feature_right, fmaps=None):
         if self.training:
-            raise NotImplementedError("pdfnet_b200.decoder: inference only (call .eval())")
+            raise NotImplementedError("pdfnet_b200.decoder: inference only (call .eval()); for training keep the "
+                                      "reference decoder: patch_reference(mode='training')")
+        if torch.is_grad_enabled() and (global_feature_left.requires_grad or global_feature_right.requires_grad):
+            raise RuntimeError("pdfnet_b200.decoder has no backward (inference only): its inputs require grad; run it "
+                               "under torch.no_grad() or keep the reference decoder with patch_reference(mode='training')")
         L.require_cuda(global_feature_left, global_feature_right)
         with torch.no_grad():
             c = self._weights()
@@ -389,4 +437,6 @@ def load_decoder(cfg, encoder_info, precision="bf16x3"):
         up = pickle.load(f)
     return decoder(assets_from_graph_dicts(left, right, dense, up), global_feature_dim=encoder_info["global_feature_dim"],
                    gcn_in_dim=cfg.GCN_IN_DIM, gcn_out_dim=cfg.GCN_OUT_DIM, graph_k=cfg.graph_k,
-                   graph_layer_num=cfg.graph_layer_num, precision=precision)
+                   graph_layer_num=cfg.graph_layer_num, precision=precision,
+                   f_in_Dim=encoder_info.get("fmaps_dim", (256, 256, 256, 256)),
+                   f_out_Dim=getattr(cfg, "IMG_DIMS", (256, 128, 64)))

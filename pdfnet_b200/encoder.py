@@ -5,8 +5,10 @@ Reference: lib/models/networks/intaghand_encoder.py — ``PointNet_Plus`` :32-15
 ``ResNetSimple.forward`` :805-813 — and lib/models/utils.py:22-26.  Class names,
 constructor arguments, parameter names (state-dict keys) and forward signatures
 are the reference's, so a reference checkpoint loads unchanged; the bodies call
-the sm_100a kernels through the C ABI.  Inference (eval-mode BatchNorm, folded on
-the host) only in this round.
+the sm_100a kernels through the C ABI.  Under ``torch.no_grad()`` (or when nothing
+requires grad) the modules run the fused inference kernels; when an autograd graph
+is expected (``.train()``, or ``.eval()`` with grad enabled and trainable inputs /
+parameters) they dispatch to the differentiable path in ``training.py``.
 """
 import math
 
@@ -23,8 +25,24 @@ nstates_plus_2 = [128, 128, 256]
 nstates_plus_3 = [512, 512, 1024, 1024, 512]
 
 
+def _grad_needed(module, *tensors):
+    """True when the caller expects an autograd graph: grad mode is on and a parameter of ``module`` or one of
+    ``tensors`` requires grad.  The fused inference kernels have no backward, so such calls are routed to
+    the differentiable path (training.py) instead of silently returning detached tensors."""
+    if not torch.is_grad_enabled():
+        return False
+    if any(t is not None and torch.is_tensor(t) and t.requires_grad for t in tensors):
+        return True
+    return module is not None and any(p.requires_grad for p in module.parameters())
+
+
 def _tranpose_and_gather_feat(feat, ind):
-    """lib/models/utils.py:22-26: feat [B,C,H,W], ind [B,n] int64 -> [B,n,C] (no full-map copy)."""
+    """lib/models/utils.py:22-26: feat [B,C,H,W], ind [B,n] int64 -> [B,n,C] (no full-map copy).
+    Differentiable w.r.t. ``feat`` (the reference gathers from maps that carry gradients:
+    intaghand_encoder.py:792,816-817, simplified.py:698-699): the backward is pdf_gather_nchw_bwd."""
+    if _grad_needed(None, feat):
+        from .training import GatherNCHWFn
+        return GatherNCHWFn.apply(feat, ind)
     return ops.gather_nchw(feat, ind)
 
 
@@ -78,10 +96,11 @@ class SFTLayer(nn.Module):
         B, Cf, n = fea.shape
         fea_rows = L.f32c(fea.transpose(1, 2)).view(B * n, Cf)
         cond_rows = L.f32c(cond).view(B * n, -1)
-        if self.training and torch.is_grad_enabled():
+        if _grad_needed(self, fea, cond):                   # train or eval mode alike (no BatchNorm in this layer)
             from .training import sft_rows
             return sft_rows(self, fea_rows, cond_rows).view(B, n, Cf)
-        return self.apply_rows(fea_rows, cond_rows).view(B, n, Cf)
+        with torch.no_grad():
+            return self.apply_rows(fea_rows, cond_rows).view(B, n, Cf)
 
     def packed_sft0(self):
         """48 floats in the layout pdf_pyramid_gather expects (only for c_fea=c_cond=3)."""
@@ -197,12 +216,16 @@ class PointNet_Plus(nn.Module):
         return tc
 
     def forward(self, points, emb, choose, clouds_per_frame=1):
-        if self.training:
-            # train-mode BatchNorm + autograd through every stage (fp32 kernels, training.py)
+        if self.training or _grad_needed(self, points, *emb):
+            # autograd through every stage (training.py): train-mode BatchNorm statistics in .train(), folded
+            # running statistics in .eval() with grad enabled (fine-tuning with frozen BatchNorm)
             from .training import pointnet_plus_train
             if clouds_per_frame != 1:
-                raise RuntimeError("PointNet_Plus (training): one cloud per frame per call, as the reference "
-                                   "(intaghand_encoder.py:805-806); BatchNorm statistics are per call")
+                if self.training:
+                    raise RuntimeError("PointNet_Plus (training): one cloud per frame per call, as the reference "
+                                       "(intaghand_encoder.py:805-806); BatchNorm statistics are per call")
+                f = torch.arange(points.shape[0], device=points.device) // clouds_per_frame
+                emb = [e[f] for e in emb]
             return pointnet_plus_train(self, points, emb, choose)
         L.require_cuda(points, choose, *emb)
         with torch.no_grad():
@@ -365,11 +388,9 @@ class HandFusion(nn.Module):
         """cloud [B,2,N,3], choose [B,2,N], center_features [B,2,1024] ->
         fuse_feat [B,2,1024] (and theta [B,2,122] = (point2mano_left, point2mano_right))."""
         B, H, N, _ = cloud.shape
-        if self.training:
+        if self.training or _grad_needed(self, cloud, center_features, *point_wise_emb):
             from .training import hand_fusion_train
-            if with_mano:
-                raise RuntimeError("HandFusion (training): the MANO head branch is inference only")
-            return hand_fusion_train(self, cloud, point_wise_emb, choose, center_features)
+            return hand_fusion_train(self, cloud, point_wise_emb, choose, center_features, with_mano=with_mano)
         feat = self.pointnet_plus(cloud.reshape(B * H, N, 3), point_wise_emb, choose.reshape(B * H, N),
                                   clouds_per_frame=H)                       # [2B,1,1024]
         rows = feat.view(B * H, 1024)
@@ -485,6 +506,10 @@ class CenterFeatures(nn.Module):
     def forward(self, x0, ind):
         """x0 [B,C,H,W] fp32 (the 1/4-resolution feature map), ind [B,2] -> center_features [B,2,c_out]."""
         L.require_cuda(x0, ind)
+        if _grad_needed(self, x0):
+            # training: the reference's own two full-map convolutions (they belong to the RGB network, which
+            # stays stock PyTorch) followed by the differentiable centre gather (intaghand_encoder.py:790-792)
+            return _tranpose_and_gather_feat(self.center_feat_up1(self.center_feat_up0(x0)), ind)
         with torch.no_grad():
             B = x0.shape[0]
             w0, w1 = self._weights(x0.device)

@@ -1,7 +1,7 @@
 """MANO tail: ``ManoLayer`` (linear blend skinning) and ``Split_coeff``.
 
-Reference: lib/models/networks/manolayer.py:100-334 and
-lib/models/hand3d/Mano_render.py:145-194.  Same constructor and forward signature;
+Reference: lib/models/networks/manolayer.py:32-48,100-334, lib/models/hand3d/Mano_render.py:145-194
+and the 21x778 joint regressor of lib/models/hand3d/Mano_model.py:309-323.  Same constructor and forward signature;
 the forward is one ``pdf_mano_lbs`` launch (one CTA per hand) instead of ~100
 small bmm/cat launches.
 """
@@ -120,7 +120,24 @@ class ManoLayer(Module):
         return self.train(False)
 
     def pca2axis(self, pca):
+        """:159-162"""
         return pca.mm(self.hands_components[:pca.shape[1]]) + self.hands_mean
+
+    def axis2pca(self, axis):
+        """:180-184"""
+        return (axis - self.hands_mean).mm(self.hands_components_inv)
+
+    def axis2Rmat(self, axis):
+        """:167-171: axis [bs,45] -> [bs,15,3,3]"""
+        return rodrigues_batch(axis.reshape(-1, 3)).view(-1, 15, 3, 3)
+
+    def myaxis2Rmat(self, axis):
+        """:173-178: axis [bs,3] or [bs,45] -> [bs,-1,3,3]"""
+        return rodrigues_batch(axis.reshape(-1, 3)).view(axis.shape[0], -1, 3, 3)
+
+    def pca2Rmat(self, pca):
+        """:164-165"""
+        return self.axis2Rmat(self.pca2axis(pca))
 
     def _kernel_tables(self, device):
         bufs = (self.v_template, self.shapedirs, self.posedirs, self.J_regressor, self.weights)
@@ -131,23 +148,67 @@ class ManoLayer(Module):
         return self._tables
 
     def forward(self, root_rotation, pose, shape, trans=None, scale=None, side="left"):
-        """root_rotation [bs,3] axis-angle, pose [bs,45] axis-angle (use_pca=False, :268-272) or
-        PCA coefficients [bs,ncomps] (use_pca=True; root_rotation must then also be given as
-        axis-angle — the matrix form of :266-267 is not supported), shape [bs,10],
-        trans [bs,3] or None, scale [bs] or None -> (v [bs,778,3], j [bs,21,3])."""
+        """use_pca=False (:268-272): root_rotation [bs,3] and pose [bs,45] axis-angle.
+        use_pca=True (:266-267, the dataset layers of interhand.py:192,220-223): root_rotation is a rotation
+        MATRIX [bs,3,3] used as is (:285) and pose holds PCA coefficients [bs,ncomps].
+        shape [bs,10], trans [bs,3] or None, scale [bs] or None -> (v [bs,778,3], j [bs,21,3]).
+        Host tensors (the reference's dataset / demo code calls the layer on CPU tensors, demo.py:155,
+        interhand.py:220,568) are staged to the current CUDA device and the result is returned on the host:
+        the skinning always runs in pdf_mano_lbs.  Inference only: a call that expects gradients raises."""
         if side not in TIPS:
             raise ValueError("side must be 'left' or 'right'")
-        if not root_rotation.is_cuda:
-            raise RuntimeError("pdfnet_b200.ManoLayer runs on CUDA tensors only (no CPU fallback)")
+        args = [root_rotation, pose, shape, trans, scale]
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in args):
+            raise RuntimeError("pdfnet_b200.ManoLayer has no backward (inference only); keep the reference layer for "
+                               "losses that differentiate through MANO: patch_reference(mode='training')")
+        host = not root_rotation.is_cuda
+        if host:
+            if not torch.cuda.is_available():
+                raise RuntimeError("pdfnet_b200.ManoLayer needs a CUDA device (no CPU fallback)")
+            dev = torch.device("cuda", torch.cuda.current_device())
+            root_rotation, pose, shape, trans, scale = [t.to(dev) if t is not None else None for t in args]
         bs = root_rotation.shape[0]
-        if self.use_pca:
-            if root_rotation.dim() != 2 or root_rotation.shape[1] != 3:
-                raise NotImplementedError("ManoLayer(use_pca=True): pass root_rotation as axis-angle [bs,3]")
-            pose = self.pca2axis(pose)
         with torch.no_grad():
-            return ops.mano_lbs(self._kernel_tables(root_rotation.device), root_rotation.reshape(bs, 3),
-                                pose.reshape(bs, 45), shape.reshape(bs, 10), trans, scale, TIPS[side],
-                                self.center_idx, self.new_skel)
+            dev = root_rotation.device
+            if self.use_pca:
+                if root_rotation.numel() != bs * 9:
+                    raise RuntimeError("ManoLayer(use_pca=True): root_rotation must be rotation matrices [bs,3,3] "
+                                       "(manolayer.py:258-260,285), got %s" % (tuple(root_rotation.shape),))
+                pose = pose.float()
+                pose = pose.mm(self.hands_components[:pose.shape[1]].to(dev)) + self.hands_mean.to(dev)   # pca2axis
+            elif root_rotation.numel() != bs * 3:
+                raise RuntimeError("ManoLayer(use_pca=False): root_rotation must be axis-angle [bs,3] "
+                                   "(manolayer.py:270), got %s" % (tuple(root_rotation.shape),))
+            v, j = ops.mano_lbs(self._kernel_tables(dev), root_rotation.reshape(bs, -1), pose.reshape(bs, 45),
+                                shape.reshape(bs, 10), trans, scale, TIPS[side], self.center_idx, self.new_skel,
+                                root_is_matrix=self.use_pca)
+        return (v.cpu(), j.cpu()) if host else (v, j)
+
+
+def rodrigues_batch(axis):
+    """manolayer.py:32-48: axis-angle [bs,3] -> rotation matrices [bs,3,3] (pdf_rodrigues); host tensors are
+    staged to the GPU and returned on the host, as in ManoLayer.forward."""
+    if torch.is_grad_enabled() and axis.requires_grad:
+        raise RuntimeError("pdfnet_b200.rodrigues_batch has no backward (inference only)")
+    if axis.is_cuda:
+        return ops.rodrigues(axis)
+    if not torch.cuda.is_available():
+        raise RuntimeError("pdfnet_b200.rodrigues_batch needs a CUDA device (no CPU fallback)")
+    return ops.rodrigues(axis.cuda()).cpu()
+
+
+def process_J_regressor(J_regressor):
+    """ManoModel.process_J_regressor (lib/models/hand3d/Mano_model.py:309-323): [16,778] rest-joint
+    regressor + one-hot finger-tip rows (745, 317, 444, 556, 673 for BOTH hands) in the 21-joint order."""
+    J = J_regressor.detach().float()
+    tips = torch.zeros((5, J.shape[1]), dtype=J.dtype, device=J.device)
+    tips[torch.arange(5), torch.tensor([745, 317, 444, 556, 673])] = 1.0
+    return torch.cat([J, tips], 0)[NEW_ORDER].contiguous()
+
+
+def regress_joints(full_regressor, verts):
+    """joints [B,21,3] = full_regressor [21,778] @ verts [B,778,3] (demo.py:217-218, simplified.py:431-434)."""
+    return ops.joint_regress(full_regressor, verts)
 
 
 def Split_coeff(theta, index, K, input_res=384, down_ratio=4):

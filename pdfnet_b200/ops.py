@@ -4,6 +4,7 @@ Everything here takes and returns CUDA tensors, allocates outputs with torch
 (the library never allocates), and enqueues on torch's current stream.
 """
 import ctypes
+import os
 
 import torch
 
@@ -45,6 +46,17 @@ def fps(xyz, n_sample, start_idx):
     return out
 
 
+CHECK_INDICES = bool(int(os.environ.get("PDF_CHECK_INDICES", "0")))
+
+
+def _check_index(ind, limit, what):
+    """The kernels clamp gather / scatter indices into [0, limit) so a bad index can never touch memory outside
+    the map.  torch.gather (what the reference calls, models/utils.py:15) raises a device-side assert instead;
+    PDF_CHECK_INDICES=1 reproduces that: an asynchronous device assert, no host synchronisation."""
+    if CHECK_INDICES and ind.numel():
+        torch._assert_async(((ind >= 0) & (ind < limit)).all(), "pdfnet_b200: %s index out of range" % what)
+
+
 def _is_nhwc(t):
     """[F,C,H,W] tensor stored channels-last (and not also plain-contiguous, as C == 1 or H*W == 1 would be)."""
     return (t.dim() == 4 and t.dtype == torch.float32 and not t.is_contiguous()
@@ -64,6 +76,9 @@ def gather_nchw(feat, ind, clouds_per_frame=1):
     Fr, C = feat.shape[0], feat.shape[1]
     HW = feat[0, 0].numel()
     B, n = ind.shape
+    if B != Fr * clouds_per_frame:
+        raise RuntimeError("gather_nchw: %d index rows for %d maps x %d clouds per frame" % (B, Fr, clouds_per_frame))
+    _check_index(ind, HW, "gather_nchw")
     out = torch.empty((B, n, C), dtype=torch.float32, device=feat.device)
     L.call("pdf_gather_nhwc" if nhwc else "pdf_gather_nchw", L.ptr(feat), B, clouds_per_frame, C, HW, L.ptr(ind), n,
            ind.stride(0), L.ptr(out), L.stream())
@@ -80,6 +95,14 @@ def pyramid_gather(xyz, choose, emb, sft0_params, n1, n2, R, clouds_per_frame=1)
     l0, l1, l2 = emb if nhwc else (L.f32c(e) for e in emb)
     B, N, _ = xyz.shape
     C1, C2 = l1.shape[1], l2.shape[1]
+    # the index arithmetic (intaghand_encoder.py:125-126) assumes maps of R, R/2 and R/4 pixels a side
+    for lvl, (e, r) in enumerate(((l0, R), (l1, R // 2), (l2, R // 4))):
+        if tuple(e.shape[-2:]) != (r, r):
+            raise RuntimeError("pyramid_gather: level %d map is %s, expected %dx%d for default_resolution=%d"
+                               % (lvl, tuple(e.shape[-2:]), r, r, R))
+    if l0.shape[1] != 3 or l0.shape[0] * clouds_per_frame < B:
+        raise RuntimeError("pyramid_gather: level 0 must be [frames,3,R,R] with frames * clouds_per_frame >= clouds")
+    _check_index(choose, R * R, "pyramid_gather (choose)")
     dev = xyz.device
     pts0 = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
     cond1 = torch.empty((B, n1, C1), dtype=torch.float32, device=dev)
@@ -258,8 +281,28 @@ def depth2pcl(depth, mask, Kinv, valid, subset_keys=None, perm=None, n_points=10
     return choose, cloud, n_cand
 
 
-def mano_lbs(tables, root, pose, shape, trans, scale, tips, center_idx, new_skel):
-    """tables: dict of device tensors in the kernel layout (see manolayer.ManoTables)."""
+def rodrigues(axis):
+    """rodrigues_batch (manolayer.py:32-48): axis-angle [n,3] -> rotation matrices [n,3,3]."""
+    L.require_cuda(axis)
+    axis = L.f32c(axis).reshape(-1, 3)
+    out = torch.empty((axis.shape[0], 3, 3), dtype=torch.float32, device=axis.device)
+    L.call("pdf_rodrigues", L.ptr(axis), axis.shape[0], L.ptr(out), L.stream())
+    return out
+
+
+def joint_regress(reg, verts):
+    """full_regressor @ verts: reg [J,778] fp32, verts [n,778,3] -> joints [n,J,3] (pdf_joint_regress)."""
+    L.require_cuda(reg, verts)
+    reg, verts = L.f32c(reg), L.f32c(verts)
+    assert reg.dim() == 2 and reg.shape[1] == 778 and verts.shape[1:] == (778, 3)
+    out = torch.empty((verts.shape[0], reg.shape[0], 3), dtype=torch.float32, device=verts.device)
+    L.call("pdf_joint_regress", L.ptr(reg), reg.shape[0], L.ptr(verts), verts.shape[0], L.ptr(out), L.stream())
+    return out
+
+
+def mano_lbs(tables, root, pose, shape, trans, scale, tips, center_idx, new_skel, root_is_matrix=False):
+    """tables: dict of device tensors in the kernel layout (see manolayer.ManoTables).
+    root_is_matrix: ``root`` is [n,3,3] rotation matrices (use_pca layers, manolayer.py:266-267)."""
     L.require_cuda(root, pose, shape, trans, scale)
     root, pose, shape = L.f32c(root), L.f32c(pose), L.f32c(shape)
     trans = L.f32c(trans) if trans is not None else None
@@ -274,7 +317,8 @@ def mano_lbs(tables, root, pose, shape, trans, scale, tips, center_idx, new_skel
         X = torch.empty((n, 145), dtype=torch.float32, device=root.device)
         L.call("pdf_mano_pose_feature", L.ptr(pose), L.ptr(shape), n, L.ptr(X), L.stream())
         v_tpose = linear(X, tables["blend_w"], tables["v_template"])
-    L.call("pdf_mano_lbs", L.ptr(tables["v_template"]), L.ptr(tables["shapedirs_t"]), L.ptr(tables["posedirs_t"]),
+    L.call("pdf_mano_lbs_rootmat" if root_is_matrix else "pdf_mano_lbs", L.ptr(tables["v_template"]),
+           L.ptr(tables["shapedirs_t"]), L.ptr(tables["posedirs_t"]),
            L.ptr(tables["j_template"]), L.ptr(tables["j_shapedirs"]), L.ptr(tables["weights_t"]), L.ptr(root),
            L.ptr(pose), L.ptr(shape), L.ptr(trans), L.ptr(scale), n, ctypes.cast(tip_arr, ctypes.c_void_p),
            -1 if center_idx is None else int(center_idx), 1 if new_skel else 0, L.ptr(v_tpose), L.ptr(v), L.ptr(j),
@@ -508,6 +552,7 @@ def gather_nchw_bwd(dout, ind, shape):
     dout = L.f32c(dout)
     ind = ind.long().contiguous()
     B, n, C = dout.shape
+    _check_index(ind, int(shape[2]) * int(shape[3]), "gather_nchw_bwd")
     dfeat = torch.zeros(tuple(shape), dtype=torch.float32, device=dout.device)
     L.call("pdf_gather_nchw_bwd", L.ptr(dout), L.ptr(ind), B, C, dfeat[0, 0].numel(), n, L.ptr(dfeat), L.stream())
     return dfeat

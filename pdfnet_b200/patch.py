@@ -3,12 +3,29 @@
 After ``patch_reference()`` the reference's modules resolve the hot-path names to
 this package: ``HandNET_GCN.forward(img, choose, cloud,
 depth, ind, K_new, valid)`` and everything above it are unchanged.
+
+Call it BEFORE the reference's trainer / dataset / demo modules are imported: those bind
+``ManoLayer``, ``rodrigues_batch`` and ``_tranpose_and_gather_feat`` by name at import time
+(``from lib.models.networks.manolayer import ManoLayer``), so only modules imported afterwards see
+the replacements.
 """
 import importlib
 
+# names whose replacement has no backward: they stay the reference's in mode="training"
+_INFERENCE_ONLY = ("load_decoder", "ManoLayer", "rodrigues_batch")
 
-def patch_reference():
-    """Requires the reference to be importable (``lib`` on sys.path).  Returns the list of patched names."""
+
+def patch_reference(mode="inference"):
+    """Requires the reference to be importable (``lib`` on sys.path).  Returns the list of patched names.
+
+    mode="inference" (default): every hot-path name is rebound, including the GCN decoder and the MANO
+    layer, which are inference-only here (they raise if a gradient is requested).
+    mode="training": the differentiable stages (grouping, gathers, SFTLayer, PointNet_Plus - forward and
+    backward on this library's kernels) are rebound; ``load_decoder``, ``ManoLayer`` and
+    ``rodrigues_batch`` stay the reference's own autograd implementations, so ``loss.backward()`` reaches
+    every parameter exactly as in the unpatched model."""
+    if mode not in ("inference", "training"):
+        raise ValueError("patch_reference: mode must be 'inference' or 'training'")
     from . import decoder, encoder, grouping, manolayer
     patched = []
     ru = importlib.import_module("lib.utils.utils")
@@ -26,7 +43,10 @@ def patch_reference():
         (renc, "_tranpose_and_gather_feat", encoder._tranpose_and_gather_feat),
         (renc, "SFTLayer", encoder.SFTLayer), (renc, "PointNet_Plus", encoder.PointNet_Plus),
         (renc, "depth2pcl", encoder.depth2pcl), (rml, "ManoLayer", manolayer.ManoLayer),
+        (rml, "rodrigues_batch", manolayer.rodrigues_batch),
     ):
+        if mode == "training" and name in _INFERENCE_ONLY:
+            continue
         setattr(mod, name, new)
         patched.append("%s.%s" % (mod.__name__, name))
     return patched

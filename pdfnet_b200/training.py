@@ -125,16 +125,15 @@ class LinearBNReLUFn(Function):
     writes it as the split-bf16 tile image which both gradient GEMMs read (dX through pdf_gemm_bf16, dW
     through pdf_gemm_tn_bf16 together with the image of x kept from the forward pass)."""
 
-    handoff = None
-
     @staticmethod
     def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, momentum, eps, precision, group=0,
                 image_only=False):
         """group > 0: the nn.MaxPool2d over ``group`` consecutive rows that ends the stack is part of the node;
         its gradient (dOut at the argmax row, zero elsewhere) is then never materialised.
         image_only: the output is consumed by another node of this kind only, so it is written ONLY as that
-        node's operand image (handed to the caller through ``LinearBNReLUFn.handoff``; the returned fp32 tensor
-        is a one-element placeholder expanded to the right shape)."""
+        node's operand image, returned as the second (non-differentiable) output; the fp32 tensor returned
+        first is then a one-element placeholder expanded to the right shape.  Without image_only the second
+        output is an empty tensor."""
         w = _c(w)
         split = precision != BF16
         M = x.shape[0]
@@ -156,11 +155,13 @@ class LinearBNReLUFn(Function):
         ctx.group = group
         ctx.save_for_backward(x if x.stride(-1) == 1 else None, w, pre, mean, rstd, gamma, beta,
                               x_img if split else None, arg)
-        LinearBNReLUFn.handoff = y_img                  # picked up by mlp_max_rows right after apply()
-        return y
+        if y_img is None:
+            y_img = torch.empty((0,), dtype=torch.uint8, device=pre.device)
+        ctx.mark_non_differentiable(y_img)
+        return y, y_img
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dimg=None):
         x, w, pre, mean, rstd, gamma, beta, x_img, arg = ctx.saved_tensors
         M, N, K = pre.shape[0], w.shape[0], w.shape[1]
         dy = _c(dy)
@@ -262,22 +263,30 @@ def mlp_max_rows(net, rows, group, precision=FP32):
     """(Conv1x1 -> BatchNorm2d(train) -> ReLU) x3 -> max over ``group`` consecutive rows."""
     h = rows
     M = rows.shape[0]
+    if not net[1].training:
+        # eval-mode BatchNorm with an autograd graph (fine-tuning with frozen statistics): the running statistics
+        # are folded into the convolution with differentiable parameter-sized torch ops; the layers themselves
+        # (forward, dX, dW) stay on LinearFn's kernels
+        for i in (0, 3, 6):
+            conv, bn = net[i], net[i + 1]
+            s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            h = LinearFn.apply(h, _conv_w(conv) * s[:, None], (conv.bias - bn.running_mean) * s + bn.bias,
+                               L.ACT_RELU, False, precision)
+        return GroupMaxFn.apply(h, group)
     fused = [_use_tc(M, _conv_w(net[i]).shape[0], _conv_w(net[i]).shape[1]) and net[i].out_channels % 64 == 0
              for i in (0, 3, 6)]
     for li, i in enumerate((0, 3, 6)):
         conv, bn = net[i], net[i + 1]
-        if not bn.training:
-            raise RuntimeError("mlp_max_rows is the train-mode path")
         momentum = bn.momentum if bn.momentum is not None else 0.1
         w = _conv_w(conv)
         if fused[li]:
             pool = group if (i == 6 and group <= 256 and M % group == 0) else 0
             # an intermediate layer whose only consumer is the next fused node hands over its operand image
             image_only = li < 2 and fused[li + 1] and precision != BF16
-            h = LinearBNReLUFn.apply(h, w, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, momentum,
-                                     bn.eps, precision, pool, image_only)
-            if LinearBNReLUFn.handoff is not None:      # h's fp32 storage is a placeholder: the values live in the image
-                h._pdf_split_img, LinearBNReLUFn.handoff = LinearBNReLUFn.handoff, None
+            h, h_img = LinearBNReLUFn.apply(h, w, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                            momentum, bn.eps, precision, pool, image_only)
+            if h_img.numel():                           # h's fp32 storage is a placeholder: the values live in the image
+                h._pdf_split_img = h_img
             pooled = pool > 0
         else:
             pooled = False
@@ -326,16 +335,43 @@ def pointnet_plus_train(net, points, emb, choose):
     return out.view(B, 1, -1)
 
 
-def hand_fusion_train(fusion, cloud, point_wise_emb, choose, center_features):
-    """ResNetSimple.forward :805-809 in training mode: one PointNet_Plus call per hand (per-hand
-    BatchNorm statistics, as in the reference), concatenation, final SFTLayer(1024,1024)."""
+def mano_head_rows(head, rows):
+    """mano_head (intaghand_encoder.py:630-643: Linear-BN1d-ReLU, Linear-BN1d-ReLU, Linear) with an autograd
+    graph: batch statistics in .train(), folded running statistics in .eval().  Always fp32-accurate GEMMs
+    (the pose parameters feed rotations)."""
+    h = rows
+    for i in (0, 3):
+        fc, bn = head[i], head[i + 1]
+        if bn.training:
+            momentum = bn.momentum if bn.momentum is not None else 0.1
+            h = LinearFn.apply(h, fc.weight, fc.bias, L.ACT_NONE, True, FP32)
+            h = BatchNormActFn.apply(h, bn.weight, bn.bias, bn.running_mean, bn.running_var, momentum, bn.eps, True)
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+        else:
+            s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            h = LinearFn.apply(h, fc.weight * s[:, None], (fc.bias - bn.running_mean) * s + bn.bias, L.ACT_RELU,
+                               False, FP32)
+    return LinearFn.apply(h, head[6].weight, head[6].bias, L.ACT_NONE, False, FP32)
+
+
+def hand_fusion_train(fusion, cloud, point_wise_emb, choose, center_features, with_mano=False):
+    """ResNetSimple.forward :805-813 with an autograd graph: one PointNet_Plus call per hand (per-hand
+    BatchNorm statistics, as in the reference), concatenation, final SFTLayer(1024,1024) and, with
+    ``with_mano``, the mano_head branch on each hand's un-fused feature (:812-813)."""
     B = cloud.shape[0]
     left = pointnet_plus_train(fusion.pointnet_plus, cloud[:, 0], point_wise_emb, choose[:, 0])
     right = pointnet_plus_train(fusion.pointnet_plus, cloud[:, 1], point_wise_emb, choose[:, 1])
     feat = torch.cat((left, right), 1)                                                  # [B,2,1024]
     prec = BF16 if fusion.pointnet_plus.precision == BF16 else FP32
     fused = sft_rows(fusion.sft, feat.reshape(B * 2, -1), _c(center_features).reshape(B * 2, -1), prec)
-    return fused.view(B, 2, -1)
+    fused = fused.view(B, 2, -1)
+    if not with_mano:
+        return fused
+    # one mano_head call per hand, as the reference (train-mode BatchNorm1d statistics are per call)
+    theta = torch.stack((mano_head_rows(fusion.mano_head, left.reshape(B, -1)),
+                         mano_head_rows(fusion.mano_head, right.reshape(B, -1))), 1)
+    return fused, theta
 
 
 def allreduce_gradients(params, world_size, group=None):

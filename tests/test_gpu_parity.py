@@ -44,6 +44,7 @@ def rel_err(a, b):
 
 # ----------------------------------------------------------------------------- neighbour search
 
+@torch.no_grad()
 def test_knn_level1_vs_reference_golden():
     from pdfnet_b200 import ops
     g = load_golden("knn_level1")
@@ -57,6 +58,7 @@ def test_knn_level1_vs_reference_golden():
     assert (np.sort(idx, -1) == np.sort(g["idx_r015"][:2].astype(np.int64), -1)).all()
 
 
+@torch.no_grad()
 def test_knn_level2_channel_major_vs_golden():
     from pdfnet_b200 import ops
     g = load_golden("knn_level2")
@@ -68,6 +70,7 @@ def test_knn_level2_channel_major_vs_golden():
 
 @pytest.mark.parametrize("n,n1,k,r2", [(1024, 512, 64, 0.01), (512, 128, 64, 0.04), (256, 64, 32, 0.02),
                                         (1000, 500, 64, 0.015), (96, 96, 96, 0.5)])
+@torch.no_grad()
 def test_knn_vs_oracle_shapes(n, n1, k, r2):
     from pdfnet_b200 import ops
     pts = synth.clouds(5, n_points=n, seed=n + k, sigma=0.07)
@@ -75,6 +78,7 @@ def test_knn_vs_oracle_shapes(n, n1, k, r2):
     assert (np.sort(idx, -1) == O.knn_ball_indices(pts.numpy(), n1, k, r2)).all()
 
 
+@torch.no_grad()
 def test_knn_full_size_properties():
     """cfg2/cfg3 sizes: 256 clouds; size-independent properties + oracle on a sample."""
     from pdfnet_b200 import ops
@@ -98,6 +102,7 @@ def test_knn_full_size_properties():
     assert (np.sort(idx[sel].cpu().numpy(), -1) == O.knn_ball_indices(pts[sel].numpy(), 512, 64, 0.01)).all()
 
 
+@torch.no_grad()
 def test_group_points_dropin():
     from pdfnet_b200 import group_points, group_points_2
     g = load_golden("knn_level1")
@@ -122,6 +127,7 @@ def test_group_points_dropin():
     assert (a == b).all()
 
 
+@torch.no_grad()
 def test_pointnet2_aliases():
     from pdfnet_b200 import farthest_point_sample, index_points, query_ball_point, sample_and_group
     pts = synth.clouds(3, seed=77).to(DEV)
@@ -139,6 +145,7 @@ def test_pointnet2_aliases():
 
 # ----------------------------------------------------------------------------- FPS
 
+@torch.no_grad()
 def test_fps_vs_reference_golden():
     from pdfnet_b200 import ops
     g = load_golden("fps")
@@ -149,6 +156,7 @@ def test_fps_vs_reference_golden():
         assert (order == O.fps_order(g["pc_" + tag], int(g["n_" + tag]), int(g["start_" + tag]))).all()
 
 
+@torch.no_grad()
 def test_fps_batch_sizes():
     from pdfnet_b200 import ops
     for n, m in ((1024, 512), (512, 128), (2000, 64), (4096, 32), (100, 100)):
@@ -162,6 +170,7 @@ def test_fps_batch_sizes():
 
 # ----------------------------------------------------------------------------- gathers / SFT / MLP
 
+@torch.no_grad()
 def test_gather_vs_golden():
     from pdfnet_b200 import _tranpose_and_gather_feat
     g = load_golden("gather")
@@ -169,6 +178,7 @@ def test_gather_vs_golden():
     assert (out.cpu().numpy() == g["out"]).all()
 
 
+@torch.no_grad()
 def test_sft_vs_golden():
     from pdfnet_b200 import SFTLayer
     g = load_golden("sft")
@@ -180,6 +190,7 @@ def test_sft_vs_golden():
         np.testing.assert_allclose(o.cpu().numpy(), g["out_" + name], rtol=2e-5, atol=2e-5)
 
 
+@torch.no_grad()
 def test_linear_kernel_modes():
     from pdfnet_b200 import _lib as L
     from pdfnet_b200 import ops
@@ -211,6 +222,7 @@ def _pointnet_case():
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+@torch.no_grad()
 def test_pointnet_plus_vs_reference_golden(precision, tol):
     from pdfnet_b200 import PointNet_Plus
     g, R, B, pts, choose, emb = _pointnet_case()
@@ -224,6 +236,7 @@ def test_pointnet_plus_vs_reference_golden(precision, tol):
     assert err < tol, err
 
 
+@torch.no_grad()
 def test_pyramid_gather_and_sft0_vs_golden():
     from pdfnet_b200 import PointNet_Plus, ops
     g, R, B, pts, choose, emb = _pointnet_case()
@@ -239,6 +252,7 @@ def test_pyramid_gather_and_sft0_vs_golden():
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+@torch.no_grad()
 def test_hand_fusion_vs_oracle(precision, tol):
     """Both hands as one 2B-cloud batch + final SFT(1024,1024) + mano_head, vs the oracle's
     two sequential per-hand passes (intaghand_encoder.py:805-813)."""
@@ -265,6 +279,7 @@ def test_hand_fusion_vs_oracle(precision, tol):
     assert rel_err(theta.cpu().numpy(), ref_theta.numpy()) < max(tol, 1e-4)
 
 
+@torch.no_grad()
 def test_sa_bf16_kernel_vs_fp32_path():
     """The tcgen05 set-abstraction kernel against the FFMA path on the same indices (both levels)."""
     from pdfnet_b200 import PointNet_Plus, ops
@@ -294,6 +309,7 @@ def test_sa_bf16_kernel_vs_fp32_path():
 
 # ----------------------------------------------------------------------------- depth -> clouds
 
+@torch.no_grad()
 def test_backproject_vs_golden():
     from pdfnet_b200 import get_points_coordinate
     g = load_golden("backproject")
@@ -303,6 +319,7 @@ def test_backproject_vs_golden():
     assert ((xyz == 0) == (g["xyz"] == 0)).all()
 
 
+@torch.no_grad()
 def test_depth2pcl_vs_reference_golden():
     from pdfnet_b200 import depth2pcl
     g = load_golden("depth2pcl")
@@ -315,6 +332,7 @@ def test_depth2pcl_vs_reference_golden():
         assert rel_err(cloud, g["cloud_" + tag]) < 1e-6, tag
 
 
+@torch.no_grad()
 def test_depth2pcl_batched_matches_per_frame_oracle():
     from pdfnet_b200 import ops
     B, R = 5, 128
@@ -337,6 +355,7 @@ def test_depth2pcl_batched_matches_per_frame_oracle():
 
 # ----------------------------------------------------------------------------- MANO tail
 
+@torch.no_grad()
 def test_mano_lbs_vs_reference_golden():
     from pdfnet_b200 import ManoLayer
     g = load_golden("mano_lbs")
@@ -351,6 +370,140 @@ def test_mano_lbs_vs_reference_golden():
             assert np.abs(j.cpu().numpy() - g["j_%s_%s" % (tag, side)]).max() < 1e-5
 
 
+@torch.no_grad()
+def test_mano_pca_matrix_root_rodrigues_and_joint_regressor():
+    """ManoLayer(use_pca=True) (matrix root + PCA coefficients, manolayer.py:266-267), stand-alone
+    rodrigues_batch (:32-48) and full_regressor @ verts (Mano_model.py:309-323) against the reference golden."""
+    from pdfnet_b200 import ManoLayer, process_J_regressor, regress_joints, rodrigues_batch
+    g = load_golden("mano_extra")
+    R = rodrigues_batch(torch.from_numpy(g["rod_axis"]).to(DEV))
+    assert np.abs(R.cpu().numpy() - g["rod_R"]).max() < 1e-6
+    assert np.abs(rodrigues_batch(torch.from_numpy(g["rod_axis"])).numpy() - g["rod_R"]).max() < 1e-6   # host in, host out
+    for side in ("left", "right"):
+        T = mano_tables(side)
+        a = {k: torch.from_numpy(g["pca_%s_%s" % (k, side)]).to(DEV) for k in ("root", "shape", "trans", "scale")}
+        for nc in (45, 30):
+            coef = torch.from_numpy(g["pca_coef%d_%s" % (nc, side)]).to(DEV)
+            for tag, kw, ci in (("plain", {}, None), ("full", dict(trans=a["trans"], scale=a["scale"]), 9)):
+                layer = ManoLayer(T, center_idx=ci, use_pca=True)
+                v, j = layer(a["root"], coef, a["shape"], side=side, **kw)
+                assert np.abs(v.cpu().numpy() - g["pca_v%d_%s_%s" % (nc, tag, side)]).max() < 1e-5
+                assert np.abs(j.cpu().numpy() - g["pca_j%d_%s_%s" % (nc, tag, side)]).max() < 1e-5
+        # host tensors (dataset-style call, interhand.py:220): staged to the GPU, returned on the host
+        layer = ManoLayer(T, center_idx=None, use_pca=True)
+        v, j = layer(a["root"].cpu(), torch.from_numpy(g["pca_coef45_" + side]), a["shape"].cpu(), side=side)
+        assert not v.is_cuda and np.abs(v.numpy() - g["pca_v45_plain_" + side]).max() < 1e-5
+        with pytest.raises(RuntimeError):
+            layer(a["root"][:, 0], torch.from_numpy(g["pca_coef45_" + side]).to(DEV), a["shape"], side=side)
+        reg = process_J_regressor(torch.from_numpy(T["J_regressor"])).to(DEV)
+        assert (reg.cpu().numpy() == g["full_regressor_" + side]).all()
+        j21 = regress_joints(reg, torch.from_numpy(g["model_v_" + side]).to(DEV))
+        assert np.abs(j21.cpu().numpy() - g["model_j21_" + side]).max() < 1e-6
+        # second LBS of the reference (ManoModel.lbs) == our skinning on the same inputs
+        l = load_golden("mano_lbs")
+        b = {k: torch.from_numpy(l["%s_%s" % (k, side)]).to(DEV) for k in ("rot", "pose", "shape", "trans")}
+        v2, _ = ManoLayer(T, center_idx=None)(b["rot"], b["pose"], b["shape"], trans=b["trans"], side=side)
+        assert np.abs(v2.cpu().numpy() - g["model_v_" + side]).max() < 1e-5
+
+
+def test_inference_only_modules_refuse_gradients_loudly():
+    """ManoLayer / rodrigues_batch / decoder have no backward: a call that expects gradients raises instead of
+    returning detached tensors (patch_reference(mode='training') keeps the reference's versions)."""
+    from pdfnet_b200 import ManoLayer, rodrigues_batch
+    T = mano_tables("left")
+    rot, pose, shape, _ = synth.mano_inputs(2, seed=5)
+    layer = ManoLayer(T, center_idx=None)
+    with pytest.raises(RuntimeError, match="no backward"):
+        layer(rot.to(DEV).requires_grad_(True), pose.to(DEV), shape.to(DEV))
+    with pytest.raises(RuntimeError, match="no backward"):
+        rodrigues_batch(rot.to(DEV).requires_grad_(True))
+    v, _ = layer(rot.to(DEV), pose.to(DEV), shape.to(DEV))      # grad mode on, nothing requires grad: fine
+    assert v.shape == (2, 778, 3)
+
+
+def test_patched_gather_and_eval_mode_modules_carry_gradients():
+    """the drop-in names must stay differentiable where the reference's are.  (1) the patched
+    _tranpose_and_gather_feat back-propagates into the map it gathers from (center_feat_up*, head losses:
+    intaghand_encoder.py:790-792, simplified.py:698); (2) CenterFeatures with trainable convs equals the
+    reference's conv+gather and its autograd; (3) PointNet_Plus / SFTLayer / HandFusion in .eval() with grad
+    enabled (fine-tuning with frozen BatchNorm) return tensors with a graph whose gradients match torch autograd
+    of the oracle restatement."""
+    import torch.nn.functional as F
+    from pdfnet_b200 import CenterFeatures, HandFusion, _tranpose_and_gather_feat
+    gen = torch.Generator().manual_seed(5)
+    # (1) conv -> gather -> loss, against permute + torch.gather
+    conv = torch.nn.Conv2d(6, 9, 3, padding=1).to(DEV)
+    x = torch.randn((3, 6, 12, 10), generator=gen).to(DEV)
+    ind = torch.randint(0, 120, (3, 2), generator=gen).to(DEV)
+    wdir = torch.randn((3, 2, 9), generator=gen).to(DEV)
+    out = _tranpose_and_gather_feat(conv(x), ind)
+    assert out.requires_grad
+    (out * wdir).sum().backward()
+    g_ours = conv.weight.grad.clone()
+    conv.weight.grad = None
+    fm = conv(x)
+    ref = fm.permute(0, 2, 3, 1).reshape(3, 120, 9).gather(1, ind[..., None].expand(-1, -1, 9))
+    assert torch.equal(out.detach(), ref.detach())
+    (ref * wdir).sum().backward()
+    assert float(g_ours.abs().max()) > 0 and rel_err(g_ours.cpu(), conv.weight.grad.cpu()) < 1e-5
+    # (2) CenterFeatures: trainable convs -> conv + differentiable gather; frozen -> the im2col inference path
+    cf = CenterFeatures(16, 24, 32).to(DEV)
+    x0 = torch.randn((2, 16, 8, 8), generator=gen).to(DEV)
+    ind2 = torch.tensor([[0, 63], [9, 36]], device=DEV)
+    o = cf(x0, ind2)
+    o.sum().backward()
+    want = F.conv2d(F.conv2d(x0, cf.center_feat_up0.weight, padding=1), cf.center_feat_up1.weight, padding=1)
+    want = want.permute(0, 2, 3, 1).reshape(2, 64, 32).gather(1, ind2[..., None].expand(-1, -1, 32))
+    assert rel_err(o.detach().cpu(), want.detach().cpu()) < 1e-5
+    assert float(cf.center_feat_up0.weight.grad.abs().max()) > 0 and float(cf.center_feat_up1.weight.grad.abs().max()) > 0
+    with torch.no_grad():
+        assert rel_err(cf(x0, ind2).cpu(), want.detach().cpu()) < 2e-5
+    # (3) eval-mode modules with grad enabled
+    R, B = 64, 2
+    opt = _opt(default_resolution=R)
+    m = HandFusion(opt)
+    m.pointnet_plus.load_state_dict(synth.pointnet_plus_state(seed=317), strict=False)
+    m.sft.load_state_dict(synth.fusion_sft_state(seed=317))
+    m.load_state_dict(synth.mano_head_state(seed=317, std=0.05), strict=False)
+    m = m.to(DEV).eval()
+    cloud = synth.clouds(2 * B, seed=47).view(B, 2, 1024, 3)
+    choose = synth.choose_indices(2 * B, R, seed=47).view(B, 2, 1024)
+    emb = synth.pyramid(B, R, seed=47)
+    cen = torch.randn((B, 2, 1024), generator=gen)
+    cen_d = cen.to(DEV).requires_grad_(True)
+    fused, theta = m(cloud.to(DEV), [e.to(DEV) for e in emb], choose.to(DEV), cen_d, with_mano=True)
+    assert fused.requires_grad and theta.requires_grad
+    with torch.no_grad():
+        fused_ng, theta_ng = m(cloud.to(DEV), [e.to(DEV) for e in emb], choose.to(DEV), cen.to(DEV), with_mano=True)
+    assert rel_err(fused.detach().cpu(), fused_ng.cpu()) < 1e-4 and rel_err(theta.detach().cpu(), theta_ng.cpu()) < 1e-4
+    gd = torch.randn(fused.shape, generator=gen)
+    ((fused * gd.to(DEV)).sum() + theta.sum()).backward()
+    # oracle: the eval-mode restatement is built from differentiable torch ops once no_grad is lifted
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running_" not in k)
+          for k, v in synth.pointnet_plus_state(seed=317).items()}
+    sft = {k: v.clone().requires_grad_(True) for k, v in synth.fusion_sft_state(seed=317).items()}
+    cen_o = cen.clone().requires_grad_(True)
+    feats = []
+    for h in (0, 1):
+        _, it = O.pointnet_plus_forward(sd, cloud[:, h], emb, choose[:, h], opt, return_intermediates=True)
+        # differentiable tail from the (index-fixing, constant) level-2 rows: netR_3 + max
+        feats.append(O.point_mlp_max(it["pts2"].unsqueeze(3), sd, "netR_3", 2).view(-1, 1, 1024))
+    fo = O.sft_layer(torch.cat(feats, 1).transpose(1, 2), cen_o, sft)
+    (fo * gd).sum().backward()
+    assert rel_err(fused.detach().cpu(), fo.detach()) < 1e-4
+    assert rel_err(cen_d.grad.cpu(), cen_o.grad) < 1e-3
+    for k in ("SFT_scale_conv1.weight", "SFT_shift_conv0.bias"):
+        assert rel_err(dict(m.sft.named_parameters())[k].grad.cpu(), sft[k].grad) < 1e-3, k
+    for k in ("netR_3.6.weight", "netR_3.7.weight", "netR_3.7.bias", "netR_3.0.weight"):
+        assert rel_err(dict(m.pointnet_plus.named_parameters())[k].grad.cpu(), sd[k].grad) < 2e-3, k
+    assert float(m.pointnet_plus.netR_1[0].weight.grad.abs().max()) > 0         # the chain reaches the first layer
+    assert float(m.mano_head[0].weight.grad.abs().max()) > 0
+    assert float(m.pointnet_plus.netR_3[1].running_mean.abs().sum()) > 0         # eval mode: buffers untouched
+    torch.testing.assert_close(m.pointnet_plus.netR_3[1].running_mean.cpu(),
+                               synth.pointnet_plus_state(seed=317)["netR_3.1.running_mean"])
+
+
+@torch.no_grad()
 def test_mano_lbs_batch_vs_oracle_and_fix_shape():
     from pdfnet_b200 import ManoLayer
     T = {k: np.array(v) for k, v in mano_tables("left").items()}
@@ -374,6 +527,7 @@ def test_mano_lbs_batch_vs_oracle_and_fix_shape():
     assert np.abs(v0.cpu().numpy()[0] - T["v_template"]).max() < 1e-6
 
 
+@torch.no_grad()
 def test_split_coeff_and_mano_tail():
     from pdfnet_b200 import ManoLayer, Split_coeff, mano_tail
     g = load_golden("split_coeff")
@@ -398,6 +552,7 @@ def test_split_coeff_and_mano_tail():
     np.testing.assert_allclose(tr.cpu().numpy(), so_r[7].numpy(), rtol=1e-6, atol=1e-7)
 
 
+@torch.no_grad()
 def test_mano_head_vs_golden():
     from pdfnet_b200 import HandFusion
     g = load_golden("mano_head")
@@ -410,6 +565,7 @@ def test_mano_head_vs_golden():
 
 # ----------------------------------------------------------------------------- error behaviour
 
+@torch.no_grad()
 def test_errors_are_loud():
     from pdfnet_b200 import PointNet_Plus, ops
     with pytest.raises(RuntimeError):
@@ -442,6 +598,7 @@ def _bf(t):
     return t.bfloat16().float()
 
 
+@torch.no_grad()
 def test_gemm_bf16_row_modes():
     from pdfnet_b200 import _lib as L
     from pdfnet_b200 import ops
@@ -483,6 +640,7 @@ def test_gemm_bf16_row_modes():
     assert torch.equal(Fd[:, :4].cpu(), F[:, :4]) and torch.equal(Fd[:, 204:].cpu(), F[:, 204:])
 
 
+@torch.no_grad()
 def test_gemm_bf16_colmax_and_many_tiles():
     from pdfnet_b200 import ops
     g = torch.Generator().manual_seed(8)
@@ -497,6 +655,7 @@ def test_gemm_bf16_colmax_and_many_tiles():
     assert rel_err(out.cpu(), ref.cpu()) < 1e-4
 
 
+@torch.no_grad()
 def test_sft_xyz_fp32():
     from pdfnet_b200 import SFTLayer, ops
     g = torch.Generator().manual_seed(9)
@@ -513,6 +672,7 @@ def test_sft_xyz_fp32():
     assert rel_err(y[:, :3].cpu(), ref.cpu()) < 1e-5 and torch.equal(y[:, 3:], x[:, 3:])
 
 
+@torch.no_grad()
 def test_gemm_split_bf16_is_fp32_accurate():
     """[hi|hi|lo] x [hi|lo|hi] operand images: fp32-accurate products on the bf16 tensor cores."""
     from pdfnet_b200 import _lib as L
@@ -531,6 +691,7 @@ def test_gemm_split_bf16_is_fp32_accurate():
     assert rel_err(plain, ref) > 20 * rel_err(out[:, :130].cpu(), ref)      # far better than plain bf16
 
 
+@torch.no_grad()
 def test_gemm_xyz_mode_matches_fp32_sft():
     """SFT1 hidden layer in XYZ mode: bf16 hidden image + fp32 modulation of the 3 xyz channels."""
     from pdfnet_b200 import _lib as L
@@ -560,6 +721,7 @@ def test_gemm_xyz_mode_matches_fp32_sft():
 
 # ----------------------------------------------------------------------------- edge cases
 
+@torch.no_grad()
 def test_knn_degenerate_clouds():
     from pdfnet_b200 import ops
     # all points identical: every distance ties at 0 -> the 64 lowest indices, nothing masked
@@ -580,6 +742,7 @@ def test_knn_degenerate_clouds():
     assert (np.sort(idx, -1) == O.knn_ball_indices(pts.numpy(), 512, 64, 1e12)).all()
 
 
+@torch.no_grad()
 def test_depth2pcl_edge_cases():
     from pdfnet_b200 import ops
     R = 64
@@ -606,6 +769,7 @@ def test_depth2pcl_edge_cases():
     assert (c2[0].cpu().numpy() == ch).all()
 
 
+@torch.no_grad()
 def test_pointnet_plus_chunking_and_two_hand_batching():
     """Internal chunking over clouds and the clouds_per_frame=2 batching give identical results."""
     from pdfnet_b200 import PointNet_Plus
@@ -627,6 +791,7 @@ def test_pointnet_plus_chunking_and_two_hand_batching():
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 1e-4)])
+@torch.no_grad()
 def test_center_features_only_at_ind(precision, tol):
     """two 3x3 convs evaluated only at `ind` == full-map convs + gather (incl. border pixels)."""
     from pdfnet_b200 import CenterFeatures
@@ -645,6 +810,7 @@ def test_center_features_only_at_ind(precision, tol):
     assert rel_err(out.cpu(), ref) < tol
 
 
+@torch.no_grad()
 def test_mano_tail_pair_matches_per_side_tail():
     from pdfnet_b200 import ManoLayer, mano_tail, mano_tail_pair
     g = torch.Generator().manual_seed(14)
@@ -660,6 +826,7 @@ def test_mano_tail_pair_matches_per_side_tail():
     assert torch.equal(t[:, 0], tl) and torch.equal(t[:, 1], tr)
 
 
+@torch.no_grad()
 def test_full_size_cfg3_properties():
     """BASELINE cfg3 size (128 frames = 256 clouds, R = 256): the tensor-core pipeline agrees with the FFMA
     pipeline on the same inputs within the bf16 tolerance, results are deterministic, both hands batched
@@ -907,6 +1074,7 @@ def test_train_tensor_core_gemms_are_fp32_accurate():
         assert rel_err(dws, dw_ref) < 2e-5
 
 
+@torch.no_grad()
 def test_captured_step_replays_the_hot_path_bit_exactly():
     """pdfnet_b200.graph.CapturedStep: the eager step and its CUDA-graph replay give identical bits,
     also after the input buffers are overwritten in place."""
@@ -932,6 +1100,7 @@ def test_captured_step_replays_the_hot_path_bit_exactly():
     assert torch.equal(out2, eager2) and not torch.equal(eager2, eager)
 
 
+@torch.no_grad()
 def test_channels_last_pyramid_is_bit_identical():
     """pyramid maps handed over in torch.channels_last are gathered in place
     (pdf_pyramid_gather_nhwc / pdf_gather_nhwc); every result equals the NCHW path bit for bit."""
@@ -1035,6 +1204,7 @@ def _decoder_outputs(res):
     return out
 
 
+@torch.no_grad()
 def test_gcn_decoder_vs_reference_golden():
     """decoder.forward (intaghand_decoder.py:180-242) against the unmodified reference: every returned
     tensor, fp32 path 1e-4 of each tensor's scale."""
@@ -1047,6 +1217,7 @@ def test_gcn_decoder_vs_reference_golden():
         assert rel_err(v.cpu().numpy(), g[k]) < 1e-4, (k, rel_err(v.cpu().numpy(), g[k]))
 
 
+@torch.no_grad()
 def test_gcn_decoder_tensor_core_and_batch():
     """Tensor-core path at a batch large enough to take it (rows >= 1024): split-bf16 operands hold the
     fp32 tolerance (2e-4 vs the oracle); deterministic; batch-independent."""
@@ -1080,6 +1251,7 @@ def test_gcn_decoder_tensor_core_and_batch():
         assert rel_err(part[k].cpu().numpy(), full[k][5:9].cpu().numpy()) < 1e-5, k
 
 
+@torch.no_grad()
 def test_decoder_primitives_vs_torch():
     """row_combine / graph_cheby_ln / mha / decoder_project against torch-CPU on ragged shapes."""
     import torch.nn.functional as F
@@ -1130,6 +1302,7 @@ def test_decoder_primitives_vs_torch():
         np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-4)
 
 
+@torch.no_grad()
 def test_gcn_decoder_single_frame_and_errors():
     """B = 1 (every GEMM below the tensor-core row threshold even in bf16x3 mode) equals the fp32 path;
     wrong feature width and train mode fail loudly."""
@@ -1147,6 +1320,7 @@ def test_gcn_decoder_single_frame_and_errors():
         m32.eval()(fuse[:, 0].cpu(), fuse[:, 1].cpu(), None)
 
 
+@torch.no_grad()
 def test_linear_smallk_streaming_kernels():
     """K <= 4 streaming linear layer (netR_1[0]) and both gradients against float64."""
     from pdfnet_b200 import ops

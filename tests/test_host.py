@@ -201,7 +201,26 @@ def test_patch_reference_rebinds_every_boundary_name(monkeypatch):
     assert enc.group_points is grouping.group_points and enc.depth2pcl is encoder.depth2pcl
     assert sys.modules["lib.models.networks.manolayer"].ManoLayer is manolayer.ManoLayer
     assert sys.modules["lib.models.networks.intaghand_model"].load_decoder is decoder.load_decoder
-    assert len(patched) == 13
+    assert sys.modules["lib.models.networks.manolayer"].rodrigues_batch is manolayer.rodrigues_batch
+    assert len(patched) == 14
+
+
+def test_patch_reference_training_mode_keeps_the_reference_autograd_modules(monkeypatch):
+    """mode='training': the inference-only replacements (decoder, ManoLayer, rodrigues_batch) are NOT installed."""
+    import types
+    import pdfnet_b200
+    names = ["lib", "lib.utils", "lib.utils.utils", "lib.models", "lib.models.utils", "lib.models.networks",
+             "lib.models.networks.intaghand_encoder", "lib.models.networks.manolayer",
+             "lib.models.networks.intaghand_decoder", "lib.models.networks.intaghand_model"]
+    for n in names:
+        monkeypatch.setitem(sys.modules, n, types.ModuleType(n))
+    patched = pdfnet_b200.patch_reference(mode="training")
+    assert len(patched) == 10 and not any(p.endswith(("load_decoder", "ManoLayer", "rodrigues_batch")) for p in patched)
+    assert not hasattr(sys.modules["lib.models.networks.manolayer"], "ManoLayer")
+    from pdfnet_b200 import encoder
+    assert sys.modules["lib.models.networks.intaghand_encoder"].PointNet_Plus is encoder.PointNet_Plus
+    with pytest.raises(ValueError):
+        pdfnet_b200.patch_reference(mode="bogus")
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/lib/models/networks/gcn_core"), reason="reference assets absent")

@@ -129,6 +129,29 @@ def test_mano_lbs():
             assert np.abs(j.numpy() - g["j_%s_%s" % (tag, side)]).max() < 1e-6
 
 
+def test_mano_extra_rodrigues_pca_and_full_regressor():
+    """Round-2 goldens (oracle/make_golden.golden_mano_extra): stand-alone rodrigues_batch, the
+    use_pca=True layer (matrix root + PCA coefficients) and ManoModel's 21x778 joint regressor / second LBS."""
+    g = load_golden("mano_extra")
+    assert np.abs(O.rodrigues(torch.from_numpy(g["rod_axis"])).numpy() - g["rod_R"]).max() < 1e-6
+    lbs = load_golden("mano_lbs")
+    for side in ("left", "right"):
+        T = mano_tables(side)
+        a = {k: g["pca_%s_%s" % (k, side)] for k in ("root", "shape", "trans", "scale")}
+        for nc in (45, 30):
+            coef = g["pca_coef%d_%s" % (nc, side)]
+            for tag, kw in (("plain", {}), ("full", dict(trans=a["trans"], scale=a["scale"], center_idx=9))):
+                v, j = O.mano_lbs(T, a["root"], coef, a["shape"], side=side, use_pca=True, **kw)
+                assert np.abs(v.numpy() - g["pca_v%d_%s_%s" % (nc, tag, side)]).max() < 1e-6
+                assert np.abs(j.numpy() - g["pca_j%d_%s_%s" % (nc, tag, side)]).max() < 1e-6
+        reg = O.full_regressor(T["J_regressor"])
+        assert (reg.numpy() == g["full_regressor_" + side]).all()
+        j21 = O.regress_joints(reg, g["model_v_" + side])
+        assert np.abs(j21.numpy() - g["model_j21_" + side]).max() < 1e-6
+        # the reference's two LBS implementations agree (SURVEY a15): ManoModel.lbs == ManoLayer on the same inputs
+        assert np.abs(g["model_v_" + side] - lbs["v_newskel_" + side]).max() < 1e-6
+
+
 def test_split_coeff():
     g = load_golden("split_coeff")
     outs = O.split_coeff(g["theta"], g["index"], g["K"], 384, 4)
