@@ -43,20 +43,34 @@ def make_opt(R):
                                  PCA_SZ=63)
 
 
-def make_inputs(n_frames, R, seed):
-    """Synthetic host inputs of the hot path for ``n_frames`` frames."""
+D2P_SEED = 317          # seed of the kernel-generated depth2pcl randomness (keys / permutation), reference seed opts.py:56
+
+
+def make_inputs(n_frames, R, seed, pyramid="bf16-nhwc", masks="u8"):
+    """Synthetic host inputs of the hot path for ``n_frames`` frames.
+
+    pyramid: 'bf16-nhwc' = what an autocast, channels-last RGB neck emits (BASELINE cfg3 "forward bf16");
+             'fp32-nchw' = the reference's own fp32 NCHW maps; 'fp32-nhwc' = fp32 channels-last.
+    masks:   'u8' (hand / not hand) or 'f32' (the reference's dtype).
+    The values are the same in every variant: fp32 maps hold the bf16-rounded numbers, so the CPU arm (fp32 NCHW)
+    and every GPU variant see identical inputs."""
     from pdfnet_b200 import synth
     depth, mask, K, valid = synth.rgbd_frames(n_frames, R, seed=seed)
-    emb = synth.pyramid(n_frames, R, seed=seed)
+    emb = [e.bfloat16() for e in synth.pyramid(n_frames, R, seed=seed)]
+    if pyramid == "bf16-nhwc":
+        emb = [e.contiguous(memory_format=torch.channels_last) for e in emb]
+    elif pyramid == "fp32-nhwc":
+        emb = [e.float().contiguous(memory_format=torch.channels_last) for e in emb]
+    else:
+        emb = [e.float() for e in emb]
+    if masks == "u8":
+        mask = (mask > 0.5).to(torch.uint8)
     g = torch.Generator().manual_seed(seed)
     center = torch.randn((n_frames, 2, 1024), generator=g)
     ind = torch.randint(0, (R // 4) ** 2, (n_frames, 2), generator=g)
-    rs = np.random.RandomState(seed)
-    keys = torch.from_numpy(np.argsort(rs.rand(n_frames, 2, R * R), axis=2).astype(np.int32))
-    perm = torch.from_numpy(np.argsort(rs.rand(n_frames, 2, 1024), axis=2).astype(np.int32))
     Kinv = torch.from_numpy(np.stack([np.linalg.inv(k) for k in K.numpy()]))   # host, as utils.py:269
     return dict(depth=depth, mask=mask, K=K, Kinv=Kinv, valid=valid, l0=emb[0], l1=emb[1], l2=emb[2], center=center,
-                ind=ind, keys=keys, perm=perm)
+                ind=ind)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -65,28 +79,50 @@ def make_inputs(n_frames, R, seed):
 # pinned to it by tests/golden).  This is the only place bench.py executes oracle/.
 # ----------------------------------------------------------------------------------------------
 
-def cpu_hot_path(inp, R, mano_tables, state):
+def cpu_hot_path(inp, R, mano_tables, state, dec=None, stage_times=None):
     from oracle import pdf_oracle as O
     opt = make_opt(R)
     B = inp["depth"].shape[0]
+
+    def tick(name, t0):
+        if stage_times is not None:
+            stage_times[name] = stage_times.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
+    t = time.perf_counter()
+    keys, perm = O.d2p_seeded_randomness(D2P_SEED, 2 * B, R * R)
+    keys, perm = keys.reshape(B, 2, R * R), perm.reshape(B, 2, 1024)
+    mask = inp["mask"].float().numpy()
     chooses, clouds = [], []
     for b in range(B):
-        ch, cl = O.depth2pcl(inp["depth"][b].numpy(), inp["mask"][b:b + 1].numpy(), inp["K"][b].numpy(),
-                             inp["valid"][b:b + 1].numpy(), inp["keys"][b].numpy(), inp["perm"][b].numpy())
+        ch, cl = O.depth2pcl(inp["depth"][b].numpy(), mask[b:b + 1], inp["K"][b].numpy(),
+                             inp["valid"][b:b + 1].numpy(), keys[b], perm[b])
         chooses.append(torch.from_numpy(ch))
         clouds.append(torch.from_numpy(cl))
     choose, cloud = torch.stack(chooses), torch.stack(clouds)
-    emb = [inp["l0"], inp["l1"], inp["l2"]]
+    t = tick("depth2pcl (a1,a2)", t)
+    emb = [inp[k].float().contiguous() for k in ("l0", "l1", "l2")]
     with torch.no_grad():
         feats = [O.pointnet_plus_forward(state["pointnet"], cloud[:, h], emb, choose[:, h], opt) for h in (0, 1)]
+        t = tick("PointNet_Plus x2 (a4-a9)", t)
         fuse = O.sft_layer(torch.cat(feats, 1).transpose(1, 2).contiguous(), inp["center"], state["sft"], "")
+        t = tick("fusion SFT (a10)", t)
         th_l = O.mano_head(feats[0][:, 0], state["mano_head"])
         th_r = O.mano_head(feats[1][:, 0], state["mano_head"])
         sl = O.split_coeff(th_l, inp["ind"][:, 0], inp["K"], R, 4)
         sr = O.split_coeff(th_r, inp["ind"][:, 1], inp["K"], R, 4)
         vl, jl = O.mano_lbs(mano_tables["left"], sl[0], sl[1], sl[2], side="left")
         vr, jr = O.mano_lbs(mano_tables["right"], sr[4], sr[5], sr[6], side="right")
-    return fuse, torch.stack((vl, vr), 1), torch.stack((jl, jr), 1)
+        t = tick("mano_head + Split_coeff + LBS (a11-a14)", t)
+        out = [fuse, torch.stack((vl, vr), 1), torch.stack((jl, jr), 1)]
+        if dec is not None:
+            sd_d, assets = dec
+            res = O.gcn_decoder_forward(sd_d, assets, fuse)
+            out += [res["verts3d_left"], res["verts3d_right"]]
+            out += [O.regress_joints(O.full_regressor(mano_tables[s]["J_regressor"]), res["verts3d_" + s])
+                    for s in ("left", "right")]
+            t = tick("GCN decoder + full_regressor (f3,a15)", t)
+    return out
 
 
 def load_states():
@@ -105,36 +141,59 @@ def load_mano_tables():
     return out
 
 
-def time_cpu(sample_frames, R, steps, warmup):
+def load_decoder_state():
+    from pdfnet_b200 import synth
+    assets = dict(np.load(os.path.join(ROOT, "tests", "golden", "gcn_assets.npz")))
+    return synth.decoder_state(317, assets["upsample"]), assets
+
+
+def time_cpu(sample_frames, R, steps, warmup, with_decoder, stage_times=None):
     torch.set_num_threads(os.cpu_count() or 1)
-    inp = make_inputs(sample_frames, R, seed=317)
+    inp = make_inputs(sample_frames, R, seed=317, pyramid="fp32-nchw", masks="u8")
     tables, state = load_mano_tables(), load_states()
+    dec = load_decoder_state() if with_decoder else None
     for _ in range(warmup):
-        cpu_hot_path(inp, R, tables, state)
+        cpu_hot_path(inp, R, tables, state, dec)
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        cpu_hot_path(inp, R, tables, state)
+        cpu_hot_path(inp, R, tables, state, dec, stage_times)
         ts.append(time.perf_counter() - t0)
     return ts
 
 
+def config_dict(args, world, B, extra=None):
+    """The keys both arms print (the driver compares them): workload, frames per GPU and step, resolution, precision,
+    input formats, parallelism."""
+    c = {"workload": workload_name(args), "frames_per_gpu": B, "resolution": args.res, "precision": args.precision,
+         "parallelism": "dp%d" % world, "pyramid": args.pyramid, "masks": args.masks, "with_decoder": args.with_decoder,
+         "randomness": "depth2pcl subset keys / permutation generated from seed %d (counter-based; the reference "
+                       "draws them from np.random)" % D2P_SEED}
+    c.update(extra or {})
+    return c
+
+
 def run_reference(args):
+    """Reference arm: the oracle port of the reference's CPU path on all host threads, on a bounded sample of
+    the same workload (same inputs, same stages incl. the GCN decoder), rank 0 only."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     sample = args.cpu_sample_frames
-    ts = time_cpu(sample, args.res, args.steps, min(args.warmup, 1))
+    stage_t = {}
+    ts = time_cpu(sample, args.res, args.steps, args.warmup, args.with_decoder, stage_t)
     ms = 1e3 * sum(ts) / len(ts)
     val = sample / (ms / 1e3)
     cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "sample_frames_per_step": sample, "resolution": args.res},
+        "config": config_dict(args, args.gpus, args.frames, {"sample_frames_per_step": sample}),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d frames/step of the same workload, torch CPU fp32, %d threads" % (sample, cores)},
+                         "sample": "%d frames/step of the same workload (of %d per GPU step), torch CPU fp32, %d threads"
+                                   % (sample, args.frames, cores),
+                         "stage_ms_per_frame": {k: round(1e3 * v / (len(ts) * sample), 3) for k, v in stage_t.items()}},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -146,7 +205,8 @@ def run_reference(args):
 def workload_name(args):
     return ("cfg3-hotpath: %d frames/GPU x 2 hands, %dx%d depth, 1024-pt clouds, N1=512 N2=128 K=64 r2=(0.015,0.04); "
             "depth2pcl+pyramid gather/SFT+SA1+SA2+global MLP+fusion SFT+mano_head+Split_coeff+LBS%s"
-            % (args.frames, args.res, args.res, "+GCN decoder" if getattr(args, "with_decoder", False) else ""))
+            % (args.frames, args.res, args.res,
+               "+GCN decoder+full_regressor" if getattr(args, "with_decoder", False) else ""))
 
 
 class ClockSampler(object):
@@ -174,18 +234,31 @@ class ClockSampler(object):
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                pw.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# algorithmic bytes per unit of the HBM-bound stages
+def stage_bytes(args, n_frames):
+    R = args.res
+    mask_b = 1 if args.masks == "u8" else 4
+    feat_b = 2 if args.pyramid.startswith("bf16") else 4
+    d2p = R * R * 4 + 2 * R * R * mask_b + 2 * 1024 * (12 + 8)                       # per frame
+    pyr_read = 1024 * 3 * feat_b + 512 * 64 * feat_b + 128 * 256 * feat_b + 1024 * 8 + 1024 * 12
+    pyr_write = 1024 * 12 + 512 * 64 * feat_b + 128 * 256 * feat_b                  # pts0 + condition rows / images
+    return {"depth2pcl": d2p * n_frames, "pyramid_gather": (pyr_read + pyr_write) * 2 * n_frames,
+            "knn1": 143360 * 2 * n_frames, "knn2": 38912 * 2 * n_frames}
 
 
 def run_ours(args):
@@ -195,16 +268,13 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     from pdfnet_b200 import HandFusion, ManoLayer, _lib, mano_tail_pair, ops, profiling
+    from pdfnet_b200.graph import CapturedStep
 
     R, B = args.res, args.frames                      # frames per GPU (weak scaling)
     opt = make_opt(R)
-    host = make_inputs(B, R, seed=317 + rank)
-    pinned = {k: v.contiguous().pin_memory() for k, v in host.items()}
+    host = make_inputs(B, R, seed=317 + rank, pyramid=args.pyramid, masks=args.masks)
+    pinned = {k: v.pin_memory() for k, v in host.items()}      # pin_memory keeps the memory format (channels-last)
     resident = {k: v.to(dev) for k, v in host.items()}
-    if args.pyramid_layout == "nhwc":                 # channels-last hand-off from the RGB neck
-        for k in ("l0", "l1", "l2"):
-            resident[k] = resident[k].contiguous(memory_format=torch.channels_last)
-            pinned[k] = host[k].contiguous(memory_format=torch.channels_last).pin_memory()
     state = load_states()
     tables = load_mano_tables()
     model = HandFusion(opt, precision=args.precision)
@@ -217,24 +287,25 @@ def run_ours(args):
     mano_r = ManoLayer(tables["right"], center_idx=None).to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     dec = None
-    if args.with_decoder:                             # the GCN decoder consuming fuse_feat
+    if args.with_decoder:                             # SURVEY 8f row f3 + a15: GCN decoder consuming fuse_feat, then the joints
         from pdfnet_b200.decoder import decoder
-        from pdfnet_b200 import synth
-        assets = dict(np.load(os.path.join(ROOT, "tests", "golden", "gcn_assets.npz")))
+        sd_d, assets = load_decoder_state()
         dec = decoder(assets, precision="fp32" if args.precision == "fp32" else "bf16x3")
-        dec.load_state_dict(synth.decoder_state(317, assets["upsample"]))
+        dec.load_state_dict(sd_d)
+        dec.set_joint_regressors(tables["left"]["J_regressor"], tables["right"]["J_regressor"])
         dec = dec.to(dev).eval()
 
     def hot_path(d):
         with profiling.stage("depth2pcl"):
-            choose, cloud, _ = ops.depth2pcl(d["depth"], d["mask"], d["Kinv"], d["valid"], d["keys"], d["perm"])
+            choose, cloud, _ = ops.depth2pcl(d["depth"], d["mask"], d["Kinv"], d["valid"], seed=D2P_SEED)
         fused, theta = model(cloud, [d["l0"], d["l1"], d["l2"]], choose, d["center"], with_mano=True)
         with profiling.stage("mano_tail"):
             verts, joints, _ = mano_tail_pair(theta, d["ind"], d["K"], mano_l, mano_r, input_res=R)
         if dec is not None:
             with profiling.stage("gcn_decoder"):
-                result, _, _, _ = dec(fused[:, 0], fused[:, 1], None)
-            return fused, verts, joints, result["verts3d"]["left"], result["verts3d"]["right"]
+                result, _, _, other = dec(fused[:, 0], fused[:, 1], None)
+            return (fused, verts, joints, result["verts3d"]["left"], result["verts3d"]["right"],
+                    other["joints3d"]["left"], other["joints3d"]["right"])
         return fused, verts, joints
 
     def barrier():
@@ -242,86 +313,130 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(step_fn, steps, warmup):
+    def timed_loop(step_fn, steps, warmup, min_seconds=0.0):
+        """CUDA events around every step, L2 flushed in between (outside the events); -> mean ms (max over ranks)."""
         for _ in range(warmup):
             step_fn()
         barrier()
-        evs = []
-        for _ in range(steps):
+        evs, t0 = [], time.perf_counter()
+        while len(evs) < steps or (time.perf_counter() - t0) < min_seconds:
             flush.fill_(1)                            # evict L2 between timed iterations
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             step_fn()
             b.record()
             evs.append((a, b))
+            if min_seconds and len(evs) % 64 == 0:
+                torch.cuda.synchronize()              # keep the launch queue bounded in the long loop
         barrier()
-        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
-        return parallel.max_over_ranks(ms, dev)
+        ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        return parallel.max_over_ranks(ms, dev), len(evs)
 
     # ---- device-resident throughput ("value") ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count()
-    ms_eager = timed_loop(lambda: hot_path(resident), args.steps, args.warmup)
+    ms_eager, _ = timed_loop(lambda: hot_path(resident), args.steps, args.warmup)
     launches = (_lib.launch_count() - l0) // (args.steps + args.warmup)
-    ms_dev, graphed = ms_eager, False
+    ms_dev, graphed, step = ms_eager, False, None
     if not args.no_graph:
-        # the same ~30 kernels replayed as one CUDA graph (no Python / ctypes launch cost in the step)
-        from pdfnet_b200.graph import CapturedStep
+        # the same kernels replayed as one CUDA graph (no Python / ctypes launch cost in the step)
         try:
             step = CapturedStep(lambda: hot_path(resident))
-            launches = step.launches                  # exact: the kernels inside the captured step
-            ms_dev, graphed = timed_loop(step.replay, args.steps, args.warmup), True
+            launches = step.launches                  # exact: the library kernels inside the captured step
+            (ms_dev, _), graphed = timed_loop(step.replay, args.steps, args.warmup), True
         except Exception as e:                        # keep the eager measurement rather than lose the line
             sys.stderr.write("bench: CUDA-graph capture failed (%s); reporting the eager launch path\n" % e)
             torch.cuda.synchronize()
-            args.no_graph = True
+            args.no_graph, step = True, None
     clocks = sampler.stop() if rank == 0 else None
+    # ---- sustained: the same step back to back for >= args.sustained_seconds (power-capped clocks) ----
+    sustained = None
+    if args.sustained_seconds > 0:
+        s2 = ClockSampler(local)
+        if rank == 0:
+            s2.start()
+        fn = step.replay if step is not None else (lambda: hot_path(resident))
+        ms_sus, n_sus = timed_loop(fn, args.steps, 0, min_seconds=args.sustained_seconds)
+        sustained = {"value": world * B / (ms_sus * 1e-3), "unit": UNIT, "ms_per_step": ms_sus, "steps": n_sus,
+                     "seconds": args.sustained_seconds, "clocks": s2.stop() if rank == 0 else None}
 
     # ---- end to end through the public API with HOST buffers ----
+    # Every step copies ALL hot-path inputs from pinned host memory and the results back.  The batch is cut into
+    # chunks and the staging buffers are double-buffered ACROSS steps: while chunk c of step i computes, the copy
+    # stream already moves later chunks / the next step's inputs, and a third stream returns the outputs.
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
-    # The batch is cut into chunks: chunk i+1 crosses PCIe on a copy stream while chunk i computes.
     n_chunks = max(1, min(args.e2e_chunks, B))
     bounds = [parallel.shard_range(B, c, n_chunks) for c in range(n_chunks)]
-    copy_stream = torch.cuda.Stream(device=dev)
-    out_host = {}
-
-    staging = {k: torch.empty_like(resident[k]) for k in pinned}
-
+    copy_stream, out_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    n_sets = 2
+    staging = [{k: torch.empty_like(resident[k]) for k in pinned} for _ in range(n_sets)]
+    names = ("fused", "verts", "joints", "gcn_verts_left", "gcn_verts_right", "gcn_joints_left", "gcn_joints_right")
     chunk_steps = None
-    if not args.no_graph:                             # one captured graph per chunk, over slices of the staging buffers
-        from pdfnet_b200.graph import CapturedStep
+    if not args.no_graph:                             # one captured graph per (staging set, chunk)
         try:
-            chunk_steps = [CapturedStep(lambda lo=lo, hi=hi: hot_path({k: v[lo:hi] for k, v in staging.items()}),
-                                        warmup=2) for lo, hi in bounds]
+            chunk_steps = [[CapturedStep(lambda lo=lo, hi=hi, st=st: hot_path({k: v[lo:hi] for k, v in st.items()}),
+                                         warmup=2) for lo, hi in bounds] for st in staging]
         except Exception as e:
             sys.stderr.write("bench: CUDA-graph capture of the e2e chunks failed (%s); eager chunks\n" % e)
             torch.cuda.synchronize()
             chunk_steps = None
+    probe = hot_path({k: v[bounds[0][0]:bounds[0][1]] for k, v in staging[0].items()})
+    out_host = [{n: torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory() for n, t in zip(names, probe)}
+                for _ in range(n_sets)]
+    consumed = [None] * n_sets                        # event: the compute of the step that last used this set is done
+    drained = [None] * n_sets                         # event: its outputs have left the device
 
-    def e2e_step():
+    def e2e_step(i):
         main = torch.cuda.current_stream()
-        copy_stream.wait_stream(main)                 # previous step has consumed the staging buffers
+        st = i % n_sets
+        if consumed[st] is not None:
+            copy_stream.wait_event(consumed[st])
         events = []
         with torch.cuda.stream(copy_stream):
             for lo, hi in bounds:
                 for k, v in pinned.items():
-                    staging[k][lo:hi].copy_(v[lo:hi], non_blocking=True)
+                    staging[st][k][lo:hi].copy_(v[lo:hi], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 events.append(ev)
+        if drained[st] is not None:
+            main.wait_event(drained[st])              # graph outputs of this set are free to be overwritten
         for ci, ((lo, hi), ev) in enumerate(zip(bounds, events)):
             main.wait_event(ev)
-            outs = chunk_steps[ci].replay() if chunk_steps else hot_path({k: v[lo:hi] for k, v in staging.items()})
-            for name, t in zip(("fused", "verts", "joints", "gcn_left", "gcn_right"), outs):
-                if name not in out_host:
-                    out_host[name] = torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
-                out_host[name][lo:hi].copy_(t, non_blocking=True)
+            outs = chunk_steps[st][ci].replay() if chunk_steps else \
+                hot_path({k: v[lo:hi] for k, v in staging[st].items()})
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(out_stream):
+                out_stream.wait_event(done)
+                for n, t in zip(names, outs):
+                    out_host[st][n][lo:hi].copy_(t, non_blocking=True)
+                    t.record_stream(out_stream)
+        consumed[st] = torch.cuda.Event()
+        consumed[st].record(main)
+        drained[st] = torch.cuda.Event()
+        drained[st].record(out_stream)
 
-    ms_e2e = timed_loop(e2e_step, args.steps, args.warmup)
+    def e2e_loop(steps, warmup):
+        for i in range(warmup):
+            e2e_step(i)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            e2e_step(warmup + i)
+        main = torch.cuda.current_stream()
+        main.wait_stream(copy_stream)
+        main.wait_stream(out_stream)                  # the last results are on the host when the clock stops
+        b.record()
+        barrier()
+        return parallel.max_over_ranks(a.elapsed_time(b) / steps, dev)
+
+    ms_e2e = e2e_loop(args.steps, args.warmup)
     torch.cuda.synchronize()
-    d2h_bytes = sum(v.numel() * v.element_size() for v in out_host.values())
+    d2h_bytes = sum(v.numel() * v.element_size() for v in out_host[0].values())
 
     # ---- per-stage timing (roofline of the dominant kernel), same inputs, L2 flushed ----
     for _ in range(2):
@@ -333,17 +448,32 @@ def run_ours(args):
     stages = profiling.summary()
     profiling.enable(False)
 
+    # ---- BASELINE cfg2 (SA microbench) and cfg5 (training step) sub-records, same process ----
+    kernels = run_cfg2(args, dev=dev, emit=False)["kernels"] if (not args.no_sub and rank == 0) else None
+    del staging, chunk_steps, out_host, probe
+    torch.cuda.empty_cache()
+    train = None
+    if not args.no_sub:
+        targs = argparse.Namespace(**vars(args))
+        targs.frames, targs.precision, targs.steps, targs.warmup = 64, "fp32", min(args.steps, 5), 3
+        try:
+            train = run_cfg5(targs, emit=False, dist_ready=(rank, world, local))
+        except Exception as e:                        # never lose the main line over the sub-record
+            train = {"error": str(e)[:200]}
+        torch.set_grad_enabled(False)
+
     if rank != 0:
         if world > 1:
             torch.distributed.barrier()
             torch.distributed.destroy_process_group()
         return
 
-    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         j = json.load(open(pk))
-        peaks = {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops"], "source": "measured"}
+        peaks = {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops"],
+                 "bf16_tflops_sustained": j.get("bf16_tflops_sustained", j["bf16_tflops"]), "source": "measured"}
     n_clouds = 2 * B
     stage_ms = {k: t for k, (c, t) in stages.items()}
     flops = {"sa1": FLOP_SA1 * n_clouds, "sa2": FLOP_SA2 * n_clouds, "global_mlp": FLOP_GLOBAL * n_clouds,
@@ -351,46 +481,61 @@ def run_ours(args):
     dom = max(flops, key=lambda k: stage_ms.get(k, 0.0))
     ach = flops[dom] / (stage_ms[dom] * 1e-3) / 1e12
     tensor_stage = args.precision == "bf16" and dom in ("sa1", "sa2", "global_mlp")
-    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/), if any
-    traffic = None
-    for cand in sorted((f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_dram_traffic.json")),
-                       reverse=True) if os.path.isdir(os.path.join(ROOT, "profiles")) else []:
-        tj = json.load(open(os.path.join(ROOT, "profiles", cand)))
+    # DRAM bytes per launch of that kernel: NOT measured in this run - read from the newest committed
+    # `ncu --set full` capture (profiles/*_dram_traffic.json) and labelled as such
+    traffic, traffic_source = None, None
+    prof_dir = os.path.join(ROOT, "profiles")
+    for cand in sorted((f for f in os.listdir(prof_dir) if f.endswith("_dram_traffic.json")), reverse=True) \
+            if os.path.isdir(prof_dir) else []:
+        tj = json.load(open(os.path.join(prof_dir, cand)))
         if dom in tj and args.precision == "bf16" and B == 128:
-            traffic = tj[dom]
+            traffic, traffic_source = tj[dom], "profiles/" + cand + " (committed ncu capture, not this run)"
         break
     roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peaks["source"],
+                "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_source,
+                "peak_source": peaks["source"] + " burst bf16 (kernel timed alone with CUDA events)",
                 "pipe": "tcgen05 bf16" if tensor_stage else "FFMA fp32 (stage not yet on tensor cores)",
                 "launch_ms": stage_ms[dom]}
     stage_report = {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}
     stage_tflops = {k: round(flops[k] / (stage_ms[k] * 1e-3) / 1e12, 2) for k in flops if k in stage_ms}
+    sb = stage_bytes(args, B)
+    stage_hbm = {k: {"ms": round(stage_ms[k], 4), "algorithmic_gbs": round(sb[k] / (stage_ms[k] * 1e-3) / 1e9, 1),
+                     "frac_of_hbm": round(sb[k] / (stage_ms[k] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)}
+                 for k in sb if k in stage_ms}
+    hot_flops = sum(flops.values()) + 16777216 * B
+    if sustained is not None:
+        sustained["hot_path_tflops"] = round(hot_flops / (sustained["ms_per_step"] * 1e-3) / 1e12, 1)
+        sustained["frac_of_sustained_bf16"] = round(sustained["hot_path_tflops"] / peaks["bf16_tflops_sustained"], 4)
+        sustained["note"] = "point-branch FLOPs (569.9 GFLOP at 128 frames) over the WHOLE step time, against the " \
+                            "sustained cuBLAS figure; the step also holds the bandwidth / latency-bound stages"
 
     cores = os.cpu_count() or 1
     cpu_baseline = None
     if world == 1:
-        cpu_ts = time_cpu(args.cpu_sample_frames, R, 3, 1)
+        st_t = {}
+        cpu_ts = time_cpu(args.cpu_sample_frames, R, 3, 1, args.with_decoder, st_t)
         cpu_baseline = {"value": args.cpu_sample_frames / min(cpu_ts), "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "%d frames of the same workload, oracle port (torch CPU fp32, %d threads), best of 3"
-                                  % (args.cpu_sample_frames, cores)}
+                                  % (args.cpu_sample_frames, cores),
+                        "stage_ms_per_frame": {k: round(1e3 * v / (3 * args.cpu_sample_frames), 3) for k, v in st_t.items()}}
 
     line = {
         "metric": METRIC, "value": world * B / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "frames_per_gpu": B, "resolution": R, "precision": args.precision,
-                   "parallelism": "dp%d" % world, "l2": "256 MiB flush write between timed iterations; inputs 1.2 GB > L2",
-                   "pyramid_layout": args.pyramid_layout,
-                   "launch": "one CUDA-graph replay per step" if graphed else "eager (one ctypes call per kernel)",
-                   "randomness": "subset keys / permutations injected as inputs (reference uses np.random)"},
+        "config": config_dict(args, world, B, {
+            "l2": "256 MiB flush write between timed iterations; inputs %.2f GB > L2" % (h2d_bytes / 1e9),
+            "launch": "one CUDA-graph replay per step" if graphed else "eager (one ctypes call per kernel)"}),
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e,
-                "chunks": n_chunks,
-                "note": "all hot-path inputs (depth, masks, K, fp32 feature pyramid, centre features, keys) copied "
-                        "from pinned host memory every step (chunked, copy stream overlapped with compute); fused "
-                        "features + MANO verts/joints copied back"},
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e, "chunks": n_chunks,
+                "h2d_gbs_per_rank": round(h2d_bytes / (ms_e2e * 1e-3) / 1e9, 2),
+                "note": "all hot-path inputs (depth, uint8 masks, K, bf16 channels-last feature pyramid, centre "
+                        "features, centre indices) copied from pinned host memory every step; staging double-buffered "
+                        "across steps (copy / compute / result streams); fused features, MANO and GCN meshes and "
+                        "joints copied back; bound by the PCIe link of the GPU (and, at N>1, of the switch it shares)"},
         "gpu_launches": int(launches), "eager_ms_per_step": ms_eager, "clocks": clocks, "roofline": roofline,
-        "stages_ms": stage_report, "stages_tflops": stage_tflops,
+        "stages_ms": stage_report, "stages_tflops": stage_tflops, "stages_hbm": stage_hbm,
+        "value_sustained": sustained, "kernels": kernels, "train": train,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
@@ -399,15 +544,16 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
 
 
-def run_cfg2(args):
+def run_cfg2(args, dev=None, emit=True):
     """BASELINE.json configs[1]: PointNet++ set-abstraction microbench, 64 clouds x 1024 points:
     FPS (1024 -> 512, cloud re-ordered so the FPS picks come first, interhand.py:857-900) ->
     ball query (r = 0.1 => r2 = 0.01, k = 64) -> fused point-MLP 3->64->64->128 + max (tcgen05).
     Reports per-kernel time, achieved algorithmic HBM GB/s (SURVEY 8d bytes) and TFLOP/s."""
     from pdfnet_b200 import PointNet_Plus, ops, synth
     torch.set_grad_enabled(False)
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(dev)
+    if dev is None:
+        dev = torch.device("cuda", 0)
+        torch.cuda.set_device(dev)
     B, N, N1, K = args.clouds, 1024, 512, 64
     pts = synth.clouds(B, seed=317).to(dev)
     start = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(317)).to(dev)
@@ -456,7 +602,7 @@ def run_cfg2(args):
                 "hbm_frac": round(bytes_[k] / (per[k] * 1e-3) / 1e9 / peaks["hbm_gbs"], 5)} for k in per}
     kern["point_mlp"]["tflops"] = round(FLOP_SA1 * B / (per["point_mlp"] * 1e-3) / 1e12, 2)
     kern["point_mlp"]["tensor_frac"] = round(kern["point_mlp"]["tflops"] / peaks["bf16_tflops"], 4)
-    print(json.dumps({
+    rec = {
         "metric": "sa_microbench_clouds_per_sec", "value": B / (ms * 1e-3), "unit": "clouds/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -466,7 +612,10 @@ def run_cfg2(args):
         "note": "FPS and the neighbour search keep the 12 KB cloud in shared memory/registers: they are SM "
                 "latency/issue bound by construction, so their HBM fraction is tiny (SURVEY 8d); %d clouds "
                 "occupy %d of 148 SMs in the one-CTA-per-cloud FPS kernel" % (B, min(B, 148)),
-    }))
+    }
+    if emit:
+        print(json.dumps(rec))
+    return rec
 
 
 def cfg5_workload(args):
@@ -537,11 +686,13 @@ def run_cfg5_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
 
-def run_cfg5(args):
+def run_cfg5(args, emit=True, dist_ready=None):
     """BASELINE.json configs[4] restricted to the hot path: one training step = train-mode forward +
-    backward on this repo's kernels, ONE flat-bucket gradient all-reduce over NCCL, Adam update."""
+    backward on this repo's kernels, bucketed gradient all-reduce over NCCL overlapped with the backward
+    pass, Adam update.  emit=False: called from the default workload, returns the record instead of printing."""
     from pdfnet_b200 import parallel
-    rank, world, local = parallel.init_distributed("nccl")
+    torch.set_grad_enabled(True)
+    rank, world, local = dist_ready if dist_ready is not None else parallel.init_distributed("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     from pdfnet_b200 import HandFusion, _lib, training
@@ -560,13 +711,14 @@ def run_cfg5(args):
     staging = {k: torch.empty_like(v) for k, v in resident.items()}
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     comm_bytes = [0]
+    sync = training.BucketedAllReduce(params, world, bucket_bytes=args.bucket_mb << 20)
 
     def train_step(d):
-        optim.zero_grad(set_to_none=True)
+        sync.zero_grad()                                       # gradients are views of the all-reduce buckets
         fused = model(d["cloud"], [d["l0"], d["l1"], d["l2"]], d["choose"], d["center"])
         loss = ((fused - d["target"]) ** 2).mean()
-        loss.backward()
-        comm_bytes[0] = training.allreduce_gradients(params, world)
+        loss.backward()                                        # hooks launch each bucket's all-reduce as it fills
+        comm_bytes[0] = sync.finish()
         optim.step()
         return loss
 
@@ -605,13 +757,15 @@ def run_cfg5(args):
     ms_e2e = timed_loop(e2e_step, args.steps, args.warmup)
     loss = float(train_step(resident).detach())
     peak_mem = torch.cuda.max_memory_allocated(dev)
+    sync.remove()
+    rec = None
     if rank == 0:
         n_clouds = 2 * B
         fwd = (FLOP_SA1 + FLOP_SA2 + FLOP_GLOBAL + FLOP_SFT1 + FLOP_SFT2) * n_clouds
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
             os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
         ach = 3 * fwd / (ms_dev * 1e-3) / 1e12                 # forward + data-gradient + weight-gradient GEMMs
-        print(json.dumps({
+        rec = {
             "metric": "train_frames_per_sec_hot_path", "value": world * B / (ms_dev * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -629,11 +783,17 @@ def run_cfg5(args):
                          "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": ach / peaks["bf16_tflops"], "traffic": None,
                          "pipe": "tcgen05 bf16; the step is dominated by HBM-bound staging / BatchNorm passes"},
-            "allreduce_bytes_per_step": comm_bytes[0], "final_loss": loss, "peak_mem_gb": peak_mem / 2 ** 30,
-            "cpu_baseline": None}))
-    if world > 1:
+            "allreduce_bytes_per_step": comm_bytes[0], "allreduce_buckets": len(sync.buckets),
+            "allreduce": "bucketed (%d MiB), launched from gradient hooks, overlapped with the backward pass" % args.bucket_mb,
+            "final_loss": loss, "peak_mem_gb": peak_mem / 2 ** 30, "cpu_baseline": None}
+        if emit:
+            print(json.dumps(rec))
+    del model, optim, sync, resident, staging
+    torch.cuda.empty_cache()
+    if emit and world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+    return rec
 
 
 def decoder_flops_per_frame():
@@ -764,11 +924,18 @@ def main():
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--cpu-sample-frames", type=int, default=16,
                     help="frames per CPU step of the reference arm / cpu_baseline leg (about 1.6 s of 16-thread CPU work each)")
-    ap.add_argument("--pyramid-layout", default="nchw", choices=["nchw", "nhwc"],
-                    help="memory format of the RGB feature pyramid inputs (nchw = what the reference neck emits; "
-                         "nhwc = torch.channels_last hand-off, SURVEY 8f row f4)")
-    ap.add_argument("--with-decoder", action="store_true",
-                    help="cfg3: also run the GCN decoder (SURVEY 8f row f3) on the fused features inside the step")
+    ap.add_argument("--pyramid", default=None, choices=["bf16-nhwc", "fp32-nchw", "fp32-nhwc"],
+                    help="dtype / memory format of the RGB feature pyramid inputs: bf16-nhwc = what an autocast "
+                         "channels-last neck emits (default in bf16 mode; BASELINE cfg3 is a bf16 forward), fp32-nchw = "
+                         "what the reference neck emits (default in fp32 mode), fp32-nhwc = SURVEY 8f row f4")
+    ap.add_argument("--masks", default="u8", choices=["u8", "f32"], help="hand mask dtype (f32 = the reference's)")
+    ap.add_argument("--no-decoder", dest="with_decoder", action="store_false",
+                    help="cfg3: leave the GCN decoder + joint regressor (SURVEY 8f row f3, a15) out of the step")
+    ap.add_argument("--no-sub", action="store_true",
+                    help="cfg3: skip the cfg2 (SA microbench) and cfg5 (training step) sub-records of the line")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0,
+                    help="cfg3: also loop the step for this long and report value_sustained (0 = off)")
+    ap.add_argument("--bucket-mb", type=int, default=4, help="cfg5: gradient all-reduce bucket size (MiB)")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch path instead of a CUDA-graph replay")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="H2D/compute overlap chunks in the e2e measurement")
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5", "decoder"],
@@ -790,6 +957,8 @@ def main():
         args.frames = 64 if args.workload == "cfg5" else 128
     if args.precision is None:
         args.precision = "fp32" if args.workload == "cfg5" else "bf16"
+    if args.pyramid is None:
+        args.pyramid = "bf16-nhwc" if args.precision == "bf16" else "fp32-nchw"
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.workload == "cfg5":
         (run_cfg5_reference if args.impl == "reference" else run_cfg5)(args)

@@ -105,6 +105,16 @@ int pdf_pyramid_gather_nhwc(const float* xyz, const int64_t* choose, int64_t n_c
                             int n_points, int n1, int n2, int R,
                             const float* l0, const float* l1, int C1, const float* l2, int C2,
                             const float* sft0_params, float* pts0, float* cond1, float* cond2, void* stream);
+/* bf16 channels-last pyramid (what an autocast / channels_last RGB neck emits; SURVEY 8d "bf16 features",
+ * 8f row f4): l0 [F,R,R,3], l1 [F,R/2,R/2,C1], l2 [F,R/4,R/4,C2] bf16.  pts0 as pdf_pyramid_gather (SFT0 in
+ * fp32 on the widened bf16 values).  The condition rows are written DIRECTLY as the bf16 tile images the SFT
+ * GEMMs read: cond1_img = image of [n_clouds*n1, C1], cond2_img = image of [n_clouds*n2, C2]
+ * (pdf_image_bytes each; C1, C2 multiples of 64; row counts multiples of 128). */
+int pdf_pyramid_gather_bf16(const float* xyz, const int64_t* choose, int64_t n_clouds, int clouds_per_frame,
+                            int n_points, int n1, int n2, int R, const void* l0, const void* l1, int C1,
+                            const void* l2, int C2, const float* sft0_params, float* pts0, void* cond1_img,
+                            void* cond2_img, void* stream);
+
 
 /* Grouping gather: out[b,g,j,c] = pts[b, idx[b,g,j], c] - (c < 3 ? pts[b,g,c] : 0).
  * Replaces lib/utils/utils.py:153-158 and :181-186.  pts addressed with
@@ -245,6 +255,19 @@ int pdf_backproject(const float* depth, const float* Kinv, int64_t B, int H, int
 int pdf_depth2pcl(const float* depth, const float* mask, const float* Kinv, const float* valid,
                   const int32_t* subset_keys, const int32_t* perm, int64_t B, int H, int W,
                   int n_points, int min_pixels, int64_t* choose, float* cloud, int32_t* n_cand, void* stream);
+/* Same cloud builder with (a) the hand masks as fp32 (mask_is_u8 = 0) or uint8 / bool (mask_is_u8 = 1: any
+ * non-zero byte is "mask > 0.5", 4x fewer bytes across PCIe and HBM) and (b) generated randomness: when
+ * subset_keys / perm are null they are replaced by counter-based functions of (seed, cloud = 2*frame + hand,
+ * pixel / slot): key = murmur-style hash (unsigned order, ties -> lower pixel), perm = a 4-round Feistel
+ * bijection of [0,1024).  pdf_depth2pcl_host_randomness materialises exactly these on the host (keys as int32
+ * in the signed order pdf_depth2pcl expects), so a caller - and the parity tests - can hand the same
+ * randomness to the reference's depth2pcl (intaghand_encoder.py:418-427, np.random.shuffle x2). */
+int pdf_depth2pcl_seeded(const float* depth, const void* mask, int mask_is_u8, const float* Kinv, const float* valid,
+                         const int32_t* subset_keys, const int32_t* perm, uint32_t seed, int64_t B, int H, int W,
+                         int n_points, int min_pixels, int64_t* choose, float* cloud, int32_t* n_cand, void* stream);
+int pdf_depth2pcl_host_randomness(uint32_t seed, int64_t n_clouds, int64_t npx, int32_t* keys_out_host,
+                                  int32_t* perm_out_host);
+
 
 /* MANO linear blend skinning, one hand per CTA, fp32.
  * Replaces ManoLayer.forward with use_pca=False (lib/models/networks/manolayer.py:

@@ -370,6 +370,38 @@ def depth2pcl(depth, mask, K, valid, subset_keys, perm, num_points=1024, min_pix
     return np.stack(chooses), np.stack(clouds)
 
 
+def _mix32(h):
+    """murmur3 finaliser on uint32 arrays."""
+    h = h.astype(np.uint32)
+    h ^= h >> np.uint32(16)
+    h = (h * np.uint32(0x85EBCA6B)).astype(np.uint32)
+    h ^= h >> np.uint32(13)
+    h = (h * np.uint32(0xC2B2AE35)).astype(np.uint32)
+    h ^= h >> np.uint32(16)
+    return h
+
+
+def d2p_seeded_randomness(seed, n_clouds, npx):
+    """The injected randomness pdf_depth2pcl_seeded generates from ``seed`` (include/pdfnet_b200.h), restated
+    in numpy: keys int32 [n_clouds, npx] (signed order = the kernel's unsigned hash order) and perm int32
+    [n_clouds, 1024] (4-round Feistel bijection on two 5-bit halves).  cloud = 2*frame + hand."""
+    with np.errstate(over="ignore"):
+        seed = np.uint32(seed & 0xFFFFFFFF)
+        c = np.arange(n_clouds, dtype=np.uint32)[:, None]
+        pix = np.arange(npx, dtype=np.uint32)[None, :]
+        cs = _mix32(seed ^ (c * np.uint32(0x27D4EB2F) + np.uint32(0x165667B1)).astype(np.uint32))
+        keys = _mix32((pix * np.uint32(0x9E3779B1)).astype(np.uint32) + cs)
+        keys = (keys ^ np.uint32(0x80000000)).view(np.int32)
+        k = _mix32((seed * np.uint32(0x9E3779B1)).astype(np.uint32) + c + np.uint32(0x7F4A7C15))
+        i = np.arange(1024, dtype=np.uint32)[None, :]
+        l, r = i >> np.uint32(5), i & np.uint32(31)
+        for rnd in range(4):
+            f = _mix32(r + np.uint32(32 * rnd) + k) & np.uint32(31)
+            l, r = r, l ^ f
+        perm = ((l << np.uint32(5)) | r).astype(np.int32)
+    return keys, perm
+
+
 # ----------------------------------------------------------------------------
 # MANO head, coefficient split, linear blend skinning
 # ----------------------------------------------------------------------------

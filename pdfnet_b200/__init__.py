@@ -20,7 +20,7 @@ _COMPUTE = {
     "mano_tail": "manolayer", "mano_tail_pair": "manolayer", "patch_reference": "patch",
     "rodrigues_batch": "manolayer", "process_J_regressor": "manolayer", "regress_joints": "manolayer",
     "decoder": "decoder", "load_decoder": "decoder", "CapturedStep": "graph", "pointnet_plus_train": "training", "hand_fusion_train": "training",
-    "allreduce_gradients": "training",
+    "allreduce_gradients": "training", "BucketedAllReduce": "training",
 }
 
 

@@ -38,6 +38,11 @@ SIGNATURES = {
     "pdf_center_im2col": [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp],
     "pdf_backproject": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
     "pdf_depth2pcl": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+    "pdf_depth2pcl_seeded": [_vp, _vp, _i32, _vp, _vp, _vp, _vp, ctypes.c_uint32, _i64, _i32, _i32, _i32, _i32, _vp, _vp,
+                             _vp, _vp],
+    "pdf_depth2pcl_host_randomness": [ctypes.c_uint32, _i64, _i64, _vp, _vp],
+    "pdf_pyramid_gather_bf16": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp,
+                                _vp, _vp, _vp],
     "pdf_mano_lbs": [_vp] * 11 + [_i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "pdf_mano_lbs_rootmat": [_vp] * 11 + [_i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "pdf_rodrigues": [_vp, _i64, _vp, _vp],

@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
           mbar_wait(smem_u32(&bars[G_STAGES + stage]), phase ^ 1);
           const uint32_t full = smem_u32(&bars[stage]);
           mbar_expect_tx(full, 2 * G_BLOCK);
-          bulk_g2s(smem_u32(smem + stage * 2 * G_BLOCK), mb + (size_t)kb * G_BLOCK, G_BLOCK, full);
+          // the M image may hold fewer k-blocks than KB: they are reused cyclically (a bf16-exact activation
+          // against a [hi | lo] split weight image reads the same activation block for both products)
+          bulk_g2s(smem_u32(smem + stage * 2 * G_BLOCK), mb + (size_t)(kb % P.m_kb) * G_BLOCK, G_BLOCK, full);
           bulk_g2s(smem_u32(smem + stage * 2 * G_BLOCK + G_BLOCK), nb + (size_t)kb * G_BLOCK, G_BLOCK, full);
           if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -474,7 +476,8 @@ extern "C" int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const voi
   using namespace pdf;
   if (m_tiles == 0 || n_tiles == 0) return PDF_OK;
   PDF_REQUIRE(m_img && n_img && bias0, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: null pointer");
-  PDF_REQUIRE(m_tiles > 0 && n_tiles > 0 && KB > 0 && KB <= m_kb && KB <= n_kb && kb_split >= 0 && kb_split < KB,
+  PDF_REQUIRE(m_tiles > 0 && n_tiles > 0 && KB > 0 && m_kb > 0 && (KB <= m_kb || KB % m_kb == 0) && KB <= n_kb &&
+                  kb_split >= 0 && kb_split < KB,
               PDF_ERR_BAD_ARG, "pdf_gemm_bf16: bad size");
   PDF_REQUIRE(act >= 0 && act <= 2, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: bad activation");
   GemmParams P;

@@ -196,6 +196,16 @@ class decoder(nn.Module):
     def get_upsample_weight(self):
         return self.unsample_layer.weight.data
 
+    def set_joint_regressors(self, J_regressor_left, J_regressor_right):
+        """Optional epilogue: with the MANO rest-joint regressors [16,778] of both hands set, forward
+        also returns the 21 joints ``full_regressor @ verts3d`` (Mano_model.py:309-323, what demo.py:217-218 and
+        simplified.py:431-434 compute right after the decoder) as ``otherInfo['joints3d'][side]`` [B,21,3]."""
+        from .manolayer import process_J_regressor
+        for side, J in (("left", J_regressor_left), ("right", J_regressor_right)):
+            reg = process_J_regressor(torch.as_tensor(np.asarray(J), dtype=torch.float32))
+            self.register_buffer("_full_regressor_" + side, reg.to(self.dense_coor.device), persistent=False)
+        return self
+
     def get_converter(self):
         return self.converter
 
@@ -398,6 +408,9 @@ class decoder(nn.Module):
                 result["verts3d"][side], result["verts2d"][side] = v778, d2
                 other["verts3d_MANO_list"][side].append(m3)
                 other["verts2d_MANO_list"][side].append(m2)
+                reg = getattr(self, "_full_regressor_" + side, None)
+                if reg is not None:
+                    other.setdefault("joints3d", {})[side] = ops.joint_regress(reg, v778)
             paramsDict = {"scale": scale, "trans2d": trans2d, "root": root}
             handDictList = [{"verts3d": verts3d, "verts2d": verts2d}]
             return result, paramsDict, handDictList, other

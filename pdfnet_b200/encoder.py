@@ -248,6 +248,7 @@ class PointNet_Plus(nn.Module):
         if frame0:
             nf = (B + cpf - 1) // cpf
             emb = [e[frame0:frame0 + nf] for e in emb]
+        emb = [e.float() if e.dtype != torch.float32 else e for e in emb]
         # level 0: pixel->point gather at three pyramid levels + SFT0 on xyz (:120-128), fp32
         with stage("pyramid_gather"):
             pts0, cond1, cond2 = ops.pyramid_gather(points, choose, emb, f["sft0"], N1, N2, opt.default_resolution,
@@ -301,9 +302,16 @@ class PointNet_Plus(nn.Module):
             emb = [e[frame0:frame0 + nf] for e in emb]
         u8 = lambda n: torch.empty((n,), dtype=torch.uint8, device=dev)
         RELU, LEAKY, BLK = L.ACT_RELU, L.ACT_LEAKY01, 16384
+        # a bf16 channels-last pyramid (autocast RGB neck) is gathered straight into the SFT GEMMs' operand images
+        bf16_emb = all(ops._is_bf16_nhwc(e) for e in emb) and (B * N1) % 128 == 0 and (B * N2) % 128 == 0
         with stage("pyramid_gather"):
-            pts0, cond1, cond2 = ops.pyramid_gather(points, choose, emb, f["sft0"], N1, N2, opt.default_resolution,
-                                                    cpf)
+            if bf16_emb:
+                pts0, c1img, c2img = ops.pyramid_gather_bf16(points, choose, emb, f["sft0"], N1, N2,
+                                                             opt.default_resolution, cpf)
+            else:
+                emb = [e.float() if e.dtype != torch.float32 else e for e in emb]
+                pts0, cond1, cond2 = ops.pyramid_gather(points, choose, emb, f["sft0"], N1, N2,
+                                                        opt.default_resolution, cpf)
         with stage("knn1"):
             idx1 = ops.knn_ball(pts0, N1, K, opt.ball_radius)
         x1 = torch.empty((B, N1, 132), dtype=torch.float32, device=dev)
@@ -311,14 +319,20 @@ class PointNet_Plus(nn.Module):
             self._sa(pts0, idx1, "netR_1", f, x1, None)
         M1, M2 = B * N1, B * N2
         t1, t2 = M1 // 128, M2 // 128
-        x1r, c1r = x1.view(M1, 132), cond1.view(M1, 64)
+        x1r = x1.view(M1, 132)
         with stage("sft1"):
             # hidden = lrelu([Ws0;Wh0] cond): split-bf16 GEMM (fp32-accurate); the same epilogue modulates
             # the 3 xyz channels of x1 in fp32 (they drive the level-2 neighbour search)
-            c1img = ops.rows_to_image(c1r, 0, 64, split=True)
             h1img = u8(t1 * 2 * BLK)
-            ops.gemm_bf16(c1img, t1, 3, tc["sft1_w0"], 1, 3, 3, tc["sft1_b0"], act=LEAKY, out_img=h1img, out_kb=2,
-                          rows_valid=M1, tile_desc=[(0, 128, 0)], xyz_w=tc["sft1_xyz"], xyz_x=x1r)
+            if bf16_emb:
+                # cond is exactly representable in bf16: its image has ONE k-block, read for both products
+                # cond x W_hi + cond x W_lo (the [hi | lo] head of the split weight image)
+                ops.gemm_bf16(c1img, t1, 1, tc["sft1_w0"], 1, 3, 2, tc["sft1_b0"], act=LEAKY, out_img=h1img, out_kb=2,
+                              rows_valid=M1, tile_desc=[(0, 128, 0)], xyz_w=tc["sft1_xyz"], xyz_x=x1r)
+            else:
+                c1img = ops.rows_to_image(cond1.view(M1, 64), 0, 64, split=True)
+                ops.gemm_bf16(c1img, t1, 3, tc["sft1_w0"], 1, 3, 3, tc["sft1_b0"], act=LEAKY, out_img=h1img, out_kb=2,
+                              rows_valid=M1, tile_desc=[(0, 128, 0)], xyz_w=tc["sft1_xyz"], xyz_x=x1r)
             # modulated features leave as bf16 rows (the level-2 gather copies them with cp.async);
             # the xyz channels stay fp32 in x1 (they drive the level-2 neighbour search)
             x1h = torch.empty((M1, 128), dtype=torch.bfloat16, device=dev)
@@ -334,7 +348,8 @@ class PointNet_Plus(nn.Module):
         x2r = x2.view(M2, 260)
         four = [(0, 128, 0), (0, 128, 2), (0, 128, 4), (0, 128, 6)]
         with stage("sft2"):
-            c2img = ops.rows_to_image(cond2.view(M2, 256), 0, 256)
+            if not bf16_emb:
+                c2img = ops.rows_to_image(cond2.view(M2, 256), 0, 256)
             h2img = u8(t2 * 8 * BLK)
             ops.gemm_bf16(c2img, t2, 4, tc["sft2_w0"], 4, 4, 4, tc["sft2_b0"], act=LEAKY, out_img=h2img, out_kb=8,
                           rows_valid=M2, tile_desc=four)
@@ -540,13 +555,14 @@ def _fold_bn_linear(fc, bn):
     return w, b.float().contiguous()
 
 
-def depth2pcl_batched(depth, mask, K_img, valid, subset_keys=None, perm=None, generator=None, min_pixels=10):
+def depth2pcl_batched(depth, mask, K_img, valid, subset_keys=None, perm=None, generator=None, min_pixels=10,
+                      seed=None):
     """Device-side depth2pcl for a whole batch.  depth [B,H,W] or [B,1,H,W],
-    mask [B,2,H,W] at depth resolution, K_img [B,3,3], valid [B,2] -> choose int64
+    mask [B,2,H,W] at depth resolution (fp32, or uint8 / bool), K_img [B,3,3], valid [B,2] -> choose int64
     [B,2,1024] (row 0 = left), cloud fp32 [B,2,1024,3].  Randomness (the two
     np.random.shuffle calls, intaghand_encoder.py:421,427) is injected: ``subset_keys``
-    int32 [B,2,H*W] and ``perm`` int32 [B,2,1024]; by default both are drawn from
-    ``generator`` on the device."""
+    int32 [B,2,H*W] and ``perm`` int32 [B,2,1024]; with ``seed`` they are generated INSIDE the kernel
+    (counter-based, no key tensors at all); otherwise both are drawn from ``generator`` on the device."""
     if depth.dim() == 4:
         depth = depth[:, 0]
     B, H, W = depth.shape
@@ -554,11 +570,12 @@ def depth2pcl_batched(depth, mask, K_img, valid, subset_keys=None, perm=None, ge
     if mask.shape[-2:] != (H, W):
         raise RuntimeError("depth2pcl_batched: mask must already be at depth resolution")
     Kinv = torch.linalg.inv(K_img.float())
-    if subset_keys is None:
-        subset_keys = torch.argsort(torch.rand((B, 2, H * W), device=dev, generator=generator), dim=2).int()
-    if perm is None:
-        perm = torch.argsort(torch.rand((B, 2, 1024), device=dev, generator=generator), dim=2).int()
-    choose, cloud, _ = ops.depth2pcl(depth, mask, Kinv, valid, subset_keys, perm, 1024, min_pixels)
+    if seed is None:
+        if subset_keys is None:
+            subset_keys = torch.argsort(torch.rand((B, 2, H * W), device=dev, generator=generator), dim=2).int()
+        if perm is None:
+            perm = torch.argsort(torch.rand((B, 2, 1024), device=dev, generator=generator), dim=2).int()
+    choose, cloud, _ = ops.depth2pcl(depth, mask, Kinv, valid, subset_keys, perm, 1024, min_pixels, seed=seed)
     return choose, cloud
 
 

@@ -113,6 +113,39 @@ def pyramid_gather(xyz, choose, emb, sft0_params, n1, n2, R, clouds_per_frame=1)
     return pts0, cond1, cond2
 
 
+def _is_bf16_nhwc(t):
+    return (t.dim() == 4 and t.dtype == torch.bfloat16
+            and (t.is_contiguous(memory_format=torch.channels_last) or t.shape[1] == 1))
+
+
+def pyramid_gather_bf16(xyz, choose, emb, sft0_params, n1, n2, R, clouds_per_frame=1):
+    """3-level gather from a bf16 channels-last pyramid + SFT0 (pdf_pyramid_gather_bf16).
+    Returns pts0 [B,N,3] fp32 and the two condition operands as bf16 TILE IMAGES (uint8 tensors):
+    image of [B*n1, C1] and of [B*n2, C2] - what the SFT GEMMs read, no intermediate rows."""
+    L.require_cuda(xyz, choose, emb[0], emb[1], emb[2], sft0_params)
+    xyz = L.f32c(xyz)
+    choose = choose.long().contiguous()
+    l0, l1, l2 = emb
+    if not all(_is_bf16_nhwc(e) for e in emb):
+        raise RuntimeError("pyramid_gather_bf16: the three maps must be bf16 in torch.channels_last memory format")
+    B, N, _ = xyz.shape
+    C1, C2 = l1.shape[1], l2.shape[1]
+    for lvl, (e, r) in enumerate(((l0, R), (l1, R // 2), (l2, R // 4))):
+        if tuple(e.shape[-2:]) != (r, r):
+            raise RuntimeError("pyramid_gather_bf16: level %d map is %s, expected %dx%d for default_resolution=%d"
+                               % (lvl, tuple(e.shape[-2:]), r, r, R))
+    if l0.shape[1] != 3 or l0.shape[0] * clouds_per_frame < B:
+        raise RuntimeError("pyramid_gather_bf16: level 0 must be [frames,3,R,R] with frames * clouds_per_frame >= clouds")
+    _check_index(choose, R * R, "pyramid_gather_bf16 (choose)")
+    dev = xyz.device
+    pts0 = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+    img1 = torch.empty((image_bytes(B * n1, C1),), dtype=torch.uint8, device=dev)
+    img2 = torch.empty((image_bytes(B * n2, C2),), dtype=torch.uint8, device=dev)
+    L.call("pdf_pyramid_gather_bf16", L.ptr(xyz), L.ptr(choose), B, clouds_per_frame, N, n1, n2, R, L.ptr(l0), L.ptr(l1),
+           C1, L.ptr(l2), C2, L.ptr(sft0_params), L.ptr(pts0), L.ptr(img1), L.ptr(img2), L.stream())
+    return pts0, img1, img2
+
+
 def group_gather(pts, idx, channel_major=False, out=None, want_center=True):
     """Grouped rows [B,N1,k,C] with centroid-relative xyz, and centres [B,N1,3]."""
     L.require_cuda(pts, idx)
@@ -262,13 +295,23 @@ def backproject(depth, Kinv):
     return xyz
 
 
-def depth2pcl(depth, mask, Kinv, valid, subset_keys=None, perm=None, n_points=1024, min_pixels=10):
-    """Batched device-side cloud builder (see pdf_depth2pcl).
+def depth2pcl(depth, mask, Kinv, valid, subset_keys=None, perm=None, n_points=1024, min_pixels=10, seed=None):
+    """Batched device-side cloud builder (see pdf_depth2pcl / pdf_depth2pcl_seeded).
+    mask: fp32 (the reference's dtype) or uint8 / bool (non-zero = hand).  Randomness: explicit
+    ``subset_keys`` int32 [B,2,H*W] / ``perm`` int32 [B,2,n]; whatever is None is generated inside the
+    kernel from ``seed`` (counter-based, reproducible on the host with d2p_host_randomness).
     Returns choose int64 [B,2,n], cloud fp32 [B,2,n,3], n_cand int32 [B,2]."""
     L.require_cuda(depth, mask, Kinv, valid, subset_keys, perm)
-    depth, mask, Kinv, valid = L.f32c(depth), L.f32c(mask), L.f32c(Kinv), L.f32c(valid)
+    depth, Kinv, valid = L.f32c(depth), L.f32c(Kinv), L.f32c(valid)
+    u8 = mask.dtype in (torch.uint8, torch.bool)
+    mask = mask.contiguous() if u8 else L.f32c(mask)
     B, H, W = depth.shape
     dev = depth.device
+    if (subset_keys is None or perm is None) and seed is None:
+        if perm is None:                                # historic behaviour of the unseeded entry: identity order
+            perm = torch.arange(n_points, dtype=torch.int32, device=dev).expand(B, 2, n_points)
+        if subset_keys is None and H * W > n_points:
+            raise RuntimeError("depth2pcl: pass subset_keys or a seed (a hand can exceed n_points pixels)")
     if subset_keys is not None:
         subset_keys = subset_keys.to(torch.int32).contiguous()
     if perm is not None:
@@ -276,9 +319,24 @@ def depth2pcl(depth, mask, Kinv, valid, subset_keys=None, perm=None, n_points=10
     choose = torch.empty((B, 2, n_points), dtype=torch.int64, device=dev)
     cloud = torch.empty((B, 2, n_points, 3), dtype=torch.float32, device=dev)
     n_cand = torch.empty((B, 2), dtype=torch.int32, device=dev)
-    L.call("pdf_depth2pcl", L.ptr(depth), L.ptr(mask), L.ptr(Kinv), L.ptr(valid), L.ptr(subset_keys), L.ptr(perm), B,
-           H, W, n_points, min_pixels, L.ptr(choose), L.ptr(cloud), L.ptr(n_cand), L.stream())
+    if u8 or seed is not None:
+        L.call("pdf_depth2pcl_seeded", L.ptr(depth), L.ptr(mask), 1 if u8 else 0, L.ptr(Kinv), L.ptr(valid),
+               L.ptr(subset_keys), L.ptr(perm), int(seed or 0) & 0xFFFFFFFF, B, H, W, n_points, min_pixels,
+               L.ptr(choose), L.ptr(cloud), L.ptr(n_cand), L.stream())
+    else:
+        L.call("pdf_depth2pcl", L.ptr(depth), L.ptr(mask), L.ptr(Kinv), L.ptr(valid), L.ptr(subset_keys), L.ptr(perm),
+               B, H, W, n_points, min_pixels, L.ptr(choose), L.ptr(cloud), L.ptr(n_cand), L.stream())
     return choose, cloud, n_cand
+
+
+def d2p_host_randomness(seed, n_clouds, npx, want_keys=True, want_perm=True):
+    """The keys int32 [n_clouds, npx] / perm int32 [n_clouds, 1024] that pdf_depth2pcl_seeded generates for
+    ``seed`` (host tensors; cloud = 2*frame + hand)."""
+    keys = torch.empty((n_clouds, npx), dtype=torch.int32) if want_keys else None
+    perm = torch.empty((n_clouds, 1024), dtype=torch.int32) if want_perm else None
+    L.call("pdf_depth2pcl_host_randomness", int(seed) & 0xFFFFFFFF, n_clouds, npx,
+           ctypes.c_void_p(keys.data_ptr()) if want_keys else None, ctypes.c_void_p(perm.data_ptr()) if want_perm else None)
+    return keys, perm
 
 
 def rodrigues(axis):

@@ -374,6 +374,88 @@ def hand_fusion_train(fusion, cloud, point_wise_emb, choose, center_features, wi
     return fused, theta
 
 
+class BucketedAllReduce(object):
+    """DDP's exchange step (main.py:44-73, base_trainer.py:94-95,147) for stand-alone use: gradients live as
+    VIEWS of a few flat buckets (filled back to front, the order in which the backward pass produces them); a
+    post-accumulate hook counts the ready gradients of a bucket and launches its NCCL all-reduce (SUM of
+    pre-divided values = mean) asynchronously the moment the last one lands, so the exchange of the late layers
+    overlaps the backward kernels of the early ones.  ``finish()`` makes the current stream wait for every
+    bucket (and exchanges buckets whose parameters received no gradient this step).
+
+        sync = BucketedAllReduce(params, world_size)
+        sync.zero_grad(); loss.backward(); sync.finish(); optimizer.step()
+    """
+
+    def __init__(self, params, world_size, bucket_bytes=4 << 20, group=None):
+        self.world, self.group = int(world_size), group
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets, self._of = [], {}
+        cur, size = [], 0
+        for p in reversed(self.params):
+            cur.append(p)
+            size += p.numel() * p.element_size()
+            if size >= bucket_bytes:
+                self._close(cur)
+                cur, size = [], 0
+        if cur:
+            self._close(cur)
+        self._hooks = []
+        if self.world > 1:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._ready))
+        self.bytes_per_step = sum(b["flat"].numel() * b["flat"].element_size() for b in self.buckets)
+
+    def _close(self, plist):
+        flat = torch.zeros(sum(p.numel() for p in plist), dtype=plist[0].dtype, device=plist[0].device)
+        off = 0
+        for p in plist:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        b = dict(flat=flat, params=plist, pending=len(plist), work=None)
+        for p in plist:
+            self._of[p] = b
+        self.buckets.append(b)
+
+    def _launch(self, b):
+        import torch.distributed as dist
+        b["flat"].mul_(1.0 / self.world)
+        b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _ready(self, p):
+        b = self._of[p]
+        b["pending"] -= 1
+        if b["pending"] == 0 and b["work"] is None:
+            self._launch(b)
+
+    def zero_grad(self):
+        """Zero the buckets (the gradients stay views of them) and re-arm the hooks."""
+        for b in self.buckets:
+            b["flat"].zero_()
+            b["pending"], b["work"] = len(b["params"]), None
+            off = 0
+            for p in b["params"]:                         # a caller may have replaced / dropped .grad
+                if p.grad is None or p.grad.data_ptr() != b["flat"].data_ptr() + off * b["flat"].element_size():
+                    p.grad = b["flat"][off:off + p.numel()].view_as(p)
+                off += p.numel()
+
+    def finish(self):
+        """-> bytes exchanged this step.  After it returns the current stream sees the averaged gradients."""
+        import torch.distributed as dist
+        if self.world <= 1 or not dist.is_initialized():
+            return 0
+        for b in self.buckets:
+            if b["work"] is None:                         # some parameter of the bucket got no gradient this step
+                self._launch(b)
+        for b in self.buckets:
+            b["work"].wait()
+        return self.bytes_per_step
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
 def allreduce_gradients(params, world_size, group=None):
     """DDP's exchange step (main.py:44-73): SUM over ranks then divide by world size, one flat
     bucket over NCCL / NVLink.  No-op outside an initialised process group."""

@@ -1,0 +1,12 @@
+#!/bin/bash
+# usage: scripts/gpurun_retry.sh <timeout-seconds> '<command>' [gpus]
+# Retries a gpurun call while the pool answers "busy / transient" (exit code 3: nothing charged).
+T=$1; CMD=$2; G=${3:-1}
+for i in $(seq 1 40); do
+  if [ "$G" = "1" ]; then /usr/local/graft/bin/gpurun --timeout "$T" -- "$CMD"; else /usr/local/graft/bin/gpurun --gpus "$G" --timeout "$T" -- "$CMD"; fi
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  echo "[retry] attempt $i: pool busy, sleeping 90 s"
+  sleep 90
+done
+exit 3

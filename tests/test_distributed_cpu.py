@@ -82,3 +82,57 @@ def test_two_rank_gradient_allreduce(tmp_path):
         assert r["none"] and r["nbytes"] == 4 * (15 + 7 + 8)
         for got, want in zip(r["grads"], expect):
             torch.testing.assert_close(got, want)
+
+
+def _bucket_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from pdfnet_b200 import parallel, training
+    parallel.init_distributed("gloo")
+    torch.manual_seed(5)                                           # same weights on every rank
+    net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(),
+                              torch.nn.Linear(16, 3))
+    unused = torch.nn.Parameter(torch.zeros(5))                    # never receives a gradient (unused head)
+    params = list(net.parameters()) + [unused]
+    sync = training.BucketedAllReduce(params, world, bucket_bytes=512)     # tiny buckets: several per step
+    x = torch.randn((8, 6), generator=torch.Generator().manual_seed(200 + rank))
+    outs = []
+    for step in range(2):                                          # second step: buckets re-armed, views intact
+        sync.zero_grad()
+        net(x * (step + 1)).pow(2).sum().backward()
+        nbytes = sync.finish()
+        outs.append([p.grad.clone() for p in params])
+    views = all(p.grad.data_ptr() >= b["flat"].data_ptr() for b in sync.buckets for p in b["params"])
+    torch.save(dict(outs=outs, nbytes=nbytes, n_buckets=len(sync.buckets), views=views),
+               os.path.join(out_dir, "b%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_bucketed_overlapped_allreduce(tmp_path):
+    """BucketedAllReduce (the cfg5 exchange, DDP semantics of base_trainer.py:94-95): gradients are views of
+    flat buckets, each bucket is all-reduced from a gradient hook as soon as it is complete, every rank ends
+    with the MEAN gradient, parameters without a gradient exchange zeros."""
+    world = 2
+    mp.spawn(_bucket_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(os.path.join(str(tmp_path), "b%d.pt" % r)) for r in range(world)]
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(),
+                              torch.nn.Linear(16, 3))
+    for step in range(2):
+        want = None
+        for r in range(world):
+            net.zero_grad()
+            x = torch.randn((8, 6), generator=torch.Generator().manual_seed(200 + r))
+            net(x * (step + 1)).pow(2).sum().backward()
+            g = [p.grad.clone() for p in net.parameters()]
+            want = g if want is None else [a + b for a, b in zip(want, g)]
+        want = [w / world for w in want]
+        for r in res:
+            for got, w in zip(r["outs"][step][:-1], want):
+                torch.testing.assert_close(got, w)
+            assert float(r["outs"][step][-1].abs().max()) == 0.0
+    n_el = sum(p.numel() for p in net.parameters()) + 5
+    assert res[0]["n_buckets"] >= 2 and res[0]["views"] and res[0]["nbytes"] == 4 * n_el

@@ -353,6 +353,92 @@ def test_depth2pcl_batched_matches_per_frame_oracle():
         assert rel_err(cloud[b].cpu().numpy(), cl) < 1e-6
 
 
+@torch.no_grad()
+def test_depth2pcl_seeded_randomness_and_uint8_masks():
+    """pdf_depth2pcl_seeded: uint8 masks and kernel-generated keys / permutation (no key tensors cross PCIe).
+    The oracle receives the SAME randomness, materialised by its own numpy restatement of the counter-based
+    functions, so choose stays bit-exact and the cloud within 1e-6; uint8 and fp32 masks, generated and
+    explicit randomness all agree bit for bit."""
+    from pdfnet_b200 import depth2pcl_batched, ops
+    B, R = 5, 128
+    depth, mask, K, valid = synth.rgbd_frames(B, R, seed=9)
+    valid[1, 0] = 0
+    mask[2, 1, :, :] = 0
+    mask[2, 1, 40:48, 8:40] = 1                       # 256 px -> wrap padding
+    mask[3, 0, :, :] = 0
+    mask[3, 0, 5:7, 5:8] = 1                          # 6 px < min_pixels -> zeros
+    depth[4, 30:60, :] = 3.0                          # beyond the noise gate
+    seed = 20261017
+    keys, perm = O.d2p_seeded_randomness(seed, 2 * B, R * R)
+    hk, hp = ops.d2p_host_randomness(seed, 2 * B, R * R)
+    assert (hk.numpy() == keys).all() and (hp.numpy() == perm).all()
+    keys, perm = keys.reshape(B, 2, R * R), perm.reshape(B, 2, 1024)
+    Kinv = torch.linalg.inv(K)
+    d, kd, vd = depth.to(DEV), Kinv.to(DEV), valid.to(DEV)
+    m_u8 = (mask > 0.5).to(torch.uint8).to(DEV)
+    ch8, cl8, n8 = ops.depth2pcl(d, m_u8, kd, vd, seed=seed)
+    for b in range(B):
+        ch, cl = O.depth2pcl(depth[b].numpy(), mask[b:b + 1].numpy(), K[b].numpy(), valid[b:b + 1].numpy(),
+                             keys[b], perm[b])
+        assert (ch8[b].cpu().numpy() == ch).all(), b
+        assert rel_err(cl8[b].cpu().numpy(), cl) < 1e-6
+    assert int(n8[3, 1]) == 6 and int(n8[1, 0]) == 0 and int(n8[2, 0]) == 256
+    # fp32 masks + generated randomness; uint8 masks + explicit randomness; bool masks: all identical
+    for mk, kw in ((mask.to(DEV), dict(seed=seed)),
+                   (m_u8, dict(subset_keys=torch.from_numpy(keys).to(DEV), perm=torch.from_numpy(perm).to(DEV))),
+                   (m_u8.bool(), dict(seed=seed))):
+        ch2, cl2, _ = ops.depth2pcl(d, mk, kd, vd, **kw)
+        assert torch.equal(ch2, ch8) and torch.equal(cl2, cl8)
+    # the unseeded fp32 entry (the reference's dtypes) with the same explicit randomness
+    ch3, cl3, _ = ops.depth2pcl(d, mask.to(DEV), kd, vd, torch.from_numpy(keys).to(DEV), torch.from_numpy(perm).to(DEV))
+    assert torch.equal(ch3, ch8) and torch.equal(cl3, cl8)
+    ch4, cl4 = depth2pcl_batched(d, m_u8, K.to(DEV), vd, seed=seed)
+    assert torch.equal(ch4, ch8) and torch.equal(cl4, cl8)
+    # a different seed selects a different subset, a different order, the same candidate set
+    ch5, _, n5 = ops.depth2pcl(d, m_u8, kd, vd, seed=seed + 1)
+    assert torch.equal(n5, n8) and not torch.equal(ch5, ch8)
+    a, b_ = ch5[2, 0].sort()[0], ch8[2, 0].sort()[0]   # wrap-padded hand: every candidate kept under both seeds
+    assert torch.equal(a, b_)
+
+
+@torch.no_grad()
+def test_bf16_channels_last_pyramid_hand_off():
+    """A bf16 channels-last pyramid (autocast RGB neck) is gathered straight into the SFT GEMMs' operand images
+    (pdf_pyramid_gather_bf16).  Result: bit-identical to the fp32 NCHW path fed the same (bf16-rounded) values -
+    the split-bf16 GEMM multiplies a zero low part there - and within the bf16 tolerance of the oracle."""
+    from pdfnet_b200 import HandFusion, ops
+    R, B = 64, 4
+    opt = _opt(default_resolution=R)
+    m = HandFusion(opt, precision="bf16")
+    m.pointnet_plus.load_state_dict(synth.pointnet_plus_state(seed=317), strict=False)
+    m.sft.load_state_dict(synth.fusion_sft_state(seed=317))
+    m = m.to(DEV).eval()
+    cloud = synth.clouds(2 * B, seed=51).view(B, 2, 1024, 3)
+    choose = synth.choose_indices(2 * B, R, seed=51).view(B, 2, 1024)
+    emb = [e.bfloat16() for e in synth.pyramid(B, R, seed=51)]
+    cen = torch.randn((B, 2, 1024), generator=torch.Generator().manual_seed(51))
+    emb_cl = [e.to(DEV).contiguous(memory_format=torch.channels_last) for e in emb]
+    emb_f32 = [e.float().to(DEV) for e in emb]
+    out_bf = m(cloud.to(DEV), emb_cl, choose.to(DEV), cen.to(DEV))
+    out_32 = m(cloud.to(DEV), emb_f32, choose.to(DEV), cen.to(DEV))
+    assert torch.equal(out_bf, out_32)
+    ref = O.fusion_tail(synth.pointnet_plus_state(seed=317), synth.fusion_sft_state(seed=317), cloud,
+                        [e.float() for e in emb], choose, cen, opt)
+    assert rel_err(out_bf.cpu(), ref) < 2e-2
+    # the images themselves: gathered rows in the SW128 tile layout
+    f = m.pointnet_plus.folded()
+    pts0, img1, img2 = ops.pyramid_gather_bf16(cloud.view(2 * B, 1024, 3).to(DEV), choose.view(2 * B, 1024).to(DEV),
+                                               emb_cl, f["sft0"], 512, 128, R, 2)
+    p0, c1, c2 = ops.pyramid_gather(cloud.view(2 * B, 1024, 3).to(DEV), choose.view(2 * B, 1024).to(DEV), emb_f32,
+                                    f["sft0"], 512, 128, R, 2)
+    assert torch.equal(pts0, p0)
+    assert torch.equal(img1, ops.rows_to_image(c1.view(-1, 64), 0, 64))
+    assert torch.equal(img2, ops.rows_to_image(c2.view(-1, 256), 0, 256))
+    # fp32 precision mode accepts the bf16 maps too (widened), and non-channels-last bf16 maps take the fp32 gather
+    out_nchw_bf16 = m(cloud.to(DEV), [e.to(DEV) for e in emb], choose.to(DEV), cen.to(DEV))
+    assert torch.equal(out_nchw_bf16, out_32)
+
+
 # ----------------------------------------------------------------------------- MANO tail
 
 @torch.no_grad()
@@ -477,7 +563,10 @@ def test_patched_gather_and_eval_mode_modules_carry_gradients():
         fused_ng, theta_ng = m(cloud.to(DEV), [e.to(DEV) for e in emb], choose.to(DEV), cen.to(DEV), with_mano=True)
     assert rel_err(fused.detach().cpu(), fused_ng.cpu()) < 1e-4 and rel_err(theta.detach().cpu(), theta_ng.cpu()) < 1e-4
     gd = torch.randn(fused.shape, generator=gen)
-    ((fused * gd.to(DEV)).sum() + theta.sum()).backward()
+    theta.sum().backward(retain_graph=True)             # the MANO-head branch reaches its own weights and the trunk
+    assert float(m.mano_head[0].weight.grad.abs().max()) > 0 and float(m.pointnet_plus.netR_3[6].weight.grad.abs().max()) > 0
+    m.zero_grad(set_to_none=True)
+    (fused * gd.to(DEV)).sum().backward()
     # oracle: the eval-mode restatement is built from differentiable torch ops once no_grad is lifted
     sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running_" not in k)
           for k, v in synth.pointnet_plus_state(seed=317).items()}
@@ -497,7 +586,6 @@ def test_patched_gather_and_eval_mode_modules_carry_gradients():
     for k in ("netR_3.6.weight", "netR_3.7.weight", "netR_3.7.bias", "netR_3.0.weight"):
         assert rel_err(dict(m.pointnet_plus.named_parameters())[k].grad.cpu(), sd[k].grad) < 2e-3, k
     assert float(m.pointnet_plus.netR_1[0].weight.grad.abs().max()) > 0         # the chain reaches the first layer
-    assert float(m.mano_head[0].weight.grad.abs().max()) > 0
     assert float(m.pointnet_plus.netR_3[1].running_mean.abs().sum()) > 0         # eval mode: buffers untouched
     torch.testing.assert_close(m.pointnet_plus.netR_3[1].running_mean.cpu(),
                                synth.pointnet_plus_state(seed=317)["netR_3.1.running_mean"])

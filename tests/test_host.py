@@ -174,6 +174,21 @@ def test_mano_pkl_loader_matches_npz_export(lib):
             assert (p[k] == d[k]).all(), k
 
 
+def test_seeded_depth2pcl_randomness_host_mirror_matches_numpy(lib):
+    """pdf_depth2pcl_host_randomness (the C mirror of the kernel's counter-based keys / permutation) equals the
+    oracle's independent numpy restatement; the permutation is a bijection of [0,1024)."""
+    from oracle import pdf_oracle as O
+    from pdfnet_b200 import ops
+    for seed in (0, 1, 317, 2 ** 32 - 1):
+        k, p = ops.d2p_host_randomness(seed, 5, 3000)
+        k2, p2 = O.d2p_seeded_randomness(seed, 5, 3000)
+        assert (k.numpy() == k2).all() and (p.numpy() == p2).all()
+        for c in range(5):
+            assert sorted(p2[c].tolist()) == list(range(1024))
+    assert not (O.d2p_seeded_randomness(1, 2, 64)[0][0] == O.d2p_seeded_randomness(1, 2, 64)[0][1]).all()
+    assert not (O.d2p_seeded_randomness(1, 1, 64)[1] == O.d2p_seeded_randomness(2, 1, 64)[1]).all()
+
+
 def test_shard_range_covers_everything():
     from pdfnet_b200.parallel import shard_range
     for n in (0, 1, 7, 128, 1024, 1025):
