@@ -428,6 +428,14 @@ int pdf_graph_cheby_ln(const float* U0, const float* U1, int64_t ldu, const floa
  * V <= 256, d in {16, 32, 64}. */
 int pdf_mha(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* Vv, int64_t ldv,
             int64_t n_samples, int V, int heads, int d, float* out, int64_t ldo, void* stream);
+/* The same attention on tensor cores (mma.sync m16n8k16, bf16 hi/lo SPLIT operands = fp32-accurate products,
+ * fp32 accumulate, online softmax), up to two problems of identical shape per launch: problem i reads
+ * q[i] / k[i] / v[i] (host arrays of device pointers; q and k may come from different hands: the R2L / L2R
+ * directions of inter_attn.py:84-108 are one launch) and writes out[i].  Row pitches in floats, even. */
+int pdf_mha_tc(const float* const* q, const float* const* k, const float* const* v, float* const* out, int n_problems,
+               int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t n_samples, int V, int heads, int d,
+               void* stream);
+
 /* projection_batch (lib/utils/utils.py:231-249) of the coarse [B,Vc,3] and dense [B,Vd,3] meshes with
  * params [B, >=3] = (scale, tx, ty), and the MANO-order lists of intaghand_decoder.py:231-240:
  * mano[b,i] = coarse[b, rev[i] / rep] (graph_upsample by rep, then GCN_to_vert). */

@@ -285,6 +285,13 @@ class decoder(nn.Module):
     def _ln(m):
         return (m.weight.detach(), m.bias.detach())
 
+    def _attention(self, problems, n, V):
+        """softmax(q k^T / sqrt(d)) v for 1-2 problems: tensor cores with split-bf16 operands on the tensor-core
+        precisions, the fp32 FFMA kernel on precision='fp32'."""
+        if self.precision != "fp32":
+            return ops.mha_tc(problems, n, V, self.heads)
+        return [ops.mha(q, k, v, n, V, self.heads, out=o) for q, k, v, o in problems]
+
     def _mlp(self, h, ff, h_img=None, M=None):
         f1 = self._linear(h, ff.fc1.weight.detach(), ff.fc1.bias.detach(), L.ACT_RELU, x_img=h_img, M=M)
         return self._linear(f1, ff.fc2.weight.detach(), ff.fc2.bias.detach())
@@ -304,7 +311,7 @@ class decoder(nn.Module):
         f, M = x.shape[1], x.shape[0]
         _, h, h_img = self._ln_for_gemm(x, None, self._ln(sa.layer_norm), False)
         qkv = self._linear(h, c[(li, name, "qkv_w")], c[(li, name, "qkv_b")], x_img=h_img, M=M)
-        a = ops.mha(qkv[:, :f], qkv[:, f:2 * f], qkv[:, 2 * f:], n, V, self.heads)
+        a = self._attention([(qkv[:, :f], qkv[:, f:2 * f], qkv[:, 2 * f:], None)], n, V)[0]
         g = self._linear(a, sa.fc.weight.detach(), sa.fc.bias.detach())
         x2, h2, h2_img = self._ln_for_gemm(x, g, self._ln(sa.ff.layer_norm), True)
         return x2, self._mlp(h2, sa.ff, h2_img, M)
@@ -328,8 +335,8 @@ class decoder(nn.Module):
             qkv = self._linear(both, c[(li, "X", "qkv_w")], c[(li, "X", "qkv_b")])        # shared projections
         q, k, v = qkv[:, :f], qkv[:, f:2 * f], qkv[:, 2 * f:]
         att = torch.empty((2 * M, f), dtype=torch.float32, device=l2.device)
-        ops.mha(q[:M], k[M:], v[M:], n, V, self.heads, out=att[:M])                         # R2L: left queries, right keys/values
-        ops.mha(q[M:], k[:M], v[:M], n, V, self.heads, out=att[M:])                         # L2R
+        # R2L (left queries, right keys / values) and L2R in one launch
+        self._attention([(q[:M], k[M:], v[M:], att[:M]), (q[M:], k[:M], v[:M], att[M:])], n, V)
         feat = self._linear(att, a.fc.weight.detach(), a.fc.bias.detach())
         x4l, h4l, h4l_img = self._ln_for_gemm(Lf, feat[:M], self._ln(a.ffL.layer_norm), True)
         x4r, h4r, h4r_img = self._ln_for_gemm(Rf, feat[M:], self._ln(a.ffR.layer_norm), True)

@@ -767,6 +767,31 @@ def mha(q, k, v, n_samples, V, heads, out=None):
     return out
 
 
+def mha_tc(problems, n_samples, V, heads):
+    """Tensor-core attention (pdf_mha_tc) for one or two problems of identical shape in ONE launch.
+    problems: [(q, k, v, out-or-None), ...] with q/k/v [n_samples*V, heads*d] column slices of fp32 rows that
+    share their row pitches.  Returns the list of outputs."""
+    outs, ptrs = [], ([], [], [], [])
+    q0, k0, v0, _ = problems[0]
+    M, f = _rows(q0).shape
+    assert M == n_samples * V and f % heads == 0 and 1 <= len(problems) <= 2
+    for q, k, v, out in problems:
+        L.require_cuda(q, k, v, out)
+        assert _rows(q).shape == (M, f) and _rows(k).shape == (M, f) and _rows(v).shape == (M, f)
+        assert q.stride(0) == q0.stride(0) and k.stride(0) == k0.stride(0) and v.stride(0) == v0.stride(0)
+        if out is None:
+            out = torch.empty((M, f), dtype=torch.float32, device=q.device)
+        assert out.stride(0) == (outs[0].stride(0) if outs else out.stride(0)) and out.stride(1) == 1
+        outs.append(out)
+        for lst, t in zip(ptrs, (q, k, v, out)):
+            L.ptr(t)                                        # registers the device for the launch guard
+            lst.append(t.data_ptr())
+    arr = [(ctypes.c_void_p * len(problems))(*lst) for lst in ptrs]
+    L.call("pdf_mha_tc", *[ctypes.cast(a, ctypes.c_void_p) for a in arr], len(problems), q0.stride(0), k0.stride(0),
+           v0.stride(0), outs[0].stride(0), n_samples, V, heads, f // heads, L.stream())
+    return outs
+
+
 def decoder_project(v_coarse, v_dense, params, img_size, rev, rep):
     """-> (coarse2d [B,Vc,2], dense2d [B,Vd,2], mano3d [B,Vd,3], mano2d [B,Vd,2]); see pdf_decoder_project."""
     L.require_cuda(v_coarse, v_dense, params, rev)

@@ -366,7 +366,7 @@ def test_depth2pcl_seeded_randomness_and_uint8_masks():
     mask[2, 1, :, :] = 0
     mask[2, 1, 40:48, 8:40] = 1                       # 256 px -> wrap padding
     mask[3, 0, :, :] = 0
-    mask[3, 0, 5:7, 5:8] = 1                          # 6 px < min_pixels -> zeros
+    mask[3, 0, 40:42, 10:13] = 1                      # 6 px < min_pixels -> zeros
     depth[4, 30:60, :] = 3.0                          # beyond the noise gate
     seed = 20261017
     keys, perm = O.d2p_seeded_randomness(seed, 2 * B, R * R)
@@ -1377,6 +1377,17 @@ def test_decoder_primitives_vs_torch():
         ref = ref.transpose(1, 2).reshape(n * V, f)
         got = ops.mha(q.to(DEV), k.to(DEV), v.to(DEV), n, V, heads)
         np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=2e-6, err_msg=str((V, heads, d)))
+        # tensor-core kernel (split-bf16 operands): fp32-accurate; q / k / v as column slices of one qkv buffer,
+        # and a second problem with swapped key / value source in the same launch (the cross-attention form)
+        qkv = torch.cat([q, k, v], 1).to(DEV)
+        qd, kd, vd = qkv[:, :f], qkv[:, f:2 * f], qkv[:, 2 * f:]
+        k2, v2 = rnd(n * V, f), rnd(n * V, f)
+        qkv2 = torch.cat([q, k2, v2], 1).to(DEV)
+        ref2 = torch.matmul(F.softmax(torch.matmul(sh(q), sh(k2).transpose(-1, -2)) / d ** 0.5, -1), sh(v2))
+        ref2 = ref2.transpose(1, 2).reshape(n * V, f)
+        o1, o2 = ops.mha_tc([(qd, kd, vd, None), (qd, qkv2[:, f:2 * f], qkv2[:, 2 * f:], None)], n, V, heads)
+        np.testing.assert_allclose(o1.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=1e-5, err_msg="tc " + str((V, heads, d)))
+        np.testing.assert_allclose(o2.cpu().numpy(), ref2.numpy(), rtol=1e-4, atol=1e-5, err_msg="tc2 " + str((V, heads, d)))
     with pytest.raises(RuntimeError):
         ops.mha(rnd(300, 32).to(DEV), rnd(300, 32).to(DEV), rnd(300, 32).to(DEV), 1, 300, 2)     # > 256 tokens
     # projection + MANO-order lists
