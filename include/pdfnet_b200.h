@@ -35,6 +35,9 @@ typedef enum {
 
 /* activation codes for pdf_linear_f32 */
 enum { PDF_ACT_NONE = 0, PDF_ACT_RELU = 1, PDF_ACT_LEAKY01 = 2 };
+/* OR-ed onto the `act` argument of pdf_gemm_bf16: out_img is written as a SPLIT image [hi | hi | lo]
+ * (out_kb = 3 x k-blocks of the output matrix), i.e. directly as the fp32-accurate M operand of the next GEMM. */
+enum { PDF_GEMM_OUT_SPLIT = 256 };
 /* epilogue modes for pdf_linear_f32 */
 enum {
   PDF_EPI_STORE = 0,     /* Y = act(acc + bias)                                   */
@@ -431,10 +434,13 @@ int pdf_mha(const float* Q, int64_t ldq, const float* K, int64_t ldk, const floa
 /* The same attention on tensor cores (mma.sync m16n8k16, bf16 hi/lo SPLIT operands = fp32-accurate products,
  * fp32 accumulate, online softmax), up to two problems of identical shape per launch: problem i reads
  * q[i] / k[i] / v[i] (host arrays of device pointers; q and k may come from different hands: the R2L / L2R
- * directions of inter_attn.py:84-108 are one launch) and writes out[i].  Row pitches in floats, even. */
-int pdf_mha_tc(const float* const* q, const float* const* k, const float* const* v, float* const* out, int n_problems,
-               int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t n_samples, int V, int heads, int d,
-               void* stream);
+ * directions of inter_attn.py:84-108 are one launch) and writes out[i] (fp32 rows, may be null) and / or
+ * out_img[i] (may be null): the split-bf16 tile image [hi | hi | lo] of the [n_samples*V, heads*d] result, i.e. the
+ * operand of the `fc` GEMM that follows; problem i's rows start at image row img_row0[i] (null = 0), so two
+ * problems can fill the two halves of ONE image.  Row pitches in floats, even. */
+int pdf_mha_tc(const float* const* q, const float* const* k, const float* const* v, float* const* out,
+               void* const* out_img, const int64_t* img_row0, int n_problems, int64_t ldq, int64_t ldk, int64_t ldv,
+               int64_t ldo, int64_t n_samples, int V, int heads, int d, void* stream);
 
 /* projection_batch (lib/utils/utils.py:231-249) of the coarse [B,Vc,3] and dense [B,Vd,3] meshes with
  * params [B, >=3] = (scale, tx, ty), and the MANO-order lists of intaghand_decoder.py:231-240:

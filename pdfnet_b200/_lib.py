@@ -72,7 +72,7 @@ SIGNATURES = {
     "pdf_graph_cheby_ln": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _f32, _i32,
                            _vp, _i64, _vp, _vp],
     "pdf_mha": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp],
-    "pdf_mha_tc": [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _vp],
+    "pdf_mha_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _vp],
     "pdf_decoder_project": [_vp, _i32, _vp, _i32, _vp, _i64, _f32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
     "pdf_mano_lbs_pair": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
 }
@@ -80,6 +80,7 @@ EXPORTS = sorted(list(SIGNATURES) + ["pdf_version", "pdf_last_error", "pdf_launc
                                      "pdf_image_bytes"])
 
 ACT_NONE, ACT_RELU, ACT_LEAKY01 = 0, 1, 2
+GEMM_OUT_SPLIT = 256          # OR-ed onto act: pdf_gemm_bf16 writes out_img as a split image [hi | hi | lo]
 EPI_STORE, EPI_SFT_SCALE, EPI_ACCUM, EPI_GROUP_MAX = 0, 1, 2, 3
 
 _lib = None

@@ -1,6 +1,6 @@
 // Device-side, batched depth2pcl: per-hand cloud construction from raw depth
 // (intaghand_encoder.py:369-491; dataset twin interhand.py:758-908).
-// One CTA (1024 threads) per (frame, hand).  The hand mask is scanned once (one 32-pixel word per lane;
+// One CTA (512 threads, two per SM) per (frame, hand).  The hand mask is scanned once (one 32-pixel word per lane;
 // 32 B of a uint8 mask or 128 B of an fp32 mask); depth is only read where the mask is set: warps walk
 // the ORDERED list of non-empty words with lane = pixel (coalesced 128 B), so the work after the mask
 // scan scales with the hand, not with the frame.  Everything else lives in shared-memory bitmasks.
@@ -11,7 +11,8 @@
 
 namespace pdf {
 
-constexpr int D2P_THREADS = 1024;
+constexpr int D2P_THREADS = 512;            // two CTAs per SM: one CTA's block-wide scans overlap the other's loads
+constexpr int D2P_WARPS = D2P_THREADS / 32;
 
 __host__ __device__ __forceinline__ uint32_t d2p_mix(uint32_t h) {     // murmur3 finaliser
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
@@ -35,7 +36,7 @@ __host__ __device__ __forceinline__ uint32_t d2p_perm1024(uint32_t seed, uint32_
 }
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
-  // 1024 threads = 32 warps; returns the exclusive prefix of v over the block.
+  // D2P_WARPS warps; returns the exclusive prefix of v over the block.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int inc = v;
 #pragma unroll
@@ -47,7 +48,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& tot
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    int w = s_warp[lane];
+    int w = lane < D2P_WARPS ? s_warp[lane] : 0;
     int winc = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -123,7 +124,7 @@ depth2pcl_kernel(const float* __restrict__ depth, const void* __restrict__ mask_
     // lane = pixel: one coalesced 128 B load per word, 8 words in flight per warp
     const float* msk = reinterpret_cast<const float*>(mask_v) + (f * 2 + mch) * (int64_t)npx;
     constexpr int U = 8;
-    for (int wb = warp * U; wb < nwords; wb += 32 * U) {
+    for (int wb = warp * U; wb < nwords; wb += D2P_WARPS * U) {
       float m[U];
 #pragma unroll
       for (int q = 0; q < U; ++q) {
@@ -164,7 +165,7 @@ depth2pcl_kernel(const float* __restrict__ depth, const void* __restrict__ mask_
   constexpr int UA = 4;                            // words (independent depth loads) in flight per warp
   double sum = 0.0;
   int cnt = 0;
-  for (int li = warp * UA; li < n_list; li += 32 * UA) {
+  for (int li = warp * UA; li < n_list; li += D2P_WARPS * UA) {
     int wq[UA];
     float d[UA];
 #pragma unroll
@@ -195,8 +196,8 @@ depth2pcl_kernel(const float* __restrict__ depth, const void* __restrict__ mask_
   if (lane == 0) { s_dsum[warp] = sum; s_warp[warp] = cnt; }
   __syncthreads();
   if (warp == 0) {
-    double s = s_dsum[lane];
-    int c = s_warp[lane];
+    double s = lane < D2P_WARPS ? s_dsum[lane] : 0.0;
+    int c = lane < D2P_WARPS ? s_warp[lane] : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -215,7 +216,7 @@ depth2pcl_kernel(const float* __restrict__ depth, const void* __restrict__ mask_
 
   // ---- pass B: candidate bitmask (:409): lo < z < hi ----
   int my_cand = 0;
-  for (int li = warp * UA; li < n_list; li += 32 * UA) {
+  for (int li = warp * UA; li < n_list; li += D2P_WARPS * UA) {
     int wq[UA];
     float d[UA];
 #pragma unroll
@@ -275,7 +276,7 @@ depth2pcl_kernel(const float* __restrict__ depth, const void* __restrict__ mask_
       if (tid < 256) s_hist[tid] = 0;
       __syncthreads();
       const uint32_t hmask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
-      for (int li = warp * U; li < n_list; li += 32 * U) {
+      for (int li = warp * U; li < n_list; li += D2P_WARPS * U) {
         uint32_t kx[U];
         bool on[U];
 #pragma unroll
@@ -310,7 +311,7 @@ depth2pcl_kernel(const float* __restrict__ depth, const void* __restrict__ mask_
       __syncthreads();
     }
     const uint32_t thr = prefix;                   // n_points-th smallest key; `remaining` ties are taken
-    for (int li = warp * U; li < n_list; li += 32 * U) {
+    for (int li = warp * U; li < n_list; li += D2P_WARPS * U) {
       uint32_t kx[U];
       bool on[U];
       int wq[U];

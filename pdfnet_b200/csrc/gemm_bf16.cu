@@ -40,6 +40,7 @@ struct GemmParams {
   float* out_f32; int64_t ld_out; int64_t rows_valid;
   const float* F; int64_t ldf;
   uint8_t* out_img; int out_kb;
+  int out_split;                 // out_img is a SPLIT image [hi | hi | lo] (3 x out_kb/3 k-blocks): the next GEMM's fp32-accurate operand
   uint16_t* out_bf16; int64_t ld_bf16;   // optional bf16 ROW-major output (same columns as out_f32, minus bf16_col_off)
   int bf16_col_off;
   float* out_max; int64_t ld_max;
@@ -248,14 +249,25 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
               }
             }
           }
-          if (P.out_img != nullptr) {
+          if (P.out_img != nullptr && c0 < ((nvalid + 63) & ~63)) {     // k-blocks past the valid columns do not exist
             uint8_t* blk = P.out_img + ((size_t)mt * P.out_kb + okb + (c0 >> 6)) * G_BLOCK;
+            const size_t part = (size_t)(P.out_kb / 3) * G_BLOCK;       // split image: distance between the three parts
 #pragma unroll
             for (int q = 0; q < 32; q += 8) {
               uint4 wv;
               wv.x = pack_bf16(y[q], y[q + 1]); wv.y = pack_bf16(y[q + 2], y[q + 3]);
               wv.z = pack_bf16(y[q + 4], y[q + 5]); wv.w = pack_bf16(y[q + 6], y[q + 7]);
-              *reinterpret_cast<uint4*>(blk + sw128_off(row, (c0 + q) & 63)) = wv;
+              const uint32_t off = sw128_off(row, (c0 + q) & 63);
+              *reinterpret_cast<uint4*>(blk + off) = wv;
+              if (P.out_split) {                                          // [hi | hi | lo]
+                uint4 wl;
+                wl.x = pack_bf16(y[q] - __uint_as_float(wv.x << 16), y[q + 1] - __uint_as_float(wv.x & 0xffff0000u));
+                wl.y = pack_bf16(y[q + 2] - __uint_as_float(wv.y << 16), y[q + 3] - __uint_as_float(wv.y & 0xffff0000u));
+                wl.z = pack_bf16(y[q + 4] - __uint_as_float(wv.z << 16), y[q + 5] - __uint_as_float(wv.z & 0xffff0000u));
+                wl.w = pack_bf16(y[q + 6] - __uint_as_float(wv.w << 16), y[q + 7] - __uint_as_float(wv.w & 0xffff0000u));
+                *reinterpret_cast<uint4*>(blk + part + off) = wv;
+                *reinterpret_cast<uint4*>(blk + 2 * part + off) = wl;
+              }
             }
           }
         }
@@ -479,9 +491,14 @@ extern "C" int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const voi
   PDF_REQUIRE(m_tiles > 0 && n_tiles > 0 && KB > 0 && m_kb > 0 && (KB <= m_kb || KB % m_kb == 0) && KB <= n_kb &&
                   kb_split >= 0 && kb_split < KB,
               PDF_ERR_BAD_ARG, "pdf_gemm_bf16: bad size");
+  const int out_split = (act & PDF_GEMM_OUT_SPLIT) ? 1 : 0;     // flag bit on the activation argument
+  act &= ~PDF_GEMM_OUT_SPLIT;
   PDF_REQUIRE(act >= 0 && act <= 2, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: bad activation");
+  PDF_REQUIRE(!out_split || (out_img && out_kb % 3 == 0 && !colmax), PDF_ERR_BAD_ARG,
+              "pdf_gemm_bf16: a split output image needs out_img with 3 x k-blocks");
   GemmParams P;
   memset(&P, 0, sizeof(P));
+  P.out_split = out_split;
   P.m_img = (const uint8_t*)m_img; P.n_img = (const uint8_t*)n_img;
   P.m_kb = m_kb; P.n_kb = n_kb; P.m_tiles = m_tiles; P.n_tiles = n_tiles; P.KB = KB; P.kb_split = kb_split;
   P.bias0 = bias0; P.bias1 = bias1; P.act = act;
@@ -506,7 +523,8 @@ extern "C" int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const voi
       P.tile_col[i] = tile_desc_host[3 * i]; P.tile_nvalid[i] = tile_desc_host[3 * i + 1]; P.tile_okb[i] = tile_desc_host[3 * i + 2];
       PDF_REQUIRE(P.tile_nvalid[i] >= 0 && P.tile_nvalid[i] <= 128 && (P.tile_col[i] % 4) == 0, PDF_ERR_BAD_ARG,
                   "pdf_gemm_bf16: bad tile descriptor %d", i);
-      PDF_REQUIRE(!out_img || P.tile_okb[i] + 2 <= out_kb, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: output image too narrow");
+      PDF_REQUIRE(!out_img || P.tile_okb[i] + (P.tile_nvalid[i] + 63) / 64 <= (out_split ? out_kb / 3 : out_kb),
+                  PDF_ERR_BAD_ARG, "pdf_gemm_bf16: output image too narrow");
       PDF_REQUIRE(!out_bf16 || ((P.tile_col[i] - bf16_col_off) % 8 == 0 && P.tile_nvalid[i] % 8 == 0), PDF_ERR_BAD_ARG,
                   "pdf_gemm_bf16: bf16 row output needs 8-column aligned tiles");
     }

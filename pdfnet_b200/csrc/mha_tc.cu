@@ -3,7 +3,8 @@
 //
 // One CTA per (problem, sample, head).  K and V^T of the head are staged in shared memory as bf16 hi / lo
 // pairs; a warp owns 16 query rows and walks the keys in chunks of 64 with an online softmax (running max
-// and sum, rescaled accumulators), so the 16 x V score tile never exists in full.  Both contractions run on
+// and sum, rescaled accumulators; scores in the log2 domain, 2^x on the SFU), so the 16 x V score tile never
+// exists in full.  Both contractions run on
 // mma.sync m16n8k16 (bf16 operands, fp32 accumulate) with SPLIT operands: x = hi + lo, products hi.hi + hi.lo
 // + lo.hi, i.e. ~2^-16 relative per product - the decoder holds a 1e-4 parity bound over ~40 chained layers,
 // which plain bf16 operands do not (measured in round 1).  The probability tile goes from the accumulator
@@ -11,18 +12,20 @@
 // shared-memory round trip.  The tiles are far too small (V <= 256, d <= 64) for a tcgen05 / TMEM pipeline to
 // pay off: one CTA's whole job is ~3 k MMAs.
 #include "pdf_common.cuh"
+#include "umma.cuh"
 
 namespace pdf {
 
 constexpr int MT_MAXV = 256;
 constexpr int MT_PROBLEMS = 2;
 
-struct MhaProblem { const float* q; const float* k; const float* v; float* out; };
+struct MhaProblem { const float* q; const float* k; const float* v; float* out; uint8_t* out_img; int64_t img_row0; };
 struct MhaParams {
   MhaProblem p[MT_PROBLEMS];
   int64_t ldq, ldk, ldv, ldo;
   int V, heads, n_samples;
   float inv_norm;
+  int img_kb;                    // k-blocks per part of the split output image (= heads * d / 64)
 };
 
 __device__ __forceinline__ uint32_t mt_pack(float lo, float hi) {            // bf16x2, element 0 in the low half
@@ -34,6 +37,12 @@ __device__ __forceinline__ uint32_t mt_pack(float lo, float hi) {            // 
 __device__ __forceinline__ void mt_split(float a, float b, uint32_t& hi, uint32_t& lo) {
   hi = mt_pack(a, b);
   lo = mt_pack(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+// 2^x on the SFU (ex2.approx, max relative error 2^-22; -inf / very negative -> 0)
+__device__ __forceinline__ float mt_exp2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 __device__ __forceinline__ void mt_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                        uint32_t b1) {
@@ -82,6 +91,7 @@ mha_tc_kernel(const MhaParams P) {
   __syncthreads();
 
   const int g = lane >> 2, t = lane & 3;          // mma fragment coordinates
+  const float qscale = P.inv_norm * 1.4426950408889634f;
   for (int qt = warp; qt * 16 < V; qt += nwarps) {
     const int r0 = qt * 16 + g, r1 = r0 + 8;      // this thread's two query rows
     // ---- Q fragments (pre-scaled by 1/sqrt(d)), split ----
@@ -94,8 +104,9 @@ mha_tc_kernel(const MhaParams P) {
         float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
         if (r0 < V) a = *reinterpret_cast<const float2*>(pb.q + (row0 + r0) * P.ldq + h * D + c);
         if (r1 < V) b = *reinterpret_cast<const float2*>(pb.q + (row0 + r1) * P.ldq + h * D + c);
-        mt_split(a.x * P.inv_norm, a.y * P.inv_norm, qh[ks][half * 2], ql[ks][half * 2]);
-        mt_split(b.x * P.inv_norm, b.y * P.inv_norm, qh[ks][half * 2 + 1], ql[ks][half * 2 + 1]);
+        // scores are kept in the log2 domain: q * (1/sqrt(d)) * log2(e), softmax via 2^x
+        mt_split(a.x * qscale, a.y * qscale, qh[ks][half * 2], ql[ks][half * 2]);
+        mt_split(b.x * qscale, b.y * qscale, qh[ks][half * 2 + 1], ql[ks][half * 2 + 1]);
       }
     }
     float o[D / 8][4];
@@ -138,7 +149,7 @@ mha_tc_kernel(const MhaParams P) {
       cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1)); cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
       cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1)); cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
       const float nm0 = fmaxf(m0, cm0), nm1 = fmaxf(m1, cm1);
-      const float sc0 = expf(m0 - nm0), sc1 = expf(m1 - nm1);
+      const float sc0 = mt_exp2(m0 - nm0), sc1 = mt_exp2(m1 - nm1);
       m0 = nm0; m1 = nm1;
       l0 *= sc0; l1 *= sc1;
 #pragma unroll
@@ -146,8 +157,8 @@ mha_tc_kernel(const MhaParams P) {
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
         if (n < nt) {
-          s[n][0] = expf(s[n][0] - m0); s[n][1] = expf(s[n][1] - m0);
-          s[n][2] = expf(s[n][2] - m1); s[n][3] = expf(s[n][3] - m1);
+          s[n][0] = mt_exp2(s[n][0] - m0); s[n][1] = mt_exp2(s[n][1] - m0);
+          s[n][2] = mt_exp2(s[n][2] - m1); s[n][3] = mt_exp2(s[n][3] - m1);
           l0 += s[n][0] + s[n][1];
           l1 += s[n][2] + s[n][3];
         }
@@ -183,8 +194,28 @@ mha_tc_kernel(const MhaParams P) {
 #pragma unroll
     for (int n = 0; n < D / 8; ++n) {
       const int c = h * D + n * 8 + 2 * t;
-      if (r0 < V) *reinterpret_cast<float2*>(pb.out + (row0 + r0) * P.ldo + c) = make_float2(o[n][0] * i0, o[n][1] * i0);
-      if (r1 < V) *reinterpret_cast<float2*>(pb.out + (row0 + r1) * P.ldo + c) = make_float2(o[n][2] * i1, o[n][3] * i1);
+      const float a0 = o[n][0] * i0, a1 = o[n][1] * i0, b0 = o[n][2] * i1, b1 = o[n][3] * i1;
+      if (pb.out != nullptr) {
+        if (r0 < V) *reinterpret_cast<float2*>(pb.out + (row0 + r0) * P.ldo + c) = make_float2(a0, a1);
+        if (r1 < V) *reinterpret_cast<float2*>(pb.out + (row0 + r1) * P.ldo + c) = make_float2(b0, b1);
+      }
+      if (pb.out_img != nullptr) {
+        // the output only feeds the `fc` GEMM: written as that GEMM's split-bf16 operand image [hi | hi | lo]
+        const size_t part = (size_t)P.img_kb * 16384;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int64_t row = pb.img_row0 + row0 + (rr ? r1 : r0);
+          if ((rr ? r1 : r0) < V) {
+            uint32_t hi, lo;
+            mt_split(rr ? b0 : a0, rr ? b1 : a1, hi, lo);
+            uint8_t* blk = pb.out_img + ((size_t)(row >> 7) * 3 * P.img_kb + (c >> 6)) * 16384 +
+                           umma::sw128_off((uint32_t)(row & 127), (uint32_t)(c & 63));
+            *reinterpret_cast<uint32_t*>(blk) = hi;
+            *reinterpret_cast<uint32_t*>(blk + part) = hi;
+            *reinterpret_cast<uint32_t*>(blk + 2 * part) = lo;
+          }
+        }
+      }
     }
   }
 }
@@ -208,12 +239,13 @@ static void mha_tc_launch(const MhaParams& P, int n_problems, cudaStream_t s) {
 // Up to two attention problems of identical shape in ONE launch (the two self-attentions, or the two cross
 // directions R2L / L2R of inter_attn.py:84-108): problem i reads q[i], k[i], v[i] and writes out[i].
 extern "C" int pdf_mha_tc(const float* const* q, const float* const* k, const float* const* v, float* const* out,
-                          int n_problems, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t n_samples,
-                          int V, int heads, int d, void* stream) {
+                          void* const* out_img, const int64_t* img_row0, int n_problems, int64_t ldq, int64_t ldk,
+                          int64_t ldv, int64_t ldo, int64_t n_samples, int V, int heads, int d, void* stream) {
   using namespace pdf;
   if (n_samples == 0 || n_problems == 0) return PDF_OK;
-  PDF_REQUIRE(q && k && v && out && n_problems >= 1 && n_problems <= MT_PROBLEMS, PDF_ERR_BAD_ARG,
+  PDF_REQUIRE(q && k && v && (out || out_img) && n_problems >= 1 && n_problems <= MT_PROBLEMS, PDF_ERR_BAD_ARG,
               "pdf_mha_tc: null pointer / 1..%d problems", MT_PROBLEMS);
+  PDF_REQUIRE(!out_img || (heads * d) % 64 == 0, PDF_ERR_BAD_ARG, "pdf_mha_tc: image output needs heads*d %% 64 == 0");
   PDF_REQUIRE(n_samples > 0 && V > 0 && V <= MT_MAXV && heads > 0 && (d == 16 || d == 32 || d == 64) &&
                   n_samples * heads < (1ll << 31),
               PDF_ERR_UNSUPPORTED, "pdf_mha_tc: supports <= 256 tokens and head dim 16 / 32 / 64");
@@ -221,14 +253,17 @@ extern "C" int pdf_mha_tc(const float* const* q, const float* const* k, const fl
   MhaParams P;
   memset(&P, 0, sizeof(P));
   for (int i = 0; i < n_problems; ++i) {
-    PDF_REQUIRE(q[i] && k[i] && v[i] && out[i], PDF_ERR_BAD_ARG, "pdf_mha_tc: null problem pointer");
-    PDF_REQUIRE(((reinterpret_cast<uintptr_t>(q[i]) | reinterpret_cast<uintptr_t>(k[i]) | reinterpret_cast<uintptr_t>(out[i])) & 7) == 0,
+    float* o = out ? out[i] : nullptr;
+    uint8_t* oi = out_img ? (uint8_t*)out_img[i] : nullptr;
+    PDF_REQUIRE(q[i] && k[i] && v[i] && (o || oi), PDF_ERR_BAD_ARG, "pdf_mha_tc: null problem pointer");
+    PDF_REQUIRE(((reinterpret_cast<uintptr_t>(q[i]) | reinterpret_cast<uintptr_t>(k[i]) | reinterpret_cast<uintptr_t>(o)) & 7) == 0,
                 PDF_ERR_BAD_ARG, "pdf_mha_tc: q / k / out must be 8-byte aligned");
-    P.p[i] = MhaProblem{q[i], k[i], v[i], out[i]};
+    P.p[i] = MhaProblem{q[i], k[i], v[i], o, oi, img_row0 ? img_row0[i] : 0};
   }
   P.ldq = ldq; P.ldk = ldk; P.ldv = ldv; P.ldo = ldo;
   P.V = V; P.heads = heads; P.n_samples = (int)n_samples;
   P.inv_norm = 1.f / sqrtf((float)d);
+  P.img_kb = heads * d / 64;
   cudaStream_t s = (cudaStream_t)stream;
   if (d == 16) mha_tc_launch<16>(P, n_problems, s);
   else if (d == 32) mha_tc_launch<32>(P, n_problems, s);

@@ -86,18 +86,34 @@ pyramid_gather_bf16_kernel(const float* __restrict__ xyz, const int64_t* __restr
     if (threadIdx.x < 48) P[threadIdx.x] = sft0[threadIdx.x];
     __syncthreads();
     const uint16_t* base = l0 + f * 3 * (int64_t)R * R;
-    for (int i = threadIdx.x; i < n_points; i += blockDim.x) {
-      int64_t pix = ch[i];
-      pix = pix < 0 ? 0 : (pix >= (int64_t)R * R ? (int64_t)R * R - 1 : pix);
-      float e[3], p[3];
+    constexpr int U0 = 4;                                     // points per thread with every load issued up front
+    for (int i0 = threadIdx.x; i0 < n_points; i0 += blockDim.x * U0) {
+      int64_t pix[U0];
+      float e[U0][3], p[U0][3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        e[c] = bf16_to_f32(__ldg(base + pix * 3 + c));
-        p[c] = xyz[(b * n_points + i) * 3 + c];
+      for (int u = 0; u < U0; ++u) {
+        const int i = i0 + u * blockDim.x;
+        pix[u] = i < n_points ? ch[i] : 0;
+        pix[u] = pix[u] < 0 ? 0 : (pix[u] >= (int64_t)R * R ? (int64_t)R * R - 1 : pix[u]);
       }
-      sft0_apply_b(P, e, p);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) pts0[(b * n_points + i) * 3 + c] = p[c];
+      for (int u = 0; u < U0; ++u) {
+        const int i = min(i0 + u * (int)blockDim.x, n_points - 1);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          e[u][c] = bf16_to_f32(__ldg(base + pix[u] * 3 + c));
+          p[u][c] = xyz[(b * n_points + i) * 3 + c];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U0; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < n_points) {
+          sft0_apply_b(P, e[u], p[u]);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) pts0[(b * n_points + i) * 3 + c] = p[u][c];
+        }
+      }
     }
   } else if (y <= PGB_PARTS) {
     const int part = y - 1, per = (n1 + PGB_PARTS - 1) / PGB_PARTS;

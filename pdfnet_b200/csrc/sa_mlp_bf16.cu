@@ -25,8 +25,13 @@
 namespace pdf {
 using namespace umma;
 
-template <int CF_, int C1_, int C2_, int C3_, int SLOTS_, bool COMPACT_ = false>
+template <int CF_, int C1_, int C2_, int C3_, int SLOTS_, bool COMPACT_ = false, bool TS_ = true>
 struct SaCfg {
+  // TS: layer 2 reads its A operand (the layer-1 activations) from TENSOR MEMORY: the layer-1 epilogue packs
+  // ReLU(D1) to bf16 in place over D1's own columns (tcgen05.st) together with the constant bias block, so the
+  // activations never cross the shared-memory port (whose 128 B/clk - MMA operand reads plus the repack stores -
+  // is what bounds these kernels), and the generic->async proxy fence of that stage goes.
+  static constexpr bool TS = TS_;
   static constexpr int CF = CF_;        // feature channels gathered with each neighbour (0 or 128)
   static constexpr int C1 = C1_, C2 = C2_, C3 = C3_, SLOTS = SLOTS_;
   // COMPACT: every accumulator of a tile (D1, D2, and layer 3 one 64-point group at a time) reuses
@@ -54,8 +59,11 @@ struct SaCfg {
 
 // (the COMPACT 8-slot plan measured slower on B200: level 1 is bound by shared-memory operand
 // bandwidth, not by the number of tiles in flight — see DESIGN.md section 3.1)
-using Sa1Cfg = SaCfg<0, 64, 64, 128, 4, false>;
-using Sa2Cfg = SaCfg<128, 128, 128, 256, 2>;
+#ifndef PDF_SA_TS
+#define PDF_SA_TS 1
+#endif
+using Sa1Cfg = SaCfg<0, 64, 64, 128, 4, false, PDF_SA_TS != 0>;
+using Sa2Cfg = SaCfg<128, 128, 128, 256, 2, false, PDF_SA_TS != 0>;
 
 // One layer = (KB SW128 K-blocks x 4 K-steps) + 1 aux K-step, accumulating into d_tmem.
 template <int KB>
@@ -72,6 +80,50 @@ __device__ __forceinline__ void issue_layer(uint32_t a_feat, uint32_t a_blk, uin
     }
   }
   mma_bf16(d_tmem, desc_none(a_aux), desc_none(b_aux), idesc, acc);
+}
+
+// Layer with the A operand in tensor memory: KB*4 K-steps over the packed activations (8 columns per step)
+// + 1 K-step over the constant bias block that follows them.
+template <int KB>
+__device__ __forceinline__ void issue_layer_ts(uint32_t a_tmem, uint32_t b_feat, uint32_t b_blk, uint32_t b_aux,
+                                               uint32_t d_tmem, uint32_t idesc) {
+  bool acc = false;
+#pragma unroll
+  for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+    for (int k16 = 0; k16 < 4; ++k16) {
+      mma_bf16_ts(d_tmem, a_tmem + (kb * 4 + k16) * 8, desc_sw128(b_feat + kb * b_blk + k16 * 32), idesc, acc);
+      acc = true;
+    }
+  }
+  mma_bf16_ts(d_tmem, a_tmem + KB * 32, desc_none(b_aux), idesc, acc);
+}
+
+// Epilogue of layer 1 in TS mode: TMEM row (fp32, C columns) -> ReLU -> bf16 pairs written back IN PLACE over
+// the first C/2 columns, followed by the 8-column bias block [0 0 0 1 | 0 0 0 1 | 0 x 8] (K = 16 step).
+template <int C>
+__device__ __forceinline__ void epilogue_repack_tmem(uint32_t tmem_row) {
+  uint32_t w[C / 2];
+#pragma unroll
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_row + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      w[c0 / 2 + q] = pack_relu_bf16(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+  }
+#pragma unroll
+  for (int c0 = 0; c0 < C / 2; c0 += 16) {
+    uint32_t t[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) t[q] = w[c0 + q];
+    tmem_st16(tmem_row + c0, t);
+  }
+  const uint32_t one_hi = 0x3F800000u;                    // bf16 (0, 1): element k = 3 / k = 7 of the block
+  const uint32_t aux[8] = {0u, one_hi, 0u, one_hi, 0u, 0u, 0u, 0u};
+  tmem_st8(tmem_row + C / 2, aux);
+  tmem_st_wait();
 }
 
 // Epilogue of layers 1/2: TMEM row (this thread's point) -> ReLU -> bf16 -> SW128 tile row.
@@ -140,6 +192,16 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
   const uint32_t d1 = d_base, d2 = Cfg::COMPACT ? d_base : d_base + Cfg::C1, d3 = d_base;
   uint32_t phase = 0;
   const int tiles_per_cloud = n_centroids >> 1;
+  // tile -> (cloud, first centroid): a shift when the tile count per cloud is a power of two (it is for the
+  // reference's 512 / 128 centroids) instead of ~20-instruction integer divisions on the per-tile path
+  const bool pow2 = (tiles_per_cloud & (tiles_per_cloud - 1)) == 0;
+  const int tshift = 31 - __clz(tiles_per_cloud);
+  auto tile_cloud = [&](int64_t t) -> int64_t {
+    return pow2 ? (int64_t)((uint32_t)t >> tshift) : (int64_t)((uint32_t)t / (uint32_t)tiles_per_cloud);
+  };
+  auto tile_g0 = [&](int64_t t) -> int {
+    return (pow2 ? (int)((uint32_t)t & (uint32_t)(tiles_per_cloud - 1)) : (int)((uint32_t)t % (uint32_t)tiles_per_cloud)) * 2;
+  };
 
   mbar_wait(smem_u32(&s_bar[0]), 0);                     // weights resident
 
@@ -147,13 +209,13 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
   // with other work if its first USE is an iteration away): the neighbour index of tile t+2 and the
   // raw coordinates of tile t+1 are in flight while tile t runs its three MMA phases.
   auto load_idx = [&](int64_t t) -> int {
-    const int64_t b = (uint32_t)t / (uint32_t)tiles_per_cloud;        // n_tiles < 2^31 (checked by the launcher)
-    const int g0 = (int)((uint32_t)t % (uint32_t)tiles_per_cloud) * 2;
+    const int64_t b = tile_cloud(t);                                  // n_tiles < 2^31 (checked by the launcher)
+    const int g0 = tile_g0(t);
     return __ldg(idx + (b * n_centroids + g0) * 64 + p);
   };
   auto load_raw = [&](int64_t t, int j, float (&sp)[3], float (&cp)[3]) {
-    const int64_t b = (uint32_t)t / (uint32_t)tiles_per_cloud;
-    const int g0 = (int)((uint32_t)t % (uint32_t)tiles_per_cloud) * 2;
+    const int64_t b = tile_cloud(t);
+    const int g0 = tile_g0(t);
     const float* cloud = pts + b * n_src * ld_pts;
     const float* src = cloud + (int64_t)j * ld_pts;
     const float* cen = cloud + (int64_t)(g0 + (p >> 6)) * ld_pts;
@@ -167,15 +229,20 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
   if (t_first + t_step < n_tiles) j_next = load_idx(t_first + t_step);
 
   for (int64_t t = t_first; t < n_tiles; t += t_step) {
-    const int64_t b = (uint32_t)t / (uint32_t)tiles_per_cloud;
-    const int g0 = (int)((uint32_t)t % (uint32_t)tiles_per_cloud) * 2;
+    const int64_t b = tile_cloud(t);
+    const int g0 = tile_g0(t);
     const float* cloud = pts + b * n_src * ld_pts;
     const int32_t* tidx = idx + (b * n_centroids + g0) * 64;
     // p_j - c_i in fp32, the reference's operand order (utils.py:142-143)
     const float rx = __fsub_rn(sp[0], cp[0]), ry = __fsub_rn(sp[1], cp[1]), rz = __fsub_rn(sp[2], cp[2]);
     if ((p & 63) == 0 && out_col0 > 0) {                   // centroid xyz (+ zero pad) into the leading columns,
       float* o = out + (b * n_centroids + g0 + (p >> 6)) * ld_out;   // straight from the prefetched registers
-      for (int c = 0; c < out_col0; ++c) o[c] = c < 3 ? cp[c] : 0.f;
+      // constant indices only: a runtime index would put cp[] in local memory and make every prefetch of the
+      // centroid coordinates wait for its loads at the spill store
+      if (out_col0 > 0) o[0] = cp[0];
+      if (out_col0 > 1) o[1] = cp[1];
+      if (out_col0 > 2) o[2] = cp[2];
+      if (out_col0 > 3) o[3] = 0.f;
     }
 
     // ---- gather: geometry/bias block (thread = row, prefetched one tile ahead) ----
@@ -235,16 +302,23 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
     }
     mbar_wait(bar, phase); phase ^= 1;
     fence_after_sync();
-    epilogue_repack<Cfg::C1>(d1 + lane_off, sa_feat, p);
-    fence_async_smem();
+    if (Cfg::TS) {
+      epilogue_repack_tmem<Cfg::C1>(d1 + lane_off);      // H1 stays in tensor memory (in place over D1)
+    } else {
+      epilogue_repack<Cfg::C1>(d1 + lane_off, sa_feat, p);
+      fence_async_smem();
+    }
     fence_before_sync();
     named_bar_sync(1 + slot, 128);
 
     // ---- layer 2: D2[p, c2] = H1[p, :] . W2[c2, :] ----
     if (p == 0) {
       fence_after_sync();
-      issue_layer<Cfg::KB2>(sa_feat, 128 * 128, sa_aux, sw + Cfg::OFF_W2, Cfg::C2 * 128, sw + Cfg::OFF_W2A, d2,
-                            idesc_bf16(128, Cfg::C2));
+      if (Cfg::TS)
+        issue_layer_ts<Cfg::KB2>(d1, sw + Cfg::OFF_W2, Cfg::C2 * 128, sw + Cfg::OFF_W2A, d2, idesc_bf16(128, Cfg::C2));
+      else
+        issue_layer<Cfg::KB2>(sa_feat, 128 * 128, sa_aux, sw + Cfg::OFF_W2, Cfg::C2 * 128, sw + Cfg::OFF_W2A, d2,
+                              idesc_bf16(128, Cfg::C2));
       commit(bar);
     }
     mbar_wait(bar, phase); phase ^= 1;

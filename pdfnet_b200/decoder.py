@@ -248,14 +248,18 @@ class decoder(nn.Module):
         """Rows enough for the tensor-core GEMM path (whose operand images the producers write directly)."""
         return self.precision != "fp32" and M >= 1024
 
-    def _linear(self, x, w, b=None, act=L.ACT_NONE, x_img=None, M=None):
+    def _linear(self, x, w, b=None, act=L.ACT_NONE, x_img=None, M=None, out_image=False, tc_min_rows=None):
+        """out_image (tensor-core path only): the result feeds nothing but the next GEMM, so it is written only as
+        that GEMM's split operand image (returned instead of rows)."""
         M = x.shape[0] if x is not None else M
-        if self._tc(M) and min(w.shape) >= 16:
+        tc = self._tc(M) if tc_min_rows is None else (self.precision != "fp32" and M >= tc_min_rows)
+        if tc and min(w.shape) >= 16:
             key = ("tc", w.data_ptr(), b.data_ptr() if b is not None else 0)     # weight image packed once
             packed = self._cache.get(key)
             if packed is None:
                 packed = self._cache[key] = ops.pack_linear_tc(w, b, split=True) + (w, b)   # keep w / b alive
-            return ops.linear_tc(x, None, None, act=act, packed=packed[:5], x_img=x_img, M=M)
+            return ops.linear_tc(x, None, None, act=act, packed=packed[:5], x_img=x_img, M=M, out_image=out_image)
+        assert not out_image
         return ops.linear(x, w, b, act=act)
 
     def _graph_layer(self, x, x_img, li, side, V, M):
@@ -285,14 +289,25 @@ class decoder(nn.Module):
     def _ln(m):
         return (m.weight.detach(), m.bias.detach())
 
-    def _attention(self, problems, n, V):
-        """softmax(q k^T / sqrt(d)) v for 1-2 problems: tensor cores with split-bf16 operands on the tensor-core
-        precisions, the fp32 FFMA kernel on precision='fp32'."""
-        if self.precision != "fp32":
-            return ops.mha_tc(problems, n, V, self.heads)
-        return [ops.mha(q, k, v, n, V, self.heads, out=o) for q, k, v, o in problems]
+    def _attention_fc(self, problems, n, V, fc):
+        """fc(softmax(q k^T / sqrt(d)) v) for 1-2 problems (stacked along the rows).  Tensor-core precisions: the
+        attention runs on mma.sync with split-bf16 operands and writes its result straight as the fc GEMM's operand
+        image; precision='fp32' (and tiny batches): FFMA attention kernel + FFMA linear."""
+        M, f = problems[0][0].shape
+        w, b = fc.weight.detach(), fc.bias.detach()
+        if self._tc(n * V) and f % 64 == 0:
+            _, img = ops.mha_tc([(q, k, v, None) for q, k, v in problems], n, V, self.heads, rows=False, image=True)
+            return self._linear(None, w, b, x_img=img, M=len(problems) * M)
+        att = torch.empty((len(problems) * M, f), dtype=torch.float32, device=problems[0][0].device)
+        for i, (q, k, v) in enumerate(problems):
+            ops.mha(q, k, v, n, V, self.heads, out=att[i * M:(i + 1) * M])
+        return self._linear(att, w, b)
 
     def _mlp(self, h, ff, h_img=None, M=None):
+        M = h.shape[0] if h is not None else M
+        if self._tc(M) and ff.fc1.out_features % 64 == 0:      # hidden activations only exist as fc2's operand image
+            f1 = self._linear(h, ff.fc1.weight.detach(), ff.fc1.bias.detach(), L.ACT_RELU, x_img=h_img, M=M, out_image=True)
+            return self._linear(None, ff.fc2.weight.detach(), ff.fc2.bias.detach(), x_img=f1, M=M)
         f1 = self._linear(h, ff.fc1.weight.detach(), ff.fc1.bias.detach(), L.ACT_RELU, x_img=h_img, M=M)
         return self._linear(f1, ff.fc2.weight.detach(), ff.fc2.bias.detach())
 
@@ -311,8 +326,7 @@ class decoder(nn.Module):
         f, M = x.shape[1], x.shape[0]
         _, h, h_img = self._ln_for_gemm(x, None, self._ln(sa.layer_norm), False)
         qkv = self._linear(h, c[(li, name, "qkv_w")], c[(li, name, "qkv_b")], x_img=h_img, M=M)
-        a = self._attention([(qkv[:, :f], qkv[:, f:2 * f], qkv[:, 2 * f:], None)], n, V)[0]
-        g = self._linear(a, sa.fc.weight.detach(), sa.fc.bias.detach())
+        g = self._attention_fc([(qkv[:, :f], qkv[:, f:2 * f], qkv[:, 2 * f:])], n, V, sa.fc)
         x2, h2, h2_img = self._ln_for_gemm(x, g, self._ln(sa.ff.layer_norm), True)
         return x2, self._mlp(h2, sa.ff, h2_img, M)
 
@@ -334,10 +348,8 @@ class decoder(nn.Module):
             Rf, _ = ops.row_combine(r2, rf, ln=self._ln(a.layer_norm2), want_sum=True, ln_out=both[M:])
             qkv = self._linear(both, c[(li, "X", "qkv_w")], c[(li, "X", "qkv_b")])        # shared projections
         q, k, v = qkv[:, :f], qkv[:, f:2 * f], qkv[:, 2 * f:]
-        att = torch.empty((2 * M, f), dtype=torch.float32, device=l2.device)
-        # R2L (left queries, right keys / values) and L2R in one launch
-        self._attention([(q[:M], k[M:], v[M:], att[:M]), (q[M:], k[:M], v[:M], att[M:])], n, V)
-        feat = self._linear(att, a.fc.weight.detach(), a.fc.bias.detach())
+        # R2L (left queries, right keys / values) and L2R in one launch, then the shared fc on the stacked result
+        feat = self._attention_fc([(q[:M], k[M:], v[M:]), (q[M:], k[:M], v[:M])], n, V, a.fc)
         x4l, h4l, h4l_img = self._ln_for_gemm(Lf, feat[:M], self._ln(a.ffL.layer_norm), True)
         x4r, h4r, h4r_img = self._ln_for_gemm(Rf, feat[M:], self._ln(a.ffR.layer_norm), True)
         return (x4l, self._mlp(h4l, a.ffL, h4l_img, M)), (x4r, self._mlp(h4r, a.ffR, h4r_img, M))
@@ -366,7 +378,7 @@ class decoder(nn.Module):
             x = {}
             for side, gfeat in (("left", global_feature_left), ("right", global_feature_right)):
                 gf = getattr(self, "gf_layer_" + side)
-                g = self._linear(L.f32c(gfeat), gf[0].weight.detach(), gf[0].bias.detach())
+                g = self._linear(L.f32c(gfeat), gf[0].weight.detach(), gf[0].bias.detach(), tc_min_rows=128)
                 gpad = torch.zeros((B, cin0), dtype=torch.float32, device=g.device)
                 ops.row_combine(g, ln=self._ln(gf[1]), ln_out=gpad[:, :cin0 - 3])
                 # Lf = cat([g repeated over the 63 vertices, pe], -1) + position embedding (:197-198, DualGraph.py:76-80)

@@ -636,7 +636,7 @@ def pack_linear_tc(w, bias=None, split=True):
     return (w_img, b, N, K, split)
 
 
-def linear_tc(x, w, bias=None, act=L.ACT_NONE, split=True, packed=None, x_img=None, M=None):
+def linear_tc(x, w, bias=None, act=L.ACT_NONE, split=True, packed=None, x_img=None, M=None, out_image=False):
     """act(x @ w.T + bias) on the tcgen05 GEMM.  split=True: split-bf16 operands (three bf16 products
     per fp32 product: fp32-accurate, ~2^-16 relative); split=False: plain bf16 operands, fp32
     accumulate.  x [M,K] fp32 rows (or ``x_img`` = its tile image and ``M``), w [N,K] fp32 (device) or
@@ -652,6 +652,13 @@ def linear_tc(x, w, bias=None, act=L.ACT_NONE, split=True, packed=None, x_img=No
         M = _rows(x).shape[0]
         assert x.shape[1] == K
         x_img = rows_to_image(x, 0, K, split=1 if split else 0)
+    if out_image:
+        # the result only feeds another GEMM: written ONLY as that GEMM's split operand image (N % 64 == 0)
+        assert split and N % 64 == 0
+        img = split_image_empty(M, N, x_img.device)
+        gemm_bf16(x_img, (M + 127) // 128, kb, w_img, nt, kb, kb, b, act=act | L.GEMM_OUT_SPLIT, out_img=img,
+                  out_kb=3 * (N // 64), rows_valid=M, tile_desc=[(128 * i, min(128, N - 128 * i), 2 * i) for i in range(nt)])
+        return img
     out = torch.empty((M, _pad4(N)), dtype=torch.float32, device=x_img.device)
     gemm_bf16(x_img, (M + 127) // 128, kb, w_img, nt, kb, kb, b, act=act, out_f32=out, rows_valid=M,
               tile_desc=_tile_desc(N))
@@ -767,10 +774,13 @@ def mha(q, k, v, n_samples, V, heads, out=None):
     return out
 
 
-def mha_tc(problems, n_samples, V, heads):
+def mha_tc(problems, n_samples, V, heads, rows=True, image=None, image_rows=None):
     """Tensor-core attention (pdf_mha_tc) for one or two problems of identical shape in ONE launch.
     problems: [(q, k, v, out-or-None), ...] with q/k/v [n_samples*V, heads*d] column slices of fp32 rows that
-    share their row pitches.  Returns the list of outputs."""
+    share their row pitches.  rows=True: fp32 row outputs (returned as a list).  image: True (allocate) or a
+    uint8 tensor: the results are ALSO / ONLY written as the split-bf16 tile image of the stacked
+    [len(problems) * n_samples * V, heads*d] matrix (problem i fills rows [i*M, (i+1)*M)) - the operand of the
+    ``fc`` GEMM that follows.  Returns outs, or (outs, image) when an image is requested."""
     outs, ptrs = [], ([], [], [], [])
     q0, k0, v0, _ = problems[0]
     M, f = _rows(q0).shape
@@ -779,17 +789,29 @@ def mha_tc(problems, n_samples, V, heads):
         L.require_cuda(q, k, v, out)
         assert _rows(q).shape == (M, f) and _rows(k).shape == (M, f) and _rows(v).shape == (M, f)
         assert q.stride(0) == q0.stride(0) and k.stride(0) == k0.stride(0) and v.stride(0) == v0.stride(0)
-        if out is None:
+        if out is None and rows:
             out = torch.empty((M, f), dtype=torch.float32, device=q.device)
-        assert out.stride(0) == (outs[0].stride(0) if outs else out.stride(0)) and out.stride(1) == 1
-        outs.append(out)
+        if out is not None:
+            assert out.stride(0) == (outs[0].stride(0) if outs else out.stride(0)) and out.stride(1) == 1
+            outs.append(out)
         for lst, t in zip(ptrs, (q, k, v, out)):
-            L.ptr(t)                                        # registers the device for the launch guard
-            lst.append(t.data_ptr())
-    arr = [(ctypes.c_void_p * len(problems))(*lst) for lst in ptrs]
-    L.call("pdf_mha_tc", *[ctypes.cast(a, ctypes.c_void_p) for a in arr], len(problems), q0.stride(0), k0.stride(0),
-           v0.stride(0), outs[0].stride(0), n_samples, V, heads, f // heads, L.stream())
-    return outs
+            if t is not None:
+                L.ptr(t)                                    # registers the device for the launch guard
+            lst.append(t.data_ptr() if t is not None else None)
+    n = len(problems)
+    arr = [(ctypes.c_void_p * n)(*lst) for lst in ptrs]
+    img_arr = row0 = None
+    if image is not None and image is not False:
+        if image is True:
+            image = split_image_empty(n * M, f, q0.device)
+        L.ptr(image)
+        img_arr = ctypes.cast((ctypes.c_void_p * n)(*([image.data_ptr()] * n)), ctypes.c_void_p)
+        row0 = ctypes.cast((ctypes.c_int64 * n)(*[i * M for i in range(n)]), ctypes.c_void_p)
+    L.call("pdf_mha_tc", ctypes.cast(arr[0], ctypes.c_void_p), ctypes.cast(arr[1], ctypes.c_void_p),
+           ctypes.cast(arr[2], ctypes.c_void_p), ctypes.cast(arr[3], ctypes.c_void_p) if outs else None, img_arr, row0, n,
+           q0.stride(0), k0.stride(0), v0.stride(0), outs[0].stride(0) if outs else 0, n_samples, V, heads, f // heads,
+           L.stream())
+    return (outs, image) if img_arr is not None else outs
 
 
 def decoder_project(v_coarse, v_dense, params, img_size, rev, rep):

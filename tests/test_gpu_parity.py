@@ -1390,6 +1390,24 @@ def test_decoder_primitives_vs_torch():
         np.testing.assert_allclose(o2.cpu().numpy(), ref2.numpy(), rtol=1e-4, atol=1e-5, err_msg="tc2 " + str((V, heads, d)))
     with pytest.raises(RuntimeError):
         ops.mha(rnd(300, 32).to(DEV), rnd(300, 32).to(DEV), rnd(300, 32).to(DEV), 1, 300, 2)     # > 256 tokens
+    # operand-image hand-offs: attention / GEMM results written directly as the next GEMM's split image are
+    # bit-identical to rows + pdf_rows_to_image (whole 128-row tiles: padded image rows are unspecified)
+    V, heads, d, n2 = 64, 4, 16, 4
+    f = heads * d
+    qkv = rnd(n2 * V, 3 * f).to(DEV)
+    qkv_b = rnd(n2 * V, 3 * f).to(DEV)
+    probs = [(qkv[:, :f], qkv_b[:, f:2 * f], qkv_b[:, 2 * f:], None), (qkv_b[:, :f], qkv[:, f:2 * f], qkv[:, 2 * f:], None)]
+    outs, img = ops.mha_tc(probs, n2, V, heads, image=True)
+    assert torch.equal(img, ops.rows_to_image(torch.cat(outs, 0), 0, f, split=1))
+    _, img_only = ops.mha_tc(probs, n2, V, heads, rows=False, image=True)
+    assert torch.equal(img_only, img)
+    x, w, b = rnd(256, 128).to(DEV), rnd(64, 128).to(DEV), rnd(64).to(DEV)
+    y = ops.linear_tc(x, w, b, act=1)
+    y_img = ops.linear_tc(x, w, b, act=1, out_image=True)
+    assert torch.equal(y_img, ops.rows_to_image(y.contiguous(), 0, 64, split=1))
+    w2, b2 = rnd(192, 128).to(DEV), rnd(192).to(DEV)
+    assert torch.equal(ops.linear_tc(x, w2, b2, out_image=True),
+                       ops.rows_to_image(ops.linear_tc(x, w2, b2).contiguous(), 0, 192, split=1))
     # projection + MANO-order lists
     B, Vc, Vd, rep = 3, 12, 20, 4
     vc, vd, params = rnd(B, Vc, 3), rnd(B, Vd, 3), rnd(B, 3)
