@@ -448,6 +448,15 @@ int pdf_mha_tc(const float* const* q, const float* const* k, const float* const*
 int pdf_decoder_project(const float* v_coarse, int Vc, const float* v_dense, int Vd, const float* params, int64_t ldp,
                         float img_size, const int64_t* rev, int rep, int64_t B, float* coarse2d, float* dense2d,
                         float* mano3d, float* mano2d, void* stream);
+/* Output heads of decoder.forward (intaghand_decoder.py:213-224) for n hand-samples (both hands stacked: the
+ * heads are shared modules): f [n*V, C] fp32 rows (pitch ldf) -> params [n,3] = params_head(avg_head(f^T)),
+ * root [n,3] = root_head(avg_head(f^T)), verts [n,V,3] = coord_head(f).  avg_w [V], avg_b [1]; the three
+ * 3-output heads as [3,C] weights + [3] biases. */
+int pdf_decoder_heads(const float* f, int64_t ldf, int64_t n, int V, int C, const float* avg_w, const float* avg_b,
+                      const float* params_w, const float* params_b, const float* root_w, const float* root_b,
+                      const float* coord_w, const float* coord_b, float* params, float* root, float* verts,
+                      void* stream);
+
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,7 @@ SIGNATURES = {
     "pdf_graph_cheby_ln": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _f32, _i32,
                            _vp, _i64, _vp, _vp],
     "pdf_mha": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp],
+    "pdf_decoder_heads": [_vp, _i64, _i64, _i32, _i32] + [_vp] * 12,
     "pdf_mha_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _vp],
     "pdf_decoder_project": [_vp, _i32, _vp, _i32, _vp, _i64, _f32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
     "pdf_mano_lbs_pair": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],

@@ -304,6 +304,56 @@ __global__ void decoder_project_kernel(const float* __restrict__ vc, int Vc, con
   }
 }
 
+// Output heads of decoder.forward (intaghand_decoder.py:213-224) for one hand-sample per CTA: the [V, C] feature
+// tile is staged once in shared memory (odd pitch) and feeds
+//   temp[c]   = avg_head(f^T)        = sum_v aw[v] f[v,c] + ab          (Linear over the VERTEX axis)
+//   params[o] = params_head(temp), root[o] = root_head(temp)            (o < 3)
+//   v[v,o]    = coord_head(f[v,:])                                       (the coarse mesh, [V,3])
+// instead of two transposed copies and four skinny FFMA GEMM launches per hand.
+__global__ void __launch_bounds__(256)
+decoder_heads_kernel(const float* __restrict__ f, int64_t ldf, int V, int C, const float* __restrict__ aw,
+                     const float* __restrict__ ab, const float* __restrict__ Wp, const float* __restrict__ bp,
+                     const float* __restrict__ Wr, const float* __restrict__ br, const float* __restrict__ Wc,
+                     const float* __restrict__ bc, float* __restrict__ params, float* __restrict__ root,
+                     float* __restrict__ verts) {
+  extern __shared__ __align__(16) float hs[];
+  const int pitch = C + 1;
+  float* sf = hs;                            // [V][C+1]
+  float* st = sf + (size_t)V * pitch;        // temp [C]
+  float* sw = st + C;                        // Wc [3][C], Wp [3][C], Wr [3][C]
+  const int64_t n = blockIdx.x;
+  const float* src = f + n * V * ldf;
+  for (int e = threadIdx.x; e < V * C; e += blockDim.x) {
+    const int v = e / C, c = e - v * C;
+    sf[v * pitch + c] = src[(int64_t)v * ldf + c];
+  }
+  for (int e = threadIdx.x; e < 3 * C; e += blockDim.x) { sw[e] = Wc[e]; sw[3 * C + e] = Wp[e]; sw[6 * C + e] = Wr[e]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int v = 0; v < V; ++v) a = fmaf(__ldg(aw + v), sf[v * pitch + c], a);
+    st[c] = a + ab[0];
+  }
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float x = sf[v * pitch + c];
+      a0 = fmaf(sw[c], x, a0); a1 = fmaf(sw[C + c], x, a1); a2 = fmaf(sw[2 * C + c], x, a2);
+    }
+    float* o = verts + (n * V + v) * 3;
+    o[0] = a0 + bc[0]; o[1] = a1 + bc[1]; o[2] = a2 + bc[2];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const int o = threadIdx.x % 3, which = threadIdx.x / 3;
+    const float* w = sw + (which ? 6 : 3) * C + o * C;
+    float a = 0.f;
+    for (int c = 0; c < C; ++c) a = fmaf(w[c], st[c], a);
+    if (which) root[n * 3 + o] = a + br[o];
+    else params[n * 3 + o] = a + bp[o];
+  }
+}
+
 template <typename F>
 static int dispatch_npl(int C, F&& f) {
   if (C <= 128) return f(std::integral_constant<int, 4>());
@@ -399,4 +449,22 @@ extern "C" int pdf_decoder_project(const float* v_coarse, int Vc, const float* v
                                                                             img_size, rev, rep, B, coarse2d, dense2d,
                                                                             mano3d, mano2d);
   return check_launch("pdf_decoder_project");
+}
+
+extern "C" int pdf_decoder_heads(const float* f, int64_t ldf, int64_t n, int V, int C, const float* avg_w,
+                                 const float* avg_b, const float* params_w, const float* params_b,
+                                 const float* root_w, const float* root_b, const float* coord_w,
+                                 const float* coord_b, float* params, float* root, float* verts, void* stream) {
+  if (n == 0) return PDF_OK;
+  PDF_REQUIRE(f && avg_w && avg_b && params_w && params_b && root_w && root_b && coord_w && coord_b && params && root &&
+                  verts, PDF_ERR_BAD_ARG, "pdf_decoder_heads: null pointer");
+  const size_t smem = sizeof(float) * ((size_t)V * (C + 1) + C + 9 * (size_t)C);
+  PDF_REQUIRE(n > 0 && V > 0 && C > 0 && ldf >= C && smem <= 200 * 1024, PDF_ERR_UNSUPPORTED,
+              "pdf_decoder_heads: bad size (the [V, C] tile must fit shared memory)");
+  static pdf::PerDeviceOnce once;
+  if (once.first()) cudaFuncSetAttribute(decoder_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  decoder_heads_kernel<<<(unsigned)n, 256, smem, (cudaStream_t)stream>>>(f, ldf, V, C, avg_w, avg_b, params_w, params_b,
+                                                                        root_w, root_b, coord_w, coord_b, params, root,
+                                                                        verts);
+  return check_launch("pdf_decoder_heads");
 }

@@ -405,21 +405,24 @@ class decoder(nn.Module):
                     x["left"] = self._level_input(al, bl, pos, 2 * V, 2)
                     x["right"] = self._level_input(ar, br, pos, 2 * V, 2)
                 else:
-                    x["left"], _ = ops.row_combine(al, bl, V_out=V, want_sum=True)
-                    x["right"], _ = ops.row_combine(ar, br, V_out=V, want_sum=True)
+                    # both hands' final features stacked: the output heads are shared modules -> one pass for both
+                    fboth = torch.empty((2, B * V, self.gcn_out_dim[-1]), dtype=torch.float32, device=al.device)
+                    ops.row_combine(al, bl, V_out=V, sum_out=fboth[0])
+                    ops.row_combine(ar, br, V_out=V, sum_out=fboth[1])
             V, fo = self.verts[2], self.gcn_out_dim[-1]
             scale, trans2d, root, verts3d, verts2d = {}, {}, {}, {}, {}
             result = {"verts3d": {}, "verts2d": {}}
             other = {"verts3d_MANO_list": {"left": [], "right": []}, "verts2d_MANO_list": {"left": [], "right": []}}
-            for side in ("left", "right"):
-                f = x[side]                                                                  # [B*252, 64]
-                ft = f.view(B, V, fo).transpose(1, 2).contiguous().view(B * fo, V)
-                temp = ops.linear(ft, self.avg_head.weight.detach(), self.avg_head.bias.detach()).view(B, fo)
-                params = ops.linear(temp, self.params_head.weight.detach(), self.params_head.bias.detach())
-                root[side] = ops.linear(temp, self.root_head.weight.detach(), self.root_head.bias.detach())
-                v252 = ops.linear(f, self.coord_head.weight.detach(), self.coord_head.bias.detach()).view(B, V, 3)
-                vt = v252.transpose(1, 2).contiguous().view(B * 3, V)
-                v778 = ops.linear(vt, self.unsample_layer.weight.detach()).view(B, 3, -1).transpose(1, 2).contiguous()
+            hd = lambda m: (m.weight, m.bias)
+            params2, root2, v252_2 = ops.decoder_heads(fboth.view(2 * B * V, fo), 2 * B, V, hd(self.avg_head),
+                                                       hd(self.params_head), hd(self.root_head), hd(self.coord_head))
+            # 252 -> 778 up-sampling of both hands as ONE GEMM over rows (sample, xyz)
+            vt = v252_2.transpose(1, 2).contiguous().view(2 * B * 3, V)
+            v778_2 = self._linear(vt, self.unsample_layer.weight.detach(), tc_min_rows=256)
+            v778_2 = v778_2.reshape(2 * B, 3, -1).transpose(1, 2).contiguous()
+            for si, side in enumerate(("left", "right")):
+                params, v252, v778 = params2[si * B:(si + 1) * B], v252_2[si * B:(si + 1) * B], v778_2[si * B:(si + 1) * B]
+                root[side] = root2[si * B:(si + 1) * B]
                 c2, d2, m3, m2 = ops.decoder_project(v252, v778, params, IMG_SIZE, getattr(self, "_rev_" + side),
                                                      self.vNum_all // V)
                 scale[side], trans2d[side] = params[:, 0], params[:, 1:]

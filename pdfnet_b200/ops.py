@@ -721,7 +721,7 @@ def split_image_empty(rows, C, device):
 
 
 def row_combine(a, b=None, rowvec=None, V_out=None, up=1, ln=None, relu=False, want_sum=False, eps=1e-6,
-                ln_out=None, sum_img=False, ln_img=False, ln_rows=True):
+                ln_out=None, sum_img=False, ln_img=False, ln_rows=True, sum_out=None):
     """t = a[src] (+ b[src]) (+ rowvec[v]); returns (t or None, LayerNorm(t) or None); see pdf_row_combine.
     ``ln`` = (gamma, beta).  Output rows = a.shape[0] * up.  sum_img / ln_img: also (or, with
     want_sum=False / ln_rows=False, only) write the result as a split-bf16 tile image; an image argument
@@ -732,7 +732,8 @@ def row_combine(a, b=None, rowvec=None, V_out=None, up=1, ln=None, relu=False, w
     if V_out is None:
         V_out = up
     dev = a.device
-    s_out = torch.empty((rows, C), dtype=torch.float32, device=dev) if want_sum else None
+    s_out = sum_out if sum_out is not None else (torch.empty((rows, C), dtype=torch.float32, device=dev) if want_sum else None)
+    assert s_out is None or (s_out.shape == (rows, C) and s_out.is_contiguous())
     if ln is not None and ln_out is None and ln_rows:
         ln_out = torch.empty((rows, C), dtype=torch.float32, device=dev)
     s_im = split_image_empty(rows, C, dev) if sum_img is True else (sum_img if sum_img is not False else None)
@@ -812,6 +813,23 @@ def mha_tc(problems, n_samples, V, heads, rows=True, image=None, image_rows=None
            q0.stride(0), k0.stride(0), v0.stride(0), outs[0].stride(0) if outs else 0, n_samples, V, heads, f // heads,
            L.stream())
     return (outs, image) if img_arr is not None else outs
+
+
+def decoder_heads(f, n, V, avg, params_head, root_head, coord_head):
+    """pdf_decoder_heads: f [n*V, C] rows -> (params [n,3], root [n,3], verts [n,V,3]); the heads are (weight, bias)."""
+    L.require_cuda(f)
+    M, C = _rows(f).shape
+    assert M == n * V
+    dev = f.device
+    params = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    root = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    verts = torch.empty((n, V, 3), dtype=torch.float32, device=dev)
+    c = lambda t: L.f32c(t.detach())
+    (aw, ab), (pw, pb), (rw, rb), (cw, cb) = [(c(w).reshape(-1) if i == 0 else c(w), c(b)) for i, (w, b) in
+                                              enumerate((avg, params_head, root_head, coord_head))]
+    L.call("pdf_decoder_heads", L.ptr(f), f.stride(0), n, V, C, L.ptr(aw), L.ptr(ab), L.ptr(pw), L.ptr(pb), L.ptr(rw),
+           L.ptr(rb), L.ptr(cw), L.ptr(cb), L.ptr(params), L.ptr(root), L.ptr(verts), L.stream())
+    return params, root, verts
 
 
 def decoder_project(v_coarse, v_dense, params, img_size, rev, rep):

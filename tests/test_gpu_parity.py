@@ -1408,6 +1408,16 @@ def test_decoder_primitives_vs_torch():
     w2, b2 = rnd(192, 128).to(DEV), rnd(192).to(DEV)
     assert torch.equal(ops.linear_tc(x, w2, b2, out_image=True),
                        ops.rows_to_image(ops.linear_tc(x, w2, b2).contiguous(), 0, 192, split=1))
+    # fused output heads (avg over vertices -> params / root, coord head) against torch
+    nh, Vh, Ch = 5, 37, 24
+    fh = rnd(nh * Vh, Ch)
+    aw, ab = rnd(1, Vh), rnd(1)
+    heads_w = [(rnd(3, Ch), rnd(3)) for _ in range(3)]
+    temp = F.linear(fh.view(nh, Vh, Ch).transpose(1, 2), aw, ab)[..., 0]
+    pr, rt, vv = ops.decoder_heads(fh.to(DEV), nh, Vh, (aw.to(DEV), ab.to(DEV)), *[(w.to(DEV), b.to(DEV)) for w, b in heads_w])
+    np.testing.assert_allclose(pr.cpu().numpy(), F.linear(temp, *heads_w[0]).numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(rt.cpu().numpy(), F.linear(temp, *heads_w[1]).numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(vv.cpu().numpy(), F.linear(fh, *heads_w[2]).view(nh, Vh, 3).numpy(), rtol=1e-4, atol=1e-5)
     # projection + MANO-order lists
     B, Vc, Vd, rep = 3, 12, 20, 4
     vc, vd, params = rnd(B, Vc, 3), rnd(B, Vd, 3), rnd(B, 3)
