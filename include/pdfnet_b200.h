@@ -38,6 +38,7 @@ enum { PDF_ACT_NONE = 0, PDF_ACT_RELU = 1, PDF_ACT_LEAKY01 = 2 };
 /* OR-ed onto the `act` argument of pdf_gemm_bf16: out_img is written as a SPLIT image [hi | hi | lo]
  * (out_kb = 3 x k-blocks of the output matrix), i.e. directly as the fp32-accurate M operand of the next GEMM. */
 enum { PDF_GEMM_OUT_SPLIT = 256 };
+#define PDF_MANO_VT_PITCH 2336
 /* epilogue modes for pdf_linear_f32 */
 enum {
   PDF_EPI_STORE = 0,     /* Y = act(acc + bias)                                   */
@@ -282,7 +283,8 @@ int pdf_depth2pcl_host_randomness(uint32_t seed, int64_t n_clouds, int64_t npx, 
  * Inputs: root [n,3] and pose [n,45] axis-angle, shape [n,10], trans [n,3] or
  * null, scale [n] or null.  tip_idx_host: the 5 finger-tip vertex ids (:305-308).
  * center_idx < 0 disables centring (:313-316).  new_skel as :328-332.
- * v_tpose (optional, may be null): blend-shaped rest vertices [n,778*3] computed beforehand as ONE
+ * v_tpose (optional, may be null): blend-shaped rest vertices, rows of 778*3 floats with row pitch
+ * PDF_MANO_VT_PITCH (= 2336: 16-byte aligned rows, so a GEMM can write them with vector stores), computed beforehand as ONE
  * dense GEMM over all hands (pdf_mano_pose_feature + pdf_linear_f32); when null the kernel
  * evaluates the blend shapes itself.
  * Outputs v [n,778,3], j [n,21,3] (joints in the reference's new_order, :110-115). */

@@ -28,8 +28,8 @@ using namespace umma;
 constexpr int G_STAGES = 4;
 constexpr int G_BLOCK = 16384;                 // one 128 x 64 bf16 block
 constexpr int G_THREADS = 320;                // producer warp + MMA warp + 8 epilogue warps
-constexpr int G_SMEM = G_STAGES * 2 * G_BLOCK + 1024 + 256 + 2 * 16 * 128 * 4 + 400 * 4;   // + staged biases, xyz weights
-constexpr int G_MAX_NT = 16;
+constexpr int G_SMEM = G_STAGES * 2 * G_BLOCK + 1024 + 256 + 2 * 20 * 128 * 4 + 400 * 4;   // + staged biases, xyz weights
+constexpr int G_MAX_NT = 20;                  // N tiles per GEMM in ROW mode (MANO blend shapes: 2334 columns = 19 tiles)
 
 struct GemmParams {
   const uint8_t* m_img; const uint8_t* n_img;

@@ -8,6 +8,7 @@
 namespace pdf {
 
 constexpr int NV = 778, NE = NV * 3;
+constexpr int VT_PITCH = PDF_MANO_VT_PITCH;   // row pitch of the precomputed blend-shape rows (16-byte aligned rows)
 
 __constant__ int c_parent[16] = {-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 0, 10, 11, 0, 13, 14};  // kintree_table[0]
 __constant__ int c_new_order[21] = {0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20};
@@ -90,7 +91,7 @@ mano_lbs_kernel(ManoTables T0, ManoTables T1, int pair, int root_is_mat,
 
   // blend shapes: v_tpose = v_template + shapedirs beta + posedirs (R - I)   (:274-282)
   if (v_tpose_in != nullptr) {              // contraction already done as one [n,145]x[145,2334] GEMM
-    for (int i = tid; i < nh * NE; i += 256) s_v[i / NE][i % NE] = v_tpose_in[h0 * NE + i];
+    for (int i = tid; i < nh * NE; i += 256) s_v[i / NE][i % NE] = v_tpose_in[(h0 + i / NE) * VT_PITCH + i % NE];
   } else
   for (int e = tid; e < NE; e += 256) {
     float a[HPC], p0[HPC], p1[HPC];

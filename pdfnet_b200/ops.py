@@ -358,6 +358,29 @@ def joint_regress(reg, verts):
     return out
 
 
+MANO_VT_PITCH = 2336         # PDF_MANO_VT_PITCH: row pitch of the precomputed blend-shape rows
+MANO_TC_MIN_HANDS = 128      # from here on the blend-shape contraction runs on the tcgen05 GEMM
+
+
+def _blend_shapes(tables, X, out):
+    """v_tpose rows = X [n,145] @ blend_w^T [145,2334] + v_template into ``out`` [n, >=2334] (row pitch free).
+    From MANO_TC_MIN_HANDS hands on: the streaming tcgen05 GEMM with split-bf16 operands ([hi|hi|lo] x [hi|lo|hi],
+    ~2^-16 relative per product: the 1e-5 m vertex bound holds with two orders of margin); the weight image is
+    packed once per table set.  Below: the FFMA kernel."""
+    n = X.shape[0]
+    if n < MANO_TC_MIN_HANDS:
+        linear(X, tables["blend_w"], tables["v_template"], out=out[:, :2334])
+        return
+    packed = tables.get("_blend_tc")
+    if packed is None:
+        packed = tables["_blend_tc"] = pack_linear_tc(tables["blend_w"], tables["v_template"], split=True)
+    w_img, b, N, K, _ = packed
+    kb = 3 * ((K + 63) // 64)
+    x_img = rows_to_image(X, 0, K, split=1)
+    gemm_bf16(x_img, (n + 127) // 128, kb, w_img, (N + 127) // 128, kb, kb, b, out_f32=out, rows_valid=n,
+              tile_desc=_tile_desc(N))
+
+
 def mano_lbs(tables, root, pose, shape, trans, scale, tips, center_idx, new_skel, root_is_matrix=False):
     """tables: dict of device tensors in the kernel layout (see manolayer.ManoTables).
     root_is_matrix: ``root`` is [n,3,3] rotation matrices (use_pca layers, manolayer.py:266-267)."""
@@ -371,10 +394,11 @@ def mano_lbs(tables, root, pose, shape, trans, scale, tips, center_idx, new_skel
     tip_arr = (ctypes.c_int32 * 5)(*[int(t) for t in tips])
     v_tpose = None
     if n >= 16 and "blend_w" in tables:
-        # blend shapes of all hands as one dense fp32 GEMM [n,145] x [145,2334] (+ v_template as bias)
+        # blend shapes of all hands as one dense GEMM [n,145] x [145,2334] (+ v_template as bias)
         X = torch.empty((n, 145), dtype=torch.float32, device=root.device)
         L.call("pdf_mano_pose_feature", L.ptr(pose), L.ptr(shape), n, L.ptr(X), L.stream())
-        v_tpose = linear(X, tables["blend_w"], tables["v_template"])
+        v_tpose = torch.empty((n, MANO_VT_PITCH), dtype=torch.float32, device=root.device)
+        _blend_shapes(tables, X, v_tpose)
     L.call("pdf_mano_lbs_rootmat" if root_is_matrix else "pdf_mano_lbs", L.ptr(tables["v_template"]),
            L.ptr(tables["shapedirs_t"]), L.ptr(tables["posedirs_t"]),
            L.ptr(tables["j_template"]), L.ptr(tables["j_shapedirs"]), L.ptr(tables["weights_t"]), L.ptr(root),
@@ -405,9 +429,9 @@ def mano_lbs_pair(tables_l, tables_r, root, pose, shape, trans, scale, tips_l, t
         # blend shapes: one [n,145] coefficient matrix, then one fp32 GEMM per side on strided rows
         X = torch.empty((n, 145), dtype=torch.float32, device=dev)
         L.call("pdf_mano_pose_feature", L.ptr(pose), L.ptr(shape), n, L.ptr(X), L.stream())
-        v_tpose = torch.empty((n, 2334), dtype=torch.float32, device=dev)
-        linear(X[0::2], tables_l["blend_w"], tables_l["v_template"], out=v_tpose[0::2])
-        linear(X[1::2], tables_r["blend_w"], tables_r["v_template"], out=v_tpose[1::2])
+        v_tpose = torch.empty((n, MANO_VT_PITCH), dtype=torch.float32, device=dev)
+        _blend_shapes(tables_l, X[0::2], v_tpose[0::2])
+        _blend_shapes(tables_r, X[1::2], v_tpose[1::2])
     L.call("pdf_mano_lbs_pair", ctypes.cast(tl, ctypes.c_void_p), ctypes.cast(tr, ctypes.c_void_p), L.ptr(root),
            L.ptr(pose), L.ptr(shape), L.ptr(trans), L.ptr(scale), n, ctypes.cast(tipl, ctypes.c_void_p),
            ctypes.cast(tipr, ctypes.c_void_p), -1 if center_idx is None else int(center_idx), 1 if new_skel else 0,
