@@ -167,6 +167,159 @@ graph_cheby_ln_kernel(const float* __restrict__ U0, const float* __restrict__ U1
   if (out_img) store_split_image<NPL>(t, C, lane, stage, out_img, r);
 }
 
+// ---- vectorised variants for the decoder's own widths (C = 64 / 128 / 256 / 512) -------------------------------
+// A row is handled by LPR lanes, each owning VEC float4 (lane l: channels 4 (l + LPR v) .. +3), so every load and
+// store is a 16-byte access and a warp covers 32 / LPR rows: 4x fewer memory instructions than one float per lane,
+// which is what bounded the generic kernels (they sit 4-5x under the HBM roofline, profiles/r02_*decoder*).
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+  // only the LPR lanes of this row's group take part (another group of the warp may already have left)
+  const unsigned m = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x & 31) / LPR * LPR));
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+  return v;
+}
+
+template <int LPR, int VEC>
+__device__ __forceinline__ void layer_norm_vec(float4 (&t)[VEC], int l, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, float eps, int relu) {
+  constexpr int C = LPR * 4 * VEC;
+  float s = 0.f;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) s += (t[v].x + t[v].y) + (t[v].z + t[v].w);
+  const float mean = group_sum<LPR>(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const float a = t[v].x - mean, b = t[v].y - mean, c = t[v].z - mean, d = t[v].w - mean;
+    q = fmaf(a, a, fmaf(b, b, fmaf(c, c, fmaf(d, d, q))));
+  }
+  const float rstd = rsqrtf(group_sum<LPR>(q) / (float)C + eps);
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const int c = 4 * (l + LPR * v);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c)), b = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float4 y;
+    y.x = fmaf((t[v].x - mean) * rstd, g.x, b.x); y.y = fmaf((t[v].y - mean) * rstd, g.y, b.y);
+    y.z = fmaf((t[v].z - mean) * rstd, g.z, b.z); y.w = fmaf((t[v].w - mean) * rstd, g.w, b.w);
+    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+    t[v] = y;
+  }
+}
+
+// the lane's 4 channels as 8 bytes of each part of the split image row ([hi | hi | lo])
+template <int LPR, int VEC>
+__device__ __forceinline__ void store_split_vec(const float4 (&t)[VEC], int l, uint8_t* __restrict__ img, int64_t r) {
+  constexpr int C = LPR * 4 * VEC, NKB = C / 64;
+  uint8_t* base = img + (size_t)(r >> 7) * (size_t)(3 * NKB) * 16384;
+  const uint32_t rr = (uint32_t)(r & 127);
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const int c = 4 * (l + LPR * v);
+    uint2 w, wl;
+    w.x = umma::pack_bf16(t[v].x, t[v].y); w.y = umma::pack_bf16(t[v].z, t[v].w);
+    wl.x = umma::pack_bf16(t[v].x - __uint_as_float(w.x << 16), t[v].y - __uint_as_float(w.x & 0xffff0000u));
+    wl.y = umma::pack_bf16(t[v].z - __uint_as_float(w.y << 16), t[v].w - __uint_as_float(w.y & 0xffff0000u));
+    const int kb = c >> 6;
+    const uint32_t off = umma::sw128_off(rr, (uint32_t)(c & 63));
+    *reinterpret_cast<uint2*>(base + (size_t)kb * 16384 + off) = w;
+    *reinterpret_cast<uint2*>(base + (size_t)(NKB + kb) * 16384 + off) = w;
+    *reinterpret_cast<uint2*>(base + (size_t)(2 * NKB + kb) * 16384 + off) = wl;
+  }
+}
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_fma(float w, float4 u, float4 t) {
+  return make_float4(fmaf(w, u.x, t.x), fmaf(w, u.y, t.y), fmaf(w, u.z, t.z), fmaf(w, u.w, t.w));
+}
+
+template <int LPR, int VEC>
+__global__ void __launch_bounds__(256)
+row_combine_vec_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
+                       const float* __restrict__ rowvec, int64_t ldr, int V_out, int up, int64_t rows_out,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
+                       float* __restrict__ sum_out, int64_t lds, float* __restrict__ ln_out, int64_t ldl,
+                       uint8_t* __restrict__ sum_img, uint8_t* __restrict__ ln_img) {
+  const int l = threadIdx.x % LPR;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
+  if (r >= rows_out) return;                                   // whole LPR-lane groups leave together
+  const int64_t smp = r / V_out;
+  const int v = (int)(r - smp * V_out);
+  const int64_t src = smp * (V_out / up) + v / up;
+  float4 t[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c = 4 * (l + LPR * i);
+    float4 x = __ldg(reinterpret_cast<const float4*>(a + src * lda + c));
+    if (b) x = f4_add(x, __ldg(reinterpret_cast<const float4*>(b + src * ldb + c)));
+    if (rowvec) x = f4_add(x, __ldg(reinterpret_cast<const float4*>(rowvec + (int64_t)v * ldr + c)));
+    t[i] = x;
+  }
+  if (sum_out) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) *reinterpret_cast<float4*>(sum_out + r * lds + 4 * (l + LPR * i)) = t[i];
+  }
+  if (sum_img) store_split_vec<LPR, VEC>(t, l, sum_img, r);
+  if (ln_out || ln_img) {
+    layer_norm_vec<LPR, VEC>(t, l, gamma, beta, eps, relu);
+    if (ln_out) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) *reinterpret_cast<float4*>(ln_out + r * ldl + 4 * (l + LPR * i)) = t[i];
+    }
+    if (ln_img) store_split_vec<LPR, VEC>(t, l, ln_img, r);
+  }
+}
+
+template <int LPR, int VEC>
+__global__ void __launch_bounds__(256)
+graph_cheby_ln_vec_kernel(const float* __restrict__ U0, const float* __restrict__ U1, int64_t ldu,
+                          const float* __restrict__ bias, const float* __restrict__ R, int64_t ldr,
+                          const float* __restrict__ bias_r, const int* __restrict__ rowptr,
+                          const int* __restrict__ colidx, const float* __restrict__ vals, int V, int64_t rows,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
+                          float* __restrict__ out, int64_t ldo, uint8_t* __restrict__ out_img) {
+  const int l = threadIdx.x % LPR;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
+  if (r >= rows) return;
+  const int64_t smp = r / V;
+  const int v = (int)(r - smp * V);
+  float4 t[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c = 4 * (l + LPR * i);
+    float4 x = f4_add(__ldg(reinterpret_cast<const float4*>(U0 + r * ldu + c)), __ldg(reinterpret_cast<const float4*>(bias + c)));
+    if (R) {
+      x = f4_add(x, __ldg(reinterpret_cast<const float4*>(R + r * ldr + c)));
+      if (bias_r) x = f4_add(x, __ldg(reinterpret_cast<const float4*>(bias_r + c)));
+    }
+    t[i] = x;
+  }
+  const int e0 = rowptr[v], e1 = rowptr[v + 1];
+  for (int e = e0; e < e1; ++e) {
+    const float w = __ldg(vals + e);
+    const float* u = U1 + (smp * V + __ldg(colidx + e)) * ldu;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) t[i] = f4_fma(w, __ldg(reinterpret_cast<const float4*>(u + 4 * (l + LPR * i))), t[i]);
+  }
+  layer_norm_vec<LPR, VEC>(t, l, gamma, beta, eps, relu);
+  if (out) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) *reinterpret_cast<float4*>(out + r * ldo + 4 * (l + LPR * i)) = t[i];
+  }
+  if (out_img) store_split_vec<LPR, VEC>(t, l, out_img, r);
+}
+
+// C in {64, 128, 256, 512} with 16-byte aligned rows -> (LPR, VEC); returns false for anything else
+template <typename F>
+static bool dispatch_vec(int C, F&& f) {
+  if (C == 64) { f(std::integral_constant<int, 16>(), std::integral_constant<int, 1>()); return true; }
+  if (C == 128) { f(std::integral_constant<int, 32>(), std::integral_constant<int, 1>()); return true; }
+  if (C == 256) { f(std::integral_constant<int, 32>(), std::integral_constant<int, 2>()); return true; }
+  if (C == 512) { f(std::integral_constant<int, 32>(), std::integral_constant<int, 4>()); return true; }
+  return false;
+}
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // one CTA per (sample, head): K and V of that head in shared memory; each warp takes FOUR query rows at a
 // time: scores with lane = key (8 keys per lane, 32 FMAs per 9 shared loads), softmax by warp shuffles,
 // probabilities through a per-warp shared tile, then P.V with lane = output channel.
@@ -376,9 +529,20 @@ extern "C" int pdf_row_combine(const float* a, int64_t lda, const float* b, int6
                   rows_out % V_out == 0 && (!(ln_out || ln_img) || (gamma && beta)) &&
                   (!(sum_img || ln_img) || C % 64 == 0),
               PDF_ERR_BAD_ARG, "pdf_row_combine: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec_ok = lda % 4 == 0 && (!b || ldb % 4 == 0) && (!rowvec || ldr % 4 == 0) && (!sum_out || lds % 4 == 0) &&
+                      (!ln_out || ldl % 4 == 0) && aligned16(a) && aligned16(b) && aligned16(rowvec) &&
+                      aligned16(sum_out) && aligned16(ln_out) && aligned16(gamma) && aligned16(beta);
+  if (vec_ok && dispatch_vec(C, [&](auto lpr, auto vec) {
+        constexpr int LPR = decltype(lpr)::value, VEC = decltype(vec)::value;
+        const unsigned g = (unsigned)((rows_out * LPR + 255) / 256);
+        row_combine_vec_kernel<LPR, VEC><<<g, 256, 0, s>>>(a, lda, b, ldb, rowvec, ldr, V_out, up, rows_out, gamma, beta, eps,
+                                                          relu, sum_out, lds, ln_out, ldl, (uint8_t*)sum_img,
+                                                          (uint8_t*)ln_img);
+      }))
+    return check_launch("pdf_row_combine");
   const unsigned grid = (unsigned)((rows_out * 32 + 255) / 256);
   const size_t smem = (sum_img || ln_img) ? (size_t)8 * C * sizeof(float) : 0;
-  cudaStream_t s = (cudaStream_t)stream;
   dispatch_npl(C, [&](auto npl) {
     row_combine_kernel<decltype(npl)::value><<<grid, 256, smem, s>>>(a, lda, b, ldb, rowvec, ldr, V_out, up, C, rows_out,
                                                                       gamma, beta, eps, relu, sum_out, lds, ln_out, ldl,
@@ -398,9 +562,19 @@ extern "C" int pdf_graph_cheby_ln(const float* U0, const float* U1, int64_t ldu,
               "pdf_graph_cheby_ln: null pointer");
   PDF_REQUIRE(rows > 0 && V > 0 && rows % V == 0 && C > 0 && C <= DEC_MAX_C && (!out_img || C % 64 == 0),
               PDF_ERR_BAD_ARG, "pdf_graph_cheby_ln: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec_ok = ldu % 4 == 0 && (!R || ldr % 4 == 0) && (!out || ldo % 4 == 0) && aligned16(U0) && aligned16(U1) &&
+                      aligned16(bias) && aligned16(R) && aligned16(bias_r) && aligned16(out) && aligned16(gamma) &&
+                      aligned16(beta);
+  if (vec_ok && dispatch_vec(C, [&](auto lpr, auto vec) {
+        constexpr int LPR = decltype(lpr)::value, VEC = decltype(vec)::value;
+        const unsigned g = (unsigned)((rows * LPR + 255) / 256);
+        graph_cheby_ln_vec_kernel<LPR, VEC><<<g, 256, 0, s>>>(U0, U1, ldu, bias, R, ldr, bias_r, rowptr, colidx, vals, V, rows,
+                                                             gamma, beta, eps, relu, out, ldo, (uint8_t*)out_img);
+      }))
+    return check_launch("pdf_graph_cheby_ln");
   const unsigned grid = (unsigned)((rows * 32 + 255) / 256);
   const size_t smem = out_img ? (size_t)8 * C * sizeof(float) : 0;
-  cudaStream_t s = (cudaStream_t)stream;
   dispatch_npl(C, [&](auto npl) {
     graph_cheby_ln_kernel<decltype(npl)::value><<<grid, 256, smem, s>>>(U0, U1, ldu, bias, R, ldr, bias_r, rowptr,
                                                                          colidx, vals, V, C, rows, gamma, beta, eps,

@@ -1248,6 +1248,40 @@ def test_train_step_bf16_operands():
     assert n >= 50
 
 
+def test_train_step_bf16_mode_vs_fp32_mode_64_clouds():
+    """The bf16 training mode pinned on a 64-cloud batch against the fp32-accurate mode (itself pinned to the
+    reference's fp64 autograd above).  Measured on B200 (scripts/train_cos64.py): output rel. error 2.9e-2,
+    cosine of the concatenated gradient 0.87, 43 of 54 tensors >= 0.9, 4 >= 0.99.  The forward error is ordinary
+    bf16 rounding; the gradient gap is NOT rounding of the gradient GEMMs (2^-9 per product averages out) but
+    re-routing: each feature is a max over 64 neighbours / 128 points followed by ReLUs, a 1 % forward perturbation
+    moves a large share of the arg-maxes, and with loss = sum(out * random direction) every re-routed path changes
+    the sign pattern of what is summed.  A per-tensor cosine of 0.99 is therefore not attainable with bf16
+    operands in the forward pass; the bounds below hold the measured behaviour (with margin) so that a real
+    regression - e.g. a wrong operand image - is caught, and the fp32-accurate mode stays the default."""
+    B, R = 64, 64
+    pts, choose, emb0 = synth.clouds(B, seed=41), synth.choose_indices(B, R, seed=41), synth.pyramid(B, R, seed=41)
+    gdir = torch.randn((B, 1, 1024), generator=torch.Generator().manual_seed(41))
+    grads, outs = {}, {}
+    for prec in ("fp32", "bf16"):
+        m = _train_module(prec, R=R)
+        emb = [e.to(DEV).requires_grad_(True) for e in emb0]
+        out = m(pts.to(DEV), emb, choose.to(DEV))
+        (out * gdir.to(DEV)).sum().backward()
+        outs[prec] = out.detach().double().cpu()
+        grads[prec] = {k: p.grad.double().reshape(-1).cpu() for k, p in
+                       list(m.named_parameters()) + [("emb%d" % i, e) for i, e in enumerate(emb)]
+                       if not k.startswith("netR_FC") and p.grad is not None}
+    assert rel_err(outs["bf16"].numpy(), outs["fp32"].numpy()) < 5e-2
+    keys = [k for k, g in grads["fp32"].items() if float(g.abs().max()) >= 1e-6]
+    cos = {k: float(torch.dot(grads["fp32"][k], grads["bf16"][k]) / (grads["fp32"][k].norm() * grads["bf16"][k].norm()))
+           for k in keys}
+    a, b = torch.cat([grads["fp32"][k] for k in keys]), torch.cat([grads["bf16"][k] for k in keys])
+    assert all(torch.isfinite(grads["bf16"][k]).all() for k in keys)
+    assert float(torch.dot(a, b) / (a.norm() * b.norm())) > 0.75
+    assert sum(c >= 0.9 for c in cos.values()) >= 36 and len(keys) >= 50
+    assert min(cos[k] for k in keys if k.startswith("netR_3")) > 0.9      # the late layers see little re-routing
+
+
 def test_train_step_fp32_gradients_are_aligned():
     """Default (fp32-accurate) training mode: every gradient tensor has cosine >= 0.999 with the
     reference's fp64 autograd."""
@@ -1348,26 +1382,34 @@ def test_decoder_primitives_vs_torch():
     gen = torch.Generator().manual_seed(21)
     rnd = lambda *s: torch.randn(s, generator=gen)
     # residual + row vector + x2 up-sampling + LayerNorm (+ReLU), C not a multiple of 32
-    n, V, C = 5, 6, 70
-    a, b, rv = rnd(n * V, C), rnd(n * V, C), rnd(2 * V, C)
-    gamma, beta = rnd(C), rnd(C)
-    t_ref = (a + b).view(n, V, C).repeat_interleave(2, dim=1) + rv
-    ln_ref = F.relu(F.layer_norm(t_ref, (C,), gamma, beta, 1e-6))
-    s_out, l_out = ops.row_combine(a.to(DEV), b.to(DEV), rowvec=rv.to(DEV), V_out=2 * V, up=2,
-                                   ln=(gamma.to(DEV), beta.to(DEV)), relu=True, want_sum=True)
-    np.testing.assert_allclose(s_out.cpu().numpy(), t_ref.reshape(-1, C).numpy(), rtol=1e-6, atol=1e-6)
-    np.testing.assert_allclose(l_out.cpu().numpy(), ln_ref.reshape(-1, C).numpy(), rtol=1e-4, atol=1e-5)
+    n, V = 5, 6
+    for C in (70, 64, 128, 256, 512):                  # generic kernel, then the float4 variants (odd row count: n*2V = 60)
+        a, b, rv = rnd(n * V, C), rnd(n * V, C), rnd(2 * V, C)
+        gamma, beta = rnd(C), rnd(C)
+        t_ref = (a + b).view(n, V, C).repeat_interleave(2, dim=1) + rv
+        ln_ref = F.relu(F.layer_norm(t_ref, (C,), gamma, beta, 1e-6))
+        s_out, l_out = ops.row_combine(a.to(DEV), b.to(DEV), rowvec=rv.to(DEV), V_out=2 * V, up=2,
+                                       ln=(gamma.to(DEV), beta.to(DEV)), relu=True, want_sum=True)
+        np.testing.assert_allclose(s_out.cpu().numpy(), t_ref.reshape(-1, C).numpy(), rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(l_out.cpu().numpy(), ln_ref.reshape(-1, C).numpy(), rtol=1e-4, atol=1e-5)
+        if C % 64 == 0:                                # image outputs == rows + pdf_rows_to_image (first whole tile)
+            a2, b2 = rnd(128, C).to(DEV), rnd(128, C).to(DEV)
+            s2, l2, s_img, l_img = ops.row_combine(a2, b2, ln=(gamma.to(DEV), beta.to(DEV)), want_sum=True, sum_img=True,
+                                                   ln_img=True)
+            assert torch.equal(s_img, ops.rows_to_image(s2, 0, C, split=1))
+            assert torch.equal(l_img, ops.rows_to_image(l2, 0, C, split=1))
     # Chebyshev graph term + shortcut + LayerNorm, wide rows (C = 600 > 512), sparse random Laplacian
-    V, C = 17, 600
+    V = 17
     Ld = rnd(V, V) * (torch.rand((V, V), generator=gen) < 0.3)
-    U, R = rnd(n * V, 2 * C), rnd(n * V, C)
-    bias, bias_r, gamma, beta = rnd(C), rnd(C), rnd(C), rnd(C)
-    t_ref = U[:, :C] + bias + torch.einsum("vu,buc->bvc", Ld, U[:, C:].view(n, V, C)).reshape(-1, C) + R + bias_r
-    ref = F.layer_norm(t_ref, (C,), gamma, beta, 1e-6)
-    Ud = U.to(DEV)
-    got = ops.graph_cheby_ln(Ud[:, :C], Ud[:, C:], bias.to(DEV), tuple(t.to(DEV) for t in _csr(Ld.numpy())), V,
-                             (gamma.to(DEV), beta.to(DEV)), False, R=R.to(DEV), bias_r=bias_r.to(DEV))
-    np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=2e-5)
+    for C in (600, 64, 128, 256):                      # generic kernel, then the float4 variants (n*V = 85 rows: odd)
+        U, R = rnd(n * V, 2 * C), rnd(n * V, C)
+        bias, bias_r, gamma, beta = rnd(C), rnd(C), rnd(C), rnd(C)
+        t_ref = U[:, :C] + bias + torch.einsum("vu,buc->bvc", Ld, U[:, C:].view(n, V, C)).reshape(-1, C) + R + bias_r
+        ref = F.layer_norm(t_ref, (C,), gamma, beta, 1e-6)
+        Ud = U.to(DEV)
+        got = ops.graph_cheby_ln(Ud[:, :C], Ud[:, C:], bias.to(DEV), tuple(t.to(DEV) for t in _csr(Ld.numpy())), V,
+                                 (gamma.to(DEV), beta.to(DEV)), False, R=R.to(DEV), bias_r=bias_r.to(DEV))
+        np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=2e-5, err_msg=str(C))
     # attention: every head size, token counts on both sides of the 32-key lane groups, cross q vs k/v
     for V, heads, d in ((63, 4, 64), (126, 4, 32), (252, 4, 16), (1, 2, 16), (33, 1, 32)):
         f = heads * d
