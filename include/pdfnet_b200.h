@@ -37,7 +37,10 @@ typedef enum {
 enum { PDF_ACT_NONE = 0, PDF_ACT_RELU = 1, PDF_ACT_LEAKY01 = 2 };
 /* OR-ed onto the `act` argument of pdf_gemm_bf16: out_img is written as a SPLIT image [hi | hi | lo]
  * (out_kb = 3 x k-blocks of the output matrix), i.e. directly as the fp32-accurate M operand of the next GEMM. */
-enum { PDF_GEMM_OUT_SPLIT = 256 };
+enum { PDF_GEMM_OUT_SPLIT = 256,
+       /* also OR-ed onto `act`: run the half-footprint configuration (2 operand stages, 256 TMEM columns, two CTAs
+        * per SM) - for short GEMMs that come in concurrent pairs on two streams; single-accumulator ROW mode only */
+       PDF_GEMM_LIGHT = 512 };
 #define PDF_MANO_VT_PITCH 2336
 /* epilogue modes for pdf_linear_f32 */
 enum {

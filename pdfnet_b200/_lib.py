@@ -82,6 +82,7 @@ EXPORTS = sorted(list(SIGNATURES) + ["pdf_version", "pdf_last_error", "pdf_launc
 
 ACT_NONE, ACT_RELU, ACT_LEAKY01 = 0, 1, 2
 GEMM_OUT_SPLIT = 256          # OR-ed onto act: pdf_gemm_bf16 writes out_img as a split image [hi | hi | lo]
+GEMM_LIGHT = 512              # OR-ed onto act: half-footprint GEMM configuration (two CTAs per SM)
 EPI_STORE, EPI_SFT_SCALE, EPI_ACCUM, EPI_GROUP_MAX = 0, 1, 2, 3
 
 _lib = None

@@ -60,15 +60,21 @@ __device__ __forceinline__ void mbar_arrive(uint32_t saddr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(saddr) : "memory");
 }
 
-template <bool COLMAX>
-__global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParams P) {
+// LIGHT: two operand stages and 256 TMEM columns instead of four and 512, so TWO CTAs fit on an SM.  The decoder's
+// GEMMs are short (3 - 24 k-blocks, a few hundred work items) and come in left-hand / right-hand pairs on two
+// streams; a full-size CTA owns its SM (150 KB of shared memory, all of tensor memory), which serialises the pair
+// and exposes every launch's fixed cost (~10 us of prologue, pipeline fill and drain).  Single accumulator only.
+template <bool COLMAX, bool LIGHT = false>
+__global__ void __launch_bounds__(G_THREADS, LIGHT ? 2 : 1) gemm_bf16_kernel(const GemmParams P) {
+  constexpr int G_STAGES = LIGHT ? 2 : pdf::G_STAGES;
+  constexpr int TMEM_COLS = LIGHT ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_STAGES * 2 * G_BLOCK);
   // bars: [0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * G_STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool dual = P.kb_split > 0;
+  const bool dual = LIGHT ? false : P.kb_split > 0;          // LIGHT: single accumulator, no xyz side channel (compile-time)
   const int acc_cols = dual ? 256 : 128;
 
   if (threadIdx.x == 0) {
@@ -76,10 +82,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
     for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bars[2 * G_STAGES + a]), 1); mbar_init(smem_u32(&bars[2 * G_STAGES + 2 + a]), COLMAX ? 4 : 8); }
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc<512>(s_tmem);
+  if (warp == 0) tmem_alloc<TMEM_COLS>(s_tmem);
   float* s_bias = reinterpret_cast<float*>(smem + G_STAGES * 2 * G_BLOCK + 256);   // [2][n_tiles*128]
   float* s_xyz = s_bias + 2 * G_MAX_NT * 128;                                     // [390]
-  const bool xyz = !COLMAX && P.xyz_w != nullptr;
+  const bool xyz = !LIGHT && !COLMAX && P.xyz_w != nullptr;
   if (!COLMAX) {
     for (int i = threadIdx.x; i < P.n_tiles * 128; i += G_THREADS) {
       s_bias[i] = P.bias0 ? P.bias0[i] : 0.f;
@@ -287,8 +293,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_kernel(const GemmParam
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tmem_base);
+  if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
+
+constexpr int G_SMEM_LIGHT = 2 * 2 * G_BLOCK + 1024 + 256 + 2 * G_MAX_NT * 128 * 4 + 400 * 4;
 
 // fp32 rows [M, ld] columns [col0, col0+K) -> bf16 image k-blocks [kb0, kb0 + ceil(K/64)) of every
 // row-tile; rows >= M and columns >= K are written as zeros.  One thread per 16-byte chunk.
@@ -491,8 +499,9 @@ extern "C" int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const voi
   PDF_REQUIRE(m_tiles > 0 && n_tiles > 0 && KB > 0 && m_kb > 0 && (KB <= m_kb || KB % m_kb == 0) && KB <= n_kb &&
                   kb_split >= 0 && kb_split < KB,
               PDF_ERR_BAD_ARG, "pdf_gemm_bf16: bad size");
-  const int out_split = (act & PDF_GEMM_OUT_SPLIT) ? 1 : 0;     // flag bit on the activation argument
-  act &= ~PDF_GEMM_OUT_SPLIT;
+  const int out_split = (act & PDF_GEMM_OUT_SPLIT) ? 1 : 0;     // flag bits on the activation argument
+  const bool light = (act & PDF_GEMM_LIGHT) && !colmax && kb_split == 0;
+  act &= ~(PDF_GEMM_OUT_SPLIT | PDF_GEMM_LIGHT);
   PDF_REQUIRE(act >= 0 && act <= 2, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: bad activation");
   PDF_REQUIRE(!out_split || (out_img && out_kb % 3 == 0 && !colmax), PDF_ERR_BAD_ARG,
               "pdf_gemm_bf16: a split output image needs out_img with 3 x k-blocks");
@@ -533,11 +542,17 @@ extern "C" int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const voi
   if (once.first()) {
     cudaFuncSetAttribute(gemm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
     cudaFuncSetAttribute(gemm_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
+    cudaFuncSetAttribute(gemm_bf16_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_LIGHT);
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = m_tiles * n_tiles;
+  if (light) {
+    if (grid > 2 * sms) grid = 2 * sms;              // two resident CTAs per SM
+    gemm_bf16_kernel<false, true><<<grid, G_THREADS, G_SMEM_LIGHT, (cudaStream_t)stream>>>(P);
+    return check_launch("pdf_gemm_bf16");
+  }
   if (grid > sms) grid = sms;
   if (colmax) gemm_bf16_kernel<true><<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(P);
   else gemm_bf16_kernel<false><<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(P);

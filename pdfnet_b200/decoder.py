@@ -258,7 +258,8 @@ class decoder(nn.Module):
             packed = self._cache.get(key)
             if packed is None:
                 packed = self._cache[key] = ops.pack_linear_tc(w, b, split=True) + (w, b)   # keep w / b alive
-            return ops.linear_tc(x, None, None, act=act, packed=packed[:5], x_img=x_img, M=M, out_image=out_image)
+            return ops.linear_tc(x, None, None, act=act, packed=packed[:5], x_img=x_img, M=M, out_image=out_image,
+                                 light=True)
         assert not out_image
         return ops.linear(x, w, b, act=act)
 

@@ -660,7 +660,8 @@ def pack_linear_tc(w, bias=None, split=True):
     return (w_img, b, N, K, split)
 
 
-def linear_tc(x, w, bias=None, act=L.ACT_NONE, split=True, packed=None, x_img=None, M=None, out_image=False):
+def linear_tc(x, w, bias=None, act=L.ACT_NONE, split=True, packed=None, x_img=None, M=None, out_image=False,
+              light=False):
     """act(x @ w.T + bias) on the tcgen05 GEMM.  split=True: split-bf16 operands (three bf16 products
     per fp32 product: fp32-accurate, ~2^-16 relative); split=False: plain bf16 operands, fp32
     accumulate.  x [M,K] fp32 rows (or ``x_img`` = its tile image and ``M``), w [N,K] fp32 (device) or
@@ -676,6 +677,8 @@ def linear_tc(x, w, bias=None, act=L.ACT_NONE, split=True, packed=None, x_img=No
         M = _rows(x).shape[0]
         assert x.shape[1] == K
         x_img = rows_to_image(x, 0, K, split=1 if split else 0)
+    if light:
+        act = act | L.GEMM_LIGHT
     if out_image:
         # the result only feeds another GEMM: written ONLY as that GEMM's split operand image (N % 64 == 0)
         assert split and N % 64 == 0
