@@ -295,15 +295,29 @@ def run_ours(args):
         dec.set_joint_regressors(tables["left"]["J_regressor"], tables["right"]["J_regressor"])
         dec = dec.to(dev).eval()
 
-    def hot_path(d):
+    mano_side = torch.cuda.Stream(device=dev)
+
+    def hot_path(d, overlap=True):
+        """One pass.  overlap: the MANO branch (head, Split_coeff, LBS - it only needs the un-fused features) runs
+        on a side stream beside the fusion SFT and the GCN decoder (a fork / join inside the captured graph);
+        overlap=False keeps everything on one stream for the per-stage timings."""
         with profiling.stage("depth2pcl"):
             choose, cloud, _ = ops.depth2pcl(d["depth"], d["mask"], d["Kinv"], d["valid"], seed=D2P_SEED)
-        fused, theta = model(cloud, [d["l0"], d["l1"], d["l2"]], choose, d["center"], with_mano=True)
-        with profiling.stage("mano_tail"):
-            verts, joints, _ = mano_tail_pair(theta, d["ind"], d["K"], mano_l, mano_r, input_res=R)
+        side = mano_side if (overlap and dec is not None) else None
+        fused, theta = model(cloud, [d["l0"], d["l1"], d["l2"]], choose, d["center"], with_mano=True, mano_stream=side)
+        if side is not None:
+            with torch.cuda.stream(side):
+                verts, joints, _ = mano_tail_pair(theta, d["ind"], d["K"], mano_l, mano_r, input_res=R)
+        else:
+            with profiling.stage("mano_tail"):
+                verts, joints, _ = mano_tail_pair(theta, d["ind"], d["K"], mano_l, mano_r, input_res=R)
         if dec is not None:
             with profiling.stage("gcn_decoder"):
                 result, _, _, other = dec(fused[:, 0], fused[:, 1], None)
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)         # join
+                for t in (verts, joints):
+                    t.record_stream(torch.cuda.current_stream())
             return (fused, verts, joints, result["verts3d"]["left"], result["verts3d"]["right"],
                     other["joints3d"]["left"], other["joints3d"]["right"])
         return fused, verts, joints
@@ -440,11 +454,11 @@ def run_ours(args):
 
     # ---- per-stage timing (roofline of the dominant kernel), same inputs, L2 flushed ----
     for _ in range(2):
-        hot_path(resident)
+        hot_path(resident, overlap=False)
     profiling.enable(True)
     for _ in range(max(5, min(args.steps, 11))):
         flush.fill_(1)
-        hot_path(resident)
+        hot_path(resident, overlap=False)
     stages = profiling.summary()
     profiling.enable(False)
 

@@ -1,5 +1,6 @@
 // Error reporting and bookkeeping shared by every entry point.
 #include <atomic>
+#include <stdlib.h>
 #include "pdf_common.cuh"
 
 namespace pdf {
@@ -13,6 +14,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = getenv("PDF_NO_PDL") == nullptr;
+  return on;
+}
 }  // namespace pdf
 
 extern "C" int pdf_version(void) { return 100; }

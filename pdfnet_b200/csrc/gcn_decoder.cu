@@ -240,6 +240,8 @@ row_combine_vec_kernel(const float* __restrict__ a, int64_t lda, const float* __
                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
                        float* __restrict__ sum_out, int64_t lds, float* __restrict__ ln_out, int64_t ldl,
                        uint8_t* __restrict__ sum_img, uint8_t* __restrict__ ln_img) {
+  pdl_wait();
+  pdl_trigger();
   const int l = threadIdx.x % LPR;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
   if (r >= rows_out) return;                                   // whole LPR-lane groups leave together
@@ -278,6 +280,8 @@ graph_cheby_ln_vec_kernel(const float* __restrict__ U0, const float* __restrict_
                           const int* __restrict__ colidx, const float* __restrict__ vals, int V, int64_t rows,
                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
                           float* __restrict__ out, int64_t ldo, uint8_t* __restrict__ out_img) {
+  pdl_wait();
+  pdl_trigger();
   const int l = threadIdx.x % LPR;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
   if (r >= rows) return;
@@ -470,6 +474,8 @@ decoder_heads_kernel(const float* __restrict__ f, int64_t ldf, int V, int C, con
                      const float* __restrict__ bc, float* __restrict__ params, float* __restrict__ root,
                      float* __restrict__ verts) {
   extern __shared__ __align__(16) float hs[];
+  pdl_wait();
+  pdl_trigger();
   const int pitch = C + 1;
   float* sf = hs;                            // [V][C+1]
   float* st = sf + (size_t)V * pitch;        // temp [C]
@@ -536,9 +542,8 @@ extern "C" int pdf_row_combine(const float* a, int64_t lda, const float* b, int6
   if (vec_ok && dispatch_vec(C, [&](auto lpr, auto vec) {
         constexpr int LPR = decltype(lpr)::value, VEC = decltype(vec)::value;
         const unsigned g = (unsigned)((rows_out * LPR + 255) / 256);
-        row_combine_vec_kernel<LPR, VEC><<<g, 256, 0, s>>>(a, lda, b, ldb, rowvec, ldr, V_out, up, rows_out, gamma, beta, eps,
-                                                          relu, sum_out, lds, ln_out, ldl, (uint8_t*)sum_img,
-                                                          (uint8_t*)ln_img);
+        launch_pdl(row_combine_vec_kernel<LPR, VEC>, dim3(g), dim3(256), 0, s, a, lda, b, ldb, rowvec, ldr, V_out, up, rows_out,
+                   gamma, beta, eps, relu, sum_out, lds, ln_out, ldl, (uint8_t*)sum_img, (uint8_t*)ln_img);
       }))
     return check_launch("pdf_row_combine");
   const unsigned grid = (unsigned)((rows_out * 32 + 255) / 256);
@@ -569,8 +574,8 @@ extern "C" int pdf_graph_cheby_ln(const float* U0, const float* U1, int64_t ldu,
   if (vec_ok && dispatch_vec(C, [&](auto lpr, auto vec) {
         constexpr int LPR = decltype(lpr)::value, VEC = decltype(vec)::value;
         const unsigned g = (unsigned)((rows * LPR + 255) / 256);
-        graph_cheby_ln_vec_kernel<LPR, VEC><<<g, 256, 0, s>>>(U0, U1, ldu, bias, R, ldr, bias_r, rowptr, colidx, vals, V, rows,
-                                                             gamma, beta, eps, relu, out, ldo, (uint8_t*)out_img);
+        launch_pdl(graph_cheby_ln_vec_kernel<LPR, VEC>, dim3(g), dim3(256), 0, s, U0, U1, ldu, bias, R, ldr, bias_r, rowptr,
+                   colidx, vals, V, rows, gamma, beta, eps, relu, out, ldo, (uint8_t*)out_img);
       }))
     return check_launch("pdf_graph_cheby_ln");
   const unsigned grid = (unsigned)((rows * 32 + 255) / 256);
@@ -637,8 +642,7 @@ extern "C" int pdf_decoder_heads(const float* f, int64_t ldf, int64_t n, int V, 
               "pdf_decoder_heads: bad size (the [V, C] tile must fit shared memory)");
   static pdf::PerDeviceOnce once;
   if (once.first()) cudaFuncSetAttribute(decoder_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  decoder_heads_kernel<<<(unsigned)n, 256, smem, (cudaStream_t)stream>>>(f, ldf, V, C, avg_w, avg_b, params_w, params_b,
-                                                                        root_w, root_b, coord_w, coord_b, params, root,
-                                                                        verts);
+  launch_pdl(decoder_heads_kernel, dim3((unsigned)n), dim3(256), smem, (cudaStream_t)stream, f, ldf, V, C, avg_w, avg_b,
+             params_w, params_b, root_w, root_b, coord_w, coord_b, params, root, verts);
   return check_launch("pdf_decoder_heads");
 }

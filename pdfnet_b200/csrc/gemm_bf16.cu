@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(G_THREADS, LIGHT ? 2 : 1) gemm_bf16_kernel(con
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<TMEM_COLS>(s_tmem);
+  pdl_wait();                                      // everything above is on-chip set-up; global memory from here on
+  pdl_trigger();
   float* s_bias = reinterpret_cast<float*>(smem + G_STAGES * 2 * G_BLOCK + 256);   // [2][n_tiles*128]
   float* s_xyz = s_bias + 2 * G_MAX_NT * 128;                                     // [390]
   const bool xyz = !LIGHT && !COLMAX && P.xyz_w != nullptr;
@@ -303,6 +305,8 @@ constexpr int G_SMEM_LIGHT = 2 * 2 * G_BLOCK + 1024 + 256 + 2 * G_MAX_NT * 128 *
 __global__ void rows_to_image_kernel(const float* __restrict__ X, int64_t ld, int64_t M, int col0, int K,
                                      uint8_t* __restrict__ img, int kb_total, int kb0, int nkb, int64_t n_chunks,
                                      int split) {
+  pdl_wait();
+  pdl_trigger();
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_chunks;
        e += (int64_t)gridDim.x * blockDim.x) {
     const int ch = (int)(e & 7);                         // 16 B chunk inside a 64-column block row
@@ -482,8 +486,8 @@ extern "C" int pdf_rows_to_image(const float* X, int64_t ld, int64_t M, int col0
   const int64_t chunks = rows_pad * nkb * 8;
   int64_t grid = (chunks + 255) / 256;
   if (grid > 148 * 32) grid = 148 * 32;
-  pdf::rows_to_image_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(X, ld, M, col0, K, (uint8_t*)img,
-                                                                              kb_total, kb0, nkb, chunks, split);
+  pdf::launch_pdl(pdf::rows_to_image_kernel, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, X, ld, M, col0, K,
+                  (uint8_t*)img, kb_total, kb0, nkb, chunks, split);
   return pdf::check_launch("pdf_rows_to_image");
 }
 
@@ -550,12 +554,12 @@ extern "C" int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const voi
   int grid = m_tiles * n_tiles;
   if (light) {
     if (grid > 2 * sms) grid = 2 * sms;              // two resident CTAs per SM
-    gemm_bf16_kernel<false, true><<<grid, G_THREADS, G_SMEM_LIGHT, (cudaStream_t)stream>>>(P);
+    launch_pdl(gemm_bf16_kernel<false, true>, dim3(grid), dim3(G_THREADS), (size_t)G_SMEM_LIGHT, (cudaStream_t)stream, P);
     return check_launch("pdf_gemm_bf16");
   }
   if (grid > sms) grid = sms;
-  if (colmax) gemm_bf16_kernel<true><<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(P);
-  else gemm_bf16_kernel<false><<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(P);
+  if (colmax) launch_pdl(gemm_bf16_kernel<true, false>, dim3(grid), dim3(G_THREADS), (size_t)G_SMEM, (cudaStream_t)stream, P);
+  else launch_pdl(gemm_bf16_kernel<false, false>, dim3(grid), dim3(G_THREADS), (size_t)G_SMEM, (cudaStream_t)stream, P);
   return check_launch("pdf_gemm_bf16");
 }
 

@@ -48,6 +48,8 @@ knn_ball_kernel(const float* __restrict__ xyz, int n_points, int n_centroids, in
                 int32_t* __restrict__ idx_out, int chunks_per_cloud, int centroids_per_cta) {
   constexpr int NP = T * 32;
   __shared__ float sx[NP], sy[NP], sz[NP];
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x / chunks_per_cloud;
   const int chunk = blockIdx.x % chunks_per_cloud;
   const float* base = xyz + (int64_t)b * stride_cloud;
@@ -216,11 +218,11 @@ extern "C" int pdf_knn_ball(const float* xyz, int64_t n_clouds, int n_points, in
   dim3 grid((unsigned)(n_clouds * chunks));
   cudaStream_t s = (cudaStream_t)stream;
   if (n_points <= 512)
-    pdf::knn_ball_kernel<16><<<grid, 256, 0, s>>>(xyz, n_points, n_centroids, k, r2, stride_cloud, stride_point,
-                                                  stride_ch, idx_out, chunks, per_cta);
+    pdf::launch_pdl(pdf::knn_ball_kernel<16>, grid, dim3(256), 0, s, xyz, n_points, n_centroids, k, r2, stride_cloud,
+                    stride_point, stride_ch, idx_out, chunks, per_cta);
   else
-    pdf::knn_ball_kernel<32><<<grid, 256, 0, s>>>(xyz, n_points, n_centroids, k, r2, stride_cloud, stride_point,
-                                                  stride_ch, idx_out, chunks, per_cta);
+    pdf::launch_pdl(pdf::knn_ball_kernel<32>, grid, dim3(256), 0, s, xyz, n_points, n_centroids, k, r2, stride_cloud,
+                    stride_point, stride_ch, idx_out, chunks, per_cta);
   return pdf::check_launch("pdf_knn_ball");
 }
 

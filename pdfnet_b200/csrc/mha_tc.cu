@@ -63,6 +63,8 @@ mha_tc_kernel(const MhaParams P) {
   uint16_t* sVh = sKl + (size_t)Vp * KP;                     // [D][VP]  (V transposed: key index contiguous)
   uint16_t* sVl = sVh + (size_t)D * VP;
 
+  pdl_wait();
+  pdl_trigger();
   const int prob = blockIdx.y;
   const int smp = blockIdx.x / P.heads, h = blockIdx.x - smp * P.heads;
   const MhaProblem pb = P.p[prob];
@@ -231,7 +233,7 @@ static void mha_tc_launch(const MhaParams& P, int n_problems, cudaStream_t s) {
   }
   const int tiles = (P.V + 15) / 16;
   const int threads = 32 * (tiles < 8 ? (tiles < 4 ? 4 : tiles) : 8);
-  mha_tc_kernel<D><<<dim3((unsigned)(P.n_samples * P.heads), (unsigned)n_problems), threads, smem, s>>>(P);
+  launch_pdl(mha_tc_kernel<D>, dim3((unsigned)(P.n_samples * P.heads), (unsigned)n_problems), dim3(threads), smem, s, P);
 }
 
 }  // namespace pdf

@@ -77,6 +77,8 @@ pyramid_gather_bf16_kernel(const float* __restrict__ xyz, const int64_t* __restr
                            const float* __restrict__ sft0, float* __restrict__ pts0, uint8_t* __restrict__ img1,
                            uint8_t* __restrict__ img2) {
   __shared__ float P[48];
+  pdl_wait();
+  pdl_trigger();
   const int64_t b = blockIdx.x;
   const int64_t f = b / clouds_per_frame;
   const int64_t* ch = choose + b * n_points;
@@ -144,8 +146,9 @@ extern "C" int pdf_pyramid_gather_bf16(const float* xyz, const int64_t* choose, 
   if (n_clouds == 0) return PDF_OK;
   PDF_REQUIRE(n_clouds < (1ll << 31) && (int64_t)R * R < (1ll << 31), PDF_ERR_UNSUPPORTED,
               "pdf_pyramid_gather_bf16: too large");
-  pdf::pyramid_gather_bf16_kernel<<<dim3((unsigned)n_clouds, 1 + 2 * pdf::PGB_PARTS), 256, 0, (cudaStream_t)stream>>>(
-      xyz, choose, clouds_per_frame, n_points, n1, n2, R, (const uint16_t*)l0, (const uint16_t*)l1, C1,
-      (const uint16_t*)l2, C2, sft0_params, pts0, (uint8_t*)cond1_img, (uint8_t*)cond2_img);
+  pdf::launch_pdl(pdf::pyramid_gather_bf16_kernel, dim3((unsigned)n_clouds, 1 + 2 * pdf::PGB_PARTS), dim3(256), 0,
+                  (cudaStream_t)stream, xyz, choose, clouds_per_frame, n_points, n1, n2, R, (const uint16_t*)l0,
+                  (const uint16_t*)l1, C1, (const uint16_t*)l2, C2, sft0_params, pts0, (uint8_t*)cond1_img,
+                  (uint8_t*)cond2_img);
   return pdf::check_launch("pdf_pyramid_gather_bf16");
 }

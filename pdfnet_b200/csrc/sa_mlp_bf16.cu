@@ -174,6 +174,8 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
   fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
 
+  pdl_wait();                                            // on-chip set-up above; global memory from here on
+  pdl_trigger();
   if (tid == 0) {                                        // resident weights: bulk copies on the TMA engine
     mbar_expect_tx(smem_u32(&s_bar[0]), Cfg::W_BYTES);
     for (int off = 0; off < Cfg::W_BYTES; off += 32768) {
@@ -468,9 +470,9 @@ static int launch_sa(const float* pts, int64_t n_clouds, int n_src, int64_t ld_p
   }
   int64_t grid = (n_tiles + Cfg::SLOTS - 1) / Cfg::SLOTS;
   if (grid > sms) grid = sms;
-  sa_mlp_max_kernel<Cfg><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(
-      pts, n_src, ld_pts, reinterpret_cast<const uint16_t*>(feat_bf16), idx, n_centroids,
-      reinterpret_cast<const uint8_t*>(wpack), out, ld_out, out_col0, n_tiles);
+  launch_pdl(sa_mlp_max_kernel<Cfg>, dim3((unsigned)grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, stream, pts, n_src,
+             ld_pts, reinterpret_cast<const uint16_t*>(feat_bf16), idx, n_centroids,
+             reinterpret_cast<const uint8_t*>(wpack), out, ld_out, out_col0, n_tiles);
   return check_launch("pdf_sa_mlp_max_bf16");
 }
 

@@ -399,9 +399,13 @@ class HandFusion(nn.Module):
             nn.Linear(1024, 512), nn.BatchNorm1d(512), nn.ReLU(inplace=True),
             nn.Linear(512, 256), nn.BatchNorm1d(256), nn.ReLU(inplace=True), nn.Linear(256, 122))
 
-    def forward(self, cloud, point_wise_emb, choose, center_features, with_mano=False):
+    def forward(self, cloud, point_wise_emb, choose, center_features, with_mano=False, mano_stream=None):
         """cloud [B,2,N,3], choose [B,2,N], center_features [B,2,1024] ->
-        fuse_feat [B,2,1024] (and theta [B,2,122] = (point2mano_left, point2mano_right))."""
+        fuse_feat [B,2,1024] (and theta [B,2,122] = (point2mano_left, point2mano_right)).
+        ``mano_stream`` (inference): the MANO head - which only reads the un-fused per-hand features - is enqueued
+        on that stream, concurrently with the fusion SFT (and whatever the caller runs on the current stream
+        afterwards, e.g. the GCN decoder); the caller joins with ``current_stream().wait_stream(mano_stream)``
+        before reading theta on another stream."""
         B, H, N, _ = cloud.shape
         if self.training or _grad_needed(self, cloud, center_features, *point_wise_emb):
             from .training import hand_fusion_train
@@ -410,6 +414,12 @@ class HandFusion(nn.Module):
                                   clouds_per_frame=H)                       # [2B,1,1024]
         rows = feat.view(B * H, 1024)
         with torch.no_grad():
+            theta = None
+            if with_mano and mano_stream is not None:      # fork: the MANO head runs beside the fusion SFT
+                mano_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(mano_stream):
+                    theta = self.mano_head_forward(rows).reshape(B, H, 122)
+                rows.record_stream(mano_stream)
             with stage("fusion_sft"):
                 cen = L.f32c(center_features).view(B * H, 1024)
                 if self.pointnet_plus.precision == "bf16":
@@ -418,6 +428,8 @@ class HandFusion(nn.Module):
                     fused = self.sft.apply_rows(rows, cen).view(B, H, 1024)
             if not with_mano:
                 return fused
+            if theta is not None:
+                return fused, theta
             with stage("mano_head"):
                 theta = self.mano_head_forward(rows).reshape(B, H, 122)
             return fused, theta

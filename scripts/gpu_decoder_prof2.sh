@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-PREC=bf16x3 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+PREC=bf16x3 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none ${PDF_NCU_EXTRA} --profile-from-start off --csv \
    --log-file gpurun_out/dec_launches.csv python scripts/decoder_profile.py > gpurun_out/dec_prof.log 2>&1
 python - <<'PY'
 import csv, collections
