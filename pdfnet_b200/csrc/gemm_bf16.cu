@@ -19,6 +19,7 @@
 //           rows and/or as the bf16 image of the next layer.
 //   COLMAX: lane = output channel (weights are the M operand), columns = the 128 points of
 //           one cloud: y[cloud, c] = relu(max_p D[c,p] + bias[c])   (netR_3 + MaxPool, :86-103).
+#include <stdlib.h>
 #include "pdf_common.cuh"
 #include "umma.cuh"
 
@@ -504,7 +505,10 @@ extern "C" int pdf_gemm_bf16(const void* m_img, int m_tiles, int m_kb, const voi
                   kb_split >= 0 && kb_split < KB,
               PDF_ERR_BAD_ARG, "pdf_gemm_bf16: bad size");
   const int out_split = (act & PDF_GEMM_OUT_SPLIT) ? 1 : 0;     // flag bits on the activation argument
-  const bool light = (act & PDF_GEMM_LIGHT) && !colmax && kb_split == 0;
+  // the half-footprint configuration only has two operand stages in flight: it pays for short K loops (<= 12 k-blocks, measured),
+  // longer ones keep the four-stage pipeline (override: PDF_GEMM_LIGHT_MAX_KB)
+  static const int light_max_kb = getenv("PDF_GEMM_LIGHT_MAX_KB") ? atoi(getenv("PDF_GEMM_LIGHT_MAX_KB")) : 12;
+  const bool light = (act & PDF_GEMM_LIGHT) && !colmax && kb_split == 0 && KB <= light_max_kb;
   act &= ~(PDF_GEMM_OUT_SPLIT | PDF_GEMM_LIGHT);
   PDF_REQUIRE(act >= 0 && act <= 2, PDF_ERR_BAD_ARG, "pdf_gemm_bf16: bad activation");
   PDF_REQUIRE(!out_split || (out_img && out_kb % 3 == 0 && !colmax), PDF_ERR_BAD_ARG,
