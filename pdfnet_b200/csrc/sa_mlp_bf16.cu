@@ -19,14 +19,20 @@
 //     as a bf16 hi+lo pair (~fp32 accuracy) and the bias is added by the MMA itself;
 //   * each slot issues its own MMAs (one elected thread) and waits on its own
 //     mbarrier; slots overlap each other's CUDA-core phases with tensor-core phases.
+#include <stdlib.h>
 #include "pdf_common.cuh"
 #include "umma.cuh"
 
 namespace pdf {
 using namespace umma;
 
-template <int CF_, int C1_, int C2_, int C3_, int SLOTS_, bool COMPACT_ = false, bool TS_ = true>
+template <int CF_, int C1_, int C2_, int C3_, int SLOTS_, bool COMPACT_ = false, bool TS_ = true, bool EARLY_ = true>
 struct SaCfg {
+  // EARLY: the inputs of tile t+1 are staged while tile t is still in its last MMA phase / its max epilogue: the
+  // geometry block is double-buffered (written before waiting for layer 3 of tile t) and the level-2 feature rows
+  // are copied (cp.async) into the operand tile the moment layer 3 has finished reading it, i.e. under the max
+  // epilogue, instead of at the top of the next iteration where their latency sat on the slot's serial chain.
+  static constexpr bool EARLY = EARLY_ && !COMPACT_;
   // TS: layer 2 reads its A operand (the layer-1 activations) from TENSOR MEMORY: the layer-1 epilogue packs
   // ReLU(D1) to bf16 in place over D1's own columns (tcgen05.st) together with the constant bias block, so the
   // activations never cross the shared-memory port (whose 128 B/clk - MMA operand reads plus the repack stores -
@@ -48,8 +54,10 @@ struct SaCfg {
   static constexpr int W_BYTES = OFF_W3A + W3_AUX;
   static constexpr int KBMAX = (KB1 > KB2 ? (KB1 > KB3 ? KB1 : KB3) : (KB2 > KB3 ? KB2 : KB3));
   static constexpr int SLOT_FEAT = KBMAX * 128 * 128;                     // activation tile, in place
-  static constexpr int SLOT_BYTES = SLOT_FEAT + 128 * 32;                 // + geometry/bias aux block
-  static constexpr int SMEM_BYTES = W_BYTES + SLOTS * SLOT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int AUX_BUFS = EARLY ? 2 : 1;
+  static constexpr int SLOT_BYTES = SLOT_FEAT + AUX_BUFS * 128 * 32;      // + geometry/bias aux block(s)
+  static constexpr int ROWIDX_BYTES = (EARLY && CF > 0) ? SLOTS * 2 * 128 * 2 : 0;   // uint16 row indices of two tiles
+  static constexpr int SMEM_BYTES = W_BYTES + SLOTS * SLOT_BYTES + 1024 /*align*/ + 256 /*barriers*/ + ROWIDX_BYTES;
   static constexpr int TMEM_PER_SLOT = COMPACT ? 64 : ((C3 > C1 + C2) ? C3 : ((C1 + C2) > 128 ? C1 + C2 : 128));
   static_assert(!COMPACT || (C1 <= 64 && C2 <= 64 && C3 == 128), "COMPACT is the level-1 plan");
   static constexpr int THREADS = SLOTS * 128;
@@ -62,8 +70,13 @@ struct SaCfg {
 #ifndef PDF_SA_TS
 #define PDF_SA_TS 1
 #endif
-using Sa1Cfg = SaCfg<0, 64, 64, 128, 4, false, PDF_SA_TS != 0>;
-using Sa2Cfg = SaCfg<128, 128, 128, 256, 2, false, PDF_SA_TS != 0>;
+#ifndef PDF_SA_EARLY
+#define PDF_SA_EARLY 1
+#endif
+using Sa1Cfg = SaCfg<0, 64, 64, 128, 4, false, PDF_SA_TS != 0, PDF_SA_EARLY != 0>;
+using Sa2Cfg = SaCfg<128, 128, 128, 256, 2, false, PDF_SA_TS != 0, PDF_SA_EARLY != 0>;
+using Sa1CfgLate = SaCfg<0, 64, 64, 128, 4, false, PDF_SA_TS != 0, false>;        // PDF_SA_EARLY=0 at run time (A/B)
+using Sa2CfgLate = SaCfg<128, 128, 128, 256, 2, false, PDF_SA_TS != 0, false>;
 
 // One layer = (KB SW128 K-blocks x 4 K-steps) + 1 aux K-step, accumulating into d_tmem.
 template <int KB>
@@ -399,6 +412,249 @@ sa_mlp_max_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, cons
   if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
+// The same stage with the inputs of tile t+1 staged under the tail of tile t (Cfg::EARLY):
+//   * tile t covers neighbour rows [128 t, 128 t + 128) of the index array and output rows 2t, 2t+1 (two centroids
+//     per tile, n_centroids even), so the per-tile addresses need no division besides cloud = t / tiles_per_cloud;
+//   * geometry block double-buffered: the relative coordinates of tile t+1 are written right after layer 3 of tile
+//     t has been ISSUED (their raw coordinates were loaded an iteration earlier), not after its epilogue;
+//   * level 2: the bf16 feature rows of tile t+1 are copied (cp.async) into the operand tile the moment layer 3 of
+//     tile t has COMPLETED (nothing reads the tile any more), so the copies fly under the max epilogue; their
+//     row indices travel through a small shared array (thread = row writes, 16 threads per row read).
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+sa_mlp_max_early_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, const uint16_t* __restrict__ feat_bf16,
+                        const int32_t* __restrict__ idx, int n_centroids, const uint8_t* __restrict__ wpack,
+                        float* __restrict__ out, int64_t ld_out, int out_col0, int64_t n_tiles) {
+  static_assert(Cfg::EARLY && !Cfg::COMPACT, "early staging plan");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_w = smem;
+  uint8_t* s_slots = smem + Cfg::W_BYTES;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_slots + Cfg::SLOTS * Cfg::SLOT_BYTES);   // [0]=weights, [1+s]=slot
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
+  uint16_t* s_rowidx = reinterpret_cast<uint16_t*>(s_bar + 32);                           // [SLOTS][2][128] (level 2)
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int slot = tid >> 7, p = tid & 127;              // p: tile row (layers 1,2) / channel lane (layer 3)
+  const int wslot = warp & 3;                            // TMEM lane quarter of this warp
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_bar[0]), 1);
+    for (int s = 0; s < Cfg::SLOTS; ++s) mbar_init(smem_u32(&s_bar[1 + s]), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(s_tmem);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+
+  pdl_wait();                                            // on-chip set-up above; global memory from here on
+  pdl_trigger();
+  if (tid == 0) {                                        // resident weights: bulk copies on the TMA engine
+    mbar_expect_tx(smem_u32(&s_bar[0]), Cfg::W_BYTES);
+    for (int off = 0; off < Cfg::W_BYTES; off += 32768) {
+      const int n = (Cfg::W_BYTES - off) < 32768 ? (Cfg::W_BYTES - off) : 32768;
+      bulk_g2s(smem_u32(s_w + off), wpack + off, n, smem_u32(&s_bar[0]));
+    }
+  }
+
+  const uint32_t sa_feat = smem_u32(s_slots + slot * Cfg::SLOT_BYTES);
+  const uint32_t sa_aux0 = sa_feat + Cfg::SLOT_FEAT;     // two geometry blocks of 4 KB
+  const uint32_t sw = smem_u32(s_w);
+  const uint32_t bar = smem_u32(&s_bar[1 + slot]);
+  const uint32_t d_base = tmem_base + slot * Cfg::TMEM_PER_SLOT;
+  const uint32_t lane_off = ((uint32_t)(wslot * 32)) << 16;
+  const uint32_t d1 = d_base, d2 = d_base + Cfg::C1, d3 = d_base;
+  uint16_t* my_rowidx = s_rowidx + slot * 256;
+  uint32_t phase = 0;
+  const uint32_t tiles_per_cloud = (uint32_t)(n_centroids >> 1);
+  const bool pow2 = (tiles_per_cloud & (tiles_per_cloud - 1)) == 0;
+  const int tshift = 31 - __clz((int)tiles_per_cloud);
+  const int64_t cloud_pitch = (int64_t)n_src * ld_pts;
+  const bool feat16 = Cfg::CF > 0 && feat_bf16 != nullptr;
+  // cloud of tile t and its first centroid (n_tiles < 2^31, checked by the launcher)
+  auto cloud_of = [&](uint32_t t) -> uint32_t { return pow2 ? (t >> tshift) : (t / tiles_per_cloud); };
+  // raw coordinates of this thread's neighbour row and of its centroid, tile t
+  auto load_raw = [&](uint32_t t, int j, float& s0, float& s1, float& s2, float& c0, float& c1, float& c2) {
+    const uint32_t b = cloud_of(t);
+    const uint32_t g = ((t - b * tiles_per_cloud) << 1) + (uint32_t)(p >> 6);
+    const float* cloud = pts + (int64_t)b * cloud_pitch;
+    const float* src = cloud + (int64_t)j * ld_pts;
+    const float* cen = cloud + (int64_t)g * ld_pts;
+    s0 = __ldg(src); s1 = __ldg(src + 1); s2 = __ldg(src + 2);
+    c0 = __ldg(cen); c1 = __ldg(cen + 1); c2 = __ldg(cen + 2);
+  };
+  // geometry / bias block of one tile (thread = row) + the centroid's leading output columns
+  auto write_aux = [&](uint32_t aux, uint32_t t, float s0, float s1, float s2, float c0, float c1, float c2) {
+    // p_j - c_i in fp32, the reference's operand order (utils.py:142-143)
+    const float rx = __fsub_rn(s0, c0), ry = __fsub_rn(s1, c1), rz = __fsub_rn(s2, c2);
+    if ((p & 63) == 0 && out_col0 > 0) {
+      float* o = out + ((int64_t)t * 2 + (p >> 6)) * ld_out;
+      o[0] = c0;
+      if (out_col0 > 1) o[1] = c1;
+      if (out_col0 > 2) o[2] = c2;
+      if (out_col0 > 3) o[3] = 0.f;
+    }
+    const float hx = __uint_as_float(pack_bf16(rx, 0.f) << 16), hy = __uint_as_float(pack_bf16(ry, 0.f) << 16),
+                hz = __uint_as_float(pack_bf16(rz, 0.f) << 16);
+    uint4 w;
+    w.x = pack_bf16(hx, hy);
+    w.y = pack_bf16(hz, 1.f);
+    w.z = pack_bf16(rx - hx, ry - hy);
+    w.w = pack_bf16(rz - hz, 1.f);
+    st_shared_v4(aux + aux_off(p, 0), w);
+    st_shared_v4(aux + aux_off(p, 8), make_uint4(0, 0, 0, 0));
+  };
+  // bf16 feature rows (256 B each) of tile t: 16 consecutive threads copy one row with cp.async (LDGSTS, no
+  // register staging), 8 rows per step, straight into the SW128 operand tile; row indices from shared memory
+  auto issue_features = [&](uint32_t t, const uint16_t* rowidx) {
+    const uint16_t* fcloud = feat_bf16 + (int64_t)cloud_of(t) * n_src * (int64_t)Cfg::CF;
+    const int ch = p & 15;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int row = i * 8 + (p >> 4);
+      const int j = rowidx[row];
+      const uint32_t dst = sa_feat + (ch >> 3) * (128 * 128) + sw128_off(row, (ch & 7) * 8);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(fcloud + (int64_t)j * Cfg::CF + ch * 8)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  mbar_wait(smem_u32(&s_bar[0]), 0);                     // weights resident
+
+  const uint32_t t_first = blockIdx.x * Cfg::SLOTS + slot, t_step = gridDim.x * Cfg::SLOTS;
+  const uint32_t nt = (uint32_t)n_tiles;
+  // invariants at the top of iteration t: geometry block [buf] = tile t (and, level 2, its feature rows are in
+  // the operand tile); (s*, c*) = raw coordinates of tile t+1; j_next = this row's neighbour index of tile t+2
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  int j_next = 0;
+  if (t_first < nt) {
+    const int j0 = __ldg(idx + (int64_t)t_first * 128 + p);
+    load_raw(t_first, j0, s0, s1, s2, c0, c1, c2);
+    write_aux(sa_aux0, t_first, s0, s1, s2, c0, c1, c2);
+    if (feat16) {
+      my_rowidx[p] = (uint16_t)j0;
+      named_bar_sync(1 + slot, 128);
+      issue_features(t_first, my_rowidx);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    if (t_first + t_step < nt) {
+      j_next = __ldg(idx + (int64_t)(t_first + t_step) * 128 + p);
+      if (feat16) my_rowidx[128 + p] = (uint16_t)j_next;
+      load_raw(t_first + t_step, j_next, s0, s1, s2, c0, c1, c2);
+    }
+    if (t_first + 2 * t_step < nt) j_next = __ldg(idx + (int64_t)(t_first + 2 * t_step) * 128 + p);
+  }
+
+  uint32_t buf = 0;
+  for (uint32_t t = t_first; t < nt; t += t_step) {
+    const uint32_t sa_aux = sa_aux0 + buf * (128 * 32);
+    const bool has_next = t + t_step < nt;
+    if (Cfg::CF > 0 && !feat16) {
+      // fp32 source rows [xyz, pad, 128 features]: one warp per row, lane l loads float4 #l (coalesced 512 B) and
+      // stores 4 bf16 into the SW128 tile.  (Legacy input form: staged here, not early.)
+      const int lane = tid & 31;
+      const float* cloud = pts + (int64_t)cloud_of(t) * cloud_pitch;
+      const int32_t* tidx = idx + (int64_t)t * 128;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const int row = wslot * 32 + r;
+        const int j = tidx[row];
+        const float4 f = __ldg(reinterpret_cast<const float4*>(cloud + (int64_t)j * ld_pts + 4) + lane);
+        uint2 w;
+        w.x = pack_bf16(f.x, f.y);
+        w.y = pack_bf16(f.z, f.w);
+        const int col = lane * 4;
+        st_shared_v2(sa_feat + (col >> 6) * (128 * 128) + sw128_off(row, col & 63), w);
+      }
+    }
+    fence_async_smem();
+    fence_before_sync();                                 // previous tile's TMEM reads are complete
+    named_bar_sync(1 + slot, 128);
+
+    // ---- layer 1: D1[p, c1] = X[p, :] . W1[c1, :] ----
+    if (p == 0) {
+      fence_after_sync();
+      issue_layer<Cfg::KB1>(sa_feat, 128 * 128, sa_aux, sw, Cfg::C1 * 128, sw + Cfg::OFF_W1A, d1,
+                            idesc_bf16(128, Cfg::C1));
+      commit(bar);
+    }
+    mbar_wait(bar, phase); phase ^= 1;
+    fence_after_sync();
+    if (Cfg::TS) {
+      epilogue_repack_tmem<Cfg::C1>(d1 + lane_off);      // H1 stays in tensor memory (in place over D1)
+    } else {
+      epilogue_repack<Cfg::C1>(d1 + lane_off, sa_feat, p);
+      fence_async_smem();
+    }
+    fence_before_sync();
+    named_bar_sync(1 + slot, 128);
+
+    // ---- layer 2: D2[p, c2] = H1[p, :] . W2[c2, :] ----
+    if (p == 0) {
+      fence_after_sync();
+      if (Cfg::TS)
+        issue_layer_ts<Cfg::KB2>(d1, sw + Cfg::OFF_W2, Cfg::C2 * 128, sw + Cfg::OFF_W2A, d2, idesc_bf16(128, Cfg::C2));
+      else
+        issue_layer<Cfg::KB2>(sa_feat, 128 * 128, sa_aux, sw + Cfg::OFF_W2, Cfg::C2 * 128, sw + Cfg::OFF_W2A, d2,
+                              idesc_bf16(128, Cfg::C2));
+      commit(bar);
+    }
+    mbar_wait(bar, phase); phase ^= 1;
+    fence_after_sync();
+    epilogue_repack<Cfg::C2>(d2 + lane_off, sa_feat, p);
+    fence_async_smem();
+    fence_before_sync();
+    named_bar_sync(1 + slot, 128);
+
+    // ---- layer 3 (transposed): D3[c3, p] = W3[c3, :] . H2[p, :] ; max over each 64-point group ----
+    if (p == 0) {
+      fence_after_sync();
+#pragma unroll
+      for (int h = 0; h < Cfg::C3 / 128; ++h)
+        issue_layer<Cfg::KB3>(sw + Cfg::OFF_W3 + h * (128 * 128), Cfg::C3 * 128, sw + Cfg::OFF_W3A + h * (128 * 32),
+                              sa_feat, 128 * 128, sa_aux, d3 + h * 128, idesc_bf16(128, 128));
+      commit(bar);
+    }
+    // ---- under layer 3: geometry of tile t+1 into the other block; raw coordinates of t+2, index of t+3 ----
+    if (has_next) write_aux(sa_aux0 + (buf ^ 1) * (128 * 32), t + t_step, s0, s1, s2, c0, c1, c2);
+    if (t + 2 * t_step < nt) {
+      if (feat16) my_rowidx[buf * 128 + p] = (uint16_t)j_next;      // rows of tile t+2 (block [buf] is free: tile t's were read an iteration ago)
+      load_raw(t + 2 * t_step, j_next, s0, s1, s2, c0, c1, c2);
+    }
+    if (t + 3 * t_step < nt) j_next = __ldg(idx + (int64_t)(t + 3 * t_step) * 128 + p);
+    mbar_wait(bar, phase); phase ^= 1;
+    fence_after_sync();
+    // layer 3 no longer reads the operand tile: the feature rows of tile t+1 land under the max epilogue
+    if (feat16 && has_next) issue_features(t + t_step, my_rowidx + (buf ^ 1) * 128);
+#pragma unroll
+    for (int h = 0; h < Cfg::C3 / 128; ++h) {
+      float m[2] = {0.f, 0.f};                           // ReLU floor
+#pragma unroll
+      for (int cc = 0; cc < 128; cc += 32) {
+        uint32_t v[32];
+        tmem_ld32(d3 + lane_off + h * 128 + cc, v);
+        tmem_ld_wait();
+        float mm = m[cc >> 6];
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) mm = max3(mm, __uint_as_float(v[q]), __uint_as_float(v[q + 1]));
+        m[cc >> 6] = mm;
+      }
+      float* o = out + (int64_t)t * 2 * ld_out + out_col0 + h * 128 + p;
+      o[0] = m[0];
+      o[ld_out] = m[1];
+    }
+    if (feat16) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    buf ^= 1;
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
 // ---- host-side weight packer -------------------------------------------------------------------
 static inline uint16_t f2bf(float f) {                   // round-to-nearest-even
   uint32_t u;
@@ -451,10 +707,11 @@ template <class Cfg>
 static int launch_sa(const float* pts, int64_t n_clouds, int n_src, int64_t ld_pts, const void* feat_bf16,
                      const int32_t* idx, int n_centroids, const void* wpack, float* out, int64_t ld_out, int out_col0,
                      cudaStream_t stream) {
+  auto kernel = sa_mlp_max_kernel<Cfg>;
+  if constexpr (Cfg::EARLY) kernel = sa_mlp_max_early_kernel<Cfg>;
   static PerDeviceOnce once;            // one flag array per template instantiation
   if (once.first()) {
-    cudaError_t e = cudaFuncSetAttribute(sa_mlp_max_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("pdf_sa_mlp_max_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return PDF_ERR_CUDA;
@@ -470,7 +727,7 @@ static int launch_sa(const float* pts, int64_t n_clouds, int n_src, int64_t ld_p
   }
   int64_t grid = (n_tiles + Cfg::SLOTS - 1) / Cfg::SLOTS;
   if (grid > sms) grid = sms;
-  launch_pdl(sa_mlp_max_kernel<Cfg>, dim3((unsigned)grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, stream, pts, n_src,
+  launch_pdl(kernel, dim3((unsigned)grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, stream, pts, n_src,
              ld_pts, reinterpret_cast<const uint16_t*>(feat_bf16), idx, n_centroids,
              reinterpret_cast<const uint8_t*>(wpack), out, ld_out, out_col0, n_tiles);
   return check_launch("pdf_sa_mlp_max_bf16");
@@ -512,8 +769,15 @@ extern "C" int pdf_sa_mlp_max_bf16(const float* pts, int64_t n_clouds, int n_src
   PDF_REQUIRE(ld_out >= out_col0 + c3, PDF_ERR_BAD_ARG, "pdf_sa_mlp_max_bf16: ld_out too small");
   if (n_clouds == 0) return PDF_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  // early staging of the next tile (default); PDF_SA_EARLY=0 keeps the round-1 schedule for A/B timing.  The early
+  // level-2 plan passes row indices through 16-bit shared cells.
+  static const bool early_env = !(getenv("PDF_SA_EARLY") && atoi(getenv("PDF_SA_EARLY")) == 0);
+  const bool early = early_env && n_src <= 65536;
   if (c_in == 3 && c1 == 64 && c2 == 64 && c3 == 128) {
     PDF_REQUIRE(ld_pts >= 3, PDF_ERR_BAD_ARG, "pdf_sa_mlp_max_bf16: ld_pts too small");
+    if (!early)
+      return pdf::launch_sa<pdf::Sa1CfgLate>(pts, n_clouds, n_src, ld_pts, nullptr, idx, n_centroids, wpack, out, ld_out,
+                                             out_col0, s);
     return pdf::launch_sa<pdf::Sa1Cfg>(pts, n_clouds, n_src, ld_pts, nullptr, idx, n_centroids, wpack, out, ld_out,
                                        out_col0, s);
   }
@@ -521,6 +785,9 @@ extern "C" int pdf_sa_mlp_max_bf16(const float* pts, int64_t n_clouds, int n_src
     PDF_REQUIRE(feat_bf16 != nullptr ? ld_pts >= 3 : (ld_pts >= 132 && (ld_pts % 4) == 0), PDF_ERR_UNSUPPORTED,
                 "pdf_sa_mlp_max_bf16: level-2 source rows must be [xyz,pad,128 features] with pitch %% 4 == 0 "
                 "unless the features are given as bf16 rows");
+    if (!early)
+      return pdf::launch_sa<pdf::Sa2CfgLate>(pts, n_clouds, n_src, ld_pts, feat_bf16, idx, n_centroids, wpack, out, ld_out,
+                                             out_col0, s);
     return pdf::launch_sa<pdf::Sa2Cfg>(pts, n_clouds, n_src, ld_pts, feat_bf16, idx, n_centroids, wpack, out, ld_out,
                                        out_col0, s);
   }

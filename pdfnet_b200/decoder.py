@@ -351,9 +351,17 @@ class decoder(nn.Module):
         q, k, v = qkv[:, :f], qkv[:, f:2 * f], qkv[:, 2 * f:]
         # R2L (left queries, right keys / values) and L2R in one launch, then the shared fc on the stacked result
         feat = self._attention_fc([(q[:M], k[M:], v[M:]), (q[M:], k[:M], v[:M])], n, V, a.fc)
+        # the two feed-forward tails are independent again: the right hand's goes to the side stream (forked here,
+        # before the left hand's kernels are queued, and NOT joined - the right hand stays there for the next level)
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            x4r, h4r, h4r_img = self._ln_for_gemm(Rf, feat[M:], self._ln(a.ffR.layer_norm), True)
+            outR = (x4r, self._mlp(h4r, a.ffR, h4r_img, M))
+        for t in (Rf, feat):
+            t.record_stream(self._side)
         x4l, h4l, h4l_img = self._ln_for_gemm(Lf, feat[:M], self._ln(a.ffL.layer_norm), True)
-        x4r, h4r, h4r_img = self._ln_for_gemm(Rf, feat[M:], self._ln(a.ffR.layer_norm), True)
-        return (x4l, self._mlp(h4l, a.ffL, h4l_img, M)), (x4r, self._mlp(h4r, a.ffR, h4r_img, M))
+        return (x4l, self._mlp(h4l, a.ffL, h4l_img, M)), outR
 
     def _level_input(self, a, b, rowvec, V_out, up):
         """Input of a DualGraph level (sum + position embedding, x2 up-sampled): it only feeds the first GEMM of
@@ -389,9 +397,11 @@ class decoder(nn.Module):
                 self._side = torch.cuda.Stream()
             for li, V in enumerate(self.verts):
                 # the two hands are independent up to the cross attention: the right hand's GraphLayer and
-                # SelfAttn run on a second stream (captured as a fork / join inside a CUDA graph)
+                # SelfAttn run on a second stream (captured as a fork / join inside a CUDA graph); from the
+                # cross attention of level 0 on the right hand's tensors are produced there (_inter_attn)
                 att = self.dual_gcn.layers[li].attn
-                self._side.wait_stream(cur)
+                if li == 0:
+                    self._side.wait_stream(cur)
                 with torch.cuda.stream(self._side):
                     xr = self._graph_layer(x["right"][0], x["right"][1], li, "right", V, B * V)
                     r2, rf = self._self_attn(xr, li, "R", att.R_self_attn_layer, B, V)
@@ -400,16 +410,20 @@ class decoder(nn.Module):
                 cur.wait_stream(self._side)
                 for t in (r2, rf):
                     t.record_stream(cur)
-                (al, bl), (ar, br) = self._inter_attn(l2, lf, r2, rf, li, B, V)
+                (al, bl), (ar, br) = self._inter_attn(l2, lf, r2, rf, li, B, V)   # (ar, br): on the side stream
                 if li != 2:                                    # add + graph_upsample(., 2) + next position embedding
                     pos = self.dual_gcn.layers[li + 1].position_embeddings.weight.detach()
                     x["left"] = self._level_input(al, bl, pos, 2 * V, 2)
-                    x["right"] = self._level_input(ar, br, pos, 2 * V, 2)
+                    with torch.cuda.stream(self._side):
+                        x["right"] = self._level_input(ar, br, pos, 2 * V, 2)
                 else:
                     # both hands' final features stacked: the output heads are shared modules -> one pass for both
                     fboth = torch.empty((2, B * V, self.gcn_out_dim[-1]), dtype=torch.float32, device=al.device)
                     ops.row_combine(al, bl, V_out=V, sum_out=fboth[0])
-                    ops.row_combine(ar, br, V_out=V, sum_out=fboth[1])
+                    fboth.record_stream(self._side)
+                    with torch.cuda.stream(self._side):
+                        ops.row_combine(ar, br, V_out=V, sum_out=fboth[1])
+                    cur.wait_stream(self._side)                # join: the output heads read both halves
             V, fo = self.verts[2], self.gcn_out_dim[-1]
             scale, trans2d, root, verts3d, verts2d = {}, {}, {}, {}, {}
             result = {"verts3d": {}, "verts2d": {}}

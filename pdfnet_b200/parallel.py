@@ -6,6 +6,7 @@ reference's DistributedSampler/DDP setup does (main.py:69-79); nothing is
 exchanged on the data path.  ``gather_results`` exists for callers that want the
 full result on every rank and for the world_size-2 gloo tests.
 """
+import ctypes
 import os
 
 import torch
@@ -59,3 +60,47 @@ def max_over_ranks(value, device):
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ---- host staging buffers -------------------------------------------------------------------------
+_cudart = None
+_host_allocs = []            # (pointer, nbytes): kept for the life of the process (staging buffers are long-lived)
+
+
+def pinned_like(t, write_combined=True):
+    """A page-locked HOST copy of ``t`` (same shape, strides and memory format) for host->device staging.
+
+    write_combined=True allocates with ``cudaHostAllocWriteCombined``: the pages are not snooped by the CPU
+    caches while the GPU's copy engine reads them, which is what one wants for buffers the CPU only ever WRITES
+    (inputs waiting for their ``copy_(non_blocking=True)``) when several GPUs pull from the same host memory
+    (bench.py e2e at N > 1).  CPU READS of such a buffer are slow - never use it for results.  Falls back to
+    ``Tensor.pin_memory()`` when the CUDA runtime library cannot be loaded (and returns ``t`` itself in a CPU-only
+    process)."""
+    global _cudart
+    if not torch.cuda.is_available():
+        return t                                         # CPU-only process: nothing to page-lock for
+    if not write_combined:
+        return t.pin_memory()
+    try:
+        if _cudart is None:
+            _cudart = ctypes.CDLL("libcudart.so.12")
+    except OSError:
+        try:
+            _cudart = ctypes.CDLL("libcudart.so")
+        except OSError:
+            return t.pin_memory()
+    src = t.detach()
+    if not (src.is_contiguous() or src.is_contiguous(memory_format=torch.channels_last)):
+        src = src.contiguous()
+    nbytes = max(1, src.numel() * src.element_size())
+    ptr = ctypes.c_void_p()
+    # portable (1) | write-combined (4)
+    rc = _cudart.cudaHostAlloc(ctypes.byref(ptr), ctypes.c_size_t(nbytes), ctypes.c_uint(1 | 4))
+    if rc != 0 or not ptr.value:
+        return t.pin_memory()
+    _host_allocs.append((ptr.value, nbytes))
+    raw = (ctypes.c_uint8 * nbytes).from_address(ptr.value)
+    flat = torch.frombuffer(raw, dtype=torch.uint8, count=nbytes).view(src.dtype)
+    out = torch.as_strided(flat, src.shape, src.stride())
+    out.copy_(src)
+    return out
