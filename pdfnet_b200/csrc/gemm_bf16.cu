@@ -74,7 +74,9 @@ __global__ void __launch_bounds__(G_THREADS, LIGHT ? 2 : 1) gemm_bf16_kernel(con
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_STAGES * 2 * G_BLOCK);
   // bars: [0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * G_STAGES + 4);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role branches are uniform branches and everything the
+  // MMA warp derives from uniform values (stage, accumulator column, descriptors) stays in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const bool dual = LIGHT ? false : P.kb_split > 0;          // LIGHT: single accumulator, no xyz side channel (compile-time)
   const int acc_cols = dual ? 256 : 128;
 
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(G_THREADS, LIGHT ? 2 : 1) gemm_bf16_kernel(con
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
   const int per_batch = P.m_tiles * P.n_tiles;
   const int n_work = per_batch * P.batches;
 
@@ -124,29 +126,34 @@ __global__ void __launch_bounds__(G_THREADS, LIGHT ? 2 : 1) gemm_bf16_kernel(con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
-      const uint32_t idesc = idesc_bf16(128, 128);
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        mbar_wait(smem_u32(&bars[2 * G_STAGES + 2 + as]), aphase ^ 1);
+    // the WHOLE warp runs the loop (uniform control flow, all operands in uniform registers); lane 0 alone issues
+    // the MMAs and their commits
+    int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+    const uint32_t idesc = idesc_bf16(128, 128);
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      mbar_wait(smem_u32(&bars[2 * G_STAGES + 2 + as]), aphase ^ 1);
+      fence_after_sync();
+      const uint32_t acc = tmem_base + as * acc_cols;
+      for (int kb = 0; kb < P.KB; ++kb) {
+        mbar_wait(smem_u32(&bars[stage]), phase);
         fence_after_sync();
-        const uint32_t acc = tmem_base + as * acc_cols;
-        for (int kb = 0; kb < P.KB; ++kb) {
-          mbar_wait(smem_u32(&bars[stage]), phase);
-          fence_after_sync();
-          const uint32_t sm = smem_u32(smem + stage * 2 * G_BLOCK), sn = sm + G_BLOCK;
-          const bool second = dual && kb >= P.kb_split;
-          const uint32_t d = acc + (second ? 128 : 0);
-          const bool first_kb = second ? (kb == P.kb_split) : (kb == 0);
+        const uint32_t sm = smem_u32(smem + stage * 2 * G_BLOCK), sn = sm + G_BLOCK;
+        const bool second = dual && kb >= P.kb_split;
+        const uint32_t d = acc + (second ? 128 : 0);
+        const bool first_kb = second ? (kb == P.kb_split) : (kb == 0);
+        if (lane == 0) {
+          const uint64_t da = desc_sw128(sm), db = desc_sw128(sn);     // +32 B per K step = +2 in the address field
 #pragma unroll
           for (int k16 = 0; k16 < 4; ++k16)
-            mma_bf16(d, desc_sw128(sm + k16 * 32), desc_sw128(sn + k16 * 32), idesc, !(first_kb && k16 == 0));
+            mma_bf16(d, da + 2 * k16, db + 2 * k16, idesc, !(first_kb && k16 == 0));
           commit(smem_u32(&bars[G_STAGES + stage]));
-          if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
         }
-        commit(smem_u32(&bars[2 * G_STAGES + as]));
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        __syncwarp();
+        if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
       }
+      if (lane == 0) commit(smem_u32(&bars[2 * G_STAGES + as]));
+      __syncwarp();
+      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else if (!COLMAX || warp < 6) {
     const int q4 = warp & 3;                               // TMEM lane quarter of this warp

@@ -424,7 +424,7 @@ template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 sa_mlp_max_early_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts, const uint16_t* __restrict__ feat_bf16,
                         const int32_t* __restrict__ idx, int n_centroids, const uint8_t* __restrict__ wpack,
-                        float* __restrict__ out, int64_t ld_out, int out_col0, int64_t n_tiles) {
+                        float* __restrict__ out, int64_t ld_out, int out_col0, int64_t n_tiles, int early_feat) {
   static_assert(Cfg::EARLY && !Cfg::COMPACT, "early staging plan");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -434,8 +434,12 @@ sa_mlp_max_early_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
   uint16_t* s_rowidx = reinterpret_cast<uint16_t*>(s_bar + 32);                           // [SLOTS][2][128] (level 2)
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int slot = tid >> 7, p = tid & 127;              // p: tile row (layers 1,2) / channel lane (layer 3)
+  const int tid = threadIdx.x;
+  // warp and slot indices through a shuffle: the compiler then KNOWS they are warp-uniform and keeps every address
+  // derived from them (operand tiles, barriers, tensor-memory columns) in uniform registers - the tcgen05 operands
+  // need no per-instruction R2UR / elect waterfall, which kept the K = 16 steps of layer 2 issue-bound
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int slot = warp >> 2, p = tid & 127;             // p: tile row (layers 1,2) / channel lane (layer 3)
   const int wslot = warp & 3;                            // TMEM lane quarter of this warp
 
   if (tid == 0) {
@@ -503,8 +507,8 @@ sa_mlp_max_early_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts
     w.y = pack_bf16(hz, 1.f);
     w.z = pack_bf16(rx - hx, ry - hy);
     w.w = pack_bf16(rz - hz, 1.f);
-    st_shared_v4(aux + aux_off(p, 0), w);
-    st_shared_v4(aux + aux_off(p, 8), make_uint4(0, 0, 0, 0));
+    st_shared_v4(aux + aux_off(p, 0), w);                // columns 8..15 of the block stay zero (written once below)
+    fence_async_smem();                                  // visible to the tensor core's (async-proxy) operand reads
   };
   // bf16 feature rows (256 B each) of tile t: 16 consecutive threads copy one row with cp.async (LDGSTS, no
   // register staging), 8 rows per step, straight into the SW128 operand tile; row indices from shared memory
@@ -522,6 +526,8 @@ sa_mlp_max_early_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
+  st_shared_v4(sa_aux0 + aux_off(p, 8), make_uint4(0, 0, 0, 0));             // zero half of both geometry blocks
+  st_shared_v4(sa_aux0 + 128 * 32 + aux_off(p, 8), make_uint4(0, 0, 0, 0));
   mbar_wait(smem_u32(&s_bar[0]), 0);                     // weights resident
 
   const uint32_t t_first = blockIdx.x * Cfg::SLOTS + slot, t_step = gridDim.x * Cfg::SLOTS;
@@ -570,7 +576,11 @@ sa_mlp_max_early_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts
         st_shared_v2(sa_feat + (col >> 6) * (128 * 128) + sw128_off(row, col & 63), w);
       }
     }
-    fence_async_smem();
+    if (feat16 && !early_feat && t != t_first) {         // late plan: the copies sit at the top of the iteration
+      issue_features(t, my_rowidx + buf * 128);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    if (Cfg::CF > 0) fence_async_smem();                 // feature rows (the geometry block was fenced when written)
     fence_before_sync();                                 // previous tile's TMEM reads are complete
     named_bar_sync(1 + slot, 128);
 
@@ -628,25 +638,47 @@ sa_mlp_max_early_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts
     mbar_wait(bar, phase); phase ^= 1;
     fence_after_sync();
     // layer 3 no longer reads the operand tile: the feature rows of tile t+1 land under the max epilogue
-    if (feat16 && has_next) issue_features(t + t_step, my_rowidx + (buf ^ 1) * 128);
+    if (feat16 && early_feat && has_next) issue_features(t + t_step, my_rowidx + (buf ^ 1) * 128);
 #pragma unroll
     for (int h = 0; h < Cfg::C3 / 128; ++h) {
-      float m[2] = {0.f, 0.f};                           // ReLU floor
+      float m[2];
 #pragma unroll
-      for (int cc = 0; cc < 128; cc += 32) {
-        uint32_t v[32];
-        tmem_ld32(d3 + lane_off + h * 128 + cc, v);
-        tmem_ld_wait();
-        float mm = m[cc >> 6];
+      for (int g = 0; g < 2; ++g) {                      // one 64-point group; independent max chains (ReLU floor = 0)
+        if constexpr (Cfg::THREADS <= 256) {             // register budget allows both 32-column loads in flight
+          uint32_t v[32], u[32];
+          tmem_ld32(d3 + lane_off + h * 128 + g * 64, v);
+          tmem_ld32(d3 + lane_off + h * 128 + g * 64 + 32, u);
+          tmem_ld_wait();
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-        for (int q = 0; q < 32; q += 2) mm = max3(mm, __uint_as_float(v[q]), __uint_as_float(v[q + 1]));
-        m[cc >> 6] = mm;
+          for (int q = 0; q < 32; q += 4) {
+            a0 = max3(a0, __uint_as_float(v[q]), __uint_as_float(v[q + 1]));
+            a1 = max3(a1, __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
+            a2 = max3(a2, __uint_as_float(u[q]), __uint_as_float(u[q + 1]));
+            a3 = max3(a3, __uint_as_float(u[q + 2]), __uint_as_float(u[q + 3]));
+          }
+          m[g] = fmaxf(max3(a0, a1, a2), a3);
+        } else {
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < 64; cc += 32) {
+            uint32_t v[32];
+            tmem_ld32(d3 + lane_off + h * 128 + g * 64 + cc, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) {
+              a0 = max3(a0, __uint_as_float(v[q]), __uint_as_float(v[q + 1]));
+              a1 = max3(a1, __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
+            }
+          }
+          m[g] = fmaxf(a0, a1);
+        }
       }
       float* o = out + (int64_t)t * 2 * ld_out + out_col0 + h * 128 + p;
       o[0] = m[0];
       o[ld_out] = m[1];
     }
-    if (feat16) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (feat16 && early_feat) asm volatile("cp.async.wait_group 0;" ::: "memory");
     buf ^= 1;
   }
 
@@ -707,11 +739,13 @@ template <class Cfg>
 static int launch_sa(const float* pts, int64_t n_clouds, int n_src, int64_t ld_pts, const void* feat_bf16,
                      const int32_t* idx, int n_centroids, const void* wpack, float* out, int64_t ld_out, int out_col0,
                      cudaStream_t stream) {
-  auto kernel = sa_mlp_max_kernel<Cfg>;
-  if constexpr (Cfg::EARLY) kernel = sa_mlp_max_early_kernel<Cfg>;
   static PerDeviceOnce once;            // one flag array per template instantiation
   if (once.first()) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e;
+    if constexpr (Cfg::EARLY)
+      e = cudaFuncSetAttribute(sa_mlp_max_early_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    else
+      e = cudaFuncSetAttribute(sa_mlp_max_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("pdf_sa_mlp_max_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return PDF_ERR_CUDA;
@@ -727,9 +761,18 @@ static int launch_sa(const float* pts, int64_t n_clouds, int n_src, int64_t ld_p
   }
   int64_t grid = (n_tiles + Cfg::SLOTS - 1) / Cfg::SLOTS;
   if (grid > sms) grid = sms;
-  launch_pdl(kernel, dim3((unsigned)grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, stream, pts, n_src,
-             ld_pts, reinterpret_cast<const uint16_t*>(feat_bf16), idx, n_centroids,
-             reinterpret_cast<const uint8_t*>(wpack), out, ld_out, out_col0, n_tiles);
+  if constexpr (Cfg::EARLY) {
+    // level-2 feature copies under the max epilogue (1) or at the top of the iteration (0, measured faster with the two
+    // slots of level 2: the early copies change how the slots' tensor phases interleave)
+    static const int early_feat = getenv("PDF_SA_EARLY_FEAT") ? atoi(getenv("PDF_SA_EARLY_FEAT")) : 0;
+    launch_pdl(sa_mlp_max_early_kernel<Cfg>, dim3((unsigned)grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, stream, pts,
+               n_src, ld_pts, reinterpret_cast<const uint16_t*>(feat_bf16), idx, n_centroids,
+               reinterpret_cast<const uint8_t*>(wpack), out, ld_out, out_col0, n_tiles, early_feat);
+  } else {
+    launch_pdl(sa_mlp_max_kernel<Cfg>, dim3((unsigned)grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, stream, pts, n_src,
+               ld_pts, reinterpret_cast<const uint16_t*>(feat_bf16), idx, n_centroids,
+               reinterpret_cast<const uint8_t*>(wpack), out, ld_out, out_col0, n_tiles);
+  }
   return check_launch("pdf_sa_mlp_max_bf16");
 }
 
