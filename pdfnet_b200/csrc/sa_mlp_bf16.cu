@@ -528,8 +528,6 @@ sa_mlp_max_early_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts
 
   st_shared_v4(sa_aux0 + aux_off(p, 8), make_uint4(0, 0, 0, 0));             // zero half of both geometry blocks
   st_shared_v4(sa_aux0 + 128 * 32 + aux_off(p, 8), make_uint4(0, 0, 0, 0));
-  mbar_wait(smem_u32(&s_bar[0]), 0);                     // weights resident
-
   const uint32_t t_first = blockIdx.x * Cfg::SLOTS + slot, t_step = gridDim.x * Cfg::SLOTS;
   const uint32_t nt = (uint32_t)n_tiles;
   // invariants at the top of iteration t: geometry block [buf] = tile t (and, level 2, its feature rows are in
@@ -553,6 +551,7 @@ sa_mlp_max_early_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts
     }
     if (t_first + 2 * t_step < nt) j_next = __ldg(idx + (int64_t)(t_first + 2 * t_step) * 128 + p);
   }
+  mbar_wait(smem_u32(&s_bar[0]), 0);                     // weights resident (their copy ran under the loads above)
 
   uint32_t buf = 0;
   for (uint32_t t = t_first; t < nt; t += t_step) {
