@@ -213,6 +213,17 @@ int pdf_gemm_bf16_batched(const void* m_img, int m_tiles, int m_kb, int64_t m_ba
                           int n_tiles, int n_kb, int64_t n_batch_stride, int KB, int batches, float* out_f32,
                           int64_t ld_out, int64_t out_batch_stride, int64_t rows_valid,
                           const int32_t* tile_desc_host, void* stream);
+/* ROW-mode GEMM for TWO groups of rows with their own weights and biases in ONE launch - the left and the right hand
+ * of the GCN decoder (intaghand_decoder.py:180-242: graph_left / graph_right, L_self_attn_layer / R_self_attn_layer,
+ * ffL / ffR have identical shapes and different parameters).  m_img holds 2 * group_m_tiles row tiles (every group
+ * padded to whole 128-row tiles), n_img / bias are the FIRST group's weight image / bias (padded to n_tiles * 128)
+ * and the second group's lie n_group_stride bytes / bias_group_stride floats further.  rows_valid counts inside each
+ * group; out_f32 / out_img cover all 2 * group_m_tiles * 128 rows.  act takes the PDF_GEMM_OUT_SPLIT / PDF_GEMM_LIGHT
+ * flags like pdf_gemm_bf16.  Single accumulator (no SFT / xyz / COLMAX modes). */
+int pdf_gemm_bf16_grouped(const void* m_img, int group_m_tiles, int m_kb, const void* n_img, int n_tiles, int n_kb,
+                          int64_t n_group_stride, int KB, const float* bias, int64_t bias_group_stride, int act,
+                          float* out_f32, int64_t ld_out, int64_t rows_valid, void* out_img, int out_kb,
+                          const int32_t* tile_desc_host, void* stream);
 /* Weight gradient straight from ROW tile images (no transposed copy): out[b][ca, cb] = sum over the rows of
  * batch b of A[r, ca] * B[r, cb], A / B = images of dY / X as written by pdf_rows_to_image (split = 1:
  * [hi|hi|lo], three products per fp32 product; split = 0: plain bf16).  The tensor core reads the K-major
@@ -431,6 +442,22 @@ int pdf_graph_cheby_ln(const float* U0, const float* U1, int64_t ldu, const floa
                        const float* bias_r, const int32_t* rowptr, const int32_t* colidx, const float* vals, int V,
                        int C, int64_t rows, const float* gamma, const float* beta, float eps, int relu, float* out,
                        int64_t ldo, void* out_img, void* stream);
+/* The two kernels above for TWO groups of rows (left / right hand) in one launch: every buffer holds
+ * 2 * rows_per_group rows (rows_per_group % 128 == 0 so that both groups start on a tile of the operand images; the
+ * first `valid` rows of each group are real, the rest is padding that is neither read nor written); per-channel
+ * parameters (bias, bias_r, gamma, beta) are stacked [2, C]; rowvec is shared (rowvec_gstride = 0) or stacked
+ * rowvec_gstride floats apart; group g reads its source rows from a / b rows [g * src_per_group, ...).
+ * C in {64, 128, 256, 512}, 16-byte aligned rows. */
+int pdf_row_combine_grouped(const float* a, int64_t lda, const float* b, int64_t ldb, const float* rowvec, int64_t ldr,
+                            int64_t rowvec_gstride, int V_out, int up, int C, int64_t rows_per_group, int64_t valid,
+                            int64_t src_per_group, const float* gamma, const float* beta, float eps, int relu,
+                            float* sum_out, int64_t lds, float* ln_out, int64_t ldl, void* sum_img, void* ln_img,
+                            void* stream);
+int pdf_graph_cheby_ln_grouped(const float* U0, const float* U1, int64_t ldu, const float* bias, const float* R,
+                               int64_t ldr, const float* bias_r, const int32_t* rowptr, const int32_t* colidx,
+                               const float* vals, int V, int C, int64_t rows_per_group, int64_t valid,
+                               const float* gamma, const float* beta, float eps, int relu, float* out, int64_t ldo,
+                               void* out_img, void* stream);
 /* softmax(q k^T / sqrt(d)) v per (sample, head) (self_attn.py:60-72, inter_attn.py:84-108); q/k/v/out
  * rows [n_samples*V, heads*d] with free pitches (q and k/v may come from different hands).
  * V <= 256, d in {16, 32, 64}. */

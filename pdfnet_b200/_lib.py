@@ -71,6 +71,12 @@ SIGNATURES = {
                         _i64, _vp, _vp, _vp],
     "pdf_graph_cheby_ln": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _f32, _i32,
                            _vp, _i64, _vp, _vp],
+    "pdf_gemm_bf16_grouped": [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i64, _vp, _i32,
+                              _vp, _vp],
+    "pdf_row_combine_grouped": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i64, _i64, _i64, _vp, _vp, _f32,
+                                _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp],
+    "pdf_graph_cheby_ln_grouped": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _vp, _vp,
+                                   _f32, _i32, _vp, _i64, _vp, _vp],
     "pdf_mha": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp],
     "pdf_decoder_heads": [_vp, _i64, _i64, _i32, _i32] + [_vp] * 12,
     "pdf_mha_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _vp],

@@ -233,21 +233,38 @@ __device__ __forceinline__ float4 f4_fma(float w, float4 u, float4 t) {
   return make_float4(fmaf(w, u.x, t.x), fmaf(w, u.y, t.y), fmaf(w, u.z, t.z), fmaf(w, u.w, t.w));
 }
 
+// Two groups of rows (the left and the right hand) in one launch: group g owns output rows
+// [g * rows_per_group, g * rows_per_group + valid) - rows_per_group is a multiple of 128 so both groups start on a tile
+// of the operand images - reads its sources from [g * src_per_group, ...) and its per-channel parameters (bias,
+// LayerNorm weights) / per-vertex rows `pstride` / `rowvec_gstride` floats after the first group's.  rows_per_group = 0: off.
+struct RowGroups {
+  int64_t rows_per_group, valid, src_per_group, pstride, rowvec_gstride;
+};
+
 template <int LPR, int VEC>
 __global__ void __launch_bounds__(256)
 row_combine_vec_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
                        const float* __restrict__ rowvec, int64_t ldr, int V_out, int up, int64_t rows_out,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
                        float* __restrict__ sum_out, int64_t lds, float* __restrict__ ln_out, int64_t ldl,
-                       uint8_t* __restrict__ sum_img, uint8_t* __restrict__ ln_img) {
+                       uint8_t* __restrict__ sum_img, uint8_t* __restrict__ ln_img, const RowGroups G) {
   pdl_wait();
   pdl_trigger();
   const int l = threadIdx.x % LPR;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
   if (r >= rows_out) return;                                   // whole LPR-lane groups leave together
-  const int64_t smp = r / V_out;
-  const int v = (int)(r - smp * V_out);
-  const int64_t src = smp * (V_out / up) + v / up;
+  int64_t rl = r, src0 = 0;
+  if (G.rows_per_group) {
+    const int g = r >= G.rows_per_group;
+    rl = r - g * G.rows_per_group;
+    if (rl >= G.valid) return;                                 // padding rows between / after the groups
+    src0 = g * G.src_per_group;
+    if (gamma) { gamma += g * G.pstride; beta += g * G.pstride; }
+    if (rowvec) rowvec += g * G.rowvec_gstride;
+  }
+  const int64_t smp = rl / V_out;
+  const int v = (int)(rl - smp * V_out);
+  const int64_t src = src0 + smp * (V_out / up) + v / up;
   float4 t[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
@@ -279,14 +296,23 @@ graph_cheby_ln_vec_kernel(const float* __restrict__ U0, const float* __restrict_
                           const float* __restrict__ bias_r, const int* __restrict__ rowptr,
                           const int* __restrict__ colidx, const float* __restrict__ vals, int V, int64_t rows,
                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
-                          float* __restrict__ out, int64_t ldo, uint8_t* __restrict__ out_img) {
+                          float* __restrict__ out, int64_t ldo, uint8_t* __restrict__ out_img, const RowGroups G) {
   pdl_wait();
   pdl_trigger();
   const int l = threadIdx.x % LPR;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
   if (r >= rows) return;
-  const int64_t smp = r / V;
-  const int v = (int)(r - smp * V);
+  int64_t rl = r, base = 0;
+  if (G.rows_per_group) {
+    const int g = r >= G.rows_per_group;
+    base = g * G.rows_per_group;
+    rl = r - base;
+    if (rl >= G.valid) return;
+    bias += g * G.pstride; gamma += g * G.pstride; beta += g * G.pstride;
+    if (bias_r) bias_r += g * G.pstride;
+  }
+  const int64_t smp = rl / V;
+  const int v = (int)(rl - smp * V);
   float4 t[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
@@ -301,7 +327,7 @@ graph_cheby_ln_vec_kernel(const float* __restrict__ U0, const float* __restrict_
   const int e0 = rowptr[v], e1 = rowptr[v + 1];
   for (int e = e0; e < e1; ++e) {
     const float w = __ldg(vals + e);
-    const float* u = U1 + (smp * V + __ldg(colidx + e)) * ldu;
+    const float* u = U1 + (base + smp * V + __ldg(colidx + e)) * ldu;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) t[i] = f4_fma(w, __ldg(reinterpret_cast<const float4*>(u + 4 * (l + LPR * i))), t[i]);
   }
@@ -543,7 +569,7 @@ extern "C" int pdf_row_combine(const float* a, int64_t lda, const float* b, int6
         constexpr int LPR = decltype(lpr)::value, VEC = decltype(vec)::value;
         const unsigned g = (unsigned)((rows_out * LPR + 255) / 256);
         launch_pdl(row_combine_vec_kernel<LPR, VEC>, dim3(g), dim3(256), 0, s, a, lda, b, ldb, rowvec, ldr, V_out, up, rows_out,
-                   gamma, beta, eps, relu, sum_out, lds, ln_out, ldl, (uint8_t*)sum_img, (uint8_t*)ln_img);
+                   gamma, beta, eps, relu, sum_out, lds, ln_out, ldl, (uint8_t*)sum_img, (uint8_t*)ln_img, RowGroups{0, 0, 0, 0, 0});
       }))
     return check_launch("pdf_row_combine");
   const unsigned grid = (unsigned)((rows_out * 32 + 255) / 256);
@@ -575,7 +601,7 @@ extern "C" int pdf_graph_cheby_ln(const float* U0, const float* U1, int64_t ldu,
         constexpr int LPR = decltype(lpr)::value, VEC = decltype(vec)::value;
         const unsigned g = (unsigned)((rows * LPR + 255) / 256);
         launch_pdl(graph_cheby_ln_vec_kernel<LPR, VEC>, dim3(g), dim3(256), 0, s, U0, U1, ldu, bias, R, ldr, bias_r, rowptr,
-                   colidx, vals, V, rows, gamma, beta, eps, relu, out, ldo, (uint8_t*)out_img);
+                   colidx, vals, V, rows, gamma, beta, eps, relu, out, ldo, (uint8_t*)out_img, RowGroups{0, 0, 0, 0, 0});
       }))
     return check_launch("pdf_graph_cheby_ln");
   const unsigned grid = (unsigned)((rows * 32 + 255) / 256);
@@ -587,6 +613,65 @@ extern "C" int pdf_graph_cheby_ln(const float* U0, const float* U1, int64_t ldu,
     return 0;
   });
   return check_launch("pdf_graph_cheby_ln");
+}
+
+// Grouped forms (two hands in one launch, see RowGroups): buffers hold 2 * rows_per_group rows (rows_per_group % 128
+// == 0, the first `valid` of each group are real); per-channel parameters are stacked [2, C] (pstride = C), the
+// per-vertex rows [2, V_out, ldr] when rowvec_gstride != 0.  Vectorised widths only (C in {64,128,256,512}).
+extern "C" int pdf_row_combine_grouped(const float* a, int64_t lda, const float* b, int64_t ldb, const float* rowvec,
+                                       int64_t ldr, int64_t rowvec_gstride, int V_out, int up, int C,
+                                       int64_t rows_per_group, int64_t valid, int64_t src_per_group, const float* gamma,
+                                       const float* beta, float eps, int relu, float* sum_out, int64_t lds,
+                                       float* ln_out, int64_t ldl, void* sum_img, void* ln_img, void* stream) {
+  if (valid == 0) return PDF_OK;
+  PDF_REQUIRE(a && (sum_out || ln_out || sum_img || ln_img), PDF_ERR_BAD_ARG, "pdf_row_combine_grouped: null pointer");
+  PDF_REQUIRE(rows_per_group > 0 && rows_per_group % 128 == 0 && valid > 0 && valid <= rows_per_group && V_out > 0 &&
+                  up >= 1 && V_out % up == 0 && valid % V_out == 0 && src_per_group >= valid / up &&
+                  (!(ln_out || ln_img) || (gamma && beta)) && (!(sum_img || ln_img) || C % 64 == 0),
+              PDF_ERR_BAD_ARG, "pdf_row_combine_grouped: bad argument");
+  const bool vec_ok = lda % 4 == 0 && (!b || ldb % 4 == 0) && (!rowvec || (ldr % 4 == 0 && rowvec_gstride % 4 == 0)) &&
+                      (!sum_out || lds % 4 == 0) && (!ln_out || ldl % 4 == 0) && aligned16(a) && aligned16(b) &&
+                      aligned16(rowvec) && aligned16(sum_out) && aligned16(ln_out) && aligned16(gamma) && aligned16(beta);
+  const int64_t rows_out = 2 * rows_per_group;
+  const RowGroups G{rows_per_group, valid, src_per_group, (int64_t)C, rowvec_gstride};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vec_ok && dispatch_vec(C, [&](auto lpr, auto vec) {
+        constexpr int LPR = decltype(lpr)::value, VEC = decltype(vec)::value;
+        const unsigned g = (unsigned)((rows_out * LPR + 255) / 256);
+        launch_pdl(row_combine_vec_kernel<LPR, VEC>, dim3(g), dim3(256), 0, s, a, lda, b, ldb, rowvec, ldr, V_out, up, rows_out,
+                   gamma, beta, eps, relu, sum_out, lds, ln_out, ldl, (uint8_t*)sum_img, (uint8_t*)ln_img, G);
+      }))
+    return check_launch("pdf_row_combine_grouped");
+  set_error("pdf_row_combine_grouped: needs C in {64,128,256,512} and 16-byte aligned rows (got C=%d)", C);
+  return PDF_ERR_UNSUPPORTED;
+}
+
+extern "C" int pdf_graph_cheby_ln_grouped(const float* U0, const float* U1, int64_t ldu, const float* bias, const float* R,
+                                          int64_t ldr, const float* bias_r, const int32_t* rowptr, const int32_t* colidx,
+                                          const float* vals, int V, int C, int64_t rows_per_group, int64_t valid,
+                                          const float* gamma, const float* beta, float eps, int relu, float* out,
+                                          int64_t ldo, void* out_img, void* stream) {
+  if (valid == 0) return PDF_OK;
+  PDF_REQUIRE(U0 && U1 && bias && rowptr && colidx && vals && gamma && beta && (out || out_img), PDF_ERR_BAD_ARG,
+              "pdf_graph_cheby_ln_grouped: null pointer");
+  PDF_REQUIRE(rows_per_group > 0 && rows_per_group % 128 == 0 && valid > 0 && valid <= rows_per_group && V > 0 &&
+                  valid % V == 0 && (!out_img || C % 64 == 0),
+              PDF_ERR_BAD_ARG, "pdf_graph_cheby_ln_grouped: bad argument");
+  const bool vec_ok = ldu % 4 == 0 && (!R || ldr % 4 == 0) && (!out || ldo % 4 == 0) && aligned16(U0) && aligned16(U1) &&
+                      aligned16(bias) && aligned16(R) && aligned16(bias_r) && aligned16(out) && aligned16(gamma) &&
+                      aligned16(beta);
+  const int64_t rows = 2 * rows_per_group;
+  const RowGroups G{rows_per_group, valid, 0, (int64_t)C, 0};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vec_ok && dispatch_vec(C, [&](auto lpr, auto vec) {
+        constexpr int LPR = decltype(lpr)::value, VEC = decltype(vec)::value;
+        const unsigned g = (unsigned)((rows * LPR + 255) / 256);
+        launch_pdl(graph_cheby_ln_vec_kernel<LPR, VEC>, dim3(g), dim3(256), 0, s, U0, U1, ldu, bias, R, ldr, bias_r, rowptr,
+                   colidx, vals, V, rows, gamma, beta, eps, relu, out, ldo, (uint8_t*)out_img, G);
+      }))
+    return check_launch("pdf_graph_cheby_ln_grouped");
+  set_error("pdf_graph_cheby_ln_grouped: needs C in {64,128,256,512} and 16-byte aligned rows (got C=%d)", C);
+  return PDF_ERR_UNSUPPORTED;
 }
 
 extern "C" int pdf_mha(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* Vv, int64_t ldv,

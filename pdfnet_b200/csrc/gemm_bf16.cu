@@ -52,6 +52,10 @@ struct GemmParams {
   // batched mode (split-K weight gradients): work item = (batch, m-tile, n-tile); operands and the
   // fp32 output advance by these strides per batch (bytes / floats)
   int batches; int64_t m_batch_stride, n_batch_stride, out_batch_stride;
+  // grouped mode (the two hands of the GCN decoder in ONE launch): row tiles [0, group_m_tiles) use the first weight
+  // image / bias, row tiles from group_m_tiles on the second (n_group_stride bytes / bias_group_stride floats further);
+  // rows_valid then counts inside each group of group_m_tiles * 128 rows.  0 = off.
+  int group_m_tiles; int64_t n_group_stride, bias_group_stride;
   int tile_col[G_MAX_NT];        // ROW mode, per N-tile: first fp32 column (F and out_f32)
   int tile_nvalid[G_MAX_NT];     //   valid output columns of this N-tile (others are written as 0 / skipped)
   int tile_okb[G_MAX_NT];        //   first k-block of this N-tile in the output image
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(G_THREADS, LIGHT ? 2 : 1) gemm_bf16_kernel(con
   if (!COLMAX) {
     for (int i = threadIdx.x; i < P.n_tiles * 128; i += G_THREADS) {
       s_bias[i] = P.bias0 ? P.bias0[i] : 0.f;
-      s_bias[G_MAX_NT * 128 + i] = dual ? P.bias1[i] : 0.f;
+      s_bias[G_MAX_NT * 128 + i] = dual ? P.bias1[i] : (P.group_m_tiles ? P.bias0[P.bias_group_stride + i] : 0.f);
     }
     if (xyz) for (int i = threadIdx.x; i < 390; i += G_THREADS) s_xyz[i] = P.xyz_w[i];
   }
@@ -112,7 +116,8 @@ __global__ void __launch_bounds__(G_THREADS, LIGHT ? 2 : 1) gemm_bf16_kernel(con
         const int bt = w / per_batch, wr = w - bt * per_batch;
         const int mt = wr / P.n_tiles, nt = wr % P.n_tiles;
         const uint8_t* mb = P.m_img + (size_t)bt * P.m_batch_stride + (size_t)mt * P.m_kb * G_BLOCK;
-        const uint8_t* nb = P.n_img + (size_t)bt * P.n_batch_stride + (size_t)nt * P.n_kb * G_BLOCK;
+        const uint8_t* nb = P.n_img + (size_t)bt * P.n_batch_stride + (size_t)nt * P.n_kb * G_BLOCK +
+                            ((P.group_m_tiles && mt >= P.group_m_tiles) ? (size_t)P.n_group_stride : 0);
         for (int kb = 0; kb < P.KB; ++kb) {
           mbar_wait(smem_u32(&bars[G_STAGES + stage]), phase ^ 1);
           const uint32_t full = smem_u32(&bars[stage]);
@@ -181,9 +186,10 @@ __global__ void __launch_bounds__(G_THREADS, LIGHT ? 2 : 1) gemm_bf16_kernel(con
         P.out_max[(int64_t)nt * P.ld_max + ch] = fmaxf(mx + P.bias0[ch], 0.f);
       } else {
         const int64_t m = (int64_t)mt * 128 + row;
-        const bool row_ok = m < P.rows_valid;
+        const bool grp1 = P.group_m_tiles && mt >= P.group_m_tiles;
+        const bool row_ok = (grp1 ? m - (int64_t)P.group_m_tiles * 128 : m) < P.rows_valid;
         const int col0 = P.tile_col[nt], nvalid = P.tile_nvalid[nt], okb = P.tile_okb[nt];
-        const uint32_t b0 = smem_u32(s_bias) + nt * 512;                    // shared addresses (explicit LDS)
+        const uint32_t b0 = smem_u32(s_bias) + nt * 512 + (grp1 ? G_MAX_NT * 512 : 0);   // shared addresses (explicit LDS)
         const uint32_t b1 = b0 + G_MAX_NT * 512;
         const uint32_t sxyz = smem_u32(s_xyz);
         const bool full = row_ok && nvalid == 128;           // fast path: no per-element masking
@@ -638,4 +644,64 @@ extern "C" int pdf_gemm_bf16_batched(const void* m_img, int m_tiles, int m_kb, i
   const int grid = (int)(n_work < sms ? n_work : sms);
   gemm_bf16_kernel<false><<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(P);
   return check_launch("pdf_gemm_bf16_batched");
+}
+
+// The same ROW-mode GEMM for TWO groups of rows with their own weights and biases in one launch (the left and the
+// right hand of the GCN decoder: identical shapes, different parameters): m_img holds 2 * group_m_tiles row tiles,
+// n_img / bias the first group's weight image / padded bias with the second group's n_group_stride bytes /
+// bias_group_stride floats further.  rows_valid counts inside each group.  Single accumulator, no SFT / xyz modes.
+extern "C" int pdf_gemm_bf16_grouped(const void* m_img, int group_m_tiles, int m_kb, const void* n_img, int n_tiles,
+                                     int n_kb, int64_t n_group_stride, int KB, const float* bias,
+                                     int64_t bias_group_stride, int act, float* out_f32, int64_t ld_out,
+                                     int64_t rows_valid, void* out_img, int out_kb, const int32_t* tile_desc_host,
+                                     void* stream) {
+  using namespace pdf;
+  if (group_m_tiles == 0 || n_tiles == 0) return PDF_OK;
+  PDF_REQUIRE(m_img && n_img && bias && tile_desc_host && (out_f32 || out_img), PDF_ERR_BAD_ARG,
+              "pdf_gemm_bf16_grouped: null pointer");
+  PDF_REQUIRE(group_m_tiles > 0 && n_tiles > 0 && n_tiles <= G_MAX_NT && KB > 0 && m_kb > 0 &&
+                  (KB <= m_kb || KB % m_kb == 0) && KB <= n_kb && n_group_stride >= 0 && bias_group_stride >= 0 &&
+                  rows_valid <= (int64_t)group_m_tiles * 128 && (!out_f32 || ld_out % 4 == 0),
+              PDF_ERR_BAD_ARG, "pdf_gemm_bf16_grouped: bad size");
+  const int out_split = (act & PDF_GEMM_OUT_SPLIT) ? 1 : 0;
+  static const int light_max_kb = getenv("PDF_GEMM_LIGHT_MAX_KB") ? atoi(getenv("PDF_GEMM_LIGHT_MAX_KB")) : 12;
+  const bool light = (act & PDF_GEMM_LIGHT) && KB <= light_max_kb;
+  act &= ~(PDF_GEMM_OUT_SPLIT | PDF_GEMM_LIGHT);
+  PDF_REQUIRE(act >= 0 && act <= 2, PDF_ERR_BAD_ARG, "pdf_gemm_bf16_grouped: bad activation");
+  PDF_REQUIRE(!out_split || (out_img && out_kb % 3 == 0), PDF_ERR_BAD_ARG,
+              "pdf_gemm_bf16_grouped: a split output image needs out_img with 3 x k-blocks");
+  GemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.out_split = out_split;
+  P.m_img = (const uint8_t*)m_img; P.n_img = (const uint8_t*)n_img;
+  P.m_kb = m_kb; P.n_kb = n_kb; P.m_tiles = 2 * group_m_tiles; P.n_tiles = n_tiles; P.KB = KB;
+  P.bias0 = bias; P.act = act;
+  P.out_f32 = out_f32; P.ld_out = ld_out; P.rows_valid = rows_valid;
+  P.out_img = (uint8_t*)out_img; P.out_kb = out_kb;
+  P.batches = 1;
+  P.group_m_tiles = group_m_tiles; P.n_group_stride = n_group_stride; P.bias_group_stride = bias_group_stride;
+  for (int i = 0; i < n_tiles; ++i) {
+    P.tile_col[i] = tile_desc_host[3 * i]; P.tile_nvalid[i] = tile_desc_host[3 * i + 1]; P.tile_okb[i] = tile_desc_host[3 * i + 2];
+    PDF_REQUIRE(P.tile_nvalid[i] >= 0 && P.tile_nvalid[i] <= 128 && (P.tile_col[i] % 4) == 0, PDF_ERR_BAD_ARG,
+                "pdf_gemm_bf16_grouped: bad tile descriptor %d", i);
+    PDF_REQUIRE(!out_img || P.tile_okb[i] + (P.tile_nvalid[i] + 63) / 64 <= (out_split ? out_kb / 3 : out_kb),
+                PDF_ERR_BAD_ARG, "pdf_gemm_bf16_grouped: output image too narrow");
+  }
+  static pdf::PerDeviceOnce once;
+  if (once.first()) {
+    cudaFuncSetAttribute(gemm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
+    cudaFuncSetAttribute(gemm_bf16_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_LIGHT);
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = P.m_tiles * n_tiles;
+  if (light) {
+    if (grid > 2 * sms) grid = 2 * sms;
+    launch_pdl(gemm_bf16_kernel<false, true>, dim3(grid), dim3(G_THREADS), (size_t)G_SMEM_LIGHT, (cudaStream_t)stream, P);
+  } else {
+    if (grid > sms) grid = sms;
+    launch_pdl(gemm_bf16_kernel<false, false>, dim3(grid), dim3(G_THREADS), (size_t)G_SMEM, (cudaStream_t)stream, P);
+  }
+  return check_launch("pdf_gemm_bf16_grouped");
 }

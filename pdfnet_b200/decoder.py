@@ -16,6 +16,8 @@ operands were measured and dropped: after ~40 chained layers the scale / transla
 (``csrc/gcn_decoder.cu``): Chebyshev graph term (sparse L) + bias + shortcut + LayerNorm + ReLU,
 residual + LayerNorm, attention, projection.  Inference only.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -192,6 +194,15 @@ class decoder(nn.Module):
             self.unsample_layer.weight.data.copy_(torch.as_tensor(np.asarray(assets["upsample"])))
         self._cache, self._cache_key = {}, None
         self._side = None
+        # both hands share one graph (true for the shipped gcn_core pickles): the grouped path can then run the two
+        # hands' Chebyshev kernels as one launch over one CSR
+        self._same_graph = all(np.array_equal(np.asarray(assets["L_left_%d" % i]), np.asarray(assets["L_right_%d" % i]))
+                               for i in range(3))
+        # Grouped path (both hands per launch) is OFF by default: measured on B200 at 128 frames it is SLOWER than the
+        # two-stream path (2.39 vs 2.16 ms per decoder pass) - the two streams' half-footprint GEMMs (two CTAs per SM)
+        # and glue kernels do overlap, while a grouped launch pays the L2-bound part of both hands back to back.
+        # PDF_DECODER_GROUPED=1 (or .grouped = True) selects it; tests keep both paths pinned to the reference.
+        self.grouped = os.environ.get("PDF_DECODER_GROUPED", "0") == "1"
 
     def get_upsample_weight(self):
         return self.unsample_layer.weight.data
@@ -371,6 +382,117 @@ class decoder(nn.Module):
             return None, s_img
         return ops.row_combine(a, b, rowvec=rowvec, V_out=V_out, up=up, want_sum=True)[0], None
 
+    # ---- grouped path: both hands as two row groups of every launch --------------------------------------------
+    # The left and the right hand run the same layers with different parameters (graph_left / graph_right,
+    # L_/R_self_attn_layer, ffL / ffR).  On two streams their kernels mostly serialise (each one fills the GPU), so
+    # every launch's fixed cost is paid twice.  Here the activations of both hands are stacked as two groups of Mp =
+    # ceil(B*V / 128) * 128 rows and every kernel takes both groups with their own parameters
+    # (pdf_gemm_bf16_grouped, pdf_graph_cheby_ln_grouped, pdf_row_combine_grouped, two problems per pdf_mha_tc):
+    # half the launches on ONE stream, same arithmetic per row as the two-stream path.
+    def _grouped_ok(self, B):
+        return (self.grouped and self.precision != "fp32" and self._same_graph and B * self.verts[0] >= 1024 and
+                self.gcn_in_dim[0] in (64, 128, 256, 512) and all(c in (64, 128, 256, 512) for c in self.gcn_out_dim) and
+                all(ci == co for ci, co in zip(self.gcn_in_dim[1:], self.gcn_out_dim[:-1])))
+
+    def _gpack(self, key, ws, bs):
+        key = ("gpack",) + tuple(key)
+        p = self._cache.get(key)
+        if p is None:
+            p = self._cache[key] = ops.pack_linear_tc_grouped([w.detach() for w in ws],
+                                                              [b.detach() if b is not None else None for b in bs])
+        return p
+
+    def _gstack(self, key, ts):
+        key = ("gstack",) + tuple(key)
+        p = self._cache.get(key)
+        if p is None:
+            p = self._cache[key] = torch.stack([t.detach() for t in ts]).contiguous()
+        return p
+
+    def _gln(self, key, ml, mr):
+        return (self._gstack(tuple(key) + ("g",), [ml.weight, mr.weight]), self._gstack(tuple(key) + ("b",), [ml.bias, mr.bias]))
+
+    def _glinear(self, key, ml, mr, x_img, Mp, M, act=L.ACT_NONE, out_image=False):
+        return ops.linear_tc_grouped(self._gpack(key, [ml.weight, mr.weight], [ml.bias, mr.bias]), x_img, Mp, M, act=act,
+                                     out_image=out_image)
+
+    def _graph_layer_grouped(self, x_img, li, V, Mp, M):
+        c = self._weights()
+        gl, gr = self.dual_gcn.layers[li].graph_left, self.dual_gcn.layers[li].graph_right
+        csr = tuple(getattr(self, "_L_left_%d_%s" % (li, n)) for n in ("rowptr", "colidx", "vals"))
+        nb = len(gl.GCN_blocks)
+        x = None
+        for bi, (bl, br) in enumerate(zip(gl.GCN_blocks, gr.GCN_blocks)):
+            co, last = bl.fc1.out_features, bi == nb - 1
+            U = ops.linear_tc_grouped(self._gpack((li, bi, "in"), [c[(li, "left", bi, "in")], c[(li, "right", bi, "in")]],
+                                                  [None, None]), x_img, Mp, M)              # [U0 | U1 | shortcut]
+            _, y_img = ops.graph_cheby_ln_grouped(U[:, :co], U[:, co:2 * co], self._gstack((li, bi, "b1"), [bl.fc1.bias, br.fc1.bias]),
+                                                  csr, V, Mp, M, self._gln((li, bi, "n2"), bl.norm2, br.norm2), True,
+                                                  want_rows=False, want_img=True)
+            U2 = ops.linear_tc_grouped(self._gpack((li, bi, "mid"), [c[(li, "left", bi, "mid")], c[(li, "right", bi, "mid")]],
+                                                   [None, None]), y_img, Mp, M)
+            x, x_img = ops.graph_cheby_ln_grouped(U2[:, :co], U2[:, co:], self._gstack((li, bi, "b2"), [bl.fc2.bias, br.fc2.bias]),
+                                                  csr, V, Mp, M, self._gln((li, bi, "n3"), bl.norm3, br.norm3), not last,
+                                                  R=U[:, 2 * co:], bias_r2=self._gstack((li, bi, "bs"), [bl.shortcut.bias, br.shortcut.bias]),
+                                                  want_rows=last, want_img=not last)
+        return x                                               # fp32 rows [2*Mp, co]: the attention residual
+
+    def _features_grouped(self, global_feature_left, global_feature_right):
+        """-> fboth [2, B*V, C]: both hands' final vertex features."""
+        c = self._weights()
+        B = global_feature_left.shape[0]
+        cin0, dev = self.gcn_in_dim[0], global_feature_left.device
+        pad = lambda m: (m + 127) // 128 * 128
+        gp2 = torch.zeros((2, B, cin0), dtype=torch.float32, device=dev)
+        for si, (side, gfeat) in enumerate((("left", global_feature_left), ("right", global_feature_right))):
+            gf = getattr(self, "gf_layer_" + side)
+            g = self._linear(L.f32c(gfeat), gf[0].weight.detach(), gf[0].bias.detach(), tc_min_rows=128)
+            ops.row_combine(g, ln=self._ln(gf[1]), ln_out=gp2[si, :, :cin0 - 3])
+        V = self.verts[0]
+        M, Mp = B * V, pad(B * V)
+        row0 = self._gstack(("row0",), [c[("row0", "left")], c[("row0", "right")]])                  # [2, V, cin0]
+        # Lf = cat([g repeated over the 63 vertices, pe], -1) + position embedding (:197-198, DualGraph.py:76-80)
+        _, x_img, _ = ops.row_combine_grouped(gp2.view(2 * B, cin0), None, Mp, M, B, rowvec=row0, rowvec_gstride=V * cin0,
+                                              V_out=V, up=V, sum_img=True)
+        for li, V in enumerate(self.verts):
+            M, Mp = B * V, pad(B * V)
+            a = self.dual_gcn.layers[li].attn
+            sl, sr = a.L_self_attn_layer, a.R_self_attn_layer
+            x = self._graph_layer_grouped(x_img, li, V, Mp, M)
+            f = x.shape[1]
+            grp = lambda t, g, c0, c1: t[g * Mp:g * Mp + M, c0:c1]
+            # SelfAttn of each hand (self_attn.py:60-84): x2 = x + fc(attention(LN(x))), f2 = MLP(LN(x2))
+            _, _, h_img = ops.row_combine_grouped(x, None, Mp, M, Mp, ln=self._gln((li, "sa_ln"), sl.layer_norm, sr.layer_norm),
+                                                  ln_img=True)
+            qkv = ops.linear_tc_grouped(self._gpack((li, "sa_qkv"), [c[(li, "L", "qkv_w")], c[(li, "R", "qkv_w")]],
+                                                    [c[(li, "L", "qkv_b")], c[(li, "R", "qkv_b")]]), h_img, Mp, M)
+            _, att_img = ops.mha_tc([(grp(qkv, g, 0, f), grp(qkv, g, f, 2 * f), grp(qkv, g, 2 * f, 3 * f), None) for g in (0, 1)],
+                                    B, V, self.heads, rows=False, image=ops.split_image_empty(2 * Mp, f, dev), image_rows=[0, Mp])
+            g1 = self._glinear((li, "sa_fc"), sl.fc, sr.fc, att_img, Mp, M)
+            x2, _, h2_img = ops.row_combine_grouped(x, g1, Mp, M, Mp, ln=self._gln((li, "sa_ffln"), sl.ff.layer_norm, sr.ff.layer_norm),
+                                                    want_sum=True, ln_img=True)
+            f1_img = self._glinear((li, "sa_fc1"), sl.ff.fc1, sr.ff.fc1, h2_img, Mp, M, act=L.ACT_RELU, out_image=True)
+            f2 = self._glinear((li, "sa_fc2"), sl.ff.fc2, sr.ff.fc2, f1_img, Mp, M)
+            # cross attention (inter_attn.py:72-125): shared projections on [LN1(Lf) ; LN2(Rf)], R2L and L2R in one launch
+            Xf, _, both_img = ops.row_combine_grouped(x2, f2, Mp, M, Mp, ln=self._gln((li, "x_ln"), a.layer_norm1, a.layer_norm2),
+                                                      want_sum=True, ln_img=True)
+            qkvx = self._linear(None, c[(li, "X", "qkv_w")], c[(li, "X", "qkv_b")], x_img=both_img, M=2 * Mp)
+            _, x_att = ops.mha_tc([(grp(qkvx, 0, 0, f), grp(qkvx, 1, f, 2 * f), grp(qkvx, 1, 2 * f, 3 * f), None),
+                                   (grp(qkvx, 1, 0, f), grp(qkvx, 0, f, 2 * f), grp(qkvx, 0, 2 * f, 3 * f), None)],
+                                  B, V, self.heads, rows=False, image=ops.split_image_empty(2 * Mp, f, dev), image_rows=[0, Mp])
+            feat = self._linear(None, a.fc.weight.detach(), a.fc.bias.detach(), x_img=x_att, M=2 * Mp)
+            x4, _, h4_img = ops.row_combine_grouped(Xf, feat, Mp, M, Mp, ln=self._gln((li, "x_ffln"), a.ffL.layer_norm, a.ffR.layer_norm),
+                                                    want_sum=True, ln_img=True)
+            f3_img = self._glinear((li, "x_fc1"), a.ffL.fc1, a.ffR.fc1, h4_img, Mp, M, act=L.ACT_RELU, out_image=True)
+            f4 = self._glinear((li, "x_fc2"), a.ffL.fc2, a.ffR.fc2, f3_img, Mp, M)
+            if li != 2:                                        # add + graph_upsample(., 2) + next position embedding
+                pos = self.dual_gcn.layers[li + 1].position_embeddings.weight.detach()
+                _, x_img, _ = ops.row_combine_grouped(x4, f4, pad(2 * M), 2 * M, Mp, rowvec=pos, V_out=2 * V, up=2, sum_img=True)
+            else:
+                fb, _, _ = ops.row_combine_grouped(x4, f4, Mp, M, Mp, V_out=V, want_sum=True)
+                fboth = fb.view(2, Mp, f)[:, :M]
+                return fboth if Mp == M else fboth.contiguous()
+
     def forward(self, global_feature_left, global_feature_right, fmaps=None):
         if self.training:
             raise NotImplementedError("pdfnet_b200.decoder: inference only (call .eval()); for training keep the "
@@ -385,7 +507,10 @@ class decoder(nn.Module):
             assert global_feature_left.shape[1] == self.gf_dim and global_feature_right.shape[1] == self.gf_dim
             cin0 = self.gcn_in_dim[0]
             x = {}
-            for side, gfeat in (("left", global_feature_left), ("right", global_feature_right)):
+            grouped = self._grouped_ok(B)
+            if grouped:
+                fboth = self._features_grouped(global_feature_left, global_feature_right)
+            for side, gfeat in (() if grouped else (("left", global_feature_left), ("right", global_feature_right))):
                 gf = getattr(self, "gf_layer_" + side)
                 g = self._linear(L.f32c(gfeat), gf[0].weight.detach(), gf[0].bias.detach(), tc_min_rows=128)
                 gpad = torch.zeros((B, cin0), dtype=torch.float32, device=g.device)
@@ -395,7 +520,7 @@ class decoder(nn.Module):
             cur = torch.cuda.current_stream()
             if self._side is None:
                 self._side = torch.cuda.Stream()
-            for li, V in enumerate(self.verts):
+            for li, V in (() if grouped else enumerate(self.verts)):
                 # the two hands are independent up to the cross attention: the right hand's GraphLayer and
                 # SelfAttn run on a second stream (captured as a fork / join inside a CUDA graph); from the
                 # cross attention of level 0 on the right hand's tensors are produced there (_inter_attn)

@@ -692,6 +692,41 @@ def linear_tc(x, w, bias=None, act=L.ACT_NONE, split=True, packed=None, x_img=No
     return out[:, :N]
 
 
+def pack_linear_tc_grouped(ws, biases):
+    """Two weights [N,K] of identical shape (the left / right hand's copy of one layer) packed for
+    linear_tc_grouped: (stacked split weight images, stacked padded biases, N, K, image bytes, bias floats)."""
+    packs = [pack_linear_tc(w, b, True) for w, b in zip(ws, biases)]
+    assert len(packs) == 2 and packs[0][2:4] == packs[1][2:4] and packs[0][0].numel() == packs[1][0].numel()
+    return (torch.cat([packs[0][0], packs[1][0]]), torch.cat([packs[0][1], packs[1][1]]), packs[0][2], packs[0][3],
+            packs[0][0].numel(), packs[0][1].numel())
+
+
+def linear_tc_grouped(packed2, x_img, Mp, M, act=L.ACT_NONE, out_image=False, light=True):
+    """act(x @ w_g.T + bias_g) for the two row groups of a stacked split image (pdf_gemm_bf16_grouped): x_img holds
+    2 * Mp rows (Mp % 128 == 0, the first M of each group real).  Returns fp32 rows [2*Mp, N] (a view of a buffer
+    with a pitch padded to 4) or, with out_image, only the split operand image of the result (N % 64 == 0)."""
+    w_img, b, N, K, wstride, bstride = packed2
+    L.require_cuda(x_img, w_img)
+    assert Mp % 128 == 0 and 0 < M <= Mp
+    kb = 3 * ((K + 63) // 64)
+    nt = (N + 127) // 128
+    act = act | (L.GEMM_LIGHT if light else 0)
+    if out_image:
+        assert N % 64 == 0
+        img = split_image_empty(2 * Mp, N, x_img.device)
+        flat = [int(v) for i in range(nt) for v in (128 * i, min(128, N - 128 * i), 2 * i)]
+        desc = (ctypes.c_int32 * len(flat))(*flat)
+        L.call("pdf_gemm_bf16_grouped", L.ptr(x_img), Mp // 128, kb, L.ptr(w_img), nt, kb, wstride, kb, L.ptr(b), bstride,
+               act | L.GEMM_OUT_SPLIT, None, 0, M, L.ptr(img), 3 * (N // 64), ctypes.cast(desc, ctypes.c_void_p), L.stream())
+        return img
+    out = torch.empty((2 * Mp, _pad4(N)), dtype=torch.float32, device=x_img.device)
+    flat = [int(v) for t in _tile_desc(N) for v in t]
+    desc = (ctypes.c_int32 * len(flat))(*flat)
+    L.call("pdf_gemm_bf16_grouped", L.ptr(x_img), Mp // 128, kb, L.ptr(w_img), nt, kb, wstride, kb, L.ptr(b), bstride, act,
+           L.ptr(out), out.stride(0), M, None, 0, ctypes.cast(desc, ctypes.c_void_p), L.stream())
+    return out[:, :N]
+
+
 def linear_tn_mn(a_img, ca, b_img, cb, M, split=True):
     """a^T b [ca, cb] from the ROW tile images of a [M,ca] and b [M,cb] (pdf_gemm_tn_bf16: the tensor core
     reads the K-major blocks as MN-major operands; no transposed copies).  Images as written by
@@ -775,6 +810,42 @@ def row_combine(a, b=None, rowvec=None, V_out=None, up=1, ln=None, relu=False, w
     return s_out, ln_out, s_im, l_im
 
 
+def row_combine_grouped(a, b, Mp, M, src_per_group, rowvec=None, rowvec_gstride=0, V_out=None, up=1, ln=None,
+                        relu=False, want_sum=False, sum_img=False, ln_img=False, eps=1e-6):
+    """pdf_row_combine_grouped: the two row groups (hands) of stacked buffers in one launch.  a / b hold the
+    sources ([2 * src_per_group, C]); outputs hold 2 * Mp rows (the first M of each group are written).  ``ln`` =
+    (gamma [2,C], beta [2,C]).  Returns (sum rows or None, sum image or None, LayerNorm image or None)."""
+    L.require_cuda(a, b, rowvec)
+    C = _rows(a).shape[1]
+    if V_out is None:
+        V_out = up
+    dev = a.device
+    s_out = torch.empty((2 * Mp, C), dtype=torch.float32, device=dev) if want_sum else None
+    s_im = split_image_empty(2 * Mp, C, dev) if sum_img else None
+    l_im = split_image_empty(2 * Mp, C, dev) if ln_img else None
+    gamma, beta = ln if ln is not None else (None, None)
+    L.call("pdf_row_combine_grouped", L.ptr(a), a.stride(0), L.ptr(b), b.stride(0) if b is not None else 0, L.ptr(rowvec),
+           rowvec.stride(-2) if rowvec is not None else 0, rowvec_gstride, V_out, up, C, Mp, M, src_per_group,
+           L.ptr(gamma), L.ptr(beta), float(eps), int(relu), L.ptr(s_out), C, None, 0, L.ptr(s_im), L.ptr(l_im), L.stream())
+    return s_out, s_im, l_im
+
+
+def graph_cheby_ln_grouped(U0, U1, bias2, csr, V, Mp, M, ln2, relu, R=None, bias_r2=None, eps=1e-6, want_rows=True,
+                           want_img=False):
+    """pdf_graph_cheby_ln_grouped: U0 / U1 / R are column slices of a [2*Mp, .] GEMM output, bias2 / bias_r2 /
+    ln2 = (gamma, beta) are stacked [2, C].  Returns (rows or None, image or None)."""
+    L.require_cuda(U0, U1, bias2, R)
+    C = _rows(U0).shape[1]
+    assert U1.stride(0) == U0.stride(0) and U0.shape[0] == 2 * Mp
+    rowptr, colidx, vals = csr
+    out = torch.empty((2 * Mp, C), dtype=torch.float32, device=U0.device) if want_rows else None
+    img = split_image_empty(2 * Mp, C, U0.device) if want_img else None
+    L.call("pdf_graph_cheby_ln_grouped", L.ptr(U0), L.ptr(U1), U0.stride(0), L.ptr(bias2), L.ptr(R),
+           R.stride(0) if R is not None else 0, L.ptr(bias_r2), L.ptr(rowptr), L.ptr(colidx), L.ptr(vals), V, C, Mp, M,
+           L.ptr(ln2[0]), L.ptr(ln2[1]), float(eps), int(relu), L.ptr(out), C, L.ptr(img), L.stream())
+    return out, img
+
+
 def graph_cheby_ln(U0, U1, bias, csr, V, ln, relu, R=None, bias_r=None, eps=1e-6, want_rows=True, want_img=False):
     """LayerNorm(U0 + bias + L.U1 (+ R + bias_r)) (+ReLU); U0/U1 (and R) are column slices of GEMM outputs.
     Returns fp32 rows, or (rows or None, split-bf16 tile image) with want_img."""
@@ -807,8 +878,9 @@ def mha_tc(problems, n_samples, V, heads, rows=True, image=None, image_rows=None
     problems: [(q, k, v, out-or-None), ...] with q/k/v [n_samples*V, heads*d] column slices of fp32 rows that
     share their row pitches.  rows=True: fp32 row outputs (returned as a list).  image: True (allocate) or a
     uint8 tensor: the results are ALSO / ONLY written as the split-bf16 tile image of the stacked
-    [len(problems) * n_samples * V, heads*d] matrix (problem i fills rows [i*M, (i+1)*M)) - the operand of the
-    ``fc`` GEMM that follows.  Returns outs, or (outs, image) when an image is requested."""
+    [len(problems) * n_samples * V, heads*d] matrix (problem i fills rows [i*M, (i+1)*M), or the rows starting at
+    image_rows[i]) - the operand of the ``fc`` GEMM that follows.  Returns outs, or (outs, image) when an image is
+    requested."""
     outs, ptrs = [], ([], [], [], [])
     q0, k0, v0, _ = problems[0]
     M, f = _rows(q0).shape
@@ -834,7 +906,9 @@ def mha_tc(problems, n_samples, V, heads, rows=True, image=None, image_rows=None
             image = split_image_empty(n * M, f, q0.device)
         L.ptr(image)
         img_arr = ctypes.cast((ctypes.c_void_p * n)(*([image.data_ptr()] * n)), ctypes.c_void_p)
-        row0 = ctypes.cast((ctypes.c_int64 * n)(*[i * M for i in range(n)]), ctypes.c_void_p)
+        starts = list(image_rows) if image_rows is not None else [i * M for i in range(n)]
+        assert len(starts) == n
+        row0 = ctypes.cast((ctypes.c_int64 * n)(*starts), ctypes.c_void_p)
     L.call("pdf_mha_tc", ctypes.cast(arr[0], ctypes.c_void_p), ctypes.cast(arr[1], ctypes.c_void_p),
            ctypes.cast(arr[2], ctypes.c_void_p), ctypes.cast(arr[3], ctypes.c_void_p) if outs else None, img_arr, row0, n,
            q0.stride(0), k0.stride(0), v0.stride(0), outs[0].stride(0) if outs else 0, n_samples, V, heads, f // heads,

@@ -1357,6 +1357,16 @@ def test_gcn_decoder_tensor_core_and_batch():
             assert rel_err(v.cpu().numpy(), ref[k].numpy()) < tol, (prec, k, rel_err(v.cpu().numpy(), ref[k].numpy()))
         again = _decoder_outputs(m(fl, fr, None))
         assert all(torch.equal(out[k], again[k]) for k in out)
+        # the grouped path (both hands as two row groups of every launch: pdf_gemm_bf16_grouped,
+        # pdf_graph_cheby_ln_grouped, pdf_row_combine_grouped) computes the same rows as the default two-stream one;
+        # here with padding between the groups: 24 * 63 rows are not a multiple of 128
+        m.grouped = True
+        assert m._grouped_ok(B)
+        grp = _decoder_outputs(m(fl, fr, None))
+        m.grouped = False
+        for k, v in grp.items():
+            assert rel_err(v.cpu().numpy(), ref[k].numpy()) < tol, (prec, "grouped", k)
+            assert rel_err(v.cpu().numpy(), out[k].cpu().numpy()) < 1e-5, (prec, "grouped vs two-stream", k)
     # 128 frames: rows per level are multiples of 128, so the cross-attention operand of both hands is written
     # as ONE tile image by the two LayerNorm kernels (decoder._inter_attn)
     fuse = torch.randn((128, 2, 1024), generator=torch.Generator().manual_seed(74))
