@@ -14,13 +14,16 @@ inert holders so state dicts round-trip between the two models).  Dense layers r
 operands were measured and dropped: after ~40 chained layers the scale / translation heads drift by
 5-9 % for a 5 % shorter step); each run of glue between two GEMMs is one fused kernel
 (``csrc/gcn_decoder.cu``): Chebyshev graph term (sparse L) + bias + shortcut + LayerNorm + ReLU,
-residual + LayerNorm, attention, projection.  Inference only.
+residual + LayerNorm, attention, projection.  The kernels are the inference path (``.eval()`` under
+``torch.no_grad()``); with a gradient wanted (``.train()``, or grad enabled and parameters / inputs that require
+it) the same function runs as differentiable torch ops in the reference's order (``_forward_autograd``).
 """
 import os
 
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _lib as L
 from . import ops
@@ -152,7 +155,7 @@ class decoder(nn.Module):
 
     def __init__(self, assets, global_feature_dim=1024, gcn_in_dim=(512, 256, 128), gcn_out_dim=(256, 128, 64),
                  graph_k=2, graph_layer_num=4, vertex_num=778, num_attn_heads=4, precision="fp32",
-                 f_in_Dim=(256, 256, 256, 256), f_out_Dim=(256, 128, 64), img_ex_params=True):
+                 f_in_Dim=(256, 256, 256, 256), f_out_Dim=(256, 128, 64), img_ex_params=True, dropout=0.05):
         super(decoder, self).__init__()
         if precision not in ("fp32", "bf16x3", "bf16"):
             raise ValueError("decoder: precision must be 'fp32' or 'bf16x3' ('bf16' is an alias of the latter)")
@@ -178,6 +181,9 @@ class decoder(nn.Module):
             for i in range(3):
                 for name, t in zip(("rowptr", "colidx", "vals"), _csr(assets["L_%s_%d" % (side, i)])):
                     self.register_buffer("_L_%s_%d_%s" % (side, i, name), t, persistent=False)
+                # dense copy for the differentiable (training) path, which multiplies it like the reference does
+                self.register_buffer("_Ld_%s_%d" % (side, i), torch.as_tensor(np.asarray(assets["L_%s_%d" % (side, i)]),
+                                                                               dtype=torch.float32), persistent=False)
         # inert img_ex_* parameter holders with the reference's shapes (intaghand_decoder.py:121-138:
         # img_size [12,24,48], grid_size 6, img_f_dim = f_in_Dim[:3], grid_f_dim = f_out_Dim)
         img = [(s, fi, 6, fo) for s, fi, fo in zip((12, 24, 48), list(f_in_Dim)[:3], f_out_Dim)] if img_ex_params else None
@@ -194,6 +200,7 @@ class decoder(nn.Module):
             self.unsample_layer.weight.data.copy_(torch.as_tensor(np.asarray(assets["upsample"])))
         self._cache, self._cache_key = {}, None
         self._side = None
+        self.dropout = float(dropout)                          # decoder(dropout=0.05), intaghand_decoder.py:90,275; training only
         # both hands share one graph (true for the shipped gcn_core pickles): the grouped path can then run the two
         # hands' Chebyshev kernels as one launch over one CSR
         self._same_graph = all(np.array_equal(np.asarray(assets["L_left_%d" % i]), np.asarray(assets["L_right_%d" % i]))
@@ -493,13 +500,108 @@ class decoder(nn.Module):
                 fboth = fb.view(2, Mp, f)[:, :M]
                 return fboth if Mp == M else fboth.contiguous()
 
+    # ---- differentiable path (training / fine-tuning) -------------------------------------------------------------
+    # The fused kernels above have no backward.  Whenever a gradient is wanted (module in .train(), or grad enabled and
+    # an input / parameter requires it) the SAME function is evaluated with differentiable torch ops on whatever
+    # device the tensors live on (ATen / cuBLAS kernels under torch.autograd: library code, not this repo's kernels),
+    # in the reference's operation ORDER - including its nn.Dropout calls (gcn.py:107, self_attn.py:69-73,
+    # inter_attn.py:26-31,96-103; p = 0.05 as load_decoder passes it, intaghand_decoder.py:275; active only in .train()) - so that a reference training step with the same
+    # RNG state sees the same masks.  Same parameters, same state dict, same return structure as the kernel path.
+    def _drop(self, t):
+        return F.dropout(t, self.dropout, True) if (self.training and self.dropout > 0) else t
+
+    def _ag_cheby(self, x, fc, Ld):
+        B, V, fin = x.shape                                    # gcn.py:34-69, K = 2: [x, Lx] interleaved, k fastest
+        x1 = torch.einsum("vu,buf->bvf", Ld, x)
+        return fc(torch.stack((x, x1), -1).reshape(B, V, fin * 2))
+
+    def _ag_graph_layer(self, x, layer, Ld):
+        nb = len(layer.GCN_blocks)
+        for bi, blk in enumerate(layer.GCN_blocks):            # GCN_ResBlock.forward, gcn.py:100-110
+            x1 = F.relu(blk.norm2(self._ag_cheby(x, blk.fc1, Ld)))
+            x1 = self._drop(self._ag_cheby(x1, blk.fc2, Ld))
+            x = blk.norm3(x1 + blk.shortcut(x))
+            if bi != nb - 1:
+                x = F.relu(x)                                  # GraphLayer.forward, gcn.py:131-137
+        return x
+
+    def _ag_mha(self, xq, xkv, m):
+        B, V, f = xq.shape
+        h, d = self.heads, f // self.heads
+        q = m.w_qs(xq).view(B, V, h, d).transpose(1, 2)
+        k = m.w_ks(xkv).view(B, V, h, d).transpose(1, 2)
+        v = m.w_vs(xkv).view(B, V, h, d).transpose(1, 2)
+        return F.softmax(torch.matmul(q, k.transpose(-1, -2)) / d ** 0.5, dim=-1), v
+
+    def _ag_mlp(self, x, ff):                                  # MLP_res_block, self_attn.py:17-33
+        return x + self._drop(ff.fc2(self._drop(F.relu(ff.fc1(ff.layer_norm(x))))))
+
+    def _ag_self_attn(self, x, sa):                            # SelfAttn.forward, self_attn.py:60-84
+        B, V, f = x.shape
+        hn = sa.layer_norm(x)
+        a, v = self._ag_mha(hn, hn, sa)
+        o = torch.matmul(self._drop(a), v).transpose(1, 2).contiguous().view(B, V, f)
+        return self._ag_mlp(x + self._drop(sa.fc(o)), sa.ff)
+
+    def _ag_inter_attn(self, Lf, Rf, a):                       # inter_attn.forward, inter_attn.py:72-125
+        B, V, f = Lf.shape
+        Lf, Rf = self._ag_self_attn(Lf, a.L_self_attn_layer), self._ag_self_attn(Rf, a.R_self_attn_layer)
+        L2, R2 = a.layer_norm1(Lf), a.layer_norm2(Rf)
+        a_r2l, Rv = self._ag_mha(L2, R2, a)                    # left queries, right keys / values
+        a_l2r, Lv = self._ag_mha(R2, L2, a)
+        a_r2l, a_l2r = self._drop(a_r2l), self._drop(a_l2r)    # dropout1 in the reference's order (:96-97)
+        f_l2r = torch.matmul(a_l2r, Lv).transpose(1, 2).contiguous().view(B, V, f)
+        f_r2l = torch.matmul(a_r2l, Rv).transpose(1, 2).contiguous().view(B, V, f)
+        f_l2r, f_r2l = self._drop(a.fc(f_l2r)), self._drop(a.fc(f_r2l))
+        return self._ag_mlp(Lf + f_r2l, a.ffL), self._ag_mlp(Rf + f_l2r, a.ffR)
+
+    def _forward_autograd(self, gl, gr):
+        B = gl.shape[0]
+        V0 = self.verts[0]
+        feats = {}
+        for side, gfeat in (("left", gl), ("right", gr)):
+            g = getattr(self, "gf_layer_" + side)(gfeat.float())
+            pe = getattr(self, "_pe_" + side).to(g.dtype)
+            feats[side] = torch.cat((g[:, None, :].expand(-1, V0, -1), pe[None].expand(B, -1, -1)), -1)   # :197-198
+        Lf, Rf = feats["left"], feats["right"]
+        for li, layer in enumerate(self.dual_gcn.layers):      # DualGraphLayer.forward, DualGraph.py:72-95
+            pos = layer.position_embeddings.weight
+            Lf = self._ag_graph_layer(Lf + pos, layer.graph_left, getattr(self, "_Ld_left_%d" % li))
+            Rf = self._ag_graph_layer(Rf + pos, layer.graph_right, getattr(self, "_Ld_right_%d" % li))
+            Lf, Rf = self._ag_inter_attn(Lf, Rf, layer.attn)
+            if li != len(self.dual_gcn.layers) - 1:
+                Lf, Rf = Lf.repeat_interleave(2, dim=1), Rf.repeat_interleave(2, dim=1)                # graph_upsample(., 2)
+        scale, trans2d, root, verts3d, verts2d = {}, {}, {}, {}, {}
+        result = {"verts3d": {}, "verts2d": {}}
+        other = {"verts3d_MANO_list": {"left": [], "right": []}, "verts2d_MANO_list": {"left": [], "right": []}}
+        proj = lambda sc, tr, v: (sc * IMG_SIZE)[:, None, None] * v[..., :2] + (tr * IMG_SIZE / 2 + IMG_SIZE / 2)[:, None]
+        for side, f in (("left", Lf), ("right", Rf)):          # intaghand_decoder.py:213-240
+            temp = self.avg_head(f.transpose(-1, -2))[..., 0]
+            params, root[side] = self.params_head(temp), self.root_head(temp)
+            v252 = self.coord_head(f)
+            v778 = self.unsample_layer(v252.transpose(1, 2)).transpose(1, 2)
+            scale[side], trans2d[side] = params[:, 0], params[:, 1:]
+            rev = getattr(self, "_rev_" + side)
+            up = lambda t: t.repeat_interleave(self.vNum_all // t.shape[1], dim=1)[:, rev]              # graph_upsample + GCN_to_vert
+            verts3d[side], verts2d[side] = v252, proj(scale[side], trans2d[side], v252)
+            result["verts3d"][side], result["verts2d"][side] = v778, proj(scale[side], trans2d[side], v778)
+            other["verts3d_MANO_list"][side].append(up(verts3d[side]))
+            other["verts2d_MANO_list"][side].append(up(verts2d[side]))
+            reg = getattr(self, "_full_regressor_" + side, None)
+            if reg is not None:
+                other.setdefault("joints3d", {})[side] = torch.matmul(reg, v778)
+        return (result, {"scale": scale, "trans2d": trans2d, "root": root},
+                [{"verts3d": verts3d, "verts2d": verts2d}], other)
+
+    def _wants_grad(self, *inputs):
+        if not torch.is_grad_enabled():
+            return False
+        return any(t.requires_grad for t in inputs) or any(p.requires_grad for n, p in self.named_parameters()
+                                                            if "img_ex_" not in n)
+
     def forward(self, global_feature_left, global_feature_right, fmaps=None):
-        if self.training:
-            raise NotImplementedError("pdfnet_b200.decoder: inference only (call .eval()); for training keep the "
-                                      "reference decoder: patch_reference(mode='training')")
-        if torch.is_grad_enabled() and (global_feature_left.requires_grad or global_feature_right.requires_grad):
-            raise RuntimeError("pdfnet_b200.decoder has no backward (inference only): its inputs require grad; run it "
-                               "under torch.no_grad() or keep the reference decoder with patch_reference(mode='training')")
+        if self.training or self._wants_grad(global_feature_left, global_feature_right):
+            return self._forward_autograd(global_feature_left, global_feature_right)
         L.require_cuda(global_feature_left, global_feature_right)
         with torch.no_grad():
             c = self._weights()

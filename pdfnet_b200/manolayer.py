@@ -147,6 +147,51 @@ class ManoLayer(Module):
             self._tables_key = key
         return self._tables
 
+    # ---- differentiable path (losses that back-propagate through MANO, e.g. CtdetLoss: simplified.py:730-736) ----
+    # pdf_mano_lbs has no backward.  When a gradient is wanted the same skinning is evaluated with differentiable
+    # torch ops on the tensors' own device (library kernels under torch.autograd, not this repo's): joint k maps a
+    # rest-pose point x to R_k (x - j_k) + t_k with R_k = R_parent R_local, t_k = R_parent (j_k - j_parent) + t_parent
+    # (the 4x4 chain of manolayer.py:287-303 written as rotation / position pairs); t_k is the posed joint.
+    def _forward_autograd(self, root_rotation, pose, shape, trans, scale, side):
+        bs = root_rotation.shape[0]
+        dev = root_rotation.device
+        f = lambda t: t.to(dev)
+        pose, shape = pose.float(), shape.float()
+        if self.use_pca:
+            pose = pose.mm(f(self.hands_components)[:pose.shape[1]]) + f(self.hands_mean)             # pca2axis
+            R_root = root_rotation.float().reshape(bs, 3, 3)
+        else:
+            R_root = _rodrigues_autograd(root_rotation.float().reshape(bs, 3))
+        R_pose = _rodrigues_autograd(pose.reshape(-1, 3)).view(bs, 15, 3, 3)
+        v_shaped = f(self.v_template) + torch.einsum("vck,bk->bvc", f(self.shapedirs), shape.reshape(bs, 10))
+        j_rest = torch.einsum("jv,bvc->bjc", f(self.J_regressor), v_shaped)
+        pose_feat = (R_pose - torch.eye(3, device=dev)).reshape(bs, 135)
+        v_tpose = v_shaped + torch.einsum("vck,bk->bvc", f(self.posedirs), pose_feat)
+        Rw, tw = [R_root], [j_rest[:, 0]]
+        for i in range(1, 16):
+            p = self.parent[i]
+            Rw.append(Rw[p].bmm(R_pose[:, i - 1]))
+            tw.append(Rw[p].bmm((j_rest[:, i] - j_rest[:, p]).unsqueeze(2))[:, :, 0] + tw[p])
+        Rw, tw = torch.stack(Rw, 1), torch.stack(tw, 1)                                              # [bs,16,3,3], [bs,16,3]
+        off = tw - torch.matmul(Rw, j_rest.unsqueeze(3))[..., 0]
+        w = f(self.weights)
+        v = torch.matmul(torch.einsum("vk,bkij->bvij", w, Rw), v_tpose.unsqueeze(3))[..., 0] + torch.einsum("vk,bki->bvi", w, off)
+        j = torch.cat([tw, v[:, TIPS[side]]], 1)[:, NEW_ORDER]
+        if self.center_idx is not None:                                                              # :310-313
+            center = j[:, self.center_idx:self.center_idx + 1]
+            v, j = v - center, j - center
+        if scale is not None:
+            v, j = v * scale.float().reshape(bs, 1, 1), j * scale.float().reshape(bs, 1, 1)
+        if trans is not None:
+            v, j = v + trans.float().reshape(bs, 1, 3), j + trans.float().reshape(bs, 1, 3)
+        if self.new_skel:                                                                            # :320-330
+            j = j.clone()
+            j[:, 5] = (v[:, 63] + v[:, 144]) / 2
+            j[:, 9] = (v[:, 271] + v[:, 220]) / 2
+            j[:, 13] = (v[:, 148] + v[:, 290]) / 2
+            j[:, 17] = (v[:, 770] + v[:, 83]) / 2
+        return v, j
+
     def forward(self, root_rotation, pose, shape, trans=None, scale=None, side="left"):
         """use_pca=False (:268-272): root_rotation [bs,3] and pose [bs,45] axis-angle.
         use_pca=True (:266-267, the dataset layers of interhand.py:192,220-223): root_rotation is a rotation
@@ -154,13 +199,15 @@ class ManoLayer(Module):
         shape [bs,10], trans [bs,3] or None, scale [bs] or None -> (v [bs,778,3], j [bs,21,3]).
         Host tensors (the reference's dataset / demo code calls the layer on CPU tensors, demo.py:155,
         interhand.py:220,568) are staged to the current CUDA device and the result is returned on the host:
-        the skinning always runs in pdf_mano_lbs.  Inference only: a call that expects gradients raises."""
+        the skinning runs in pdf_mano_lbs.  A call whose inputs require grad takes the differentiable torch path
+        (``_forward_autograd``) on the tensors' own device instead."""
         if side not in TIPS:
             raise ValueError("side must be 'left' or 'right'")
         args = [root_rotation, pose, shape, trans, scale]
         if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in args):
-            raise RuntimeError("pdfnet_b200.ManoLayer has no backward (inference only); keep the reference layer for "
-                               "losses that differentiate through MANO: patch_reference(mode='training')")
+            if self.use_pca and root_rotation.numel() != root_rotation.shape[0] * 9:
+                raise RuntimeError("ManoLayer(use_pca=True): root_rotation must be rotation matrices [bs,3,3]")
+            return self._forward_autograd(root_rotation, pose, shape, trans, scale, side)
         host = not root_rotation.is_cuda
         if host:
             if not torch.cuda.is_available():
@@ -185,11 +232,22 @@ class ManoLayer(Module):
         return (v.cpu(), j.cpu()) if host else (v, j)
 
 
+def _rodrigues_autograd(axis):
+    """manolayer.py:32-48 with differentiable torch ops: R = I + sin(t) K + (1 - cos(t)) K^2, t = |a| + 1e-8."""
+    angle = torch.norm(axis, p=2, dim=1, keepdim=True) + 1e-8
+    a = axis / angle
+    z = torch.zeros_like(a[:, 0])
+    K = torch.stack((z, -a[:, 2], a[:, 1], a[:, 2], z, -a[:, 0], -a[:, 1], a[:, 0], z), 1).view(-1, 3, 3)
+    s, c = torch.sin(angle).unsqueeze(2), torch.cos(angle).unsqueeze(2)
+    return torch.eye(3, dtype=axis.dtype, device=axis.device) + s * K + (1 - c) * K.bmm(K)
+
+
 def rodrigues_batch(axis):
     """manolayer.py:32-48: axis-angle [bs,3] -> rotation matrices [bs,3,3] (pdf_rodrigues); host tensors are
-    staged to the GPU and returned on the host, as in ManoLayer.forward."""
+    staged to the GPU and returned on the host, as in ManoLayer.forward.  An input that requires grad takes the
+    differentiable torch formulation on its own device."""
     if torch.is_grad_enabled() and axis.requires_grad:
-        raise RuntimeError("pdfnet_b200.rodrigues_batch has no backward (inference only)")
+        return _rodrigues_autograd(axis)
     if axis.is_cuda:
         return ops.rodrigues(axis)
     if not torch.cuda.is_available():

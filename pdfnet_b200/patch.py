@@ -11,21 +11,24 @@ the replacements.
 """
 import importlib
 
-# names whose replacement has no backward: they stay the reference's in mode="training"
+# names whose replacement runs its BACKWARD (and its train-mode forward) on differentiable torch ops rather than on
+# this library's kernels (decoder._forward_autograd, ManoLayer._forward_autograd): mode="training" leaves them the
+# reference's own modules, mode="training-all" rebinds them too
 _INFERENCE_ONLY = ("load_decoder", "ManoLayer", "rodrigues_batch")
 
 
 def patch_reference(mode="inference"):
     """Requires the reference to be importable (``lib`` on sys.path).  Returns the list of patched names.
 
-    mode="inference" (default): every hot-path name is rebound, including the GCN decoder and the MANO
-    layer, which are inference-only here (they raise if a gradient is requested).
-    mode="training": the differentiable stages (grouping, gathers, SFTLayer, PointNet_Plus - forward and
-    backward on this library's kernels) are rebound; ``load_decoder``, ``ManoLayer`` and
-    ``rodrigues_batch`` stay the reference's own autograd implementations, so ``loss.backward()`` reaches
-    every parameter exactly as in the unpatched model."""
-    if mode not in ("inference", "training"):
-        raise ValueError("patch_reference: mode must be 'inference' or 'training'")
+    mode="inference" (default) / "training-all": every hot-path name is rebound, including the GCN decoder and the
+    MANO layer.  Those two run their kernels under ``torch.no_grad()`` / in ``.eval()`` and switch to differentiable
+    torch ops whenever a gradient is wanted (``decoder._forward_autograd`` - same dropout calls in the same order as
+    the reference, tests/test_decoder_autograd.py - and ``ManoLayer._forward_autograd``).
+    mode="training": only the stages whose forward AND backward run on this library's kernels (grouping, gathers,
+    SFTLayer, PointNet_Plus) are rebound; ``load_decoder``, ``ManoLayer`` and ``rodrigues_batch`` stay the
+    reference's own modules.  Either way ``loss.backward()`` reaches every parameter as in the unpatched model."""
+    if mode not in ("inference", "training", "training-all"):
+        raise ValueError("patch_reference: mode must be 'inference', 'training' or 'training-all'")
     from . import decoder, encoder, grouping, manolayer
     patched = []
     ru = importlib.import_module("lib.utils.utils")

@@ -3,6 +3,7 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
+torch.set_grad_enabled(False)             # inference: the kernel path (a wanted gradient selects the torch autograd path)
 from conftest import load_golden
 from pdfnet_b200 import synth, _lib
 from pdfnet_b200.decoder import decoder

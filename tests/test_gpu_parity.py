@@ -492,19 +492,24 @@ def test_mano_pca_matrix_root_rodrigues_and_joint_regressor():
         assert np.abs(v2.cpu().numpy() - g["model_v_" + side]).max() < 1e-5
 
 
-def test_inference_only_modules_refuse_gradients_loudly():
-    """ManoLayer / rodrigues_batch / decoder have no backward: a call that expects gradients raises instead of
-    returning detached tensors (patch_reference(mode='training') keeps the reference's versions)."""
+def test_kernel_only_modules_switch_to_autograd_when_a_gradient_is_wanted():
+    """ManoLayer / rodrigues_batch kernels have no backward: a call whose inputs require grad never returns detached
+    tensors - it takes the differentiable torch formulation, which agrees with the kernel to 1e-5 m and carries a
+    gradient back to the inputs."""
     from pdfnet_b200 import ManoLayer, rodrigues_batch
     T = mano_tables("left")
     rot, pose, shape, _ = synth.mano_inputs(2, seed=5)
     layer = ManoLayer(T, center_idx=None)
-    with pytest.raises(RuntimeError, match="no backward"):
-        layer(rot.to(DEV).requires_grad_(True), pose.to(DEV), shape.to(DEV))
-    with pytest.raises(RuntimeError, match="no backward"):
-        rodrigues_batch(rot.to(DEV).requires_grad_(True))
-    v, _ = layer(rot.to(DEV), pose.to(DEV), shape.to(DEV))      # grad mode on, nothing requires grad: fine
-    assert v.shape == (2, 778, 3)
+    v, j = layer(rot.to(DEV), pose.to(DEV), shape.to(DEV))      # grad mode on, nothing requires grad: the kernel
+    assert v.shape == (2, 778, 3) and not v.requires_grad
+    rg, pg = rot.to(DEV).requires_grad_(True), pose.to(DEV).requires_grad_(True)
+    va, ja = layer(rg, pg, shape.to(DEV))
+    assert va.requires_grad and float((va - v).abs().max()) < 1e-5 and float((ja - j).abs().max()) < 1e-5
+    (va.sum() + ja.sum()).backward()
+    assert float(rg.grad.abs().max()) > 0 and float(pg.grad.abs().max()) > 0
+    Rk = rodrigues_batch(rot.to(DEV))
+    Ra = rodrigues_batch(rot.to(DEV).requires_grad_(True))
+    assert Ra.requires_grad and float((Ra - Rk).abs().max()) < 1e-6
 
 
 def test_patched_gather_and_eval_mode_modules_carry_gradients():
@@ -1484,7 +1489,7 @@ def test_decoder_primitives_vs_torch():
 @torch.no_grad()
 def test_gcn_decoder_single_frame_and_errors():
     """B = 1 (every GEMM below the tensor-core row threshold even in bf16x3 mode) equals the fp32 path;
-    wrong feature width and train mode fail loudly."""
+    a wrong feature width and CPU tensors fail loudly; a wanted gradient switches to the differentiable path."""
     m, _ = _decoder("bf16x3")
     m32, _ = _decoder("fp32")
     fuse = torch.randn((1, 2, 1024), generator=torch.Generator().manual_seed(73)).to(DEV)
@@ -1493,10 +1498,17 @@ def test_gcn_decoder_single_frame_and_errors():
     assert all(torch.equal(a[k], b[k]) for k in a)
     with pytest.raises(AssertionError):
         m32(fuse[:, 0, :512], fuse[:, 1, :512], None)
-    with pytest.raises(NotImplementedError):
-        m32.train()(fuse[:, 0], fuse[:, 1], None)
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError):                          # the kernel path has no CPU fallback
         m32.eval()(fuse[:, 0].cpu(), fuse[:, 1].cpu(), None)
+    # a wanted gradient (eval-mode fine-tuning here) takes the differentiable torch path: same values, with a graph
+    with torch.enable_grad():
+        fg = fuse.clone().requires_grad_(True)
+        g = _decoder_outputs(m32(fg[:, 0], fg[:, 1], None))
+        assert all(v.requires_grad for v in g.values())
+        for k in g:
+            assert rel_err(g[k].detach().cpu().numpy(), b[k].cpu().numpy()) < 1e-4, k
+        g["verts3d_left"].sum().backward()
+        assert float(fg.grad.abs().max()) > 0
 
 
 @torch.no_grad()

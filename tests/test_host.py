@@ -221,7 +221,8 @@ def test_patch_reference_rebinds_every_boundary_name(monkeypatch):
 
 
 def test_patch_reference_training_mode_keeps_the_reference_autograd_modules(monkeypatch):
-    """mode='training': the inference-only replacements (decoder, ManoLayer, rodrigues_batch) are NOT installed."""
+    """mode='training': the replacements whose backward is torch autograd rather than this library's kernels (decoder,
+    ManoLayer, rodrigues_batch) are NOT installed; mode='training-all' installs them too."""
     import types
     import pdfnet_b200
     names = ["lib", "lib.utils", "lib.utils.utils", "lib.models", "lib.models.utils", "lib.models.networks",
@@ -234,6 +235,7 @@ def test_patch_reference_training_mode_keeps_the_reference_autograd_modules(monk
     assert not hasattr(sys.modules["lib.models.networks.manolayer"], "ManoLayer")
     from pdfnet_b200 import encoder
     assert sys.modules["lib.models.networks.intaghand_encoder"].PointNet_Plus is encoder.PointNet_Plus
+    assert len(pdfnet_b200.patch_reference(mode="training-all")) == 14      # + load_decoder (x2), ManoLayer, rodrigues_batch
     with pytest.raises(ValueError):
         pdfnet_b200.patch_reference(mode="bogus")
 
