@@ -41,6 +41,9 @@ enum { PDF_GEMM_OUT_SPLIT = 256,
        /* also OR-ed onto `act`: run the half-footprint configuration (2 operand stages, 256 TMEM columns, two CTAs
         * per SM) - for short GEMMs that come in concurrent pairs on two streams; single-accumulator ROW mode only */
        PDF_GEMM_LIGHT = 512 };
+/* OR-ed onto the `relu` argument of pdf_bn_act_fwd / pdf_bn_act_bwd / pdf_bn_maxpool_bwd: the image output is ONE plain
+ * bf16 tile image (C/64 k-blocks per row tile) instead of the split image [hi | hi | lo] - the bf16 training mode */
+enum { PDF_BN_PLAIN_IMAGE = 2 };
 #define PDF_MANO_VT_PITCH 2336
 /* epilogue modes for pdf_linear_f32 */
 enum {

@@ -89,6 +89,7 @@ EXPORTS = sorted(list(SIGNATURES) + ["pdf_version", "pdf_last_error", "pdf_launc
 ACT_NONE, ACT_RELU, ACT_LEAKY01 = 0, 1, 2
 GEMM_OUT_SPLIT = 256          # OR-ed onto act: pdf_gemm_bf16 writes out_img as a split image [hi | hi | lo]
 GEMM_LIGHT = 512              # OR-ed onto act: half-footprint GEMM configuration (two CTAs per SM)
+BN_PLAIN_IMAGE = 2            # OR-ed onto relu (pdf_bn_act_fwd / _bwd / pdf_bn_maxpool_bwd): plain bf16 image output
 EPI_STORE, EPI_SFT_SCALE, EPI_ACCUM, EPI_GROUP_MAX = 0, 1, 2, 3
 
 _lib = None

@@ -225,7 +225,7 @@ bn_bwd_image_kernel(const float* __restrict__ dY, int64_t lddy, const float* __r
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const double* __restrict__ sums, int relu, int64_t M, int C,
                     uint8_t* __restrict__ img, const float* __restrict__ dOut, int64_t lddo,
-                    const uint8_t* __restrict__ arg, int G) {
+                    const uint8_t* __restrict__ arg, int G, int plain) {
   // thread = one 8-channel chunk (fixed for the thread's lifetime, its coefficients live in registers) of a run
   // of rows: 256 threads = (C/8 chunks) x (256 / (C/8) rows per pass)
   const int cq = C >> 3, nkb = C >> 6;
@@ -283,11 +283,13 @@ bn_bwd_image_kernel(const float* __restrict__ dY, int64_t lddy, const float* __r
     wl.y = umma::pack_bf16(d[2] - __uint_as_float(w.y << 16), d[3] - __uint_as_float(w.y & 0xffff0000u));
     wl.z = umma::pack_bf16(d[4] - __uint_as_float(w.z << 16), d[5] - __uint_as_float(w.z & 0xffff0000u));
     wl.w = umma::pack_bf16(d[6] - __uint_as_float(w.w << 16), d[7] - __uint_as_float(w.w & 0xffff0000u));
-    uint8_t* base = img + (size_t)(r >> 7) * (size_t)(3 * nkb) * 16384;
+    uint8_t* base = img + (size_t)(r >> 7) * (size_t)((plain ? 1 : 3) * nkb) * 16384;
     const uint32_t off = umma::sw128_off((uint32_t)(r & 127), kcol);
     *reinterpret_cast<uint4*>(base + (size_t)kb * 16384 + off) = w;
-    *reinterpret_cast<uint4*>(base + (size_t)(nkb + kb) * 16384 + off) = w;
-    *reinterpret_cast<uint4*>(base + (size_t)(2 * nkb + kb) * 16384 + off) = wl;
+    if (!plain) {                                      // plain: one bf16 image (bf16 training mode), else [hi | hi | lo]
+      *reinterpret_cast<uint4*>(base + (size_t)(nkb + kb) * 16384 + off) = w;
+      *reinterpret_cast<uint4*>(base + (size_t)(2 * nkb + kb) * 16384 + off) = wl;
+    }
   }
 }
 
@@ -296,7 +298,7 @@ bn_bwd_image_kernel(const float* __restrict__ dY, int64_t lddy, const float* __r
 __global__ void __launch_bounds__(256)
 bn_fwd_image_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    int relu, int64_t M, int C, float* __restrict__ Y, int64_t ldy, uint8_t* __restrict__ img) {
+                    int relu, int64_t M, int C, float* __restrict__ Y, int64_t ldy, uint8_t* __restrict__ img, int plain) {
   const int cq = C >> 3, nkb = C >> 6;
   const int q = threadIdx.x % cq, rl = threadIdx.x / cq, rows_cta = 256 / cq;
   if (rl >= rows_cta) return;
@@ -332,11 +334,13 @@ bn_fwd_image_kernel(const float* __restrict__ X, int64_t ldx, const float* __res
     wl.y = umma::pack_bf16(d[2] - __uint_as_float(w.y << 16), d[3] - __uint_as_float(w.y & 0xffff0000u));
     wl.z = umma::pack_bf16(d[4] - __uint_as_float(w.z << 16), d[5] - __uint_as_float(w.z & 0xffff0000u));
     wl.w = umma::pack_bf16(d[6] - __uint_as_float(w.w << 16), d[7] - __uint_as_float(w.w & 0xffff0000u));
-    uint8_t* base = img + (size_t)(r >> 7) * (size_t)(3 * nkb) * 16384;
+    uint8_t* base = img + (size_t)(r >> 7) * (size_t)((plain ? 1 : 3) * nkb) * 16384;
     const uint32_t off = umma::sw128_off((uint32_t)(r & 127), kcol);
     *reinterpret_cast<uint4*>(base + (size_t)kb * 16384 + off) = w;
-    *reinterpret_cast<uint4*>(base + (size_t)(nkb + kb) * 16384 + off) = w;
-    *reinterpret_cast<uint4*>(base + (size_t)(2 * nkb + kb) * 16384 + off) = wl;
+    if (!plain) {
+      *reinterpret_cast<uint4*>(base + (size_t)(nkb + kb) * 16384 + off) = w;
+      *reinterpret_cast<uint4*>(base + (size_t)(2 * nkb + kb) * 16384 + off) = wl;
+    }
   }
 }
 
@@ -577,6 +581,8 @@ extern "C" int pdf_bn_act_fwd(const float* X, int64_t ldx, const float* mean, co
                               void* stream) {
   PDF_REQUIRE(X && mean && rstd && gamma && beta && (Y || Y_img) && M >= 0 && C > 0, PDF_ERR_BAD_ARG,
               "pdf_bn_act_fwd: bad argument");
+  const int plain = (relu & PDF_BN_PLAIN_IMAGE) ? 1 : 0;      // flag bit on `relu`: image written as one plain bf16 image
+  relu &= 1;
   if (Y_img) {
     PDF_REQUIRE(C % 64 == 0 && C <= 2048 && ldx % 4 == 0 && aligned16(X) && (!Y || (ldy % 4 == 0 && aligned16(Y))),
                 PDF_ERR_BAD_ARG, "pdf_bn_act_fwd: the image output needs C %% 64 == 0 and 16-byte aligned rows");
@@ -585,7 +591,7 @@ extern "C" int pdf_bn_act_fwd(const float* X, int64_t ldx, const float* mean, co
     int64_t gx = ((((M + 127) >> 7) << 7) + rows_cta - 1) / rows_cta;
     if (gx > 148 * 16) gx = 148 * 16;
     bn_fwd_image_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(X, ldx, mean, rstd, gamma, beta, relu, M, C, Y,
-                                                                         ldy, (uint8_t*)Y_img);
+                                                                         ldy, (uint8_t*)Y_img, plain);
     return check_launch("pdf_bn_act_fwd");
   }
   EwArgs p = {};
@@ -597,6 +603,8 @@ extern "C" int pdf_bn_act_fwd(const float* X, int64_t ldx, const float* mean, co
 extern "C" int pdf_bn_act_bwd(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* X, int64_t ldx,
                               const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
                               int64_t M, int C, double* sums, float* dX, int64_t lddx, void* dX_img, void* stream) {
+  const int plain = (relu & PDF_BN_PLAIN_IMAGE) ? 1 : 0;
+  relu &= 1;
   PDF_REQUIRE(dY && X && mean && rstd && gamma && sums && (dX || dX_img) && M >= 0 && C > 0 && (Y || beta || !relu),
               PDF_ERR_BAD_ARG, "pdf_bn_act_bwd: bad argument");
   PDF_REQUIRE(!dX_img || (C % 64 == 0 && beta && !Y && lddy % 4 == 0 && ldx % 4 == 0 && aligned16(dY) && aligned16(X)),
@@ -615,7 +623,7 @@ extern "C" int pdf_bn_act_bwd(const float* dY, int64_t lddy, const float* Y, int
     int64_t gx = ((((M + 127) >> 7) << 7) + rows_cta - 1) / rows_cta;
     if (gx > 148 * 16) gx = 148 * 16;
     bn_bwd_image_kernel<<<(unsigned)gx, 256, 0, s>>>(dY, lddy, X, ldx, mean, rstd, gamma, beta, sums, relu, M, C,
-                                                     (uint8_t*)dX_img, nullptr, 0, nullptr, 1);
+                                                     (uint8_t*)dX_img, nullptr, 0, nullptr, 1, plain);
     rc = check_launch("pdf_bn_act_bwd");
     if (rc != PDF_OK || !dX) return rc;
   }
@@ -684,6 +692,8 @@ extern "C" int pdf_group_max(const float* Y, int64_t ldy, int G, int64_t groups,
 extern "C" int pdf_bn_maxpool_bwd(const float* dOut, int64_t lddo, const uint8_t* arg, int G, const float* X, int64_t ldx,
                                   const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
                                   int64_t M, int C, double* sums, void* dX_img, void* stream) {
+  const int plain = (relu & PDF_BN_PLAIN_IMAGE) ? 1 : 0;
+  relu &= 1;
   PDF_REQUIRE(dOut && arg && X && mean && rstd && gamma && beta && sums && dX_img && M >= 0 && C > 0 && G > 0 &&
                   G <= 256 && M % G == 0,
               PDF_ERR_BAD_ARG, "pdf_bn_maxpool_bwd: bad argument");
@@ -706,7 +716,7 @@ extern "C" int pdf_bn_maxpool_bwd(const float* dOut, int64_t lddo, const uint8_t
   int64_t gxi = ((((M + 127) >> 7) << 7) + rows_cta - 1) / rows_cta;
   if (gxi > 148 * 16) gxi = 148 * 16;
   bn_bwd_image_kernel<<<(unsigned)gxi, 256, 0, s>>>(nullptr, 0, X, ldx, mean, rstd, gamma, beta, sums, relu, M, C,
-                                                    (uint8_t*)dX_img, dOut, lddo, arg, G);
+                                                    (uint8_t*)dX_img, dOut, lddo, arg, G, plain);
   return check_launch("pdf_bn_maxpool_bwd");
 }
 

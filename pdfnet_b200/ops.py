@@ -492,18 +492,25 @@ def bn_batch_stats(x, eps, momentum, running_mean=None, running_var=None):
     return mean, rstd
 
 
-def bn_act_fwd(x, mean, rstd, gamma, beta, relu=True, rows=True, image=False):
-    """[relu](BatchNorm(x)) as fp32 rows and/or (image=True, C % 64 == 0) as the split-bf16 tile image of the
-    next layer's GEMM.  Returns rows, or (rows or None, image)."""
+def plain_image_empty(rows, C, device):
+    """Uninitialised plain bf16 tile image for a [rows, C] matrix, C % 64 == 0."""
+    assert C % 64 == 0
+    return torch.empty((((rows + 127) // 128) * (C // 64) * 16384,), dtype=torch.uint8, device=device)
+
+
+def bn_act_fwd(x, mean, rstd, gamma, beta, relu=True, rows=True, image=False, plain=False):
+    """[relu](BatchNorm(x)) as fp32 rows and/or (image=True, C % 64 == 0) as the tile image of the next layer's
+    GEMM (split-bf16, or one plain bf16 image with plain=True).  Returns rows, or (rows or None, image)."""
     M, C = _rows(x).shape
     y = torch.empty((M, C), dtype=torch.float32, device=x.device) if rows else None
-    img = split_image_empty(M, C, x.device) if image else None
+    img = (plain_image_empty if plain else split_image_empty)(M, C, x.device) if image else None
+    relu = int(relu) | (L.BN_PLAIN_IMAGE if plain else 0)
     L.call("pdf_bn_act_fwd", L.ptr(x), x.stride(0), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), int(relu), M,
            C, L.ptr(y), y.stride(0) if y is not None else 0, L.ptr(img), L.stream())
     return (y, img) if image else y
 
 
-def bn_act_bwd(dy, y, x, mean, rstd, gamma, relu=True, beta=None, image=False):
+def bn_act_bwd(dy, y, x, mean, rstd, gamma, relu=True, beta=None, image=False, plain=False):
     """-> (dx, dgamma, dbeta).  y=None with beta given: the ReLU mask is recomputed from x (no read of y).
     image=True (needs y=None, beta, C % 64 == 0): dx is returned as the split-bf16 tile image the gradient
     GEMMs read instead of fp32 rows."""
@@ -511,7 +518,8 @@ def bn_act_bwd(dy, y, x, mean, rstd, gamma, relu=True, beta=None, image=False):
     dy = _rows(dy if dy.stride(1) == 1 else dy.contiguous())
     sums = torch.empty((2 * C,), dtype=torch.float64, device=x.device)
     dx = None if image else torch.empty((M, C), dtype=torch.float32, device=x.device)
-    img = split_image_empty(M, C, x.device) if image else None
+    img = (plain_image_empty if plain else split_image_empty)(M, C, x.device) if image else None
+    relu = int(relu) | (L.BN_PLAIN_IMAGE if plain else 0)
     L.call("pdf_bn_act_bwd", L.ptr(dy), dy.stride(0), L.ptr(y), y.stride(0) if y is not None else 0, L.ptr(x),
            x.stride(0), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(beta), int(relu), M, C, L.ptr(sums), L.ptr(dx),
            dx.stride(0) if dx is not None else 0, L.ptr(img), L.stream())
@@ -597,13 +605,14 @@ def group_max(y, G, want_arg=False):
     return (out, arg) if want_arg else out
 
 
-def bn_maxpool_bwd(dout, arg, G, x, mean, rstd, gamma, beta, relu=True):
+def bn_maxpool_bwd(dout, arg, G, x, mean, rstd, gamma, beta, relu=True, plain=False):
     """BatchNorm(+ReLU) backward fed by the max-pool gradient (never materialised): -> (dx split tile image,
     dgamma, dbeta); see pdf_bn_maxpool_bwd."""
     M, C = _rows(x).shape
     dout = _rows(dout if dout.stride(1) == 1 else dout.contiguous())
     sums = torch.empty((2 * C,), dtype=torch.float64, device=x.device)
-    img = split_image_empty(M, C, x.device)
+    img = (plain_image_empty if plain else split_image_empty)(M, C, x.device)
+    relu = int(relu) | (L.BN_PLAIN_IMAGE if plain else 0)
     L.call("pdf_bn_maxpool_bwd", L.ptr(dout), dout.stride(0), L.ptr(arg), G, L.ptr(x), x.stride(0), L.ptr(mean),
            L.ptr(rstd), L.ptr(gamma), L.ptr(beta), int(relu), M, C, L.ptr(sums), L.ptr(img), L.stream())
     return img, sums[C:].float(), sums[:C].float()

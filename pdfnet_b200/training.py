@@ -33,8 +33,9 @@ def _use_tc(M, N, K):
 TENSOR_CORE_GEMMS = True     # tcgen05 GEMMs for forward, dX and dW (False: FFMA kernels everywhere)
 
 # GEMM operand precision per mode: "fp32" -> split-bf16 (fp32-accurate), "bf16" -> plain bf16 operands
-# with fp32 accumulation (BASELINE cfg5 "training step bf16").  The layers that decide neighbour
-# indices (SFT0 and the xyz channels through SFT1) are small / FFMA or split in both modes.
+# with fp32 accumulation for the forward, data-gradient AND weight-gradient GEMMs (BASELINE cfg5 "training
+# step bf16": one third of the operand bytes).  The layers that decide neighbour indices (SFT0 and the xyz
+# channels through SFT1) are small / FFMA or split in both modes.
 FP32, BF16 = "fp32", "bf16"
 
 
@@ -60,7 +61,7 @@ class LinearFn(Function):
         else:
             y = ops.linear(x, w, b, act=act)
         ctx.act, ctx.tc, ctx.bias_before_bn, ctx.split, ctx.smallk = act, tc, bias_before_bn, split, smallk
-        ctx.save_for_backward(x, w, y if act != L.ACT_NONE else None, x_img if (tc and split) else None)
+        ctx.save_for_backward(x, w, y if act != L.ACT_NONE else None, x_img if tc else None)
         return y
 
     @staticmethod
@@ -71,25 +72,22 @@ class LinearFn(Function):
             dy = ops.act_bwd(dy, y, ctx.act)
         dx = dw = None
         M, N, K = dy.shape[0], w.shape[0], w.shape[1]
-        dy_img = ops.rows_to_image(dy, 0, N, split=1) if ctx.tc else None      # shared by the dX and dW GEMMs
+        # fp32 mode: split images (fp32-accurate gradient GEMMs); bf16 mode: ONE plain bf16 image of dY feeds both
+        # gradient GEMMs, against the plain image of x kept from the forward pass (what "bf16 training" means in
+        # every framework: bf16 operands, fp32 accumulation, for forward, dX and dW alike)
+        sp = ctx.split
+        dy_img = ops.rows_to_image(dy, 0, N, split=1 if sp else 0) if ctx.tc else None   # shared by the dX and dW GEMMs
         if ctx.needs_input_grad[0]:
-            # the data gradient is the chain that carries every upstream gradient (and ends in the xyz
-            # coordinates, where centroid-relative differences cancel): always fp32-accurate
             if ctx.smallk and dy.stride(0) % 4 == 0 and dy.data_ptr() % 16 == 0:
                 dx = ops.linear_smallk(1, dy, w)
             else:
                 wt = w.t().contiguous()
-                dx = ops.linear_tc(None, wt, split=True, x_img=dy_img, M=M) if ctx.tc else ops.linear(dy, wt)
+                dx = ops.linear_tc(None, wt, split=sp, x_img=dy_img, M=M) if ctx.tc else ops.linear(dy, wt)
         if ctx.needs_input_grad[1]:
             if ctx.smallk:
                 dw = ops.linear_smallk(2, dy, x)
             else:
-                if ctx.tc:
-                    if x_img is None:                   # bf16 mode kept a plain image: the gradient wants the split one
-                        x_img = ops.rows_to_image(x, 0, K, split=1)
-                    dw = ops.linear_tn_mn(dy_img, N, x_img, K, M, split=True)
-                else:
-                    dw = ops.linear_tn(dy, x)
+                dw = ops.linear_tn_mn(dy_img, N, x_img, K, M, split=sp) if ctx.tc else ops.linear_tn(dy, x)
         db = None
         if ctx.needs_input_grad[2]:
             # a bias in front of train-mode BatchNorm has an identically zero gradient (BatchNorm removes
@@ -137,24 +135,23 @@ class LinearBNReLUFn(Function):
         w = _c(w)
         split = precision != BF16
         M = x.shape[0]
-        x_img = getattr(x, "_pdf_split_img", None) if split else None
+        x_img = getattr(x, "_pdf_split_img" if split else "_pdf_plain_img", None)
         if x_img is None:
             x = _c(x)
             x_img = ops.rows_to_image(x, 0, x.shape[1], split=1 if split else 0)
         pre = ops.linear_tc(None, w, b, split=split, x_img=x_img, M=M)
         mean, rstd = ops.bn_batch_stats(pre, eps, momentum, running_mean, running_var)
         arg = None
-        if image_only and split and not group:
-            _, y_img = ops.bn_act_fwd(pre, mean, rstd, gamma, beta, True, rows=False, image=True)
+        if image_only and not group:
+            _, y_img = ops.bn_act_fwd(pre, mean, rstd, gamma, beta, True, rows=False, image=True, plain=not split)
             y = torch.empty((1, 1), dtype=torch.float32, device=pre.device).expand(M, w.shape[0])
         else:
             y_img = None
             y = ops.bn_act_fwd(pre, mean, rstd, gamma, beta, True)
             if group:
                 y, arg = ops.group_max(y, group, want_arg=True)
-        ctx.group = group
-        ctx.save_for_backward(x if x.stride(-1) == 1 else None, w, pre, mean, rstd, gamma, beta,
-                              x_img if split else None, arg)
+        ctx.group, ctx.split = group, split
+        ctx.save_for_backward(x if x.stride(-1) == 1 else None, w, pre, mean, rstd, gamma, beta, x_img, arg)
         if y_img is None:
             y_img = torch.empty((0,), dtype=torch.uint8, device=pre.device)
         ctx.mark_non_differentiable(y_img)
@@ -167,17 +164,17 @@ class LinearBNReLUFn(Function):
         dy = _c(dy)
         if dy.stride(0) % 4 or dy.data_ptr() % 16:
             dy = dy.contiguous()
+        sp = ctx.split                                  # bf16 mode: plain bf16 gradient image, plain-bf16 gradient GEMMs
         if ctx.group:
-            dpre_img, dgamma, dbeta = ops.bn_maxpool_bwd(dy, arg, ctx.group, pre, mean, rstd, gamma, beta, True)
+            dpre_img, dgamma, dbeta = ops.bn_maxpool_bwd(dy, arg, ctx.group, pre, mean, rstd, gamma, beta, True, plain=not sp)
         else:
-            dpre_img, dgamma, dbeta = ops.bn_act_bwd(dy, None, pre, mean, rstd, gamma, True, beta=beta, image=True)
+            dpre_img, dgamma, dbeta = ops.bn_act_bwd(dy, None, pre, mean, rstd, gamma, True, beta=beta, image=True,
+                                                     plain=not sp)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.linear_tc(None, w.t().contiguous(), split=True, x_img=dpre_img, M=M)
+            dx = ops.linear_tc(None, w.t().contiguous(), split=sp, x_img=dpre_img, M=M)
         if ctx.needs_input_grad[1]:
-            if x_img is None:                           # bf16 mode kept a plain image: the gradient wants the split one
-                x_img = ops.rows_to_image(x, 0, K, split=1)
-            dw = ops.linear_tn_mn(dpre_img, N, x_img, K, M, split=True)
+            dw = ops.linear_tn_mn(dpre_img, N, x_img, K, M, split=sp)
         if ctx.needs_input_grad[2]:                     # bias in front of BatchNorm: identically zero gradient
             db = torch.zeros((N,), dtype=torch.float32, device=w.device)
         return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None, None
@@ -282,11 +279,11 @@ def mlp_max_rows(net, rows, group, precision=FP32):
         if fused[li]:
             pool = group if (i == 6 and group <= 256 and M % group == 0) else 0
             # an intermediate layer whose only consumer is the next fused node hands over its operand image
-            image_only = li < 2 and fused[li + 1] and precision != BF16
+            image_only = li < 2 and fused[li + 1]
             h, h_img = LinearBNReLUFn.apply(h, w, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                             momentum, bn.eps, precision, pool, image_only)
             if h_img.numel():                           # h's fp32 storage is a placeholder: the values live in the image
-                h._pdf_split_img = h_img
+                setattr(h, "_pdf_plain_img" if precision == BF16 else "_pdf_split_img", h_img)
             pooled = pool > 0
         else:
             pooled = False
