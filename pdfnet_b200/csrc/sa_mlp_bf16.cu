@@ -51,7 +51,9 @@ struct SaCfg {
   static constexpr int W3_FEAT = KB3 * C3 * 128, W3_AUX = C3 * 32;
   static constexpr int OFF_W1A = W1_FEAT, OFF_W2 = OFF_W1A + W1_AUX, OFF_W2A = OFF_W2 + W2_FEAT;
   static constexpr int OFF_W3 = OFF_W2A + W2_AUX, OFF_W3A = OFF_W3 + W3_FEAT;
-  static constexpr int W_BYTES = OFF_W3A + W3_AUX;
+  static constexpr int W_BYTES = OFF_W3A + W3_AUX;                        // the part that lives in shared memory
+  static constexpr int OFF_B3 = W_BYTES;                                  // fp32 bias of layer 3, read from global once per thread
+  static constexpr int PACK_BYTES = W_BYTES + C3 * 4;                     //   (early kernel: added after the max)
   static constexpr int KBMAX = (KB1 > KB2 ? (KB1 > KB3 ? KB1 : KB3) : (KB2 > KB3 ? KB2 : KB3));
   static constexpr int SLOT_FEAT = KBMAX * 128 * 128;                     // activation tile, in place
   static constexpr int AUX_BUFS = EARLY ? 2 : 1;
@@ -79,7 +81,7 @@ using Sa1CfgLate = SaCfg<0, 64, 64, 128, 4, false, PDF_SA_TS != 0, false>;      
 using Sa2CfgLate = SaCfg<128, 128, 128, 256, 2, false, PDF_SA_TS != 0, false>;
 
 // One layer = (KB SW128 K-blocks x 4 K-steps) + 1 aux K-step, accumulating into d_tmem.
-template <int KB>
+template <int KB, bool AUX = true>
 __device__ __forceinline__ void issue_layer(uint32_t a_feat, uint32_t a_blk, uint32_t a_aux, uint32_t b_feat,
                                             uint32_t b_blk, uint32_t b_aux, uint32_t d_tmem, uint32_t idesc) {
   bool acc = false;
@@ -92,7 +94,7 @@ __device__ __forceinline__ void issue_layer(uint32_t a_feat, uint32_t a_blk, uin
       acc = true;
     }
   }
-  mma_bf16(d_tmem, desc_none(a_aux), desc_none(b_aux), idesc, acc);
+  if (AUX) mma_bf16(d_tmem, desc_none(a_aux), desc_none(b_aux), idesc, acc);
 }
 
 // Layer with the A operand in tensor memory: KB*4 K-steps over the packed activations (8 columns per step)
@@ -553,6 +555,10 @@ sa_mlp_max_early_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts
   }
   mbar_wait(smem_u32(&s_bar[0]), 0);                     // weights resident (their copy ran under the loads above)
 
+  float b3[Cfg::C3 / 128];                               // layer-3 bias of this thread's channel(s)
+#pragma unroll
+  for (int h = 0; h < Cfg::C3 / 128; ++h) b3[h] = __ldg(reinterpret_cast<const float*>(wpack + Cfg::OFF_B3) + h * 128 + p);
+
   uint32_t buf = 0;
   for (uint32_t t = t_first; t < nt; t += t_step) {
     const uint32_t sa_aux = sa_aux0 + buf * (128 * 32);
@@ -579,16 +585,21 @@ sa_mlp_max_early_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts
       issue_features(t, my_rowidx + buf * 128);
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    if (Cfg::CF > 0) fence_async_smem();                 // feature rows (the geometry block was fenced when written)
-    fence_before_sync();                                 // previous tile's TMEM reads are complete
-    named_bar_sync(1 + slot, 128);
-
     // ---- layer 1: D1[p, c1] = X[p, :] . W1[c1, :] ----
-    if (p == 0) {
-      fence_after_sync();
-      issue_layer<Cfg::KB1>(sa_feat, 128 * 128, sa_aux, sw, Cfg::C1 * 128, sw + Cfg::OFF_W1A, d1,
-                            idesc_bf16(128, Cfg::C1));
-      commit(bar);
+    // Level 1 (no feature rows): layer 1 of tile t+1 only needs its geometry block and D3's FIRST 64 columns, so it
+    // was issued from inside tile t's max epilogue (below) and its round trip ran under the second half of that
+    // epilogue; only a slot's first tile issues it here.
+    constexpr bool EARLY_L1 = Cfg::CF == 0;
+    if (!EARLY_L1 || t == t_first) {
+      if (Cfg::CF > 0) fence_async_smem();               // feature rows (the geometry block was fenced when written)
+      fence_before_sync();                               // previous tile's TMEM reads are complete
+      named_bar_sync(1 + slot, 128);
+      if (p == 0) {
+        fence_after_sync();
+        issue_layer<Cfg::KB1>(sa_feat, 128 * 128, sa_aux, sw, Cfg::C1 * 128, sw + Cfg::OFF_W1A, d1,
+                              idesc_bf16(128, Cfg::C1));
+        commit(bar);
+      }
     }
     mbar_wait(bar, phase); phase ^= 1;
     fence_after_sync();
@@ -621,10 +632,11 @@ sa_mlp_max_early_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts
     // ---- layer 3 (transposed): D3[c3, p] = W3[c3, :] . H2[p, :] ; max over each 64-point group ----
     if (p == 0) {
       fence_after_sync();
+      // no bias K-step here: max_p(x_p + b) = max_p(x_p) + b, the fp32 bias is added once per channel after the max
 #pragma unroll
       for (int h = 0; h < Cfg::C3 / 128; ++h)
-        issue_layer<Cfg::KB3>(sw + Cfg::OFF_W3 + h * (128 * 128), Cfg::C3 * 128, sw + Cfg::OFF_W3A + h * (128 * 32),
-                              sa_feat, 128 * 128, sa_aux, d3 + h * 128, idesc_bf16(128, 128));
+        issue_layer<Cfg::KB3, false>(sw + Cfg::OFF_W3 + h * (128 * 128), Cfg::C3 * 128, 0, sa_feat, 128 * 128, 0,
+                                     d3 + h * 128, idesc_bf16(128, 128));
       commit(bar);
     }
     // ---- under layer 3: geometry of tile t+1 into the other block; raw coordinates of t+2, index of t+3 ----
@@ -648,7 +660,7 @@ sa_mlp_max_early_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts
           tmem_ld32(d3 + lane_off + h * 128 + g * 64, v);
           tmem_ld32(d3 + lane_off + h * 128 + g * 64 + 32, u);
           tmem_ld_wait();
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          float a0 = -3.0e38f, a1 = -3.0e38f, a2 = -3.0e38f, a3 = -3.0e38f;
 #pragma unroll
           for (int q = 0; q < 32; q += 4) {
             a0 = max3(a0, __uint_as_float(v[q]), __uint_as_float(v[q + 1]));
@@ -656,9 +668,9 @@ sa_mlp_max_early_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts
             a2 = max3(a2, __uint_as_float(u[q]), __uint_as_float(u[q + 1]));
             a3 = max3(a3, __uint_as_float(u[q + 2]), __uint_as_float(u[q + 3]));
           }
-          m[g] = fmaxf(max3(a0, a1, a2), a3);
+          m[g] = fmaxf(fmaxf(max3(a0, a1, a2), a3) + b3[h], 0.f);     // relu(max + bias)
         } else {
-          float a0 = 0.f, a1 = 0.f;
+          float a0 = -3.0e38f, a1 = -3.0e38f;
 #pragma unroll
           for (int cc = 0; cc < 64; cc += 32) {
             uint32_t v[32];
@@ -670,7 +682,19 @@ sa_mlp_max_early_kernel(const float* __restrict__ pts, int n_src, int64_t ld_pts
               a1 = max3(a1, __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
             }
           }
-          m[g] = fmaxf(a0, a1);
+          m[g] = fmaxf(fmaxf(a0, a1) + b3[h], 0.f);                   // relu(max + bias)
+        }
+        if (EARLY_L1 && g == 0 && has_next) {
+          // every thread has read columns [0, 64) of D3 (group 0): D1 of tile t+1 may overwrite them now, while the
+          // second group's columns are still being reduced
+          fence_before_sync();
+          named_bar_sync(1 + slot, 128);
+          if (p == 0) {
+            fence_after_sync();
+            issue_layer<Cfg::KB1>(sa_feat, 128 * 128, sa_aux0 + (buf ^ 1) * (128 * 32), sw, Cfg::C1 * 128, sw + Cfg::OFF_W1A,
+                                  d1, idesc_bf16(128, Cfg::C1));
+            commit(bar);
+          }
         }
       }
       float* o = out + (int64_t)t * 2 * ld_out + out_col0 + h * 128 + p;
@@ -704,7 +728,7 @@ static inline float bf2f(uint16_t h) {
 template <class Cfg>
 static void pack_weights(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                          const float* b3, int c_in, uint8_t* out) {
-  memset(out, 0, Cfg::W_BYTES);
+  memset(out, 0, Cfg::PACK_BYTES);
   auto put = [&](int off, uint32_t byte, float v) {
     const uint16_t h = f2bf(v);
     memcpy(out + off + byte, &h, 2);
@@ -728,6 +752,7 @@ static void pack_weights(const float* W1, const float* b1, const float* W2, cons
     aux_bias(Cfg::OFF_W2A, r, b2[r]);
     for (int k = 0; k < Cfg::C1; ++k) put(Cfg::OFF_W2 + (k >> 6) * Cfg::C2 * 128, sw128_off(r, k & 63), W2[r * Cfg::C1 + k]);
   }
+  memcpy(out + Cfg::OFF_B3, b3, (size_t)Cfg::C3 * sizeof(float));
   for (int r = 0; r < Cfg::C3; ++r) {
     aux_bias(Cfg::OFF_W3A, r, b3[r]);
     for (int k = 0; k < Cfg::C2; ++k) put(Cfg::OFF_W3 + (k >> 6) * Cfg::C3 * 128, sw128_off(r, k & 63), W3[r * Cfg::C2 + k]);
@@ -778,8 +803,8 @@ static int launch_sa(const float* pts, int64_t n_clouds, int n_src, int64_t ld_p
 }  // namespace pdf
 
 extern "C" int64_t pdf_sa_pack_size(int c_in, int c1, int c2, int c3) {
-  if (c_in == 3 && c1 == 64 && c2 == 64 && c3 == 128) return pdf::Sa1Cfg::W_BYTES;
-  if (c_in == 131 && c1 == 128 && c2 == 128 && c3 == 256) return pdf::Sa2Cfg::W_BYTES;
+  if (c_in == 3 && c1 == 64 && c2 == 64 && c3 == 128) return pdf::Sa1Cfg::PACK_BYTES;
+  if (c_in == 131 && c1 == 128 && c2 == 128 && c3 == 256) return pdf::Sa2Cfg::PACK_BYTES;
   return -1;
 }
 
