@@ -1560,3 +1560,19 @@ def test_bn_backward_image_and_maxpool_forms():
         assert not val[M:].any()                                              # zero pad rows: dW reduces over them
         np.testing.assert_allclose(dg.cpu().numpy(), dgamma.cpu().numpy(), rtol=1e-4, atol=1e-4)
         np.testing.assert_allclose(db.cpu().numpy(), dbeta.cpu().numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_write_combined_staging_buffers():
+    """parallel.pinned_like: page-locked (write-combined) host copies keep shape, strides and memory format, are
+    seen as pinned by torch (so copy_(non_blocking=True) is a true async H2D copy) and round-trip bit for bit."""
+    from pdfnet_b200 import parallel
+    a = torch.randn((3, 8, 6, 5)).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    b = torch.arange(24, dtype=torch.int64).reshape(2, 12)
+    for t in (a, b):
+        for wc in (True, False):
+            h = parallel.pinned_like(t, write_combined=wc)
+            assert h.shape == t.shape and h.stride() == t.stride() and h.dtype == t.dtype and h.is_pinned()
+            d = torch.empty_like(t, device=DEV)
+            d.copy_(h, non_blocking=True)
+            torch.cuda.synchronize()
+            assert torch.equal(d.cpu(), t)

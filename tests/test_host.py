@@ -35,8 +35,8 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.pdf_version() >= 100
-    assert lib.pdf_sa_pack_size(3, 64, 64, 128) == 32768
-    assert lib.pdf_sa_pack_size(131, 128, 128, 256) == 147456
+    assert lib.pdf_sa_pack_size(3, 64, 64, 128) == 32768 + 128 * 4        # bf16 operand tiles + fp32 layer-3 bias
+    assert lib.pdf_sa_pack_size(131, 128, 128, 256) == 147456 + 256 * 4
     assert lib.pdf_sa_pack_size(3, 64, 64, 64) == -1
 
 
@@ -138,7 +138,8 @@ def test_sa_weight_image_layout(lib):
     w2, b2 = torch.randn((64, 64), generator=g), torch.randn((64,), generator=g)
     w3, b3 = torch.randn((128, 64), generator=g), torch.randn((128,), generator=g)
     img = ops.sa_pack_weights(w1, b1, w2, b2, w3, b3).numpy()
-    assert img.shape == (32768,)
+    assert img.shape == (32768 + 128 * 4,)
+    assert (img[32768:].view(np.float32) == b3.numpy()).all()            # fp32 layer-3 bias after the operand tiles
     bf = lambda t: t.bfloat16().float().numpy()
     _, aux1 = _unpack_image(img, 0, 0, 64, 0)
     assert (aux1[:, 0:3] == bf(w1)).all() and (aux1[:, 4:7] == bf(w1)).all()
@@ -156,6 +157,7 @@ def test_sa_weight_image_layout(lib):
     assert (feat1 == bf(w1b[:, 3:])).all() and (aux1[:, 0:3] == bf(w1b[:, :3])).all()
     feat3, _ = _unpack_image(img, 36864 * 2, 36864 * 2 + 65536, 256, 128)
     assert (feat3 == bf(w3b)).all()
+    assert (img[147456:].view(np.float32) == b3b.numpy()).all()
 
 
 def test_mano_pkl_loader_matches_npz_export(lib):
