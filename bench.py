@@ -493,6 +493,27 @@ def run_ours(args):
     kernels = run_cfg2(args, dev=dev, emit=False)["kernels"] if (not args.no_sub and rank == 0) else None
     del staging, chunk_steps, out_host, probe
     torch.cuda.empty_cache()
+
+    # ---- BASELINE cfg4 AS STATED: a FIXED batch of 1024 frames sharded over the N GPUs (strong scaling, no collective);
+    # at N = 8 that is the weak-scaling line above (128 frames per GPU), at N = 2 / 4 each GPU takes 512 / 256 frames ----
+    cfg4 = None
+    if not args.no_sub and world > 1 and 1024 % world == 0 and B == 128:
+        F4 = 1024 // world
+        try:
+            if F4 == B:
+                ms4 = ms_dev
+            else:
+                res4 = {k: v.to(dev) for k, v in make_inputs(F4, R, seed=4317 + rank, pyramid=args.pyramid, masks=args.masks).items()}
+                step4 = CapturedStep(lambda: hot_path(res4))
+                ms4, _ = timed_loop(step4.replay, min(args.steps, 5), 2)
+                del step4, res4
+                torch.cuda.empty_cache()
+            cfg4 = {"workload": "cfg4: 1024 frames sharded over %d GPUs (%d per GPU), same step as the main line" % (world, F4),
+                    "total_frames": 1024, "frames_per_gpu": F4, "ms_per_step": ms4, "value": 1024 / (ms4 * 1e-3),
+                    "unit": UNIT, "scaling": "strong"}
+        except Exception as e:
+            cfg4 = {"error": str(e)[:200]}
+            torch.cuda.synchronize()
     train = None
     if not args.no_sub:
         targs = argparse.Namespace(**vars(args))
@@ -583,7 +604,7 @@ def run_ours(args):
                         "joints copied back; bound by the PCIe link of the GPU (and, at N>1, of the switch it shares)"},
         "gpu_launches": int(launches), "eager_ms_per_step": ms_eager, "clocks": clocks, "roofline": roofline,
         "stages_ms": stage_report, "stages_tflops": stage_tflops, "stages_hbm": stage_hbm,
-        "value_sustained": sustained, "kernels": kernels, "train": train,
+        "value_sustained": sustained, "kernels": kernels, "train": train, "cfg4": cfg4,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))

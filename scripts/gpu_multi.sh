@@ -21,6 +21,6 @@ for f in ("gpurun_out/bench_${N}gpu.json", "gpurun_out/bench_${N}gpu_pinned.json
         print(f, "unreadable", e); continue
     print(f, "N", j["n_gpus"], "value", round(j["value"]), "ms", round(j["ms_per_step"],3), "e2e", round(j["e2e"]["value"]), round(j["e2e"]["ms_per_step"],3), j["e2e"]["h2d_gbs_per_rank"], j["e2e"].get("host_alloc"))
     t = j.get("train")
-    print("  train", t and {k: t.get(k) for k in ("value","ms_per_step","allreduce_bytes_per_step","allreduce_buckets","error")})
+    print("  cfg4", j.get("cfg4")); print("  train", t and {k: t.get(k) for k in ("value","ms_per_step","allreduce_bytes_per_step","allreduce_buckets","error")})
 PY
 cat gpurun_out/topo_${N}gpu.txt | head -30
