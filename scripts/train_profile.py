@@ -15,7 +15,7 @@ from pdfnet_b200 import HandFusion  # noqa: E402
 
 R, B = 256, int(os.environ.get("PDF_TRAIN_FRAMES", 64))
 dev = torch.device("cuda", 0)
-model = HandFusion(bench.make_opt(R), precision="fp32")
+model = HandFusion(bench.make_opt(R), precision=os.environ.get("PDF_TRAIN_PRECISION", "fp32"))
 st = bench.load_states()
 sd = {"pointnet_plus." + k: v for k, v in st["pointnet"].items()}
 sd.update({"sft." + k: v for k, v in st["sft"].items()})
