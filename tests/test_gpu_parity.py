@@ -307,6 +307,43 @@ def test_sa_bf16_kernel_vs_fp32_path():
     assert e2 < 3e-2, e2
 
 
+@torch.no_grad()
+def test_sa_bf16_kernel_tile_mappings():
+    """The early-staging kernel's tile -> (cloud, centroid) mapping: a centroid count whose tiles per cloud are not a
+    power of two (384 -> 192 tiles, the division path), a single cloud with fewer tiles than slots (idle slots), and
+    level 2 fed by fp32 feature rows (the legacy input form, staged at the loop top) - each against the FFMA path."""
+    from pdfnet_b200 import PointNet_Plus, ops
+    m32 = PointNet_Plus(_opt(default_resolution=64), precision="fp32")
+    m32.load_state_dict(synth.pointnet_plus_state(seed=317), strict=False)
+    m16 = PointNet_Plus(_opt(default_resolution=64), precision="bf16")
+    m16.load_state_dict(synth.pointnet_plus_state(seed=317), strict=False)
+    m32, m16 = m32.to(DEV).eval(), m16.to(DEV).eval()
+    f32, f16 = m32.folded(), m16.folded()
+    for B, N1 in ((3, 384), (1, 128), (5, 512)):
+        pts = synth.clouds(B, seed=20 + B).to(DEV)
+        idx1 = ops.knn_ball(pts, N1, 64, 0.015)
+        res = []
+        for m, f in ((m32, f32), (m16, f16)):
+            x1 = torch.zeros((B, N1, 132), device=DEV)
+            x1[:, :, 0:3] = pts[:, :N1]
+            m._sa(pts, idx1, "netR_1", f, x1, None)
+            res.append(x1)
+        assert (res[0][:, :, :4] == res[1][:, :, :4]).all()
+        assert rel_err(res[1].cpu().numpy(), res[0].cpu().numpy()) < 2e-2, (B, N1)
+        # level 2 from fp32 rows [xyz, pad, 128 features] (feat_bf16=None)
+        N2 = N1 // 4 // 2 * 2
+        x1 = res[0]
+        idx2 = ops.knn_ball(x1, N2, 64, 0.04)
+        x2a = torch.zeros((B, N2, 260), device=DEV)
+        x2a[:, :, 0:3] = x1[:, :N2, 0:3]
+        m32._sa(x1, idx2, "netR_2", f32, x2a, f32["netR_2_w1pad"])
+        x2b = torch.zeros((B, N2, 260), device=DEV)
+        (w1, _), (w2, _), (w3, _) = f16["netR_2"]
+        ops.sa_mlp_max_bf16(x1, idx2, f16["netR_2_pack"], w1.shape[1], w1.shape[0], w2.shape[0], w3.shape[0], x2b, 4)
+        assert (x2b[:, :, :3] == x1[:, :N2, :3]).all()
+        assert rel_err(x2b[:, :, 4:].cpu().numpy(), x2a[:, :, 4:].cpu().numpy()) < 3e-2, (B, N1, "level 2")
+
+
 # ----------------------------------------------------------------------------- depth -> clouds
 
 @torch.no_grad()
