@@ -660,8 +660,23 @@ class decoder(nn.Module):
                                                        hd(self.params_head), hd(self.root_head), hd(self.coord_head))
             # 252 -> 778 up-sampling of both hands as ONE GEMM over rows (sample, xyz)
             vt = v252_2.transpose(1, 2).contiguous().view(2 * B * 3, V)
-            v778_2 = self._linear(vt, self.unsample_layer.weight.detach(), tc_min_rows=256)
-            v778_2 = v778_2.reshape(2 * B, 3, -1).transpose(1, 2).contiguous()
+            # with the joint regressors set (a15) the 21 joints ride along as 2 x 21 extra output columns of the same
+            # GEMM: joints = full_regressor @ (U @ v252) = (full_regressor @ U) @ v252, the product of the two constant
+            # matrices taken once in fp64 - no separate regression launch per hand
+            Wup, nv = self.unsample_layer.weight.detach(), self.vNum_mano
+            have_reg = all(getattr(self, "_full_regressor_" + sd, None) is not None for sd in ("left", "right"))
+            if have_reg:
+                key = ("up+joints", Wup.data_ptr(), Wup._version, self._full_regressor_left.data_ptr(),
+                       self._full_regressor_right.data_ptr())
+                Wcat = self._cache.get(key)
+                if Wcat is None:
+                    Wcat = self._cache[key] = torch.cat(
+                        [Wup] + [(getattr(self, "_full_regressor_" + sd).double() @ Wup.double()).float()
+                                 for sd in ("left", "right")], 0).contiguous()
+                up_out = self._linear(vt, Wcat, tc_min_rows=256)
+            else:
+                up_out = self._linear(vt, Wup, tc_min_rows=256)
+            v778_2 = up_out[:, :nv].reshape(2 * B, 3, nv).transpose(1, 2).contiguous()
             for si, side in enumerate(("left", "right")):
                 params, v252, v778 = params2[si * B:(si + 1) * B], v252_2[si * B:(si + 1) * B], v778_2[si * B:(si + 1) * B]
                 root[side] = root2[si * B:(si + 1) * B]
@@ -672,9 +687,11 @@ class decoder(nn.Module):
                 result["verts3d"][side], result["verts2d"][side] = v778, d2
                 other["verts3d_MANO_list"][side].append(m3)
                 other["verts2d_MANO_list"][side].append(m2)
-                reg = getattr(self, "_full_regressor_" + side, None)
-                if reg is not None:
-                    other.setdefault("joints3d", {})[side] = ops.joint_regress(reg, v778)
+                if have_reg:
+                    jc = up_out[si * B * 3:(si + 1) * B * 3, nv + 21 * si:nv + 21 * (si + 1)]
+                    other.setdefault("joints3d", {})[side] = jc.reshape(B, 3, 21).transpose(1, 2).contiguous()
+                elif getattr(self, "_full_regressor_" + side, None) is not None:
+                    other.setdefault("joints3d", {})[side] = ops.joint_regress(getattr(self, "_full_regressor_" + side), v778)
             paramsDict = {"scale": scale, "trans2d": trans2d, "root": root}
             handDictList = [{"verts3d": verts3d, "verts2d": verts2d}]
             return result, paramsDict, handDictList, other

@@ -1427,6 +1427,26 @@ def test_gcn_decoder_tensor_core_and_batch():
 
 
 @torch.no_grad()
+def test_gcn_decoder_joint_regressor_epilogue():
+    """decoder.set_joint_regressors (a15): otherInfo['joints3d'][side] == full_regressor @ verts3d
+    (Mano_model.py:309-323 applied as demo.py:217-218 does), on the FFMA path (B = 2) and on the tensor-core path where
+    the joints are extra output columns of the up-sampling GEMM (B = 96: 576 rows)."""
+    from pdfnet_b200 import process_J_regressor
+    m, _ = _decoder("bf16x3")
+    Jl, Jr = mano_tables("left")["J_regressor"], mano_tables("right")["J_regressor"]
+    m.set_joint_regressors(Jl, Jr)
+    for B in (2, 96):
+        fuse = torch.randn((B, 2, 1024), generator=torch.Generator().manual_seed(80 + B)).to(DEV)
+        result, _, _, other = m(fuse[:, 0], fuse[:, 1], None)
+        for side, J in (("left", Jl), ("right", Jr)):
+            reg = process_J_regressor(torch.as_tensor(np.asarray(J), dtype=torch.float32)).double()
+            want = torch.matmul(reg, result["verts3d"][side].double().cpu())
+            got = other["joints3d"][side]
+            assert tuple(got.shape) == (B, 21, 3)
+            assert rel_err(got.cpu().numpy(), want.numpy()) < 1e-5, (B, side, rel_err(got.cpu().numpy(), want.numpy()))
+
+
+@torch.no_grad()
 def test_decoder_primitives_vs_torch():
     """row_combine / graph_cheby_ln / mha / decoder_project against torch-CPU on ragged shapes."""
     import torch.nn.functional as F
