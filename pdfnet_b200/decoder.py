@@ -612,23 +612,25 @@ class decoder(nn.Module):
             grouped = self._grouped_ok(B)
             if grouped:
                 fboth = self._features_grouped(global_feature_left, global_feature_right)
-            for side, gfeat in (() if grouped else (("left", global_feature_left), ("right", global_feature_right))):
-                gf = getattr(self, "gf_layer_" + side)
-                g = self._linear(L.f32c(gfeat), gf[0].weight.detach(), gf[0].bias.detach(), tc_min_rows=128)
-                gpad = torch.zeros((B, cin0), dtype=torch.float32, device=g.device)
-                ops.row_combine(g, ln=self._ln(gf[1]), ln_out=gpad[:, :cin0 - 3])
-                # Lf = cat([g repeated over the 63 vertices, pe], -1) + position embedding (:197-198, DualGraph.py:76-80)
-                x[side] = self._level_input(gpad, None, c[("row0", side)], self.verts[0], self.verts[0])
             cur = torch.cuda.current_stream()
             if self._side is None:
                 self._side = torch.cuda.Stream()
+            if not grouped:
+                self._side.wait_stream(cur)                    # fork: the right hand lives on the side stream from its gf layer on
+                global_feature_right.record_stream(self._side)
+            for side, gfeat in (() if grouped else (("left", global_feature_left), ("right", global_feature_right))):
+                with torch.cuda.stream(self._side if side == "right" else cur):
+                    gf = getattr(self, "gf_layer_" + side)
+                    g = self._linear(L.f32c(gfeat), gf[0].weight.detach(), gf[0].bias.detach(), tc_min_rows=128)
+                    gpad = torch.zeros((B, cin0), dtype=torch.float32, device=g.device)
+                    ops.row_combine(g, ln=self._ln(gf[1]), ln_out=gpad[:, :cin0 - 3])
+                    # Lf = cat([g repeated over the 63 vertices, pe], -1) + position embedding (:197-198, DualGraph.py:76-80)
+                    x[side] = self._level_input(gpad, None, c[("row0", side)], self.verts[0], self.verts[0])
             for li, V in (() if grouped else enumerate(self.verts)):
                 # the two hands are independent up to the cross attention: the right hand's GraphLayer and
                 # SelfAttn run on a second stream (captured as a fork / join inside a CUDA graph); from the
                 # cross attention of level 0 on the right hand's tensors are produced there (_inter_attn)
                 att = self.dual_gcn.layers[li].attn
-                if li == 0:
-                    self._side.wait_stream(cur)
                 with torch.cuda.stream(self._side):
                     xr = self._graph_layer(x["right"][0], x["right"][1], li, "right", V, B * V)
                     r2, rf = self._self_attn(xr, li, "R", att.R_self_attn_layer, B, V)
