@@ -324,6 +324,22 @@ def run_ours(args):
                     other["joints3d"]["left"], other["joints3d"]["right"])
         return fused, verts, joints
 
+    def hot_front(d):
+        """Pipeline stage 1 (everything up to fuse_feat + the MANO branch, which joins before the stage ends)."""
+        choose, cloud, _ = ops.depth2pcl(d["depth"], d["mask"], d["Kinv"], d["valid"], seed=D2P_SEED)
+        fused, theta = model(cloud, [d["l0"], d["l1"], d["l2"]], choose, d["center"], with_mano=True, mano_stream=mano_side)
+        with torch.cuda.stream(mano_side):
+            verts, joints, _ = mano_tail_pair(theta, d["ind"], d["K"], mano_l, mano_r, input_res=R)
+        torch.cuda.current_stream().wait_stream(mano_side)
+        for t in (verts, joints):
+            t.record_stream(torch.cuda.current_stream())
+        return fused, (fused, verts, joints)
+
+    def hot_back(fused):
+        """Pipeline stage 2: GCN decoder + joint regressor on a batch's fuse_feat."""
+        result, _, _, other = dec(fused[:, 0], fused[:, 1], None)
+        return (result["verts3d"]["left"], result["verts3d"]["right"], other["joints3d"]["left"], other["joints3d"]["right"])
+
     def barrier():
         if world > 1:
             torch.distributed.barrier()
@@ -366,6 +382,30 @@ def run_ours(args):
             sys.stderr.write("bench: CUDA-graph capture failed (%s); reporting the eager launch path\n" % e)
             torch.cuda.synchronize()
             args.no_graph, step = True, None
+    # ---- the same work software-pipelined over consecutive batches: replay i = point branch of batch i beside the
+    # GCN decoder of batch i-1 (pdfnet_b200.graph.PipelinedStep); checked against the serial step's outputs ----
+    pipelined = None
+    if step is not None and dec is not None and args.pipeline:
+        try:
+            from pdfnet_b200.graph import PipelinedStep
+            prio = int(os.environ.get("PDF_PIPE_BACK_PRIO", "0"))
+            if prio:
+                dec._side = torch.cuda.Stream(device=dev, priority=prio)
+            pstep = PipelinedStep(lambda: hot_front(resident), hot_back, back_priority=prio)
+            ms_pipe, _ = timed_loop(pstep.replay, args.steps, args.warmup)
+            fo, bo = pstep.replay()
+            torch.cuda.synchronize()
+            ref_out = step.replay()
+            torch.cuda.synchronize()
+            same = all(torch.equal(a, b) for a, b in zip(tuple(fo) + tuple(bo), ref_out))
+            dr = pstep.flush()
+            torch.cuda.synchronize()
+            same = same and all(torch.equal(a, b) for a, b in zip(dr, ref_out[3:]))
+            pipelined = {"ms_per_step": ms_pipe, "value": world * B / (ms_pipe * 1e-3), "unit": UNIT,
+                         "launches": pstep.launches, "outputs_equal_serial_step": bool(same), "back_priority": prio}
+        except Exception as e:
+            pipelined = {"error": str(e)[:200]}
+            torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     # ---- sustained: the same step back to back for >= args.sustained_seconds (power-capped clocks) ----
     sustained = None
@@ -604,7 +644,7 @@ def run_ours(args):
                         "joints copied back; bound by the PCIe link of the GPU (and, at N>1, of the switch it shares)"},
         "gpu_launches": int(launches), "eager_ms_per_step": ms_eager, "clocks": clocks, "roofline": roofline,
         "stages_ms": stage_report, "stages_tflops": stage_tflops, "stages_hbm": stage_hbm,
-        "value_sustained": sustained, "kernels": kernels, "train": train, "cfg4": cfg4,
+        "pipelined": pipelined, "value_sustained": sustained, "kernels": kernels, "train": train, "cfg4": cfg4,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
@@ -1005,6 +1045,10 @@ def main():
     ap.add_argument("--sustained-seconds", type=float, default=2.0,
                     help="cfg3: also loop the step for this long and report value_sustained (0 = off)")
     ap.add_argument("--bucket-mb", type=int, default=4, help="cfg5: gradient all-reduce bucket size (MiB)")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="cfg3: also time the step software-pipelined over consecutive batches (point branch of batch i beside "
+                         "the GCN decoder of batch i-1, pdfnet_b200.graph.PipelinedStep) -> 'pipelined' sub-record; measured: no "
+                         "gain (3.11 vs 3.15 ms, DESIGN 3.5), hence off by default")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch path instead of a CUDA-graph replay")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="H2D/compute overlap chunks in the e2e measurement")
     ap.add_argument("--host-alloc", default="wc", choices=["wc", "pinned"],

@@ -1383,6 +1383,50 @@ def test_gcn_decoder_vs_reference_golden():
 
 
 @torch.no_grad()
+def test_pipelined_step_equals_the_serial_pass():
+    """pdfnet_b200.graph.PipelinedStep: replay i runs the point branch of batch i beside the GCN decoder of batch
+    i-1 (two streams inside one graph).  The decoder results delivered one replay later - and by flush() for the
+    last batch - equal the serial pass bit for bit."""
+    from pdfnet_b200 import HandFusion
+    from pdfnet_b200.graph import PipelinedStep
+    R, B = 64, 16
+    opt = _opt(default_resolution=R)
+    m = HandFusion(opt, "bf16")
+    m.pointnet_plus.load_state_dict(synth.pointnet_plus_state(seed=317), strict=False)
+    m.sft.load_state_dict(synth.fusion_sft_state(seed=317))
+    m = m.to(DEV).eval()
+    dec, _ = _decoder("bf16x3")
+    cloud = synth.clouds(2 * B, seed=81).view(B, 2, 1024, 3).to(DEV)
+    choose = synth.choose_indices(2 * B, R, seed=81).view(B, 2, 1024).to(DEV)
+    emb = [e.to(DEV) for e in synth.pyramid(B, R, seed=81)]
+    cen = torch.randn((B, 2, 1024), generator=torch.Generator().manual_seed(81)).to(DEV)
+
+    def front():
+        fused = m(cloud, emb, choose, cen)
+        return fused, (fused,)
+
+    def back(fused):
+        res = dec(fused[:, 0], fused[:, 1], None)
+        return res[0]["verts3d"]["left"], res[0]["verts3d"]["right"]
+
+    def serial():
+        fused = m(cloud, emb, choose, cen)
+        return (fused.clone(),) + tuple(t.clone() for t in back(fused))
+
+    step = PipelinedStep(front, back)
+    assert step.launches > 100
+    ref_a = serial()                                             # batch A
+    step.replay()                                                # front(A) | back(warm-up hand-over)
+    cloud.copy_(synth.clouds(2 * B, seed=82).view(B, 2, 1024, 3))   # batch B, same buffers
+    ref_b = serial()
+    (fused_b,), dec_a = step.replay()                            # front(B) | back(A)
+    assert torch.equal(fused_b, ref_b[0]) and not torch.equal(ref_a[0], ref_b[0])
+    assert all(torch.equal(x, y) for x, y in zip(dec_a, ref_a[1:]))
+    dec_b = step.flush()                                         # back(B)
+    assert all(torch.equal(x, y) for x, y in zip(dec_b, ref_b[1:]))
+
+
+@torch.no_grad()
 def test_gcn_decoder_tensor_core_and_batch():
     """Tensor-core path at a batch large enough to take it (rows >= 1024): split-bf16 operands hold the
     fp32 tolerance (2e-4 vs the oracle); deterministic; batch-independent."""
