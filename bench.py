@@ -419,80 +419,162 @@ def run_ours(args):
                      "seconds": args.sustained_seconds, "clocks": s2.stop() if rank == 0 else None}
 
     # ---- end to end through the public API with HOST buffers ----
-    # Every step copies ALL hot-path inputs from pinned host memory and the results back.  The batch is cut into
-    # chunks and the staging buffers are double-buffered ACROSS steps: while chunk c of step i computes, the copy
-    # stream already moves later chunks / the next step's inputs, and a third stream returns the outputs.
-    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
+    # Every step takes ALL hot-path inputs from page-locked host memory and returns the results there.  The batch is
+    # cut into chunks and the staging buffers are double-buffered ACROSS steps: while chunk c of step i computes, the
+    # copy stream already moves later chunks / the next step's inputs, and a third stream returns the outputs.
+    # Two hand-offs of the RGB feature pyramid (92 % of the input bytes) are measured:
+    #   zero-copy: the bf16 channels-last maps STAY in page-locked host memory and the gather kernel reads the pixels
+    #              `choose` selects in place over the PCIe link (2 x (1024 x 6 + 512 x 128 + 128 x 512) B of a frame's
+    #              4.6 MB); depth, masks, intrinsics, centre features / indices are copied as before;
+    #   copy:      every input, the whole pyramid included, is copied to device staging buffers first.
+    input_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
     n_chunks = max(1, min(args.e2e_chunks, B))
     bounds = [parallel.shard_range(B, c, n_chunks) for c in range(n_chunks)]
     copy_stream, out_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     n_sets = 2
-    staging = [{k: torch.empty_like(resident[k]) for k in pinned} for _ in range(n_sets)]
     names = ("fused", "verts", "joints", "gcn_verts_left", "gcn_verts_right", "gcn_joints_left", "gcn_joints_right")
-    chunk_steps = None
-    if not args.no_graph:                             # one captured graph per (staging set, chunk)
+    PYR = ("l0", "l1", "l2")
+    zc_possible = args.pyramid == "bf16-nhwc" and args.precision == "bf16"
+    d2h_bytes = [0]
+
+    def pcie_rx_sampler(stop, rows):
+        """NVML PCIe receive throughput of this GPU (KB/s over 20 ms windows) while the e2e loop runs."""
         try:
-            chunk_steps = [[CapturedStep(lambda lo=lo, hi=hi, st=st: hot_path({k: v[lo:hi] for k, v in st.items()}),
-                                         warmup=2) for lo, hi in bounds] for st in staging]
-        except Exception as e:
-            sys.stderr.write("bench: CUDA-graph capture of the e2e chunks failed (%s); eager chunks\n" % e)
-            torch.cuda.synchronize()
-            chunk_steps = None
-    probe = hot_path({k: v[bounds[0][0]:bounds[0][1]] for k, v in staging[0].items()})
-    out_host = [{n: torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory() for n, t in zip(names, probe)}
-                for _ in range(n_sets)]
-    consumed = [None] * n_sets                        # event: the compute of the step that last used this set is done
-    drained = [None] * n_sets                         # event: its outputs have left the device
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            while not stop.is_set():
+                rows.append(pynvml.nvmlDeviceGetPcieThroughput(h, pynvml.NVML_PCIE_UTIL_RX_BYTES))
+        except Exception:
+            pass
 
-    def e2e_step(i):
-        main = torch.cuda.current_stream()
-        st = i % n_sets
-        if consumed[st] is not None:
-            copy_stream.wait_event(consumed[st])
-        events = []
-        with torch.cuda.stream(copy_stream):
-            for lo, hi in bounds:
-                for k, v in pinned.items():
-                    staging[st][k][lo:hi].copy_(v[lo:hi], non_blocking=True)
+    zc_arg = args.e2e_zero_copy_levels
+    if zc_arg == "auto":
+        zc_arg = "l1,l2" if world == 1 else "l0,l1,l2"
+    zc_levels = tuple(k for k in PYR if k in zc_arg.split(","))
+    comp_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.e2e_streams))]
+    zc_px_bytes = {"l0": 1024 * 6, "l1": 512 * 128, "l2": 128 * 512}          # per cloud (SURVEY 8d, bf16 features)
+
+    def measure_e2e(zero_copy):
+        zc = zc_levels if zero_copy else ()
+        # host side: two page-locked pyramid sets read in place alternately (no step re-reads the addresses of the
+        # step before it); device side: double-buffered staging for everything that is copied
+        host_sets = [pinned] + [{k: (parallel.pinned_like(pinned[k], write_combined=(args.host_alloc == "wc")) if k in zc
+                                     else pinned[k]) for k in pinned} for _ in range(n_sets - 1)]
+        staging = [{k: (host_sets[st][k] if k in zc else torch.empty_like(resident[k])) for k in pinned}
+                   for st in range(n_sets)]
+        copied = [k for k in pinned if k not in zc]
+        copy_bytes = sum(pinned[k].numel() * pinned[k].element_size() for k in copied)
+        zc_bytes = 2 * B * sum(zc_px_bytes[k] for k in zc)                            # algorithmic bytes read in place
+        chunk_steps = None
+        if not args.no_graph:                         # one captured graph per (staging set, chunk)
+            try:
+                chunk_steps = [[CapturedStep(lambda lo=lo, hi=hi, st=st: hot_path({k: v[lo:hi] for k, v in st.items()}),
+                                             warmup=2) for lo, hi in bounds] for st in staging]
+            except Exception as e:
+                sys.stderr.write("bench: CUDA-graph capture of the e2e chunks failed (%s); eager chunks\n" % e)
+                torch.cuda.synchronize()
+                chunk_steps = None
+        probe = hot_path({k: v[bounds[0][0]:bounds[0][1]] for k, v in staging[0].items()})
+        out_host = [{n: torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory() for n, t in zip(names, probe)}
+                    for _ in range(n_sets)]
+        d2h_bytes[0] = sum(v.numel() * v.element_size() for v in out_host[0].values())
+        consumed = [None] * n_sets                    # event: the compute of the step that last used this set is done
+        drained = [None] * n_sets                     # event: its outputs have left the device
+
+        def e2e_step(i):
+            # chunks alternate between the compute streams: while one chunk computes, the next one's depth2pcl and
+            # (in zero-copy mode) its gather over the PCIe link are already under way
+            st = i % n_sets
+            for ev in consumed[st] or ():
+                copy_stream.wait_event(ev)
+            events = []
+            with torch.cuda.stream(copy_stream):
+                for lo, hi in bounds:
+                    for k in copied:
+                        staging[st][k][lo:hi].copy_(pinned[k][lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    events.append(ev)
+            for ci, ((lo, hi), ev) in enumerate(zip(bounds, events)):
+                S = comp_streams[(i * n_chunks + ci) % len(comp_streams)]
+                with torch.cuda.stream(S):
+                    if drained[st] is not None:
+                        S.wait_event(drained[st])     # graph outputs of this set are free to be overwritten
+                    S.wait_event(ev)
+                    outs = chunk_steps[st][ci].replay() if chunk_steps else \
+                        hot_path({k: v[lo:hi] for k, v in staging[st].items()})
+                    done = torch.cuda.Event()
+                    done.record(S)
+                with torch.cuda.stream(out_stream):
+                    out_stream.wait_event(done)
+                    for n, t in zip(names, outs):
+                        out_host[st][n][lo:hi].copy_(t, non_blocking=True)
+                        t.record_stream(out_stream)
+            consumed[st] = []
+            for S in comp_streams:
                 ev = torch.cuda.Event()
-                ev.record(copy_stream)
-                events.append(ev)
-        if drained[st] is not None:
-            main.wait_event(drained[st])              # graph outputs of this set are free to be overwritten
-        for ci, ((lo, hi), ev) in enumerate(zip(bounds, events)):
-            main.wait_event(ev)
-            outs = chunk_steps[st][ci].replay() if chunk_steps else \
-                hot_path({k: v[lo:hi] for k, v in staging[st].items()})
-            done = torch.cuda.Event()
-            done.record(main)
-            with torch.cuda.stream(out_stream):
-                out_stream.wait_event(done)
-                for n, t in zip(names, outs):
-                    out_host[st][n][lo:hi].copy_(t, non_blocking=True)
-                    t.record_stream(out_stream)
-        consumed[st] = torch.cuda.Event()
-        consumed[st].record(main)
-        drained[st] = torch.cuda.Event()
-        drained[st].record(out_stream)
+                ev.record(S)
+                consumed[st].append(ev)
+            drained[st] = torch.cuda.Event()
+            drained[st].record(out_stream)
 
-    def e2e_loop(steps, warmup):
-        for i in range(warmup):
+        for S in comp_streams:
+            S.wait_stream(torch.cuda.current_stream())
+        for i in range(args.warmup):
             e2e_step(i)
         barrier()
+        stop, rows = threading.Event(), []
+        th = threading.Thread(target=pcie_rx_sampler, args=(stop, rows), daemon=True)
+        steps = max(args.steps, 40)                   # >= 40 steps: the region spans several 20 ms NVML windows
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        th.start()
         a.record()
+        for S in comp_streams + [copy_stream]:
+            S.wait_event(a)                           # nothing of the timed steps starts before the clock does
         for i in range(steps):
-            e2e_step(warmup + i)
+            e2e_step(args.warmup + i)
         main = torch.cuda.current_stream()
+        for S in comp_streams:
+            main.wait_stream(S)
         main.wait_stream(copy_stream)
         main.wait_stream(out_stream)                  # the last results are on the host when the clock stops
         b.record()
+        torch.cuda.synchronize()
+        stop.set()
         barrier()
-        return parallel.max_over_ranks(a.elapsed_time(b) / steps, dev)
+        ms = parallel.max_over_ranks(a.elapsed_time(b) / steps, dev)
+        # the zero-copy results are the copy path's results: same kernels on the same values
+        res = {n: out_host[(args.warmup + steps - 1) % n_sets][n].clone() for n in names}
+        th.join(timeout=1.0)
+        rx = sorted(rows[1:-1]) if len(rows) > 2 else sorted(rows)
+        rec = {"value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+               "h2d_bytes_per_step": copy_bytes + zc_bytes, "copied_bytes_per_step": copy_bytes,
+               "zero_copy_bytes_per_step": zc_bytes, "d2h_bytes_per_step": d2h_bytes[0],
+               "pcie_rx_gbs_nvml": round(rx[len(rx) // 2] * 1024 / 1e9, 2) if rx else None}
+        del chunk_steps, staging, probe, out_host
+        torch.cuda.empty_cache()
+        return rec, res
 
-    ms_e2e = e2e_loop(args.steps, args.warmup)
+    e2e_modes = {}
+    res_by_mode = {}
+    for mode in (("zero-copy", "copy") if zc_possible else ("copy",)):
+        try:
+            e2e_modes[mode], res_by_mode[mode] = measure_e2e(mode == "zero-copy")
+        except Exception as e:
+            if mode == "copy":
+                raise
+            sys.stderr.write("bench: zero-copy e2e failed (%s); copy mode only\n" % e)
+            torch.cuda.synchronize()
+    if "zero-copy" in e2e_modes:
+        e2e_modes["zero-copy"]["equals_copy_mode"] = bool(all(torch.equal(res_by_mode["zero-copy"][n], res_by_mode["copy"][n])
+                                                              for n in names))
+    e2e_mode = args.e2e_pyramid if args.e2e_pyramid in e2e_modes else "copy"
+    ms_e2e = e2e_modes[e2e_mode]["ms_per_step"]
+    h2d_bytes = e2e_modes[e2e_mode]["h2d_bytes_per_step"]
+    d2h_bytes = d2h_bytes[0]
+    del res_by_mode
     torch.cuda.synchronize()
-    d2h_bytes = sum(v.numel() * v.element_size() for v in out_host[0].values())
 
     # ---- per-stage timing (roofline of the dominant kernel), same inputs, L2 flushed ----
     # The eager launch path is CPU-bound (one ctypes call per kernel): without a head start the event pairs would
@@ -531,7 +613,6 @@ def run_ours(args):
 
     # ---- BASELINE cfg2 (SA microbench) and cfg5 (training step) sub-records, same process ----
     kernels = run_cfg2(args, dev=dev, emit=False)["kernels"] if (not args.no_sub and rank == 0) else None
-    del staging, chunk_steps, out_host, probe
     torch.cuda.empty_cache()
 
     # ---- BASELINE cfg4 AS STATED: a FIXED batch of 1024 frames sharded over the N GPUs (strong scaling, no collective);
@@ -632,16 +713,22 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": config_dict(args, world, B, {
-            "l2": "256 MiB flush write between timed iterations; inputs %.2f GB > L2" % (h2d_bytes / 1e9),
+            "l2": "256 MiB flush write between timed iterations; inputs %.2f GB > L2" % (input_bytes / 1e9),
             "launch": "one CUDA-graph replay per step" if graphed else "eager (one ctypes call per kernel)"}),
-        "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e, "chunks": n_chunks,
-                "host_alloc": args.host_alloc,
-                "h2d_gbs_per_rank": round(h2d_bytes / (ms_e2e * 1e-3) / 1e9, 2),
-                "note": "all hot-path inputs (depth, uint8 masks, K, bf16 channels-last feature pyramid, centre "
-                        "features, centre indices) copied from pinned host memory every step; staging double-buffered "
-                        "across steps (copy / compute / result streams); fused features, MANO and GCN meshes and "
-                        "joints copied back; bound by the PCIe link of the GPU (and, at N>1, of the switch it shares)"},
+        "e2e": dict(e2e_modes[e2e_mode], **{
+            "chunks": n_chunks, "compute_streams": len(comp_streams), "host_alloc": args.host_alloc,
+            "pyramid_handoff": e2e_mode, "zero_copy_levels": list(zc_levels) if e2e_mode == "zero-copy" else [],
+            "input_bytes_on_host_per_step": input_bytes,
+            "h2d_gbs_per_rank": round(h2d_bytes / (ms_e2e * 1e-3) / 1e9, 2),
+            "note": ("all hot-path inputs live in page-locked host memory every step.  depth, uint8 masks, K, centre "
+                     "features and centre indices are copied to the device; the bf16 channels-last feature pyramid "
+                     + ("is NOT copied: the gather kernel reads the pixels `choose` selects in place over the PCIe link "
+                        "(zero_copy_bytes_per_step = algorithmic bytes of those pixels; two host pyramid sets read "
+                        "alternately); " if e2e_mode == "zero-copy" else "is copied whole; ")
+                     + "staging double-buffered across steps (copy / compute / result streams); fused features, MANO "
+                       "and GCN meshes and joints copied back to pinned host memory inside the timed region; "
+                       "pcie_rx_gbs_nvml = the GPU's own PCIe receive counter (median 20 ms window) during the loop")}),
+        "e2e_other_handoff": {k: v for k, v in e2e_modes.items() if k != e2e_mode},
         "gpu_launches": int(launches), "eager_ms_per_step": ms_eager, "clocks": clocks, "roofline": roofline,
         "stages_ms": stage_report, "stages_tflops": stage_tflops, "stages_hbm": stage_hbm,
         "pipelined": pipelined, "value_sustained": sustained, "kernels": kernels, "train": train, "cfg4": cfg4,
@@ -1050,7 +1137,17 @@ def main():
                          "the GCN decoder of batch i-1, pdfnet_b200.graph.PipelinedStep) -> 'pipelined' sub-record; measured: no "
                          "gain (3.11 vs 3.15 ms, DESIGN 3.5), hence off by default")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch path instead of a CUDA-graph replay")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="H2D/compute overlap chunks in the e2e measurement")
+    ap.add_argument("--e2e-pyramid", default="zero-copy", choices=["zero-copy", "copy"],
+                    help="e2e hand-off of the host-resident bf16 feature pyramid: zero-copy = the gather kernel reads the "
+                         "selected pixels in place from page-locked host memory (default), copy = dense host->device copy "
+                         "of the maps first; both are measured, the other one is reported as e2e_other_handoff")
+    ap.add_argument("--e2e-zero-copy-levels", default="auto",
+                    help="which pyramid maps the zero-copy hand-off reads in place (the rest is copied).  auto: l1,l2 on one "
+                         "GPU (l0's 6-byte pixels cost a PCIe read each: with the link to itself the dense 50 MB copy of l0 "
+                         "is 2 %% faster than 262 k tiny reads), l0,l1,l2 when several GPUs share the host's memory "
+                         "(35 %% fewer bytes over PCIe per step)")
+    ap.add_argument("--e2e-streams", type=int, default=2, help="compute streams the e2e chunks alternate between")
+    ap.add_argument("--e2e-chunks", type=int, default=2, help="H2D/compute overlap chunks in the e2e measurement")
     ap.add_argument("--host-alloc", default="wc", choices=["wc", "pinned"],
                     help="e2e input staging buffers: write-combined page-locked memory (cudaHostAllocWriteCombined) or "
                          "torch's pin_memory()")

@@ -124,6 +124,13 @@ int pdf_pyramid_gather_bf16(const float* xyz, const int64_t* choose, int64_t n_c
                             int n_points, int n1, int n2, int R, const void* l0, const void* l1, int C1,
                             const void* l2, int C2, const float* sft0_params, float* pts0, void* cond1_img,
                             void* cond2_img, void* stream);
+/* Zero-copy hand-off of a HOST-resident pyramid: l0 / l1 / l2 of pdf_pyramid_gather_bf16 may each be the device
+ * alias of a page-locked, mapped host buffer (this call; cudaHostGetDevicePointer).  The gather then reads only the
+ * pixels `choose` selects (2 x (1024 x 6 + 512 x 128 + 128 x 512) B of a 4.6 MB frame) over the PCIe link, in
+ * place of a dense host->device copy of the maps (the reference moves whole maps: `.cuda()` of the batch,
+ * lib/trains/base_trainer.py:66-68, then _tranpose_and_gather_feat copies them once more, lib/models/utils.py:12-26).
+ * Returns PDF_ERR_BAD_ARG when `host` is not mapped page-locked memory. */
+int pdf_host_device_pointer(const void* host, void** device_out);
 
 
 /* Grouping gather: out[b,g,j,c] = pts[b, idx[b,g,j], c] - (c < 3 ? pts[b,g,c] : 0).

@@ -82,6 +82,7 @@ SIGNATURES = {
     "pdf_mha_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _vp],
     "pdf_decoder_project": [_vp, _i32, _vp, _i32, _vp, _i64, _f32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
     "pdf_mano_lbs_pair": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
+    "pdf_host_device_pointer": [_vp, _vp],
 }
 EXPORTS = sorted(list(SIGNATURES) + ["pdf_version", "pdf_last_error", "pdf_launch_count", "pdf_sa_pack_size",
                                      "pdf_image_bytes"])
@@ -156,6 +157,19 @@ def ptr(t):
             raise RuntimeError("pdfnet_b200: tensors of one call live on different devices (cuda:%d and %s)"
                                % (dev, t.device))
     return ctypes.c_void_p(t.data_ptr())
+
+
+def host_ptr(t):
+    """Device alias of a page-locked (pinned) HOST tensor, for the kernels that read a host-resident input in
+    place (zero-copy; pdf_host_device_pointer).  Raises when the tensor is not pinned, mapped host memory."""
+    if t.is_cuda:
+        return ptr(t)
+    out = ctypes.c_void_p()
+    rc = load().pdf_host_device_pointer(ctypes.c_void_p(t.data_ptr()), ctypes.byref(out))
+    if rc != 0 or not out.value:
+        raise RuntimeError("pdfnet_b200: a host tensor handed to a kernel must be page-locked (pin_memory() / "
+                           "parallel.pinned_like): %s" % load().pdf_last_error().decode("utf-8", "replace"))
+    return out
 
 
 def stream():

@@ -23,3 +23,19 @@ bool pdl_enabled() {
 extern "C" int pdf_version(void) { return 100; }
 extern "C" const char* pdf_last_error(void) { return pdf::g_err; }
 extern "C" int64_t pdf_launch_count(void) { return (int64_t)pdf::g_launches.load(); }
+
+// Device-side alias of a page-locked, mapped HOST buffer (cudaHostAlloc / cudaHostRegister memory): kernels that only
+// touch a sparse subset of a large host-resident input (pdf_pyramid_gather_bf16 reads 2 x 1664 pixels of a frame's
+// feature pyramid) can read it in place over the PCIe link instead of having the whole tensor copied first.
+extern "C" int pdf_host_device_pointer(const void* host, void** device_out) {
+  PDF_REQUIRE(host && device_out, PDF_ERR_BAD_ARG, "pdf_host_device_pointer: null pointer");
+  void* d = nullptr;
+  const cudaError_t e = cudaHostGetDevicePointer(&d, const_cast<void*>(host), 0);
+  if (e != cudaSuccess || d == nullptr) {
+    cudaGetLastError();
+    pdf::set_error("pdf_host_device_pointer: %p is not mapped page-locked host memory (%s)", host, cudaGetErrorString(e));
+    return PDF_ERR_BAD_ARG;
+  }
+  *device_out = d;
+  return PDF_OK;
+}

@@ -227,7 +227,10 @@ class PointNet_Plus(nn.Module):
                 f = torch.arange(points.shape[0], device=points.device) // clouds_per_frame
                 emb = [e[f] for e in emb]
             return pointnet_plus_train(self, points, emb, choose)
-        L.require_cuda(points, choose, *emb)
+        # maps of a bf16 channels-last pyramid may stay in page-locked HOST memory: the gather reads them in place
+        # (zero-copy, ops.pyramid_gather_bf16 checks that they are pinned)
+        in_place_ok = self.precision == "bf16" and all(ops._is_bf16_nhwc(e) for e in emb)
+        L.require_cuda(points, choose, *(() if in_place_ok else emb))
         with torch.no_grad():
             B = points.shape[0]
             chunk = self.chunk_clouds or (256 if self.precision == "fp32" else 2048)

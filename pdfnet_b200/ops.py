@@ -122,7 +122,7 @@ def pyramid_gather_bf16(xyz, choose, emb, sft0_params, n1, n2, R, clouds_per_fra
     """3-level gather from a bf16 channels-last pyramid + SFT0 (pdf_pyramid_gather_bf16).
     Returns pts0 [B,N,3] fp32 and the two condition operands as bf16 TILE IMAGES (uint8 tensors):
     image of [B*n1, C1] and of [B*n2, C2] - what the SFT GEMMs read, no intermediate rows."""
-    L.require_cuda(xyz, choose, emb[0], emb[1], emb[2], sft0_params)
+    L.require_cuda(xyz, choose, sft0_params)       # the maps may be page-locked HOST tensors (read in place, below)
     xyz = L.f32c(xyz)
     choose = choose.long().contiguous()
     l0, l1, l2 = emb
@@ -141,8 +141,10 @@ def pyramid_gather_bf16(xyz, choose, emb, sft0_params, n1, n2, R, clouds_per_fra
     pts0 = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
     img1 = torch.empty((image_bytes(B * n1, C1),), dtype=torch.uint8, device=dev)
     img2 = torch.empty((image_bytes(B * n2, C2),), dtype=torch.uint8, device=dev)
-    L.call("pdf_pyramid_gather_bf16", L.ptr(xyz), L.ptr(choose), B, clouds_per_frame, N, n1, n2, R, L.ptr(l0), L.ptr(l1),
-           C1, L.ptr(l2), C2, L.ptr(sft0_params), L.ptr(pts0), L.ptr(img1), L.ptr(img2), L.stream())
+    # a map living in page-locked host memory is gathered in place over the PCIe link (zero-copy): only the pixels
+    # `choose` selects cross the link instead of the whole map (L.host_ptr raises for pageable memory)
+    L.call("pdf_pyramid_gather_bf16", L.ptr(xyz), L.ptr(choose), B, clouds_per_frame, N, n1, n2, R, L.host_ptr(l0),
+           L.host_ptr(l1), C1, L.host_ptr(l2), C2, L.ptr(sft0_params), L.ptr(pts0), L.ptr(img1), L.ptr(img2), L.stream())
     return pts0, img1, img2
 
 

@@ -94,8 +94,8 @@ def pinned_like(t, write_combined=True):
         src = src.contiguous()
     nbytes = max(1, src.numel() * src.element_size())
     ptr = ctypes.c_void_p()
-    # portable (1) | write-combined (4)
-    rc = _cudart.cudaHostAlloc(ctypes.byref(ptr), ctypes.c_size_t(nbytes), ctypes.c_uint(1 | 4))
+    # portable (1) | mapped (2: kernels may read the buffer in place, _lib.host_ptr) | write-combined (4)
+    rc = _cudart.cudaHostAlloc(ctypes.byref(ptr), ctypes.c_size_t(nbytes), ctypes.c_uint(1 | 2 | 4))
     if rc != 0 or not ptr.value:
         return t.pin_memory()
     _host_allocs.append((ptr.value, nbytes))

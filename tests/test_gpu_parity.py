@@ -1231,6 +1231,39 @@ def test_captured_step_replays_the_hot_path_bit_exactly():
 
 
 @torch.no_grad()
+def test_host_resident_pyramid_is_gathered_in_place():
+    """Zero-copy hand-off: a bf16 channels-last pyramid left in page-locked HOST memory (torch pin_memory() and the
+    write-combined mapped buffers of parallel.pinned_like) gives the bits of the device-resident maps, through the op
+    and through HandFusion; pageable host memory is refused loudly."""
+    from pdfnet_b200 import HandFusion, ops, parallel
+    R, B = 64, 4
+    opt = _opt(default_resolution=R)
+    emb = [e.bfloat16().contiguous(memory_format=torch.channels_last) for e in synth.pyramid(B, R, seed=91)]
+    emb_dev = [e.to(DEV) for e in emb]
+    m = HandFusion(opt, "bf16")
+    m.pointnet_plus.load_state_dict(synth.pointnet_plus_state(seed=317), strict=False)
+    m.sft.load_state_dict(synth.fusion_sft_state(seed=317))
+    m = m.to(DEV).eval()
+    cloud = synth.clouds(2 * B, seed=91).view(B, 2, 1024, 3).to(DEV)
+    choose = synth.choose_indices(2 * B, R, seed=91).view(B, 2, 1024).to(DEV)
+    cen = torch.randn((B, 2, 1024), generator=torch.Generator().manual_seed(91)).to(DEV)
+    sft0 = m.pointnet_plus.folded()["sft0"]
+    ref_op = ops.pyramid_gather_bf16(cloud.view(2 * B, 1024, 3), choose.view(2 * B, 1024), emb_dev, sft0, 512, 128, R, 2)
+    ref = m(cloud, emb_dev, choose, cen)
+    for host in ([e.pin_memory() for e in emb], [parallel.pinned_like(e, write_combined=True) for e in emb]):
+        assert all(not e.is_cuda and ops._is_bf16_nhwc(e) for e in host)
+        got_op = ops.pyramid_gather_bf16(cloud.view(2 * B, 1024, 3), choose.view(2 * B, 1024), host, sft0, 512, 128, R, 2)
+        assert all(torch.equal(a, b) for a, b in zip(got_op, ref_op))
+        assert torch.equal(m(cloud, host, choose, cen), ref)
+        assert torch.equal(m(cloud[1:3], [e[1:3] for e in host], choose[1:3], cen[1:3]),
+                           m(cloud[1:3], [e[1:3] for e in emb_dev], choose[1:3], cen[1:3]))            # frame slices
+        mixed = [emb_dev[0], host[1], host[2]]                   # level 0 on the device, levels 1 / 2 read in place
+        assert torch.equal(m(cloud, mixed, choose, cen), ref)
+    with pytest.raises(RuntimeError):
+        m(cloud, emb, choose, cen)                               # pageable host memory: no silent staging copy
+
+
+@torch.no_grad()
 def test_channels_last_pyramid_is_bit_identical():
     """pyramid maps handed over in torch.channels_last are gathered in place
     (pdf_pyramid_gather_nhwc / pdf_gather_nhwc); every result equals the NCHW path bit for bit."""
