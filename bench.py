@@ -450,7 +450,7 @@ def run_ours(args):
 
     zc_arg = args.e2e_zero_copy_levels
     if zc_arg == "auto":
-        zc_arg = "l1,l2" if world == 1 else "l0,l1,l2"
+        zc_arg = "l1,l2" if world <= 2 else "l0,l1,l2"      # up to 2 ranks the host feeds every link at full speed (measured)
     zc_levels = tuple(k for k in PYR if k in zc_arg.split(","))
     comp_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.e2e_streams))]
     zc_px_bytes = {"l0": 1024 * 6, "l1": 512 * 128, "l2": 128 * 512}          # per cloud (SURVEY 8d, bf16 features)
@@ -1143,9 +1143,9 @@ def main():
                          "of the maps first; both are measured, the other one is reported as e2e_other_handoff")
     ap.add_argument("--e2e-zero-copy-levels", default="auto",
                     help="which pyramid maps the zero-copy hand-off reads in place (the rest is copied).  auto: l1,l2 on one "
-                         "GPU (l0's 6-byte pixels cost a PCIe read each: with the link to itself the dense 50 MB copy of l0 "
-                         "is 2 %% faster than 262 k tiny reads), l0,l1,l2 when several GPUs share the host's memory "
-                         "(35 %% fewer bytes over PCIe per step)")
+                         "or two GPUs (l0's 6-byte pixels cost a PCIe read each: while the host feeds every link at full "
+                         "speed the dense 50 MB copy of l0 is 2 - 8 %% faster than 262 k tiny reads), l0,l1,l2 from four GPUs "
+                         "on, where the host's memory system is the limit (35 %% fewer bytes over PCIe per step)")
     ap.add_argument("--e2e-streams", type=int, default=2, help="compute streams the e2e chunks alternate between")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="H2D/compute overlap chunks in the e2e measurement")
     ap.add_argument("--host-alloc", default="wc", choices=["wc", "pinned"],
