@@ -215,7 +215,26 @@ class PointNet_Plus(nn.Module):
         tc["n3_w3"], tc["n3_b3"] = img(w3), b3
         return tc
 
-    def forward(self, points, emb, choose, clouds_per_frame=1):
+    def gather(self, points, emb, choose, clouds_per_frame=1):
+        """Stage 1 of the bf16 inference path on its own: pixel -> point gather of the bf16 channels-last pyramid
+        (+ SFT0) -> ``(pts0, cond1_image, cond2_image)`` to be handed to ``forward(..., gathered=)``.  With a
+        host-resident pyramid (zero-copy) this is the only part of the path that waits on the PCIe link, so a caller
+        can run it for batch i+1 on a second stream while batch i computes (bench.py e2e)."""
+        if self.precision != "bf16" or not all(ops._is_bf16_nhwc(e) for e in emb):
+            raise RuntimeError("PointNet_Plus.gather: bf16 mode with a bf16 channels-last pyramid only")
+        L.require_cuda(points, choose)
+        N1, N2 = self.sample_num_level1, self.sample_num_level2
+        with torch.no_grad(), stage("pyramid_gather"):
+            return ops.pyramid_gather_bf16(points, choose, emb, self.folded()["sft0"], N1, N2,
+                                           self.opt.default_resolution, clouds_per_frame)
+
+    def forward(self, points, emb, choose, clouds_per_frame=1, gathered=None):
+        if gathered is not None:                       # inference, stage 1 already done (self.gather)
+            if self.training or self.precision != "bf16":
+                raise RuntimeError("PointNet_Plus.forward(gathered=...): bf16 inference path only")
+            L.require_cuda(points, *gathered)
+            with torch.no_grad():
+                return self._forward_chunk_bf16(points, None, None, clouds_per_frame, 0, gathered=gathered)
         if self.training or _grad_needed(self, points, *emb):
             # autograd through every stage (training.py): train-mode BatchNorm statistics in .train(), folded
             # running statistics in .eval() with grad enabled (fine-tuning with frozen BatchNorm)
@@ -288,7 +307,7 @@ class PointNet_Plus(nn.Module):
             out = ops.linear(h, w3, b3, act=L.ACT_RELU, epilogue=L.EPI_GROUP_MAX, group=N2)
         return out.view(B, 1, nstates_plus_3[2])
 
-    def _forward_chunk_bf16(self, points, emb, choose, cpf, frame0):
+    def _forward_chunk_bf16(self, points, emb, choose, cpf, frame0, gathered=None):
         """Tensor-core pipeline: fused tcgen05 set-abstraction kernels + streaming tcgen05 GEMMs over
         bf16 tile images for SFT1 / SFT2 / netR_3.  Everything that decides neighbour indices (SFT0,
         the xyz channels of SFT1, both neighbour searches) stays fp32."""
@@ -306,9 +325,15 @@ class PointNet_Plus(nn.Module):
         u8 = lambda n: torch.empty((n,), dtype=torch.uint8, device=dev)
         RELU, LEAKY, BLK = L.ACT_RELU, L.ACT_LEAKY01, 16384
         # a bf16 channels-last pyramid (autocast RGB neck) is gathered straight into the SFT GEMMs' operand images
-        bf16_emb = all(ops._is_bf16_nhwc(e) for e in emb) and (B * N1) % 128 == 0 and (B * N2) % 128 == 0
+        bf16_emb = gathered is not None or (all(ops._is_bf16_nhwc(e) for e in emb) and (B * N1) % 128 == 0
+                                            and (B * N2) % 128 == 0)
         with stage("pyramid_gather"):
-            if bf16_emb:
+            if gathered is not None:
+                pts0, c1img, c2img = gathered
+                if tuple(pts0.shape) != (B, points.shape[1], 3) or c1img.numel() != ops.image_bytes(B * N1, 64) or \
+                        c2img.numel() != ops.image_bytes(B * N2, 256):
+                    raise RuntimeError("PointNet_Plus.forward(gathered=...): not the output of gather() for these clouds")
+            elif bf16_emb:
                 pts0, c1img, c2img = ops.pyramid_gather_bf16(points, choose, emb, f["sft0"], N1, N2,
                                                              opt.default_resolution, cpf)
             else:
@@ -402,7 +427,13 @@ class HandFusion(nn.Module):
             nn.Linear(1024, 512), nn.BatchNorm1d(512), nn.ReLU(inplace=True),
             nn.Linear(512, 256), nn.BatchNorm1d(256), nn.ReLU(inplace=True), nn.Linear(256, 122))
 
-    def forward(self, cloud, point_wise_emb, choose, center_features, with_mano=False, mano_stream=None):
+    def gather(self, cloud, point_wise_emb, choose):
+        """``PointNet_Plus.gather`` for both hands of every frame (cloud [B,2,N,3], choose [B,2,N])."""
+        B, H, N, _ = cloud.shape
+        return self.pointnet_plus.gather(cloud.reshape(B * H, N, 3), point_wise_emb, choose.reshape(B * H, N),
+                                         clouds_per_frame=H)
+
+    def forward(self, cloud, point_wise_emb, choose, center_features, with_mano=False, mano_stream=None, gathered=None):
         """cloud [B,2,N,3], choose [B,2,N], center_features [B,2,1024] ->
         fuse_feat [B,2,1024] (and theta [B,2,122] = (point2mano_left, point2mano_right)).
         ``mano_stream`` (inference): the MANO head - which only reads the un-fused per-hand features - is enqueued
@@ -410,11 +441,14 @@ class HandFusion(nn.Module):
         afterwards, e.g. the GCN decoder); the caller joins with ``current_stream().wait_stream(mano_stream)``
         before reading theta on another stream."""
         B, H, N, _ = cloud.shape
-        if self.training or _grad_needed(self, cloud, center_features, *point_wise_emb):
+        if gathered is not None:                       # inference with the gather stage done beforehand (self.gather)
+            feat = self.pointnet_plus(cloud.reshape(B * H, N, 3), None, None, clouds_per_frame=H, gathered=gathered)
+        elif self.training or _grad_needed(self, cloud, center_features, *point_wise_emb):
             from .training import hand_fusion_train
             return hand_fusion_train(self, cloud, point_wise_emb, choose, center_features, with_mano=with_mano)
-        feat = self.pointnet_plus(cloud.reshape(B * H, N, 3), point_wise_emb, choose.reshape(B * H, N),
-                                  clouds_per_frame=H)                       # [2B,1,1024]
+        else:
+            feat = self.pointnet_plus(cloud.reshape(B * H, N, 3), point_wise_emb, choose.reshape(B * H, N),
+                                      clouds_per_frame=H)                   # [2B,1,1024]
         rows = feat.view(B * H, 1024)
         with torch.no_grad():
             theta = None

@@ -1259,6 +1259,12 @@ def test_host_resident_pyramid_is_gathered_in_place():
                            m(cloud[1:3], [e[1:3] for e in emb_dev], choose[1:3], cen[1:3]))            # frame slices
         mixed = [emb_dev[0], host[1], host[2]]                   # level 0 on the device, levels 1 / 2 read in place
         assert torch.equal(m(cloud, mixed, choose, cen), ref)
+        # the pass split at the gather (stage A = HandFusion.gather, stage B = forward(gathered=...))
+        g = m.gather(cloud, mixed, choose)
+        assert all(torch.equal(a, b) for a, b in zip(g, ref_op))
+        assert torch.equal(m(cloud, None, None, cen, gathered=g), ref)
+    with pytest.raises(RuntimeError):
+        m(cloud, None, None, cen, gathered=(ref_op[0][:2], ref_op[1], ref_op[2]))     # not these clouds' gather
     with pytest.raises(RuntimeError):
         m(cloud, emb, choose, cen)                               # pageable host memory: no silent staging copy
 
