@@ -462,6 +462,7 @@ def run_ours(args):
         zc_arg = "l1,l2" if world <= 2 else "l0,l1,l2"      # up to 2 ranks the host feeds every link at full speed (measured)
     zc_levels = tuple(k for k in PYR if k in zc_arg.split(","))
     comp_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.e2e_streams))]
+    pinned_alt = {}
     zc_px_bytes = {"l0": 1024 * 6, "l1": 512 * 128, "l2": 128 * 512}          # per cloud (SURVEY 8d, bf16 features)
 
     def measure_e2e(zero_copy, prefetch=False):
@@ -473,29 +474,43 @@ def run_ours(args):
         n_sets = 3 if prefetch else 2                 # split schedule: a third staging set keeps the copies off stage B's heels
         # host side: two page-locked pyramid sets read in place alternately (no step re-reads the addresses of the
         # step before it); device side: double-buffered staging for everything that is copied
-        host_sets = [pinned, {k: (parallel.pinned_like(pinned[k], write_combined=(args.host_alloc == "wc")) if k in zc
-                                  else pinned[k]) for k in pinned}]
-        staging = [{k: (host_sets[st % 2][k] if k in zc else torch.empty_like(resident[k])) for k in pinned}
-                   for st in range(n_sets)]
-        copied = [k for k in pinned if k not in zc]
-        copy_bytes = sum(pinned[k].numel() * pinned[k].element_size() for k in copied)
-        zc_bytes = 2 * B * sum(zc_px_bytes[k] for k in zc)                            # algorithmic bytes read in place
-        chunk_steps = a_steps = None
-        if prefetch:                                  # two graphs per staging set: stage A, stage B on A's outputs
-            a_steps = [CapturedStep(lambda st=st: hot_stage_a(st), warmup=2) for st in staging]
-            chunk_steps = [[CapturedStep(lambda st=st, a=a: hot_path(st, pre=a.outputs), warmup=2)]
-                           for st, a in zip(staging, a_steps)]
-        elif not args.no_graph:                       # one captured graph per (staging set, chunk)
-            try:
-                chunk_steps = [[CapturedStep(lambda lo=lo, hi=hi, st=st: hot_path({k: v[lo:hi] for k, v in st.items()}),
-                                             warmup=2) for lo, hi in bounds] for st in staging]
-            except Exception as e:
-                sys.stderr.write("bench: CUDA-graph capture of the e2e chunks failed (%s); eager chunks\n" % e)
-                torch.cuda.synchronize()
-                chunk_steps = None
-        probe = hot_path({k: v[bounds[0][0]:bounds[0][1]] for k, v in staging[0].items()})
-        out_host = [{n: torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory() for n, t in zip(names, probe)}
-                    for _ in range(n_sets)]
+        # set-up (page-locked allocations, graph captures) can fail on ONE rank only; the timed part below holds
+        # barriers, so the ranks first agree that every one of them got through it
+        fail = None
+        chunk_steps = a_steps = staging = probe = out_host = None
+        try:
+            for k in zc:                                  # second page-locked copy of the maps read in place (kept across modes)
+                if k not in pinned_alt:
+                    pinned_alt[k] = parallel.pinned_like(pinned[k], write_combined=(args.host_alloc == "wc"))
+            host_sets = [pinned, {k: (pinned_alt[k] if k in zc else pinned[k]) for k in pinned}]
+            staging = [{k: (host_sets[st % 2][k] if k in zc else torch.empty_like(resident[k])) for k in pinned}
+                       for st in range(n_sets)]
+            copied = [k for k in pinned if k not in zc]
+            copy_bytes = sum(pinned[k].numel() * pinned[k].element_size() for k in copied)
+            zc_bytes = 2 * B * sum(zc_px_bytes[k] for k in zc)                            # algorithmic bytes read in place
+            chunk_steps = a_steps = None
+            if prefetch:                                  # two graphs per staging set: stage A, stage B on A's outputs
+                a_steps = [CapturedStep(lambda st=st: hot_stage_a(st), warmup=2) for st in staging]
+                chunk_steps = [[CapturedStep(lambda st=st, a=a: hot_path(st, pre=a.outputs), warmup=2)]
+                               for st, a in zip(staging, a_steps)]
+            elif not args.no_graph:                       # one captured graph per (staging set, chunk)
+                try:
+                    chunk_steps = [[CapturedStep(lambda lo=lo, hi=hi, st=st: hot_path({k: v[lo:hi] for k, v in st.items()}),
+                                                 warmup=2) for lo, hi in bounds] for st in staging]
+                except Exception as e:
+                    sys.stderr.write("bench: CUDA-graph capture of the e2e chunks failed (%s); eager chunks\n" % e)
+                    torch.cuda.synchronize()
+                    chunk_steps = None
+            probe = hot_path({k: v[bounds[0][0]:bounds[0][1]] for k, v in staging[0].items()})
+            out_host = [{n: torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory() for n, t in zip(names, probe)}
+                        for _ in range(n_sets)]
+        except Exception as e:
+            fail = str(e)[:200]
+            torch.cuda.synchronize()
+        if parallel.max_over_ranks(1.0 if fail else 0.0, dev) > 0:
+            del chunk_steps, a_steps, staging, probe, out_host
+            torch.cuda.empty_cache()
+            raise RuntimeError("e2e set-up failed on %s: %s" % ("this rank" if fail else "another rank", fail))
         d2h_bytes[0] = sum(v.numel() * v.element_size() for v in out_host[0].values())
         consumed = [None] * n_sets                    # event: the compute of the step that last used this set is done
         drained = [None] * n_sets                     # event: its outputs have left the device
