@@ -51,6 +51,35 @@ def test_no_cpu_fallback(lib):
         layer(torch.zeros((1, 3)), torch.zeros((1, 45)), torch.zeros((1, 10)))
 
 
+def test_host_resident_pyramid_interface_fails_loudly(lib):
+    """Zero-copy hand-off (pdf_host_device_pointer / PointNet_Plus.gather / forward(gathered=)): argument errors and
+    pageable memory are reported, nothing is dereferenced; the split pass exists for the bf16 inference path only."""
+    import ctypes
+    from pdfnet_b200 import HandFusion, PointNet_Plus, _lib
+    assert lib.pdf_host_device_pointer(None, None) == -1
+    assert b"null" in lib.pdf_last_error()
+    out = ctypes.c_void_p()
+    buf = torch.zeros(64)                                            # pageable (and, here, no CUDA device at all)
+    assert lib.pdf_host_device_pointer(ctypes.c_void_p(buf.data_ptr()), ctypes.byref(out)) == -1 and not out.value
+    with pytest.raises(RuntimeError, match="page-locked"):
+        _lib.host_ptr(buf)
+    emb = [e.bfloat16().contiguous(memory_format=torch.channels_last) for e in synth.pyramid(1, 64, seed=3)]
+    cloud, choose = synth.clouds(2, seed=3), synth.choose_indices(2, 64, seed=3)
+    with pytest.raises(RuntimeError, match="bf16"):
+        PointNet_Plus(_opt(), "fp32").eval().gather(cloud, emb, choose, 2)
+    with pytest.raises(RuntimeError, match="bf16"):
+        PointNet_Plus(_opt(), "bf16").eval().gather(cloud, [e.float() for e in emb], choose, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        PointNet_Plus(_opt(), "bf16").eval().gather(cloud, emb, choose, 2)       # CPU clouds: no fallback
+    g = (torch.zeros((2, 1024, 3)), torch.zeros(1, dtype=torch.uint8), torch.zeros(1, dtype=torch.uint8))
+    with pytest.raises(RuntimeError, match="bf16 inference"):
+        PointNet_Plus(_opt(), "fp32").eval()(cloud, None, None, 2, gathered=g)
+    with pytest.raises(RuntimeError, match="bf16 inference"):
+        PointNet_Plus(_opt(), "bf16").train()(cloud, None, None, 2, gathered=g)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        HandFusion(_opt(), "bf16").eval()(cloud.view(1, 2, 1024, 3), None, None, torch.zeros((1, 2, 1024)), gathered=g)
+
+
 def test_bad_arguments_return_errors_not_crashes(lib):
     # argument validation happens before any CUDA call, so it is testable without a GPU
     assert lib.pdf_knn_ball(None, 1, 1024, 512, 64, 0.01, 0, 0, 0, None, None) == -1
