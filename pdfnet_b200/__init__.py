@@ -4,8 +4,8 @@ Drop-in surface (same names as the reference):
     group_points, group_points_2, _tranpose_and_gather_feat, SFTLayer, PointNet_Plus,
     depth2pcl, get_points_coordinate, ManoLayer, Split_coeff
 plus the pointnet2-style aliases farthest_point_sample, query_ball_point, index_points,
-sample_and_group, the fused two-hand tail HandFusion, patch_reference(), CapturedStep (CUDA-graph
-replay of a step) and the training-mode entry points (PointNet_Plus / HandFusion in .train()).
+sample_and_group, the fused two-hand tail HandFusion, patch_reference(), CapturedStep / PipelinedStep
+(CUDA-graph replay of a step / of two overlapped stages of consecutive batches) and the training-mode entry points (PointNet_Plus / HandFusion in .train()).
 Compute modules need the CUDA library (pdfnet_b200/lib/libpdfnet_b200.so); there is no
 CPU fallback.  ``pdfnet_b200.synth`` and ``pdfnet_b200.parallel`` are pure host code.
 """
@@ -19,7 +19,7 @@ _COMPUTE = {
     "get_points_coordinate": "encoder", "ManoLayer": "manolayer", "Split_coeff": "manolayer",
     "mano_tail": "manolayer", "mano_tail_pair": "manolayer", "patch_reference": "patch",
     "rodrigues_batch": "manolayer", "process_J_regressor": "manolayer", "regress_joints": "manolayer",
-    "decoder": "decoder", "load_decoder": "decoder", "CapturedStep": "graph", "pointnet_plus_train": "training", "hand_fusion_train": "training",
+    "decoder": "decoder", "load_decoder": "decoder", "CapturedStep": "graph", "PipelinedStep": "graph", "pointnet_plus_train": "training", "hand_fusion_train": "training",
     "allreduce_gradients": "training", "BucketedAllReduce": "training",
 }
 
